@@ -1,0 +1,294 @@
+/*
+ * flowagg.h — C ABI of the B200 flow-aggregation engine (libflowagg.so).
+ *
+ * This is the drop-in boundary for the netobserv agent's per-packet hot path.
+ * A thin cgo wrapper implements the Go interface
+ * `agent.ebpfFlowFetcher` (reference pkg/agent/agent.go:94-102) and the
+ * gopipes stage `Accounter.Account` (reference pkg/flow/account.go:58) on top
+ * of these entry points.  Only plain pointers and sizes cross the boundary;
+ * no CUDA or torch types appear in any signature.
+ *
+ * Record layouts are an independent restatement of the agent's ring-buffer /
+ * BPF-map ABI (offsets listed in SURVEY.md §8a, verified against the golden
+ * byte vectors of reference pkg/model/record_test.go:19-102,193-224,323-347).
+ * All integers are little-endian; every struct is "not packed" C layout.
+ *
+ * Error convention (mirrors the reference: never abort on data, count and
+ * continue — pkg/tracer/tracer.go:1090-1092): every function returns an int,
+ * 0 = OK, negative = -errno style failure (FA_E_*), positive = a condition the
+ * caller is expected to handle (FA_FULL).
+ *
+ * Threading: at most one thread in fa_ingest*() and one other thread in
+ * fa_evict()/fa_purge_stale_dns() at the same time (exactly the reference's
+ * model: one RingBufTracer/Accounter goroutine, one single-flight evictor —
+ * pkg/flow/tracer_map.go:83-101).  The engine never retains a host pointer
+ * after the call that received it returns.
+ */
+#ifndef FLOWAGG_H
+#define FLOWAGG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- layouts */
+
+#define FA_IP_LEN 16
+#define FA_MAC_LEN 6
+#define FA_MAX_OBSERVED_INTF 6
+#define FA_DNS_NAME_LEN 32
+
+/* Flow key, 40 bytes (reference bpf/types.h:191-204; Go mirror
+ * pkg/ebpf/bpf_x86_bpfel.go:110-120).  IPv4 is carried as ::ffff:a.b.c.d.
+ * Byte 39 is padding: ignored on input, always 0 on output (Go `==` on
+ * BpfFlowId ignores the blank field). */
+typedef struct fa_flow_id {
+    uint8_t  src_ip[FA_IP_LEN];      /*  0 */
+    uint8_t  dst_ip[FA_IP_LEN];      /* 16 */
+    uint16_t src_port;               /* 32 host order */
+    uint16_t dst_port;               /* 34 */
+    uint8_t  transport_protocol;     /* 36 */
+    uint8_t  icmp_type;              /* 37 */
+    uint8_t  icmp_code;              /* 38 */
+    uint8_t  pad_;                   /* 39 */
+} fa_flow_id;
+
+/* Per-flow accumulators, 104 bytes (reference bpf/types.h:94-126; Go mirror
+ * pkg/ebpf/bpf_x86_bpfel.go:124-153). */
+typedef struct fa_flow_metrics {
+    uint64_t start_mono_time_ts;                        /*   0 */
+    uint64_t end_mono_time_ts;                          /*   8 */
+    uint64_t bytes;                                     /*  16 */
+    uint32_t packets;                                   /*  24 wraps mod 2^32 */
+    uint16_t eth_protocol;                              /*  28 */
+    uint16_t flags;                                     /*  30 */
+    uint8_t  src_mac[FA_MAC_LEN];                       /*  32 */
+    uint8_t  dst_mac[FA_MAC_LEN];                       /*  38 */
+    uint32_t if_index_first_seen;                       /*  44 */
+    uint32_t lock;                                      /*  48 */
+    uint32_t sampling;                                  /*  52 */
+    uint8_t  direction_first_seen;                      /*  56 */
+    uint8_t  errno_;                                    /*  57 */
+    uint8_t  dscp;                                      /*  58 */
+    uint8_t  nb_observed_intf;                          /*  59 */
+    uint8_t  observed_direction[FA_MAX_OBSERVED_INTF];   /*  60 */
+    uint8_t  pad0_[2];                                  /*  66 */
+    uint32_t observed_intf[FA_MAX_OBSERVED_INTF];       /*  68 */
+    uint16_t ssl_version;                               /*  92 */
+    uint16_t tls_cipher_suite;                          /*  94 */
+    uint16_t tls_key_share;                             /*  96 */
+    uint8_t  tls_types;                                 /*  98 */
+    uint8_t  misc_flags;                                /*  99 */
+    uint8_t  pad1_[4];                                  /* 100 */
+} fa_flow_metrics;
+
+/* Ring-buffer wire record == Go model.RawRecord, 144 bytes
+ * (reference bpf/types.h:212-215; pkg/model/record.go:63). */
+typedef struct fa_flow_record {
+    fa_flow_id      id;        /*  0 */
+    fa_flow_metrics metrics;   /* 40 */
+} fa_flow_record;
+
+/* DNS feature metrics, 64 bytes (reference bpf/types.h:131-140). */
+typedef struct fa_dns_metrics {
+    uint64_t start_mono_time_ts;     /*  0 */
+    uint64_t end_mono_time_ts;       /*  8 */
+    uint64_t latency;                /* 16 */
+    uint16_t id;                     /* 24 */
+    uint16_t flags;                  /* 26 */
+    uint16_t eth_protocol;           /* 28 */
+    uint8_t  errno_;                 /* 30 */
+    char     name[FA_DNS_NAME_LEN];  /* 31 */
+    uint8_t  pad_;                   /* 63 */
+} fa_dns_metrics;
+
+/* RTT / IPsec feature metrics, 32 bytes (reference bpf/types.h:174-181). */
+typedef struct fa_additional_metrics {
+    uint64_t start_mono_time_ts;     /*  0 */
+    uint64_t end_mono_time_ts;       /*  8 */
+    uint64_t flow_rtt;               /* 16 */
+    int32_t  ipsec_encrypted_ret;    /* 24 */
+    uint16_t eth_protocol;           /* 28 */
+    uint8_t  ipsec_encrypted;        /* 30 bool */
+    uint8_t  pad_;                   /* 31 */
+} fa_additional_metrics;
+
+/* Feature-stream input records: the key plus one feature sample — what the
+ * reference keeps per CPU slot in aggregated_flows_dns / additional_flow_metrics
+ * (bpf/maps_definition.h:24-31,64-71). */
+typedef struct fa_dns_record {
+    fa_flow_id     id;               /*  0 */
+    fa_dns_metrics dns;              /* 40 */
+} fa_dns_record;                     /* 104 bytes */
+
+typedef struct fa_additional_record {
+    fa_flow_id            id;          /*  0 */
+    fa_additional_metrics additional;  /* 40 */
+} fa_additional_record;              /* 72 bytes */
+
+/* ------------------------------------------------------------- error codes */
+
+#define FA_OK          0
+#define FA_FULL        1    /* ACCOUNTER mode: the flow cache reached max_entries at
+                               record `*consumed`; call fa_evict() (reason "full",
+                               reference pkg/flow/account.go:85-94) and resume. */
+#define FA_E_INVAL   (-22)
+#define FA_E_NOMEM   (-12)
+#define FA_E_CUDA    (-5)   /* CUDA runtime failure; see fa_last_error() */
+#define FA_E_NODEV   (-19)  /* no usable CUDA device: the engine has NO CPU fallback */
+#define FA_E_2BIG    (-7)   /* output capacity too small */
+#define FA_E_CLOSED  (-9)
+
+/* ------------------------------------------------------------------ config */
+
+enum fa_mode {
+    FA_MODE_ACCOUNTER  = 0, /* pkg/flow/account.go + pkg/model/flow_content.go:28-61 */
+    FA_MODE_KERNEL_MAP = 1  /* bpf/flows.c:98-143,222-288 (hit/miss semantics of aggregated_flows) */
+};
+
+typedef struct fa_config {
+    uint32_t abi_version;     /* FA_ABI_VERSION */
+    int32_t  device;          /* CUDA device ordinal */
+    uint32_t mode;            /* enum fa_mode */
+    uint32_t flags;           /* FA_F_* */
+    uint64_t max_entries;     /* CACHE_MAX_FLOWS (reference pkg/config/config.go:146): live-flow cap */
+    uint64_t max_batch;       /* largest number of records staged per kernel launch (0 = default 1<<22) */
+    uint32_t cms_log2_width;  /* count-min width = 2^this (0 = default 20) */
+    uint32_t cms_depth;       /* count-min rows (0 = default 4, max 8) */
+    uint32_t hll_precision;   /* HyperLogLog p (0 = default 14, 4..18) */
+    uint32_t reserved0;
+    uint64_t sketch_seed;     /* seed of the sketch hash family */
+    void*    cuda_stream;     /* optional cudaStream_t to run ingest work on (NULL = engine-owned) */
+} fa_config;
+
+#define FA_F_ENABLE_RTT     0x1u  /* ENABLE_RTT            (config.go:230) */
+#define FA_F_ENABLE_DNS     0x2u  /* ENABLE_DNS_TRACKING   (config.go:236) */
+#define FA_F_ENABLE_SKETCH  0x4u  /* fused count-min + HyperLogLog update in fa_ingest */
+
+typedef struct fa_stats {
+    uint64_t records_ingested;    /* flow records consumed by fa_ingest          */
+    uint64_t dns_ingested;
+    uint64_t additional_ingested;
+    uint64_t flows_evicted;       /* EvictedFlowsCounter                          */
+    uint64_t evictions;           /* EvictionCounter                              */
+    uint64_t live_flows;          /* FlowBufferSizeGauge("accounter-entries")     */
+    uint64_t spills;              /* records that found the table physically full */
+    uint64_t order_fixups;        /* flows whose order-dependent fields needed the ordered re-fold */
+    uint64_t full_cuts;           /* times fa_ingest returned FA_FULL             */
+    uint64_t kernel_launches;     /* CUDA kernels launched by the engine          */
+    uint64_t h2d_bytes;           /* bytes copied host->device by fa_ingest*      */
+    uint64_t d2h_bytes;           /* bytes copied device->host by fa_evict etc.   */
+    uint64_t observed_intf_missed;/* KERNEL_MAP mode: OBSERVED_INTF_MISSED counter */
+    uint64_t reserved[3];
+} fa_stats;
+
+typedef struct fa_engine fa_engine;
+
+/* ----------------------------------------------------------------- engine */
+
+uint32_t fa_abi_version(void);
+const char* fa_last_error(void);               /* thread-local description of the last failure */
+
+/* Replaces: tracer.NewFlowFetcher's map sizing (pkg/tracer/tracer.go:157-176)
+ * and flow.NewAccounter (pkg/flow/account.go:34-53). */
+int  fa_create(const fa_config* cfg, fa_engine** out);
+/* Replaces: FlowFetcher.Close (pkg/tracer/tracer.go:834-838). */
+void fa_destroy(fa_engine* e);
+
+/* Aggregate n 144-byte flow records (host or device pointer; detected).
+ * Replaces: the per-record body of Accounter.Account (pkg/flow/account.go:82-96)
+ * fed by RingBufTracer (pkg/flow/tracer_ringbuf.go:112-134), and in
+ * KERNEL_MAP mode the map update of flow_monitor (bpf/flows.c:222-288).
+ * Stream order == array order.  *consumed (may be NULL) receives the number of
+ * records folded; it is < n only when the call returns FA_FULL. */
+int fa_ingest(fa_engine* e, const void* flow_records, size_t n, size_t* consumed);
+
+/* Fold n (flow_id + additional_metrics) samples: RTT keep-max, IPsec rules.
+ * Replaces: bpf/rtt_tracker.h:12-22,73-91 + AccumulateAdditional
+ * (pkg/model/flow_content.go:154-177). */
+int fa_ingest_additional(fa_engine* e, const void* additional_records, size_t n);
+
+/* Fold n (flow_id + dns_metrics) samples.
+ * Replaces: bpf/flows.c:145-158,291-330 + AccumulateDNS
+ * (pkg/model/flow_content.go:76-96). */
+int fa_ingest_dns(fa_engine* e, const void* dns_records, size_t n);
+
+/* Lookup-and-delete every live flow (host or device output pointers).
+ * Replaces: FlowFetcher.LookupAndDeleteMap (pkg/tracer/tracer.go:1063-1157)
+ * and Accounter.evict's map hand-over (pkg/flow/account.go:67-68,86-87).
+ * out_records: cap x 144 B.  out_dns (cap x 64 B), out_additional (cap x 32 B)
+ * and out_present (cap bytes; bit0 = has DNS, bit1 = has additional) may be NULL.
+ * Output order is unspecified, as in the reference (Go map iteration). */
+int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additional,
+             uint8_t* out_present, size_t cap, size_t* n_out);
+
+/* Number of live flows right now (len(c.entries), account.go:98). */
+int fa_live_flows(fa_engine* e, size_t* n);
+
+/* Replaces: FlowFetcher.DeleteMapsStaleEntries (pkg/tracer/tracer.go:1229-1257). */
+int fa_purge_stale_dns(fa_engine* e, uint64_t mono_now_ns, uint64_t timeout_ns);
+
+/* Count-min point queries for n 40-byte keys (new capability; no reference). */
+int fa_cms_query(fa_engine* e, const void* keys, size_t n, uint64_t* estimates);
+/* HyperLogLog distinct-flow estimate (new capability; no reference). */
+int fa_hll_estimate(fa_engine* e, double* estimate);
+/* Raw sketch state for exact cross-checks / multi-GPU merges:
+ * cms: depth x width u64 (row-major); hll: 2^p u8 registers. Host pointers. */
+int fa_sketch_export(fa_engine* e, uint64_t* cms_out, size_t cms_words, uint8_t* hll_out, size_t hll_regs);
+int fa_sketch_reset(fa_engine* e);
+
+/* Replaces: ReadGlobalCounter (pkg/tracer/tracer.go:1190-1226) + the metrics the
+ * hot path increments (pkg/metrics/metrics.go:66-161). */
+int fa_get_stats(fa_engine* e, fa_stats* out);
+
+/* Block until all queued engine work has finished. */
+int fa_sync(fa_engine* e);
+
+/* -------------------------------------------------- multi-GPU routing (K3) */
+
+/* owner = fa_owner_hash(key) % n_shards; independent of the in-table probe hash. */
+uint64_t fa_owner_hash(const fa_flow_id* key);
+
+/* Partition n device-resident flow records by owner into `out` (n x 144 B,
+ * grouped by shard, order within a shard preserved by source index) and write
+ * the n_shards per-shard counts to counts_host.  All pointers except counts_host
+ * are device pointers. */
+int fa_route(fa_engine* e, const void* flow_records, size_t n, uint32_t n_shards,
+             void* out, uint64_t* counts_host);
+
+/* ------------------------------------------- memory + synthetic generator */
+
+int fa_device_alloc(fa_engine* e, size_t bytes, void** out);
+int fa_device_free(fa_engine* e, void* p);
+int fa_host_alloc(size_t bytes, void** out);   /* pinned host memory */
+int fa_host_free(void* p);
+
+enum fa_gen_dist { FA_GEN_UNIFORM = 0, FA_GEN_ZIPF = 1 };
+
+/* Counter-based synthetic stream: record i depends only on
+ * (seed, first_index + i), so any slice can be generated anywhere. */
+typedef struct fa_gen_params {
+    uint64_t seed;
+    uint64_t n_keys;          /* distinct 5-tuples (<= 2^32) */
+    uint32_t dist;            /* enum fa_gen_dist */
+    uint32_t zipf_s_milli;    /* Zipf exponent x 1000 (e.g. 1100) */
+    uint64_t t0_ns;           /* ts(i) = t0_ns + i: strictly monotone */
+    uint32_t varying_desc;    /* 0: per-key-constant MAC/ifindex/dscp/... ; 1: per-record random (order-dependent fields exercised) */
+    uint32_t reserved;
+} fa_gen_params;
+
+/* dst may be a host or a device pointer (host generation runs on the CPU and is
+ * bit-identical to the device generator). */
+int fa_gen_records(fa_engine* e, const fa_gen_params* p, uint64_t first_index, size_t n, void* dst);
+/* The 40-byte key of rank r (0-based) of the generator's key universe. Host pointer. */
+int fa_gen_key(const fa_gen_params* p, uint64_t rank, fa_flow_id* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWAGG_H */

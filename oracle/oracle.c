@@ -1,0 +1,510 @@
+/*
+ * oracle.c — CPU restatement of the reference's flow-aggregation algorithms.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h for the rules and the parity status).
+ * Every function cites the reference file:line it follows; nothing here is
+ * copied — the reference is Go / eBPF C, this is a byte-offset restatement.
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------ field access */
+/* offsets inside flow_metrics (reference bpf/types.h:94-126) */
+enum {
+    M_START = 0, M_END = 8, M_BYTES = 16, M_PACKETS = 24, M_ETH = 28, M_FLAGS = 30,
+    M_SRCMAC = 32, M_DSTMAC = 38, M_IFINDEX = 44, M_LOCK = 48, M_SAMPLING = 52,
+    M_DIR = 56, M_ERRNO = 57, M_DSCP = 58, M_NBOBS = 59, M_OBSDIR = 60, M_PAD0 = 66,
+    M_OBSINTF = 68, M_SSLVER = 92, M_CIPHER = 94, M_KEYSHARE = 96, M_TLSTYPES = 98,
+    M_MISC = 99, M_PAD1 = 100
+};
+/* dns_metrics (bpf/types.h:131-140) */
+enum { D_START = 0, D_END = 8, D_LATENCY = 16, D_ID = 24, D_FLAGS = 26, D_ETH = 28, D_ERRNO = 30, D_NAME = 31 };
+/* additional_metrics (bpf/types.h:174-181) */
+enum { A_START = 0, A_END = 8, A_RTT = 16, A_IPSEC_RET = 24, A_ETH = 28, A_IPSEC_ENC = 30 };
+
+static inline uint64_t ld64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint16_t ld16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+static inline void st64(uint8_t* p, uint64_t v) { memcpy(p, &v, 8); }
+static inline void st32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
+static inline void st16(uint8_t* p, uint16_t v) { memcpy(p, &v, 2); }
+
+static inline int all_zero6(const uint8_t* m) { /* pkg/model/flow_content.go:200-207 AllZerosMac */
+    return (m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0;
+}
+
+/* -------------------------------------------------------------- ReadFrom */
+void oracle_read_from(const uint8_t* wire, uint8_t* rec) {
+    /* pkg/model/record.go:227-231 + pkg/ebpf/bpf_x86_bpfel.go:110-153: blank fields
+     * (`_ [1]byte`, `_ [2]byte`, `_ [4]byte`) are skipped by binary.Read -> zero. */
+    memcpy(rec, wire, OR_REC_SIZE);
+    rec[39] = 0;
+    rec[OR_ID_SIZE + M_PAD0] = 0; rec[OR_ID_SIZE + M_PAD0 + 1] = 0;
+    memset(rec + OR_ID_SIZE + M_PAD1, 0, 4);
+}
+
+/* --------------------------------------------------------- AccumulateBase */
+void oracle_accumulate_base(uint8_t* p, const uint8_t* o) {
+    /* pkg/model/flow_content.go:28-61 */
+    uint64_t ps = ld64(p + M_START), os = ld64(o + M_START);
+    if (ps == 0 || (ps > os && os != 0)) st64(p + M_START, os);             /* :36-38 */
+    uint64_t pe = ld64(p + M_END), oe = ld64(o + M_END);
+    if (pe == 0 || pe < oe) st64(p + M_END, oe);                              /* :39-41 */
+    st64(p + M_BYTES, ld64(p + M_BYTES) + ld64(o + M_BYTES));                 /* :42 */
+    st32(p + M_PACKETS, ld32(p + M_PACKETS) + ld32(o + M_PACKETS));           /* :43 u32 wrap */
+    st16(p + M_FLAGS, (uint16_t)(ld16(p + M_FLAGS) | ld16(o + M_FLAGS)));     /* :44 */
+    if (ld16(o + M_ETH) != 0) st16(p + M_ETH, ld16(o + M_ETH));               /* :45-47 */
+    if (all_zero6(p + M_SRCMAC)) memcpy(p + M_SRCMAC, o + M_SRCMAC, 6);       /* :48-50 */
+    if (all_zero6(p + M_DSTMAC)) memcpy(p + M_DSTMAC, o + M_DSTMAC, 6);       /* :51-53 */
+    if (o[M_DSCP] != 0) p[M_DSCP] = o[M_DSCP];                                /* :54-56 */
+    if (ld32(o + M_SAMPLING) != 0) st32(p + M_SAMPLING, ld32(o + M_SAMPLING));/* :57-59 */
+}
+
+/* ------------------------------------------------------- feature folds */
+static void build_base_from_additional(uint8_t* base, uint64_t start, uint64_t end, uint16_t eth) {
+    /* pkg/model/flow_content.go:63-74 */
+    uint64_t bs = ld64(base + M_START);
+    if (bs == 0 || (bs > start && start != 0)) st64(base + M_START, start);
+    uint64_t be = ld64(base + M_END);
+    if (be == 0 || be < end) st64(base + M_END, end);
+    if (ld16(base + M_ETH) == 0) st16(base + M_ETH, eth);
+}
+
+static void merge_dns_block(oracle_content* p, const uint8_t* o) {
+    /* pkg/model/flow_content.go:81-95 */
+    if (!p->has_dns) { memcpy(p->dns, o, OR_DNS_SIZE); p->has_dns = 1; return; }   /* :81-84 */
+    st16(p->dns + D_FLAGS, (uint16_t)(ld16(p->dns + D_FLAGS) | ld16(o + D_FLAGS))); /* :86 */
+    if (ld16(o + D_ID) != 0) st16(p->dns + D_ID, ld16(o + D_ID));                   /* :87-89 */
+    if (p->dns[D_ERRNO] != o[D_ERRNO]) p->dns[D_ERRNO] = o[D_ERRNO];                /* :90-92 */
+    if (ld64(p->dns + D_LATENCY) < ld64(o + D_LATENCY))                             /* :93-95 */
+        st64(p->dns + D_LATENCY, ld64(o + D_LATENCY));
+}
+void oracle_accumulate_dns(oracle_content* p, const uint8_t* o) {
+    /* pkg/model/flow_content.go:76-96 */
+    build_base_from_additional(p->metrics, ld64(o + D_START), ld64(o + D_END), ld16(o + D_ETH));   /* :80 */
+    merge_dns_block(p, o);
+}
+
+static void merge_additional_block(oracle_content* p, const uint8_t* o) {
+    /* pkg/model/flow_content.go:159-176 */
+    if (!p->has_additional) { memcpy(p->additional, o, OR_ADD_SIZE); p->has_additional = 1; return; }
+    if (ld64(p->additional + A_RTT) < ld64(o + A_RTT))                               /* :164-166 */
+        st64(p->additional + A_RTT, ld64(o + A_RTT));
+    int32_t pr = (int32_t)ld32(p->additional + A_IPSEC_RET), orr = (int32_t)ld32(o + A_IPSEC_RET);
+    if (pr < orr) {                                                                  /* :168-171 */
+        p->additional[A_IPSEC_ENC] = o[A_IPSEC_ENC];
+        st32(p->additional + A_IPSEC_RET, (uint32_t)orr);
+        pr = orr;
+    }
+    if (pr == orr && o[A_IPSEC_ENC]) p->additional[A_IPSEC_ENC] = o[A_IPSEC_ENC];    /* :172-176 */
+}
+void oracle_accumulate_additional(oracle_content* p, const uint8_t* o) {
+    /* pkg/model/flow_content.go:154-177 */
+    build_base_from_additional(p->metrics, ld64(o + A_START), ld64(o + A_END), ld16(o + A_ETH));   /* :158 */
+    merge_additional_block(p, o);
+}
+
+void oracle_new_record_times(uint64_t now_unix_ns, uint64_t mono_now_ns, uint64_t start_mono,
+                             uint64_t end_mono, uint64_t* tfs, uint64_t* tfe) {
+    /* pkg/model/record.go:90-97: time.Duration(monoNow - start) then now.Add(-delta) */
+    *tfs = now_unix_ns - (mono_now_ns - start_mono);
+    *tfe = now_unix_ns - (mono_now_ns - end_mono);
+}
+
+/* ------------------------------------------------------------ hash spec */
+static inline uint64_t fmix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull; x ^= x >> 33;
+    return x;
+}
+uint64_t oracle_key_premix(const uint8_t* k) {
+    /* 5 LE words, byte 39 (padding) masked out */
+    const uint64_t P1 = 0x9E3779B97F4A7C15ull, P2 = 0xC2B2AE3D27D4EB4Full;
+    uint64_t w0 = ld64(k), w1 = ld64(k + 8), w2 = ld64(k + 16), w3 = ld64(k + 24),
+             w4 = ld64(k + 32) & 0x00FFFFFFFFFFFFFFull;
+    uint64_t h = 0x243F6A8885A308D3ull;
+    h = (h ^ w0) * P1; h ^= h >> 32;
+    h = (h ^ w1) * P2; h ^= h >> 29;
+    h = (h ^ w2) * P1; h ^= h >> 32;
+    h = (h ^ w3) * P2; h ^= h >> 29;
+    h = (h ^ w4) * P1; h ^= h >> 32;
+    return h;
+}
+uint64_t oracle_slot_hash(const uint8_t* k) { return fmix64(oracle_key_premix(k)); }
+uint64_t oracle_owner_hash(const uint8_t* k) { return fmix64(oracle_key_premix(k) ^ 0xA0761D6478BD642Full); }
+
+/* ------------------------------------------------------------- flat map */
+typedef struct {
+    uint8_t key[OR_ID_SIZE];
+    oracle_content c;
+    /* flowmap only: what the feature samples contribute to the base via
+     * buildBaseFromAdditional, kept apart so that the result does not depend on how
+     * fa_ingest / fa_ingest_dns / fa_ingest_additional calls interleave; combined at
+     * evict in LookupAndDeleteMap's order: base, then DNS, then additional
+     * (pkg/tracer/tracer.go:1094-1151). */
+    uint8_t  has_base;
+    uint64_t fs[2], fe[2];     /* [0]=dns [1]=additional: min non-zero start / max end */
+    uint16_t feth[2];          /* first non-zero eth_protocol in sample order */
+} entry_t;
+
+typedef struct {
+    uint32_t* idx;     /* 0 = empty, else entry index + 1 */
+    size_t    cap;     /* power of two */
+    entry_t*  ents;
+    size_t    n, ents_cap;
+} fmap;
+
+static void fmap_init(fmap* m, size_t hint) {
+    size_t cap = 64; while (cap < hint * 2) cap <<= 1;
+    m->cap = cap; m->idx = (uint32_t*)calloc(cap, sizeof(uint32_t));
+    m->ents_cap = hint < 16 ? 16 : hint; m->ents = (entry_t*)malloc(m->ents_cap * sizeof(entry_t)); m->n = 0;
+}
+static void fmap_free(fmap* m) { free(m->idx); free(m->ents); m->idx = NULL; m->ents = NULL; m->n = 0; }
+static void fmap_clear(fmap* m) { memset(m->idx, 0, m->cap * sizeof(uint32_t)); m->n = 0; }
+static void fmap_grow(fmap* m) {
+    size_t ncap = m->cap * 2; uint32_t* nidx = (uint32_t*)calloc(ncap, sizeof(uint32_t));
+    for (size_t i = 0; i < m->n; i++) {
+        size_t s = (size_t)oracle_slot_hash(m->ents[i].key) & (ncap - 1);
+        while (nidx[s]) s = (s + 1) & (ncap - 1);
+        nidx[s] = (uint32_t)(i + 1);
+    }
+    free(m->idx); m->idx = nidx; m->cap = ncap;
+}
+/* returns entry; *found tells whether it pre-existed. key compare = 40 bytes (pad already zeroed) */
+static entry_t* fmap_get(fmap* m, const uint8_t* key, int create, int* found) {
+    size_t s = (size_t)oracle_slot_hash(key) & (m->cap - 1);
+    for (;;) {
+        uint32_t v = m->idx[s];
+        if (!v) break;
+        entry_t* e = &m->ents[v - 1];
+        if (memcmp(e->key, key, OR_ID_SIZE) == 0) { *found = 1; return e; }
+        s = (s + 1) & (m->cap - 1);
+    }
+    *found = 0;
+    if (!create) return NULL;
+    if ((m->n + 1) * 2 > m->cap) { fmap_grow(m); return fmap_get(m, key, create, found); }
+    if (m->n == m->ents_cap) { m->ents_cap *= 2; m->ents = (entry_t*)realloc(m->ents, m->ents_cap * sizeof(entry_t)); }
+    entry_t* e = &m->ents[m->n];
+    memset(e, 0, sizeof(*e));
+    memcpy(e->key, key, OR_ID_SIZE);
+    m->idx[s] = (uint32_t)(++m->n);
+    return e;
+}
+static size_t fmap_dump_records(const fmap* m, uint8_t* out, size_t cap) {
+    size_t k = m->n < cap ? m->n : cap;
+    for (size_t i = 0; i < k; i++) {
+        memcpy(out + i * OR_REC_SIZE, m->ents[i].key, OR_ID_SIZE);
+        memcpy(out + i * OR_REC_SIZE + OR_ID_SIZE, m->ents[i].c.metrics, OR_MET_SIZE);
+    }
+    return m->n;
+}
+
+/* ------------------------------------------------------------ Accounter */
+typedef struct generation { uint8_t* recs; size_t n; struct generation* next; } generation;
+struct oracle_accounter {
+    size_t max_entries;
+    fmap   entries;
+    generation *gen_head, *gen_tail; size_t gen_pending;
+};
+
+oracle_accounter* oracle_accounter_new(size_t max_entries) {
+    oracle_accounter* a = (oracle_accounter*)calloc(1, sizeof(*a));
+    a->max_entries = max_entries;
+    fmap_init(&a->entries, max_entries < (1u << 20) ? max_entries : (1u << 20));
+    return a;
+}
+void oracle_accounter_free(oracle_accounter* a) {
+    if (!a) return;
+    while (a->gen_head) { generation* g = a->gen_head; a->gen_head = g->next; free(g->recs); free(g); }
+    fmap_free(&a->entries); free(a);
+}
+size_t oracle_accounter_len(const oracle_accounter* a) { return a->entries.n; }
+
+static void accounter_push_generation(oracle_accounter* a) {
+    generation* g = (generation*)calloc(1, sizeof(*g));
+    g->n = a->entries.n; g->recs = (uint8_t*)malloc(g->n ? g->n * OR_REC_SIZE : 1);
+    fmap_dump_records(&a->entries, g->recs, g->n);
+    if (a->gen_tail) a->gen_tail->next = g; else a->gen_head = g;
+    a->gen_tail = g; a->gen_pending++;
+    fmap_clear(&a->entries);
+}
+
+void oracle_accounter_account(oracle_accounter* a, const uint8_t* wire, size_t n) {
+    uint8_t rec[OR_REC_SIZE];
+    for (size_t i = 0; i < n; i++) {
+        oracle_read_from(wire + i * OR_REC_SIZE, rec);                  /* tracer_ringbuf.go:112-134 */
+        int found; entry_t* e = fmap_get(&a->entries, rec, 0, &found);
+        if (found) {
+            oracle_accumulate_base(e->c.metrics, rec + OR_ID_SIZE);      /* account.go:82-83 */
+        } else {
+            if (a->entries.n >= a->max_entries) accounter_push_generation(a);   /* account.go:85-94 */
+            e = fmap_get(&a->entries, rec, 1, &found);
+            memcpy(e->c.metrics, rec + OR_ID_SIZE, OR_MET_SIZE);         /* account.go:95: whole 104 B kept */
+        }
+    }
+}
+size_t oracle_accounter_evict(oracle_accounter* a, uint8_t* out, size_t cap) {
+    size_t n = fmap_dump_records(&a->entries, out, cap);                /* account.go:63-80,102-124 */
+    fmap_clear(&a->entries);
+    return n;
+}
+size_t oracle_accounter_pending(const oracle_accounter* a) { return a->gen_pending; }
+size_t oracle_accounter_next_generation_len(const oracle_accounter* a) { return a->gen_head ? a->gen_head->n : 0; }
+size_t oracle_accounter_pop_generation(oracle_accounter* a, uint8_t* out, size_t cap) {
+    generation* g = a->gen_head; if (!g) return 0;
+    size_t k = g->n < cap ? g->n : cap; memcpy(out, g->recs, k * OR_REC_SIZE);
+    size_t n = g->n; a->gen_head = g->next; if (!a->gen_head) a->gen_tail = NULL; a->gen_pending--;
+    free(g->recs); free(g);
+    return n;
+}
+
+size_t oracle_accounter_sharded_run(const uint8_t* wire, size_t n, int n_threads, uint8_t* out, size_t cap) {
+    /* CPU-baseline only: T private Accounters, thread t owns keys with owner_hash % T == t.
+     * Pass 1 computes each record's owner once; pass 2 lets every thread walk the
+     * stream and fold only its own records (keeps stream order inside a key). */
+    if (n_threads < 1) n_threads = 1;
+    uint8_t* owner = (uint8_t*)malloc(n ? n : 1);
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (long long i = 0; i < (long long)n; i++)
+        owner[i] = (uint8_t)(oracle_owner_hash(wire + (size_t)i * OR_REC_SIZE) % (uint64_t)n_threads);
+    fmap* maps = (fmap*)calloc((size_t)n_threads, sizeof(fmap));
+#pragma omp parallel num_threads(n_threads)
+    {
+#ifdef _OPENMP
+        int t = omp_get_thread_num();
+#else
+        int t = 0;
+#endif
+        fmap* m = &maps[t]; fmap_init(m, 1u << 16);
+        uint8_t rec[OR_REC_SIZE];
+        for (size_t i = 0; i < n; i++) {
+            if (owner[i] != t) continue;
+            oracle_read_from(wire + i * OR_REC_SIZE, rec);
+            int found; entry_t* e = fmap_get(m, rec, 1, &found);
+            if (found) oracle_accumulate_base(e->c.metrics, rec + OR_ID_SIZE);
+            else memcpy(e->c.metrics, rec + OR_ID_SIZE, OR_MET_SIZE);
+        }
+    }
+    size_t total = 0;
+    for (int t = 0; t < n_threads; t++) {
+        size_t room = total < cap ? cap - total : 0;
+        if (out) fmap_dump_records(&maps[t], out + total * OR_REC_SIZE, room);
+        total += maps[t].n; fmap_free(&maps[t]);
+    }
+    free(maps); free(owner);
+    return total;
+}
+
+/* -------------------------------------------------------------- flowmap */
+struct oracle_flowmap { fmap m; };
+oracle_flowmap* oracle_flowmap_new(void) { oracle_flowmap* m = (oracle_flowmap*)calloc(1, sizeof(*m)); fmap_init(&m->m, 1024); return m; }
+void oracle_flowmap_free(oracle_flowmap* m) { if (m) { fmap_free(&m->m); free(m); } }
+size_t oracle_flowmap_len(const oracle_flowmap* m) { return m->m.n; }
+
+void oracle_flowmap_account(oracle_flowmap* m, const uint8_t* wire, size_t n) {
+    uint8_t rec[OR_REC_SIZE];
+    for (size_t i = 0; i < n; i++) {
+        oracle_read_from(wire + i * OR_REC_SIZE, rec);
+        int found; entry_t* e = fmap_get(&m->m, rec, 1, &found);
+        if (e->has_base) oracle_accumulate_base(e->c.metrics, rec + OR_ID_SIZE);   /* account.go:82-83 */
+        else { memcpy(e->c.metrics, rec + OR_ID_SIZE, OR_MET_SIZE); e->has_base = 1; }  /* account.go:95 */
+    }
+}
+static void feature_base_effect(entry_t* e, int which, uint64_t s, uint64_t en, uint16_t eth) {
+    if (e->fs[which] == 0 || (e->fs[which] > s && s != 0)) e->fs[which] = s;
+    if (e->fe[which] == 0 || e->fe[which] < en) e->fe[which] = en;
+    if (e->feth[which] == 0) e->feth[which] = eth;
+}
+void oracle_flowmap_fold_dns(oracle_flowmap* m, const uint8_t* recs, size_t n) {
+    uint8_t key[OR_ID_SIZE];
+    for (size_t i = 0; i < n; i++) {
+        memcpy(key, recs + i * OR_DNSREC_SIZE, OR_ID_SIZE); key[39] = 0;
+        int found; entry_t* e = fmap_get(&m->m, key, 1, &found);      /* empty base if absent: tracer.go:1179-1182 */
+        uint8_t dns[OR_DNS_SIZE]; memcpy(dns, recs + i * OR_DNSREC_SIZE + OR_ID_SIZE, OR_DNS_SIZE);
+        dns[63] = 0;                                                  /* trailing pad: blank in the Go mirror */
+        feature_base_effect(e, 0, ld64(dns + D_START), ld64(dns + D_END), ld16(dns + D_ETH));
+        merge_dns_block(&e->c, dns);
+    }
+}
+void oracle_flowmap_fold_additional(oracle_flowmap* m, const uint8_t* recs, size_t n) {
+    uint8_t key[OR_ID_SIZE];
+    for (size_t i = 0; i < n; i++) {
+        memcpy(key, recs + i * OR_ADDREC_SIZE, OR_ID_SIZE); key[39] = 0;
+        int found; entry_t* e = fmap_get(&m->m, key, 1, &found);
+        uint8_t add[OR_ADD_SIZE]; memcpy(add, recs + i * OR_ADDREC_SIZE + OR_ID_SIZE, OR_ADD_SIZE);
+        add[31] = 0;
+        feature_base_effect(e, 1, ld64(add + A_START), ld64(add + A_END), ld16(add + A_ETH));
+        merge_additional_block(&e->c, add);
+    }
+}
+size_t oracle_flowmap_evict(oracle_flowmap* m, uint8_t* out, uint8_t* out_dns, uint8_t* out_add,
+                            uint8_t* out_present, size_t cap) {
+    size_t k = m->m.n < cap ? m->m.n : cap;
+    for (size_t i = 0; i < k; i++) {
+        const entry_t* e = &m->m.ents[i];
+        uint8_t met[OR_MET_SIZE];
+        if (e->has_base) memcpy(met, e->c.metrics, OR_MET_SIZE); else memset(met, 0, OR_MET_SIZE);
+        if (e->c.has_dns) build_base_from_additional(met, e->fs[0], e->fe[0], e->feth[0]);
+        if (e->c.has_additional) build_base_from_additional(met, e->fs[1], e->fe[1], e->feth[1]);
+        memcpy(out + i * OR_REC_SIZE, e->key, OR_ID_SIZE);
+        memcpy(out + i * OR_REC_SIZE + OR_ID_SIZE, met, OR_MET_SIZE);
+        if (out_dns) { if (e->c.has_dns) memcpy(out_dns + i * OR_DNS_SIZE, e->c.dns, OR_DNS_SIZE); else memset(out_dns + i * OR_DNS_SIZE, 0, OR_DNS_SIZE); }
+        if (out_add) { if (e->c.has_additional) memcpy(out_add + i * OR_ADD_SIZE, e->c.additional, OR_ADD_SIZE); else memset(out_add + i * OR_ADD_SIZE, 0, OR_ADD_SIZE); }
+        if (out_present) out_present[i] = (uint8_t)((e->c.has_dns ? 1 : 0) | (e->c.has_additional ? 2 : 0));
+    }
+    size_t n = m->m.n; fmap_clear(&m->m);
+    return n;
+}
+
+/* ----------------------------------------------------------- KERNEL_MAP */
+struct oracle_kmap {
+    size_t max_entries; int ringbuf;
+    fmap m;
+    uint8_t* spill; size_t n_spill, spill_cap;
+    uint64_t fail_create, intf_missed;
+};
+oracle_kmap* oracle_kmap_new(size_t max_entries, int ringbuf_fallback) {
+    oracle_kmap* k = (oracle_kmap*)calloc(1, sizeof(*k));
+    k->max_entries = max_entries; k->ringbuf = ringbuf_fallback;
+    fmap_init(&k->m, max_entries < (1u << 20) ? max_entries : (1u << 20));
+    return k;
+}
+void oracle_kmap_free(oracle_kmap* k) { if (k) { fmap_free(&k->m); free(k->spill); free(k); } }
+size_t oracle_kmap_len(const oracle_kmap* k) { return k->m.n; }
+uint64_t oracle_kmap_counter_fail_create(const oracle_kmap* k) { return k->fail_create; }
+uint64_t oracle_kmap_counter_intf_missed(const oracle_kmap* k) { return k->intf_missed; }
+
+static int add_observed_intf(uint8_t* v, uint32_t if_index, uint8_t direction) {
+    /* bpf/flows.c:76-96 */
+    uint8_t nb = v[M_NBOBS];
+    if (nb >= 6) return 1;
+    for (uint8_t i = 0; i < nb; i++) {
+        if (ld32(v + M_OBSINTF + 4 * i) == if_index) {
+            if (v[M_OBSDIR + i] != direction && v[M_OBSDIR + i] != 3) v[M_OBSDIR + i] = 3;
+            return 0;
+        }
+    }
+    st32(v + M_OBSINTF + 4 * nb, if_index);
+    v[M_OBSDIR + nb] = direction;
+    v[M_NBOBS] = (uint8_t)(nb + 1);
+    return 0;
+}
+
+static void update_existing_flow(oracle_kmap* k, uint8_t* agg, const uint8_t* key, const uint8_t* ev) {
+    /* bpf/flows.c:98-143; ev = the packet event's metrics block */
+    uint32_t if_index = ld32(ev + M_IFINDEX);
+    uint64_t ts = ld64(ev + M_START);
+    if (ld32(agg + M_IFINDEX) == if_index) {
+        st32(agg + M_PACKETS, ld32(agg + M_PACKETS) + 1);
+        st64(agg + M_BYTES, ld64(agg + M_BYTES) + ld64(ev + M_BYTES));
+        st64(agg + M_END, ts);                                         /* last writer, not max */
+        st16(agg + M_FLAGS, (uint16_t)(ld16(agg + M_FLAGS) | ld16(ev + M_FLAGS)));
+        agg[M_DSCP] = ev[M_DSCP];
+        st32(agg + M_SAMPLING, ld32(ev + M_SAMPLING));
+        uint16_t hv = ld16(ev + M_SSLVER); uint8_t ty = ev[M_TLSTYPES];
+        if (hv > 0 && ld16(agg + M_SSLVER) != hv) {
+            if (ld16(agg + M_SSLVER) == 0) st16(agg + M_SSLVER, hv);
+            else agg[M_MISC] |= 0x01;                                  /* MISC_FLAGS_SSL_MISMATCH */
+        }
+        if (ld16(ev + M_CIPHER) > 0 && ty == 0x02) st16(agg + M_CIPHER, ld16(ev + M_CIPHER));
+        if (ld16(ev + M_KEYSHARE) > 0 && ty == 0x02) st16(agg + M_KEYSHARE, ld16(ev + M_KEYSHARE));
+        agg[M_TLSTYPES] |= ty;
+    } else if (if_index != 0) {
+        st64(agg + M_END, ts);
+        st16(agg + M_FLAGS, (uint16_t)(ld16(agg + M_FLAGS) | ld16(ev + M_FLAGS)));
+        if (add_observed_intf(agg, if_index, ev[M_DIR]) > 0 && key[36] != 0) k->intf_missed++;  /* :134-142 */
+    }
+}
+
+void oracle_kmap_packets(oracle_kmap* k, const uint8_t* wire, size_t n) {
+    uint8_t rec[OR_REC_SIZE];
+    for (size_t i = 0; i < n; i++) {
+        oracle_read_from(wire + i * OR_REC_SIZE, rec);
+        const uint8_t* ev = rec + OR_ID_SIZE;
+        int found; entry_t* e = fmap_get(&k->m, rec, 0, &found);        /* flows.c:222 */
+        if (found) { update_existing_flow(k, e->c.metrics, rec, ev); continue; }
+        /* flows.c:228-245 new_flow */
+        uint8_t nf[OR_MET_SIZE]; memset(nf, 0, sizeof nf);
+        st32(nf + M_IFINDEX, ld32(ev + M_IFINDEX)); nf[M_DIR] = ev[M_DIR];
+        st32(nf + M_PACKETS, 1); st64(nf + M_BYTES, ld64(ev + M_BYTES));
+        st16(nf + M_ETH, ld16(ev + M_ETH));
+        st64(nf + M_START, ld64(ev + M_START)); st64(nf + M_END, ld64(ev + M_START));
+        st16(nf + M_FLAGS, ld16(ev + M_FLAGS)); nf[M_DSCP] = ev[M_DSCP];
+        st32(nf + M_SAMPLING, ld32(ev + M_SAMPLING));
+        memcpy(nf + M_DSTMAC, ev + M_DSTMAC, 6); memcpy(nf + M_SRCMAC, ev + M_SRCMAC, 6);
+        st16(nf + M_SSLVER, ld16(ev + M_SSLVER)); st16(nf + M_CIPHER, ld16(ev + M_CIPHER));
+        st16(nf + M_KEYSHARE, ld16(ev + M_KEYSHARE)); nf[M_TLSTYPES] = ev[M_TLSTYPES];
+        if (k->m.n < k->max_entries) {                                  /* flows.c:247 BPF_NOEXIST */
+            e = fmap_get(&k->m, rec, 1, &found);
+            memcpy(e->c.metrics, nf, OR_MET_SIZE);
+        } else if (k->ringbuf) {                                        /* flows.c:262-279, errno = E2BIG */
+            nf[M_ERRNO] = 7;
+            if (k->n_spill == k->spill_cap) { k->spill_cap = k->spill_cap ? k->spill_cap * 2 : 64; k->spill = (uint8_t*)realloc(k->spill, k->spill_cap * OR_REC_SIZE); }
+            memcpy(k->spill + k->n_spill * OR_REC_SIZE, rec, OR_ID_SIZE);
+            memcpy(k->spill + k->n_spill * OR_REC_SIZE + OR_ID_SIZE, nf, OR_MET_SIZE);
+            k->n_spill++;
+        } else {
+            k->fail_create++;                                           /* flows.c:285 */
+        }
+    }
+}
+size_t oracle_kmap_evict(oracle_kmap* k, uint8_t* out, size_t cap) {
+    size_t n = fmap_dump_records(&k->m, out, cap); fmap_clear(&k->m); return n;
+}
+size_t oracle_kmap_spilled(oracle_kmap* k, uint8_t* out, size_t cap) {
+    if (!out) return k->n_spill;                   /* peek */
+    size_t c = k->n_spill < cap ? k->n_spill : cap;
+    if (out && c) memcpy(out, k->spill, c * OR_REC_SIZE);
+    size_t n = k->n_spill; k->n_spill = 0; return n;
+}
+
+/* ------------------------------------------------------------- sketches */
+void oracle_cms_update(uint64_t* table, uint32_t lw, uint32_t depth, uint64_t seed, const uint8_t* wire, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t* r = wire + i * OR_REC_SIZE;
+        uint64_t h = oracle_key_premix(r);
+        uint64_t a = fmix64(h ^ 0xE7037ED1A0B428DBull ^ seed);
+        uint64_t b = fmix64(h ^ 0x8EBC6AF09C88C6E3ull ^ seed) | 1ull;
+        uint64_t w = ld32(r + OR_ID_SIZE + M_PACKETS);
+        for (uint32_t d = 0; d < depth; d++) {
+            uint64_t g = (a + (uint64_t)d * b) * 0x9E3779B97F4A7C15ull;
+            table[((size_t)d << lw) + (size_t)(g >> (64 - lw))] += w;
+        }
+    }
+}
+void oracle_cms_query(const uint64_t* table, uint32_t lw, uint32_t depth, uint64_t seed, const uint8_t* keys, size_t n, uint64_t* est) {
+    for (size_t i = 0; i < n; i++) {
+        uint64_t h = oracle_key_premix(keys + i * OR_ID_SIZE);
+        uint64_t a = fmix64(h ^ 0xE7037ED1A0B428DBull ^ seed);
+        uint64_t b = fmix64(h ^ 0x8EBC6AF09C88C6E3ull ^ seed) | 1ull;
+        uint64_t m = UINT64_MAX;
+        for (uint32_t d = 0; d < depth; d++) {
+            uint64_t g = (a + (uint64_t)d * b) * 0x9E3779B97F4A7C15ull;
+            uint64_t v = table[((size_t)d << lw) + (size_t)(g >> (64 - lw))];
+            if (v < m) m = v;
+        }
+        est[i] = m;
+    }
+}
+void oracle_hll_update(uint8_t* regs, uint32_t p, uint64_t seed, const uint8_t* wire, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        uint64_t h = fmix64(oracle_key_premix(wire + i * OR_REC_SIZE) ^ 0x589965CC75374CC3ull ^ seed);
+        uint32_t idx = (uint32_t)(h >> (64 - p));
+        uint64_t rest = h << p;                       /* remaining 64-p bits, left aligned */
+        uint32_t rho = rest ? (uint32_t)__builtin_clzll(rest) + 1 : (64 - p) + 1;
+        if (rho > 64 - p + 1) rho = 64 - p + 1;
+        if (regs[idx] < rho) regs[idx] = (uint8_t)rho;
+    }
+}
+double oracle_hll_estimate(const uint8_t* regs, uint32_t p) {
+    size_t m = (size_t)1 << p; double sum = 0.0; size_t zeros = 0;
+    for (size_t i = 0; i < m; i++) { sum += ldexp(1.0, -(int)regs[i]); if (!regs[i]) zeros++; }
+    double alpha = m >= 128 ? 0.7213 / (1.0 + 1.079 / (double)m) : (m == 64 ? 0.709 : (m == 32 ? 0.697 : 0.673));
+    double e = alpha * (double)m * (double)m / sum;
+    if (e <= 2.5 * (double)m && zeros) e = (double)m * log((double)m / (double)zeros);
+    return e;
+}

@@ -1,0 +1,133 @@
+/*
+ * oracle.h — CPU restatement of the netobserv agent's flow-aggregation hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under netobserv_ebpf_agent_b200/ may
+ * include, link or call this; only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs use it, and only as the
+ * checker or the timed CPU baseline.
+ *
+ * Parity status: PINNED for ACCOUNTER mode, ReadFrom decoding, AccumulateDNS,
+ * AccumulateAdditional and NewRecord time conversion against the reference's
+ * own known-answer tests (tests/test_oracle_goldens.py transcribes
+ * pkg/flow/account_test.go:47-217, pkg/model/record_test.go:19-102,193-224,
+ * 323-347, pkg/model/flow_content_test.go:11-53,184-246,338-380).
+ * SOURCE-PINNED, TEST-UNPINNED (the reference has no unit test): the
+ * order-dependent fields of AccumulateBase (eth_protocol/dscp/sampling/MACs)
+ * and all of KERNEL_MAP mode (bpf/flows.c:76-143,222-288).
+ * PARITY UNPINNED: count-min sketch and HyperLogLog — they do not exist in the
+ * reference; the oracle restates this repo's own spec
+ * and tests additionally validate them against exact counts within (eps,delta).
+ *
+ * The Go toolchain is absent from the build image, so the reference itself
+ * cannot be compiled: there is no oracle/_ref.
+ *
+ * Everything works on raw little-endian byte buffers with the offsets below;
+ * the product header include/flowagg.h is deliberately NOT included.
+ */
+#ifndef FLOWAGG_ORACLE_H
+#define FLOWAGG_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* sizes (reference bpf/types.h:94-126,131-140,174-181,191-215) */
+enum {
+    OR_ID_SIZE = 40, OR_MET_SIZE = 104, OR_REC_SIZE = 144,
+    OR_DNS_SIZE = 64, OR_ADD_SIZE = 32,
+    OR_DNSREC_SIZE = 104, OR_ADDREC_SIZE = 72
+};
+
+/* --- pkg/model/record.go:227-231 ReadFrom: binary.Read of 144 bytes; blank (padding)
+ * struct fields are skipped by encoding/binary, i.e. come out zero. */
+void oracle_read_from(const uint8_t* wire144, uint8_t* rec144);
+
+/* --- pkg/model/flow_content.go:28-61 */
+void oracle_accumulate_base(uint8_t* p_metrics104, const uint8_t* o_metrics104);
+
+/* BpfFlowContent restated: base metrics + optional feature blocks. */
+typedef struct oracle_content {
+    uint8_t metrics[OR_MET_SIZE];
+    uint8_t dns[OR_DNS_SIZE];
+    uint8_t additional[OR_ADD_SIZE];
+    uint8_t has_dns;
+    uint8_t has_additional;
+} oracle_content;
+
+/* --- pkg/model/flow_content.go:63-96 */
+void oracle_accumulate_dns(oracle_content* p, const uint8_t* dns64);
+/* --- pkg/model/flow_content.go:154-177 */
+void oracle_accumulate_additional(oracle_content* p, const uint8_t* add32);
+
+/* --- pkg/model/record.go:90-97: wall = now - (monoNow - mono), u64 arithmetic. */
+void oracle_new_record_times(uint64_t now_unix_ns, uint64_t mono_now_ns,
+                             uint64_t start_mono, uint64_t end_mono,
+                             uint64_t* time_flow_start_ns, uint64_t* time_flow_end_ns);
+
+/* --- pkg/flow/account.go:58-124: the Accounter as a sequential state machine. */
+typedef struct oracle_accounter oracle_accounter;
+oracle_accounter* oracle_accounter_new(size_t max_entries);
+void   oracle_accounter_free(oracle_accounter* a);
+/* Feed n wire records (each goes through ReadFrom, tracer_ringbuf.go:112-134).
+ * Evictions of reason "full" (account.go:85-94) are queued as generations. */
+void   oracle_accounter_account(oracle_accounter* a, const uint8_t* wire, size_t n);
+size_t oracle_accounter_len(const oracle_accounter* a);
+/* Timer / closing eviction (account.go:63-80): moves all entries out. Returns count
+ * (writes at most cap records, in first-insertion order). */
+size_t oracle_accounter_evict(oracle_accounter* a, uint8_t* out_recs, size_t cap);
+/* "full" generations queued by _account, oldest first. */
+size_t oracle_accounter_pending(const oracle_accounter* a);
+size_t oracle_accounter_next_generation_len(const oracle_accounter* a);
+size_t oracle_accounter_pop_generation(oracle_accounter* a, uint8_t* out_recs, size_t cap);
+
+/* Multi-thread variant used only as the `--impl reference` CPU baseline: records are
+ * partitioned by key hash over n_threads private Accounters (no max_entries cut). */
+size_t oracle_accounter_sharded_run(const uint8_t* wire, size_t n, int n_threads,
+                                    uint8_t* out_recs, size_t cap);
+
+/* --- Map path with feature folds: LookupAndDeleteMap's merged view
+ * (pkg/tracer/tracer.go:1063-1187) under the record-by-record fold contract
+ * (SURVEY.md §8 a12'). */
+typedef struct oracle_flowmap oracle_flowmap;
+oracle_flowmap* oracle_flowmap_new(void);
+void   oracle_flowmap_free(oracle_flowmap* m);
+void   oracle_flowmap_account(oracle_flowmap* m, const uint8_t* wire, size_t n);          /* ACCOUNTER fold */
+void   oracle_flowmap_fold_dns(oracle_flowmap* m, const uint8_t* dnsrecs, size_t n);       /* n x 104 B */
+void   oracle_flowmap_fold_additional(oracle_flowmap* m, const uint8_t* addrecs, size_t n);/* n x 72 B */
+size_t oracle_flowmap_len(const oracle_flowmap* m);
+size_t oracle_flowmap_evict(oracle_flowmap* m, uint8_t* out_recs, uint8_t* out_dns,
+                            uint8_t* out_add, uint8_t* out_present, size_t cap);
+
+/* --- KERNEL_MAP mode: bpf/flows.c:76-143 (update_existing_flow, add_observed_intf)
+ * and :222-288 (lookup / insert NOEXIST / spill).  Each input record is one packet
+ * event whose metrics carry (ts=start, len=bytes, flags, dscp, sampling, ifindex,
+ * direction, eth, macs, tls*). */
+typedef struct oracle_kmap oracle_kmap;
+oracle_kmap* oracle_kmap_new(size_t max_entries, int ringbuf_fallback);
+void   oracle_kmap_free(oracle_kmap* m);
+void   oracle_kmap_packets(oracle_kmap* m, const uint8_t* wire, size_t n);
+size_t oracle_kmap_len(const oracle_kmap* m);
+size_t oracle_kmap_evict(oracle_kmap* m, uint8_t* out_recs, size_t cap);
+/* records spilled to the ring buffer (errno = E2BIG = 7), in order */
+size_t oracle_kmap_spilled(oracle_kmap* m, uint8_t* out_recs, size_t cap);
+uint64_t oracle_kmap_counter_fail_create(const oracle_kmap* m);
+uint64_t oracle_kmap_counter_intf_missed(const oracle_kmap* m);
+
+/* --- hashes + sketches (this repo's spec; PARITY UNPINNED, see header comment) */
+uint64_t oracle_key_premix(const uint8_t* key40);
+uint64_t oracle_slot_hash(const uint8_t* key40);
+uint64_t oracle_owner_hash(const uint8_t* key40);
+void   oracle_cms_update(uint64_t* table, uint32_t log2_width, uint32_t depth, uint64_t seed,
+                         const uint8_t* wire, size_t n);          /* += packets per record */
+void   oracle_cms_query(const uint64_t* table, uint32_t log2_width, uint32_t depth, uint64_t seed,
+                        const uint8_t* keys40, size_t n, uint64_t* est);
+void   oracle_hll_update(uint8_t* regs, uint32_t p, uint64_t seed, const uint8_t* wire, size_t n);
+double oracle_hll_estimate(const uint8_t* regs, uint32_t p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
