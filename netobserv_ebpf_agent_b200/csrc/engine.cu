@@ -1,0 +1,642 @@
+// engine.cu — the C ABI of libflowagg.so (include/flowagg.h) and the host-side engine:
+// device memory, streams, staging of host batches, the ACCOUNTER "full" logic, stats.
+// There is NO CPU fallback: without a CUDA device fa_create fails with FA_E_NODEV.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/flowagg.h"
+#include "flowgen.h"
+#include "kernels.cuh"
+
+static_assert(sizeof(fa_flow_id) == 40, "flow_id ABI");
+static_assert(sizeof(fa_flow_metrics) == 104, "flow_metrics ABI");
+static_assert(sizeof(fa_flow_record) == 144, "flow_record ABI");
+static_assert(sizeof(fa_dns_metrics) == 64, "dns_metrics ABI");
+static_assert(sizeof(fa_additional_metrics) == 32, "additional_metrics ABI");
+static_assert(sizeof(fa_dns_record) == 104 && sizeof(fa_additional_record) == 72, "feature record ABI");
+static_assert(offsetof(fa_flow_metrics, if_index_first_seen) == 44 && offsetof(fa_flow_metrics, observed_intf) == 68 &&
+              offsetof(fa_flow_metrics, ssl_version) == 92 && offsetof(fa_flow_metrics, misc_flags) == 99, "flow_metrics offsets");
+static_assert(offsetof(fa_dns_metrics, name) == 31 && offsetof(fa_additional_metrics, ipsec_encrypted) == 30, "feature offsets");
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(FA_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+enum PtrKind { PTR_PAGEABLE, PTR_PINNED, PTR_DEVICE };
+PtrKind classify(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return PTR_PAGEABLE; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return PTR_DEVICE;
+    if (a.type == cudaMemoryTypeHost) return PTR_PINNED;
+    return PTR_PAGEABLE;
+}
+
+// ---------------------------------------------------------------- Zipf threshold tables
+struct ZipfTable {
+    std::vector<uint64_t> thresholds;
+    std::vector<uint32_t> first, size;
+    uint64_t* d_thresholds = nullptr; uint32_t* d_first = nullptr; uint32_t* d_size = nullptr;   // per device, lazily
+    int device = -1;
+};
+std::mutex g_zipf_mu;
+std::map<std::pair<uint64_t, uint32_t>, ZipfTable*> g_zipf;
+
+// Ranks 1..N split into octaves [2^o, 2^(o+1)), each octave into <= 256 equal sub-ranges.
+ZipfTable* zipf_table(uint64_t n_keys, uint32_t s_milli) {
+    std::lock_guard<std::mutex> lk(g_zipf_mu);
+    auto key = std::make_pair(n_keys, s_milli);
+    auto it = g_zipf.find(key);
+    if (it != g_zipf.end()) return it->second;
+    ZipfTable* z = new ZipfTable();
+    const double s = s_milli / 1000.0;
+    std::vector<long double> mass;
+    for (uint64_t lo = 1; lo <= n_keys; lo <<= 1) {
+        const uint64_t hi = std::min<uint64_t>(n_keys + 1, lo << 1);      // ranks [lo, hi)
+        const uint64_t span = hi - lo;
+        const uint64_t parts = std::min<uint64_t>(span, 256);
+        for (uint64_t pi = 0; pi < parts; pi++) {
+            const uint64_t a = lo + span * pi / parts, b = lo + span * (pi + 1) / parts;
+            long double m = 0;
+            for (uint64_t k = a; k < b; k++) m += std::pow((double)k, -s);
+            z->first.push_back((uint32_t)(a - 1));
+            z->size.push_back((uint32_t)(b - a));
+            mass.push_back(m);
+        }
+    }
+    long double total = 0; for (auto m : mass) total += m;
+    long double run = 0;
+    z->thresholds.resize(mass.size());
+    for (size_t i = 0; i < mass.size(); i++) {
+        run += mass[i];
+        long double f = run / total * 18446744073709551616.0L;
+        z->thresholds[i] = f >= 18446744073709551615.0L ? ~0ull : (uint64_t)f;
+    }
+    z->thresholds.back() = ~0ull;
+    g_zipf[key] = z;
+    return z;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------ engine
+struct fa_engine {
+    fa_config cfg{};
+    int device = 0, sm_count = 148;
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;
+    std::mutex mu;
+
+    fa::Table table{};
+    uint64_t slots = 0, epoch = 0;
+    fa::Counters* d_ctr = nullptr;
+    fa::Counters* h_ctr = nullptr;            // pinned mirror
+    uint64_t max_batch = 0;
+
+    // staging for host input (double buffered)
+    uint8_t* d_stage[2] = {nullptr, nullptr};
+    uint8_t* h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};   // kernel that consumed the stage finished
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};       // H2D copy into the stage finished
+    int stage_cur = 0;
+
+    fa::FixupScratch* d_scratch = nullptr;
+    uint32_t* d_spill_idx = nullptr;
+    uint32_t* d_cut_set = nullptr; uint32_t cut_set_slots = 0;
+    uint32_t* d_cut_bitmap = nullptr; uint32_t* d_cut_out = nullptr; uint32_t* h_cut_out = nullptr;
+
+    uint8_t* d_evict = nullptr; uint64_t evict_cap = 0;
+    uint32_t* d_route_tmp = nullptr; unsigned long long* d_route_counts = nullptr;
+
+    fa::SketchParams sk{};
+
+    // live-flow bookkeeping for the "full" rule
+    uint64_t live_known = 0;                  // exact as of the last sync
+    uint64_t unsynced_records = 0;            // records launched since then (upper bound on new flows)
+
+    fa_stats st{};
+};
+
+namespace {
+
+int sync_counters(fa_engine* e) {
+    CU(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(fa::Counters), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->live_known = e->h_ctr->live;
+    e->unsynced_records = 0;
+    return FA_OK;
+}
+
+// Launch K1 on a device-resident chunk (n <= max_batch).
+int launch_chunk(fa_engine* e, const uint8_t* d_recs, uint32_t n) {
+    fa::AggLaunch a{};
+    a.recs = reinterpret_cast<const uint4*>(d_recs);
+    a.n = n;
+    a.table = e->table;
+    a.epoch = ++e->epoch;
+    a.ctr = e->d_ctr;
+    a.spill_idx = e->d_spill_idx;
+    a.sk = (e->cfg.flags & FA_F_ENABLE_SKETCH) ? e->sk : fa::SketchParams{};
+    a.scratch = e->d_scratch;
+    a.sm_count = e->sm_count;
+    e->st.kernel_launches += fa::launch_aggregate(a, e->stream);
+    CU(cudaGetLastError());
+    e->unsynced_records += n;
+    e->st.records_ingested += n;
+    return FA_OK;
+}
+
+// ACCOUNTER mode: fold a device-resident chunk honouring max_entries.
+// Returns FA_OK (all folded) or FA_FULL with *consumed < n.
+int ingest_chunk_accounter(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint32_t* consumed) {
+    *consumed = 0;
+    const uint64_t M = e->cfg.max_entries;
+    if (e->live_known + e->unsynced_records + n > M) {
+        int rc = sync_counters(e);                     // exact live count
+        if (rc) return rc;
+    }
+    if (e->live_known + e->unsynced_records + n <= M) { // cannot overflow: fast path
+        int rc = launch_chunk(e, d_recs, n);
+        if (rc) return rc;
+        *consumed = n;
+        return FA_OK;
+    }
+    // slow path: find the first record whose key is new while the cache is full
+    e->st.kernel_launches += fa::launch_full_cut(reinterpret_cast<const uint4*>(d_recs), n, e->table, e->live_known, M,
+                                                 e->d_cut_set, e->cut_set_slots, e->d_cut_bitmap, e->d_cut_out,
+                                                 e->sm_count, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(e->h_cut_out, e->d_cut_out, 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    const uint32_t cut = *e->h_cut_out;
+    if (cut > 0) {
+        int rc = launch_chunk(e, d_recs, cut);
+        if (rc) return rc;
+        rc = sync_counters(e);
+        if (rc) return rc;
+    }
+    *consumed = cut;
+    if (cut < n) { e->st.full_cuts++; return FA_FULL; }
+    return FA_OK;
+}
+
+int ingest_device(fa_engine* e, const uint8_t* d_recs, size_t n, size_t* consumed) {
+    size_t done = 0;
+    while (done < n) {
+        const uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
+        uint32_t took = 0;
+        int rc = ingest_chunk_accounter(e, d_recs + done * fa::kRecBytes, c, &took);
+        done += took;
+        if (rc != FA_OK) { if (consumed) *consumed = done; return rc; }
+    }
+    if (consumed) *consumed = done;
+    return FA_OK;
+}
+
+int ingest_host(fa_engine* e, const uint8_t* h_recs, size_t n, size_t* consumed, bool pinned) {
+    size_t done = 0;
+    int rc = FA_OK;
+    while (done < n) {
+        const uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
+        const int sidx = e->stage_cur; e->stage_cur ^= 1;
+        CU(cudaEventSynchronize(e->ev_stage_free[sidx]));            // previous consumer of this stage is done
+        const size_t bytes = (size_t)c * fa::kRecBytes;
+        const uint8_t* src = h_recs + done * fa::kRecBytes;
+        if (!pinned) { memcpy(e->h_stage[sidx], src, bytes); src = e->h_stage[sidx]; }
+        CU(cudaMemcpyAsync(e->d_stage[sidx], src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        CU(cudaEventRecord(e->ev_copied[sidx], e->copy_stream));
+        CU(cudaStreamWaitEvent(e->stream, e->ev_copied[sidx], 0));
+        e->st.h2d_bytes += bytes;
+        uint32_t took = 0;
+        rc = ingest_chunk_accounter(e, e->d_stage[sidx], c, &took);
+        CU(cudaEventRecord(e->ev_stage_free[sidx], e->stream));
+        done += took;
+        if (rc != FA_OK) break;
+    }
+    // the caller's buffer must not be referenced after return
+    CU(cudaStreamSynchronize(e->copy_stream));
+    if (consumed) *consumed = done;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t fa_abi_version(void) { return FA_ABI_VERSION; }
+const char* fa_last_error(void) { return g_err.c_str(); }
+
+int fa_create(const fa_config* cfg, fa_engine** out) {
+    if (!cfg || !out) return fail(FA_E_INVAL, "fa_create: null argument");
+    if (cfg->abi_version != FA_ABI_VERSION) return fail(FA_E_INVAL, "fa_create: abi_version %u != %u", cfg->abi_version, FA_ABI_VERSION);
+    if (cfg->max_entries == 0) return fail(FA_E_INVAL, "fa_create: max_entries must be >= 1");
+    if (cfg->mode != FA_MODE_ACCOUNTER) return fail(FA_E_INVAL, "fa_create: mode %u not available in this build", cfg->mode);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(FA_E_NODEV, "fa_create: no CUDA device; this engine has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FA_E_INVAL, "fa_create: device %d out of range (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(FA_E_NODEV, "fa_create: device sm_%d%d is not Blackwell (sm_100a kernels only)", prop.major, prop.minor);
+
+    fa_engine* e = new (std::nothrow) fa_engine();
+    if (!e) return fail(FA_E_NOMEM, "fa_create: out of memory");
+    e->cfg = *cfg;
+    e->device = cfg->device;
+    e->sm_count = prop.multiProcessorCount;
+    e->max_batch = cfg->max_batch ? cfg->max_batch : (1ull << 22);
+    if (e->max_batch > (1ull << 28)) e->max_batch = 1ull << 28;
+    if (cfg->cuda_stream) { e->stream = (cudaStream_t)cfg->cuda_stream; }
+    else { CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+
+    // table: load factor <= 0.75 at max_entries
+    uint64_t want = cfg->max_entries + cfg->max_entries / 3 + 1;
+    uint64_t slots = 1024; while (slots < want) slots <<= 1;
+    e->slots = slots;
+    e->table.mask = slots - 1;
+    CU(cudaMalloc(&e->table.ident, slots * fa::kIdentBytes));
+    CU(cudaMalloc(&e->table.hot, slots * fa::kHotBytes));
+    CU(cudaMemsetAsync(e->table.ident, 0, slots * fa::kIdentBytes, e->stream));
+    CU(cudaMemsetAsync(e->table.hot, 0, slots * fa::kHotBytes, e->stream));
+    CU(cudaMalloc(&e->d_ctr, sizeof(fa::Counters)));
+    CU(cudaMemsetAsync(e->d_ctr, 0, sizeof(fa::Counters), e->stream));
+    CU(cudaHostAlloc(&e->h_ctr, sizeof(fa::Counters), cudaHostAllocDefault));
+    memset(e->h_ctr, 0, sizeof(fa::Counters));
+
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&e->ev_stage_free[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
+    }
+    CU(cudaMalloc(&e->d_scratch, (e->max_batch + 1) * sizeof(fa::FixupScratch)));
+    {
+        // initial state of every scratch entry: {~0, 0, 0, 0, ~0, ~0, 0, 0}
+        std::vector<fa::FixupScratch> init(4096, fa::FixupScratch{0xFFFFFFFFu, 0u, 0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u});
+        for (uint64_t off = 0; off < e->max_batch + 1; off += init.size()) {
+            const size_t k = (size_t)std::min<uint64_t>(init.size(), e->max_batch + 1 - off);
+            CU(cudaMemcpyAsync(e->d_scratch + off, init.data(), k * sizeof(fa::FixupScratch), cudaMemcpyHostToDevice, e->stream));
+        }
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    CU(cudaMalloc(&e->d_spill_idx, e->max_batch * sizeof(uint32_t)));
+    uint32_t cs = 1024; while ((uint64_t)cs < 2 * e->max_batch) cs <<= 1;
+    e->cut_set_slots = cs;
+    CU(cudaMalloc(&e->d_cut_set, (size_t)cs * 4));
+    CU(cudaMalloc(&e->d_cut_bitmap, (e->max_batch + 31) / 32 * 4 + 4));
+    CU(cudaMalloc(&e->d_cut_out, 4));
+    CU(cudaHostAlloc(&e->h_cut_out, 4, cudaHostAllocDefault));
+
+    // sketches
+    e->sk.log2w = cfg->cms_log2_width ? cfg->cms_log2_width : 20;
+    e->sk.depth = cfg->cms_depth ? cfg->cms_depth : 4;
+    e->sk.p = cfg->hll_precision ? cfg->hll_precision : 14;
+    e->sk.seed = cfg->sketch_seed;
+    if (e->sk.depth > 8 || e->sk.log2w < 4 || e->sk.log2w > 30 || e->sk.p < 4 || e->sk.p > 18) {
+        fa_destroy(e);
+        return fail(FA_E_INVAL, "fa_create: sketch parameters out of range");
+    }
+    if (cfg->flags & FA_F_ENABLE_SKETCH) {
+        const size_t cms_bytes = ((size_t)e->sk.depth << e->sk.log2w) * 8;
+        CU(cudaMalloc(&e->sk.cms, cms_bytes));
+        CU(cudaMemsetAsync(e->sk.cms, 0, cms_bytes, e->stream));
+        CU(cudaMalloc(&e->sk.hll, ((size_t)1 << e->sk.p) * 4));
+        CU(cudaMemsetAsync(e->sk.hll, 0, ((size_t)1 << e->sk.p) * 4, e->stream));
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return FA_OK;
+}
+
+void fa_destroy(fa_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+    cudaFree(e->table.ident); cudaFree(e->table.hot); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns);
+    cudaFree(e->d_ctr); if (e->h_ctr) cudaFreeHost(e->h_ctr);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(e->d_stage[i]); if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
+        if (e->ev_stage_free[i]) cudaEventDestroy(e->ev_stage_free[i]);
+        if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+    }
+    cudaFree(e->d_scratch); cudaFree(e->d_spill_idx); cudaFree(e->d_cut_set); cudaFree(e->d_cut_bitmap); cudaFree(e->d_cut_out);
+    if (e->h_cut_out) cudaFreeHost(e->h_cut_out);
+    cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts);
+    cudaFree(e->sk.cms); cudaFree(e->sk.hll);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int fa_ingest(fa_engine* e, const void* recs, size_t n, size_t* consumed) {
+    if (consumed) *consumed = 0;
+    if (!e) return fail(FA_E_INVAL, "fa_ingest: null engine");
+    if (n == 0) return FA_OK;
+    if (!recs) return fail(FA_E_INVAL, "fa_ingest: null records");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    const PtrKind k = classify(recs);
+    if (k == PTR_DEVICE) {
+        if (reinterpret_cast<uintptr_t>(recs) & 15) return fail(FA_E_INVAL, "fa_ingest: device records must be 16-byte aligned");
+        return ingest_device(e, static_cast<const uint8_t*>(recs), n, consumed);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (!e->d_stage[i]) CU(cudaMalloc(&e->d_stage[i], e->max_batch * fa::kRecBytes));
+        if (k == PTR_PAGEABLE && !e->h_stage[i]) CU(cudaHostAlloc(&e->h_stage[i], e->max_batch * fa::kRecBytes, cudaHostAllocDefault));
+    }
+    return ingest_host(e, static_cast<const uint8_t*>(recs), n, consumed, k == PTR_PINNED);
+}
+
+int fa_ingest_additional(fa_engine* e, const void*, size_t) {
+    if (!e) return fail(FA_E_INVAL, "fa_ingest_additional: null engine");
+    return fail(FA_E_INVAL, "fa_ingest_additional: engine was created without FA_F_ENABLE_RTT");
+}
+int fa_ingest_dns(fa_engine* e, const void*, size_t) {
+    if (!e) return fail(FA_E_INVAL, "fa_ingest_dns: null engine");
+    return fail(FA_E_INVAL, "fa_ingest_dns: engine was created without FA_F_ENABLE_DNS");
+}
+
+int fa_live_flows(fa_engine* e, size_t* n) {
+    if (!e || !n) return fail(FA_E_INVAL, "fa_live_flows: null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    int rc = sync_counters(e);
+    if (rc) return rc;
+    *n = (size_t)e->live_known;
+    return FA_OK;
+}
+
+int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additional, uint8_t* out_present,
+             size_t cap, size_t* n_out) {
+    if (n_out) *n_out = 0;
+    if (!e || !n_out) return fail(FA_E_INVAL, "fa_evict: null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    int rc = sync_counters(e);
+    if (rc) return rc;
+    const uint64_t live = e->live_known;
+    e->st.evictions++;
+    if (live == 0) return FA_OK;
+    if (!out_records) return fail(FA_E_INVAL, "fa_evict: null out_records");
+    if (cap < live) return fail(FA_E_2BIG, "fa_evict: capacity %zu < %llu live flows", cap, (unsigned long long)live);
+    const PtrKind k = classify(out_records);
+    uint8_t* d_out = nullptr;
+    if (k == PTR_DEVICE) {
+        d_out = static_cast<uint8_t*>(out_records);
+    } else {
+        if (e->evict_cap < live) {
+            cudaFree(e->d_evict); e->d_evict = nullptr; e->evict_cap = 0;
+            uint64_t want = std::max<uint64_t>(live, std::min<uint64_t>(e->cfg.max_entries, live * 2));
+            CU(cudaMalloc(&e->d_evict, want * fa::kRecBytes));
+            e->evict_cap = want;
+        }
+        d_out = e->d_evict;
+    }
+    CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
+    e->st.kernel_launches += fa::launch_evict(e->table, reinterpret_cast<uint4*>(d_out), nullptr, nullptr, nullptr, live,
+                                              e->d_ctr, e->sm_count, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(&e->d_ctr->live, 0, sizeof(unsigned long long), e->stream));
+    if (k != PTR_DEVICE) {
+        CU(cudaMemcpyAsync(out_records, d_out, live * fa::kRecBytes, cudaMemcpyDeviceToHost, e->stream));
+        e->st.d2h_bytes += live * fa::kRecBytes;
+    }
+    CU(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(fa::Counters), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->h_ctr->evict_out != live)
+        return fail(FA_E_CUDA, "fa_evict: table scan found %llu flows, counter says %llu", (unsigned long long)e->h_ctr->evict_out, (unsigned long long)live);
+    if (out_present) memset(out_present, 0, live);
+    (void)out_dns; (void)out_additional;
+    e->live_known = 0; e->unsynced_records = 0;
+    e->st.flows_evicted += live;
+    *n_out = (size_t)live;
+    return FA_OK;
+}
+
+int fa_purge_stale_dns(fa_engine* e, uint64_t, uint64_t) {
+    if (!e) return fail(FA_E_INVAL, "fa_purge_stale_dns: null engine");
+    return FA_OK;   // pre-computed-latency DNS contract (SURVEY.md §8 a12'): no query table to purge
+}
+
+int fa_cms_query(fa_engine* e, const void* keys, size_t n, uint64_t* est) {
+    if (!e || (!keys && n) || (!est && n)) return fail(FA_E_INVAL, "fa_cms_query: null argument");
+    if (!(e->cfg.flags & FA_F_ENABLE_SKETCH)) return fail(FA_E_INVAL, "fa_cms_query: engine was created without FA_F_ENABLE_SKETCH");
+    if (n == 0) return FA_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    uint8_t* d_keys = nullptr; unsigned long long* d_est = nullptr;
+    CU(cudaMalloc(&d_keys, n * 40 + 16));
+    CU(cudaMalloc(&d_est, n * 8));
+    CU(cudaMemcpyAsync(d_keys, keys, n * 40, cudaMemcpyDefault, e->stream));
+    e->st.kernel_launches += fa::launch_cms_query(e->sk, reinterpret_cast<const uint4*>(d_keys), (uint32_t)n, d_est, e->stream);
+    CU(cudaMemcpyAsync(est, d_est, n * 8, cudaMemcpyDefault, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(d_keys); cudaFree(d_est);
+    return FA_OK;
+}
+
+int fa_sketch_export(fa_engine* e, uint64_t* cms_out, size_t cms_words, uint8_t* hll_out, size_t hll_regs) {
+    if (!e) return fail(FA_E_INVAL, "fa_sketch_export: null engine");
+    if (!(e->cfg.flags & FA_F_ENABLE_SKETCH)) return fail(FA_E_INVAL, "fa_sketch_export: engine was created without FA_F_ENABLE_SKETCH");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    const size_t words = (size_t)e->sk.depth << e->sk.log2w, regs = (size_t)1 << e->sk.p;
+    if (cms_out) {
+        if (cms_words < words) return fail(FA_E_2BIG, "fa_sketch_export: cms buffer too small");
+        CU(cudaMemcpyAsync(cms_out, e->sk.cms, words * 8, cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (hll_out) {
+        if (hll_regs < regs) return fail(FA_E_2BIG, "fa_sketch_export: hll buffer too small");
+        uint8_t* d_regs = nullptr;
+        CU(cudaMalloc(&d_regs, regs));
+        e->st.kernel_launches += fa::launch_hll_pack(e->sk, d_regs, e->stream);
+        CU(cudaMemcpyAsync(hll_out, d_regs, regs, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        cudaFree(d_regs);
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    return FA_OK;
+}
+
+int fa_sketch_reset(fa_engine* e) {
+    if (!e) return fail(FA_E_INVAL, "fa_sketch_reset: null engine");
+    if (!(e->cfg.flags & FA_F_ENABLE_SKETCH)) return FA_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemsetAsync(e->sk.cms, 0, ((size_t)e->sk.depth << e->sk.log2w) * 8, e->stream));
+    CU(cudaMemsetAsync(e->sk.hll, 0, ((size_t)1 << e->sk.p) * 4, e->stream));
+    return FA_OK;
+}
+
+int fa_hll_estimate(fa_engine* e, double* estimate) {
+    if (!e || !estimate) return fail(FA_E_INVAL, "fa_hll_estimate: null argument");
+    const size_t m = (size_t)1 << e->sk.p;
+    std::vector<uint8_t> regs(m);
+    int rc = fa_sketch_export(e, nullptr, 0, regs.data(), m);
+    if (rc) return rc;
+    double sum = 0.0; size_t zeros = 0;
+    for (size_t i = 0; i < m; i++) { sum += std::ldexp(1.0, -(int)regs[i]); if (!regs[i]) zeros++; }
+    const double alpha = m >= 128 ? 0.7213 / (1.0 + 1.079 / (double)m) : (m == 64 ? 0.709 : (m == 32 ? 0.697 : 0.673));
+    double est = alpha * (double)m * (double)m / sum;
+    if (est <= 2.5 * (double)m && zeros) est = (double)m * std::log((double)m / (double)zeros);
+    *estimate = est;
+    return FA_OK;
+}
+
+int fa_get_stats(fa_engine* e, fa_stats* out) {
+    if (!e || !out) return fail(FA_E_INVAL, "fa_get_stats: null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    int rc = sync_counters(e);
+    if (rc) return rc;
+    e->st.live_flows = e->h_ctr->live;
+    e->st.spills = e->h_ctr->spills;
+    e->st.order_fixups = e->h_ctr->fixups_total;
+    *out = e->st;
+    return FA_OK;
+}
+
+int fa_sync(fa_engine* e) {
+    if (!e) return fail(FA_E_INVAL, "fa_sync: null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->copy_stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return FA_OK;
+}
+
+// ------------------------------------------------------------------ routing
+uint64_t fa_owner_hash(const fa_flow_id* key) {
+    uint64_t w[5];
+    memcpy(w, key, 40);
+    return fa::owner_hash(fa::key_premix(w[0], w[1], w[2], w[3], w[4]));
+}
+
+int fa_route(fa_engine* e, const void* recs, size_t n, uint32_t n_shards, void* out, uint64_t* counts_host) {
+    if (!e || !counts_host || (n && (!recs || !out))) return fail(FA_E_INVAL, "fa_route: null argument");
+    if (n_shards == 0 || n_shards > 16) return fail(FA_E_INVAL, "fa_route: n_shards must be 1..16");
+    if (n > e->max_batch) return fail(FA_E_INVAL, "fa_route: n %zu > max_batch %llu", n, (unsigned long long)e->max_batch);
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    if (!e->d_route_tmp) {
+        const size_t ctas = (e->max_batch + 2047) / 2048;
+        CU(cudaMalloc(&e->d_route_tmp, (e->max_batch + 16 * ctas + 16) * 4));
+        CU(cudaMalloc(&e->d_route_counts, 16 * 8));
+    }
+    e->st.kernel_launches += fa::launch_route(reinterpret_cast<const uint4*>(recs), (uint32_t)n, n_shards,
+                                              reinterpret_cast<uint4*>(out), e->d_route_counts, e->d_route_tmp, e->sm_count, e->stream);
+    CU(cudaGetLastError());
+    unsigned long long h[16];
+    CU(cudaMemcpyAsync(h, e->d_route_counts, n_shards * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for (uint32_t i = 0; i < n_shards; i++) counts_host[i] = h[i];
+    return FA_OK;
+}
+
+// ------------------------------------------------------------------ memory + generator
+int fa_device_alloc(fa_engine* e, size_t bytes, void** out) {
+    if (!e || !out) return fail(FA_E_INVAL, "fa_device_alloc: null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMalloc(out, bytes ? bytes : 16));
+    return FA_OK;
+}
+int fa_device_free(fa_engine* e, void* p) {
+    if (!e) return fail(FA_E_INVAL, "fa_device_free: null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaFree(p));
+    return FA_OK;
+}
+int fa_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(FA_E_INVAL, "fa_host_alloc: null argument");
+    CU(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+    return FA_OK;
+}
+int fa_host_free(void* p) { CU(cudaFreeHost(p)); return FA_OK; }
+
+static int gen_params(const fa_gen_params* p, int device, fa::GenDeviceParams* g) {
+    if (!p || p->n_keys == 0 || p->n_keys > (1ull << 32)) return fail(FA_E_INVAL, "fa_gen: n_keys must be 1..2^32");
+    g->seed = p->seed; g->n_keys = p->n_keys; g->t0_ns = p->t0_ns; g->dist = p->dist; g->varying_desc = p->varying_desc;
+    g->thresholds = nullptr; g->bucket_first = nullptr; g->bucket_size = nullptr; g->n_buckets = 0; g->reserved = 0;
+    if (p->dist == FA_GEN_ZIPF) {
+        ZipfTable* z = zipf_table(p->n_keys, p->zipf_s_milli ? p->zipf_s_milli : 1100);
+        g->n_buckets = (uint32_t)z->thresholds.size();
+        if (device < 0) {
+            g->thresholds = z->thresholds.data(); g->bucket_first = z->first.data(); g->bucket_size = z->size.data();
+        } else {
+            std::lock_guard<std::mutex> lk(g_zipf_mu);
+            if (z->device != device) {
+                if (z->d_thresholds) { cudaFree(z->d_thresholds); cudaFree(z->d_first); cudaFree(z->d_size); }
+                CU(cudaMalloc(&z->d_thresholds, z->thresholds.size() * 8));
+                CU(cudaMalloc(&z->d_first, z->first.size() * 4));
+                CU(cudaMalloc(&z->d_size, z->size.size() * 4));
+                CU(cudaMemcpy(z->d_thresholds, z->thresholds.data(), z->thresholds.size() * 8, cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(z->d_first, z->first.data(), z->first.size() * 4, cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(z->d_size, z->size.data(), z->size.size() * 4, cudaMemcpyHostToDevice));
+                z->device = device;
+            }
+            g->thresholds = z->d_thresholds; g->bucket_first = z->d_first; g->bucket_size = z->d_size;
+        }
+    }
+    return FA_OK;
+}
+
+int fa_gen_records(fa_engine* e, const fa_gen_params* p, uint64_t first_index, size_t n, void* dst) {
+    if (!dst && n) return fail(FA_E_INVAL, "fa_gen_records: null dst");
+    const PtrKind k = e ? classify(dst) : PTR_PAGEABLE;
+    fa::GenDeviceParams g;
+    if (k == PTR_DEVICE) {
+        CU(cudaSetDevice(e->device));
+        int rc = gen_params(p, e->device, &g);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> lk(e->mu);
+        size_t done = 0;
+        while (done < n) {
+            const uint32_t c = (uint32_t)std::min<size_t>(n - done, 1u << 24);
+            e->st.kernel_launches += fa::launch_generate(g, first_index + done, c, reinterpret_cast<uint4*>(static_cast<uint8_t*>(dst) + done * fa::kRecBytes), e->stream);
+            done += c;
+        }
+        CU(cudaGetLastError());
+        return FA_OK;
+    }
+    int rc = gen_params(p, -1, &g);
+    if (rc) return rc;
+    uint8_t* o = static_cast<uint8_t*>(dst);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t w[36];
+        fa::gen_record_words(g, first_index + i, w);
+        memcpy(o + i * fa::kRecBytes, w, fa::kRecBytes);
+    }
+    return FA_OK;
+}
+
+int fa_gen_key(const fa_gen_params* p, uint64_t rank, fa_flow_id* out) {
+    if (!p || !out) return fail(FA_E_INVAL, "fa_gen_key: null argument");
+    uint32_t w[10];
+    fa::gen_key_words(p->seed, rank, w);
+    memcpy(out, w, 40);
+    return FA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// kernels.cuh — launch wrappers implemented in the .cu files (internal to libflowagg.so).
+#pragma once
+#include "common.cuh"
+
+namespace fa {
+
+struct SketchParams {
+    unsigned long long* cms;   // depth x 2^log2w u64, or nullptr
+    uint32_t*           hll;   // 2^p u32 registers (value = rho), or nullptr
+    uint32_t log2w, depth, p;
+    uint64_t seed;
+};
+
+// scratch entry of the ordered re-fold (one per flow flagged TAG_DIRTY in a launch)
+struct FixupScratch {
+    uint32_t first;   // min record index of the flow in this launch          (init 0xFFFFFFFF)
+    uint32_t eth;     // 1 + max index with eth_protocol != 0                 (init 0)
+    uint32_t dscp;    // 1 + max index with dscp != 0
+    uint32_t samp;    // 1 + max index with sampling != 0
+    uint32_t smac;    // min index with src_mac != 0                          (init 0xFFFFFFFF)
+    uint32_t dmac;    // min index with dst_mac != 0
+    uint32_t slot_lo, slot_hi;
+};
+
+struct AggLaunch {
+    const uint4* recs;       // n x 144 B, 16-byte aligned, device memory
+    uint32_t     n;
+    Table        table;
+    uint64_t     epoch;
+    Counters*    ctr;
+    uint32_t*    spill_idx;  // indices of records that found the table physically full
+    SketchParams sk;
+    FixupScratch* scratch;   // capacity >= n + 1 entries, pre-initialised
+    int          sm_count;
+};
+
+// K1: fold a batch of flow records into the table (ACCOUNTER semantics) and, when any
+// flow saw records with differing order-dependent fields, re-fold those flows in stream order.
+// Returns the number of kernels launched.
+int launch_aggregate(const AggLaunch& a, cudaStream_t st);
+
+// K2: lookup-and-delete every live flow of `table` into out_recs (device pointer, cap records).
+// The number found is left in ctr->evict_out (can exceed cap; only cap are written).
+int launch_evict(const Table& table, uint4* out_recs, uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present,
+                 unsigned long long cap, Counters* ctr, int sm_count, cudaStream_t st);
+
+// Overflow pre-pass (ACCOUNTER "full" cut, reference pkg/flow/account.go:85-94): finds the index of the
+// first record whose key is new when the cache already holds max_entries flows. Result in *cut_out
+// (device; == n when the whole batch fits).  idx_set: scratch of set_slots u32 (power of two >= 2n),
+// bitmap: scratch of (n+31)/32 u32.
+int launch_full_cut(const uint4* recs, uint32_t n, const Table& table, unsigned long long live,
+                    unsigned long long max_entries, uint32_t* idx_set, uint32_t set_slots, uint32_t* bitmap,
+                    uint32_t* cut_out, int sm_count, cudaStream_t st);
+
+// sketches
+int launch_cms_query(const SketchParams& sk, const uint4* keys, uint32_t n, unsigned long long* est, cudaStream_t st);
+int launch_hll_pack(const SketchParams& sk, uint8_t* out_regs, cudaStream_t st);
+
+// generator
+struct GenDeviceParams;
+int launch_generate(const GenDeviceParams& g, uint64_t first_index, uint32_t n, uint4* dst, cudaStream_t st);
+
+// routing (K3)
+int launch_route(const uint4* recs, uint32_t n, uint32_t n_shards, uint4* out, unsigned long long* counts_dev,
+                 uint32_t* tmp_owner, int sm_count, cudaStream_t st);
+
+}  // namespace fa

@@ -1,0 +1,169 @@
+"""FlowAggEngine — thin object wrapper over the C ABI (include/flowagg.h)."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import (FA_ABI_VERSION, FA_FULL, FA_GEN_UNIFORM, FA_MODE_ACCOUNTER, REC_BYTES, Config, FlowAggError,  # noqa: F401
+                   GenParams, Stats, check, lib)
+
+
+def _ptr(x):
+    """Pointer of a numpy array / torch tensor / int address."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):          # torch tensor (host or device)
+        assert x.is_contiguous()
+        return C.c_void_p(x.data_ptr())
+    raise TypeError(type(x))
+
+
+def _nbytes(x):
+    if isinstance(x, np.ndarray):
+        return x.nbytes
+    return x.numel() * x.element_size()
+
+
+class FlowAggEngine:
+    """One engine == one GPU flow cache (the reference's aggregated_flows map + Accounter)."""
+
+    def __init__(self, max_entries, device=0, mode=FA_MODE_ACCOUNTER, flags=0, max_batch=0, cms_log2_width=0,
+                 cms_depth=0, hll_precision=0, sketch_seed=0, cuda_stream=None):
+        cfg = Config(abi_version=FA_ABI_VERSION, device=device, mode=mode, flags=flags, max_entries=max_entries,
+                     max_batch=max_batch, cms_log2_width=cms_log2_width, cms_depth=cms_depth,
+                     hll_precision=hll_precision, sketch_seed=sketch_seed, cuda_stream=cuda_stream)
+        self._h = C.c_void_p()
+        check(lib().fa_create(C.byref(cfg), C.byref(self._h)))
+        self.max_entries = max_entries
+
+    # -- ingest -----------------------------------------------------------------
+    def ingest(self, recs, n=None):
+        """Fold records (numpy host array, torch host/device tensor, or raw address with n).
+        Returns (status, consumed): status is FA_OK or FA_FULL."""
+        if n is None:
+            nb = _nbytes(recs)
+            assert nb % REC_BYTES == 0
+            n = nb // REC_BYTES
+        consumed = C.c_size_t(0)
+        rc = check(lib().fa_ingest(self._h, _ptr(recs), n, C.byref(consumed)))
+        return rc, consumed.value
+
+    def ingest_all(self, recs, on_full):
+        """Accounter loop: fold everything, calling on_full(evicted_records) at each "full" cut
+        (reference pkg/flow/account.go:85-94)."""
+        buf = np.ascontiguousarray(recs).view(np.uint8).reshape(-1)
+        n = buf.size // REC_BYTES
+        done = 0
+        while done < n:
+            rc, took = self.ingest(buf[done * REC_BYTES:])
+            done += took
+            if rc == FA_FULL:
+                on_full(self.evict())
+
+    def ingest_dns(self, recs):
+        nb = _nbytes(recs)
+        check(lib().fa_ingest_dns(self._h, _ptr(recs), nb // 104))
+
+    def ingest_additional(self, recs):
+        nb = _nbytes(recs)
+        check(lib().fa_ingest_additional(self._h, _ptr(recs), nb // 72))
+
+    # -- evict ------------------------------------------------------------------
+    def live_flows(self):
+        n = C.c_size_t(0)
+        check(lib().fa_live_flows(self._h, C.byref(n)))
+        return n.value
+
+    def evict(self, features=False):
+        """Lookup-and-delete all flows -> (n,144) uint8 array [, dns (n,64), additional (n,32), present (n,)]."""
+        n = self.live_flows()
+        cap = max(n, 1)
+        out = np.zeros((cap, REC_BYTES), dtype=np.uint8)
+        got = C.c_size_t(0)
+        if features:
+            dns = np.zeros((cap, 64), dtype=np.uint8)
+            add = np.zeros((cap, 32), dtype=np.uint8)
+            pres = np.zeros(cap, dtype=np.uint8)
+            check(lib().fa_evict(self._h, _ptr(out), _ptr(dns), _ptr(add), _ptr(pres), cap, C.byref(got)))
+            g = got.value
+            return out[:g], dns[:g], add[:g], pres[:g]
+        check(lib().fa_evict(self._h, _ptr(out), None, None, None, cap, C.byref(got)))
+        return out[: got.value]
+
+    def evict_into(self, out, cap):
+        """Evict into a caller buffer (host or device address / tensor). Returns flow count."""
+        got = C.c_size_t(0)
+        check(lib().fa_evict(self._h, _ptr(out), None, None, None, cap, C.byref(got)))
+        return got.value
+
+    # -- sketches ---------------------------------------------------------------
+    def cms_query(self, keys):
+        k = np.ascontiguousarray(keys).view(np.uint8).reshape(-1, 40)
+        est = np.zeros(len(k), dtype=np.uint64)
+        check(lib().fa_cms_query(self._h, _ptr(k), len(k), _ptr(est)))
+        return est
+
+    def hll_estimate(self):
+        d = C.c_double(0)
+        check(lib().fa_hll_estimate(self._h, C.byref(d)))
+        return d.value
+
+    def sketch_export(self, log2w, depth, p):
+        cms = np.zeros(depth << log2w, dtype=np.uint64)
+        hll = np.zeros(1 << p, dtype=np.uint8)
+        check(lib().fa_sketch_export(self._h, _ptr(cms), cms.size, _ptr(hll), hll.size))
+        return cms.reshape(depth, 1 << log2w), hll
+
+    def sketch_reset(self):
+        check(lib().fa_sketch_reset(self._h))
+
+    # -- misc -------------------------------------------------------------------
+    def stats(self):
+        s = Stats()
+        check(lib().fa_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def sync(self):
+        check(lib().fa_sync(self._h))
+
+    def route(self, recs_dev, n, n_shards, out_dev):
+        counts = np.zeros(n_shards, dtype=np.uint64)
+        check(lib().fa_route(self._h, _ptr(recs_dev), n, n_shards, _ptr(out_dev), _ptr(counts)))
+        return counts
+
+    def gen_records(self, params, first_index, n, dst):
+        check(lib().fa_gen_records(self._h, C.byref(params), first_index, n, _ptr(dst)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().fa_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gen_records_host(params, first_index, n):
+    """CPU instance of the synthetic stream generator (bit-identical to the device one)."""
+    out = np.zeros((n, REC_BYTES), dtype=np.uint8)
+    check(lib().fa_gen_records(None, C.byref(params), first_index, n, _ptr(out)))
+    return out
+
+
+def gen_key(params, rank):
+    out = np.zeros(40, dtype=np.uint8)
+    check(lib().fa_gen_key(C.byref(params), rank, _ptr(out)))
+    return out
