@@ -131,9 +131,15 @@ struct fa_engine {
 
     fa::SketchParams sk{};
 
-    // live-flow bookkeeping for the "full" rule
-    uint64_t live_known = 0;                  // exact as of the last sync
-    uint64_t unsynced_records = 0;            // records launched since then (upper bound on new flows)
+    // live-flow bookkeeping for the "full" rule: live_known is exact as of the last retired
+    // launch; unsynced_records bounds the flows that launches still in flight can add.
+    uint64_t live_known = 0;
+    uint64_t unsynced_records = 0;
+    static constexpr int kLiveRing = 8;
+    unsigned long long* h_live_ring = nullptr;   // pinned, kLiveRing entries
+    cudaEvent_t ev_live[kLiveRing] = {};
+    uint32_t ring_n[kLiveRing] = {};
+    uint32_t ring_head = 0, ring_tail = 0;       // monotonically increasing; slot = idx % kLiveRing
 
     fa_stats st{};
 };
@@ -145,7 +151,19 @@ int sync_counters(fa_engine* e) {
     CU(cudaStreamSynchronize(e->stream));
     e->live_known = e->h_ctr->live;
     e->unsynced_records = 0;
+    e->ring_head = e->ring_tail;
     return FA_OK;
+}
+
+// Retire launches whose live-count read-back has landed (never blocks).
+void retire_completed(fa_engine* e) {
+    while (e->ring_head != e->ring_tail) {
+        const uint32_t s = e->ring_head % fa_engine::kLiveRing;
+        if (cudaEventQuery(e->ev_live[s]) != cudaSuccess) { cudaGetLastError(); break; }
+        e->live_known = e->h_live_ring[s];
+        e->unsynced_records -= e->ring_n[s];
+        e->ring_head++;
+    }
 }
 
 // Launch K1 on a device-resident chunk (n <= max_batch).
@@ -164,6 +182,16 @@ int launch_chunk(fa_engine* e, const uint8_t* d_recs, uint32_t n) {
     CU(cudaGetLastError());
     e->unsynced_records += n;
     e->st.records_ingested += n;
+    // asynchronous read-back of the live-flow count after this launch
+    if (e->ring_tail - e->ring_head == fa_engine::kLiveRing) {
+        CU(cudaEventSynchronize(e->ev_live[e->ring_head % fa_engine::kLiveRing]));
+        retire_completed(e);
+    }
+    const uint32_t s = e->ring_tail % fa_engine::kLiveRing;
+    CU(cudaMemcpyAsync(&e->h_live_ring[s], &e->d_ctr->live, 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaEventRecord(e->ev_live[s], e->stream));
+    e->ring_n[s] = n;
+    e->ring_tail++;
     return FA_OK;
 }
 
@@ -172,6 +200,7 @@ int launch_chunk(fa_engine* e, const uint8_t* d_recs, uint32_t n) {
 int ingest_chunk_accounter(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint32_t* consumed) {
     *consumed = 0;
     const uint64_t M = e->cfg.max_entries;
+    retire_completed(e);
     if (e->live_known + e->unsynced_records + n > M) {
         int rc = sync_counters(e);                     // exact live count
         if (rc) return rc;
@@ -287,6 +316,8 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     CU(cudaMemsetAsync(e->d_ctr, 0, sizeof(fa::Counters), e->stream));
     CU(cudaHostAlloc(&e->h_ctr, sizeof(fa::Counters), cudaHostAllocDefault));
     memset(e->h_ctr, 0, sizeof(fa::Counters));
+    CU(cudaHostAlloc(&e->h_live_ring, fa_engine::kLiveRing * 8, cudaHostAllocDefault));
+    for (int i = 0; i < fa_engine::kLiveRing; i++) CU(cudaEventCreateWithFlags(&e->ev_live[i], cudaEventDisableTiming));
 
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&e->ev_stage_free[i], cudaEventDisableTiming));
@@ -338,6 +369,8 @@ void fa_destroy(fa_engine* e) {
     if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
     cudaFree(e->table.ident); cudaFree(e->table.hot); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns);
     cudaFree(e->d_ctr); if (e->h_ctr) cudaFreeHost(e->h_ctr);
+    if (e->h_live_ring) cudaFreeHost(e->h_live_ring);
+    for (int i = 0; i < fa_engine::kLiveRing; i++) if (e->ev_live[i]) cudaEventDestroy(e->ev_live[i]);
     for (int i = 0; i < 2; i++) {
         cudaFree(e->d_stage[i]); if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
         if (e->ev_stage_free[i]) cudaEventDestroy(e->ev_stage_free[i]);
@@ -430,7 +463,7 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
         return fail(FA_E_CUDA, "fa_evict: table scan found %llu flows, counter says %llu", (unsigned long long)e->h_ctr->evict_out, (unsigned long long)live);
     if (out_present) memset(out_present, 0, live);
     (void)out_dns; (void)out_additional;
-    e->live_known = 0; e->unsynced_records = 0;
+    e->live_known = 0; e->unsynced_records = 0; e->ring_head = e->ring_tail;
     e->st.flows_evicted += live;
     *n_out = (size_t)live;
     return FA_OK;
