@@ -22,32 +22,105 @@
 namespace fa {
 
 constexpr int kTile      = 256;                 // records per tile == threads per CTA
-constexpr int kStages    = 2;
 constexpr int kTileChunks = kTile * kRecChunks; // uint4 per tile
 constexpr int kRepSlots  = 512;
 constexpr uint32_t kRepEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kResSpill = 0xFFFFFFFFu;
 constexpr uint32_t kProbeLimit = 8192;
+constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
 
+// 49.7 KB per CTA -> 4 CTAs (32 warps) per SM.
 struct __align__(128) AggSmem {
-    uint4    tile[kStages][kTileChunks];          // 73,728 B
-    uint4    acc[kTile * 2];                      //  8,192 B  hot-line layout per record slot
-    unsigned long long hs[kTile];                 //  2,048 B  slot hash of each record
-    uint32_t rep[2][kRepSlots];                   //  4,096 B
+    uint4    tile[kTileChunks];                   // 36,864 B  one TMA-staged tile of records
+    uint32_t acc[kTile][8];                       //  8,192 B  what duplicates add to their representative
+    uint32_t hs[kTile];                           //  1,024 B  low 32 bits of the slot hash
+    uint32_t res[kTile];                          //  1,024 B  table slot found for each representative
+    uint32_t rep[kRepSlots];                      //  2,048 B  tile-local key -> representative index
     uint8_t  tdirty[kTile];                       //    256 B
-    unsigned long long full_bar[kStages];
+    uint8_t  list[kTile / 32][32];                //    256 B  per-warp compacted representatives
+    uint8_t  slow[kTile / 32][32];                //    256 B  per-warp flows that need the general probe loop
+    unsigned long long full_bar;
     uint32_t n_insert, n_spill, any_dirty, pad;
 };
 
-__device__ __forceinline__ void issue_tile_load(AggSmem& s, int stage, const uint4* recs, uint32_t n, uint32_t tile_idx) {
+__device__ __forceinline__ void issue_tile_load(AggSmem& s, const uint4* recs, uint32_t n, uint32_t tile_idx) {
     const uint32_t first = tile_idx * kTile;
     const uint32_t cnt = min((uint32_t)kTile, n - first);
     const uint32_t bytes = cnt * kRecBytes;
-    mbar_expect_tx(&s.full_bar[stage], bytes);
-    tma_load_1d(&s.tile[stage][0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar[stage]);
+    mbar_expect_tx(&s.full_bar, bytes);
+    tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
+}
+
+// General probe of one flow per 8-lane group (4 flows per call): claims empty slots, waits for
+// slots being published, walks collisions, marks descriptor mismatches.  Returns the slot
+// (kResSpill when the table is physically full) in every lane of the group.
+__device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch, bool active, uint32_t start_slot,
+                                                  uint4 rchunk, bool cta_dirty, int g, int j, uint4 cmask,
+                                                  uint32_t& my_inserts, uint32_t* any_dirty) {
+    uint64_t slot = start_slot;
+    bool done = !active;
+    uint32_t nprobe = 0, result = kResSpill;
+    uint64_t reload_slot = ~0ull;
+    for (;;) {
+        uint4 line = make_uint4(0, 0, 0, 0);
+        if (!done) line = ld_cg_u4(&t.ident[slot * 8 + j]);
+        const uint32_t tag_lo = __shfl_sync(0xFFFFFFFFu, line.z, g * 8 + 2);
+        const uint32_t tag_hi = __shfl_sync(0xFFFFFFFFu, line.w, g * 8 + 2);
+        const uint64_t tag = u64_of(tag_lo, tag_hi);
+        const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq4_masked(line, rchunk, cmask)) >> (g * 8)) & 0xFFu;
+        const uint32_t state = (uint32_t)(tag & TAG_STATE_MASK);
+        unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[slot * 8 + 2]) + 1;
+        uint32_t won = 0;
+        if (!done && state == 0 && j == 2) {
+            const unsigned long long want = (epoch << TAG_EPOCH_SHIFT) | TAG_HAS_BASE | TAG_CLAIMED;
+            won = atomicCAS(tagp, 0ull, want) == 0ull ? 1u : 0u;
+        }
+        won = __shfl_sync(0xFFFFFFFFu, won, g * 8 + 2);
+        if (won) {
+            const uint4 v = and4(rchunk, cmask);
+            if (j == 2) *reinterpret_cast<uint2*>(&t.ident[slot * 8 + 2]) = make_uint2(v.x, v.y);   // key tail only
+            else st_cg_u4(&t.ident[slot * 8 + j], v);           // j==3: word0 (aux) = 0, word1 = eth
+            __threadfence();
+        }
+        __syncwarp();
+        bool hit = false;
+        if (won) {
+            if (j == 2) {
+                const unsigned long long pub = (epoch << TAG_EPOCH_SHIFT) | TAG_HAS_BASE | TAG_PUBLISHED |
+                                               (cta_dirty ? TAG_DIRTY : 0ull);
+                *reinterpret_cast<volatile unsigned long long*>(tagp) = pub;
+                my_inserts++;
+                if (cta_dirty) *any_dirty = 1;
+            }
+            hit = true;
+        } else if (!done && state == (uint32_t)TAG_PUBLISHED) {
+            const bool born_now = (tag >> TAG_EPOCH_SHIFT) == epoch;
+            if (born_now && reload_slot != slot) {
+                // published during this launch: the chunks read together with the tag may predate
+                // it.  Re-read the line once, ordered after the tag observation.
+                reload_slot = slot;
+                __threadfence();
+            } else if ((eqb & 0x07u) == 0x07u) {
+                hit = true;
+                const bool desc_eq = (eqb & 0xF8u) == 0xF8u;
+                if ((!desc_eq || cta_dirty) && j == 2) {
+                    if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                    *any_dirty = 1;
+                }
+            } else {
+                slot = (slot + 1) & t.mask;
+                if (++nprobe > kProbeLimit) done = true;         // physically full: result stays kResSpill
+            }
+        }
+        // CLAIMED by someone else, or lost the CAS: retry the same slot next iteration
+        if (hit) { result = (uint32_t)slot; done = true; }
+        if (__all_sync(0xFFFFFFFFu, done)) break;
+    }
+    return result;
 }
 
 template <bool kSketch>
-__global__ void __launch_bounds__(kTile, 2)
+__global__ void __launch_bounds__(kTile, 4)
 aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
                  uint32_t* __restrict__ spill_idx, SketchParams sk) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -56,211 +129,194 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     const uint32_t n_tiles = (n + kTile - 1) / kTile;
 
     if (tid == 0) {
-        for (int i = 0; i < kStages; i++) mbar_init(&s.full_bar[i], 1);
+        mbar_init(&s.full_bar, 1);
         fence_barrier_init();
         s.n_insert = 0; s.n_spill = 0; s.any_dirty = 0;
     }
-    s.rep[0][tid] = kRepEmpty; s.rep[0][tid + kTile] = kRepEmpty;
-    s.rep[1][tid] = kRepEmpty; s.rep[1][tid + kTile] = kRepEmpty;
+    s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;
+    *reinterpret_cast<uint4*>(&s.acc[tid][0]) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(&s.acc[tid][4]) = make_uint4(0, 0, 0, 0);
+    s.tdirty[tid] = 0;
     __syncthreads();
-    if (tid == 0) {
-        for (int i = 0; i < kStages; i++) {
-            uint32_t ti = blockIdx.x + i * gridDim.x;
-            if (ti < n_tiles) issue_tile_load(s, i, recs, n, ti);
-        }
-    }
+    if (tid == 0 && blockIdx.x < n_tiles) issue_tile_load(s, recs, n, blockIdx.x);
 
     const int g = lane >> 3;                  // flow group inside the warp (4 groups of 8 lanes)
     const int j = lane & 7;                   // 16-byte chunk of the identity line handled by this lane
     const uint4 cmask = chunk_mask(j);
     const int rc = rec_chunk_of_line_chunk(j);
+    const uint32_t tmask = (uint32_t)t.mask;
     uint32_t my_inserts = 0, my_spills = 0;
+    const uint4* T = s.tile;
 
     for (uint32_t it = 0;; ++it) {
         const uint32_t tile_idx = blockIdx.x + it * gridDim.x;
         if (tile_idx >= n_tiles) break;
-        const int stage = it % kStages;
-        const uint32_t parity = (it / kStages) & 1u;
         const uint32_t first = tile_idx * kTile;
         const uint32_t cnt = min((uint32_t)kTile, n - first);
-        mbar_wait(&s.full_bar[stage], parity);
-        const uint4* T = s.tile[stage];
-        uint32_t* rep = s.rep[it & 1];
-        uint32_t* rep_next = s.rep[(it & 1) ^ 1];
+        mbar_wait(&s.full_bar, it & 1u);
 
-        // ---------------------------------------------------------- P1: hash + elect
+        // ------------------------------------------------------ E: hash, elect, fold duplicates
         const bool valid = (uint32_t)tid < cnt;
-        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0, r4 = r0;
-        uint64_t h = 0, premix = 0;
-        int my_rep = tid;
-        s.acc[tid * 2] = make_uint4(0, 0, 0, 0);
-        s.acc[tid * 2 + 1] = make_uint4(0, 0, 0, 0);
-        s.tdirty[tid] = 0;
+        uint4 r2 = make_uint4(0, 0, 0, 0), r3 = r2, r4 = r2;
+        uint64_t premix = 0;
+        bool is_rep = valid;
         if (valid) {
             const uint4* R = T + tid * kRecChunks;
-            r0 = R[0]; r1 = R[1]; r2 = R[2]; r3 = R[3]; r4 = R[4];
+            const uint4 r0 = R[0], r1 = R[1];
+            r2 = R[2]; r3 = R[3]; r4 = R[4];
             premix = key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y), u64_of(r1.z, r1.w),
                                 u64_of(r2.x, r2.y));
-            h = slot_hash(premix);
-            s.hs[tid] = h;
+            const uint64_t h = slot_hash(premix);
+            s.hs[tid] = (uint32_t)h;
+            const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+            const uint64_t v_ns = 0ull - v_start;
             uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
-            const uint4 m2 = chunk_mask(2);
             for (;;) {
-                uint32_t old = atomicCAS(&rep[rs], kRepEmpty, (uint32_t)tid);
+                const uint32_t old = atomicCAS(&s.rep[rs], kRepEmpty, (uint32_t)tid);
                 if (old == kRepEmpty) break;
                 const uint4* O = T + old * kRecChunks;
-                uint4 o0 = O[0], o1 = O[1], o2 = O[2];
-                if (eq4_masked(o0, r0, chunk_mask(0)) && eq4_masked(o1, r1, chunk_mask(1)) && eq4_masked(o2, r2, m2)) {
-                    my_rep = (int)old;
+                const uint4 o2 = O[2];
+                if (eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
+                    eq4_masked(O[1], r1, chunk_mask(1))) {
+                    // Same key.  Fold into that representative with 32-bit shared atomics when the high
+                    // words of the timestamps agree (the common case); otherwise go to the table on our own.
+                    const uint4 o3 = O[3];
+                    const uint64_t o_ns = 0ull - u64_of(o2.z, o2.w), o_end = u64_of(o3.x, o3.y);
+                    const bool ok = (v_start == 0 || (uint32_t)(v_ns >> 32) == (uint32_t)(o_ns >> 32)) &&
+                                    (v_end == 0 || (uint32_t)(v_end >> 32) == (uint32_t)(o_end >> 32));
+                    if (ok) {
+                        is_rep = false;
+                        uint32_t* A = s.acc[old];
+                        const uint32_t b_lo = r3.z, b_hi = r3.w;
+                        const uint32_t prev = atomicAdd(&A[0], b_lo);
+                        const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
+                        if (hi_add) atomicAdd(&A[1], hi_add);
+                        atomicAdd(&A[2], r4.x);
+                        const uint32_t fl = r4.y >> 16;
+                        if (fl) atomicOr(&A[3], fl);
+                        if (v_start) atomicMax(&A[4], (uint32_t)v_ns);
+                        if (v_end) atomicMax(&A[5], (uint32_t)v_end);
+                        // exact descriptor compare against the representative (74 bytes, padding masked)
+                        bool same = eq4_masked(O[4], r4, chunk_mask(3));
+#pragma unroll
+                        for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
+                        if (!same) s.tdirty[old] = 1;
+                    }
                     break;
                 }
                 rs = (rs + 1) & (kRepSlots - 1);
             }
         }
-        __syncthreads();
+        __syncthreads();                                           // S1: all folds of this tile are in acc[]
 
-        // ---------------------------------------------------------- P2: fold duplicates into their representative
-        const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y), v_bytes = u64_of(r3.z, r3.w);
-        const uint32_t v_packets = r4.x, v_flags = r4.y >> 16;
-        if (valid && my_rep != tid) {
-            unsigned long long* A = reinterpret_cast<unsigned long long*>(&s.acc[my_rep * 2]);
-            atomicAdd(&A[0], (unsigned long long)v_bytes);
-            if (v_start) atomicMax(&A[1], (unsigned long long)(0ull - v_start));
-            if (v_end) atomicMax(&A[2], (unsigned long long)v_end);
-            uint32_t* A32 = reinterpret_cast<uint32_t*>(&A[3]);
-            atomicAdd(&A32[0], v_packets);
-            if (v_flags) atomicOr(&A32[1], v_flags);
-            // exact descriptor compare against the representative (74 bytes, padding masked)
-            const uint4* R = T + tid * kRecChunks;
-            const uint4* O = T + my_rep * kRecChunks;
-            bool same = eq4_masked(O[4], r4, chunk_mask(3));
-#pragma unroll
-            for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
-            if (!same) s.tdirty[my_rep] = 1;
-        }
-        rep_next[tid] = kRepEmpty; rep_next[tid + kTile] = kRepEmpty;
-        __syncthreads();
-
-        // ---------------------------------------------------------- P3: representatives -> global table
-        const bool is_rep = valid && my_rep == tid;
+        // ------------------------------------------------------ representatives: totals in registers
+        uint64_t t_bytes = 0, t_ns = 0, t_end = 0;
+        uint32_t t_packets = 0, t_flags = 0;
         if (is_rep) {
-            unsigned long long* A = reinterpret_cast<unsigned long long*>(&s.acc[tid * 2]);
-            uint32_t* A32 = reinterpret_cast<uint32_t*>(&A[3]);
-            A[0] += v_bytes;
-            unsigned long long ns = 0ull - v_start;           // 0 stays 0 ("unset")
-            if (ns > A[1]) A[1] = ns;
-            if (v_end > A[2]) A[2] = v_end;
-            A32[0] += v_packets;
-            A32[1] |= v_flags;
+            const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[tid][0]);
+            const uint2 a1 = *reinterpret_cast<const uint2*>(&s.acc[tid][4]);
+            const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+            const uint64_t v_ns = 0ull - v_start;
+            t_bytes = u64_of(r3.z, r3.w) + u64_of(a0.x, a0.y);
+            t_packets = r4.x + a0.z;
+            t_flags = (r4.y >> 16) | a0.w;
+            const uint64_t c_ns = u64_of(a1.x, (uint32_t)(v_ns >> 32)), c_end = u64_of(a1.y, (uint32_t)(v_end >> 32));
+            t_ns = c_ns > v_ns ? c_ns : v_ns;
+            t_end = c_end > v_end ? c_end : v_end;
+            *reinterpret_cast<uint4*>(&s.acc[tid][0]) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint2*>(&s.acc[tid][4]) = make_uint2(0, 0);
             if (kSketch) {
-                const uint32_t pk = A32[0];
                 const uint64_t a = cms_hash_a(premix, sk.seed), b = cms_hash_b(premix, sk.seed);
                 for (uint32_t d = 0; d < sk.depth; d++)
-                    red_add_u64(sk.cms + ((size_t)d << sk.log2w) + cms_index(a, b, d, sk.log2w), pk);
+                    red_add_u64(sk.cms + ((size_t)d << sk.log2w) + cms_index(a, b, d, sk.log2w), t_packets);
                 const uint64_t hh = hll_hash(premix, sk.seed);
                 const uint32_t idx = (uint32_t)(hh >> (64 - sk.p));
                 const uint64_t rest = hh << sk.p;
-                uint32_t rho = rest ? (uint32_t)__clzll((long long)rest) + 1u : (64u - sk.p) + 1u;
+                const uint32_t rho = rest ? (uint32_t)__clzll((long long)rest) + 1u : (64u - sk.p) + 1u;
                 if (__ldcg(&sk.hll[idx]) < rho) red_max_u32(&sk.hll[idx], rho);
             }
         }
+        s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;   // nobody reads the election table after S1
+
+        // ------------------------------------------------------ per-warp list of representatives
+        const uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_rep);
+        const uint32_t nreps = __popc(pending);
+        if (is_rep) s.list[warp][__popc(pending & ((1u << lane) - 1u))] = (uint8_t)lane;
         __syncwarp();
 
-        uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_rep);
-        while (pending) {
-            const uint32_t src = __fns(pending, 0, g + 1);       // g-th pending representative of this warp
-            const bool active = src < 32u;
+        // ------------------------------------------------------ cooperative probe: 8 lanes per flow
+        uint32_t nslow = 0;
+        for (uint32_t base = 0; base < nreps; base += 4 * kInflight) {
+            uint4 line[kInflight];
+            uint32_t ridx[kInflight];
+            uint32_t slot[kInflight];
 #pragma unroll
-            for (int k = 0; k < 4; k++) pending &= pending - 1;   // (x & (x-1)) of 0 is 0
-            const int ridx = warp * 32 + (active ? (int)src : 0);  // record slot inside the tile
-            const uint4 rchunk = T[ridx * kRecChunks + rc];
-            const uint64_t hh = s.hs[ridx];
-            const bool cta_dirty = s.tdirty[ridx] != 0;
-            uint64_t slot = hh & t.mask;
-            bool done = !active;
-            uint32_t nprobe = 0;
-            uint64_t reload_slot = ~0ull;
-            for (;;) {
-                uint4 line = make_uint4(0, 0, 0, 0);
-                if (!done) line = ld_cg_u4(&t.ident[slot * 8 + j]);
-                const uint32_t tag_lo = __shfl_sync(0xFFFFFFFFu, line.z, g * 8 + 2);
-                const uint32_t tag_hi = __shfl_sync(0xFFFFFFFFu, line.w, g * 8 + 2);
+            for (int r = 0; r < kInflight; r++) {                  // issue: up to 16 identity lines in flight per warp
+                const uint32_t k = base + r * 4 + g;
+                const bool act = k < nreps;
+                ridx[r] = warp * 32 + (act ? s.list[warp][k] : 0);
+                slot[r] = s.hs[ridx[r]] & tmask;
+                line[r] = make_uint4(0, 0, 0, 0);
+                if (act) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
+            }
+#pragma unroll
+            for (int r = 0; r < kInflight; r++) {                  // resolve: first-probe hits on settled flows
+                const uint32_t k = base + r * 4 + g;
+                const bool act = k < nreps;
+                const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
+                const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq4_masked(line[r], rchunk, cmask)) >> (g * 8)) & 0xFFu;
+                const uint32_t tag_lo = __shfl_sync(0xFFFFFFFFu, line[r].z, g * 8 + 2);
+                const uint32_t tag_hi = __shfl_sync(0xFFFFFFFFu, line[r].w, g * 8 + 2);
                 const uint64_t tag = u64_of(tag_lo, tag_hi);
-                const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq4_masked(line, rchunk, cmask)) >> (g * 8)) & 0xFFu;
-                const uint32_t state = (uint32_t)(tag & TAG_STATE_MASK);
-                unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[slot * 8 + 2]) + 1;
-
-                // ---- claim an empty slot
-                uint32_t won = 0;
-                if (!done && state == 0 && j == 2) {
-                    const unsigned long long want = (epoch << TAG_EPOCH_SHIFT) | TAG_HAS_BASE | TAG_CLAIMED;
-                    won = atomicCAS(tagp, 0ull, want) == 0ull ? 1u : 0u;
-                }
-                won = __shfl_sync(0xFFFFFFFFu, won, g * 8 + 2);
-                if (won) {
-                    uint4 v = and4(rchunk, cmask);
-                    if (j == 2) {
-                        *reinterpret_cast<uint2*>(&t.ident[slot * 8 + 2]) = make_uint2(v.x, v.y);   // key tail only
-                    } else {
-                        st_cg_u4(&t.ident[slot * 8 + j], v);     // j==3: word0 (aux) = 0, word1 = eth
-                    }
-                    __threadfence();
-                }
-                __syncwarp();
-                bool hit = false;
-                if (won) {
-                    if (j == 2) {
-                        const unsigned long long pub = (epoch << TAG_EPOCH_SHIFT) | TAG_HAS_BASE | TAG_PUBLISHED |
-                                                       (cta_dirty ? TAG_DIRTY : 0ull);
-                        *reinterpret_cast<volatile unsigned long long*>(tagp) = pub;
-                        my_inserts++;
-                        if (cta_dirty) s.any_dirty = 1;
-                    }
-                    hit = true;
-                } else if (!done && state == (uint32_t)TAG_PUBLISHED) {
-                    const bool born_now = (tag >> TAG_EPOCH_SHIFT) == epoch;
-                    if (born_now && reload_slot != slot) {
-                        // published during this launch: the chunks read together with the tag may
-                        // predate it. Re-read the line once, ordered after the tag observation.
-                        reload_slot = slot;
-                        __threadfence();
-                    } else if ((eqb & 0x07u) == 0x07u) {
-                        hit = true;
-                        const bool desc_eq = (eqb & 0xF8u) == 0xF8u;
-                        if ((!desc_eq || cta_dirty) && j == 2) {
-                            if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
-                            s.any_dirty = 1;
-                        }
-                    } else {
-                        slot = (slot + 1) & t.mask;
-                        if (++nprobe > kProbeLimit) {           // table physically full: spill, never drop silently
-                            done = true;
-                            if (j == 0) {
-                                unsigned long long k = atomicAdd(&ctr->scratch[2], 1ull);   // per-launch cursor
-                                spill_idx[k] = first + (uint32_t)ridx;
-                                my_spills++;
-                            }
-                        }
+                const bool settled = (tag & TAG_STATE_MASK) == TAG_PUBLISHED && (tag >> TAG_EPOCH_SHIFT) != epoch;
+                const bool fast = act && settled && (eqb & 0x07u) == 0x07u;
+                if (fast && j == 0) s.res[ridx[r]] = slot[r];
+                if (fast && j == 2) {
+                    const bool cta_dirty = s.tdirty[ridx[r]] != 0;
+                    if ((eqb & 0xF8u) != 0xF8u || cta_dirty) {
+                        unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
+                        if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                        s.any_dirty = 1;
                     }
                 }
-                // state CLAIMED by someone else, or lost the CAS: retry the same slot next iteration
-                if (hit) {
-                    uint8_t* hot = reinterpret_cast<uint8_t*>(t.hot) + slot * kHotBytes;
-                    const unsigned long long* A = reinterpret_cast<const unsigned long long*>(&s.acc[ridx * 2]);
-                    if (j == 0) red_add_u64(hot, A[0]);
-                    else if (j == 1) { if (A[1]) red_max_u64(hot + 8, A[1]); }
-                    else if (j == 2) { if (A[2]) red_max_u64(hot + 16, A[2]); }
-                    else if (j == 3) red_add_u32(hot + 24, (uint32_t)A[3]);
-                    else if (j == 4) { uint32_t f = (uint32_t)(A[3] >> 32); if (f) red_or_u32(hot + 28, f); }
-                    done = true;
-                }
-                if (__all_sync(0xFFFFFFFFu, done)) break;
+                const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, act && !fast && j == 0);
+                if (act && !fast && j == 0) s.slow[warp][nslow + __popc(slowb & ((1u << lane) - 1u))] = (uint8_t)(ridx[r] & 31u);
+                nslow += __popc(slowb);
             }
         }
-        __syncthreads();                         // everyone is done with this stage
+        __syncwarp();
+        for (uint32_t base = 0; base < nslow; base += 4) {         // inserts, collisions, in-flight publishes
+            const uint32_t k = base + g;
+            const bool act = k < nslow;
+            const uint32_t ri = warp * 32 + (act ? s.slow[warp][k] : 0);
+            const uint4 rchunk = T[ri * kRecChunks + rc];
+            const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0, g, j, cmask,
+                                               my_inserts, &s.any_dirty);
+            if (act && j == 0) s.res[ri] = got;
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------ one lane per flow: fire-and-forget reductions
+        if (is_rep) {
+            const uint32_t slot = s.res[tid];
+            s.tdirty[tid] = 0;
+            if (slot != kResSpill) {
+                uint8_t* hot = reinterpret_cast<uint8_t*>(t.hot) + (size_t)slot * kHotBytes;
+                red_add_u64(hot, t_bytes);
+                if (t_ns) red_max_u64(hot + 8, t_ns);
+                if (t_end) red_max_u64(hot + 16, t_end);
+                red_add_u32(hot + 24, t_packets);
+                if (t_flags) red_or_u32(hot + 28, t_flags);
+            } else {                                               // table physically full: spill, never drop silently
+                const unsigned long long kk = atomicAdd(&ctr->scratch[2], 1ull);
+                spill_idx[kk] = first + (uint32_t)tid;
+                my_spills++;
+            }
+        }
+        __syncthreads();                                           // S2: the tile buffer is free again
         if (tid == 0) {
-            const uint32_t nt = tile_idx + kStages * gridDim.x;
-            if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, stage, recs, n, nt); }
+            const uint32_t nt = tile_idx + gridDim.x;
+            if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, recs, n, nt); }
         }
     }
 
@@ -388,7 +444,7 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
         attr_done = true;
     }
     const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
-    const int grid = (int)min((uint32_t)(a.sm_count * 2), n_tiles);
+    const int grid = (int)min((uint32_t)(a.sm_count * 4), n_tiles);
     if (a.sk.cms) aggregate_kernel<true><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk);
     else aggregate_kernel<false><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk);
     const int fgrid = a.sm_count * 2;
