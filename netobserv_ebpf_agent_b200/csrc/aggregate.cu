@@ -21,29 +21,31 @@
 
 namespace fa {
 
-constexpr int kTile      = 256;                 // records per tile == threads per CTA
-constexpr int kTileChunks = kTile * kRecChunks; // uint4 per tile
-constexpr int kRepSlots  = 512;
 constexpr uint32_t kRepEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kResSpill = 0xFFFFFFFFu;
 constexpr uint32_t kProbeLimit = 8192;
-constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
 
-// 49.7 KB per CTA -> 4 CTAs (32 warps) per SM.
+// kTile = records per tile = threads per CTA.  kTile 256: ~52 KB per CTA -> 4 CTAs (32 warps) per SM.
+template <int kTile>
 struct __align__(128) AggSmem {
-    uint4    tile[kTileChunks];                   // 36,864 B  one TMA-staged tile of records
+    static constexpr int kRepSlots = 2 * kTile;
+    uint4    tile[kTile * kRecChunks];            // 36,864 B  one TMA-staged tile of records
     uint32_t acc[kTile][8];                       //  8,192 B  what duplicates add to their representative
     uint32_t hs[kTile];                           //  1,024 B  low 32 bits of the slot hash
     uint32_t res[kTile];                          //  1,024 B  table slot found for each representative
     uint32_t rep[kRepSlots];                      //  2,048 B  tile-local key -> representative index
-    uint8_t  tdirty[kTile];                       //    256 B
-    uint8_t  list[kTile / 32][32];                //    256 B  per-warp compacted representatives
+    uint32_t mir_lo[kTile];                       //  1,024 B  start mirror of the flow found (see common.cuh)
+    uint16_t mir_hi[kTile];                       //    512 B
+    uint16_t fseen[kTile];                        //    512 B  tcp flags already present in the flow's hot line
+    uint8_t  tdirty[kTile];                       //    256 B  set by duplicates whose descriptor differs
+    uint8_t  glist[kTile];                        //    256 B  CTA-wide compacted list of representatives
     uint8_t  slow[kTile / 32][32];                //    256 B  per-warp flows that need the general probe loop
     unsigned long long full_bar;
-    uint32_t n_insert, n_spill, any_dirty, pad;
+    uint32_t n_insert, n_spill, any_dirty, nrep;
 };
 
-__device__ __forceinline__ void issue_tile_load(AggSmem& s, const uint4* recs, uint32_t n, uint32_t tile_idx) {
+template <int kTile>
+__device__ __forceinline__ void issue_tile_load(AggSmem<kTile>& s, const uint4* recs, uint32_t n, uint32_t tile_idx) {
     const uint32_t first = tile_idx * kTile;
     const uint32_t cnt = min((uint32_t)kTile, n - first);
     const uint32_t bytes = cnt * kRecBytes;
@@ -55,7 +57,7 @@ __device__ __forceinline__ void issue_tile_load(AggSmem& s, const uint4* recs, u
 // slots being published, walks collisions, marks descriptor mismatches.  Returns the slot
 // (kResSpill when the table is physically full) in every lane of the group.
 __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch, bool active, uint32_t start_slot,
-                                                  uint4 rchunk, bool cta_dirty, int g, int j, uint4 cmask,
+                                                  uint4 rchunk, bool cta_dirty, uint64_t ins_ns, int g, int j, uint4 cmask,
                                                   uint32_t& my_inserts, uint32_t* any_dirty) {
     uint64_t slot = start_slot;
     bool done = !active;
@@ -77,9 +79,13 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
         }
         won = __shfl_sync(0xFFFFFFFFu, won, g * 8 + 2);
         if (won) {
-            const uint4 v = and4(rchunk, cmask);
+            uint4 v = and4(rchunk, cmask);
+            if (j == 3) {                                       // start mirror around eth_protocol
+                const uint64_t m48 = ins_ns >> 16;
+                v.x = (uint32_t)m48; v.y |= (uint32_t)(m48 >> 32) << 16;
+            }
             if (j == 2) *reinterpret_cast<uint2*>(&t.ident[slot * 8 + 2]) = make_uint2(v.x, v.y);   // key tail only
-            else st_cg_u4(&t.ident[slot * 8 + j], v);           // j==3: word0 (aux) = 0, word1 = eth
+            else st_cg_u4(&t.ident[slot * 8 + j], v);
             __threadfence();
         }
         __syncwarp();
@@ -119,19 +125,24 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
     return result;
 }
 
-template <bool kSketch>
-__global__ void __launch_bounds__(kTile, 4)
+// kProf: per-warp cycle counters per phase (FA_PHASE_PROFILE=1), summed into prof[0..7].
+#define FA_PROF_MARK(i) do { if (kProf) { const long long now_ = clock64(); pacc[i] += now_ - pt; pt = now_; } } while (0)
+
+template <int kTile, int kInflight, int kMinBlocks, bool kSketch, bool kProf>
+__global__ void __launch_bounds__(kTile, kMinBlocks)
 aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
-                 uint32_t* __restrict__ spill_idx, SketchParams sk) {
+                 uint32_t* __restrict__ spill_idx, SketchParams sk, unsigned long long* prof, uint32_t opt) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    AggSmem& s = *reinterpret_cast<AggSmem*>(smem_raw);
+    using Smem = AggSmem<kTile>;
+    constexpr int kRepSlots = Smem::kRepSlots;
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_tiles = (n + kTile - 1) / kTile;
 
     if (tid == 0) {
         mbar_init(&s.full_bar, 1);
         fence_barrier_init();
-        s.n_insert = 0; s.n_spill = 0; s.any_dirty = 0;
+        s.n_insert = 0; s.n_spill = 0; s.any_dirty = 0; s.nrep = 0;
     }
     s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;
     *reinterpret_cast<uint4*>(&s.acc[tid][0]) = make_uint4(0, 0, 0, 0);
@@ -145,8 +156,11 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     const uint4 cmask = chunk_mask(j);
     const int rc = rec_chunk_of_line_chunk(j);
     const uint32_t tmask = (uint32_t)t.mask;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t my_inserts = 0, my_spills = 0;
     const uint4* T = s.tile;
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pt = kProf ? clock64() : 0;
 
     for (uint32_t it = 0;; ++it) {
         const uint32_t tile_idx = blockIdx.x + it * gridDim.x;
@@ -154,67 +168,153 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         const uint32_t first = tile_idx * kTile;
         const uint32_t cnt = min((uint32_t)kTile, n - first);
         mbar_wait(&s.full_bar, it & 1u);
+        FA_PROF_MARK(0);                                           // waiting for the tile
 
         // ------------------------------------------------------ E: hash, elect, fold duplicates
-        const bool valid = (uint32_t)tid < cnt;
-        uint4 r2 = make_uint4(0, 0, 0, 0), r3 = r2, r4 = r2;
-        uint64_t premix = 0;
-        bool is_rep = valid;
-        if (valid) {
-            const uint4* R = T + tid * kRecChunks;
-            const uint4 r0 = R[0], r1 = R[1];
-            r2 = R[2]; r3 = R[3]; r4 = R[4];
-            premix = key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y), u64_of(r1.z, r1.w),
-                                u64_of(r2.x, r2.y));
-            const uint64_t h = slot_hash(premix);
-            s.hs[tid] = (uint32_t)h;
-            const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
-            const uint64_t v_ns = 0ull - v_start;
-            uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
-            for (;;) {
-                const uint32_t old = atomicCAS(&s.rep[rs], kRepEmpty, (uint32_t)tid);
-                if (old == kRepEmpty) break;
-                const uint4* O = T + old * kRecChunks;
-                const uint4 o2 = O[2];
-                if (eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
-                    eq4_masked(O[1], r1, chunk_mask(1))) {
-                    // Same key.  Fold into that representative with 32-bit shared atomics when the high
-                    // words of the timestamps agree (the common case); otherwise go to the table on our own.
-                    const uint4 o3 = O[3];
-                    const uint64_t o_ns = 0ull - u64_of(o2.z, o2.w), o_end = u64_of(o3.x, o3.y);
-                    const bool ok = (v_start == 0 || (uint32_t)(v_ns >> 32) == (uint32_t)(o_ns >> 32)) &&
-                                    (v_end == 0 || (uint32_t)(v_end >> 32) == (uint32_t)(o_end >> 32));
-                    if (ok) {
-                        is_rep = false;
-                        uint32_t* A = s.acc[old];
-                        const uint32_t b_lo = r3.z, b_hi = r3.w;
-                        const uint32_t prev = atomicAdd(&A[0], b_lo);
-                        const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
-                        if (hi_add) atomicAdd(&A[1], hi_add);
-                        atomicAdd(&A[2], r4.x);
-                        const uint32_t fl = r4.y >> 16;
-                        if (fl) atomicOr(&A[3], fl);
-                        if (v_start) atomicMax(&A[4], (uint32_t)v_ns);
-                        if (v_end) atomicMax(&A[5], (uint32_t)v_end);
-                        // exact descriptor compare against the representative (74 bytes, padding masked)
-                        bool same = eq4_masked(O[4], r4, chunk_mask(3));
-#pragma unroll
-                        for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
-                        if (!same) s.tdirty[old] = 1;
-                    }
-                    break;
+        {
+            const bool valid = (uint32_t)tid < cnt;
+            bool is_rep = valid;
+            if (valid) {
+                const uint4* R = T + tid * kRecChunks;
+                const uint4 r0 = R[0], r1 = R[1], r2 = R[2];
+                const uint64_t h = slot_hash(key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
+                                                        u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)));
+                s.hs[tid] = (uint32_t)h;
+                if (opt & 1u) {   // start the table lines of this key on their way into L2 while the tile is being folded
+                    const size_t home = (size_t)((uint32_t)h & tmask);
+                    prefetch_l2(&t.ident[home * 8]);
+                    prefetch_l2(&t.hot[home * 2]);
                 }
-                rs = (rs + 1) & (kRepSlots - 1);
+                uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
+                for (;;) {
+                    const uint32_t old = atomicCAS(&s.rep[rs], kRepEmpty, (uint32_t)tid);
+                    if (old == kRepEmpty) break;
+                    const uint4* O = T + old * kRecChunks;
+                    const uint4 o2 = O[2];
+                    if (eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
+                        eq4_masked(O[1], r1, chunk_mask(1))) {
+                        // Same key.  Fold into that representative with 32-bit shared atomics when the high
+                        // words of the timestamps agree (the common case); otherwise go to the table on our own.
+                        const uint4 r3 = R[3], r4 = R[4], o3 = O[3];
+                        const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+                        const uint64_t v_ns = 0ull - v_start;
+                        const uint64_t o_ns = 0ull - u64_of(o2.z, o2.w), o_end = u64_of(o3.x, o3.y);
+                        const bool ok = (v_start == 0 || (uint32_t)(v_ns >> 32) == (uint32_t)(o_ns >> 32)) &&
+                                        (v_end == 0 || (uint32_t)(v_end >> 32) == (uint32_t)(o_end >> 32));
+                        if (ok) {
+                            is_rep = false;
+                            uint32_t* A = s.acc[old];
+                            const uint32_t b_lo = r3.z, b_hi = r3.w;
+                            const uint32_t prev = atomicAdd(&A[0], b_lo);
+                            const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
+                            if (hi_add) atomicAdd(&A[1], hi_add);
+                            atomicAdd(&A[2], r4.x);
+                            const uint32_t fl = r4.y >> 16;
+                            if (fl) atomicOr(&A[3], fl);
+                            if (v_start) atomicMax(&A[4], (uint32_t)v_ns);
+                            if (v_end) atomicMax(&A[5], (uint32_t)v_end);
+                            // exact descriptor compare against the representative (74 bytes, padding masked)
+                            bool same = eq4_masked(O[4], r4, chunk_mask(3));
+#pragma unroll
+                            for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
+                            if (!same) s.tdirty[old] = 1;
+                        }
+                        break;
+                    }
+                    rs = (rs + 1) & (kRepSlots - 1);
+                }
+            }
+            // CTA-wide list of representatives, so that every warp probes an equal share
+            const uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_rep);
+            uint32_t lbase = 0;
+            if (lane == 0 && pending) lbase = atomicAdd(&s.nrep, (uint32_t)__popc(pending));
+            lbase = __shfl_sync(0xFFFFFFFFu, lbase, 0);
+            if (is_rep) s.glist[lbase + __popc(pending & lt_mask)] = (uint8_t)tid;
+        }
+        FA_PROF_MARK(1);                                           // E phase
+        __syncthreads();                                           // S1: folds, hashes and the list are complete
+        FA_PROF_MARK(2);                                           // S1 wait
+
+        const uint32_t nrep_total = s.nrep;
+        const uint32_t share = ((nrep_total + kTile / 32 - 1) / (kTile / 32) + 3u) & ~3u;   // multiple of 4
+        const uint32_t k_begin = min(nrep_total, (uint32_t)warp * share);
+        const uint32_t k_end = min(nrep_total, k_begin + share);
+        s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;   // nobody reads the election table after S1
+
+        // ------------------------------------------------------ cooperative probe: 8 lanes per flow
+        uint32_t nslow = 0;
+        for (uint32_t base = k_begin; base < k_end; base += 4 * kInflight) {
+            uint4 line[kInflight];
+            uint32_t ridx[kInflight];
+            uint32_t slot[kInflight];
+#pragma unroll
+            for (int r = 0; r < kInflight; r++) {                  // issue: up to 16 identity lines in flight per warp
+                const uint32_t k = base + r * 4 + g;
+                const bool act = k < k_end;
+                ridx[r] = act ? s.glist[k] : 0;
+                slot[r] = s.hs[ridx[r]] & tmask;
+                line[r] = make_uint4(0, 0, 0, 0);
+                if (act) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
+            }
+#pragma unroll
+            for (int r = 0; r < kInflight; r++) {                  // resolve: first-probe hits on settled flows
+                const bool act = base + r * 4 + g < k_end;
+                const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
+                bool eq = eq4_masked(line[r], rchunk, cmask);
+                const uint64_t tag = u64_of(line[r].z, line[r].w);  // meaningful in lane j == 2 only
+                if (j == 2) eq = eq && (tag & TAG_STATE_MASK) == TAG_PUBLISHED && (tag >> TAG_EPOCH_SHIFT) != epoch;
+                const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq) >> (g * 8)) & 0xFFu;
+                const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches at its home slot
+                if (fast && j == 0) s.res[ridx[r]] = slot[r];
+                if (fast && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
+                if (fast && j == 2) {
+                    s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                    if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[r]] != 0) {
+                        unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
+                        if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                        s.any_dirty = 1;
+                    }
+                }
+                const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, act && !fast && j == 0);
+                if (slowb) {
+                    if (act && !fast && j == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx[r];
+                    nslow += __popc(slowb);
+                }
             }
         }
-        __syncthreads();                                           // S1: all folds of this tile are in acc[]
+        __syncwarp();
+        FA_PROF_MARK(3);                                           // pipelined first-probe phase
+        for (uint32_t base = 0; base < nslow; base += 4) {         // inserts, collisions, in-flight publishes
+            const uint32_t k = base + g;
+            const bool act = k < nslow;
+            const uint32_t ri = act ? s.slow[warp][k] : 0;
+            const uint4 rchunk = T[ri * kRecChunks + rc];
+            const uint4 c2 = T[ri * kRecChunks + 2];
+            const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
+            const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
+            const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0,
+                                               dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &s.any_dirty);
+            if (act && j == 0) s.res[ri] = got;
+            if (act && j == 2) s.fseen[ri] = 0;                     // unknown: issue every reduction
+            if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
+        }
+        __syncwarp();
+        FA_PROF_MARK(4);                                           // general probe loop
 
-        // ------------------------------------------------------ representatives: totals in registers
+        // ------------------------------------------------------ one lane per flow: totals into registers
+        const bool mine = k_begin + lane < k_end;
+        uint32_t my_ridx = 0, my_slot = kResSpill;
         uint64_t t_bytes = 0, t_ns = 0, t_end = 0;
         uint32_t t_packets = 0, t_flags = 0;
-        if (is_rep) {
-            const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[tid][0]);
-            const uint2 a1 = *reinterpret_cast<const uint2*>(&s.acc[tid][4]);
+        if (mine) {
+            my_ridx = s.glist[k_begin + lane];
+            my_slot = s.res[my_ridx];
+            const uint64_t floor_ns = u64_of(s.mir_lo[my_ridx], s.mir_hi[my_ridx]) << 16;   // <= hot.nstart, always
+            const uint32_t seen = s.fseen[my_ridx];
+            const uint4* R = T + my_ridx * kRecChunks;
+            const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
+            const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
+            const uint2 a1 = *reinterpret_cast<const uint2*>(&s.acc[my_ridx][4]);
             const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
             const uint64_t v_ns = 0ull - v_start;
             t_bytes = u64_of(r3.z, r3.w) + u64_of(a0.x, a0.y);
@@ -223,9 +323,15 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             const uint64_t c_ns = u64_of(a1.x, (uint32_t)(v_ns >> 32)), c_end = u64_of(a1.y, (uint32_t)(v_end >> 32));
             t_ns = c_ns > v_ns ? c_ns : v_ns;
             t_end = c_end > v_end ? c_end : v_end;
-            *reinterpret_cast<uint4*>(&s.acc[tid][0]) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint2*>(&s.acc[tid][4]) = make_uint2(0, 0);
+            if (t_ns <= floor_ns) t_ns = 0;                        // cannot raise hot.nstart: skip that reduction
+            t_flags &= ~seen;                                      // only flag bits the hot line does not have yet
+            *reinterpret_cast<uint4*>(&s.acc[my_ridx][0]) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint2*>(&s.acc[my_ridx][4]) = make_uint2(0, 0);
+            s.tdirty[my_ridx] = 0;
             if (kSketch) {
+                const uint4 r0 = R[0], r1 = R[1];
+                const uint64_t premix = key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
+                                                   u64_of(r1.z, r1.w), u64_of(r2.x, r2.y));
                 const uint64_t a = cms_hash_a(premix, sk.seed), b = cms_hash_b(premix, sk.seed);
                 for (uint32_t d = 0; d < sk.depth; d++)
                     red_add_u64(sk.cms + ((size_t)d << sk.log2w) + cms_index(a, b, d, sk.log2w), t_packets);
@@ -236,88 +342,39 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 if (__ldcg(&sk.hll[idx]) < rho) red_max_u32(&sk.hll[idx], rho);
             }
         }
-        s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;   // nobody reads the election table after S1
-
-        // ------------------------------------------------------ per-warp list of representatives
-        const uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_rep);
-        const uint32_t nreps = __popc(pending);
-        if (is_rep) s.list[warp][__popc(pending & ((1u << lane) - 1u))] = (uint8_t)lane;
-        __syncwarp();
-
-        // ------------------------------------------------------ cooperative probe: 8 lanes per flow
-        uint32_t nslow = 0;
-        for (uint32_t base = 0; base < nreps; base += 4 * kInflight) {
-            uint4 line[kInflight];
-            uint32_t ridx[kInflight];
-            uint32_t slot[kInflight];
-#pragma unroll
-            for (int r = 0; r < kInflight; r++) {                  // issue: up to 16 identity lines in flight per warp
-                const uint32_t k = base + r * 4 + g;
-                const bool act = k < nreps;
-                ridx[r] = warp * 32 + (act ? s.list[warp][k] : 0);
-                slot[r] = s.hs[ridx[r]] & tmask;
-                line[r] = make_uint4(0, 0, 0, 0);
-                if (act) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
-            }
-#pragma unroll
-            for (int r = 0; r < kInflight; r++) {                  // resolve: first-probe hits on settled flows
-                const uint32_t k = base + r * 4 + g;
-                const bool act = k < nreps;
-                const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
-                const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq4_masked(line[r], rchunk, cmask)) >> (g * 8)) & 0xFFu;
-                const uint32_t tag_lo = __shfl_sync(0xFFFFFFFFu, line[r].z, g * 8 + 2);
-                const uint32_t tag_hi = __shfl_sync(0xFFFFFFFFu, line[r].w, g * 8 + 2);
-                const uint64_t tag = u64_of(tag_lo, tag_hi);
-                const bool settled = (tag & TAG_STATE_MASK) == TAG_PUBLISHED && (tag >> TAG_EPOCH_SHIFT) != epoch;
-                const bool fast = act && settled && (eqb & 0x07u) == 0x07u;
-                if (fast && j == 0) s.res[ridx[r]] = slot[r];
-                if (fast && j == 2) {
-                    const bool cta_dirty = s.tdirty[ridx[r]] != 0;
-                    if ((eqb & 0xF8u) != 0xF8u || cta_dirty) {
-                        unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
-                        if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
-                        s.any_dirty = 1;
-                    }
-                }
-                const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, act && !fast && j == 0);
-                if (act && !fast && j == 0) s.slow[warp][nslow + __popc(slowb & ((1u << lane) - 1u))] = (uint8_t)(ridx[r] & 31u);
-                nslow += __popc(slowb);
-            }
+        FA_PROF_MARK(5);                                           // totals
+        __syncthreads();                                           // S2: nobody reads the tile buffer any more
+        FA_PROF_MARK(6);                                           // S2 wait
+        if (tid == 0) {
+            s.nrep = 0;
+            const uint32_t nt = tile_idx + gridDim.x;
+            if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, recs, n, nt); }
         }
-        __syncwarp();
-        for (uint32_t base = 0; base < nslow; base += 4) {         // inserts, collisions, in-flight publishes
-            const uint32_t k = base + g;
-            const bool act = k < nslow;
-            const uint32_t ri = warp * 32 + (act ? s.slow[warp][k] : 0);
-            const uint4 rchunk = T[ri * kRecChunks + rc];
-            const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0, g, j, cmask,
-                                               my_inserts, &s.any_dirty);
-            if (act && j == 0) s.res[ri] = got;
-        }
-        __syncwarp();
 
-        // ------------------------------------------------------ one lane per flow: fire-and-forget reductions
-        if (is_rep) {
-            const uint32_t slot = s.res[tid];
-            s.tdirty[tid] = 0;
-            if (slot != kResSpill) {
-                uint8_t* hot = reinterpret_cast<uint8_t*>(t.hot) + (size_t)slot * kHotBytes;
+        // ------------------------------------------------------ fire-and-forget reductions on the hot lines
+        if (mine) {
+            if (my_slot != kResSpill) {
+                uint8_t* hot = reinterpret_cast<uint8_t*>(t.hot) + (size_t)my_slot * kHotBytes;
                 red_add_u64(hot, t_bytes);
                 if (t_ns) red_max_u64(hot + 8, t_ns);
                 if (t_end) red_max_u64(hot + 16, t_end);
                 red_add_u32(hot + 24, t_packets);
-                if (t_flags) red_or_u32(hot + 28, t_flags);
+                if (t_flags) {
+                    red_or_u32(hot + 28, t_flags);
+                    red_or_u64(reinterpret_cast<uint8_t*>(&t.ident[(size_t)my_slot * 8 + 2]) + 8,
+                               (unsigned long long)t_flags << TAG_FLAGS_SHIFT);
+                }
             } else {                                               // table physically full: spill, never drop silently
                 const unsigned long long kk = atomicAdd(&ctr->scratch[2], 1ull);
-                spill_idx[kk] = first + (uint32_t)tid;
+                spill_idx[kk] = first + my_ridx;
                 my_spills++;
             }
         }
-        __syncthreads();                                           // S2: the tile buffer is free again
-        if (tid == 0) {
-            const uint32_t nt = tile_idx + gridDim.x;
-            if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, recs, n, nt); }
-        }
+        FA_PROF_MARK(7);                                           // reductions
+    }
+    if (kProf && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
     }
 
     // ---------------------------------------------------------- counters
@@ -346,7 +403,12 @@ __device__ __forceinline__ bool key_equal_line(const uint4* line, uint4 k0, uint
     return eq4_masked(l0, k0, chunk_mask(0)) && eq4_masked(l1, k1, chunk_mask(1)) && eq4_masked(l2, k2, chunk_mask(2));
 }
 
-__global__ void fixup_scan_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, Counters* ctr, FixupScratch* scratch) {
+__device__ __forceinline__ uint32_t scratch_home(uint64_t slot, uint32_t smask) {
+    return (uint32_t)((slot * 0x9E3779B97F4A7C15ull) >> 32) & smask;
+}
+
+__global__ void fixup_scan_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, Counters* ctr, FixupScratch* scratch,
+                                  uint32_t smask) {
     if (*reinterpret_cast<volatile unsigned long long*>(&ctr->dirty) == 0ull) return;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint4* R = recs + (size_t)i * kRecChunks;
@@ -363,43 +425,41 @@ __global__ void fixup_scan_kernel(const uint4* __restrict__ recs, uint32_t n, Ta
             slot = (slot + 1) & t.mask;
         }
         if (!found || !(tag & TAG_DIRTY)) continue;
-        uint32_t* auxp = reinterpret_cast<uint32_t*>(&t.ident[slot * 8 + 3]);
-        uint32_t aux = *reinterpret_cast<volatile uint32_t*>(auxp);
-        if (aux == 0) {
-            const uint32_t mine = (uint32_t)atomicAdd(&ctr->scratch[0], 1ull) + 1u;
-            const uint32_t old = atomicCAS(auxp, 0u, mine);
-            aux = old ? old : mine;
+        uint32_t si = scratch_home(slot, smask);
+        for (;;) {                                                   // find-or-insert the flow's scratch entry
+            const unsigned long long k = atomicCAS(&scratch[si].key, 0ull, slot + 1);
+            if (k == 0ull || k == slot + 1) break;
+            si = (si + 1) & smask;
         }
-        FixupScratch* sc = &scratch[aux];
-        sc->slot_lo = (uint32_t)slot; sc->slot_hi = (uint32_t)(slot >> 32);
+        FixupScratch* sc = &scratch[si];
         const uint4 r4 = R[4], r5 = R[5], r6 = R[6];
-        atomicMin(&sc->first, i);
+        atomicMax(&sc->nfirst, ~i);
         if (r4.y & 0xFFFFu) atomicMax(&sc->eth, i + 1);
         if ((r6.x >> 16) & 0xFFu) atomicMax(&sc->dscp, i + 1);
         if (r5.w) atomicMax(&sc->samp, i + 1);
-        if (r4.z | (r4.w & 0xFFFFu)) atomicMin(&sc->smac, i);
-        if ((r4.w >> 16) | r5.x) atomicMin(&sc->dmac, i);
+        if (r4.z | (r4.w & 0xFFFFu)) atomicMax(&sc->nsmac, ~i);
+        if ((r4.w >> 16) | r5.x) atomicMax(&sc->ndmac, ~i);
     }
 }
 
 __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint64_t epoch, Counters* ctr,
-                                   FixupScratch* scratch, unsigned int* ticket) {
+                                   FixupScratch* scratch, uint32_t scratch_slots, unsigned int* ticket) {
     if (*reinterpret_cast<volatile unsigned long long*>(&ctr->dirty) == 0ull) return;
-    const uint32_t count = (uint32_t)*reinterpret_cast<volatile unsigned long long*>(&ctr->scratch[0]);
     uint32_t fixed = 0;
-    for (uint32_t a = 1 + blockIdx.x * blockDim.x + threadIdx.x; a <= count; a += gridDim.x * blockDim.x) {
-        FixupScratch sc = scratch[a];
-        scratch[a] = FixupScratch{0xFFFFFFFFu, 0u, 0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u};
-        if (sc.first == 0xFFFFFFFFu) continue;            // index allocated but lost the CAS race
-        const uint64_t slot = u64_of(sc.slot_lo, sc.slot_hi);
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < scratch_slots; a += gridDim.x * blockDim.x) {
+        const FixupScratch sc = scratch[a];
+        if (sc.key == 0ull) continue;
+        scratch[a] = FixupScratch{0ull, 0u, 0u, 0u, 0u, 0u, 0u};
+        const uint64_t slot = sc.key - 1;
         uint4* L = &t.ident[slot * 8];
         unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&L[2]) + 1;
         const unsigned long long tag = *tagp;
         const bool is_new = (tag >> TAG_EPOCH_SHIFT) == epoch;
         // current descriptor state: line chunks 3..7 <-> record chunks 4..8
         uint4 d3 = L[3], d4 = L[4], d5 = L[5], d6 = L[6], d7 = L[7];
+        const uint32_t mir_lo = d3.x, mir_hi = d3.y & 0xFFFF0000u;    // immutable start mirror stays
         if (is_new) {                                      // state = the flow's first record, whole (account.go:95)
-            const uint4* F = recs + (size_t)sc.first * kRecChunks;
+            const uint4* F = recs + (size_t)(~sc.nfirst) * kRecChunks;
             d3 = and4(F[4], chunk_mask(3)); d4 = F[5]; d5 = and4(F[6], chunk_mask(5)); d6 = F[7]; d7 = and4(F[8], chunk_mask(7));
         }
         // eth_protocol / dscp / sampling: last non-zero in stream order (flow_content.go:45-47,54-59)
@@ -407,17 +467,17 @@ __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint
         if (sc.dscp) { const uint4 x = recs[(size_t)(sc.dscp - 1) * kRecChunks + 6]; d5.x = (d5.x & 0xFF00FFFFu) | (x.x & 0x00FF0000u); }
         if (sc.samp) { const uint4 x = recs[(size_t)(sc.samp - 1) * kRecChunks + 5]; d4.w = x.w; }
         // MACs: first non-zero in stream order, only while still all-zero (flow_content.go:48-53)
-        if ((d3.z | (d3.w & 0xFFFFu)) == 0u && sc.smac != 0xFFFFFFFFu) {
-            const uint4 x = recs[(size_t)sc.smac * kRecChunks + 4];
+        if ((d3.z | (d3.w & 0xFFFFu)) == 0u && sc.nsmac != 0u) {
+            const uint4 x = recs[(size_t)(~sc.nsmac) * kRecChunks + 4];
             d3.z = x.z; d3.w = (d3.w & 0xFFFF0000u) | (x.w & 0xFFFFu);
         }
-        if (((d3.w >> 16) | d4.x) == 0u && sc.dmac != 0xFFFFFFFFu) {
-            const uint4 x4 = recs[(size_t)sc.dmac * kRecChunks + 4], x5 = recs[(size_t)sc.dmac * kRecChunks + 5];
+        if (((d3.w >> 16) | d4.x) == 0u && sc.ndmac != 0u) {
+            const uint4 x4 = recs[(size_t)(~sc.ndmac) * kRecChunks + 4], x5 = recs[(size_t)(~sc.ndmac) * kRecChunks + 5];
             d3.w = (d3.w & 0xFFFFu) | (x4.w & 0xFFFF0000u); d4.x = x5.x;
         }
-        d3.x = 0u;                                        // aux back to 0
+        d3.x = mir_lo; d3.y = (d3.y & 0xFFFFu) | mir_hi;
         L[3] = d3; L[4] = d4; L[5] = d5; L[6] = d6; L[7] = d7;
-        *tagp = tag & ~(unsigned long long)TAG_DIRTY;
+        atomicAnd(tagp, ~(unsigned long long)TAG_DIRTY);
         fixed++;
     }
     if (fixed) atomicAdd(&ctr->fixups_total, (unsigned long long)fixed);
@@ -428,28 +488,42 @@ __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint
         if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
             *ticket = 0u;
             ctr->dirty = 0ull;
-            ctr->scratch[0] = 0ull;
             __threadfence();
         }
     }
 }
 
-int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
-    if (a.n == 0) return 0;
+template <int kTile, int kInflight, int kMinBlocks>
+static void launch_variant(const AggLaunch& a, cudaStream_t st) {
     static bool attr_done = false;
-    const int smem = (int)sizeof(AggSmem);
+    const int smem = (int)sizeof(AggSmem<kTile>);
     if (!attr_done) {
-        cudaFuncSetAttribute(aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<kTile, kInflight, kMinBlocks, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<kTile, kInflight, kMinBlocks, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<kTile, kInflight, kMinBlocks, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
     const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
-    const int grid = (int)min((uint32_t)(a.sm_count * 4), n_tiles);
-    if (a.sk.cms) aggregate_kernel<true><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk);
-    else aggregate_kernel<false><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk);
+    const int grid = (int)min((uint32_t)(a.sm_count * kMinBlocks), n_tiles);
+    if (a.prof)
+        aggregate_kernel<kTile, kInflight, kMinBlocks, false, true><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, a.prof, a.opt);
+    else if (a.sk.cms)
+        aggregate_kernel<kTile, kInflight, kMinBlocks, true, false><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, nullptr, a.opt);
+    else
+        aggregate_kernel<kTile, kInflight, kMinBlocks, false, false><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, nullptr, a.opt);
+}
+
+int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
+    if (a.n == 0) return 0;
+    switch ((a.opt >> 1) & 3u) {            // FA_K1_OPT bits 1-2: kernel shape experiments
+        case 1:  launch_variant<256, 8, 3>(a, st); break;
+        case 2:  launch_variant<128, 4, 8>(a, st); break;
+        case 3:  launch_variant<128, 8, 6>(a, st); break;
+        default: launch_variant<256, 4, 4>(a, st); break;
+    }
     const int fgrid = a.sm_count * 2;
-    fixup_scan_kernel<<<fgrid, 256, 0, st>>>(a.recs, a.n, a.table, a.ctr, a.scratch);
-    fixup_apply_kernel<<<fgrid, 256, 0, st>>>(a.recs, a.table, a.epoch, a.ctr, a.scratch,
+    fixup_scan_kernel<<<fgrid, 256, 0, st>>>(a.recs, a.n, a.table, a.ctr, a.scratch, a.scratch_slots - 1);
+    fixup_apply_kernel<<<fgrid, 256, 0, st>>>(a.recs, a.table, a.epoch, a.ctr, a.scratch, a.scratch_slots,
                                               reinterpret_cast<unsigned int*>(&a.ctr->scratch[1]));
     return 3;
 }

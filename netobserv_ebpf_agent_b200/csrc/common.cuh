@@ -28,10 +28,10 @@ constexpr int R_START = 40, R_END = 48, R_BYTES = 56, R_PACKETS = 64, R_ETH = 68
 //
 // identity line (read-mostly; written once when the flow is created):
 //   [  0.. 40) key (byte 39 forced to 0)
-//   [ 40.. 48) tag   u64: 0 = EMPTY, else (epoch << 8) | flags | state
-//   [ 48.. 52) aux   u32: scratch index while an ordered re-fold is pending
-//   [ 52.. 54) eth_protocol
-//   [ 54.. 56) spare
+//   [ 40.. 48) tag   u64: 0 = EMPTY, else (epoch << 24) | (tcp flags already OR-ed into the hot line << 8) | bits
+//   [ 48.. 52) start mirror, low 32 bits   } m48 = (0 - start_at_insert) >> 16: an immutable lower bound of
+//   [ 52.. 54) eth_protocol                } hot.nstart, so records that cannot lower the start skip that RED
+//   [ 54.. 56) start mirror, high 16 bits  }
 //   [ 56..128) descriptor = record bytes [72..144) with padding zeroed
 // so that line chunk j (16 B) lines up with record chunk {0,1,2,4,5,6,7,8}[j].
 //
@@ -49,7 +49,8 @@ constexpr uint64_t TAG_CLAIMED    = 0x1ull;
 constexpr uint64_t TAG_PUBLISHED  = 0x2ull;
 constexpr uint64_t TAG_DIRTY      = 0x4ull;   // order-dependent fields must be re-folded in stream order
 constexpr uint64_t TAG_HAS_BASE   = 0x8ull;   // at least one base flow record was folded (vs feature-only entry)
-constexpr int      TAG_EPOCH_SHIFT = 8;
+constexpr int      TAG_FLAGS_SHIFT = 8;    // 16 bits: flag bits known to be set in hot.flags already
+constexpr int      TAG_EPOCH_SHIFT = 24;   // 40-bit launch counter
 
 struct Table {
     uint4*   ident;      // slots x 8 uint4
@@ -145,6 +146,12 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Ask L2 to fetch a byte range (SASS: UBLKPF); used to run the HBM read of the next tiles ahead of
+// the shared-memory staging of the current one.
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // L2-coherent 128-bit load (bypasses L1: table lines are written by other SMs in the same launch).
 __device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) { return __ldcg(p); }
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) { return __ldcg(p); }
@@ -157,6 +164,8 @@ __device__ __forceinline__ void red_add_u64(void* p, unsigned long long v) { asm
 __device__ __forceinline__ void red_max_u64(void* p, unsigned long long v) { asm volatile("red.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void red_min_u64(void* p, unsigned long long v) { asm volatile("red.global.min.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void red_add_u32(void* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_or_u64(void* p, unsigned long long v) { asm volatile("red.global.or.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void red_or_u32(void* p, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_max_u32(void* p, uint32_t v) { asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_min_u32(void* p, uint32_t v) { asm volatile("red.global.min.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }

@@ -121,7 +121,7 @@ struct fa_engine {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};       // H2D copy into the stage finished
     int stage_cur = 0;
 
-    fa::FixupScratch* d_scratch = nullptr;
+    fa::FixupScratch* d_scratch = nullptr; uint32_t scratch_slots = 0;
     uint32_t* d_spill_idx = nullptr;
     uint32_t* d_cut_set = nullptr; uint32_t cut_set_slots = 0;
     uint32_t* d_cut_bitmap = nullptr; uint32_t* d_cut_out = nullptr; uint32_t* h_cut_out = nullptr;
@@ -130,6 +130,8 @@ struct fa_engine {
     uint32_t* d_route_tmp = nullptr; unsigned long long* d_route_counts = nullptr;
 
     fa::SketchParams sk{};
+    unsigned long long* d_prof = nullptr;     // FA_PHASE_PROFILE=1: per-phase warp-cycle counters of K1
+    uint32_t k1_opt = 0;                      // FA_K1_OPT: experiment switches
 
     // live-flow bookkeeping for the "full" rule: live_known is exact as of the last retired
     // launch; unsynced_records bounds the flows that launches still in flight can add.
@@ -177,7 +179,10 @@ int launch_chunk(fa_engine* e, const uint8_t* d_recs, uint32_t n) {
     a.spill_idx = e->d_spill_idx;
     a.sk = (e->cfg.flags & FA_F_ENABLE_SKETCH) ? e->sk : fa::SketchParams{};
     a.scratch = e->d_scratch;
+    a.scratch_slots = e->scratch_slots;
     a.sm_count = e->sm_count;
+    a.prof = e->d_prof;
+    a.opt = e->k1_opt;
     e->st.kernel_launches += fa::launch_aggregate(a, e->stream);
     CU(cudaGetLastError());
     e->unsynced_records += n;
@@ -323,14 +328,11 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
         CU(cudaEventCreateWithFlags(&e->ev_stage_free[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
     }
-    CU(cudaMalloc(&e->d_scratch, (e->max_batch + 1) * sizeof(fa::FixupScratch)));
     {
-        // initial state of every scratch entry: {~0, 0, 0, 0, ~0, ~0, 0, 0}
-        std::vector<fa::FixupScratch> init(4096, fa::FixupScratch{0xFFFFFFFFu, 0u, 0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u});
-        for (uint64_t off = 0; off < e->max_batch + 1; off += init.size()) {
-            const size_t k = (size_t)std::min<uint64_t>(init.size(), e->max_batch + 1 - off);
-            CU(cudaMemcpyAsync(e->d_scratch + off, init.data(), k * sizeof(fa::FixupScratch), cudaMemcpyHostToDevice, e->stream));
-        }
+        uint32_t ss = 1024; while ((uint64_t)ss < 2 * e->max_batch) ss <<= 1;
+        e->scratch_slots = ss;
+        CU(cudaMalloc(&e->d_scratch, (size_t)ss * sizeof(fa::FixupScratch)));
+        CU(cudaMemsetAsync(e->d_scratch, 0, (size_t)ss * sizeof(fa::FixupScratch), e->stream));
         CU(cudaStreamSynchronize(e->stream));
     }
     CU(cudaMalloc(&e->d_spill_idx, e->max_batch * sizeof(uint32_t)));
@@ -357,6 +359,10 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
         CU(cudaMalloc(&e->sk.hll, ((size_t)1 << e->sk.p) * 4));
         CU(cudaMemsetAsync(e->sk.hll, 0, ((size_t)1 << e->sk.p) * 4, e->stream));
     }
+    if (const char* ko = getenv("FA_K1_OPT")) e->k1_opt = (uint32_t)strtoul(ko, nullptr, 0);
+    if (const char* pp = getenv("FA_PHASE_PROFILE")) {
+        if (pp[0] == '1') { CU(cudaMalloc(&e->d_prof, 8 * 8)); CU(cudaMemsetAsync(e->d_prof, 0, 64, e->stream)); }
+    }
     CU(cudaStreamSynchronize(e->stream));
     *out = e;
     return FA_OK;
@@ -366,6 +372,18 @@ void fa_destroy(fa_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->d_prof) {
+        unsigned long long p[8];
+        if (cudaMemcpy(p, e->d_prof, 64, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            static const char* names[8] = {"tile wait", "hash+elect+fold", "S1 barrier", "pipelined probe", "general probe",
+                                           "totals", "S2 barrier", "reductions"};
+            double tot = 0; for (int i = 0; i < 8; i++) tot += (double)p[i];
+            fprintf(stderr, "[flowagg] K1 phase profile (warp-cycles):");
+            for (int i = 0; i < 8; i++) fprintf(stderr, " %s %.1f%%;", names[i], tot > 0 ? 100.0 * p[i] / tot : 0.0);
+            fprintf(stderr, " total %.3g\n", tot);
+        }
+        cudaFree(e->d_prof);
+    }
     if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
     cudaFree(e->table.ident); cudaFree(e->table.hot); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns);
     cudaFree(e->d_ctr); if (e->h_ctr) cudaFreeHost(e->h_ctr);

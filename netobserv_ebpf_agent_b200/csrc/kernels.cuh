@@ -12,14 +12,15 @@ struct SketchParams {
 };
 
 // scratch entry of the ordered re-fold (one per flow flagged TAG_DIRTY in a launch)
+// (an open-addressed set keyed by table slot; capacity = power of two >= 2 x max_batch)
 struct FixupScratch {
-    uint32_t first;   // min record index of the flow in this launch          (init 0xFFFFFFFF)
-    uint32_t eth;     // 1 + max index with eth_protocol != 0                 (init 0)
+    unsigned long long key;  // table slot + 1, 0 = empty
+    uint32_t nfirst;  // ~(min record index of the flow in this launch)       all-zero == initial state
+    uint32_t eth;     // 1 + max index with eth_protocol != 0
     uint32_t dscp;    // 1 + max index with dscp != 0
     uint32_t samp;    // 1 + max index with sampling != 0
-    uint32_t smac;    // min index with src_mac != 0                          (init 0xFFFFFFFF)
-    uint32_t dmac;    // min index with dst_mac != 0
-    uint32_t slot_lo, slot_hi;
+    uint32_t nsmac;   // ~(min index with src_mac != 0), 0 = none
+    uint32_t ndmac;   // ~(min index with dst_mac != 0), 0 = none
 };
 
 struct AggLaunch {
@@ -30,8 +31,11 @@ struct AggLaunch {
     Counters*    ctr;
     uint32_t*    spill_idx;  // indices of records that found the table physically full
     SketchParams sk;
-    FixupScratch* scratch;   // capacity >= n + 1 entries, pre-initialised
+    FixupScratch* scratch;   // scratch_slots entries, all-zero between launches
+    uint32_t     scratch_slots;
     int          sm_count;
+    unsigned long long* prof; // 8 phase cycle counters (FA_PHASE_PROFILE=1) or nullptr
+    uint32_t     opt;        // experiment switches (FA_K1_OPT), 0 = default
 };
 
 // K1: fold a batch of flow records into the table (ACCOUNTER semantics) and, when any
