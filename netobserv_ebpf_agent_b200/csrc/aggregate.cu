@@ -2,55 +2,113 @@
 // open-addressed flow table with the semantics of the reference's userspace Accounter
 // (pkg/flow/account.go:82-96 + pkg/model/flow_content.go:28-61).
 //
-// Pipeline per CTA (persistent, 256 threads, tiles of 256 records):
-//   TMA bulk copy (cp.async.bulk + mbarrier, 2 stages) stages a 36 KB tile of records in
-//   shared memory -> each thread hashes one record -> duplicates of a key inside the tile
-//   elect one representative through a shared-memory index table and fold into it with
-//   shared-memory atomics -> each warp then walks its representatives 4 at a time, 8 lanes
-//   per flow: one coalesced 128-byte identity-line load per probe, a masked 16-byte compare
-//   per lane, ballot to agree on hit / miss / claim, and five fire-and-forget reductions
-//   (RED.add/max/or) on the 32-byte hot line.
+// One persistent CTA per SM, 1024 threads = 4 teams of 256.  Each team owns a stream of
+// 256-record tiles and synchronises with a named barrier; all teams share a small cache of
+// the hottest flows.  Per tile:
+//   TMA bulk copy (cp.async.bulk + mbarrier) stages 36 KB of records in shared memory
+//   -> E: each thread hashes one record; a record of a cached hot flow folds straight into
+//      the cache's shared-memory accumulators; otherwise duplicates of a key inside the tile
+//      elect one representative (shared-memory CAS table) and fold into it with 32-bit
+//      shared atomics
+//   -> probe: the team's representatives are dealt evenly to its 8 warps; 8 lanes per flow,
+//      16 identity lines (128 B each, one coalesced load) in flight per warp, a masked 16-byte
+//      compare per lane and one ballot decide hit / miss
+//   -> general loop (rare): inserts (CAS-claim, write, fence, publish), collisions, flows
+//      being published by another SM
+//   -> one lane per flow: three fire-and-forget reductions on the 32-byte hot line
+//      (RED.add bytes, RED.add packets, RED.max end; start / flags only when they can change it).
+// The cache is flushed with the same reductions when the CTA runs out of tiles.
 //
 // Exactness of the order-dependent fields (eth_protocol / dscp / sampling = last non-zero,
 // MACs = first non-zero, everything else = first record; flow_content.go:45-59,
 // account.go:95): while every record of a flow carries the same 74-byte descriptor the
-// merge result does not depend on order, so the fast path only *compares* descriptors.
-// Any mismatch flags the flow TAG_DIRTY and the two re-fold kernels below recompute those
-// fields from the batch in stream-index order.
+// merge result does not depend on order, so the fast path only *compares* descriptors
+// (exactly, all 74 bytes).  Any mismatch flags the flow TAG_DIRTY and the two re-fold kernels
+// below recompute those fields from the batch in stream-index order.
 #include "kernels.cuh"
 
 namespace fa {
 
+constexpr int kTile      = 256;                 // records per tile == threads per team
+constexpr int kTeams     = 4;                   // teams per CTA (one CTA per SM)
+constexpr int kCtaThreads = kTile * kTeams;
+constexpr int kRepSlots  = 2 * kTile;
+constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
+constexpr int kHotEntries = 64;                 // CTA-wide cache of hot flows
+constexpr uint32_t kHotMinDups = 2;             // a flow with >= 3 records in one tile becomes a cache candidate
 constexpr uint32_t kRepEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kResSpill = 0xFFFFFFFFu;
 constexpr uint32_t kProbeLimit = 8192;
 
-// kTile = records per tile = threads per CTA.  kTile 256: ~52 KB per CTA -> 4 CTAs (32 warps) per SM.
-template <int kTile>
-struct __align__(128) AggSmem {
-    static constexpr int kRepSlots = 2 * kTile;
+struct __align__(128) TeamSmem {                  // 51,984 B per team
     uint4    tile[kTile * kRecChunks];            // 36,864 B  one TMA-staged tile of records
     uint32_t acc[kTile][8];                       //  8,192 B  what duplicates add to their representative
     uint32_t hs[kTile];                           //  1,024 B  low 32 bits of the slot hash
     uint32_t res[kTile];                          //  1,024 B  table slot found for each representative
-    uint32_t rep[kRepSlots];                      //  2,048 B  tile-local key -> representative index
     uint32_t mir_lo[kTile];                       //  1,024 B  start mirror of the flow found (see common.cuh)
+    uint32_t rep[kRepSlots];                      //  2,048 B  tile-local key -> representative index
     uint16_t mir_hi[kTile];                       //    512 B
     uint16_t fseen[kTile];                        //    512 B  tcp flags already present in the flow's hot line
     uint8_t  tdirty[kTile];                       //    256 B  set by duplicates whose descriptor differs
-    uint8_t  glist[kTile];                        //    256 B  CTA-wide compacted list of representatives
+    uint8_t  glist[kTile];                        //    256 B  team-wide compacted list of representatives
     uint8_t  slow[kTile / 32][32];                //    256 B  per-warp flows that need the general probe loop
     unsigned long long full_bar;
-    uint32_t n_insert, n_spill, any_dirty, nrep;
+    uint32_t nrep, pad;
+};
+struct __align__(16) HotEntry {                   // 208 B: a stride of 52 words keeps 8 entries on distinct banks
+    uint4    line[8];                             // copy of the flow's identity line
+    uint32_t acc[8];                              // bytes lo/hi, packets, flags, ns lo (max), end lo (max), hits, -
+    uint32_t state;                               // 0 empty, 1 being filled, 2 live
+    uint32_t hash;                                // low 32 bits of the slot hash
+    uint32_t slot;
+    uint32_t ns_hi, end_hi;                       // high words the 32-bit max windows are relative to
+    uint32_t pad[7];
+};
+static_assert(sizeof(HotEntry) == 208, "HotEntry stride");
+struct __align__(128) AggSmem {                   // 220,240 B of the 227 KB an sm_100 CTA may use
+    TeamSmem team[kTeams];
+    HotEntry hot[kHotEntries];
+    uint32_t n_insert, n_spill, any_dirty, pad;
 };
 
-template <int kTile>
-__device__ __forceinline__ void issue_tile_load(AggSmem<kTile>& s, const uint4* recs, uint32_t n, uint32_t tile_idx) {
+__device__ __forceinline__ void team_sync(int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(kTile) : "memory");
+}
+
+__device__ __forceinline__ void issue_tile_load(TeamSmem& s, const uint4* recs, uint32_t n, uint32_t tile_idx) {
     const uint32_t first = tile_idx * kTile;
     const uint32_t cnt = min((uint32_t)kTile, n - first);
     const uint32_t bytes = cnt * kRecBytes;
     mbar_expect_tx(&s.full_bar, bytes);
     tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
+}
+
+// Reductions of one flow's folded totals onto its hot line.  floor_ns <= hot.nstart always
+// (immutable start mirror), `seen` are flag bits the hot line is known to hold already.
+__device__ __forceinline__ void reduce_to_hot(const Table& t, uint32_t slot, uint64_t bytes, uint32_t packets,
+                                              uint64_t ns, uint64_t end, uint32_t flags, uint64_t floor_ns, uint32_t seen) {
+    uint8_t* hot = reinterpret_cast<uint8_t*>(t.hot) + (size_t)slot * kHotBytes;
+    red_add_u64(hot, bytes);
+    if (ns > floor_ns) red_max_u64(hot + 8, ns);
+    if (end) red_max_u64(hot + 16, end);
+    red_add_u32(hot + 24, packets);
+    flags &= ~seen;
+    if (flags) {
+        red_or_u32(hot + 28, flags);
+        red_or_u64(reinterpret_cast<uint8_t*>(&t.ident[(size_t)slot * 8 + 2]) + 8, (unsigned long long)flags << TAG_FLAGS_SHIFT);
+    }
+}
+
+// Fused sketches (new capability, no reference): count-min += packets, HyperLogLog register = max(rho).
+__device__ __forceinline__ void sketch_update(const SketchParams& sk, uint64_t premix, uint32_t packets) {
+    const uint64_t a = cms_hash_a(premix, sk.seed), b = cms_hash_b(premix, sk.seed);
+    for (uint32_t d = 0; d < sk.depth; d++)
+        red_add_u64(sk.cms + ((size_t)d << sk.log2w) + cms_index(a, b, d, sk.log2w), packets);
+    const uint64_t hh = hll_hash(premix, sk.seed);
+    const uint32_t idx = (uint32_t)(hh >> (64 - sk.p));
+    const uint64_t rest = hh << sk.p;
+    const uint32_t rho = rest ? (uint32_t)__clzll((long long)rest) + 1u : (64u - sk.p) + 1u;
+    if (__ldcg(&sk.hll[idx]) < rho) red_max_u32(&sk.hll[idx], rho);
 }
 
 // General probe of one flow per 8-lane group (4 flows per call): claims empty slots, waits for
@@ -128,28 +186,33 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
 // kProf: per-warp cycle counters per phase (FA_PHASE_PROFILE=1), summed into prof[0..7].
 #define FA_PROF_MARK(i) do { if (kProf) { const long long now_ = clock64(); pacc[i] += now_ - pt; pt = now_; } } while (0)
 
-template <int kTile, int kInflight, int kMinBlocks, bool kSketch, bool kProf>
-__global__ void __launch_bounds__(kTile, kMinBlocks)
+template <bool kSketch, bool kProf>
+__global__ void __launch_bounds__(kCtaThreads, 1)
 aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
                  uint32_t* __restrict__ spill_idx, SketchParams sk, unsigned long long* prof, uint32_t opt) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    using Smem = AggSmem<kTile>;
-    constexpr int kRepSlots = Smem::kRepSlots;
-    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    AggSmem& cs = *reinterpret_cast<AggSmem*>(smem_raw);
+    const int team = threadIdx.x >> 8;
+    const int tid = threadIdx.x & (kTile - 1), lane = tid & 31, warp = tid >> 5;     // within the team
+    TeamSmem& s = cs.team[team];
     const uint32_t n_tiles = (n + kTile - 1) / kTile;
+    const uint32_t tile_stride = gridDim.x * kTeams;
+    const uint32_t tile0 = blockIdx.x * kTeams + team;
+    const bool use_cache = (opt & 2u) == 0;
 
+    if (threadIdx.x == 0) { cs.n_insert = 0; cs.n_spill = 0; cs.any_dirty = 0; }
+    if (threadIdx.x < kHotEntries) cs.hot[threadIdx.x].state = 0;
     if (tid == 0) {
         mbar_init(&s.full_bar, 1);
         fence_barrier_init();
-        s.n_insert = 0; s.n_spill = 0; s.any_dirty = 0; s.nrep = 0;
+        s.nrep = 0;
     }
     s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;
     *reinterpret_cast<uint4*>(&s.acc[tid][0]) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(&s.acc[tid][4]) = make_uint4(0, 0, 0, 0);
     s.tdirty[tid] = 0;
     __syncthreads();
-    if (tid == 0 && blockIdx.x < n_tiles) issue_tile_load(s, recs, n, blockIdx.x);
+    if (tid == 0 && tile0 < n_tiles) issue_tile_load(s, recs, n, tile0);
 
     const int g = lane >> 3;                  // flow group inside the warp (4 groups of 8 lanes)
     const int j = lane & 7;                   // 16-byte chunk of the identity line handled by this lane
@@ -161,16 +224,17 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     const uint4* T = s.tile;
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long pt = kProf ? clock64() : 0;
+    uint32_t c_cached = 0, c_reps = 0, c_slow = 0, c_install = 0;      // kProf only
 
     for (uint32_t it = 0;; ++it) {
-        const uint32_t tile_idx = blockIdx.x + it * gridDim.x;
+        const uint32_t tile_idx = tile0 + it * tile_stride;
         if (tile_idx >= n_tiles) break;
         const uint32_t first = tile_idx * kTile;
         const uint32_t cnt = min((uint32_t)kTile, n - first);
         mbar_wait(&s.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
 
-        // ------------------------------------------------------ E: hash, elect, fold duplicates
+        // ------------------------------------------------------ E: hash, cache / elect, fold duplicates
         {
             const bool valid = (uint32_t)tid < cnt;
             bool is_rep = valid;
@@ -180,51 +244,76 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint64_t h = slot_hash(key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
                                                         u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)));
                 s.hs[tid] = (uint32_t)h;
-                if (opt & 1u) {   // start the table lines of this key on their way into L2 while the tile is being folded
-                    const size_t home = (size_t)((uint32_t)h & tmask);
-                    prefetch_l2(&t.ident[home * 8]);
-                    prefetch_l2(&t.hot[home * 2]);
-                }
-                uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
-                for (;;) {
-                    const uint32_t old = atomicCAS(&s.rep[rs], kRepEmpty, (uint32_t)tid);
-                    if (old == kRepEmpty) break;
-                    const uint4* O = T + old * kRecChunks;
-                    const uint4 o2 = O[2];
-                    if (eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
-                        eq4_masked(O[1], r1, chunk_mask(1))) {
-                        // Same key.  Fold into that representative with 32-bit shared atomics when the high
-                        // words of the timestamps agree (the common case); otherwise go to the table on our own.
-                        const uint4 r3 = R[3], r4 = R[4], o3 = O[3];
-                        const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
-                        const uint64_t v_ns = 0ull - v_start;
-                        const uint64_t o_ns = 0ull - u64_of(o2.z, o2.w), o_end = u64_of(o3.x, o3.y);
-                        const bool ok = (v_start == 0 || (uint32_t)(v_ns >> 32) == (uint32_t)(o_ns >> 32)) &&
-                                        (v_end == 0 || (uint32_t)(v_end >> 32) == (uint32_t)(o_end >> 32));
-                        if (ok) {
-                            is_rep = false;
-                            uint32_t* A = s.acc[old];
-                            const uint32_t b_lo = r3.z, b_hi = r3.w;
-                            const uint32_t prev = atomicAdd(&A[0], b_lo);
-                            const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
-                            if (hi_add) atomicAdd(&A[1], hi_add);
-                            atomicAdd(&A[2], r4.x);
-                            const uint32_t fl = r4.y >> 16;
-                            if (fl) atomicOr(&A[3], fl);
-                            if (v_start) atomicMax(&A[4], (uint32_t)v_ns);
-                            if (v_end) atomicMax(&A[5], (uint32_t)v_end);
-                            // exact descriptor compare against the representative (74 bytes, padding masked)
-                            bool same = eq4_masked(O[4], r4, chunk_mask(3));
+                // ---- hot-flow cache: an exact 114-byte match folds the record on-chip, no table traffic
+                HotEntry& ce = cs.hot[((uint32_t)h >> 26) & (kHotEntries - 1)];
+                if (use_cache && *reinterpret_cast<volatile uint32_t*>(&ce.state) == 2u && ce.hash == (uint32_t)h) {
+                    const uint4 r3 = R[3], r4 = R[4];
+                    bool same = eq4_masked(ce.line[0], r0, chunk_mask(0)) && eq4_masked(ce.line[1], r1, chunk_mask(1)) &&
+                                eq4_masked(ce.line[2], r2, chunk_mask(2)) && eq4_masked(ce.line[3], r4, chunk_mask(3));
 #pragma unroll
-                            for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
-                            if (!same) s.tdirty[old] = 1;
-                        }
-                        break;
+                    for (int c = 5; c < 9; c++) same = same && eq4_masked(ce.line[c - 1], R[c], chunk_mask(c - 1));
+                    const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+                    const uint64_t v_ns = 0ull - v_start;
+                    same = same && (v_start == 0 || (uint32_t)(v_ns >> 32) == ce.ns_hi) &&
+                           (v_end == 0 || (uint32_t)(v_end >> 32) == ce.end_hi);
+                    if (same) {
+                        is_rep = false;
+                        if (kProf) c_cached++;
+                        uint32_t* A = ce.acc;
+                        const uint32_t b_lo = r3.z, b_hi = r3.w;
+                        const uint32_t prev = atomicAdd(&A[0], b_lo);
+                        const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
+                        if (hi_add) atomicAdd(&A[1], hi_add);
+                        atomicAdd(&A[2], r4.x);
+                        const uint32_t fl = r4.y >> 16;
+                        if (fl & ~A[3]) atomicOr(&A[3], fl);
+                        if (v_start && (uint32_t)v_ns > A[4]) atomicMax(&A[4], (uint32_t)v_ns);
+                        if (v_end && (uint32_t)v_end > A[5]) atomicMax(&A[5], (uint32_t)v_end);
                     }
-                    rs = (rs + 1) & (kRepSlots - 1);
+                }
+                if (is_rep) {
+                    uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&s.rep[rs], kRepEmpty, (uint32_t)tid);
+                        if (old == kRepEmpty) break;
+                        const uint4* O = T + old * kRecChunks;
+                        const uint4 o2 = O[2];
+                        if (eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
+                            eq4_masked(O[1], r1, chunk_mask(1))) {
+                            // Same key.  Fold into that representative with 32-bit shared atomics when the high
+                            // words of the timestamps agree (the common case); otherwise go to the table on our own.
+                            const uint4 r3 = R[3], r4 = R[4], o3 = O[3];
+                            const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+                            const uint64_t v_ns = 0ull - v_start;
+                            const uint64_t o_ns = 0ull - u64_of(o2.z, o2.w), o_end = u64_of(o3.x, o3.y);
+                            const bool ok = (v_start == 0 || (uint32_t)(v_ns >> 32) == (uint32_t)(o_ns >> 32)) &&
+                                            (v_end == 0 || (uint32_t)(v_end >> 32) == (uint32_t)(o_end >> 32));
+                            if (ok) {
+                                is_rep = false;
+                                uint32_t* A = s.acc[old];
+                                const uint32_t b_lo = r3.z, b_hi = r3.w;
+                                const uint32_t prev = atomicAdd(&A[0], b_lo);
+                                const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
+                                if (hi_add) atomicAdd(&A[1], hi_add);
+                                atomicAdd(&A[2], r4.x);
+                                const uint32_t fl = r4.y >> 16;
+                                if (fl) atomicOr(&A[3], fl);
+                                if (v_start) atomicMax(&A[4], (uint32_t)v_ns);
+                                if (v_end) atomicMax(&A[5], (uint32_t)v_end);
+                                atomicAdd(&A[6], 1u);                // duplicates seen: cache candidacy
+                                // exact descriptor compare against the representative (74 bytes, padding masked)
+                                bool same = eq4_masked(O[4], r4, chunk_mask(3));
+#pragma unroll
+                                for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
+                                if (!same) s.tdirty[old] = 1;
+                            }
+                            break;
+                        }
+                        rs = (rs + 1) & (kRepSlots - 1);
+                    }
                 }
             }
-            // CTA-wide list of representatives, so that every warp probes an equal share
+            // team-wide list of representatives, so that every warp probes an equal share
             const uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_rep);
             uint32_t lbase = 0;
             if (lane == 0 && pending) lbase = atomicAdd(&s.nrep, (uint32_t)__popc(pending));
@@ -232,7 +321,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             if (is_rep) s.glist[lbase + __popc(pending & lt_mask)] = (uint8_t)tid;
         }
         FA_PROF_MARK(1);                                           // E phase
-        __syncthreads();                                           // S1: folds, hashes and the list are complete
+        team_sync(team);                                           // S1: folds, hashes and the list are complete
         FA_PROF_MARK(2);                                           // S1 wait
 
         const uint32_t nrep_total = s.nrep;
@@ -272,7 +361,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                     if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[r]] != 0) {
                         unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
                         if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
-                        s.any_dirty = 1;
+                        cs.any_dirty = 1;
                     }
                 }
                 const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, act && !fast && j == 0);
@@ -283,6 +372,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             }
         }
         __syncwarp();
+        if (kProf && lane == 0) { c_reps += k_end - k_begin; c_slow += nslow; }
         FA_PROF_MARK(3);                                           // pipelined first-probe phase
         for (uint32_t base = 0; base < nslow; base += 4) {         // inserts, collisions, in-flight publishes
             const uint32_t k = base + g;
@@ -293,7 +383,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
             const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
             const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0,
-                                               dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &s.any_dirty);
+                                               dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &cs.any_dirty);
             if (act && j == 0) s.res[ri] = got;
             if (act && j == 2) s.fseen[ri] = 0;                     // unknown: issue every reduction
             if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
@@ -303,18 +393,18 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
 
         // ------------------------------------------------------ one lane per flow: totals into registers
         const bool mine = k_begin + lane < k_end;
-        uint32_t my_ridx = 0, my_slot = kResSpill;
-        uint64_t t_bytes = 0, t_ns = 0, t_end = 0;
+        uint32_t my_ridx = 0, my_slot = kResSpill, seen = 0;
+        uint64_t t_bytes = 0, t_ns = 0, t_end = 0, floor_ns = 0;
         uint32_t t_packets = 0, t_flags = 0;
         if (mine) {
             my_ridx = s.glist[k_begin + lane];
             my_slot = s.res[my_ridx];
-            const uint64_t floor_ns = u64_of(s.mir_lo[my_ridx], s.mir_hi[my_ridx]) << 16;   // <= hot.nstart, always
-            const uint32_t seen = s.fseen[my_ridx];
+            floor_ns = u64_of(s.mir_lo[my_ridx], s.mir_hi[my_ridx]) << 16;   // <= hot.nstart, always
+            seen = s.fseen[my_ridx];
             const uint4* R = T + my_ridx * kRecChunks;
             const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
             const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
-            const uint2 a1 = *reinterpret_cast<const uint2*>(&s.acc[my_ridx][4]);
+            const uint4 a1 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][4]);
             const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
             const uint64_t v_ns = 0ull - v_start;
             t_bytes = u64_of(r3.z, r3.w) + u64_of(a0.x, a0.y);
@@ -323,47 +413,44 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             const uint64_t c_ns = u64_of(a1.x, (uint32_t)(v_ns >> 32)), c_end = u64_of(a1.y, (uint32_t)(v_end >> 32));
             t_ns = c_ns > v_ns ? c_ns : v_ns;
             t_end = c_end > v_end ? c_end : v_end;
-            if (t_ns <= floor_ns) t_ns = 0;                        // cannot raise hot.nstart: skip that reduction
-            t_flags &= ~seen;                                      // only flag bits the hot line does not have yet
             *reinterpret_cast<uint4*>(&s.acc[my_ridx][0]) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint2*>(&s.acc[my_ridx][4]) = make_uint2(0, 0);
+            *reinterpret_cast<uint4*>(&s.acc[my_ridx][4]) = make_uint4(0, 0, 0, 0);
             s.tdirty[my_ridx] = 0;
+            // a flow that shows up several times in one tile is hot: give it a cache entry if one is free
+            if (use_cache && a1.z >= kHotMinDups && my_slot != kResSpill) {
+                const uint32_t hh = s.hs[my_ridx];
+                HotEntry& ce = cs.hot[(hh >> 26) & (kHotEntries - 1)];
+                if (*reinterpret_cast<volatile uint32_t*>(&ce.state) == 0u && atomicCAS(&ce.state, 0u, 1u) == 0u) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) ce.line[c] = ld_cg_u4(&t.ident[(size_t)my_slot * 8 + c]);
+                    *reinterpret_cast<uint4*>(&ce.acc[0]) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(&ce.acc[4]) = make_uint4(0, 0, 0, 0);
+                    ce.hash = hh; ce.slot = my_slot;
+                    ce.ns_hi = (uint32_t)(v_ns >> 32); ce.end_hi = (uint32_t)(v_end >> 32);
+                    __threadfence_block();
+                    *reinterpret_cast<volatile uint32_t*>(&ce.state) = 2u;
+                    if (kProf) c_install++;
+                }
+            }
             if (kSketch) {
                 const uint4 r0 = R[0], r1 = R[1];
-                const uint64_t premix = key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
-                                                   u64_of(r1.z, r1.w), u64_of(r2.x, r2.y));
-                const uint64_t a = cms_hash_a(premix, sk.seed), b = cms_hash_b(premix, sk.seed);
-                for (uint32_t d = 0; d < sk.depth; d++)
-                    red_add_u64(sk.cms + ((size_t)d << sk.log2w) + cms_index(a, b, d, sk.log2w), t_packets);
-                const uint64_t hh = hll_hash(premix, sk.seed);
-                const uint32_t idx = (uint32_t)(hh >> (64 - sk.p));
-                const uint64_t rest = hh << sk.p;
-                const uint32_t rho = rest ? (uint32_t)__clzll((long long)rest) + 1u : (64u - sk.p) + 1u;
-                if (__ldcg(&sk.hll[idx]) < rho) red_max_u32(&sk.hll[idx], rho);
+                sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
+                                             u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)), t_packets);
             }
         }
         FA_PROF_MARK(5);                                           // totals
-        __syncthreads();                                           // S2: nobody reads the tile buffer any more
+        team_sync(team);                                           // S2: nobody reads the tile buffer any more
         FA_PROF_MARK(6);                                           // S2 wait
         if (tid == 0) {
             s.nrep = 0;
-            const uint32_t nt = tile_idx + gridDim.x;
+            const uint32_t nt = tile_idx + tile_stride;
             if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, recs, n, nt); }
         }
 
         // ------------------------------------------------------ fire-and-forget reductions on the hot lines
         if (mine) {
             if (my_slot != kResSpill) {
-                uint8_t* hot = reinterpret_cast<uint8_t*>(t.hot) + (size_t)my_slot * kHotBytes;
-                red_add_u64(hot, t_bytes);
-                if (t_ns) red_max_u64(hot + 8, t_ns);
-                if (t_end) red_max_u64(hot + 16, t_end);
-                red_add_u32(hot + 24, t_packets);
-                if (t_flags) {
-                    red_or_u32(hot + 28, t_flags);
-                    red_or_u64(reinterpret_cast<uint8_t*>(&t.ident[(size_t)my_slot * 8 + 2]) + 8,
-                               (unsigned long long)t_flags << TAG_FLAGS_SHIFT);
-                }
+                reduce_to_hot(t, my_slot, t_bytes, t_packets, t_ns, t_end, t_flags, floor_ns, seen);
             } else {                                               // table physically full: spill, never drop silently
                 const unsigned long long kk = atomicAdd(&ctr->scratch[2], 1ull);
                 spill_idx[kk] = first + my_ridx;
@@ -372,23 +459,48 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         }
         FA_PROF_MARK(7);                                           // reductions
     }
-    if (kProf && lane == 0) {
+    if (kProf) {
+        c_cached = __reduce_add_sync(0xFFFFFFFFu, c_cached);
+        c_install = __reduce_add_sync(0xFFFFFFFFu, c_install);
+        if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+            for (int i = 0; i < 8; i++) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+            atomicAdd(&prof[8], (unsigned long long)c_cached);
+            atomicAdd(&prof[9], (unsigned long long)c_reps);
+            atomicAdd(&prof[10], (unsigned long long)c_slow);
+            atomicAdd(&prof[11], (unsigned long long)c_install);
+        }
     }
 
-    // ---------------------------------------------------------- counters
+    // ---------------------------------------------------------- counters + cache flush
     my_inserts = __reduce_add_sync(0xFFFFFFFFu, my_inserts);
     my_spills = __reduce_add_sync(0xFFFFFFFFu, my_spills);
     if (lane == 0) {
-        if (my_inserts) atomicAdd(&s.n_insert, my_inserts);
-        if (my_spills) atomicAdd(&s.n_spill, my_spills);
+        if (my_inserts) atomicAdd(&cs.n_insert, my_inserts);
+        if (my_spills) atomicAdd(&cs.n_spill, my_spills);
     }
-    __syncthreads();
-    if (tid == 0) {
-        if (s.n_insert) atomicAdd(&ctr->live, (unsigned long long)s.n_insert);
-        if (s.n_spill) atomicAdd(&ctr->spills, (unsigned long long)s.n_spill);
-        if (s.any_dirty) *reinterpret_cast<volatile unsigned long long*>(&ctr->dirty) = 1ull;
+    __syncthreads();                                               // every team is out of tiles
+    if (threadIdx.x < kHotEntries) {
+        const HotEntry& ce = cs.hot[threadIdx.x];
+        if (ce.state == 2u) {
+            const uint32_t* A = ce.acc;
+            const uint64_t tag = u64_of(ce.line[2].z, ce.line[2].w);
+            const uint64_t floor_ns = u64_of(ce.line[3].x, ce.line[3].y >> 16) << 16;
+            // ns / end windows: an untouched window (0) reads as a value no larger than the installing
+            // record's own, which the table already holds -> a harmless no-op max.
+            reduce_to_hot(t, ce.slot, u64_of(A[0], A[1]), A[2], u64_of(A[4], ce.ns_hi), u64_of(A[5], ce.end_hi), A[3],
+                          floor_ns, (uint32_t)(tag >> TAG_FLAGS_SHIFT) & 0xFFFFu);
+            if (kSketch) {
+                const uint4 k0 = ce.line[0], k1 = ce.line[1], k2 = ce.line[2];
+                sketch_update(sk, key_premix(u64_of(k0.x, k0.y), u64_of(k0.z, k0.w), u64_of(k1.x, k1.y),
+                                             u64_of(k1.z, k1.w), u64_of(k2.x, k2.y)), A[2]);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (cs.n_insert) atomicAdd(&ctr->live, (unsigned long long)cs.n_insert);
+        if (cs.n_spill) atomicAdd(&ctr->spills, (unsigned long long)cs.n_spill);
+        if (cs.any_dirty) *reinterpret_cast<volatile unsigned long long*>(&ctr->dirty) = 1ull;
     }
 }
 
@@ -493,34 +605,24 @@ __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint
     }
 }
 
-template <int kTile, int kInflight, int kMinBlocks>
-static void launch_variant(const AggLaunch& a, cudaStream_t st) {
+int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
+    if (a.n == 0) return 0;
     static bool attr_done = false;
-    const int smem = (int)sizeof(AggSmem<kTile>);
+    const int smem = (int)sizeof(AggSmem);
     if (!attr_done) {
-        cudaFuncSetAttribute(aggregate_kernel<kTile, kInflight, kMinBlocks, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<kTile, kInflight, kMinBlocks, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<kTile, kInflight, kMinBlocks, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
     const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
-    const int grid = (int)min((uint32_t)(a.sm_count * kMinBlocks), n_tiles);
+    const int grid = (int)min((uint32_t)a.sm_count, (n_tiles + kTeams - 1) / kTeams);
     if (a.prof)
-        aggregate_kernel<kTile, kInflight, kMinBlocks, false, true><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, a.prof, a.opt);
+        aggregate_kernel<false, true><<<grid, kCtaThreads, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, a.prof, a.opt);
     else if (a.sk.cms)
-        aggregate_kernel<kTile, kInflight, kMinBlocks, true, false><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, nullptr, a.opt);
+        aggregate_kernel<true, false><<<grid, kCtaThreads, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, nullptr, a.opt);
     else
-        aggregate_kernel<kTile, kInflight, kMinBlocks, false, false><<<grid, kTile, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, nullptr, a.opt);
-}
-
-int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
-    if (a.n == 0) return 0;
-    switch ((a.opt >> 1) & 3u) {            // FA_K1_OPT bits 1-2: kernel shape experiments
-        case 1:  launch_variant<256, 8, 3>(a, st); break;
-        case 2:  launch_variant<128, 4, 8>(a, st); break;
-        case 3:  launch_variant<128, 8, 6>(a, st); break;
-        default: launch_variant<256, 4, 4>(a, st); break;
-    }
+        aggregate_kernel<false, false><<<grid, kCtaThreads, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, nullptr, a.opt);
     const int fgrid = a.sm_count * 2;
     fixup_scan_kernel<<<fgrid, 256, 0, st>>>(a.recs, a.n, a.table, a.ctr, a.scratch, a.scratch_slots - 1);
     fixup_apply_kernel<<<fgrid, 256, 0, st>>>(a.recs, a.table, a.epoch, a.ctr, a.scratch, a.scratch_slots,

@@ -361,7 +361,7 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     }
     if (const char* ko = getenv("FA_K1_OPT")) e->k1_opt = (uint32_t)strtoul(ko, nullptr, 0);
     if (const char* pp = getenv("FA_PHASE_PROFILE")) {
-        if (pp[0] == '1') { CU(cudaMalloc(&e->d_prof, 8 * 8)); CU(cudaMemsetAsync(e->d_prof, 0, 64, e->stream)); }
+        if (pp[0] == '1') { CU(cudaMalloc(&e->d_prof, 16 * 8)); CU(cudaMemsetAsync(e->d_prof, 0, 128, e->stream)); }
     }
     CU(cudaStreamSynchronize(e->stream));
     *out = e;
@@ -373,14 +373,18 @@ void fa_destroy(fa_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->d_prof) {
-        unsigned long long p[8];
-        if (cudaMemcpy(p, e->d_prof, 64, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        unsigned long long p[16];
+        if (cudaMemcpy(p, e->d_prof, 128, cudaMemcpyDeviceToHost) == cudaSuccess) {
             static const char* names[8] = {"tile wait", "hash+elect+fold", "S1 barrier", "pipelined probe", "general probe",
                                            "totals", "S2 barrier", "reductions"};
             double tot = 0; for (int i = 0; i < 8; i++) tot += (double)p[i];
             fprintf(stderr, "[flowagg] K1 phase profile (warp-cycles):");
             for (int i = 0; i < 8; i++) fprintf(stderr, " %s %.1f%%;", names[i], tot > 0 ? 100.0 * p[i] / tot : 0.0);
             fprintf(stderr, " total %.3g\n", tot);
+            fprintf(stderr, "[flowagg] K1 records %llu: cache hits %.1f%%, representatives %.1f%% (general-loop %.2f%%), cache installs %llu\n",
+                    (unsigned long long)e->st.records_ingested, 100.0 * p[8] / (double)std::max<uint64_t>(1, e->st.records_ingested),
+                    100.0 * p[9] / (double)std::max<uint64_t>(1, e->st.records_ingested),
+                    100.0 * p[10] / (double)std::max<uint64_t>(1, e->st.records_ingested), p[11]);
         }
         cudaFree(e->d_prof);
     }
