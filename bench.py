@@ -156,41 +156,27 @@ def run_ours(args, wl):
     ring = max(1, min(args.ring, args.steps + args.warmup))
     stream = torch.cuda.current_stream()
     eng = fa.FlowAggEngine(args.max_entries, device=local, max_batch=args.max_batch, cuda_stream=stream.cuda_stream)
-    gp = fa.GenParams(seed=wl["seed"] + 1000 * rank, n_keys=wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100,
+    # one key universe for the whole job; every rank generates its own slice of the record stream
+    gp = fa.GenParams(seed=wl["seed"], n_keys=wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100,
                       t0_ns=1_000_000, varying_desc=0)
     batches = []
     for i in range(ring):
         t = torch.empty(B * REC, dtype=torch.uint8, device=dev)
-        eng.gen_records(gp, i * B, B, t)
+        eng.gen_records(gp, (i * world + rank) * B, B, t)
         batches.append(t)
     eng.sync()
 
     if world > 1:
-        send = torch.empty(args.max_batch * REC, dtype=torch.uint8, device=dev)
-        recv = torch.empty(int(args.max_batch * 1.5) * REC, dtype=torch.uint8, device=dev)
-        cnt_out = torch.empty(world, dtype=torch.int64, device=dev)
+        from netobserv_ebpf_agent_b200.sharded import ShardedAggregator
+        agg = ShardedAggregator(eng, args.max_batch, dev)   # K3 route -> NCCL all-to-all -> K1 on the owner
 
     def step(i):
         src = batches[i % ring]
         if world == 1:
             rc, took = eng.ingest(src.data_ptr(), B)
             assert rc == 0 and took == B, (rc, took)
-            return
-        done = 0
-        while done < B:                               # K3 route -> all-to-all -> K1 on the owner
-            c = min(args.max_batch, B - done)
-            counts = eng.route(src.data_ptr() + done * REC, c, world, send)
-            cnt_in = torch.from_numpy(counts.astype(np.int64)).to(dev)
-            dist.all_to_all_single(cnt_out, cnt_in)
-            outc = cnt_out.cpu().numpy()
-            tot = int(outc.sum())
-            assert tot * REC <= recv.numel(), "receive buffer too small"
-            dist.all_to_all_single(recv[: tot * REC], send[: c * REC],
-                                   output_split_sizes=[int(x) * REC for x in outc],
-                                   input_split_sizes=[int(x) * REC for x in counts])
-            rc, took = eng.ingest(recv.data_ptr(), tot)
-            assert rc == 0 and took == tot, (rc, took)
-            done += c
+        else:
+            agg.ingest(src, B)
 
     def barrier():
         if world > 1:

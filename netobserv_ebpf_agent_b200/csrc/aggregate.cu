@@ -130,10 +130,14 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
         const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq4_masked(line, rchunk, cmask)) >> (g * 8)) & 0xFFu;
         const uint32_t state = (uint32_t)(tag & TAG_STATE_MASK);
         unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[slot * 8 + 2]) + 1;
+        // Claim either an empty slot, or the base of a flow that so far exists only through feature
+        // samples (no TAG_HAS_BASE: its first base record is adopted whole, pkg/flow/account.go:95).
+        const bool base_claim = state == (uint32_t)TAG_PUBLISHED && !(tag & TAG_HAS_BASE) && (eqb & 0x07u) == 0x07u;
         uint32_t won = 0;
-        if (!done && state == 0 && j == 2) {
+        if (!done && (state == 0 || base_claim) && j == 2) {
+            const unsigned long long expect = state == 0 ? 0ull : (unsigned long long)tag;
             const unsigned long long want = (epoch << TAG_EPOCH_SHIFT) | TAG_HAS_BASE | TAG_CLAIMED;
-            won = atomicCAS(tagp, 0ull, want) == 0ull ? 1u : 0u;
+            won = atomicCAS(tagp, expect, want) == expect ? (state == 0 ? 1u : 2u) : 0u;
         }
         won = __shfl_sync(0xFFFFFFFFu, won, g * 8 + 2);
         if (won) {
@@ -153,11 +157,11 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
                 const unsigned long long pub = (epoch << TAG_EPOCH_SHIFT) | TAG_HAS_BASE | TAG_PUBLISHED |
                                                (cta_dirty ? TAG_DIRTY : 0ull);
                 *reinterpret_cast<volatile unsigned long long*>(tagp) = pub;
-                my_inserts++;
+                if (won == 1u) my_inserts++;                   // a base claim does not add a flow
                 if (cta_dirty) *any_dirty = 1;
             }
             hit = true;
-        } else if (!done && state == (uint32_t)TAG_PUBLISHED) {
+        } else if (!done && state == (uint32_t)TAG_PUBLISHED && !base_claim) {
             const bool born_now = (tag >> TAG_EPOCH_SHIFT) == epoch;
             if (born_now && reload_slot != slot) {
                 // published during this launch: the chunks read together with the tag may predate
@@ -351,7 +355,8 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
                 bool eq = eq4_masked(line[r], rchunk, cmask);
                 const uint64_t tag = u64_of(line[r].z, line[r].w);  // meaningful in lane j == 2 only
-                if (j == 2) eq = eq && (tag & TAG_STATE_MASK) == TAG_PUBLISHED && (tag >> TAG_EPOCH_SHIFT) != epoch;
+                if (j == 2) eq = eq && (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                                 (tag >> TAG_EPOCH_SHIFT) != epoch;
                 const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq) >> (g * 8)) & 0xFFu;
                 const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches at its home slot
                 if (fast && j == 0) s.res[ridx[r]] = slot[r];

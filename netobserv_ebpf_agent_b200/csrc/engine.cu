@@ -127,6 +127,10 @@ struct fa_engine {
     uint32_t* d_cut_bitmap = nullptr; uint32_t* d_cut_out = nullptr; uint32_t* h_cut_out = nullptr;
 
     uint8_t* d_evict = nullptr; uint64_t evict_cap = 0;
+    uint8_t* d_evict_dns = nullptr; uint8_t* d_evict_add = nullptr; uint8_t* d_evict_present = nullptr;
+    uint32_t* d_slot_of_out = nullptr; uint64_t feat_evict_cap = 0;
+    uint32_t* d_slot_of = nullptr;            // per-sample slot scratch of the feature folds
+    uint64_t feat_seq[2] = {0, 0};            // running sample numbers (additional, dns)
     uint32_t* d_route_tmp = nullptr; unsigned long long* d_route_counts = nullptr;
 
     fa::SketchParams sk{};
@@ -276,6 +280,11 @@ int ingest_host(fa_engine* e, const uint8_t* h_recs, size_t n, size_t* consumed,
 
 }  // namespace
 
+static uint64_t e_max_batch_tmp(const fa_config* cfg) {
+    uint64_t mb = cfg->max_batch ? cfg->max_batch : (1ull << 22);
+    return mb > (1ull << 28) ? (1ull << 28) : mb;
+}
+
 extern "C" {
 
 uint32_t fa_abi_version(void) { return FA_ABI_VERSION; }
@@ -317,6 +326,15 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     CU(cudaMalloc(&e->table.hot, slots * fa::kHotBytes));
     CU(cudaMemsetAsync(e->table.ident, 0, slots * fa::kIdentBytes, e->stream));
     CU(cudaMemsetAsync(e->table.hot, 0, slots * fa::kHotBytes, e->stream));
+    if (cfg->flags & FA_F_ENABLE_RTT) {
+        CU(cudaMalloc(&e->table.feat_add, slots * 80));
+        CU(cudaMemsetAsync(e->table.feat_add, 0, slots * 80, e->stream));
+    }
+    if (cfg->flags & FA_F_ENABLE_DNS) {
+        CU(cudaMalloc(&e->table.feat_dns, slots * 128));
+        CU(cudaMemsetAsync(e->table.feat_dns, 0, slots * 128, e->stream));
+    }
+    if (cfg->flags & (FA_F_ENABLE_RTT | FA_F_ENABLE_DNS)) CU(cudaMalloc(&e->d_slot_of, e_max_batch_tmp(cfg) * 4));
     CU(cudaMalloc(&e->d_ctr, sizeof(fa::Counters)));
     CU(cudaMemsetAsync(e->d_ctr, 0, sizeof(fa::Counters), e->stream));
     CU(cudaHostAlloc(&e->h_ctr, sizeof(fa::Counters), cudaHostAllocDefault));
@@ -401,6 +419,7 @@ void fa_destroy(fa_engine* e) {
     cudaFree(e->d_scratch); cudaFree(e->d_spill_idx); cudaFree(e->d_cut_set); cudaFree(e->d_cut_bitmap); cudaFree(e->d_cut_out);
     if (e->h_cut_out) cudaFreeHost(e->h_cut_out);
     cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts);
+    cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out); cudaFree(e->d_slot_of);
     cudaFree(e->sk.cms); cudaFree(e->sk.hll);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -425,14 +444,49 @@ int fa_ingest(fa_engine* e, const void* recs, size_t n, size_t* consumed) {
     return ingest_host(e, static_cast<const uint8_t*>(recs), n, consumed, k == PTR_PINNED);
 }
 
-int fa_ingest_additional(fa_engine* e, const void*, size_t) {
-    if (!e) return fail(FA_E_INVAL, "fa_ingest_additional: null engine");
-    return fail(FA_E_INVAL, "fa_ingest_additional: engine was created without FA_F_ENABLE_RTT");
+static int ingest_feature(fa_engine* e, int kind, const void* recs, size_t n, const char* who) {
+    const uint32_t flag = kind == 0 ? FA_F_ENABLE_RTT : FA_F_ENABLE_DNS;
+    if (!e) return fail(FA_E_INVAL, "%s: null engine", who);
+    if (!(e->cfg.flags & flag)) return fail(FA_E_INVAL, "%s: engine was created without %s", who, kind == 0 ? "FA_F_ENABLE_RTT" : "FA_F_ENABLE_DNS");
+    if (n == 0) return FA_OK;
+    if (!recs) return fail(FA_E_INVAL, "%s: null records", who);
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    const size_t rec_bytes = kind == 0 ? fa::kAddRecBytes : fa::kDnsRecBytes;
+    const PtrKind k = classify(recs);
+    if (k == PTR_DEVICE && (reinterpret_cast<uintptr_t>(recs) & 7)) return fail(FA_E_INVAL, "%s: device records must be 8-byte aligned", who);
+    // feature samples may create flows: never let the table pass 7/8 of its slots
+    int rc = sync_counters(e);
+    if (rc) return rc;
+    if (e->live_known + n > e->slots - e->slots / 8)
+        return fail(FA_E_2BIG, "%s: %zu samples could overfill the flow table (%llu live of %llu slots): evict first", who, n,
+                    (unsigned long long)e->live_known, (unsigned long long)e->slots);
+    if (k != PTR_DEVICE && !e->d_stage[0]) CU(cudaMalloc(&e->d_stage[0], e->max_batch * fa::kRecBytes));
+    size_t done = 0;
+    while (done < n) {
+        const uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
+        const uint8_t* src = static_cast<const uint8_t*>(recs) + done * rec_bytes;
+        const uint8_t* d = src;
+        if (k != PTR_DEVICE) {
+            CU(cudaMemcpyAsync(e->d_stage[0], src, (size_t)c * rec_bytes, cudaMemcpyHostToDevice, e->stream));
+            CU(cudaStreamSynchronize(e->stream));          // the caller's buffer is not referenced after return
+            e->st.h2d_bytes += (size_t)c * rec_bytes;
+            d = e->d_stage[0];
+        }
+        e->st.kernel_launches += fa::launch_feature_fold(kind, d, c, e->table, ++e->epoch, e->feat_seq[kind], e->d_slot_of,
+                                                         e->d_ctr, e->sm_count, e->stream);
+        CU(cudaGetLastError());
+        e->feat_seq[kind] += c;
+        e->unsynced_records += c;
+        if (kind == 0) e->st.additional_ingested += c; else e->st.dns_ingested += c;
+        if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->stream));   // d_stage[0] is reused by the next chunk
+        done += c;
+    }
+    return FA_OK;
 }
-int fa_ingest_dns(fa_engine* e, const void*, size_t) {
-    if (!e) return fail(FA_E_INVAL, "fa_ingest_dns: null engine");
-    return fail(FA_E_INVAL, "fa_ingest_dns: engine was created without FA_F_ENABLE_DNS");
-}
+
+int fa_ingest_additional(fa_engine* e, const void* recs, size_t n) { return ingest_feature(e, 0, recs, n, "fa_ingest_additional"); }
+int fa_ingest_dns(fa_engine* e, const void* recs, size_t n) { return ingest_feature(e, 1, recs, n, "fa_ingest_dns"); }
 
 int fa_live_flows(fa_engine* e, size_t* n) {
     if (!e || !n) return fail(FA_E_INVAL, "fa_live_flows: null argument");
@@ -457,6 +511,7 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
     if (live == 0) return FA_OK;
     if (!out_records) return fail(FA_E_INVAL, "fa_evict: null out_records");
     if (cap < live) return fail(FA_E_2BIG, "fa_evict: capacity %zu < %llu live flows", cap, (unsigned long long)live);
+    const bool feats = e->table.feat_add || e->table.feat_dns;
     const PtrKind k = classify(out_records);
     uint8_t* d_out = nullptr;
     if (k == PTR_DEVICE) {
@@ -470,21 +525,47 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
         }
         d_out = e->d_evict;
     }
+    // feature outputs are staged on the device unless the caller handed device pointers
+    uint8_t *d_dns = nullptr, *d_add = nullptr, *d_pres = nullptr;
+    if (feats) {
+        if (e->feat_evict_cap < live) {
+            cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out);
+            e->d_evict_dns = e->d_evict_add = e->d_evict_present = nullptr; e->d_slot_of_out = nullptr; e->feat_evict_cap = 0;
+            uint64_t want = std::max<uint64_t>(live, std::min<uint64_t>(e->cfg.max_entries, live * 2));
+            CU(cudaMalloc(&e->d_evict_dns, want * 64)); CU(cudaMalloc(&e->d_evict_add, want * 32));
+            CU(cudaMalloc(&e->d_evict_present, want)); CU(cudaMalloc(&e->d_slot_of_out, want * 4));
+            e->feat_evict_cap = want;
+        }
+        d_dns = out_dns ? (classify(out_dns) == PTR_DEVICE ? static_cast<uint8_t*>(out_dns) : e->d_evict_dns) : nullptr;
+        d_add = out_additional ? (classify(out_additional) == PTR_DEVICE ? static_cast<uint8_t*>(out_additional) : e->d_evict_add) : nullptr;
+        d_pres = out_present ? (classify(out_present) == PTR_DEVICE ? out_present : e->d_evict_present) : nullptr;
+    }
     CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
-    e->st.kernel_launches += fa::launch_evict(e->table, reinterpret_cast<uint4*>(d_out), nullptr, nullptr, nullptr, live,
+    e->st.kernel_launches += fa::launch_evict(e->table, reinterpret_cast<uint4*>(d_out), feats ? e->d_slot_of_out : nullptr, live,
                                               e->d_ctr, e->sm_count, e->stream);
+    if (feats)
+        e->st.kernel_launches += fa::launch_evict_features(e->table, e->d_slot_of_out, live, d_out, d_dns, d_add, d_pres,
+                                                           e->sm_count, e->stream);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(&e->d_ctr->live, 0, sizeof(unsigned long long), e->stream));
     if (k != PTR_DEVICE) {
         CU(cudaMemcpyAsync(out_records, d_out, live * fa::kRecBytes, cudaMemcpyDeviceToHost, e->stream));
         e->st.d2h_bytes += live * fa::kRecBytes;
     }
+    if (feats) {
+        if (out_dns && d_dns == e->d_evict_dns) { CU(cudaMemcpyAsync(out_dns, d_dns, live * 64, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += live * 64; }
+        if (out_additional && d_add == e->d_evict_add) { CU(cudaMemcpyAsync(out_additional, d_add, live * 32, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += live * 32; }
+        if (out_present && d_pres == e->d_evict_present) { CU(cudaMemcpyAsync(out_present, d_pres, live, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += live; }
+    }
     CU(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(fa::Counters), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (e->h_ctr->evict_out != live)
         return fail(FA_E_CUDA, "fa_evict: table scan found %llu flows, counter says %llu", (unsigned long long)e->h_ctr->evict_out, (unsigned long long)live);
-    if (out_present) memset(out_present, 0, live);
-    (void)out_dns; (void)out_additional;
+    if (!feats) {
+        if (out_present && classify(out_present) != PTR_DEVICE) memset(out_present, 0, live);
+        if (out_dns && classify(out_dns) != PTR_DEVICE) memset(out_dns, 0, live * 64);
+        if (out_additional && classify(out_additional) != PTR_DEVICE) memset(out_additional, 0, live * 32);
+    }
     e->live_known = 0; e->unsynced_records = 0; e->ring_head = e->ring_tail;
     e->st.flows_evicted += live;
     *n_out = (size_t)live;

@@ -11,8 +11,7 @@
 namespace fa {
 
 __global__ void __launch_bounds__(256)
-evict_kernel(Table t, uint4* __restrict__ out, uint8_t* __restrict__ out_dns, uint8_t* __restrict__ out_add,
-             uint8_t* __restrict__ out_present, unsigned long long cap, Counters* ctr) {
+evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_out, unsigned long long cap, Counters* ctr) {
     const int lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
     const uint64_t slots = t.mask + 1;
     const uint64_t quads = slots >> 2;                 // slots is a power of two >= 4
@@ -49,7 +48,7 @@ evict_kernel(Table t, uint4* __restrict__ out, uint8_t* __restrict__ out_dns, ui
             } else {
                 O[j + 1] = line;                                        // desc[8..72)
             }
-            if (out_present && j == 0) out_present[idx] = 0;            // feature folds: filled by the feature evict pass
+            if (slot_of_out && j == 0) slot_of_out[idx] = (uint32_t)slot;   // for the feature pass
         }
         // delete: tag -> EMPTY, hot line -> identity
         if (live && j == 2) *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(&t.ident[slot * 8 + 2]) + 8) = make_uint2(0u, 0u);
@@ -57,9 +56,9 @@ evict_kernel(Table t, uint4* __restrict__ out, uint8_t* __restrict__ out_dns, ui
     }
 }
 
-int launch_evict(const Table& table, uint4* out_recs, uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present,
+int launch_evict(const Table& table, uint4* out_recs, uint32_t* slot_of_out,
                  unsigned long long cap, Counters* ctr, int sm_count, cudaStream_t st) {
-    evict_kernel<<<sm_count * 8, 256, 0, st>>>(table, out_recs, out_dns, out_add, out_present, cap, ctr);
+    evict_kernel<<<sm_count * 8, 256, 0, st>>>(table, out_recs, slot_of_out, cap, ctr);
     return 1;
 }
 

@@ -1,0 +1,250 @@
+// features.cu — K6: per-flow folds of the feature streams the reference keeps in per-CPU BPF maps.
+//
+//   additional_metrics (RTT / IPsec): bpf/rtt_tracker.h:12-22,73-91 + AccumulateAdditional
+//                                     (pkg/model/flow_content.go:154-177)
+//   dns_metrics:                      bpf/flows.c:145-158,291-330 + AccumulateDNS (flow_content.go:76-96)
+//   base effects of both:             buildBaseFromAdditional (flow_content.go:63-74)
+//   merged view at eviction:          LookupAndDeleteMap (pkg/tracer/tracer.go:1098-1151,1159-1187)
+//
+// Contract (SURVEY.md §8 a12'): every sample is folded as if it were one per-CPU slot, in stream
+// order.  Order-independent parts use plain atomics (rtt / latency = max, flags = or, start = min
+// non-zero, end = max; IPsec: max return code, "encrypted" = or over the samples holding that max).
+// Order-dependent parts are made exact with a 64-bit running sample number packed into the atomic:
+//   first sample of a flow (its block is adopted whole)   -> max of ~seq, then a second pass copies it
+//   dns id = last non-zero, errno = last                   -> max of (seq+1)<<16 | value
+//   eth_protocol handed to an empty base = first non-zero  -> max of ~(seq<<16 | eth)
+// A flow seen only through a feature stream gets a table entry without TAG_HAS_BASE
+// (tracer.go:1179-1182: an all-zero base); K1 adopts the first base record whole when it arrives.
+#include "kernels.cuh"
+
+namespace fa {
+
+// ---- per-slot state, all-zero == empty ------------------------------------------------------
+// additional: 5 x uint4 (80 B)
+//   [ 0] nfirst = max ~seq            [ 8] rtt max
+//   [16] ipsec  = max (ret ^ 0x80000000) << 1 | enc          [24] nfs = max(0 - start)   (base effect)
+//   [32] fe = max end (base effect)   [40] neth = max ~(seq << 16 | eth)  over eth != 0  (base effect)
+//   [48] first.start                  [56] first.end
+//   [64] first.eth (u16) ...
+// dns: 8 x uint4 (128 B)
+//   [ 0] nfirst                       [ 8] latency max
+//   [16] id_last  = max (seq+1) << 16 | id   over id != 0     [24] errno_last = max (seq+1) << 16 | errno
+//   [32] nfs                          [40] fe
+//   [48] neth                         [56] flags (or, u32) | first.eth (u16 @60)
+//   [64] first.start                  [72] first.end          [80..112) first.name[32]   [112..128) spare
+constexpr int kAddState = 5;    // uint4 per slot
+constexpr int kDnsState = 8;
+
+__device__ __forceinline__ uint64_t ld_u64_unaligned8(const uint8_t* p) { return *reinterpret_cast<const uint64_t*>(p); }
+
+// Find the flow's slot, creating a feature-only entry when the key is new.  One thread per sample.
+__device__ uint32_t find_or_create(const Table& t, uint64_t epoch, const uint64_t k[5], unsigned long long* n_created) {
+    const uint64_t kk4 = k[4] & 0x00FFFFFFFFFFFFFFull;
+    const uint64_t h = slot_hash(key_premix(k[0], k[1], k[2], k[3], k[4]));
+    uint64_t slot = h & t.mask;
+    for (uint32_t probes = 0; probes < 65536; ) {
+        unsigned long long* L = reinterpret_cast<unsigned long long*>(&t.ident[slot * 8]);
+        unsigned long long* tagp = L + 5;
+        unsigned long long tag = ld_cg_u64(tagp);
+        const uint32_t state = (uint32_t)(tag & TAG_STATE_MASK);
+        if (state == 0) {
+            if (atomicCAS(tagp, 0ull, TAG_CLAIMED) == 0ull) {
+                // key, then an all-zero descriptor (the base is empty until a base record arrives)
+                L[0] = k[0]; L[1] = k[1]; L[2] = k[2]; L[3] = k[3]; L[4] = kk4;
+#pragma unroll
+                for (int c = 6; c < 16; c++) L[c] = 0ull;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long*>(tagp) = TAG_PUBLISHED;   // no TAG_HAS_BASE, epoch 0
+                atomicAdd(n_created, 1ull);
+                return (uint32_t)slot;
+            }
+            continue;                                   // lost the race: look at the slot again
+        }
+        if (state == (uint32_t)TAG_CLAIMED) continue;   // being published by someone else
+        __threadfence();                                // order the key reads after the tag observation
+        if (ld_cg_u64(L) == k[0] && ld_cg_u64(L + 1) == k[1] && ld_cg_u64(L + 2) == k[2] && ld_cg_u64(L + 3) == k[3] &&
+            (ld_cg_u64(L + 4) & 0x00FFFFFFFFFFFFFFull) == kk4)
+            return (uint32_t)slot;
+        slot = (slot + 1) & t.mask;
+        probes++;
+    }
+    return 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ void load_key(const uint8_t* rec, uint64_t k[5]) {
+#pragma unroll
+    for (int i = 0; i < 5; i++) k[i] = ld_u64_unaligned8(rec + 8 * i);    // records are 8-byte aligned (72 / 104 B)
+}
+
+__global__ void additional_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, uint64_t seq0,
+                                       uint32_t* __restrict__ slot_of, Counters* ctr) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint8_t* R = recs + (size_t)i * kAddRecBytes;
+        uint64_t k[5]; load_key(R, k);
+        const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
+        slot_of[i] = slot;
+        if (slot == 0xFFFFFFFFu) { atomicAdd(&ctr->spills, 1ull); continue; }
+        const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48), rtt = ld_u64_unaligned8(R + 56);
+        const uint32_t ret = *reinterpret_cast<const uint32_t*>(R + 64);
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(R + 68);         // eth u16 | enc u8 | pad
+        const uint32_t eth = w & 0xFFFFu, enc = ((w >> 16) & 0xFFu) ? 1u : 0u;
+        const uint64_t seq = seq0 + i;
+        uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_add) + (size_t)slot * (kAddState * 16);
+        red_max_u64(S + 0, ~seq);
+        if (rtt) red_max_u64(S + 8, rtt);
+        red_max_u64(S + 16, ((uint64_t)(ret ^ 0x80000000u) << 1) | enc | (1ull << 40));   // bit 40: "has a sample"
+        if (start) red_max_u64(S + 24, 0ull - start);
+        if (end) red_max_u64(S + 32, end);
+        if (eth) red_max_u64(S + 40, ~((seq << 16) | eth));
+    }
+}
+// second pass: the sample that turned out to be the flow's first one writes the adopted block fields
+__global__ void additional_first_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t seq0,
+                                        const uint32_t* __restrict__ slot_of) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = slot_of[i];
+        if (slot == 0xFFFFFFFFu) continue;
+        uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_add) + (size_t)slot * (kAddState * 16);
+        if (*reinterpret_cast<const uint64_t*>(S) != ~(seq0 + i)) continue;
+        const uint8_t* R = recs + (size_t)i * kAddRecBytes;
+        *reinterpret_cast<uint64_t*>(S + 48) = ld_u64_unaligned8(R + 40);
+        *reinterpret_cast<uint64_t*>(S + 56) = ld_u64_unaligned8(R + 48);
+        *reinterpret_cast<uint32_t*>(S + 64) = *reinterpret_cast<const uint32_t*>(R + 68) & 0xFFFFu;
+    }
+}
+
+__global__ void dns_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, uint64_t seq0,
+                                uint32_t* __restrict__ slot_of, Counters* ctr) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint8_t* R = recs + (size_t)i * kDnsRecBytes;
+        uint64_t k[5]; load_key(R, k);
+        const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
+        slot_of[i] = slot;
+        if (slot == 0xFFFFFFFFu) { atomicAdd(&ctr->spills, 1ull); continue; }
+        const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48), lat = ld_u64_unaligned8(R + 56);
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(R + 64);        // id u16 | flags u16
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(R + 68);        // eth u16 | errno u8 | name[0]
+        const uint32_t id = w0 & 0xFFFFu, flags = w0 >> 16, eth = w1 & 0xFFFFu, err = (w1 >> 16) & 0xFFu;
+        const uint64_t seq = seq0 + i;
+        uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_dns) + (size_t)slot * (kDnsState * 16);
+        red_max_u64(S + 0, ~seq);
+        if (lat) red_max_u64(S + 8, lat);
+        if (id) red_max_u64(S + 16, ((seq + 1) << 16) | id);
+        red_max_u64(S + 24, ((seq + 1) << 16) | err);
+        if (start) red_max_u64(S + 32, 0ull - start);
+        if (end) red_max_u64(S + 40, end);
+        if (eth) red_max_u64(S + 48, ~((seq << 16) | eth));
+        if (flags) red_or_u32(S + 56, flags);
+    }
+}
+__global__ void dns_first_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t seq0,
+                                 const uint32_t* __restrict__ slot_of) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = slot_of[i];
+        if (slot == 0xFFFFFFFFu) continue;
+        uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_dns) + (size_t)slot * (kDnsState * 16);
+        if (*reinterpret_cast<const uint64_t*>(S) != ~(seq0 + i)) continue;
+        const uint8_t* R = recs + (size_t)i * kDnsRecBytes;
+        *reinterpret_cast<uint16_t*>(S + 60) = *reinterpret_cast<const uint16_t*>(R + 68);    // first.eth
+        *reinterpret_cast<uint64_t*>(S + 64) = ld_u64_unaligned8(R + 40);
+        *reinterpret_cast<uint64_t*>(S + 72) = ld_u64_unaligned8(R + 48);
+        for (int b = 0; b < 32; b++) S[80 + b] = R[71 + b];                                    // name[32] at +31 of dns_metrics
+    }
+}
+
+int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& t, uint64_t epoch, uint64_t seq0,
+                        uint32_t* slot_of, Counters* ctr, int sm_count, cudaStream_t st) {
+    if (!n) return 0;
+    const int grid = sm_count * 8;
+    if (kind == 0) {
+        additional_fold_kernel<<<grid, 256, 0, st>>>(recs, n, t, epoch, seq0, slot_of, ctr);
+        additional_first_kernel<<<grid, 256, 0, st>>>(recs, n, t, seq0, slot_of);
+    } else {
+        dns_fold_kernel<<<grid, 256, 0, st>>>(recs, n, t, epoch, seq0, slot_of, ctr);
+        dns_first_kernel<<<grid, 256, 0, st>>>(recs, n, t, seq0, slot_of);
+    }
+    return 2;
+}
+
+// ---- eviction: patch the base with the feature effects, emit and clear the feature blocks -----------
+__device__ __forceinline__ void build_base(uint64_t& bs, uint64_t& be, uint32_t& beth, uint64_t nfs, uint64_t fe, uint64_t neth) {
+    // buildBaseFromAdditional (flow_content.go:63-74) with the fold of all samples of one feature
+    const uint64_t s = 0ull - nfs;                       // min non-zero start of the samples, 0 if none
+    if (bs == 0 || (bs > s && s != 0)) bs = s;
+    if (be == 0 || be < fe) be = fe;
+    if (beth == 0 && neth != 0) beth = (uint32_t)(~neth) & 0xFFFFu;
+}
+
+__global__ void evict_features_kernel(Table t, const uint32_t* __restrict__ slot_of_out, unsigned long long n_out,
+                                      uint8_t* __restrict__ out_recs, uint8_t* __restrict__ out_dns,
+                                      uint8_t* __restrict__ out_add, uint8_t* __restrict__ out_present) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_out;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t slot = slot_of_out[i];
+        uint8_t* O = out_recs + i * kRecBytes;
+        uint64_t bs = *reinterpret_cast<uint64_t*>(O + R_START), be = *reinterpret_cast<uint64_t*>(O + R_END);
+        uint32_t beth = *reinterpret_cast<uint16_t*>(O + R_ETH);
+        uint8_t present = 0;
+        if (t.feat_dns) {                                 // DNS first, then additional: tracer.go:1098-1106,1143-1151
+            uint64_t* S = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(t.feat_dns) + (size_t)slot * (kDnsState * 16));
+            if (S[0] != 0) {
+                present |= 1;
+                build_base(bs, be, beth, S[4], S[5], S[6]);
+                if (out_dns) {
+                    uint8_t* D = out_dns + i * 64;
+                    const uint8_t* Sb = reinterpret_cast<const uint8_t*>(S);
+                    *reinterpret_cast<uint64_t*>(D + 0) = S[8];                              // first.start
+                    *reinterpret_cast<uint64_t*>(D + 8) = S[9];                              // first.end
+                    *reinterpret_cast<uint64_t*>(D + 16) = S[1];                             // latency max
+                    *reinterpret_cast<uint16_t*>(D + 24) = (uint16_t)(S[2] & 0xFFFFu);       // id: last non-zero
+                    *reinterpret_cast<uint16_t*>(D + 26) = (uint16_t)(*reinterpret_cast<const uint32_t*>(Sb + 56));  // flags
+                    *reinterpret_cast<uint16_t*>(D + 28) = *reinterpret_cast<const uint16_t*>(Sb + 60);              // first.eth
+                    D[30] = (uint8_t)(S[3] & 0xFFu);                                         // errno: last
+                    for (int b = 0; b < 32; b++) D[31 + b] = Sb[80 + b];
+                    D[63] = 0;
+                }
+#pragma unroll
+                for (int c = 0; c < 16; c++) S[c] = 0ull;
+            } else if (out_dns) {
+                for (int c = 0; c < 8; c++) reinterpret_cast<uint64_t*>(out_dns + i * 64)[c] = 0ull;
+            }
+        }
+        if (t.feat_add) {
+            uint64_t* S = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(t.feat_add) + (size_t)slot * (kAddState * 16));
+            if (S[0] != 0) {
+                present |= 2;
+                build_base(bs, be, beth, S[3], S[4], S[5]);
+                if (out_add) {
+                    uint8_t* A = out_add + i * 32;
+                    *reinterpret_cast<uint64_t*>(A + 0) = S[6];                              // first.start
+                    *reinterpret_cast<uint64_t*>(A + 8) = S[7];                              // first.end
+                    *reinterpret_cast<uint64_t*>(A + 16) = S[1];                             // rtt max
+                    const uint64_t ip = S[2];
+                    *reinterpret_cast<uint32_t*>(A + 24) = (uint32_t)((ip >> 1) & 0xFFFFFFFFu) ^ 0x80000000u;
+                    *reinterpret_cast<uint16_t*>(A + 28) = (uint16_t)(S[8] & 0xFFFFu);       // first.eth
+                    A[30] = (uint8_t)(ip & 1u);
+                    A[31] = 0;
+                }
+#pragma unroll
+                for (int c = 0; c < 10; c++) S[c] = 0ull;
+            } else if (out_add) {
+                for (int c = 0; c < 4; c++) reinterpret_cast<uint64_t*>(out_add + i * 32)[c] = 0ull;
+            }
+        }
+        if (present) {
+            *reinterpret_cast<uint64_t*>(O + R_START) = bs;
+            *reinterpret_cast<uint64_t*>(O + R_END) = be;
+            *reinterpret_cast<uint16_t*>(O + R_ETH) = (uint16_t)beth;
+        }
+        if (out_present) out_present[i] = present;
+    }
+}
+
+int launch_evict_features(const Table& t, const uint32_t* slot_of_out, unsigned long long n_out, uint8_t* out_recs,
+                          uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present, int sm_count, cudaStream_t st) {
+    if (!n_out) return 0;
+    evict_features_kernel<<<sm_count * 8, 256, 0, st>>>(t, slot_of_out, n_out, out_recs, out_dns, out_add, out_present);
+    return 1;
+}
+
+}  // namespace fa

@@ -45,7 +45,8 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st);
 
 // K2: lookup-and-delete every live flow of `table` into out_recs (device pointer, cap records).
 // The number found is left in ctr->evict_out (can exceed cap; only cap are written).
-int launch_evict(const Table& table, uint4* out_recs, uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present,
+// slot_of_out (optional): receives the table slot of every emitted flow, for the feature pass.
+int launch_evict(const Table& table, uint4* out_recs, uint32_t* slot_of_out,
                  unsigned long long cap, Counters* ctr, int sm_count, cudaStream_t st);
 
 // Overflow pre-pass (ACCOUNTER "full" cut, reference pkg/flow/account.go:85-94): finds the index of the
@@ -55,6 +56,12 @@ int launch_evict(const Table& table, uint4* out_recs, uint8_t* out_dns, uint8_t*
 int launch_full_cut(const uint4* recs, uint32_t n, const Table& table, unsigned long long live,
                     unsigned long long max_entries, uint32_t* idx_set, uint32_t set_slots, uint32_t* bitmap,
                     uint32_t* cut_out, int sm_count, cudaStream_t st);
+
+// K6 feature folds (kind 0 = additional_metrics 72-B records, 1 = dns_metrics 104-B records); slot_of: n u32 scratch
+int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& t, uint64_t epoch, uint64_t seq0,
+                        uint32_t* slot_of, Counters* ctr, int sm_count, cudaStream_t st);
+int launch_evict_features(const Table& t, const uint32_t* slot_of_out, unsigned long long n_out, uint8_t* out_recs,
+                          uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present, int sm_count, cudaStream_t st);
 
 // sketches
 int launch_cms_query(const SketchParams& sk, const uint4* keys, uint32_t n, unsigned long long* est, cudaStream_t st);

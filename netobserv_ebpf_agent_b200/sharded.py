@@ -1,0 +1,75 @@
+"""Hash-sharded multi-GPU aggregation: owner = fa_owner_hash(flow_id) % world.
+
+One process per GPU.  Per batch: K3 (`fa_route`) groups the local records by owner -> the per-owner counts are
+exchanged -> one variable-size all-to-all moves every record to its owning rank (NCCL over NVLink on GPUs, gloo in the
+CPU tests) -> the owner folds what it received with K1.  Eviction needs no collective: the key sets are disjoint.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import REC_BYTES, lib
+
+
+def owner_of(keys40, world):
+    """Owning rank of each 40-byte key (host side; same function K3 uses on the device)."""
+    k = np.ascontiguousarray(keys40).view(np.uint8).reshape(-1, 40)
+    out = np.empty(len(k), dtype=np.int64)
+    f = lib().fa_owner_hash
+    for i in range(len(k)):
+        out[i] = f(C.c_void_p(k[i].ctypes.data)) % world
+    return out
+
+
+def route_host(records, world):
+    """CPU twin of K3: stable partition of (n,144) records by owner -> (grouped records, counts[world])."""
+    r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, REC_BYTES)
+    own = owner_of(r[:, :40], world)
+    order = np.argsort(own, kind="stable")
+    return r[order], np.bincount(own, minlength=world).astype(np.int64)
+
+
+def exchange(send, send_counts, group=None):
+    """All-to-all of fixed-size records.
+
+    send: 1-D uint8 torch tensor holding the records grouped by destination rank; send_counts: records per
+    destination (len == world).  Returns (recv tensor, recv_counts list).  Works for CUDA tensors over NCCL and for
+    CPU tensors over gloo."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    cin = torch.as_tensor(np.asarray(send_counts, dtype=np.int64), device=send.device)
+    cout = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(cout, cin, group=group)
+    out_counts = [int(x) for x in cout.cpu().tolist()]
+    in_counts = [int(x) for x in send_counts]
+    recv = torch.empty(sum(out_counts) * REC_BYTES, dtype=torch.uint8, device=send.device)
+    dist.all_to_all_single(recv, send[: sum(in_counts) * REC_BYTES],
+                           output_split_sizes=[c * REC_BYTES for c in out_counts],
+                           input_split_sizes=[c * REC_BYTES for c in in_counts], group=group)
+    return recv, out_counts
+
+
+class ShardedAggregator:
+    """GPU path: route on the device, exchange over NCCL, fold on the owner."""
+
+    def __init__(self, engine, max_batch, device):
+        import torch
+        import torch.distributed as dist
+        self.eng, self.max_batch, self.world = engine, max_batch, dist.get_world_size()
+        self.send = torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device)
+
+    def ingest(self, records, n):
+        """records: device tensor / address of n local records.  Returns records folded on this rank."""
+        folded, done = 0, 0
+        base = records.data_ptr() if hasattr(records, "data_ptr") else int(records)
+        while done < n:
+            c = min(self.max_batch, n - done)
+            counts = self.eng.route(base + done * REC_BYTES, c, self.world, self.send)
+            recv, out_counts = exchange(self.send, counts)
+            tot = sum(out_counts)
+            rc, took = self.eng.ingest(recv.data_ptr(), tot)
+            assert rc == 0 and took == tot, (rc, took)
+            folded += tot
+            done += c
+        return folded
