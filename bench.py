@@ -154,7 +154,11 @@ def run_ours(args, wl):
 
     B = args.batch                                   # records per step per GPU
     ring = max(1, min(args.ring, args.steps + args.warmup))
-    stream = torch.cuda.current_stream()
+    # Everything (engine kernels, NCCL, timing events) runs on ONE explicit torch stream: the legacy default
+    # stream has handle 0, which the engine would take as "create your own".
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng = fa.FlowAggEngine(args.max_entries, device=local, max_batch=args.max_batch, cuda_stream=stream.cuda_stream)
     # one key universe for the whole job; every rank generates its own slice of the record stream
     gp = fa.GenParams(seed=wl["seed"], n_keys=wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100,

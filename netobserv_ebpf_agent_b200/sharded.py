@@ -54,8 +54,11 @@ class ShardedAggregator:
     """GPU path: route on the device, exchange over NCCL, fold on the owner."""
 
     def __init__(self, engine, max_batch, device):
+        """The engine must have been created on the CURRENT torch stream (cuda_stream=torch.cuda.current_stream()
+        .cuda_stream of a non-default stream): route, the NCCL exchange and the fold are then stream-ordered."""
         import torch
         import torch.distributed as dist
+        assert torch.cuda.current_stream().cuda_stream != 0, "use an explicit torch.cuda.Stream (see bench.py)"
         self.eng, self.max_batch, self.world = engine, max_batch, dist.get_world_size()
         self.send = torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device)
 

@@ -29,7 +29,9 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", device_id=dev)
     import netobserv_ebpf_agent_b200 as fa
     from netobserv_ebpf_agent_b200.sharded import ShardedAggregator, owner_of
-    eng = fa.FlowAggEngine(1 << 18, device=rank, max_batch=30_000, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=dev)             # engine, NCCL and copies share one explicit stream
+    torch.cuda.set_stream(stream)
+    eng = fa.FlowAggEngine(1 << 18, device=rank, max_batch=30_000, cuda_stream=stream.cuda_stream)
     agg = ShardedAggregator(eng, 30_000, dev)
     for b in range(3):
         local = gen_host(seed=50, n=100_000, n_keys=40_000, dist=1, first=(b * world + rank) * 100_000)
