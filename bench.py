@@ -159,6 +159,8 @@ def run_ours(args, wl):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
+    if world > 1:
+        args.max_batch = B          # one route -> exchange -> fold round per step: amortises the host-side syncs
     eng = fa.FlowAggEngine(args.max_entries, device=local, max_batch=args.max_batch, cuda_stream=stream.cuda_stream)
     # one key universe for the whole job; every rank generates its own slice of the record stream
     gp = fa.GenParams(seed=wl["seed"], n_keys=wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100,

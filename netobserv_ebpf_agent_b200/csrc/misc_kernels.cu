@@ -196,35 +196,43 @@ __global__ void route_scan_kernel(uint32_t* cta_hist, uint32_t n_ctas, uint32_t 
 __global__ void route_scatter_kernel(const uint4* __restrict__ recs, uint32_t n, uint32_t n_shards,
                                      const uint32_t* __restrict__ owner, const uint32_t* __restrict__ cta_off,
                                      uint4* __restrict__ out) {
-    // one warp-ordered pass per CTA keeps source order inside a shard
+    // Stable in-CTA partition: per round of 256 records every warp counts its records per shard with
+    // ballots, a tiny shared-memory prefix over the 8 warps gives each record its position.
+    __shared__ uint32_t wcount[kRouteThreads / 32][kMaxShards];
     __shared__ uint32_t cursor[kMaxShards];
     if (threadIdx.x < n_shards) cursor[threadIdx.x] = cta_off[threadIdx.x * gridDim.x + blockIdx.x];
-    __syncthreads();
     const uint32_t base = blockIdx.x * kRoutePerCta;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t round = 0; round < kRoutePerCta / kRouteThreads; round++) {
         const uint32_t i = base + round * kRouteThreads + threadIdx.x;
         const bool valid = i < n;
         const uint32_t o = valid ? owner[i] : 0xFFFFFFFFu;
+        uint32_t rank = 0;
+        for (uint32_t s = 0; s < n_shards; s++) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, o == s);
+            if (o == s) rank = __popc(m & ((1u << lane) - 1u));
+            if (lane == 0) wcount[warp][s] = __popc(m);
+        }
+        __syncthreads();
         uint32_t dst = 0;
-        // warps take turns so that positions follow source order
-        for (int w = 0; w < kRouteThreads / 32; w++) {
-            if (warp == w) {
-                for (uint32_t s = 0; s < n_shards; s++) {
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, o == s);
-                    if (o == s) dst = cursor[s] + __popc(m & ((1u << lane) - 1u));
-                    __syncwarp();
-                    if (lane == 0 && m) cursor[s] += __popc(m);
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
+        if (valid) {
+            dst = cursor[o] + rank;
+            for (int w = 0; w < warp; w++) dst += wcount[w][o];
+        }
+        __syncthreads();
+        if (threadIdx.x < n_shards) {
+            uint32_t t = 0;
+            for (int w = 0; w < kRouteThreads / 32; w++) t += wcount[w][threadIdx.x];
+            cursor[threadIdx.x] += t;
         }
         if (valid) {
             const uint4* R = recs + (size_t)i * kRecChunks;
             uint4* O = out + (size_t)dst * kRecChunks;
+            uint4 v[kRecChunks];
 #pragma unroll
-            for (int c = 0; c < kRecChunks; c++) O[c] = R[c];
+            for (int c = 0; c < kRecChunks; c++) v[c] = ld_stream_u4(R + c);
+#pragma unroll
+            for (int c = 0; c < kRecChunks; c++) O[c] = v[c];
         }
     }
 }

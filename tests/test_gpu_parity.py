@@ -182,3 +182,20 @@ def test_evict_capacity_error_and_empty_evict():
         rc = lib().fa_evict(eng._h, C.c_void_p(out.ctypes.data), None, None, None, 10, C.byref(got))
         assert rc == -7 and eng.live_flows() == distinct      # FA_E_2BIG, nothing deleted
         assert len(eng.evict()) == distinct and eng.live_flows() == 0
+
+
+@pytest.mark.parametrize("n,shards", [(1, 2), (2047, 2), (2049, 3), (100_000, 8), (65_536, 16)])
+def test_route_by_hash_matches_host_partition(n, shards):
+    """K3: stable partition by owner_hash(key) % shards == the host twin (same order inside a shard)."""
+    import torch
+    import netobserv_ebpf_agent_b200 as fa
+    from netobserv_ebpf_agent_b200.sharded import route_host
+    recs = gen_host(seed=15, n=n, n_keys=5_000, dist=1)
+    want, want_counts = route_host(recs, shards)
+    with fa.FlowAggEngine(1000, max_batch=1 << 17) as eng:
+        src = torch.from_numpy(np.ascontiguousarray(recs).reshape(-1).copy()).cuda()
+        dst = torch.zeros_like(src)
+        counts = eng.route(src, n, shards, dst)
+        eng.sync()
+        assert np.array_equal(counts.astype(np.int64), want_counts)
+        assert np.array_equal(dst.cpu().numpy().reshape(-1, 144), want)
