@@ -24,6 +24,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 REC = 144
+# DRAM bytes per record of K1 from the committed ncu --set full capture (profiles/r1_k1_aggregate_ncu_summary.txt:
+# dram__bytes_read.sum 718.85 MB + dram__bytes_write.sum 18.88 MB for a 4,194,304-record launch of the zipf1m
+# workload) -> 175.9 B/record against 144 algorithmic bytes (ratio 1.22: table lines + write-backs, no re-reads).
+NCU_DRAM_BYTES_PER_RECORD = {"zipf1m": (718.847232e6 + 18.878720e6) / 4194304}
 WORKLOADS = {
     "zipf1m": dict(n_keys=1_000_000, dist=1, seed=2, label="1e9-record stream, 1M Zipf-1.1 5-tuples (BASELINE configs[1])"),
     "zipf10m": dict(n_keys=10_000_000, dist=1, seed=2, label="1e9-record stream, 10M Zipf-1.1 5-tuples (north_star headline)"),
@@ -263,9 +267,12 @@ def run_ours(args, wl):
                            f"{ring} distinct batches cycled)",
                            "parallelism": "1 GPU" if world == 1 else f"hash-sharded x{world}, K3 route + NCCL all-to-all"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src,
+                             "traffic": (NCU_DRAM_BYTES_PER_RECORD[args.workload] * min(B, args.max_batch)
+                                         if args.workload in NCU_DRAM_BYTES_PER_RECORD and world == 1 else None),
+                             "algorithmic_bytes_per_launch": REC * min(B, args.max_batch), "peak_source": peak_src,
                              "kernel": "fa::aggregate_kernel (K1); 144 algorithmic bytes per record; duration = CUDA-event "
-                                       "time of one step (K1 launches + 2 early-exit re-fold kernels each)"},
+                                       "time of one step = %d K1 launch(es) + 2 early-exit re-fold kernels each; traffic = "
+                                       "ncu dram bytes/record x records per launch" % max(1, B // min(B, args.max_batch))},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "order_fixups": st1["order_fixups"] - st0["order_fixups"], "spills": st1["spills"]}
         if e2e:
@@ -286,8 +293,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="zipf1m", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=1 << 24, help="records per step per GPU (2^24 x 60 steps ~ 1e9)")
-    ap.add_argument("--max-batch", type=int, default=1 << 22, help="records per K1 launch")
-    ap.add_argument("--max-entries", type=int, default=1 << 25)
+    ap.add_argument("--max-batch", type=int, default=1 << 24, help="records per K1 launch")
+    ap.add_argument("--max-entries", type=int, default=1 << 26,
+                    help="flow-cache capacity; >= flows + 3 x max_batch keeps fa_ingest on its zero-sync path")
     ap.add_argument("--ring", type=int, default=8, help="distinct pre-generated input batches cycled through")
     ap.add_argument("--e2e-batch", type=int, default=1 << 22)
     ap.add_argument("--e2e-steps", type=int, default=12)

@@ -204,52 +204,95 @@ static size_t fmap_dump_records(const fmap* m, uint8_t* out, size_t cap) {
 }
 
 /* ------------------------------------------------------------ Accounter */
+/* Lean flat map for the Accounter: one 144-byte record (key + metrics) per flow, in insertion order. */
+typedef struct {
+    uint32_t* idx; size_t cap;       /* open addressing; 0 = empty, else entry index + 1 */
+    uint8_t*  recs; size_t n, recs_cap;
+} amap;
+static void amap_init(amap* m, size_t hint) {
+    size_t cap = 64; while (cap < hint * 2) cap <<= 1;
+    m->cap = cap; m->idx = (uint32_t*)calloc(cap, sizeof(uint32_t));
+    m->recs_cap = hint < 16 ? 16 : hint; m->recs = (uint8_t*)malloc(m->recs_cap * OR_REC_SIZE); m->n = 0;
+}
+static void amap_free(amap* m) { free(m->idx); free(m->recs); m->idx = NULL; m->recs = NULL; m->n = 0; }
+static void amap_clear(amap* m) { memset(m->idx, 0, m->cap * sizeof(uint32_t)); m->n = 0; }
+static void amap_grow(amap* m) {
+    size_t ncap = m->cap * 2; uint32_t* nidx = (uint32_t*)calloc(ncap, sizeof(uint32_t));
+    for (size_t i = 0; i < m->n; i++) {
+        size_t s = (size_t)oracle_slot_hash(m->recs + i * OR_REC_SIZE) & (ncap - 1);
+        while (nidx[s]) s = (s + 1) & (ncap - 1);
+        nidx[s] = (uint32_t)(i + 1);
+    }
+    free(m->idx); m->idx = nidx; m->cap = ncap;
+}
+/* the Accounter's per-record step (account.go:82-96 without the maxEntries test): fold or insert */
+static inline void amap_account(amap* m, const uint8_t* rec /* after ReadFrom */) {
+    size_t s = (size_t)oracle_slot_hash(rec) & (m->cap - 1);
+    for (;;) {
+        uint32_t v = m->idx[s];
+        if (!v) break;
+        uint8_t* e = m->recs + (size_t)(v - 1) * OR_REC_SIZE;
+        if (memcmp(e, rec, OR_ID_SIZE) == 0) { oracle_accumulate_base(e + OR_ID_SIZE, rec + OR_ID_SIZE); return; }
+        s = (s + 1) & (m->cap - 1);
+    }
+    if ((m->n + 1) * 2 > m->cap) { amap_grow(m); amap_account(m, rec); return; }
+    if (m->n == m->recs_cap) { m->recs_cap *= 2; m->recs = (uint8_t*)realloc(m->recs, m->recs_cap * OR_REC_SIZE); }
+    memcpy(m->recs + m->n * OR_REC_SIZE, rec, OR_REC_SIZE);               /* account.go:95: whole 104 B kept */
+    m->idx[s] = (uint32_t)(++m->n);
+}
+static inline int amap_has(const amap* m, const uint8_t* rec) {
+    size_t s = (size_t)oracle_slot_hash(rec) & (m->cap - 1);
+    for (;;) {
+        uint32_t v = m->idx[s];
+        if (!v) return 0;
+        if (memcmp(m->recs + (size_t)(v - 1) * OR_REC_SIZE, rec, OR_ID_SIZE) == 0) return 1;
+        s = (s + 1) & (m->cap - 1);
+    }
+}
+
 typedef struct generation { uint8_t* recs; size_t n; struct generation* next; } generation;
 struct oracle_accounter {
     size_t max_entries;
-    fmap   entries;
+    amap   entries;
     generation *gen_head, *gen_tail; size_t gen_pending;
 };
 
 oracle_accounter* oracle_accounter_new(size_t max_entries) {
     oracle_accounter* a = (oracle_accounter*)calloc(1, sizeof(*a));
     a->max_entries = max_entries;
-    fmap_init(&a->entries, max_entries < (1u << 20) ? max_entries : (1u << 20));
+    amap_init(&a->entries, max_entries < (1u << 20) ? max_entries : (1u << 20));
     return a;
 }
 void oracle_accounter_free(oracle_accounter* a) {
     if (!a) return;
     while (a->gen_head) { generation* g = a->gen_head; a->gen_head = g->next; free(g->recs); free(g); }
-    fmap_free(&a->entries); free(a);
+    amap_free(&a->entries); free(a);
 }
 size_t oracle_accounter_len(const oracle_accounter* a) { return a->entries.n; }
 
 static void accounter_push_generation(oracle_accounter* a) {
     generation* g = (generation*)calloc(1, sizeof(*g));
     g->n = a->entries.n; g->recs = (uint8_t*)malloc(g->n ? g->n * OR_REC_SIZE : 1);
-    fmap_dump_records(&a->entries, g->recs, g->n);
+    memcpy(g->recs, a->entries.recs, g->n * OR_REC_SIZE);
     if (a->gen_tail) a->gen_tail->next = g; else a->gen_head = g;
     a->gen_tail = g; a->gen_pending++;
-    fmap_clear(&a->entries);
+    amap_clear(&a->entries);
 }
 
 void oracle_accounter_account(oracle_accounter* a, const uint8_t* wire, size_t n) {
     uint8_t rec[OR_REC_SIZE];
     for (size_t i = 0; i < n; i++) {
         oracle_read_from(wire + i * OR_REC_SIZE, rec);                  /* tracer_ringbuf.go:112-134 */
-        int found; entry_t* e = fmap_get(&a->entries, rec, 0, &found);
-        if (found) {
-            oracle_accumulate_base(e->c.metrics, rec + OR_ID_SIZE);      /* account.go:82-83 */
-        } else {
-            if (a->entries.n >= a->max_entries) accounter_push_generation(a);   /* account.go:85-94 */
-            e = fmap_get(&a->entries, rec, 1, &found);
-            memcpy(e->c.metrics, rec + OR_ID_SIZE, OR_MET_SIZE);         /* account.go:95: whole 104 B kept */
-        }
+        if (a->entries.n >= a->max_entries && !amap_has(&a->entries, rec))
+            accounter_push_generation(a);                               /* account.go:85-94: new key, cache full */
+        amap_account(&a->entries, rec);                                 /* account.go:82-83 / :95 */
     }
 }
 size_t oracle_accounter_evict(oracle_accounter* a, uint8_t* out, size_t cap) {
-    size_t n = fmap_dump_records(&a->entries, out, cap);                /* account.go:63-80,102-124 */
-    fmap_clear(&a->entries);
+    size_t k = a->entries.n < cap ? a->entries.n : cap;                 /* account.go:63-80,102-124 */
+    memcpy(out, a->entries.recs, k * OR_REC_SIZE);
+    size_t n = a->entries.n;
+    amap_clear(&a->entries);
     return n;
 }
 size_t oracle_accounter_pending(const oracle_accounter* a) { return a->gen_pending; }
@@ -263,39 +306,58 @@ size_t oracle_accounter_pop_generation(oracle_accounter* a, uint8_t* out, size_t
 }
 
 size_t oracle_accounter_sharded_run(const uint8_t* wire, size_t n, int n_threads, uint8_t* out, size_t cap) {
-    /* CPU-baseline only: T private Accounters, thread t owns keys with owner_hash % T == t.
-     * Pass 1 computes each record's owner once; pass 2 lets every thread walk the
-     * stream and fold only its own records (keeps stream order inside a key). */
+    /* CPU-baseline only (bench.py --impl reference): T private Accounters, thread t owns the keys with
+     * owner_hash % T == t.  Pass 1 (parallel over contiguous chunks): owner of every record + per-chunk
+     * histograms.  Pass 2: stable scatter of record indices into per-owner lists.  Pass 3: every thread folds
+     * its own list in stream order.  No maxEntries cut. */
     if (n_threads < 1) n_threads = 1;
-    uint8_t* owner = (uint8_t*)malloc(n ? n : 1);
-#pragma omp parallel for num_threads(n_threads) schedule(static)
-    for (long long i = 0; i < (long long)n; i++)
-        owner[i] = (uint8_t)(oracle_owner_hash(wire + (size_t)i * OR_REC_SIZE) % (uint64_t)n_threads);
-    fmap* maps = (fmap*)calloc((size_t)n_threads, sizeof(fmap));
+    const size_t T = (size_t)n_threads;
+    uint16_t* owner = (uint16_t*)malloc((n ? n : 1) * sizeof(uint16_t));
+    uint32_t* list = (uint32_t*)malloc((n ? n : 1) * sizeof(uint32_t));
+    size_t* hist = (size_t*)calloc(T * T + 1, sizeof(size_t));          /* hist[chunk][owner] */
+    size_t* start = (size_t*)calloc(T + 1, sizeof(size_t));
+    amap* maps = (amap*)calloc(T, sizeof(amap));
 #pragma omp parallel num_threads(n_threads)
     {
 #ifdef _OPENMP
-        int t = omp_get_thread_num();
+        const size_t t = (size_t)omp_get_thread_num();
 #else
-        int t = 0;
+        const size_t t = 0;
 #endif
-        fmap* m = &maps[t]; fmap_init(m, 1u << 16);
+        const size_t lo = n * t / T, hi = n * (t + 1) / T;
+        for (size_t i = lo; i < hi; i++) {
+            const uint16_t o = (uint16_t)(oracle_owner_hash(wire + i * OR_REC_SIZE) % T);
+            owner[i] = o; hist[t * T + o]++;
+        }
+#pragma omp barrier
+#pragma omp single
+        {
+            size_t run = 0;
+            for (size_t o = 0; o < T; o++) {
+                start[o] = run;
+                for (size_t c = 0; c < T; c++) { const size_t v = hist[c * T + o]; hist[c * T + o] = run; run += v; }
+            }
+            start[T] = run;
+        }
+        for (size_t i = lo; i < hi; i++) list[hist[t * T + owner[i]]++] = (uint32_t)i;
+#pragma omp barrier
+        amap* m = &maps[t];
+        amap_init(m, (start[t + 1] - start[t]) / 4 + 1024);
         uint8_t rec[OR_REC_SIZE];
-        for (size_t i = 0; i < n; i++) {
-            if (owner[i] != t) continue;
-            oracle_read_from(wire + i * OR_REC_SIZE, rec);
-            int found; entry_t* e = fmap_get(m, rec, 1, &found);
-            if (found) oracle_accumulate_base(e->c.metrics, rec + OR_ID_SIZE);
-            else memcpy(e->c.metrics, rec + OR_ID_SIZE, OR_MET_SIZE);
+        for (size_t k = start[t]; k < start[t + 1]; k++) {
+            oracle_read_from(wire + (size_t)list[k] * OR_REC_SIZE, rec);
+            amap_account(m, rec);
         }
     }
     size_t total = 0;
-    for (int t = 0; t < n_threads; t++) {
-        size_t room = total < cap ? cap - total : 0;
-        if (out) fmap_dump_records(&maps[t], out + total * OR_REC_SIZE, room);
-        total += maps[t].n; fmap_free(&maps[t]);
+    for (size_t t = 0; t < T; t++) {
+        if (out && total < cap) {
+            const size_t k = maps[t].n < cap - total ? maps[t].n : cap - total;
+            memcpy(out + total * OR_REC_SIZE, maps[t].recs, k * OR_REC_SIZE);
+        }
+        total += maps[t].n; amap_free(&maps[t]);
     }
-    free(maps); free(owner);
+    free(maps); free(owner); free(list); free(hist); free(start);
     return total;
 }
 
