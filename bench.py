@@ -178,7 +178,8 @@ def run_ours(args, wl):
 
     if world > 1:
         from netobserv_ebpf_agent_b200.sharded import ShardedAggregator
-        agg = ShardedAggregator(eng, args.max_batch, dev)   # K3 route -> NCCL all-to-all -> K1 on the owner
+        # local combine (K1+K2) -> K3 route -> NCCL all-to-all -> K1 on the owner
+        agg = ShardedAggregator(eng, args.max_batch, dev, combine=not args.no_combine)
 
     def step(i):
         src = batches[i % ring]
@@ -265,7 +266,10 @@ def run_ours(args, wl):
                            "max_entries": args.max_entries, "max_batch": args.max_batch, "live_flows": int(flows),
                            "input_ring_batches": ring, "l2_policy": f"inputs larger than L2 ({B * REC / 1e6:.0f} MB per step, "
                            f"{ring} distinct batches cycled)",
-                           "parallelism": "1 GPU" if world == 1 else f"hash-sharded x{world}, K3 route + NCCL all-to-all"},
+                           "parallelism": "1 GPU" if world == 1 else
+                           f"hash-sharded x{world}: " + ("" if args.no_combine else "per-batch local combine (K1+K2) -> ") +
+                           "K3 route -> NCCL all-to-all -> K1 on the owner",
+                           "exchanged_records_per_step_rank0": (agg.exchanged_records // (args.steps + args.warmup)) if world > 1 else None},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (NCU_DRAM_BYTES_PER_RECORD[args.workload] * min(B, args.max_batch)
                                          if args.workload in NCU_DRAM_BYTES_PER_RECORD and world == 1 else None),
@@ -302,6 +306,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 25)
     ap.add_argument("--ref-sample", type=int, default=1 << 24)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-combine", action="store_true", help="N>1: route raw records instead of per-batch partial flows")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

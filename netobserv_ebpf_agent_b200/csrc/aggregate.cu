@@ -157,7 +157,10 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
                 const unsigned long long pub = (epoch << TAG_EPOCH_SHIFT) | TAG_HAS_BASE | TAG_PUBLISHED |
                                                (cta_dirty ? TAG_DIRTY : 0ull);
                 *reinterpret_cast<volatile unsigned long long*>(tagp) = pub;
-                if (won == 1u) my_inserts++;                   // a base claim does not add a flow
+                if (won == 1u) {                               // a base claim does not add a flow
+                    my_inserts++;
+                    red_or_u32(&t.occ[slot >> 5], 1u << (slot & 31));
+                }
                 if (cta_dirty) *any_dirty = 1;
             }
             hit = true;

@@ -326,6 +326,8 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     CU(cudaMalloc(&e->table.hot, slots * fa::kHotBytes));
     CU(cudaMemsetAsync(e->table.ident, 0, slots * fa::kIdentBytes, e->stream));
     CU(cudaMemsetAsync(e->table.hot, 0, slots * fa::kHotBytes, e->stream));
+    CU(cudaMalloc(&e->table.occ, slots / 8));
+    CU(cudaMemsetAsync(e->table.occ, 0, slots / 8, e->stream));
     if (cfg->flags & FA_F_ENABLE_RTT) {
         CU(cudaMalloc(&e->table.feat_add, slots * 80));
         CU(cudaMemsetAsync(e->table.feat_add, 0, slots * 80, e->stream));
@@ -407,7 +409,7 @@ void fa_destroy(fa_engine* e) {
         cudaFree(e->d_prof);
     }
     if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
-    cudaFree(e->table.ident); cudaFree(e->table.hot); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns);
+    cudaFree(e->table.ident); cudaFree(e->table.hot); cudaFree(e->table.occ); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns);
     cudaFree(e->d_ctr); if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_live_ring) cudaFreeHost(e->h_live_ring);
     for (int i = 0; i < fa_engine::kLiveRing; i++) if (e->ev_live[i]) cudaEventDestroy(e->ev_live[i]);

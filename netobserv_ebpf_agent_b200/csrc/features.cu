@@ -55,6 +55,7 @@ __device__ uint32_t find_or_create(const Table& t, uint64_t epoch, const uint64_
                 for (int c = 6; c < 16; c++) L[c] = 0ull;
                 __threadfence();
                 *reinterpret_cast<volatile unsigned long long*>(tagp) = TAG_PUBLISHED;   // no TAG_HAS_BASE, epoch 0
+                red_or_u32(&t.occ[slot >> 5], 1u << (slot & 31));
                 atomicAdd(n_created, 1ull);
                 return (uint32_t)slot;
             }

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, combine):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -32,7 +32,7 @@ def _worker(rank, world, port, q):
     stream = torch.cuda.Stream(device=dev)             # engine, NCCL and copies share one explicit stream
     torch.cuda.set_stream(stream)
     eng = fa.FlowAggEngine(1 << 18, device=rank, max_batch=30_000, cuda_stream=stream.cuda_stream)
-    agg = ShardedAggregator(eng, 30_000, dev)
+    agg = ShardedAggregator(eng, 30_000, dev, combine=combine)
     for b in range(3):
         local = gen_host(seed=50, n=100_000, n_keys=40_000, dist=1, first=(b * world + rank) * 100_000)
         t = torch.from_numpy(np.ascontiguousarray(local).reshape(-1).copy()).to(dev)
@@ -41,18 +41,20 @@ def _worker(rank, world, port, q):
     assert (owner_of(out[:, :40], world) == rank).all()
     q.put((rank, out.copy()))
     dist.barrier()
+    agg.close()
     eng.close()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_sharded_parity():
+@pytest.mark.parametrize("combine", [False, True])
+def test_two_gpu_sharded_parity(combine):
     import torch.multiprocessing as mp
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, combine)) for r in range(world)]
     for p in procs:
         p.start()
     outs = dict(q.get(timeout=300) for _ in range(world))
