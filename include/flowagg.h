@@ -227,6 +227,13 @@ int fa_ingest_dns(fa_engine* e, const void* dns_records, size_t n);
 int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additional,
              uint8_t* out_present, size_t cap, size_t* n_out);
 
+/* Lookup-and-RESET (no reference analogue; building block of the multi-GPU local combiner, the counterpart of
+ * the reference folding its per-CPU maps in user space, pkg/tracer/tracer.go:1159-1187): every flow that received
+ * records since the previous drain is written to out_records (device memory, cap x 144 B) as a partial flow record
+ * and its counters are reset to the fold identity; the flows themselves stay cached.  A partial whose start is
+ * already covered by an earlier partial carries start = 0 ("unset"), which AccumulateBase ignores. */
+int fa_drain_active(fa_engine* e, void* out_records_dev, size_t cap, size_t* n_out);
+
 /* Number of live flows right now (len(c.entries), account.go:98). */
 int fa_live_flows(fa_engine* e, size_t* n);
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "fa_ingest_dns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_evict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                            C.POINTER(C.c_size_t)]),
+    "fa_drain_active": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_live_flows": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
     "fa_purge_stale_dns": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "fa_cms_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

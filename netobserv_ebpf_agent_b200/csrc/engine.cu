@@ -574,6 +574,26 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
     return FA_OK;
 }
 
+int fa_drain_active(fa_engine* e, void* out_records_dev, size_t cap, size_t* n_out) {
+    if (n_out) *n_out = 0;
+    if (!e || !n_out || !out_records_dev) return fail(FA_E_INVAL, "fa_drain_active: null argument");
+    if (classify(out_records_dev) != PTR_DEVICE) return fail(FA_E_INVAL, "fa_drain_active: out_records must be device memory");
+    if (e->table.feat_add || e->table.feat_dns) return fail(FA_E_INVAL, "fa_drain_active: not available with feature folds enabled");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
+    e->st.kernel_launches += fa::launch_evict(e->table, static_cast<uint4*>(out_records_dev), nullptr, cap, e->d_ctr,
+                                              e->sm_count, e->stream, /*drain=*/true);
+    CU(cudaGetLastError());
+    int rc = sync_counters(e);
+    if (rc) return rc;
+    if (e->h_ctr->evict_out > cap)
+        return fail(FA_E_2BIG, "fa_drain_active: %llu active flows > capacity %zu (flows beyond it were reset but not written)",
+                    (unsigned long long)e->h_ctr->evict_out, cap);
+    *n_out = (size_t)e->h_ctr->evict_out;
+    return FA_OK;
+}
+
 int fa_purge_stale_dns(fa_engine* e, uint64_t, uint64_t) {
     if (!e) return fail(FA_E_INVAL, "fa_purge_stale_dns: null engine");
     return FA_OK;   // pre-computed-latency DNS contract (SURVEY.md §8 a12'): no query table to purge

@@ -11,6 +11,10 @@
 
 namespace fa {
 
+// kDrain = false: lookup-and-delete (the flow is removed).  kDrain = true: "lookup-and-reset": flows that
+// received records since the last drain are emitted and their hot line is zeroed, but they stay in the table
+// (identity line, tag, bitmap untouched) so the next batch hits them on the fast path.
+template <bool kDrain>
 __global__ void __launch_bounds__(256)
 evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_out, unsigned long long cap, Counters* ctr) {
     const int lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
@@ -23,27 +27,39 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
     for (uint64_t w0 = warp_global * 32; w0 < n_words; w0 += n_warps * 32) {
         const uint64_t wi = w0 + lane;                  // 32 consecutive bitmap words per warp iteration (coalesced)
         uint32_t mybits = wi < n_words ? t.occ[wi] : 0u;
-        if (mybits) t.occ[wi] = 0u;
+        if (!kDrain && mybits) t.occ[wi] = 0u;
         uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, mybits != 0u);
         while (nonempty) {
             const int src = __ffs(nonempty) - 1; nonempty &= nonempty - 1;
             uint32_t bits = __shfl_sync(0xFFFFFFFFu, mybits, src);
             const uint64_t word_slot0 = (w0 + src) * 32;
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->evict_out, (unsigned long long)__popc(bits));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (!kDrain) {
+                if (lane == 0) base = atomicAdd(&ctr->evict_out, (unsigned long long)__popc(bits));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            }
             uint32_t done_before = 0;
             while (bits) {                              // up to 4 flows (one per 8-lane group) per round
                 const uint32_t pos = __fns(bits, 0, g + 1);
-                const bool live = pos < 32u;
+                bool live = pos < 32u;
                 const uint64_t slot = word_slot0 + (live ? pos : 0u);
-                const unsigned long long idx = base + done_before + g;
+                unsigned long long idx = base + done_before + g;
                 const uint32_t taken = min(4, __popc(bits));
                 for (uint32_t k = 0; k < taken; k++) bits &= bits - 1;
                 done_before += taken;
                 uint4 line = make_uint4(0, 0, 0, 0), hot = make_uint4(0, 0, 0, 0);
-                if (live) line = ld_cg_u4(&t.ident[slot * 8 + j]);
                 if (live && j < 2) hot = ld_cg_u4(&t.hot[slot * 2 + j]);
+                if (kDrain) {
+                    // active = any field of the hot line moved since the last drain
+                    const uint32_t act = __ballot_sync(0xFFFFFFFFu, (hot.x | hot.y | hot.z | hot.w) != 0u);
+                    live = live && ((act >> (g * 8)) & 3u) != 0u;
+                    const uint32_t lg = __ballot_sync(0xFFFFFFFFu, live && j == 0);
+                    unsigned long long rb = 0;
+                    if (lane == 0 && lg) rb = atomicAdd(&ctr->evict_out, (unsigned long long)__popc(lg));
+                    rb = __shfl_sync(0xFFFFFFFFu, rb, 0);
+                    idx = rb + __popc(lg & ((1u << (g * 8)) - 1u));
+                }
+                if (live) line = ld_cg_u4(&t.ident[slot * 8 + j]);
                 // hot chunk 0 = (bytes, nstart), hot chunk 1 = (end, packets, flags)
                 const uint32_t b_lo = __shfl_sync(0xFFFFFFFFu, hot.x, g * 8), b_hi = __shfl_sync(0xFFFFFFFFu, hot.y, g * 8);
                 const uint32_t ns_lo = __shfl_sync(0xFFFFFFFFu, hot.z, g * 8), ns_hi = __shfl_sync(0xFFFFFFFFu, hot.w, g * 8);
@@ -64,8 +80,8 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
                     }
                     if (slot_of_out && j == 0) slot_of_out[idx] = (uint32_t)slot;   // for the feature pass
                 }
-                // delete: tag -> EMPTY, hot line -> identity
-                if (live && j == 2) *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(&t.ident[slot * 8 + 2]) + 8) = make_uint2(0u, 0u);
+                // delete: tag -> EMPTY, hot line -> identity  (drain: hot line only)
+                if (!kDrain && live && j == 2) *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(&t.ident[slot * 8 + 2]) + 8) = make_uint2(0u, 0u);
                 if (live && j < 2) t.hot[slot * 2 + j] = make_uint4(0, 0, 0, 0);
             }
         }
@@ -73,8 +89,9 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
 }
 
 int launch_evict(const Table& table, uint4* out_recs, uint32_t* slot_of_out,
-                 unsigned long long cap, Counters* ctr, int sm_count, cudaStream_t st) {
-    evict_kernel<<<sm_count * 8, 256, 0, st>>>(table, out_recs, slot_of_out, cap, ctr);
+                 unsigned long long cap, Counters* ctr, int sm_count, cudaStream_t st, bool drain) {
+    if (drain) evict_kernel<true><<<sm_count * 8, 256, 0, st>>>(table, out_recs, slot_of_out, cap, ctr);
+    else evict_kernel<false><<<sm_count * 8, 256, 0, st>>>(table, out_recs, slot_of_out, cap, ctr);
     return 1;
 }
 

@@ -46,8 +46,9 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st);
 // K2: lookup-and-delete every live flow of `table` into out_recs (device pointer, cap records).
 // The number found is left in ctr->evict_out (can exceed cap; only cap are written).
 // slot_of_out (optional): receives the table slot of every emitted flow, for the feature pass.
+// drain: emit + reset only the flows that received records since the last drain; nothing is removed.
 int launch_evict(const Table& table, uint4* out_recs, uint32_t* slot_of_out,
-                 unsigned long long cap, Counters* ctr, int sm_count, cudaStream_t st);
+                 unsigned long long cap, Counters* ctr, int sm_count, cudaStream_t st, bool drain = false);
 
 // Overflow pre-pass (ACCOUNTER "full" cut, reference pkg/flow/account.go:85-94): finds the index of the
 // first record whose key is new when the cache already holds max_entries flows. Result in *cut_out

@@ -100,6 +100,12 @@ class FlowAggEngine:
         check(lib().fa_evict(self._h, _ptr(out), None, None, None, cap, C.byref(got)))
         return got.value
 
+    def drain_active(self, out_dev, cap):
+        """Emit + reset the flows touched since the last drain into a device buffer (flows stay cached)."""
+        got = C.c_size_t(0)
+        check(lib().fa_drain_active(self._h, _ptr(out_dev), cap, C.byref(got)))
+        return got.value
+
     # -- sketches ---------------------------------------------------------------
     def cms_query(self, keys):
         k = np.ascontiguousarray(keys).view(np.uint8).reshape(-1, 40)

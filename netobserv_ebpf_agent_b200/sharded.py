@@ -70,8 +70,8 @@ class ShardedAggregator:
         self.send = torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device)
         self.local = None
         if combine:
-            # capacity == batch size: a batch can never overflow the scratch table, so it always takes the fast path
-            self.local = FlowAggEngine(max_batch, device=device.index, max_batch=max_batch,
+            # scratch flow table of the combiner; flows stay cached across batches (drain, not evict)
+            self.local = FlowAggEngine(4 * max_batch, device=device.index, max_batch=max_batch,
                                        cuda_stream=torch.cuda.current_stream().cuda_stream)
             self.part = torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device)
         self.exchanged_records = 0
@@ -86,17 +86,30 @@ class ShardedAggregator:
             done += c
             if self.local is not None:
                 rc, took = self.local.ingest(src, c)
-                assert rc == 0 and took == c, (rc, took)
-                c = self.local.evict_into(self.part, self.max_batch)
+                if rc != 0:                          # scratch table full: flush it completely, then fold the rest
+                    import torch
+                    live = self.local.live_flows()
+                    big = torch.empty(max(live, 1) * REC_BYTES, dtype=torch.uint8, device=self.part.device)
+                    k = self.local.evict_into(big, live)
+                    for off in range(0, k, self.max_batch):
+                        folded += self._exchange_and_fold(big.data_ptr() + off * REC_BYTES, min(self.max_batch, k - off))
+                    del big
+                    rc, took2 = self.local.ingest(src + took * REC_BYTES, c - took)
+                    assert rc == 0 and took + took2 == c, (rc, took, took2)
+                # partial flow records of this batch; the flows stay cached in the scratch table
+                c = self.local.drain_active(self.part, self.max_batch)
                 src = self.part.data_ptr()
-            self.exchanged_records += c
-            counts = self.eng.route(src, c, self.world, self.send)
-            recv, out_counts = exchange(self.send, counts)
-            tot = sum(out_counts)
-            rc, took = self.eng.ingest(recv.data_ptr(), tot)
-            assert rc == 0 and took == tot, (rc, took)
-            folded += tot
+            folded += self._exchange_and_fold(src, c)
         return folded
+
+    def _exchange_and_fold(self, src, c):
+        self.exchanged_records += c
+        counts = self.eng.route(src, c, self.world, self.send)
+        recv, out_counts = exchange(self.send, counts)
+        tot = sum(out_counts)
+        rc, took = self.eng.ingest(recv.data_ptr(), tot)
+        assert rc == 0 and took == tot, (rc, took)
+        return tot
 
     def close(self):
         if self.local is not None:

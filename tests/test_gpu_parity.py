@@ -199,3 +199,33 @@ def test_route_by_hash_matches_host_partition(n, shards):
         eng.sync()
         assert np.array_equal(counts.astype(np.int64), want_counts)
         assert np.array_equal(dst.cpu().numpy().reshape(-1, 144), want)
+
+
+@pytest.mark.parametrize("varying", [0, 1])
+def test_drain_active_partials_fold_to_the_same_flows(varying):
+    """fa_drain_active: per-batch partial flow records (flows stay cached) re-folded by a second engine — the
+    multi-GPU combiner path — give exactly the flows of the plain stream when descriptors are per-key constants;
+    commutative fields are exact in every case."""
+    import torch
+    import netobserv_ebpf_agent_b200 as fa
+    batches = [gen_host(seed=16, n=50_000, n_keys=8_000, dist=1, varying=varying, first=i * 50_000) for i in range(4)]
+    with fa.FlowAggEngine(1 << 17, max_batch=60_000) as local, fa.FlowAggEngine(1 << 15) as owner:
+        part = torch.zeros(60_000 * 144, dtype=torch.uint8, device="cuda")
+        total_partials = 0
+        for b in batches:
+            local.ingest(b)
+            k = local.drain_active(part, 60_000)
+            assert 0 < k <= len(np.unique(b[:, :40], axis=0))
+            total_partials += k
+            owner.ingest(part.data_ptr(), k)
+        assert local.drain_active(part, 60_000) == 0          # nothing touched since the last drain
+        got = O.sort_records(owner.evict())
+        assert local.live_flows() == len(got)                 # the combiner kept its flows cached
+    want = oracle_generations(batches, 1 << 20)[0]
+    g, w = rec_view(got), rec_view(want)
+    for f in ("bytes", "packets", "flags", "start", "end"):
+        assert np.array_equal(g[f], w[f]), f
+    assert np.array_equal(got[:, :40], want[:, :40])
+    if not varying:
+        assert np.array_equal(got, want)
+    assert total_partials < sum(len(b) for b in batches)
