@@ -53,7 +53,7 @@ struct __align__(128) TeamSmem {                  // 51,984 B per team
     uint8_t  glist[kTile];                        //    256 B  team-wide compacted list of representatives
     uint8_t  slow[kTile / 32][32];                //    256 B  per-warp flows that need the general probe loop
     unsigned long long full_bar;
-    uint32_t nrep, pad;
+    uint32_t nrep, next_chunk;
 };
 struct __align__(16) HotEntry {                   // 208 B: a stride of 52 words keeps 8 entries on distinct banks
     uint4    line[8];                             // copy of the flow's identity line
@@ -212,7 +212,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     if (tid == 0) {
         mbar_init(&s.full_bar, 1);
         fence_barrier_init();
-        s.nrep = 0;
+        s.nrep = 0; s.next_chunk = 0;
     }
     s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;
     *reinterpret_cast<uint4*>(&s.acc[tid][0]) = make_uint4(0, 0, 0, 0);
@@ -231,7 +231,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     const uint4* T = s.tile;
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long pt = kProf ? clock64() : 0;
-    uint32_t c_cached = 0, c_reps = 0, c_slow = 0, c_install = 0;      // kProf only
+    uint32_t c_cached = 0, c_reps = 0, c_slow = 0, c_install = 0, c_collide = 0, c_p1fast = 0, c_unsettled = 0;   // kProf only
 
     for (uint32_t it = 0;; ++it) {
         const uint32_t tile_idx = tile0 + it * tile_stride;
@@ -332,138 +332,157 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         FA_PROF_MARK(2);                                           // S1 wait
 
         const uint32_t nrep_total = s.nrep;
-        const uint32_t share = ((nrep_total + kTile / 32 - 1) / (kTile / 32) + 3u) & ~3u;   // multiple of 4
-        const uint32_t k_begin = min(nrep_total, (uint32_t)warp * share);
-        const uint32_t k_end = min(nrep_total, k_begin + share);
         s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;   // nobody reads the election table after S1
 
-        // ------------------------------------------------------ cooperative probe: 8 lanes per flow
-        uint32_t nslow = 0;
-        for (uint32_t base = k_begin; base < k_end; base += 4 * kInflight) {
+        // ------------------------------------------------------ probe: warps pull chunks of 16 flows (dynamic
+        // balancing: a warp stuck behind a DRAM miss or an insert simply takes fewer chunks)
+        for (;;) {
+            uint32_t c0 = 0;
+            if (lane == 0) c0 = atomicAdd(&s.next_chunk, 4u * kInflight);
+            c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
+            if (c0 >= nrep_total) break;
+            const uint32_t c_end = min(nrep_total, c0 + 4u * kInflight);
             uint4 line[kInflight];
             uint32_t ridx[kInflight];
             uint32_t slot[kInflight];
+            uint32_t pend = 0;                                     // rounds of this lane group still to be probed
 #pragma unroll
-            for (int r = 0; r < kInflight; r++) {                  // issue: up to 16 identity lines in flight per warp
-                const uint32_t k = base + r * 4 + g;
-                const bool act = k < k_end;
-                ridx[r] = act ? s.glist[k] : 0;
+            for (int r = 0; r < kInflight; r++) {
+                const uint32_t k = c0 + r * 4 + g;
+                ridx[r] = 0;
+                if (k < c_end) { pend |= 1u << r; ridx[r] = s.glist[k]; }
                 slot[r] = s.hs[ridx[r]] & tmask;
-                line[r] = make_uint4(0, 0, 0, 0);
-                if (act) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
             }
+            uint32_t nslow = 0;
+            // 8 lanes per flow, 16 identity lines in flight per warp; pass 0 = home slot, pass 1 = next slot for
+            // the flows whose home slot is held by another settled flow
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
 #pragma unroll
-            for (int r = 0; r < kInflight; r++) {                  // resolve: first-probe hits on settled flows
-                const bool act = base + r * 4 + g < k_end;
-                const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
-                bool eq = eq4_masked(line[r], rchunk, cmask);
-                const uint64_t tag = u64_of(line[r].z, line[r].w);  // meaningful in lane j == 2 only
-                if (j == 2) eq = eq && (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
-                                 (tag >> TAG_EPOCH_SHIFT) != epoch;
-                const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq) >> (g * 8)) & 0xFFu;
-                const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches at its home slot
-                if (fast && j == 0) s.res[ridx[r]] = slot[r];
-                if (fast && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
-                if (fast && j == 2) {
-                    s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
-                    if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[r]] != 0) {
-                        unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
-                        if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
-                        cs.any_dirty = 1;
+                for (int r = 0; r < kInflight; r++) {
+                    line[r] = make_uint4(0, 0, 0, 0);
+                    if ((pend >> r) & 1u) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
+                }
+#pragma unroll
+                for (int r = 0; r < kInflight; r++) {
+                    const bool act = (pend >> r) & 1u;
+                    const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
+                    bool eq = eq4_masked(line[r], rchunk, cmask);
+                    const uint64_t tag = u64_of(line[r].z, line[r].w);  // meaningful in lane j == 2 only
+                    bool settled = false;
+                    if (j == 2) {
+                        settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                                  (tag >> TAG_EPOCH_SHIFT) != epoch;
+                        eq = eq && settled;
+                    }
+                    const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq) >> (g * 8)) & 0xFFu;
+                    const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g * 8 + 2)) & 1u;
+                    const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches
+                    if (fast && j == 0) s.res[ridx[r]] = slot[r];
+                    if (fast && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
+                    if (fast && j == 2) {
+                        s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                        if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[r]] != 0) {
+                            unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
+                            if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                            cs.any_dirty = 1;
+                        }
+                    }
+                    const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
+                    const bool to_slow = act && !fast && !collide;
+                    if (collide) slot[r] = (slot[r] + 1) & tmask;
+                    else pend &= ~(1u << r);
+                    if (kProf && j == 0) {
+                        if (collide) c_collide++;
+                        if (fast && pass == 1) c_p1fast++;
+                        if (act && !fast && !gsettled) c_unsettled++;
+                    }
+                    const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j == 0);
+                    if (slowb) {
+                        if (to_slow && j == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx[r];
+                        nslow += __popc(slowb);
                     }
                 }
-                const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, act && !fast && j == 0);
-                if (slowb) {
-                    if (act && !fast && j == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx[r];
-                    nslow += __popc(slowb);
-                }
+                if (!__any_sync(0xFFFFFFFFu, pend != 0u)) break;
             }
-        }
-        __syncwarp();
-        if (kProf && lane == 0) { c_reps += k_end - k_begin; c_slow += nslow; }
-        FA_PROF_MARK(3);                                           // pipelined first-probe phase
-        for (uint32_t base = 0; base < nslow; base += 4) {         // inserts, collisions, in-flight publishes
-            const uint32_t k = base + g;
-            const bool act = k < nslow;
-            const uint32_t ri = act ? s.slow[warp][k] : 0;
-            const uint4 rchunk = T[ri * kRecChunks + rc];
-            const uint4 c2 = T[ri * kRecChunks + 2];
-            const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
-            const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
-            const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0,
-                                               dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &cs.any_dirty);
-            if (act && j == 0) s.res[ri] = got;
-            if (act && j == 2) s.fseen[ri] = 0;                     // unknown: issue every reduction
-            if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
-        }
-        __syncwarp();
-        FA_PROF_MARK(4);                                           // general probe loop
+            __syncwarp();
+            if (kProf && lane == 0) { c_reps += c_end - c0; c_slow += nslow; }
+            FA_PROF_MARK(3);                                       // pipelined probe passes
+            for (uint32_t base = 0; base < nslow; base += 4) {     // inserts, long collision chains, in-flight publishes
+                const uint32_t k = base + g;
+                const bool act = k < nslow;
+                const uint32_t ri = act ? s.slow[warp][k] : 0;
+                const uint4 rchunk = T[ri * kRecChunks + rc];
+                const uint4 c2 = T[ri * kRecChunks + 2];
+                const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
+                const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
+                const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0,
+                                                   dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &cs.any_dirty);
+                if (act && j == 0) s.res[ri] = got;
+                if (act && j == 2) s.fseen[ri] = 0;                 // unknown: issue every reduction
+                if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
+            }
+            __syncwarp();
+            FA_PROF_MARK(4);                                       // general probe loop
 
-        // ------------------------------------------------------ one lane per flow: totals into registers
-        const bool mine = k_begin + lane < k_end;
-        uint32_t my_ridx = 0, my_slot = kResSpill, seen = 0;
-        uint64_t t_bytes = 0, t_ns = 0, t_end = 0, floor_ns = 0;
-        uint32_t t_packets = 0, t_flags = 0;
-        if (mine) {
-            my_ridx = s.glist[k_begin + lane];
-            my_slot = s.res[my_ridx];
-            floor_ns = u64_of(s.mir_lo[my_ridx], s.mir_hi[my_ridx]) << 16;   // <= hot.nstart, always
-            seen = s.fseen[my_ridx];
-            const uint4* R = T + my_ridx * kRecChunks;
-            const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
-            const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
-            const uint4 a1 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][4]);
-            const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
-            const uint64_t v_ns = 0ull - v_start;
-            t_bytes = u64_of(r3.z, r3.w) + u64_of(a0.x, a0.y);
-            t_packets = r4.x + a0.z;
-            t_flags = (r4.y >> 16) | a0.w;
-            const uint64_t c_ns = u64_of(a1.x, (uint32_t)(v_ns >> 32)), c_end = u64_of(a1.y, (uint32_t)(v_end >> 32));
-            t_ns = c_ns > v_ns ? c_ns : v_ns;
-            t_end = c_end > v_end ? c_end : v_end;
-            *reinterpret_cast<uint4*>(&s.acc[my_ridx][0]) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(&s.acc[my_ridx][4]) = make_uint4(0, 0, 0, 0);
-            s.tdirty[my_ridx] = 0;
-            // a flow that shows up several times in one tile is hot: give it a cache entry if one is free
-            if (use_cache && a1.z >= kHotMinDups && my_slot != kResSpill) {
-                const uint32_t hh = s.hs[my_ridx];
-                HotEntry& ce = cs.hot[(hh >> 26) & (kHotEntries - 1)];
-                if (*reinterpret_cast<volatile uint32_t*>(&ce.state) == 0u && atomicCAS(&ce.state, 0u, 1u) == 0u) {
+            // -------------------------------------------------- one lane per flow: totals, then the reductions
+            if (c0 + lane < c_end) {
+                const uint32_t my_ridx = s.glist[c0 + lane];
+                const uint32_t my_slot = s.res[my_ridx];
+                const uint64_t floor_ns = u64_of(s.mir_lo[my_ridx], s.mir_hi[my_ridx]) << 16;   // <= hot.nstart, always
+                const uint32_t seen = s.fseen[my_ridx];
+                const uint4* R = T + my_ridx * kRecChunks;
+                const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
+                const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][4]);
+                const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+                const uint64_t v_ns = 0ull - v_start;
+                const uint64_t t_bytes = u64_of(r3.z, r3.w) + u64_of(a0.x, a0.y);
+                const uint32_t t_packets = r4.x + a0.z;
+                const uint32_t t_flags = (r4.y >> 16) | a0.w;
+                const uint64_t c_ns = u64_of(a1.x, (uint32_t)(v_ns >> 32)), c_endts = u64_of(a1.y, (uint32_t)(v_end >> 32));
+                const uint64_t t_ns = c_ns > v_ns ? c_ns : v_ns;
+                const uint64_t t_end = c_endts > v_end ? c_endts : v_end;
+                *reinterpret_cast<uint4*>(&s.acc[my_ridx][0]) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(&s.acc[my_ridx][4]) = make_uint4(0, 0, 0, 0);
+                s.tdirty[my_ridx] = 0;
+                // a flow that shows up several times in one tile is hot: give it a cache entry if one is free
+                if (use_cache && a1.z >= kHotMinDups && my_slot != kResSpill) {
+                    const uint32_t hh = s.hs[my_ridx];
+                    HotEntry& ce = cs.hot[(hh >> 26) & (kHotEntries - 1)];
+                    if (*reinterpret_cast<volatile uint32_t*>(&ce.state) == 0u && atomicCAS(&ce.state, 0u, 1u) == 0u) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) ce.line[c] = ld_cg_u4(&t.ident[(size_t)my_slot * 8 + c]);
-                    *reinterpret_cast<uint4*>(&ce.acc[0]) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4*>(&ce.acc[4]) = make_uint4(0, 0, 0, 0);
-                    ce.hash = hh; ce.slot = my_slot;
-                    ce.ns_hi = (uint32_t)(v_ns >> 32); ce.end_hi = (uint32_t)(v_end >> 32);
-                    __threadfence_block();
-                    *reinterpret_cast<volatile uint32_t*>(&ce.state) = 2u;
-                    if (kProf) c_install++;
+                        for (int c = 0; c < 8; c++) ce.line[c] = ld_cg_u4(&t.ident[(size_t)my_slot * 8 + c]);
+                        *reinterpret_cast<uint4*>(&ce.acc[0]) = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(&ce.acc[4]) = make_uint4(0, 0, 0, 0);
+                        ce.hash = hh; ce.slot = my_slot;
+                        ce.ns_hi = (uint32_t)(v_ns >> 32); ce.end_hi = (uint32_t)(v_end >> 32);
+                        __threadfence_block();
+                        *reinterpret_cast<volatile uint32_t*>(&ce.state) = 2u;
+                        if (kProf) c_install++;
+                    }
+                }
+                if (kSketch) {
+                    const uint4 r0 = R[0], r1 = R[1];
+                    sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
+                                                 u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)), t_packets);
+                }
+                if (my_slot != kResSpill) {
+                    reduce_to_hot(t, my_slot, t_bytes, t_packets, t_ns, t_end, t_flags, floor_ns, seen);
+                } else {                                           // table physically full: spill, never drop silently
+                    const unsigned long long kk = atomicAdd(&ctr->scratch[2], 1ull);
+                    spill_idx[kk] = first + my_ridx;
+                    my_spills++;
                 }
             }
-            if (kSketch) {
-                const uint4 r0 = R[0], r1 = R[1];
-                sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
-                                             u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)), t_packets);
-            }
+            FA_PROF_MARK(5);                                       // totals + reductions
         }
-        FA_PROF_MARK(5);                                           // totals
         team_sync(team);                                           // S2: nobody reads the tile buffer any more
         FA_PROF_MARK(6);                                           // S2 wait
         if (tid == 0) {
-            s.nrep = 0;
+            s.nrep = 0; s.next_chunk = 0;
             const uint32_t nt = tile_idx + tile_stride;
             if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, recs, n, nt); }
-        }
-
-        // ------------------------------------------------------ fire-and-forget reductions on the hot lines
-        if (mine) {
-            if (my_slot != kResSpill) {
-                reduce_to_hot(t, my_slot, t_bytes, t_packets, t_ns, t_end, t_flags, floor_ns, seen);
-            } else {                                               // table physically full: spill, never drop silently
-                const unsigned long long kk = atomicAdd(&ctr->scratch[2], 1ull);
-                spill_idx[kk] = first + my_ridx;
-                my_spills++;
-            }
         }
         FA_PROF_MARK(7);                                           // reductions
     }
@@ -477,6 +496,14 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             atomicAdd(&prof[9], (unsigned long long)c_reps);
             atomicAdd(&prof[10], (unsigned long long)c_slow);
             atomicAdd(&prof[11], (unsigned long long)c_install);
+        }
+        c_collide = __reduce_add_sync(0xFFFFFFFFu, c_collide);
+        c_p1fast = __reduce_add_sync(0xFFFFFFFFu, c_p1fast);
+        c_unsettled = __reduce_add_sync(0xFFFFFFFFu, c_unsettled);
+        if (lane == 0) {
+            atomicAdd(&prof[12], (unsigned long long)c_collide);
+            atomicAdd(&prof[13], (unsigned long long)c_p1fast);
+            atomicAdd(&prof[14], (unsigned long long)c_unsettled);
         }
     }
 

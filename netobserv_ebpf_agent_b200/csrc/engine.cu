@@ -405,6 +405,7 @@ void fa_destroy(fa_engine* e) {
                     (unsigned long long)e->st.records_ingested, 100.0 * p[8] / (double)std::max<uint64_t>(1, e->st.records_ingested),
                     100.0 * p[9] / (double)std::max<uint64_t>(1, e->st.records_ingested),
                     100.0 * p[10] / (double)std::max<uint64_t>(1, e->st.records_ingested), p[11]);
+            fprintf(stderr, "[flowagg] K1 probes: home-slot collisions %llu, resolved one slot on %llu, unsettled at first probe %llu\n", p[12], p[13], p[14]);
         }
         cudaFree(e->d_prof);
     }
