@@ -43,10 +43,12 @@ constexpr uint32_t kProbeLimit = 8192;
 struct __align__(128) TeamSmem {                  // 51,984 B per team
     uint4    tile[kTile * kRecChunks];            // 36,864 B  one TMA-staged tile of records
     uint32_t acc[kTile][8];                       //  8,192 B  what duplicates add to their representative
-    uint4    res[kTile];                          //  4,096 B  probe result per representative: {slot, start mirror low,
-                                                  //           mirror high | flags-seen << 16, compare bits}
     uint32_t hs[kTile];                           //  1,024 B  low 32 bits of the slot hash
+    uint32_t res[kTile];                          //  1,024 B  table slot found for each representative
+    uint32_t mir_lo[kTile];                       //  1,024 B  start mirror of the flow found (see common.cuh)
     uint32_t rep[kRepSlots];                      //  2,048 B  tile-local key -> representative index
+    uint16_t mir_hi[kTile];                       //    512 B
+    uint16_t fseen[kTile];                        //    512 B  tcp flags already present in the flow's hot line
     uint8_t  tdirty[kTile];                       //    256 B  set by duplicates whose descriptor differs
     uint8_t  glist[kTile];                        //    256 B  team-wide compacted list of representatives
     uint8_t  slow[kTile / 32][32];                //    256 B  per-warp flows that need the general probe loop
@@ -341,19 +343,17 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             if (c0 >= nrep_total) break;
             const uint32_t c_end = min(nrep_total, c0 + 4u * kInflight);
             uint4 line[kInflight];
-            uint32_t ridx4 = 0;                                    // record index of each round, one byte each
+            uint32_t ridx[kInflight];
             uint32_t slot[kInflight];
             uint32_t pend = 0;                                     // rounds of this lane group still to be probed
 #pragma unroll
             for (int r = 0; r < kInflight; r++) {
                 const uint32_t k = c0 + r * 4 + g;
-                uint32_t ri = 0;
-                if (k < c_end) { pend |= 1u << r; ri = s.glist[k]; }
-                ridx4 |= ri << (8 * r);
-                slot[r] = s.hs[ri] & tmask;
+                ridx[r] = 0;
+                if (k < c_end) { pend |= 1u << r; ridx[r] = s.glist[k]; }
+                slot[r] = s.hs[ridx[r]] & tmask;
             }
             uint32_t nslow = 0;
-            const uint32_t epoch_lo = (uint32_t)epoch;
             // 8 lanes per flow, 16 identity lines in flight per warp; pass 0 = home slot, pass 1 = next slot for
             // the flows whose home slot is held by another settled flow
 #pragma unroll 1
@@ -363,41 +363,43 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                     line[r] = make_uint4(0, 0, 0, 0);
                     if ((pend >> r) & 1u) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
                 }
-                uint32_t slowmask = 0;                             // rounds of this group that need the general loop
 #pragma unroll
                 for (int r = 0; r < kInflight; r++) {
                     const bool act = (pend >> r) & 1u;
-                    const uint32_t ri = (ridx4 >> (8 * r)) & 0xFFu;
-                    const uint4 rchunk = T[ri * kRecChunks + rc];
+                    const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
                     bool eq = eq4_masked(line[r], rchunk, cmask);
-                    // lane j == 2 holds the tag: published, has a base, and not created by this launch (the low 32
-                    // bits of the epoch differing is sufficient; equal low bits just take the general loop)
-                    const bool settled = (line[r].z & (uint32_t)(TAG_STATE_MASK | TAG_HAS_BASE)) == (uint32_t)(TAG_PUBLISHED | TAG_HAS_BASE) &&
-                                         ((line[r].z >> TAG_EPOCH_SHIFT) | (line[r].w << (32 - TAG_EPOCH_SHIFT))) != epoch_lo;
-                    if (j == 2) eq = eq && settled;
+                    const uint64_t tag = u64_of(line[r].z, line[r].w);  // meaningful in lane j == 2 only
+                    bool settled = false;
+                    if (j == 2) {
+                        settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                                  (tag >> TAG_EPOCH_SHIFT) != epoch;
+                        eq = eq && settled;
+                    }
                     const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq) >> (g * 8)) & 0xFFu;
+                    const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g * 8 + 2)) & 1u;
                     const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches
-                    // one 16-byte store by lane 3 hands everything the reduce step needs to the flow's lane
-                    const uint32_t fseen = __shfl_sync(0xFFFFFFFFu, line[r].z >> TAG_FLAGS_SHIFT, g * 8 + 2) & 0xFFFFu;
-                    if (fast && j == 3)
-                        s.res[ri] = make_uint4(slot[r], line[r].x, (line[r].y >> 16) | (fseen << 16), eqb);
-                    if (fast) pend &= ~(1u << r);
-                    else if (act) slowmask |= 1u << r;
-                }
-                if (__any_sync(0xFFFFFFFFu, slowmask != 0u)) {     // uncommon: collisions, inserts, flows being published
-#pragma unroll
-                    for (int r = 0; r < kInflight; r++) {
-                        const bool miss = (slowmask >> r) & 1u;
-                        const bool settled = (line[r].z & (uint32_t)(TAG_STATE_MASK | TAG_HAS_BASE)) == (uint32_t)(TAG_PUBLISHED | TAG_HAS_BASE) &&
-                                             ((line[r].z >> TAG_EPOCH_SHIFT) | (line[r].w << (32 - TAG_EPOCH_SHIFT))) != epoch_lo;
-                        const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled && j == 2) >> (g * 8 + 2)) & 1u;
-                        const bool collide = miss && gsettled && pass == 0;     // other settled flow: look one slot on
-                        const bool to_slow = miss && !collide;
-                        if (collide) slot[r] = (slot[r] + 1) & tmask;
-                        else pend &= ~(1u << r);
-                        if (kProf && j == 0) { if (collide) c_collide++; if (miss && !gsettled) c_unsettled++; }
-                        const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j == 0);
-                        if (to_slow && j == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (uint8_t)(ridx4 >> (8 * r));
+                    if (fast && j == 0) s.res[ridx[r]] = slot[r];
+                    if (fast && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
+                    if (fast && j == 2) {
+                        s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                        if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[r]] != 0) {
+                            unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
+                            if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                            cs.any_dirty = 1;
+                        }
+                    }
+                    const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
+                    const bool to_slow = act && !fast && !collide;
+                    if (collide) slot[r] = (slot[r] + 1) & tmask;
+                    else pend &= ~(1u << r);
+                    if (kProf && j == 0) {
+                        if (collide) c_collide++;
+                        if (fast && pass == 1) c_p1fast++;
+                        if (act && !fast && !gsettled) c_unsettled++;
+                    }
+                    const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j == 0);
+                    if (slowb) {
+                        if (to_slow && j == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx[r];
                         nslow += __popc(slowb);
                     }
                 }
@@ -416,8 +418,9 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
                 const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0,
                                                    dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &cs.any_dirty);
-                // mirror 0 / no flags seen: issue every reduction; compare bits 0xFF: dirty marking was done in the loop
-                if (act && j == 0) s.res[ri] = make_uint4(got, 0u, 0u, 0xFFu);
+                if (act && j == 0) s.res[ri] = got;
+                if (act && j == 2) s.fseen[ri] = 0;                 // unknown: issue every reduction
+                if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
             }
             __syncwarp();
             FA_PROF_MARK(4);                                       // general probe loop
@@ -425,15 +428,9 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             // -------------------------------------------------- one lane per flow: totals, then the reductions
             if (c0 + lane < c_end) {
                 const uint32_t my_ridx = s.glist[c0 + lane];
-                const uint4 pr = s.res[my_ridx];
-                const uint32_t my_slot = pr.x;
-                const uint64_t floor_ns = u64_of(pr.y, pr.z & 0xFFFFu) << 16;   // start mirror: <= hot.nstart, always
-                const uint32_t seen = pr.z >> 16;
-                if (((pr.w & 0xF8u) != 0xF8u || s.tdirty[my_ridx] != 0) && my_slot != kResSpill) {
-                    // the record's 74-byte descriptor differs from the flow's (or a duplicate's did): ordered re-fold
-                    atomicOr(reinterpret_cast<unsigned long long*>(&t.ident[(size_t)my_slot * 8 + 2]) + 1, (unsigned long long)TAG_DIRTY);
-                    cs.any_dirty = 1;
-                }
+                const uint32_t my_slot = s.res[my_ridx];
+                const uint64_t floor_ns = u64_of(s.mir_lo[my_ridx], s.mir_hi[my_ridx]) << 16;   // <= hot.nstart, always
+                const uint32_t seen = s.fseen[my_ridx];
                 const uint4* R = T + my_ridx * kRecChunks;
                 const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
                 const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
