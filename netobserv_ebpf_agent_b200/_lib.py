@@ -75,7 +75,8 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(HERE, "libflowagg.so")
+    # FA_LIB_NAME: load an alternative build of the same ABI (A/B experiments only)
+    return os.path.join(HERE, os.environ.get("FA_LIB_NAME", "libflowagg.so"))
 
 
 def lib():
