@@ -189,6 +189,10 @@ def run_ours(args, wl):
         else:
             agg.ingest(src, B)
 
+    def finish():                                    # N>1: drain + exchange the batch still in a scratch table
+        if world > 1:
+            agg.flush()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -196,6 +200,7 @@ def run_ours(args, wl):
 
     for i in range(args.warmup):
         step(i)
+    finish()
     barrier()
     st0 = eng.stats()
     sampler = ClockSampler(local)
@@ -206,6 +211,8 @@ def run_ours(args, wl):
     ev[0].record()
     for i in range(args.steps):
         step(args.warmup + i)
+        if i == args.steps - 1:
+            finish()
         ev[i + 1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -55,52 +55,77 @@ class ShardedAggregator:
 
     combine=True puts a local combiner in front of the exchange (the reference does the same thing with its
     per-CPU maps folded in user space, pkg/tracer/tracer.go:1159-1187): each batch is first aggregated into a
-    scratch flow table on the source GPU (K1), lookup-and-deleted (K2) into partial 144-byte flow records, and only
-    those partials are routed — the owner folds partials exactly like single-packet records (AccumulateBase).
-    On heavy-tailed traffic this cuts the bytes crossing NVLink by an order of magnitude."""
+    scratch flow table on the source GPU (K1), drained (K2 in lookup-and-reset mode) into partial 144-byte flow
+    records, and only those partials are routed — the owner folds partials exactly like single-packet records
+    (AccumulateBase).  On heavy-tailed traffic this cuts the bytes crossing NVLink by an order of magnitude.
 
-    def __init__(self, engine, max_batch, device, combine=True):
-        """The engine must have been created on the CURRENT torch stream (cuda_stream=torch.cuda.current_stream()
-        .cuda_stream of a non-default stream): route, the NCCL exchange and the fold are then stream-ordered."""
+    pipeline=True (with combine) ping-pongs two scratch tables on their own streams: while the host drains,
+    routes and exchanges the partials of batch k (several small kernels and host synchronisations), the GPU is
+    already folding batch k+1 into the other scratch table.  Call flush() before reading results."""
+
+    def __init__(self, engine, max_batch, device, combine=True, pipeline=True):
+        """The owner engine must have been created on the CURRENT torch stream (cuda_stream=torch.cuda.
+        current_stream().cuda_stream of a non-default stream): route, the NCCL exchange and the fold are then
+        stream-ordered."""
         import torch
         import torch.distributed as dist
         from .engine import FlowAggEngine
         assert torch.cuda.current_stream().cuda_stream != 0, "use an explicit torch.cuda.Stream (see bench.py)"
         self.eng, self.max_batch, self.world = engine, max_batch, dist.get_world_size()
         self.send = torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device)
-        self.local = None
+        self.locals, self.parts, self.streams = [], [], []
+        self.pending, self.turn = None, 0
         if combine:
-            # scratch flow table of the combiner; flows stay cached across batches (drain, not evict)
-            self.local = FlowAggEngine(4 * max_batch, device=device.index, max_batch=max_batch,
-                                       cuda_stream=torch.cuda.current_stream().cuda_stream)
-            self.part = torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device)
+            for _ in range(2 if pipeline else 1):
+                st = torch.cuda.Stream(device=device) if pipeline else torch.cuda.current_stream()
+                # scratch flow table of the combiner; flows stay cached across batches (drain, not evict)
+                self.locals.append(FlowAggEngine(2 * max_batch, device=device.index, max_batch=max_batch,
+                                                 cuda_stream=st.cuda_stream))
+                self.parts.append(torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device))
+                self.streams.append(st)
         self.exchanged_records = 0
 
     def ingest(self, records, n):
-        """records: device tensor / address of n local records.  Returns records folded on this rank."""
+        """records: device tensor / address of n local records (they must stay valid until flush())."""
+        import torch
         folded, done = 0, 0
         base = records.data_ptr() if hasattr(records, "data_ptr") else int(records)
         while done < n:
             c = min(self.max_batch, n - done)
             src = base + done * REC_BYTES
             done += c
-            if self.local is not None:
-                rc, took = self.local.ingest(src, c)
-                if rc != 0:                          # scratch table full: flush it completely, then fold the rest
-                    import torch
-                    live = self.local.live_flows()
-                    big = torch.empty(max(live, 1) * REC_BYTES, dtype=torch.uint8, device=self.part.device)
-                    k = self.local.evict_into(big, live)
-                    for off in range(0, k, self.max_batch):
-                        folded += self._exchange_and_fold(big.data_ptr() + off * REC_BYTES, min(self.max_batch, k - off))
-                    del big
-                    rc, took2 = self.local.ingest(src + took * REC_BYTES, c - took)
-                    assert rc == 0 and took + took2 == c, (rc, took, took2)
-                # partial flow records of this batch; the flows stay cached in the scratch table
-                c = self.local.drain_active(self.part, self.max_batch)
-                src = self.part.data_ptr()
-            folded += self._exchange_and_fold(src, c)
+            if not self.locals:
+                folded += self._exchange_and_fold(src, c)
+                continue
+            i = self.turn
+            self.turn = (self.turn + 1) % len(self.locals)
+            if self.pending == i:                    # single scratch table: finish the previous batch first
+                folded += self._finish(i)
+            self.streams[i].wait_stream(torch.cuda.current_stream())   # the batch may have been produced on the main stream
+            rc, took = self.locals[i].ingest(src, c)                   # asynchronous on the scratch table's stream
+            if self.pending is not None and self.pending != i:
+                folded += self._finish(self.pending)                   # overlaps with the fold just launched
+            if rc != 0:                              # scratch table full: flush it completely, then fold the rest
+                live = self.locals[i].live_flows()
+                big = torch.empty(max(live, 1) * REC_BYTES, dtype=torch.uint8, device=self.send.device)
+                k = self.locals[i].evict_into(big, live)
+                for off in range(0, k, self.max_batch):
+                    folded += self._exchange_and_fold(big.data_ptr() + off * REC_BYTES, min(self.max_batch, k - off))
+                del big
+                rc, took2 = self.locals[i].ingest(src + took * REC_BYTES, c - took)
+                assert rc == 0 and took + took2 == c, (rc, took, took2)
+            self.pending = i
         return folded
+
+    def _finish(self, i):
+        # partial flow records of the batch folded into scratch table i; the flows stay cached there
+        c = self.locals[i].drain_active(self.parts[i], self.max_batch)     # host-synchronous on that table's stream
+        self.pending = None
+        return self._exchange_and_fold(self.parts[i].data_ptr(), c)
+
+    def flush(self):
+        """Drain + exchange whatever is still sitting in a scratch table."""
+        return self._finish(self.pending) if self.pending is not None else 0
 
     def _exchange_and_fold(self, src, c):
         self.exchanged_records += c
@@ -112,5 +137,6 @@ class ShardedAggregator:
         return tot
 
     def close(self):
-        if self.local is not None:
-            self.local.close()
+        for l in self.locals:
+            l.close()
+        self.locals = []

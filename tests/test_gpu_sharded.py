@@ -33,10 +33,13 @@ def _worker(rank, world, port, q, combine):
     torch.cuda.set_stream(stream)
     eng = fa.FlowAggEngine(1 << 18, device=rank, max_batch=30_000, cuda_stream=stream.cuda_stream)
     agg = ShardedAggregator(eng, 30_000, dev, combine=combine)
+    keep = []
     for b in range(3):
         local = gen_host(seed=50, n=100_000, n_keys=40_000, dist=1, first=(b * world + rank) * 100_000)
         t = torch.from_numpy(np.ascontiguousarray(local).reshape(-1).copy()).to(dev)
         agg.ingest(t, 100_000)
+        keep.append(t)                               # batches stay valid until flush()
+    agg.flush()
     out = eng.evict()
     assert (owner_of(out[:, :40], world) == rank).all()
     q.put((rank, out.copy()))
