@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Throughput of the secondary kernels (not the headline bench): fused count-min + HyperLogLog (BASELINE config 3
+shape, scaled), RTT / DNS feature folds (config 5 shape, scaled), K2 evict.  Prints one JSON line per measurement."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import netobserv_ebpf_agent_b200 as fa  # noqa: E402
+
+REC = 144
+dev = torch.device("cuda", 0)
+stream = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(stream)
+
+
+def timed(fn, n_iter):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(n_iter):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / 1e3
+
+
+def sketch_bench(n_keys=100_000_000, B=1 << 24, steps=12):
+    eng = fa.FlowAggEngine(1 << 27, flags=fa.FA_F_ENABLE_SKETCH, cms_log2_width=20, cms_depth=4, hll_precision=14,
+                           max_batch=B, cuda_stream=stream.cuda_stream)
+    gp = fa.GenParams(seed=3, n_keys=n_keys, dist=1, zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0)
+    ring = []
+    for i in range(4):
+        t = torch.empty(B * REC, dtype=torch.uint8, device=dev)
+        eng.gen_records(gp, i * B, B, t)
+        ring.append(t)
+    eng.sync()
+    for i in range(2):
+        eng.ingest(ring[i % 4].data_ptr(), B)
+    dt = timed(lambda i: eng.ingest(ring[i % 4].data_ptr(), B), steps)
+    n = (steps + 2) * B
+    flows = eng.live_flows()
+    est = eng.hll_estimate()
+    print(json.dumps({"bench": "K1 + fused count-min(w=2^20,d=4) + HLL(p=14)", "workload": f"{n_keys} Zipf-1.1 keys",
+                      "Mpkts_s": B * steps / dt / 1e6, "records": n, "distinct_exact": flows, "hll_estimate": est,
+                      "hll_rel_err": abs(est - flows) / flows}), flush=True)
+    eng.close()
+
+
+def feature_bench(n_keys=1_000_000, B=1 << 22, steps=8):
+    from test_gpu_features import keys_of, make_add, make_dns
+    import oracle_lib as O
+    eng = fa.FlowAggEngine(1 << 24, flags=fa.FA_F_ENABLE_RTT | fa.FA_F_ENABLE_DNS, max_batch=B, cuda_stream=stream.cuda_stream)
+    rng = np.random.default_rng(5)
+    gp = fa.GenParams(seed=5, n_keys=n_keys, dist=1, zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0)
+    base = torch.empty(B * REC, dtype=torch.uint8, device=dev)
+    eng.gen_records(gp, 0, B, base)
+    eng.sync()
+    keys = base.cpu().numpy().reshape(-1, REC)[:200_000, :40]
+    dns = torch.from_numpy(O.as_bytes(make_dns(rng, keys, B // 4)).copy()).to(dev)
+    add = torch.from_numpy(O.as_bytes(make_add(rng, keys, B // 4)).copy()).to(dev)
+    eng.ingest(base.data_ptr(), B)
+    eng.ingest_dns(dns); eng.ingest_additional(add)
+    t_dns = timed(lambda i: eng.ingest_dns(dns), steps)
+    t_add = timed(lambda i: eng.ingest_additional(add), steps)
+    t0 = time.perf_counter()
+    out = eng.evict(features=True)
+    t_ev = time.perf_counter() - t0
+    print(json.dumps({"bench": "K6 feature folds", "dns_Msamples_s": (B // 4) * steps / t_dns / 1e6,
+                      "additional_Msamples_s": (B // 4) * steps / t_add / 1e6, "flows": len(out[0]),
+                      "evict_with_features_to_host_s": t_ev}), flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    sketch_bench()
+    feature_bench()
