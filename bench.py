@@ -176,7 +176,8 @@ def run_ours(args, wl):
     assert stream.cuda_stream != 0
     if world > 1:
         args.max_batch = B          # one route -> exchange -> fold round per step: amortises the host-side syncs
-    eng = fa.FlowAggEngine(args.max_entries, device=local, max_batch=args.max_batch, cuda_stream=stream.cuda_stream)
+    eng = fa.FlowAggEngine(args.max_entries, device=local, max_batch=args.max_batch, cuda_stream=stream.cuda_stream,
+                           flags=fa.FA_F_NO_FULL_CUT if (world > 1 and args.exchange == "peer") else 0)
     # one key universe for the whole job; every rank generates its own slice of the record stream
     gp = fa.GenParams(seed=wl["seed"], n_keys=wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100,
                       t0_ns=1_000_000, varying_desc=0)
@@ -188,9 +189,13 @@ def run_ours(args, wl):
     eng.sync()
 
     if world > 1:
-        from netobserv_ebpf_agent_b200.sharded import ShardedAggregator
-        # local combine (K1+K2) -> K3 route -> NCCL all-to-all -> K1 on the owner
-        agg = ShardedAggregator(eng, args.max_batch, dev, combine=not args.no_combine)
+        from netobserv_ebpf_agent_b200.sharded import PeerShardedAggregator, ShardedAggregator
+        if args.exchange == "peer":
+            # local combine (K1+K2) -> K3 fused with the exchange (peer stores over NVLink) -> K1 on the owner
+            agg = PeerShardedAggregator(eng, args.max_batch, dev)
+        else:
+            # local combine (K1+K2) -> K3 route -> NCCL all-to-all -> K1 on the owner
+            agg = ShardedAggregator(eng, args.max_batch, dev, combine=not args.no_combine)
 
     def step(i):
         src = batches[i % ring]
@@ -286,7 +291,8 @@ def run_ours(args, wl):
                            f"{ring} distinct batches cycled)",
                            "parallelism": "1 GPU" if world == 1 else
                            f"hash-sharded x{world}: " + ("" if args.no_combine else "per-batch local combine (K1+K2) -> ") +
-                           "K3 route -> NCCL all-to-all -> K1 on the owner",
+                           ("K3 fused with the exchange (peer stores over NVLink, device-side counts)" if args.exchange == "peer"
+                            else "K3 route -> NCCL all-to-all") + " -> K1 on the owner",
                            "exchanged_records_per_step_rank0": (agg.exchanged_records // (args.steps + args.warmup)) if world > 1 else None},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (NCU_DRAM_BYTES_PER_RECORD[args.workload] * min(B, args.max_batch)
@@ -325,6 +331,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1 << 24)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-combine", action="store_true", help="N>1: route raw records instead of per-batch partial flows")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: 'peer' = K3 stores into the owners' buffers over NVLink (no host sync); 'nccl' = all_to_all_single")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

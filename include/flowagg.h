@@ -169,6 +169,8 @@ typedef struct fa_config {
 #define FA_F_ENABLE_RTT     0x1u  /* ENABLE_RTT            (config.go:230) */
 #define FA_F_ENABLE_DNS     0x2u  /* ENABLE_DNS_TRACKING   (config.go:236) */
 #define FA_F_ENABLE_SKETCH  0x4u  /* fused count-min + HyperLogLog update in fa_ingest */
+#define FA_F_NO_FULL_CUT    0x8u  /* never return FA_FULL: max_entries only sizes the table (KERNEL_MAP-style caches,
+                                     multi-GPU scratch / owner tables); a physically full table spills (fa_stats.spills) */
 
 typedef struct fa_stats {
     uint64_t records_ingested;    /* flow records consumed by fa_ingest          */
@@ -267,6 +269,27 @@ uint64_t fa_owner_hash(const fa_flow_id* key);
  * are device pointers. */
 int fa_route(fa_engine* e, const void* flow_records, size_t n, uint32_t n_shards,
              void* out, uint64_t* counts_host);
+
+/* ---- fused routing + exchange over peer memory (one process per GPU, same box) ----
+ * The owners' receive buffers and record counters are plain device allocations (fa_device_alloc) exported with
+ * CUDA IPC and mapped by every peer.  fa_route_peer is K3 fused with the all-to-all: it partitions the records by
+ * owner and stores them straight into the owners' buffers over NVLink, reserving room with one remote atomic per
+ * CTA and shard.  Sizes never travel through the host: *_counted entry points read their record count from device
+ * memory, so a whole round (combine, drain, route+exchange, owner fold) is enqueued without a host synchronisation. */
+#define FA_IPC_HANDLE_BYTES 64
+int fa_ipc_export(fa_engine* e, void* dev_ptr, uint8_t handle_out[FA_IPC_HANDLE_BYTES]);
+int fa_ipc_open(fa_engine* e, const uint8_t handle[FA_IPC_HANDLE_BYTES], void** out);
+int fa_ipc_close(fa_engine* e, void* mapped);
+/* Like fa_drain_active, but asynchronous: the number of partial records lands in *n_dev_out (device memory). */
+int fa_drain_active_counted(fa_engine* e, void* out_records_dev, size_t cap, uint64_t* n_dev_out);
+/* Partition min(*n_dev, max_n) device-resident records (n_dev may be NULL: exactly max_n) by owner and store them
+ * into peer_bufs[owner] (capacity cap records each), advancing *peer_counts[owner]. Records that do not fit are
+ * counted in *overflow_dev. */
+int fa_route_peer(fa_engine* e, const void* records_dev, const uint64_t* n_dev, size_t max_n, uint32_t n_shards,
+                  void* const* peer_bufs, uint64_t* const* peer_counts, size_t cap, uint64_t* overflow_dev);
+/* fa_ingest for a device-resident batch whose size (<= max_n) is only known on the device; reset_count != 0
+ * zeroes *n_dev after the fold has been enqueued.  Requires FA_F_NO_FULL_CUT. */
+int fa_ingest_counted(fa_engine* e, const void* records_dev, uint64_t* n_dev, size_t max_n, int reset_count);
 
 /* ------------------------------------------- memory + synthetic generator */
 

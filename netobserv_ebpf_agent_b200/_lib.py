@@ -8,7 +8,7 @@ REC_BYTES, ID_BYTES, DNS_BYTES, ADD_BYTES, DNSREC_BYTES, ADDREC_BYTES = 144, 40,
 FA_OK, FA_FULL = 0, 1
 FA_E_INVAL, FA_E_NOMEM, FA_E_CUDA, FA_E_NODEV, FA_E_2BIG, FA_E_CLOSED = -22, -12, -5, -19, -7, -9
 FA_MODE_ACCOUNTER, FA_MODE_KERNEL_MAP = 0, 1
-FA_F_ENABLE_RTT, FA_F_ENABLE_DNS, FA_F_ENABLE_SKETCH = 1, 2, 4
+FA_F_ENABLE_RTT, FA_F_ENABLE_DNS, FA_F_ENABLE_SKETCH, FA_F_NO_FULL_CUT = 1, 2, 4, 8
 FA_GEN_UNIFORM, FA_GEN_ZIPF = 0, 1
 FA_ABI_VERSION = 1
 
@@ -53,6 +53,13 @@ SIGNATURES = {
     "fa_evict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                            C.POINTER(C.c_size_t)]),
     "fa_drain_active": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "fa_drain_active_counted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "fa_route_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p]),
+    "fa_ingest_counted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "fa_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fa_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fa_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fa_live_flows": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
     "fa_purge_stale_dns": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "fa_cms_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

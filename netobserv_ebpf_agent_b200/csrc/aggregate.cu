@@ -193,7 +193,7 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
 // kProf: per-warp cycle counters per phase (FA_PHASE_PROFILE=1), summed into prof[0..7].
 #define FA_PROF_MARK(i) do { if (kProf) { const long long now_ = clock64(); pacc[i] += now_ - pt; pt = now_; } } while (0)
 
-template <bool kSketch, bool kProf>
+template <bool kSketch, bool kProf, bool kDevN>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
                  uint32_t* __restrict__ spill_idx, SketchParams sk, unsigned long long* prof, uint32_t opt) {
@@ -202,6 +202,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     const int team = threadIdx.x >> 8;
     const int tid = threadIdx.x & (kTile - 1), lane = tid & 31, warp = tid >> 5;     // within the team
     TeamSmem& s = cs.team[team];
+    if (kDevN) n = min(n, (uint32_t)ctr->launch_n);            // size known on the device only (multi-GPU receive side)
     const uint32_t n_tiles = (n + kTile - 1) / kTile;
     const uint32_t tile_stride = gridDim.x * kTeams;
     const uint32_t tile0 = blockIdx.x * kTeams + team;
@@ -555,8 +556,9 @@ __device__ __forceinline__ uint32_t scratch_home(uint64_t slot, uint32_t smask) 
 }
 
 __global__ void fixup_scan_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, Counters* ctr, FixupScratch* scratch,
-                                  uint32_t smask) {
+                                  uint32_t smask, uint32_t opt) {
     if (*reinterpret_cast<volatile unsigned long long*>(&ctr->dirty) == 0ull) return;
+    if (opt & 16u) n = min(n, (uint32_t)ctr->launch_n);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint4* R = recs + (size_t)i * kRecChunks;
         const uint4 k0 = R[0], k1 = R[1], k2 = R[2];
@@ -645,21 +647,30 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
     static bool attr_done = false;
     const int smem = (int)sizeof(AggSmem);
     if (!attr_done) {
-        cudaFuncSetAttribute(aggregate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
     const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
     const int grid = (int)min((uint32_t)a.sm_count, (n_tiles + kTeams - 1) / kTeams);
+    const bool dev_n = (a.opt & 16u) != 0;                 // a.n is an upper bound, the count is in ctr->launch_n
+#define FA_K1_ARGS a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk
     if (a.prof)
-        aggregate_kernel<false, true><<<grid, kCtaThreads, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, a.prof, a.opt);
+        aggregate_kernel<false, true, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, a.prof, a.opt);
+    else if (a.sk.cms && dev_n)
+        aggregate_kernel<true, false, true><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
     else if (a.sk.cms)
-        aggregate_kernel<true, false><<<grid, kCtaThreads, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, nullptr, a.opt);
+        aggregate_kernel<true, false, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
+    else if (dev_n)
+        aggregate_kernel<false, false, true><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
     else
-        aggregate_kernel<false, false><<<grid, kCtaThreads, smem, st>>>(a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk, nullptr, a.opt);
+        aggregate_kernel<false, false, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
+#undef FA_K1_ARGS
     const int fgrid = a.sm_count * 2;
-    fixup_scan_kernel<<<fgrid, 256, 0, st>>>(a.recs, a.n, a.table, a.ctr, a.scratch, a.scratch_slots - 1);
+    fixup_scan_kernel<<<fgrid, 256, 0, st>>>(a.recs, a.n, a.table, a.ctr, a.scratch, a.scratch_slots - 1, a.opt);
     fixup_apply_kernel<<<fgrid, 256, 0, st>>>(a.recs, a.table, a.epoch, a.ctr, a.scratch, a.scratch_slots,
                                               reinterpret_cast<unsigned int*>(&a.ctr->scratch[1]));
     return 3;

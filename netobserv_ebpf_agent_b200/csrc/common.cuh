@@ -69,6 +69,7 @@ struct Counters {
     unsigned long long fixups_total;  // running total of ordered re-folds
     unsigned long long evict_out;     // output cursor of the evict kernel
     unsigned long long scratch[3];
+    unsigned long long launch_n;      // record count of a launch whose size is only known on the device (opt bit 4)
 };
 
 // ------------------------------------------------------------------ hash spec

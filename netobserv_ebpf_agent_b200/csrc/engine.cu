@@ -210,6 +210,12 @@ int ingest_chunk_accounter(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint
     *consumed = 0;
     const uint64_t M = e->cfg.max_entries;
     retire_completed(e);
+    if (e->cfg.flags & FA_F_NO_FULL_CUT) {              // max_entries only sizes the table
+        int rc = launch_chunk(e, d_recs, n);
+        if (rc) return rc;
+        *consumed = n;
+        return FA_OK;
+    }
     if (e->live_known + e->unsynced_records + n > M) {
         int rc = sync_counters(e);                     // exact live count
         if (rc) return rc;
@@ -595,6 +601,78 @@ int fa_drain_active(fa_engine* e, void* out_records_dev, size_t cap, size_t* n_o
     return FA_OK;
 }
 
+int fa_drain_active_counted(fa_engine* e, void* out_records_dev, size_t cap, uint64_t* n_dev_out) {
+    if (!e || !out_records_dev || !n_dev_out) return fail(FA_E_INVAL, "fa_drain_active_counted: null argument");
+    if (e->table.feat_add || e->table.feat_dns) return fail(FA_E_INVAL, "fa_drain_active_counted: not available with feature folds enabled");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
+    e->st.kernel_launches += fa::launch_evict(e->table, static_cast<uint4*>(out_records_dev), nullptr, cap, e->d_ctr,
+                                              e->sm_count, e->stream, /*drain=*/true);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(n_dev_out, &e->d_ctr->evict_out, 8, cudaMemcpyDeviceToDevice, e->stream));
+    return FA_OK;
+}
+
+int fa_route_peer(fa_engine* e, const void* recs, const uint64_t* n_dev, size_t max_n, uint32_t n_shards,
+                  void* const* peer_bufs, uint64_t* const* peer_counts, size_t cap, uint64_t* overflow_dev) {
+    if (!e || !recs || !peer_bufs || !peer_counts || !overflow_dev) return fail(FA_E_INVAL, "fa_route_peer: null argument");
+    if (n_shards == 0 || n_shards > 16) return fail(FA_E_INVAL, "fa_route_peer: n_shards must be 1..16");
+    if (max_n > 0xFFFFFFFFull) return fail(FA_E_INVAL, "fa_route_peer: max_n too large");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    fa::PeerTargets pt{};
+    for (uint32_t i = 0; i < n_shards; i++) {
+        pt.buf[i] = static_cast<uint4*>(peer_bufs[i]);
+        pt.count[i] = reinterpret_cast<unsigned long long*>(peer_counts[i]);
+    }
+    e->st.kernel_launches += fa::launch_route_peer(static_cast<const uint4*>(recs), reinterpret_cast<const unsigned long long*>(n_dev),
+                                                   (uint32_t)max_n, n_shards, pt, cap, reinterpret_cast<unsigned long long*>(overflow_dev), e->stream);
+    CU(cudaGetLastError());
+    return FA_OK;
+}
+
+int fa_ingest_counted(fa_engine* e, const void* recs, uint64_t* n_dev, size_t max_n, int reset_count) {
+    if (!e || !recs || !n_dev) return fail(FA_E_INVAL, "fa_ingest_counted: null argument");
+    if (!(e->cfg.flags & FA_F_NO_FULL_CUT)) return fail(FA_E_INVAL, "fa_ingest_counted: engine needs FA_F_NO_FULL_CUT");
+    if (max_n == 0 || max_n > e->max_batch) return fail(FA_E_INVAL, "fa_ingest_counted: max_n must be 1..max_batch");
+    if (reinterpret_cast<uintptr_t>(recs) & 15) return fail(FA_E_INVAL, "fa_ingest_counted: records must be 16-byte aligned");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(&e->d_ctr->launch_n, n_dev, 8, cudaMemcpyDeviceToDevice, e->stream));
+    const uint32_t saved = e->k1_opt;
+    e->k1_opt |= 16u;
+    int rc = launch_chunk(e, static_cast<const uint8_t*>(recs), (uint32_t)max_n);
+    e->k1_opt = saved;
+    if (rc) return rc;
+    if (reset_count) CU(cudaMemsetAsync(n_dev, 0, 8, e->stream));
+    return FA_OK;
+}
+
+int fa_ipc_export(fa_engine* e, void* dev_ptr, uint8_t handle_out[FA_IPC_HANDLE_BYTES]) {
+    if (!e || !dev_ptr || !handle_out) return fail(FA_E_INVAL, "fa_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == FA_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle_out, &h, sizeof h);
+    return FA_OK;
+}
+int fa_ipc_open(fa_engine* e, const uint8_t handle[FA_IPC_HANDLE_BYTES], void** out) {
+    if (!e || !handle || !out) return fail(FA_E_INVAL, "fa_ipc_open: null argument");
+    CU(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CU(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return FA_OK;
+}
+int fa_ipc_close(fa_engine* e, void* mapped) {
+    if (!e) return fail(FA_E_INVAL, "fa_ipc_close: null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaIpcCloseMemHandle(mapped));
+    return FA_OK;
+}
+
 int fa_purge_stale_dns(fa_engine* e, uint64_t, uint64_t) {
     if (!e) return fail(FA_E_INVAL, "fa_purge_stale_dns: null engine");
     return FA_OK;   // pre-computed-latency DNS contract (SURVEY.md §8 a12'): no query table to purge
@@ -719,6 +797,7 @@ int fa_device_alloc(fa_engine* e, size_t bytes, void** out) {
     if (!e || !out) return fail(FA_E_INVAL, "fa_device_alloc: null argument");
     CU(cudaSetDevice(e->device));
     CU(cudaMalloc(out, bytes ? bytes : 16));
+    CU(cudaMemset(*out, 0, bytes ? bytes : 16));       // zero-initialised (counters, receive buffers)
     return FA_OK;
 }
 int fa_device_free(fa_engine* e, void* p) {

@@ -72,6 +72,11 @@ int launch_hll_pack(const SketchParams& sk, uint8_t* out_regs, cudaStream_t st);
 struct GenDeviceParams;
 int launch_generate(const GenDeviceParams& g, uint64_t first_index, uint32_t n, uint4* dst, cudaStream_t st);
 
+// routing fused with the exchange: destinations are peer-mapped receive buffers + their record counters
+struct PeerTargets { uint4* buf[16]; unsigned long long* count[16]; };
+int launch_route_peer(const uint4* recs, const unsigned long long* n_dev, uint32_t max_n, uint32_t n_shards,
+                      const PeerTargets& pt, unsigned long long cap, unsigned long long* overflow, cudaStream_t st);
+
 // routing (K3)
 int launch_route(const uint4* recs, uint32_t n, uint32_t n_shards, uint4* out, unsigned long long* counts_dev,
                  uint32_t* tmp_owner, int sm_count, cudaStream_t st);

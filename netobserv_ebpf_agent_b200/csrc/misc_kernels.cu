@@ -236,6 +236,84 @@ __global__ void route_scatter_kernel(const uint4* __restrict__ recs, uint32_t n,
         }
     }
 }
+// ------------------------------------------------------------------ K3 fused with the exchange: peer stores
+// One kernel partitions the records by owner AND delivers them: every CTA reserves room in each owner's
+// receive buffer with one remote atomicAdd (system scope, over NVLink) and stores its records straight
+// into peer memory (mapped with CUDA IPC).  No NCCL call, no size known to the host: the owner reads its
+// record count from its own memory.  n itself may live on the device (count of a preceding drain).
+__global__ void route_peer_kernel(const uint4* __restrict__ recs, const unsigned long long* __restrict__ n_dev, uint32_t max_n,
+                                  uint32_t n_shards, PeerTargets pt, unsigned long long cap, unsigned long long* overflow) {
+    __shared__ uint32_t wcount[kRouteThreads / 32][kMaxShards];
+    __shared__ uint32_t cta_cnt[kMaxShards];
+    __shared__ unsigned long long cursor[kMaxShards];
+    __shared__ uint8_t own[kRoutePerCta];
+    const uint32_t n = n_dev ? (uint32_t)min((unsigned long long)max_n, *n_dev) : max_n;
+    const uint32_t base = blockIdx.x * kRoutePerCta;
+    if (base >= n) return;
+    if (threadIdx.x < kMaxShards) cta_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < kRoutePerCta; k += kRouteThreads) {
+        const uint32_t i = base + k;
+        uint32_t o = 0xFFu;
+        if (i < n) {
+            const uint4* R = recs + (size_t)i * kRecChunks;
+            const uint4 k0 = R[0], k1 = R[1], k2 = R[2];
+            const uint64_t pm = key_premix(u64_of(k0.x, k0.y), u64_of(k0.z, k0.w), u64_of(k1.x, k1.y), u64_of(k1.z, k1.w), u64_of(k2.x, k2.y));
+            o = (uint32_t)(owner_hash(pm) % n_shards);
+            atomicAdd(&cta_cnt[o], 1u);
+        }
+        own[k] = (uint8_t)o;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_shards)                          // reserve this CTA's range in every owner's receive buffer
+        cursor[threadIdx.x] = cta_cnt[threadIdx.x] ? atomicAdd_system(pt.count[threadIdx.x], (unsigned long long)cta_cnt[threadIdx.x]) : 0ull;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t round = 0; round < kRoutePerCta / kRouteThreads; round++) {
+        const uint32_t k = round * kRouteThreads + threadIdx.x;
+        const uint32_t i = base + k;
+        const uint32_t o = own[k];
+        const bool valid = o != 0xFFu;
+        uint32_t rank = 0;
+        for (uint32_t s = 0; s < n_shards; s++) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, o == s);
+            if (o == s) rank = __popc(m & ((1u << lane) - 1u));
+            if (lane == 0) wcount[warp][s] = __popc(m);
+        }
+        __syncthreads();
+        unsigned long long dst = 0;
+        if (valid) {
+            dst = cursor[o] + rank;
+            for (int w = 0; w < warp; w++) dst += wcount[w][o];
+        }
+        __syncthreads();
+        if (threadIdx.x < n_shards) {
+            uint32_t t = 0;
+            for (int w = 0; w < kRouteThreads / 32; w++) t += wcount[w][threadIdx.x];
+            cursor[threadIdx.x] += t;
+        }
+        if (valid) {
+            if (dst < cap) {
+                const uint4* R = recs + (size_t)i * kRecChunks;
+                uint4* O = pt.buf[o] + dst * kRecChunks;                 // peer (or local) memory
+                uint4 v[kRecChunks];
+#pragma unroll
+                for (int c = 0; c < kRecChunks; c++) v[c] = ld_stream_u4(R + c);
+#pragma unroll
+                for (int c = 0; c < kRecChunks; c++) O[c] = v[c];
+            } else {
+                atomicAdd(overflow, 1ull);                                // receive buffer too small: counted, reported at flush
+            }
+        }
+    }
+    __threadfence_system();                                               // peer stores visible before the kernel retires
+}
+int launch_route_peer(const uint4* recs, const unsigned long long* n_dev, uint32_t max_n, uint32_t n_shards,
+                      const PeerTargets& pt, unsigned long long cap, unsigned long long* overflow, cudaStream_t st) {
+    if (!max_n) return 0;
+    route_peer_kernel<<<(max_n + kRoutePerCta - 1) / kRoutePerCta, kRouteThreads, 0, st>>>(recs, n_dev, max_n, n_shards, pt, cap, overflow);
+    return 1;
+}
+
 int launch_route(const uint4* recs, uint32_t n, uint32_t n_shards, uint4* out, unsigned long long* counts_dev,
                  uint32_t* tmp, int sm_count, cudaStream_t st) {
     if (!n) { cudaMemsetAsync(counts_dev, 0, n_shards * sizeof(unsigned long long), st); return 0; }

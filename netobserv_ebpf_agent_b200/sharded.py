@@ -140,3 +140,114 @@ class ShardedAggregator:
         for l in self.locals:
             l.close()
         self.locals = []
+
+
+class PeerShardedAggregator:
+    """Sharded aggregation with the exchange fused into K3: no NCCL data movement, no host synchronisation.
+
+    Per batch, all enqueued on one stream without waiting for anything:
+      K1 into the scratch table (local combine) -> K2 drain (count stays on the device) ->
+      K3 `fa_route_peer`: partition the partials by owner and store them straight into the owners' receive
+      buffers over NVLink (CUDA IPC mappings, one remote atomicAdd per CTA and shard reserves the room) ->
+      a 4-byte NCCL all-reduce as stream-ordered barrier -> the owner folds what it received
+      (`fa_ingest_counted`, count read from its own device memory) and re-arms the buffer.
+    Receive buffers are double-buffered so that batch k+1 may be delivered while batch k is being folded."""
+
+    def __init__(self, engine, max_batch, device, recv_cap=None):
+        import torch
+        import torch.distributed as dist
+        from ._lib import FA_F_NO_FULL_CUT, check
+        from .engine import FlowAggEngine
+        assert torch.cuda.current_stream().cuda_stream != 0, "use an explicit torch.cuda.Stream (see bench.py)"
+        self.eng, self.max_batch = engine, max_batch
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.recv_cap = recv_cap or max_batch
+        self.local = FlowAggEngine(2 * max_batch, device=device.index, max_batch=max_batch, flags=FA_F_NO_FULL_CUT,
+                                   cuda_stream=torch.cuda.current_stream().cuda_stream)
+        self.part = torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device)
+        self.part_n = torch.zeros(1, dtype=torch.int64, device=device)
+        self.token = torch.zeros(1, dtype=torch.int32, device=device)
+        L = lib()
+
+        def dalloc(nbytes):
+            p = C.c_void_p()
+            check(L.fa_device_alloc(engine._h, nbytes, C.byref(p)))
+            return p.value
+        self.mine = [(dalloc(self.recv_cap * REC_BYTES), dalloc(8)) for _ in range(2)]     # (buffer, counter) x 2
+        self.overflow = dalloc(8)
+        # exchange the IPC handles of the four allocations and map every peer's
+        hbuf = np.zeros((4, 64), dtype=np.uint8)
+        for i, p in enumerate([self.mine[0][0], self.mine[0][1], self.mine[1][0], self.mine[1][1]]):
+            check(L.fa_ipc_export(engine._h, C.c_void_p(p), C.c_void_p(hbuf[i].ctypes.data)))
+        mine_t = torch.from_numpy(hbuf.reshape(-1).copy()).to(device)
+        all_t = [torch.empty_like(mine_t) for _ in range(self.world)]
+        dist.all_gather(all_t, mine_t)
+        self.mapped = []
+        self.bufs = [(C.c_void_p * 16)() for _ in range(2)]
+        self.cnts = [(C.c_void_p * 16)() for _ in range(2)]
+        for r in range(self.world):
+            hs = all_t[r].cpu().numpy().reshape(4, 64)
+            ptrs = []
+            for i in range(4):
+                if r == self.rank:
+                    ptrs.append([self.mine[0][0], self.mine[0][1], self.mine[1][0], self.mine[1][1]][i])
+                else:
+                    q = C.c_void_p()
+                    hh = np.ascontiguousarray(hs[i])
+                    check(L.fa_ipc_open(engine._h, C.c_void_p(hh.ctypes.data), C.byref(q)))
+                    self.mapped.append(q.value)
+                    ptrs.append(q.value)
+            self.bufs[0][r], self.cnts[0][r], self.bufs[1][r], self.cnts[1][r] = ptrs
+        dist.barrier()
+        self.step = 0
+        self.exchanged_records = 0      # not known on the host in this mode
+
+    def ingest(self, records, n):
+        import torch.distributed as dist
+        from ._lib import check
+        L = lib()
+        base = records.data_ptr() if hasattr(records, "data_ptr") else int(records)
+        done = 0
+        while done < n:
+            c = min(self.max_batch, n - done)
+            b = self.step & 1
+            rc, took = self.local.ingest(base + done * REC_BYTES, c)
+            assert rc == 0 and took == c, (rc, took)
+            check(L.fa_drain_active_counted(self.local._h, C.c_void_p(self.part.data_ptr()), self.max_batch,
+                                            C.c_void_p(self.part_n.data_ptr())))
+            check(L.fa_route_peer(self.eng._h, C.c_void_p(self.part.data_ptr()), C.c_void_p(self.part_n.data_ptr()),
+                                  self.max_batch, self.world, self.bufs[b], self.cnts[b], self.recv_cap,
+                                  C.c_void_p(self.overflow)))
+            dist.all_reduce(self.token)                    # stream-ordered barrier: every rank has delivered batch `step`
+            check(L.fa_ingest_counted(self.eng._h, C.c_void_p(self.mine[b][0]), C.c_void_p(self.mine[b][1]),
+                                      self.recv_cap, 1))
+            self.step += 1
+            done += c
+        return 0
+
+    def flush(self):
+        import torch
+        torch.cuda.current_stream().synchronize()
+        ov = np.zeros(1, dtype=np.uint64)
+        import ctypes
+        cudart = ctypes.CDLL("libcudart.so")
+        cudart.cudaMemcpy(ctypes.c_void_p(ov.ctypes.data), ctypes.c_void_p(self.overflow), 8, 2)
+        if int(ov[0]):
+            raise RuntimeError(f"peer receive buffer overflow: {int(ov[0])} records did not fit (raise recv_cap)")
+        return 0
+
+    def close(self):
+        import torch.distributed as dist
+        from ._lib import check
+        torch_sync = __import__("torch").cuda.synchronize
+        torch_sync()
+        dist.barrier()
+        L = lib()
+        for q in self.mapped:
+            L.fa_ipc_close(self.eng._h, C.c_void_p(q))
+        self.mapped = []
+        dist.barrier()
+        for bufp, cntp in self.mine:
+            L.fa_device_free(self.eng._h, C.c_void_p(bufp)); L.fa_device_free(self.eng._h, C.c_void_p(cntp))
+        L.fa_device_free(self.eng._h, C.c_void_p(self.overflow))
+        self.local.close()

@@ -31,8 +31,13 @@ def _worker(rank, world, port, q, combine):
     from netobserv_ebpf_agent_b200.sharded import ShardedAggregator, owner_of
     stream = torch.cuda.Stream(device=dev)             # engine, NCCL and copies share one explicit stream
     torch.cuda.set_stream(stream)
-    eng = fa.FlowAggEngine(1 << 18, device=rank, max_batch=30_000, cuda_stream=stream.cuda_stream)
-    agg = ShardedAggregator(eng, 30_000, dev, combine=combine)
+    from netobserv_ebpf_agent_b200.sharded import PeerShardedAggregator
+    if combine == "peer":
+        eng = fa.FlowAggEngine(1 << 18, device=rank, max_batch=100_000, cuda_stream=stream.cuda_stream, flags=fa.FA_F_NO_FULL_CUT)
+        agg = PeerShardedAggregator(eng, 100_000, dev)
+    else:
+        eng = fa.FlowAggEngine(1 << 18, device=rank, max_batch=30_000, cuda_stream=stream.cuda_stream)
+        agg = ShardedAggregator(eng, 30_000, dev, combine=combine)
     keep = []
     for b in range(3):
         local = gen_host(seed=50, n=100_000, n_keys=40_000, dist=1, first=(b * world + rank) * 100_000)
@@ -50,7 +55,7 @@ def _worker(rank, world, port, q, combine):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("combine", [False, True])
+@pytest.mark.parametrize("combine", [False, True, "peer"])
 def test_two_gpu_sharded_parity(combine):
     import torch.multiprocessing as mp
     world = 2
