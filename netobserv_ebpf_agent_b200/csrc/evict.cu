@@ -22,44 +22,62 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
     const uint64_t n_words = slots >> 5;               // slots is a power of two >= 1024
     const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    // The occupancy bitmap (1 bit per slot, set when a flow is created) lets a warp skip 32 empty slots with one
-    // broadcast load: eviction costs ~ (128 + 32 + 144) bytes per LIVE flow, not per slot.
+    // The occupancy bitmap (1 bit per slot, set when a flow is created) lets a warp skip 1024 empty slots with one
+    // coalesced load: eviction costs ~ (128 + 32 + 144) bytes per LIVE flow, not per slot.  One output-cursor
+    // atomic per warp iteration (1024 slots).
     for (uint64_t w0 = warp_global * 32; w0 < n_words; w0 += n_warps * 32) {
-        const uint64_t wi = w0 + lane;                  // 32 consecutive bitmap words per warp iteration (coalesced)
+        const uint64_t wi = w0 + lane;                  // lane l owns bitmap word w0 + l
         uint32_t mybits = wi < n_words ? t.occ[wi] : 0u;
         if (!kDrain && mybits) t.occ[wi] = 0u;
         uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, mybits != 0u);
+        if (nonempty == 0u) continue;
+        if (kDrain) {
+            // which of the live flows received records since the last drain?  One lane per slot of a word:
+            // the 32 hot lines of a word are 1 KB of contiguous memory.
+            uint32_t ne = nonempty, myact = 0;
+            while (ne) {
+                const int src = __ffs(ne) - 1; ne &= ne - 1;
+                const uint32_t bits = __shfl_sync(0xFFFFFFFFu, mybits, src);
+                bool act = false;
+                if ((bits >> lane) & 1u) {
+                    const uint64_t slot = (w0 + src) * 32 + lane;
+                    const uint4 h0 = ld_cg_u4(&t.hot[slot * 2]), h1 = ld_cg_u4(&t.hot[slot * 2 + 1]);
+                    act = (h0.x | h0.y | h0.z | h0.w | h1.x | h1.y | h1.z | h1.w) != 0u;
+                }
+                const uint32_t am = __ballot_sync(0xFFFFFFFFu, act);
+                if (lane == src) myact = am;
+            }
+            mybits = myact;
+            nonempty = __ballot_sync(0xFFFFFFFFu, mybits != 0u);
+            if (nonempty == 0u) continue;
+        }
+        // one reservation for everything this warp iteration emits; exclusive prefix over the lanes' word counts
+        const uint32_t mycnt = __popc(mybits);
+        uint32_t incl = mycnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->evict_out, (unsigned long long)total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        const unsigned long long mybase = base + incl - mycnt;
         while (nonempty) {
             const int src = __ffs(nonempty) - 1; nonempty &= nonempty - 1;
             uint32_t bits = __shfl_sync(0xFFFFFFFFu, mybits, src);
+            const unsigned long long wbase = __shfl_sync(0xFFFFFFFFu, mybase, src);
             const uint64_t word_slot0 = (w0 + src) * 32;
-            unsigned long long base = 0;
-            if (!kDrain) {
-                if (lane == 0) base = atomicAdd(&ctr->evict_out, (unsigned long long)__popc(bits));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            }
             uint32_t done_before = 0;
             while (bits) {                              // up to 4 flows (one per 8-lane group) per round
                 const uint32_t pos = __fns(bits, 0, g + 1);
-                bool live = pos < 32u;
+                const bool live = pos < 32u;
                 const uint64_t slot = word_slot0 + (live ? pos : 0u);
-                unsigned long long idx = base + done_before + g;
+                const unsigned long long idx = wbase + done_before + g;
                 const uint32_t taken = min(4, __popc(bits));
                 for (uint32_t k = 0; k < taken; k++) bits &= bits - 1;
                 done_before += taken;
                 uint4 line = make_uint4(0, 0, 0, 0), hot = make_uint4(0, 0, 0, 0);
-                if (live && j < 2) hot = ld_cg_u4(&t.hot[slot * 2 + j]);
-                if (kDrain) {
-                    // active = any field of the hot line moved since the last drain
-                    const uint32_t act = __ballot_sync(0xFFFFFFFFu, (hot.x | hot.y | hot.z | hot.w) != 0u);
-                    live = live && ((act >> (g * 8)) & 3u) != 0u;
-                    const uint32_t lg = __ballot_sync(0xFFFFFFFFu, live && j == 0);
-                    unsigned long long rb = 0;
-                    if (lane == 0 && lg) rb = atomicAdd(&ctr->evict_out, (unsigned long long)__popc(lg));
-                    rb = __shfl_sync(0xFFFFFFFFu, rb, 0);
-                    idx = rb + __popc(lg & ((1u << (g * 8)) - 1u));
-                }
                 if (live) line = ld_cg_u4(&t.ident[slot * 8 + j]);
+                if (live && j < 2) hot = ld_cg_u4(&t.hot[slot * 2 + j]);
                 // hot chunk 0 = (bytes, nstart), hot chunk 1 = (end, packets, flags)
                 const uint32_t b_lo = __shfl_sync(0xFFFFFFFFu, hot.x, g * 8), b_hi = __shfl_sync(0xFFFFFFFFu, hot.y, g * 8);
                 const uint32_t ns_lo = __shfl_sync(0xFFFFFFFFu, hot.z, g * 8), ns_hi = __shfl_sync(0xFFFFFFFFu, hot.w, g * 8);
