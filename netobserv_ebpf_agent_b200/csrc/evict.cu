@@ -32,20 +32,14 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
         uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, mybits != 0u);
         if (nonempty == 0u) continue;
         if (kDrain) {
-            // which of the live flows received records since the last drain?  One lane per slot of a word:
-            // the 32 hot lines of a word are 1 KB of contiguous memory.
-            uint32_t ne = nonempty, myact = 0;
-            while (ne) {
-                const int src = __ffs(ne) - 1; ne &= ne - 1;
-                const uint32_t bits = __shfl_sync(0xFFFFFFFFu, mybits, src);
-                bool act = false;
-                if ((bits >> lane) & 1u) {
-                    const uint64_t slot = (w0 + src) * 32 + lane;
-                    const uint4 h0 = ld_cg_u4(&t.hot[slot * 2]), h1 = ld_cg_u4(&t.hot[slot * 2 + 1]);
-                    act = (h0.x | h0.y | h0.z | h0.w | h1.x | h1.y | h1.z | h1.w) != 0u;
-                }
-                const uint32_t am = __ballot_sync(0xFFFFFFFFu, act);
-                if (lane == src) myact = am;
+            // which of the live flows received records since the last drain?  Every lane walks the set bits of its
+            // own bitmap word (32 independent chains of 32-byte hot-line reads in flight per warp).
+            uint32_t rest = mybits, myact = 0;
+            while (rest) {
+                const int b = __ffs(rest) - 1; rest &= rest - 1;
+                const uint64_t slot = wi * 32 + b;
+                const uint4 h0 = ld_cg_u4(&t.hot[slot * 2]), h1 = ld_cg_u4(&t.hot[slot * 2 + 1]);
+                if ((h0.x | h0.y | h0.z | h0.w | h1.x | h1.y | h1.z | h1.w) != 0u) myact |= 1u << b;
             }
             mybits = myact;
             nonempty = __ballot_sync(0xFFFFFFFFu, mybits != 0u);
@@ -60,21 +54,25 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&ctr->evict_out, (unsigned long long)total);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        const unsigned long long mybase = base + incl - mycnt;
-        while (nonempty) {
-            const int src = __ffs(nonempty) - 1; nonempty &= nonempty - 1;
-            uint32_t bits = __shfl_sync(0xFFFFFFFFu, mybits, src);
-            const unsigned long long wbase = __shfl_sync(0xFFFFFFFFu, mybase, src);
-            const uint64_t word_slot0 = (w0 + src) * 32;
-            uint32_t done_before = 0;
-            while (bits) {                              // up to 4 flows (one per 8-lane group) per round
-                const uint32_t pos = __fns(bits, 0, g + 1);
-                const bool live = pos < 32u;
-                const uint64_t slot = word_slot0 + (live ? pos : 0u);
-                const unsigned long long idx = wbase + done_before + g;
-                const uint32_t taken = min(4, __popc(bits));
-                for (uint32_t k = 0; k < taken; k++) bits &= bits - 1;
-                done_before += taken;
+        // rounds of 4 flows (one per 8-lane group), taken across all 32 words of the window
+        for (uint32_t f0 = 0; f0 < total; f0 += 4) {
+            {
+                const uint32_t f = f0 + g;                              // this group's flow number in the window
+                const bool live = f < total;
+                // owner word = first lane whose inclusive prefix exceeds f (f differs per group: four ballots)
+                uint32_t src = 0, within = 0;
+                {
+                    const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, incl > f0), m1 = __ballot_sync(0xFFFFFFFFu, incl > f0 + 1),
+                             m2 = __ballot_sync(0xFFFFFFFFu, incl > f0 + 2), m3 = __ballot_sync(0xFFFFFFFFu, incl > f0 + 3);
+                    const uint32_t mm = g == 0 ? m0 : g == 1 ? m1 : g == 2 ? m2 : m3;
+                    src = mm ? (uint32_t)(__ffs(mm) - 1) : 0u;
+                }
+                const uint32_t sbits = __shfl_sync(0xFFFFFFFFu, mybits, src);
+                const uint32_t sincl = __shfl_sync(0xFFFFFFFFu, incl, src), scnt = __shfl_sync(0xFFFFFFFFu, mycnt, src);
+                within = live ? f - (sincl - scnt) : 0u;                // rank of the flow inside its word
+                const uint32_t pos = live ? __fns(sbits, 0, within + 1) : 0u;
+                const uint64_t slot = (w0 + src) * 32 + pos;
+                const unsigned long long idx = base + f;
                 uint4 line = make_uint4(0, 0, 0, 0), hot = make_uint4(0, 0, 0, 0);
                 if (live) line = ld_cg_u4(&t.ident[slot * 8 + j]);
                 if (live && j < 2) hot = ld_cg_u4(&t.hot[slot * 2 + j]);
