@@ -218,7 +218,16 @@ def run_ours(args, wl):
         step(i)
     finish()
     barrier()
-    st0 = eng.stats()
+
+    def all_stats():                                 # owner engine + the combiner's scratch engine(s)
+        s = eng.stats()
+        if world > 1:
+            for loc in ([agg.local] if hasattr(agg, "local") else agg.locals):
+                ls = loc.stats()
+                for k in ("kernel_launches", "order_fixups", "spills"):
+                    s[k] += ls[k]
+        return s
+    st0 = all_stats()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -234,7 +243,7 @@ def run_ours(args, wl):
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    st1 = eng.stats()
+    st1 = all_stats()
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
