@@ -111,10 +111,10 @@ def cpu_baseline_port(wl, sample_records, passes=4):
 
 def run_reference(args, wl):
     """--impl reference: the reference's CPU path for this step (Accounter restatement), all host threads."""
-    import oracle_lib as O
     rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if rank != 0:                                    # under torchrun only rank 0 runs the CPU arm
         return
+    import oracle_lib as O
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     n = args.ref_sample
     sample = host_sample(wl, n)
