@@ -644,7 +644,10 @@ __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint
 
 int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
     if (a.n == 0) return 0;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};                // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& attr_done = attr_done_dev[dev & 63];
     const int smem = (int)sizeof(AggSmem);
     if (!attr_done) {
         cudaFuncSetAttribute(aggregate_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

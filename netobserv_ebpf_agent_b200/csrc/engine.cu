@@ -314,6 +314,7 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
 
     fa_engine* e = new (std::nothrow) fa_engine();
     if (!e) return fail(FA_E_NOMEM, "fa_create: out of memory");
+    struct Guard { fa_engine* e; ~Guard() { if (e) fa_destroy(e); } } guard{e};   // releases everything on any early return
     e->cfg = *cfg;
     e->device = cfg->device;
     e->sm_count = prop.multiProcessorCount;
@@ -374,10 +375,8 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     e->sk.depth = cfg->cms_depth ? cfg->cms_depth : 4;
     e->sk.p = cfg->hll_precision ? cfg->hll_precision : 14;
     e->sk.seed = cfg->sketch_seed;
-    if (e->sk.depth > 8 || e->sk.log2w < 4 || e->sk.log2w > 30 || e->sk.p < 4 || e->sk.p > 18) {
-        fa_destroy(e);
+    if (e->sk.depth > 8 || e->sk.log2w < 4 || e->sk.log2w > 30 || e->sk.p < 4 || e->sk.p > 18)
         return fail(FA_E_INVAL, "fa_create: sketch parameters out of range");
-    }
     if (cfg->flags & FA_F_ENABLE_SKETCH) {
         const size_t cms_bytes = ((size_t)e->sk.depth << e->sk.log2w) * 8;
         CU(cudaMalloc(&e->sk.cms, cms_bytes));
@@ -390,6 +389,7 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
         if (pp[0] == '1') { CU(cudaMalloc(&e->d_prof, 16 * 8)); CU(cudaMemsetAsync(e->d_prof, 0, 128, e->stream)); }
     }
     CU(cudaStreamSynchronize(e->stream));
+    guard.e = nullptr;
     *out = e;
     return FA_OK;
 }
