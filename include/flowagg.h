@@ -171,6 +171,10 @@ typedef struct fa_config {
 #define FA_F_ENABLE_SKETCH  0x4u  /* fused count-min + HyperLogLog update in fa_ingest */
 #define FA_F_NO_FULL_CUT    0x8u  /* never return FA_FULL: max_entries only sizes the table (KERNEL_MAP-style caches,
                                      multi-GPU scratch / owner tables); a physically full table spills (fa_stats.spills) */
+#define FA_F_RINGBUF_FALLBACK 0x10u /* KERNEL_MAP mode: ENABLE_FLOWS_RINGBUF_FALLBACK (config.go:286-288): packets whose flow
+                                     cannot be created because the map is full are kept as single-packet records
+                                     (errno = E2BIG, bpf/flows.c:262-279) and read back with fa_read_spilled(); without
+                                     it they only increment hashmap_fail_create (flows.c:285) */
 
 typedef struct fa_stats {
     uint64_t records_ingested;    /* flow records consumed by fa_ingest          */
@@ -185,8 +189,10 @@ typedef struct fa_stats {
     uint64_t kernel_launches;     /* CUDA kernels launched by the engine          */
     uint64_t h2d_bytes;           /* bytes copied host->device by fa_ingest*      */
     uint64_t d2h_bytes;           /* bytes copied device->host by fa_evict etc.   */
-    uint64_t observed_intf_missed;/* KERNEL_MAP mode: OBSERVED_INTF_MISSED counter */
-    uint64_t reserved[3];
+    uint64_t observed_intf_missed;/* KERNEL_MAP mode: OBSERVED_INTF_MISSED counter (flows.c:134-142) */
+    uint64_t hashmap_fail_create; /* KERNEL_MAP mode: HASHMAP_FAIL_CREATE_FLOW (flows.c:285)               */
+    uint64_t ringbuf_spilled;     /* KERNEL_MAP mode: single-packet records handed to the fallback ring     */
+    uint64_t ringbuf_dropped;     /* ... that found the ring full ("couldn't reserve space", flows.c:270)   */
 } fa_stats;
 
 typedef struct fa_engine fa_engine;
@@ -238,6 +244,12 @@ int fa_drain_active(fa_engine* e, void* out_records_dev, size_t cap, size_t* n_o
 
 /* Number of live flows right now (len(c.entries), account.go:98). */
 int fa_live_flows(fa_engine* e, size_t* n);
+
+/* KERNEL_MAP mode with FA_F_RINGBUF_FALLBACK.  Replaces: FlowFetcher.ReadRingBuf on `direct_flows`
+ * (pkg/tracer/tracer.go:1052-1054; bpf/flows.c:262-279), batched: copies out and removes the single-packet
+ * records spilled since the last call (at most 131072 are kept = the reference's 16 MiB ring,
+ * bpf/maps_definition.h:7-11; later ones are dropped and counted).  out: host or device, cap records. */
+int fa_read_spilled(fa_engine* e, void* out_records, size_t cap, size_t* n_out);
 
 /* Replaces: FlowFetcher.DeleteMapsStaleEntries (pkg/tracer/tracer.go:1229-1257). */
 int fa_purge_stale_dns(fa_engine* e, uint64_t mono_now_ns, uint64_t timeout_ns);

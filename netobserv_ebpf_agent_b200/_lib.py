@@ -8,7 +8,7 @@ REC_BYTES, ID_BYTES, DNS_BYTES, ADD_BYTES, DNSREC_BYTES, ADDREC_BYTES = 144, 40,
 FA_OK, FA_FULL = 0, 1
 FA_E_INVAL, FA_E_NOMEM, FA_E_CUDA, FA_E_NODEV, FA_E_2BIG, FA_E_CLOSED = -22, -12, -5, -19, -7, -9
 FA_MODE_ACCOUNTER, FA_MODE_KERNEL_MAP = 0, 1
-FA_F_ENABLE_RTT, FA_F_ENABLE_DNS, FA_F_ENABLE_SKETCH, FA_F_NO_FULL_CUT = 1, 2, 4, 8
+FA_F_ENABLE_RTT, FA_F_ENABLE_DNS, FA_F_ENABLE_SKETCH, FA_F_NO_FULL_CUT, FA_F_RINGBUF_FALLBACK = 1, 2, 4, 8, 16
 FA_GEN_UNIFORM, FA_GEN_ZIPF = 0, 1
 FA_ABI_VERSION = 1
 
@@ -30,7 +30,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "records_ingested", "dns_ingested", "additional_ingested", "flows_evicted", "evictions", "live_flows",
         "spills", "order_fixups", "full_cuts", "kernel_launches", "h2d_bytes", "d2h_bytes",
-        "observed_intf_missed")] + [("reserved", C.c_uint64 * 3)]
+        "observed_intf_missed", "hashmap_fail_create", "ringbuf_spilled", "ringbuf_dropped")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
@@ -61,6 +61,7 @@ SIGNATURES = {
     "fa_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "fa_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fa_live_flows": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "fa_read_spilled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_purge_stale_dns": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "fa_cms_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "fa_hll_estimate": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

@@ -17,6 +17,7 @@
 #include "../../include/flowagg.h"
 #include "flowgen.h"
 #include "kernels.cuh"
+#include "kmap_body.cuh"
 
 static_assert(sizeof(fa_flow_id) == 40, "flow_id ABI");
 static_assert(sizeof(fa_flow_metrics) == 104, "flow_metrics ABI");
@@ -147,8 +148,24 @@ struct fa_engine {
     uint32_t ring_n[kLiveRing] = {};
     uint32_t ring_head = 0, ring_tail = 0;       // monotonically increasing; slot = idx % kLiveRing
 
+    // KERNEL_MAP mode (kmap.cu): metrics lines, per-batch scratch, fallback ring
+    uint8_t* km_met = nullptr;
+    uint32_t* km_slot_of = nullptr;
+    fa::KmBEntry* km_bset = nullptr; uint32_t km_bset_slots = 0;
+    uint32_t* km_blist = nullptr;
+    uint8_t* km_spill = nullptr; uint64_t km_spill_cap = 0;
+    fa::KmCounters* d_km_ctr = nullptr;
+    fa::KmCounters* h_km_ctr = nullptr;       // pinned mirror
+    uint64_t km_spilled_total = 0;            // records read back by fa_read_spilled so far
+
     fa_stats st{};
 };
+
+namespace fa {
+int launch_kmap_batch(KmParams P, uint32_t cut, int sm_count, cudaStream_t st);
+int launch_kmap_evict(const Table& t, uint8_t* met, uint8_t* out, unsigned long long cap, unsigned long long* cursor,
+                      int sm_count, cudaStream_t st);
+}
 
 namespace {
 
@@ -172,6 +189,22 @@ void retire_completed(fa_engine* e) {
     }
 }
 
+// Book-keeping after the launches of one chunk: asynchronous read-back of the live-flow count.
+int note_launch(fa_engine* e, uint32_t n) {
+    e->unsynced_records += n;
+    e->st.records_ingested += n;
+    if (e->ring_tail - e->ring_head == fa_engine::kLiveRing) {
+        CU(cudaEventSynchronize(e->ev_live[e->ring_head % fa_engine::kLiveRing]));
+        retire_completed(e);
+    }
+    const uint32_t s = e->ring_tail % fa_engine::kLiveRing;
+    CU(cudaMemcpyAsync(&e->h_live_ring[s], &e->d_ctr->live, 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaEventRecord(e->ev_live[s], e->stream));
+    e->ring_n[s] = n;
+    e->ring_tail++;
+    return FA_OK;
+}
+
 // Launch K1 on a device-resident chunk (n <= max_batch).
 int launch_chunk(fa_engine* e, const uint8_t* d_recs, uint32_t n) {
     fa::AggLaunch a{};
@@ -189,19 +222,7 @@ int launch_chunk(fa_engine* e, const uint8_t* d_recs, uint32_t n) {
     a.opt = e->k1_opt;
     e->st.kernel_launches += fa::launch_aggregate(a, e->stream);
     CU(cudaGetLastError());
-    e->unsynced_records += n;
-    e->st.records_ingested += n;
-    // asynchronous read-back of the live-flow count after this launch
-    if (e->ring_tail - e->ring_head == fa_engine::kLiveRing) {
-        CU(cudaEventSynchronize(e->ev_live[e->ring_head % fa_engine::kLiveRing]));
-        retire_completed(e);
-    }
-    const uint32_t s = e->ring_tail % fa_engine::kLiveRing;
-    CU(cudaMemcpyAsync(&e->h_live_ring[s], &e->d_ctr->live, 8, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaEventRecord(e->ev_live[s], e->stream));
-    e->ring_n[s] = n;
-    e->ring_tail++;
-    return FA_OK;
+    return note_launch(e, n);
 }
 
 // ACCOUNTER mode: fold a device-resident chunk honouring max_entries.
@@ -245,12 +266,55 @@ int ingest_chunk_accounter(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint
     return FA_OK;
 }
 
+// KERNEL_MAP mode: the map update of flow_monitor (bpf/flows.c:222-288) for a device-resident chunk.  The map
+// never "fills and flushes": once max_entries flows are live, packets of unknown flows go to the fallback ring
+// (or only count), so the whole chunk is always consumed.
+int ingest_chunk_kmap(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint32_t* consumed) {
+    *consumed = 0;
+    const uint64_t M = e->cfg.max_entries;
+    retire_completed(e);
+    if (e->live_known + e->unsynced_records + n > M) {
+        int rc = sync_counters(e);                     // exact live count
+        if (rc) return rc;
+    }
+    uint32_t cut = n;                                  // records [cut, n) find the map full
+    if (e->live_known + e->unsynced_records + n > M) {
+        e->st.kernel_launches += fa::launch_full_cut(reinterpret_cast<const uint4*>(d_recs), n, e->table, e->live_known, M,
+                                                     e->d_cut_set, e->cut_set_slots, e->d_cut_bitmap, e->d_cut_out,
+                                                     e->sm_count, e->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(e->h_cut_out, e->d_cut_out, 4, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        cut = *e->h_cut_out;
+        if (cut < n) e->st.full_cuts++;
+    }
+    fa::KmParams P{};
+    P.recs = d_recs; P.n = n;
+    P.ringbuf = (e->cfg.flags & FA_F_RINGBUF_FALLBACK) ? 1 : 0;
+    P.t = e->table; P.met = e->km_met;
+    P.epoch = ++e->epoch;
+    P.slot_of = e->km_slot_of;
+    P.live = &e->d_ctr->live;
+    P.c = e->d_km_ctr;
+    P.spill = e->km_spill; P.spill_cap = e->km_spill_cap;
+    P.bset = e->km_bset; P.bset_mask = e->km_bset_slots - 1; P.blist = e->km_blist;
+    e->st.kernel_launches += fa::launch_kmap_batch(P, cut, e->sm_count, e->stream);
+    CU(cudaGetLastError());
+    *consumed = n;
+    return note_launch(e, n);
+}
+
+int ingest_chunk(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint32_t* consumed) {
+    return e->cfg.mode == FA_MODE_KERNEL_MAP ? ingest_chunk_kmap(e, d_recs, n, consumed)
+                                             : ingest_chunk_accounter(e, d_recs, n, consumed);
+}
+
 int ingest_device(fa_engine* e, const uint8_t* d_recs, size_t n, size_t* consumed) {
     size_t done = 0;
     while (done < n) {
         const uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
         uint32_t took = 0;
-        int rc = ingest_chunk_accounter(e, d_recs + done * fa::kRecBytes, c, &took);
+        int rc = ingest_chunk(e, d_recs + done * fa::kRecBytes, c, &took);
         done += took;
         if (rc != FA_OK) { if (consumed) *consumed = done; return rc; }
     }
@@ -273,7 +337,7 @@ int ingest_host(fa_engine* e, const uint8_t* h_recs, size_t n, size_t* consumed,
         CU(cudaStreamWaitEvent(e->stream, e->ev_copied[sidx], 0));
         e->st.h2d_bytes += bytes;
         uint32_t took = 0;
-        rc = ingest_chunk_accounter(e, e->d_stage[sidx], c, &took);
+        rc = ingest_chunk(e, e->d_stage[sidx], c, &took);
         CU(cudaEventRecord(e->ev_stage_free[sidx], e->stream));
         done += took;
         if (rc != FA_OK) break;
@@ -300,7 +364,20 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     if (!cfg || !out) return fail(FA_E_INVAL, "fa_create: null argument");
     if (cfg->abi_version != FA_ABI_VERSION) return fail(FA_E_INVAL, "fa_create: abi_version %u != %u", cfg->abi_version, FA_ABI_VERSION);
     if (cfg->max_entries == 0) return fail(FA_E_INVAL, "fa_create: max_entries must be >= 1");
-    if (cfg->mode != FA_MODE_ACCOUNTER) return fail(FA_E_INVAL, "fa_create: mode %u not available in this build", cfg->mode);
+    if (cfg->mode != FA_MODE_ACCOUNTER && cfg->mode != FA_MODE_KERNEL_MAP) return fail(FA_E_INVAL, "fa_create: unknown mode %u", cfg->mode);
+    const bool kmap = cfg->mode == FA_MODE_KERNEL_MAP;
+    if (kmap) {
+        // The KERNEL_MAP kernels are checked against the oracle through their host emulation only
+        // (tests/test_kmap_emulation.py); until they have passed tests/test_gpu_kernel_map.py on a B200 the mode
+        // has to be asked for explicitly.  There is no fallback to ACCOUNTER semantics.
+        const char* ex = getenv("FA_EXPERIMENTAL_KERNEL_MAP");
+        if (!ex || ex[0] != '1')
+            return fail(FA_E_INVAL, "fa_create: mode KERNEL_MAP is experimental in this build (set FA_EXPERIMENTAL_KERNEL_MAP=1)");
+        if (cfg->flags & (FA_F_ENABLE_RTT | FA_F_ENABLE_DNS | FA_F_ENABLE_SKETCH | FA_F_NO_FULL_CUT))
+            return fail(FA_E_INVAL, "fa_create: mode KERNEL_MAP supports only FA_F_RINGBUF_FALLBACK (flags 0x%x)", cfg->flags);
+    } else if (cfg->flags & FA_F_RINGBUF_FALLBACK) {
+        return fail(FA_E_INVAL, "fa_create: FA_F_RINGBUF_FALLBACK needs mode KERNEL_MAP");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -330,9 +407,29 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     e->slots = slots;
     e->table.mask = slots - 1;
     CU(cudaMalloc(&e->table.ident, slots * fa::kIdentBytes));
-    CU(cudaMalloc(&e->table.hot, slots * fa::kHotBytes));
     CU(cudaMemsetAsync(e->table.ident, 0, slots * fa::kIdentBytes, e->stream));
-    CU(cudaMemsetAsync(e->table.hot, 0, slots * fa::kHotBytes, e->stream));
+    if (!kmap) {
+        CU(cudaMalloc(&e->table.hot, slots * fa::kHotBytes));
+        CU(cudaMemsetAsync(e->table.hot, 0, slots * fa::kHotBytes, e->stream));
+    } else {
+        if (slots > (1ull << 31)) return fail(FA_E_INVAL, "fa_create: KERNEL_MAP mode supports at most 2^31 slots");
+        CU(cudaMalloc(&e->km_met, slots * fa::kMetLineBytes));
+        CU(cudaMemsetAsync(e->km_met, 0, slots * fa::kMetLineBytes, e->stream));
+        CU(cudaMalloc(&e->km_slot_of, e->max_batch * 4));
+        uint32_t bs = 1024; while ((uint64_t)bs < 2 * e->max_batch) bs <<= 1;
+        e->km_bset_slots = bs;
+        CU(cudaMalloc(&e->km_bset, (size_t)bs * sizeof(fa::KmBEntry)));
+        CU(cudaMemsetAsync(e->km_bset, 0, (size_t)bs * sizeof(fa::KmBEntry), e->stream));
+        CU(cudaMalloc(&e->km_blist, e->max_batch * 4));
+        if (cfg->flags & FA_F_RINGBUF_FALLBACK) {
+            e->km_spill_cap = 131072;                   // >= the 16 MiB direct_flows ring (bpf/maps_definition.h:7-11)
+            CU(cudaMalloc(&e->km_spill, e->km_spill_cap * fa::kRecBytes));
+        }
+        CU(cudaMalloc(&e->d_km_ctr, sizeof(fa::KmCounters)));
+        CU(cudaMemsetAsync(e->d_km_ctr, 0, sizeof(fa::KmCounters), e->stream));
+        CU(cudaHostAlloc(&e->h_km_ctr, sizeof(fa::KmCounters), cudaHostAllocDefault));
+        memset(e->h_km_ctr, 0, sizeof(fa::KmCounters));
+    }
     CU(cudaMalloc(&e->table.occ, slots / 8));
     CU(cudaMemsetAsync(e->table.occ, 0, slots / 8, e->stream));
     if (cfg->flags & FA_F_ENABLE_RTT) {
@@ -430,6 +527,8 @@ void fa_destroy(fa_engine* e) {
     cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts);
     cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out); cudaFree(e->d_slot_of);
     cudaFree(e->sk.cms); cudaFree(e->sk.hll);
+    cudaFree(e->km_met); cudaFree(e->km_slot_of); cudaFree(e->km_bset); cudaFree(e->km_blist); cudaFree(e->km_spill);
+    cudaFree(e->d_km_ctr); if (e->h_km_ctr) cudaFreeHost(e->h_km_ctr);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -520,6 +619,38 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
     if (live == 0) return FA_OK;
     if (!out_records) return fail(FA_E_INVAL, "fa_evict: null out_records");
     if (cap < live) return fail(FA_E_2BIG, "fa_evict: capacity %zu < %llu live flows", cap, (unsigned long long)live);
+    if (e->cfg.mode == FA_MODE_KERNEL_MAP) {
+        const bool dev_out = classify(out_records) == PTR_DEVICE;
+        uint8_t* d_out = static_cast<uint8_t*>(out_records);
+        if (!dev_out) {
+            if (e->evict_cap < live) {
+                cudaFree(e->d_evict); e->d_evict = nullptr; e->evict_cap = 0;
+                uint64_t want = std::max<uint64_t>(live, std::min<uint64_t>(e->cfg.max_entries, live * 2));
+                CU(cudaMalloc(&e->d_evict, want * fa::kRecBytes));
+                e->evict_cap = want;
+            }
+            d_out = e->d_evict;
+        }
+        CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
+        e->st.kernel_launches += fa::launch_kmap_evict(e->table, e->km_met, d_out, live, &e->d_ctr->evict_out, e->sm_count, e->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(&e->d_ctr->live, 0, sizeof(unsigned long long), e->stream));
+        if (!dev_out) {
+            CU(cudaMemcpyAsync(out_records, d_out, live * fa::kRecBytes, cudaMemcpyDeviceToHost, e->stream));
+            e->st.d2h_bytes += live * fa::kRecBytes;
+        }
+        CU(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(fa::Counters), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if (e->h_ctr->evict_out != live)
+            return fail(FA_E_CUDA, "fa_evict: table scan found %llu flows, counter says %llu", (unsigned long long)e->h_ctr->evict_out, (unsigned long long)live);
+        if (out_present && classify(out_present) != PTR_DEVICE) memset(out_present, 0, live);
+        if (out_dns && classify(out_dns) != PTR_DEVICE) memset(out_dns, 0, live * 64);
+        if (out_additional && classify(out_additional) != PTR_DEVICE) memset(out_additional, 0, live * 32);
+        e->live_known = 0; e->unsynced_records = 0; e->ring_head = e->ring_tail;
+        e->st.flows_evicted += live;
+        *n_out = (size_t)live;
+        return FA_OK;
+    }
     const bool feats = e->table.feat_add || e->table.feat_dns;
     const PtrKind k = classify(out_records);
     uint8_t* d_out = nullptr;
@@ -586,6 +717,7 @@ int fa_drain_active(fa_engine* e, void* out_records_dev, size_t cap, size_t* n_o
     if (!e || !n_out || !out_records_dev) return fail(FA_E_INVAL, "fa_drain_active: null argument");
     if (classify(out_records_dev) != PTR_DEVICE) return fail(FA_E_INVAL, "fa_drain_active: out_records must be device memory");
     if (e->table.feat_add || e->table.feat_dns) return fail(FA_E_INVAL, "fa_drain_active: not available with feature folds enabled");
+    if (e->cfg.mode != FA_MODE_ACCOUNTER) return fail(FA_E_INVAL, "fa_drain_active: ACCOUNTER mode only");
     std::lock_guard<std::mutex> lk(e->mu);
     CU(cudaSetDevice(e->device));
     CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
@@ -604,6 +736,7 @@ int fa_drain_active(fa_engine* e, void* out_records_dev, size_t cap, size_t* n_o
 int fa_drain_active_counted(fa_engine* e, void* out_records_dev, size_t cap, uint64_t* n_dev_out) {
     if (!e || !out_records_dev || !n_dev_out) return fail(FA_E_INVAL, "fa_drain_active_counted: null argument");
     if (e->table.feat_add || e->table.feat_dns) return fail(FA_E_INVAL, "fa_drain_active_counted: not available with feature folds enabled");
+    if (e->cfg.mode != FA_MODE_ACCOUNTER) return fail(FA_E_INVAL, "fa_drain_active_counted: ACCOUNTER mode only");
     std::lock_guard<std::mutex> lk(e->mu);
     CU(cudaSetDevice(e->device));
     CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
@@ -635,6 +768,7 @@ int fa_route_peer(fa_engine* e, const void* recs, const uint64_t* n_dev, size_t 
 int fa_ingest_counted(fa_engine* e, const void* recs, uint64_t* n_dev, size_t max_n, int reset_count) {
     if (!e || !recs || !n_dev) return fail(FA_E_INVAL, "fa_ingest_counted: null argument");
     if (!(e->cfg.flags & FA_F_NO_FULL_CUT)) return fail(FA_E_INVAL, "fa_ingest_counted: engine needs FA_F_NO_FULL_CUT");
+    if (e->cfg.mode != FA_MODE_ACCOUNTER) return fail(FA_E_INVAL, "fa_ingest_counted: ACCOUNTER mode only");
     if (max_n == 0 || max_n > e->max_batch) return fail(FA_E_INVAL, "fa_ingest_counted: max_n must be 1..max_batch");
     if (reinterpret_cast<uintptr_t>(recs) & 15) return fail(FA_E_INVAL, "fa_ingest_counted: records must be 16-byte aligned");
     std::lock_guard<std::mutex> lk(e->mu);
@@ -752,7 +886,38 @@ int fa_get_stats(fa_engine* e, fa_stats* out) {
     e->st.live_flows = e->h_ctr->live;
     e->st.spills = e->h_ctr->spills;
     e->st.order_fixups = e->h_ctr->fixups_total;
+    if (e->d_km_ctr) {
+        CU(cudaMemcpyAsync(e->h_km_ctr, e->d_km_ctr, sizeof(fa::KmCounters), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        e->st.observed_intf_missed = e->h_km_ctr->intf_missed;
+        e->st.hashmap_fail_create = e->h_km_ctr->fail_create;
+        e->st.ringbuf_dropped = e->h_km_ctr->spill_dropped;
+        e->st.ringbuf_spilled = e->km_spilled_total + std::min<uint64_t>(e->h_km_ctr->spill_cursor, e->km_spill_cap);
+        e->st.spills = e->h_km_ctr->table_full;
+    }
     *out = e->st;
+    return FA_OK;
+}
+
+int fa_read_spilled(fa_engine* e, void* out_records, size_t cap, size_t* n_out) {
+    if (n_out) *n_out = 0;
+    if (!e || !n_out) return fail(FA_E_INVAL, "fa_read_spilled: null argument");
+    if (e->cfg.mode != FA_MODE_KERNEL_MAP || !(e->cfg.flags & FA_F_RINGBUF_FALLBACK))
+        return fail(FA_E_INVAL, "fa_read_spilled: needs mode KERNEL_MAP with FA_F_RINGBUF_FALLBACK");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(e->h_km_ctr, e->d_km_ctr, sizeof(fa::KmCounters), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    const uint64_t n = std::min<uint64_t>(e->h_km_ctr->spill_cursor, e->km_spill_cap);
+    if (n == 0) return FA_OK;
+    if (!out_records) return fail(FA_E_INVAL, "fa_read_spilled: null out_records");
+    if (cap < n) return fail(FA_E_2BIG, "fa_read_spilled: capacity %zu < %llu spilled records", cap, (unsigned long long)n);
+    CU(cudaMemcpyAsync(out_records, e->km_spill, n * fa::kRecBytes, cudaMemcpyDefault, e->stream));
+    CU(cudaMemsetAsync(&e->d_km_ctr->spill_cursor, 0, sizeof(unsigned long long), e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (classify(out_records) != PTR_DEVICE) e->st.d2h_bytes += n * fa::kRecBytes;
+    e->km_spilled_total += n;
+    *n_out = (size_t)n;
     return FA_OK;
 }
 

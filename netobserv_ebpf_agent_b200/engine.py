@@ -94,6 +94,14 @@ class FlowAggEngine:
         check(lib().fa_evict(self._h, _ptr(out), None, None, None, cap, C.byref(got)))
         return out[: got.value]
 
+    def read_spilled(self, cap=131072):
+        """KERNEL_MAP mode with FA_F_RINGBUF_FALLBACK: the single-packet records that could not enter the full map
+        (the batched equivalent of reading the direct_flows ring buffer) -> (n,144) uint8 array."""
+        out = np.zeros((max(cap, 1), REC_BYTES), dtype=np.uint8)
+        got = C.c_size_t(0)
+        check(lib().fa_read_spilled(self._h, _ptr(out), cap, C.byref(got)))
+        return out[: got.value]
+
     def evict_into(self, out, cap):
         """Evict into a caller buffer (host or device address / tensor). Returns flow count."""
         got = C.c_size_t(0)

@@ -78,6 +78,30 @@ def feature_bench(n_keys=1_000_000, B=1 << 22, steps=8):
     eng.close()
 
 
+def kmap_bench(n_keys=1_000_000, B=1 << 24, steps=12):
+    """KERNEL_MAP mode (kmap.cu: 7 passes per batch) on the headline workload's stream; needs FA_EXPERIMENTAL_KERNEL_MAP=1."""
+    eng = fa.FlowAggEngine(1 << 24, mode=fa.FA_MODE_KERNEL_MAP, max_batch=B, cuda_stream=stream.cuda_stream)
+    gp = fa.GenParams(seed=2, n_keys=n_keys, dist=1, zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0)
+    ring = []
+    for i in range(4):
+        t = torch.empty(B * REC, dtype=torch.uint8, device=dev)
+        eng.gen_records(gp, i * B, B, t)
+        ring.append(t)
+    eng.sync()
+    for i in range(2):
+        eng.ingest(ring[i % 4].data_ptr(), B)
+    dt = timed(lambda i: eng.ingest(ring[i % 4].data_ptr(), B), steps)
+    st = eng.stats()
+    print(json.dumps({"bench": "KERNEL_MAP mode map update", "workload": f"{n_keys} Zipf-1.1 keys, batch {B}",
+                      "Mpkts_s": B * steps / dt / 1e6, "flows": eng.live_flows(), "kernel_launches": st["kernel_launches"]}), flush=True)
+    eng.close()
+
+
 if __name__ == "__main__":
-    sketch_bench()
-    feature_bench()
+    which = sys.argv[1:] or ["sketch", "features"] + (["kmap"] if os.environ.get("FA_EXPERIMENTAL_KERNEL_MAP") == "1" else [])
+    if "sketch" in which:
+        sketch_bench()
+    if "features" in which:
+        feature_bench()
+    if "kmap" in which:
+        kmap_bench()
