@@ -818,14 +818,15 @@ int fa_cms_query(fa_engine* e, const void* keys, size_t n, uint64_t* est) {
     if (n == 0) return FA_OK;
     std::lock_guard<std::mutex> lk(e->mu);
     CU(cudaSetDevice(e->device));
-    uint8_t* d_keys = nullptr; unsigned long long* d_est = nullptr;
-    CU(cudaMalloc(&d_keys, n * 40 + 16));
-    CU(cudaMalloc(&d_est, n * 8));
+    struct DevBuf { void* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } } keys_buf, est_buf;   // freed on every return path
+    CU(cudaMalloc(&keys_buf.p, n * 40 + 16));
+    CU(cudaMalloc(&est_buf.p, n * 8));
+    uint8_t* d_keys = static_cast<uint8_t*>(keys_buf.p);
+    unsigned long long* d_est = static_cast<unsigned long long*>(est_buf.p);
     CU(cudaMemcpyAsync(d_keys, keys, n * 40, cudaMemcpyDefault, e->stream));
     e->st.kernel_launches += fa::launch_cms_query(e->sk, reinterpret_cast<const uint4*>(d_keys), (uint32_t)n, d_est, e->stream);
     CU(cudaMemcpyAsync(est, d_est, n * 8, cudaMemcpyDefault, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    cudaFree(d_keys); cudaFree(d_est);
     return FA_OK;
 }
 
