@@ -193,7 +193,11 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
 // kProf: per-warp cycle counters per phase (FA_PHASE_PROFILE=1), summed into prof[0..7].
 #define FA_PROF_MARK(i) do { if (kProf) { const long long now_ = clock64(); pacc[i] += now_ - pt; pt = now_; } } while (0)
 
-template <bool kSketch, bool kProf, bool kDevN>
+// kVar: experiment variants, separate instantiations so that the default kernel's code is untouched (FA_K1_OPT bits
+// 5, 6 and 7 select them at launch): 1 = ask L2 for the team's next tile while the current one is processed,
+// 2 = branch-free record compares in the fold phase (OR-accumulated differences instead of short-circuit tests),
+// 4 = 4 lanes per flow in the pipelined probe passes.
+template <bool kSketch, bool kProf, bool kDevN, int kVar = 0>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
                  uint32_t* __restrict__ spill_idx, SketchParams sk, unsigned long long* prof, uint32_t opt) {
@@ -241,6 +245,13 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         const uint32_t cnt = min((uint32_t)kTile, n - first);
         mbar_wait(&s.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
+        if ((kVar & 1) && tid == 0) {
+            const uint32_t nt = tile_idx + tile_stride;
+            if (nt < n_tiles) {
+                const uint32_t nfirst = nt * kTile;
+                tma_prefetch_l2(recs + (size_t)nfirst * kRecChunks, min((uint32_t)kTile, n - nfirst) * kRecBytes);
+            }
+        }
 
         // ------------------------------------------------------ E: hash, cache / elect, fold duplicates
         {
@@ -256,10 +267,19 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 HotEntry& ce = cs.hot[((uint32_t)h >> 26) & (kHotEntries - 1)];
                 if (use_cache && *reinterpret_cast<volatile uint32_t*>(&ce.state) == 2u && ce.hash == (uint32_t)h) {
                     const uint4 r3 = R[3], r4 = R[4];
-                    bool same = eq4_masked(ce.line[0], r0, chunk_mask(0)) && eq4_masked(ce.line[1], r1, chunk_mask(1)) &&
-                                eq4_masked(ce.line[2], r2, chunk_mask(2)) && eq4_masked(ce.line[3], r4, chunk_mask(3));
+                    bool same;
+                    if (kVar & 2) {
+                        uint32_t d = diff4_masked(ce.line[0], r0, chunk_mask(0)) | diff4_masked(ce.line[1], r1, chunk_mask(1)) |
+                                     diff4_masked(ce.line[2], r2, chunk_mask(2)) | diff4_masked(ce.line[3], r4, chunk_mask(3));
 #pragma unroll
-                    for (int c = 5; c < 9; c++) same = same && eq4_masked(ce.line[c - 1], R[c], chunk_mask(c - 1));
+                        for (int c = 5; c < 9; c++) d |= diff4_masked(ce.line[c - 1], R[c], chunk_mask(c - 1));
+                        same = d == 0u;
+                    } else {
+                        same = eq4_masked(ce.line[0], r0, chunk_mask(0)) && eq4_masked(ce.line[1], r1, chunk_mask(1)) &&
+                               eq4_masked(ce.line[2], r2, chunk_mask(2)) && eq4_masked(ce.line[3], r4, chunk_mask(3));
+#pragma unroll
+                        for (int c = 5; c < 9; c++) same = same && eq4_masked(ce.line[c - 1], R[c], chunk_mask(c - 1));
+                    }
                     const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
                     const uint64_t v_ns = 0ull - v_start;
                     same = same && (v_start == 0 || (uint32_t)(v_ns >> 32) == ce.ns_hi) &&
@@ -286,8 +306,12 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         if (old == kRepEmpty) break;
                         const uint4* O = T + old * kRecChunks;
                         const uint4 o2 = O[2];
-                        if (eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
-                            eq4_masked(O[1], r1, chunk_mask(1))) {
+                        const bool key_eq = (kVar & 2)
+                            ? (diff4_masked(o2, r2, chunk_mask(2)) | diff4_masked(O[0], r0, chunk_mask(0)) |
+                               diff4_masked(O[1], r1, chunk_mask(1))) == 0u
+                            : (eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
+                               eq4_masked(O[1], r1, chunk_mask(1)));
+                        if (key_eq) {
                             // Same key.  Fold into that representative with 32-bit shared atomics when the high
                             // words of the timestamps agree (the common case); otherwise go to the table on our own.
                             const uint4 r3 = R[3], r4 = R[4], o3 = O[3];
@@ -310,9 +334,17 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                                 if (v_end) atomicMax(&A[5], (uint32_t)v_end);
                                 atomicAdd(&A[6], 1u);                // duplicates seen: cache candidacy
                                 // exact descriptor compare against the representative (74 bytes, padding masked)
-                                bool same = eq4_masked(O[4], r4, chunk_mask(3));
+                                bool same;
+                                if (kVar & 2) {
+                                    uint32_t d = diff4_masked(O[4], r4, chunk_mask(3));
 #pragma unroll
-                                for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
+                                    for (int c = 5; c < 9; c++) d |= diff4_masked(O[c], R[c], chunk_mask(c - 1));
+                                    same = d == 0u;
+                                } else {
+                                    same = eq4_masked(O[4], r4, chunk_mask(3));
+#pragma unroll
+                                    for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
+                                }
                                 if (!same) s.tdirty[old] = 1;
                             }
                             break;
@@ -347,14 +379,84 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             uint32_t ridx[kInflight];
             uint32_t slot[kInflight];
             uint32_t pend = 0;                                     // rounds of this lane group still to be probed
+            if (!(kVar & 4)) {
 #pragma unroll
-            for (int r = 0; r < kInflight; r++) {
-                const uint32_t k = c0 + r * 4 + g;
-                ridx[r] = 0;
-                if (k < c_end) { pend |= 1u << r; ridx[r] = s.glist[k]; }
-                slot[r] = s.hs[ridx[r]] & tmask;
+                for (int r = 0; r < kInflight; r++) {
+                    const uint32_t k = c0 + r * 4 + g;
+                    ridx[r] = 0;
+                    if (k < c_end) { pend |= 1u << r; ridx[r] = s.glist[k]; }
+                    slot[r] = s.hs[ridx[r]] & tmask;
+                }
             }
             uint32_t nslow = 0;
+            if (kVar & 4) {
+                // Variant: 4 lanes per flow, each lane owns line chunks j4 and j4 + 4.  Same 16 lines in flight per
+                // warp, but one round now serves 8 flows, so the per-round bookkeeping (ballots, result stores,
+                // slow-list compaction) is issued half as often.  Costs one more L1 wavefront per line.
+                const int g4 = lane >> 2, j4 = lane & 3;
+                const uint4 cmaskA = chunk_mask(j4), cmaskB = chunk_mask(j4 + 4);
+                const int rcA = rec_chunk_of_line_chunk(j4), rcB = j4 + 5;
+                constexpr int kRounds = 2;
+                uint32_t ridx4[kRounds], slot4[kRounds];
+                uint32_t pend4 = 0;
+#pragma unroll
+                for (int r = 0; r < kRounds; r++) {
+                    const uint32_t k = c0 + r * 8 + g4;
+                    ridx4[r] = 0;
+                    if (k < c_end) { pend4 |= 1u << r; ridx4[r] = s.glist[k]; }
+                    slot4[r] = s.hs[ridx4[r]] & tmask;
+                }
+#pragma unroll 1
+                for (int pass = 0; pass < 2; pass++) {
+                    uint4 lineA[kRounds], lineB[kRounds];
+#pragma unroll
+                    for (int r = 0; r < kRounds; r++) {
+                        lineA[r] = make_uint4(0, 0, 0, 0); lineB[r] = make_uint4(0, 0, 0, 0);
+                        if ((pend4 >> r) & 1u) {
+                            lineA[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4]);
+                            lineB[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4 + 4]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < kRounds; r++) {
+                        const bool act = (pend4 >> r) & 1u;
+                        const uint4* RR = T + ridx4[r] * kRecChunks;
+                        bool eqA = eq4_masked(lineA[r], RR[rcA], cmaskA);
+                        const bool eqB = eq4_masked(lineB[r], RR[rcB], cmaskB);
+                        const uint64_t tag = u64_of(lineA[r].z, lineA[r].w);   // meaningful in lane j4 == 2 only
+                        bool settled = false;
+                        if (j4 == 2) {
+                            settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                                      (tag >> TAG_EPOCH_SHIFT) != epoch;
+                            eqA = eqA && settled;
+                        }
+                        const uint32_t eqb = ((__ballot_sync(0xFFFFFFFFu, eqA) >> (g4 * 4)) & 0xFu) |
+                                             (((__ballot_sync(0xFFFFFFFFu, eqB) >> (g4 * 4)) & 0xFu) << 4);
+                        const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g4 * 4 + 2)) & 1u;
+                        const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches
+                        if (fast && j4 == 0) s.res[ridx4[r]] = slot4[r];
+                        if (fast && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
+                        if (fast && j4 == 2) {
+                            s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                            if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx4[r]] != 0) {
+                                unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot4[r] * 8 + 2]) + 1;
+                                if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                                cs.any_dirty = 1;
+                            }
+                        }
+                        const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
+                        const bool to_slow = act && !fast && !collide;
+                        if (collide) slot4[r] = (slot4[r] + 1) & tmask;
+                        else pend4 &= ~(1u << r);
+                        const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j4 == 0);
+                        if (slowb) {
+                            if (to_slow && j4 == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx4[r];
+                            nslow += __popc(slowb);
+                        }
+                    }
+                    if (!__any_sync(0xFFFFFFFFu, pend4 != 0u)) break;
+                }
+            } else {
             // 8 lanes per flow, 16 identity lines in flight per warp; pass 0 = home slot, pass 1 = next slot for
             // the flows whose home slot is held by another settled flow
 #pragma unroll 1
@@ -405,6 +507,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                     }
                 }
                 if (!__any_sync(0xFFFFFFFFu, pend != 0u)) break;
+            }
             }
             __syncwarp();
             if (kProf && lane == 0) { c_reps += c_end - c0; c_slow += nslow; }
@@ -655,6 +758,11 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
         cudaFuncSetAttribute(aggregate_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(aggregate_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(aggregate_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
     const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
@@ -669,6 +777,16 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
         aggregate_kernel<true, false, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
     else if (dev_n)
         aggregate_kernel<false, false, true><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
+    else if ((a.opt & 224u) == 128u)                      // experiment variants (plain ingest only)
+        aggregate_kernel<false, false, false, 4><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
+    else if ((a.opt & 224u) == 160u)
+        aggregate_kernel<false, false, false, 5><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
+    else if ((a.opt & 96u) == 32u)
+        aggregate_kernel<false, false, false, 1><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
+    else if ((a.opt & 96u) == 64u)
+        aggregate_kernel<false, false, false, 2><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
+    else if ((a.opt & 96u) == 96u)
+        aggregate_kernel<false, false, false, 3><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
     else
         aggregate_kernel<false, false, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
 #undef FA_K1_ARGS

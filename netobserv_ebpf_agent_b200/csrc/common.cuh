@@ -120,6 +120,11 @@ FA_HD bool  eq4_masked(uint4 a, uint4 b, uint4 m) {
     return (((a.x ^ b.x) & m.x) | ((a.y ^ b.y) & m.y) | ((a.z ^ b.z) & m.z) | ((a.w ^ b.w) & m.w)) == 0u;
 }
 
+// OR of the masked differences of two chunks: 0 iff equal (for OR-accumulated, branch-free compares)
+FA_HD uint32_t diff4_masked(uint4 a, uint4 b, uint4 m) {
+    return ((a.x ^ b.x) & m.x) | ((a.y ^ b.y) & m.y) | ((a.z ^ b.z) & m.z) | ((a.w ^ b.w) & m.w);
+}
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
