@@ -254,39 +254,68 @@ def run_ours(args, wl):
     flows = eng.live_flows()
 
     # ---------------------------------------------------------------- end-to-end through the C ABI, host buffers
+    # Every rank feeds its own slice from pinned host memory over its own PCIe link (N > 1: through the sharded
+    # aggregator, whose local engine does the H2D copy); the timed region has the copies, a per-step read-back and
+    # the final lookup-and-delete to host memory.  Preparation failures are agreed on by all ranks before the
+    # loop starts, so a rank can never be left alone inside a collective.
     e2e = None
-    if world == 1 and not args.no_e2e:
-        Be = args.e2e_batch
-        eng.evict_into(batches[0].data_ptr(), B)          # reset the cache (flows <= B)
-        hring = []
-        for i in range(min(4, ring + 1)):
-            h = torch.empty(Be * REC, dtype=torch.uint8).pin_memory()
-            d = torch.empty(Be * REC, dtype=torch.uint8, device=dev)
-            eng.gen_records(gp, i * Be, Be, d)
-            eng.sync()
-            h.copy_(d)
-            hring.append(h)
-            del d
-        out_host = torch.empty(min(args.max_entries, wl["n_keys"]) * REC, dtype=torch.uint8).pin_memory()
-        for i in range(2):
-            eng.ingest(hring[i % len(hring)].data_ptr(), Be)
-        eng.live_flows()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        d2h = 0
-        for i in range(args.e2e_steps):
-            rc, took = eng.ingest(hring[i % len(hring)].data_ptr(), Be)       # H2D inside
-            assert rc == 0 and took == Be
-            eng.live_flows()                                                  # per-step result read-back (64 B)
-            d2h += 64
-        nfl = eng.evict_into(out_host.data_ptr(), out_host.numel() // REC)     # final lookup-and-delete to host
-        d2h += nfl * REC
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e = {"value": Be * args.e2e_steps / dt / 1e6, "unit": "Mpkts/s",
-               "h2d_bytes_per_step": Be * REC, "d2h_bytes_per_step": d2h // args.e2e_steps,
-               "records_per_step": Be, "steps": args.e2e_steps, "flows_evicted": int(nfl),
-               "note": "fa_ingest(pinned host records) + fa_live_flows per step, final fa_evict to host inside the timed region"}
+    host_ok = world == 1 or args.exchange == "peer"       # the NCCL variant's scratch streams are device-input only
+    if not args.no_e2e and host_ok:
+        Be = min(args.e2e_batch, args.max_batch)
+        prep_err = None
+        hring, out_host = [], None
+        try:
+            if world == 1:
+                eng.evict_into(batches[0].data_ptr(), B)      # reset the cache (flows <= B)
+            for i in range(min(4, ring + 1)):
+                h = torch.empty(Be * REC, dtype=torch.uint8).pin_memory()
+                d = torch.empty(Be * REC, dtype=torch.uint8, device=dev)
+                eng.gen_records(gp, ((ring + i) * world + rank) * B, Be, d)
+                eng.sync()
+                h.copy_(d)
+                hring.append(h)
+                del d
+            out_host = torch.empty(min(args.max_entries, wl["n_keys"]) * REC, dtype=torch.uint8).pin_memory()
+        except Exception as ex:                                # noqa: BLE001 - reported in the JSON line
+            prep_err = repr(ex)
+        ok = torch.tensor([0 if prep_err else 1], device=dev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            def e2e_step(i):
+                h = hring[i % len(hring)]
+                if world == 1:
+                    rc, took = eng.ingest(h.data_ptr(), Be)   # H2D inside
+                    assert rc == 0 and took == Be
+                else:
+                    agg.ingest(h, Be)                          # H2D inside the local combiner's fa_ingest
+            for i in range(2):
+                e2e_step(i)
+            eng.live_flows()
+            barrier()
+            t0 = time.perf_counter()
+            d2h = 0
+            for i in range(args.e2e_steps):
+                e2e_step(i)
+                eng.live_flows()                               # per-step result read-back (64 B)
+                d2h += 64
+            finish()
+            nfl = eng.evict_into(out_host.data_ptr(), out_host.numel() // REC)   # final lookup-and-delete to host
+            d2h += nfl * REC
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            e2e = {"value": world * Be * args.e2e_steps / dt / 1e6, "unit": "Mpkts/s",
+                   "h2d_bytes_per_step": world * Be * REC, "d2h_bytes_per_step": d2h // args.e2e_steps,
+                   "records_per_step": world * Be, "steps": args.e2e_steps, "flows_evicted_rank0": int(nfl),
+                   "note": ("fa_ingest(pinned host records) + fa_live_flows per step, final fa_evict to host inside the "
+                            "timed region; wall clock, max over ranks; every rank feeds its slice over its own PCIe link"
+                            + ("" if world == 1 else "; d2h bytes are rank 0's"))}
+        elif rank == 0:
+            e2e = {"value": None, "unit": "Mpkts/s", "error": prep_err or "preparation failed on another rank"}
 
     if rank == 0:
         peak, peak_src = peaks()
