@@ -71,9 +71,7 @@ struct __align__(128) AggSmem {                   // 220,240 B of the 227 KB an 
     uint32_t n_insert, n_spill, any_dirty, pad;
 };
 
-__device__ __forceinline__ void team_sync(int team) {
-    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(kTile) : "memory");
-}
+__device__ __forceinline__ void team_sync(int team) { named_barrier_sync(team + 1, kTile); }
 
 __device__ __forceinline__ void issue_tile_load(TeamSmem& s, const uint4* recs, uint32_t n, uint32_t tile_idx) {
     const uint32_t first = tile_idx * kTile;
@@ -201,7 +199,7 @@ template <bool kSketch, bool kProf, bool kDevN, int kVar = 0>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
                  uint32_t* __restrict__ spill_idx, SketchParams sk, unsigned long long* prof, uint32_t opt) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    FA_DYN_SMEM(smem_raw);
     AggSmem& cs = *reinterpret_cast<AggSmem*>(smem_raw);
     const int team = threadIdx.x >> 8;
     const int tid = threadIdx.x & (kTile - 1), lane = tid & 31, warp = tid >> 5;     // within the team
@@ -745,6 +743,7 @@ __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint
     }
 }
 
+#ifndef FA_HOST_EMUL
 int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
     if (a.n == 0) return 0;
     static bool attr_done_dev[64] = {};                // function attributes are per device
@@ -796,5 +795,6 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
                                               reinterpret_cast<unsigned int*>(&a.ctr->scratch[1]));
     return 3;
 }
+#endif  // FA_HOST_EMUL
 
 }  // namespace fa

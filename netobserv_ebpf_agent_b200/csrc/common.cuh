@@ -125,6 +125,13 @@ FA_HD uint32_t diff4_masked(uint4 a, uint4 b, uint4 m) {
     return ((a.x ^ b.x) & m.x) | ((a.y ^ b.y) & m.y) | ((a.z ^ b.z) & m.z) | ((a.w ^ b.w) & m.w);
 }
 
+// dynamic shared memory of a kernel; the host emulation of the tests (tests/emul/simt.h) hands out a per-CTA buffer
+#ifdef FA_HOST_EMUL
+#define FA_DYN_SMEM(name) uint8_t* name = simt::ctx().cta->smem
+#else
+#define FA_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#endif
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,6 +150,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// named barrier over `count` threads of the CTA (SASS: BAR.SYNC id, count)
+__device__ __forceinline__ void named_barrier_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -104,11 +104,13 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
     }
 }
 
+#ifndef FA_HOST_EMUL
 int launch_evict(const Table& table, uint4* out_recs, uint32_t* slot_of_out,
                  unsigned long long cap, Counters* ctr, int sm_count, cudaStream_t st, bool drain) {
     if (drain) evict_kernel<true><<<sm_count * 8, 256, 0, st>>>(table, out_recs, slot_of_out, cap, ctr);
     else evict_kernel<false><<<sm_count * 8, 256, 0, st>>>(table, out_recs, slot_of_out, cap, ctr);
     return 1;
 }
+#endif  // FA_HOST_EMUL
 
 }  // namespace fa

@@ -1,0 +1,109 @@
+// k1_emul.cpp — K1 (aggregate_kernel + the two re-fold kernels) and K2 (evict_kernel) of the product, compiled for
+// the host on top of simt.h and run with one OS thread per CUDA thread (test infrastructure, never part of
+// libflowagg.so).  tests/test_k1_emulation.py compares what comes out with the oracle's Accounter.  This lets a change
+// to the kernels' logic (e.g. the experiment variants, template parameter kVar) be checked for bit-exactness on the
+// CPU at small sizes before any GPU time is spent on it; speed, registers and the device memory model are not covered.
+#define FA_HOST_EMUL 1
+#include "simt.h"
+
+#include "../../netobserv_ebpf_agent_b200/csrc/aggregate.cu"
+#include "../../netobserv_ebpf_agent_b200/csrc/evict.cu"
+
+using namespace fa;
+
+namespace {
+struct Emul {
+    Table t{};
+    uint64_t slots = 0, epoch = 0;
+    Counters* ctr = nullptr;
+    FixupScratch* scratch = nullptr; uint32_t scratch_slots = 0;
+    uint32_t* spill_idx = nullptr;
+    uint64_t max_batch = 0;
+};
+void* zalloc(size_t bytes) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 1024, bytes ? bytes : 1024)) abort();
+    memset(p, 0, bytes ? bytes : 1024);
+    return p;
+}
+template <int kVar>
+void run_k1(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt) {
+    const uint64_t epoch = e->epoch;
+    Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx;
+    SketchParams sk{};
+    simt::launch(grid, kCtaThreads, sizeof(AggSmem), [=] {
+        aggregate_kernel<false, false, false, kVar>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
+    });
+}
+}  // namespace
+
+extern "C" {
+
+void* k1_emul_new(uint64_t max_entries, uint64_t max_batch) {
+    Emul* e = new Emul();
+    uint64_t want = max_entries + max_entries / 3 + 1, slots = 1024;
+    while (slots < want) slots <<= 1;
+    e->slots = slots; e->max_batch = max_batch;
+    e->t.mask = slots - 1;
+    e->t.ident = static_cast<uint4*>(zalloc(slots * kIdentBytes));
+    e->t.hot = static_cast<uint4*>(zalloc(slots * kHotBytes));
+    e->t.occ = static_cast<uint32_t*>(zalloc(slots / 8));
+    e->ctr = static_cast<Counters*>(zalloc(sizeof(Counters)));
+    uint32_t ss = 1024; while ((uint64_t)ss < 2 * max_batch) ss <<= 1;
+    e->scratch_slots = ss;
+    e->scratch = static_cast<FixupScratch*>(zalloc((size_t)ss * sizeof(FixupScratch)));
+    e->spill_idx = static_cast<uint32_t*>(zalloc(max_batch * 4));
+    return e;
+}
+void k1_emul_free(void* h) {
+    Emul* e = static_cast<Emul*>(h);
+    free(e->t.ident); free(e->t.hot); free(e->t.occ); free(e->ctr); free(e->scratch); free(e->spill_idx);
+    delete e;
+}
+
+// one launch_aggregate: K1 (variant kVar = var) on `grid` CTAs, then the ordered re-fold.  recs: 16-byte aligned.
+int k1_emul_ingest(void* h, const uint8_t* recs8, uint32_t n, unsigned grid, int var, uint32_t opt) {
+    Emul* e = static_cast<Emul*>(h);
+    if (n == 0 || n > e->max_batch || (reinterpret_cast<uintptr_t>(recs8) & 15)) return -1;
+    const uint4* recs = reinterpret_cast<const uint4*>(recs8);
+    e->epoch++;
+    const uint32_t n_tiles = (n + kTile - 1) / kTile;
+    grid = std::min<unsigned>(grid, (n_tiles + kTeams - 1) / kTeams);
+    switch (var) {
+        case 0: run_k1<0>(e, recs, n, grid, opt); break;
+        case 1: run_k1<1>(e, recs, n, grid, opt); break;
+        case 2: run_k1<2>(e, recs, n, grid, opt); break;
+        case 3: run_k1<3>(e, recs, n, grid, opt); break;
+        case 4: run_k1<4>(e, recs, n, grid, opt); break;
+        case 5: run_k1<5>(e, recs, n, grid, opt); break;
+        default: return -2;
+    }
+    Table t = e->t; Counters* ctr = e->ctr; FixupScratch* sc = e->scratch; const uint32_t ss = e->scratch_slots;
+    const uint64_t epoch = e->epoch;
+    simt::launch(2, 256, 0, [=] { fixup_scan_kernel(recs, n, t, ctr, sc, ss - 1, opt); });
+    simt::launch(2, 256, 0, [=] {
+        fixup_apply_kernel(recs, t, epoch, ctr, sc, ss, reinterpret_cast<unsigned int*>(&ctr->scratch[1]));
+    });
+    for (uint32_t i = 0; i < ss; i++) if (sc[i].key) return -3;       // scratch must be clean between launches
+    return 0;
+}
+
+uint64_t k1_emul_live(void* h) { return static_cast<Emul*>(h)->ctr->live; }
+uint64_t k1_emul_counter(void* h, int which) {
+    Counters* c = static_cast<Emul*>(h)->ctr;
+    return which == 0 ? c->live : which == 1 ? c->spills : which == 2 ? c->fixups_total : c->dirty;
+}
+
+// K2: lookup-and-delete everything; returns the number of flows found
+uint64_t k1_emul_evict(void* h, uint8_t* out, uint64_t cap) {
+    Emul* e = static_cast<Emul*>(h);
+    Table t = e->t; Counters* ctr = e->ctr;
+    ctr->evict_out = 0;
+    uint4* o = reinterpret_cast<uint4*>(out);
+    simt::launch(2, 256, 0, [=] { evict_kernel<false>(t, o, nullptr, cap, ctr); });
+    const uint64_t n = ctr->evict_out;
+    ctr->live = 0;
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+"""Builds the host-emulation libraries under tests/emul/ (g++, no CUDA device needed; the CUDA toolkit's headers are
+only used for the vector types).  Test infrastructure: nothing here is part of, or linked into, libflowagg.so."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMUL = os.path.join(HERE, "emul")
+BUILD = os.path.join(EMUL, "_build")
+CSRC = os.path.join(HERE, "..", "netobserv_ebpf_agent_b200", "csrc")
+
+
+def build(name, deps, flags=()):
+    """Compile tests/emul/<name>.cpp into tests/emul/_build/lib<name>.so if any of `deps` is newer."""
+    os.makedirs(BUILD, exist_ok=True)
+    src = os.path.join(EMUL, name + ".cpp")
+    so = os.path.join(BUILD, "lib" + name + ".so")
+    newest = max(os.path.getmtime(p) for p in [src] + list(deps))
+    if not os.path.exists(so) or os.path.getmtime(so) < newest:
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        tmp = so + f".tmp{os.getpid()}"
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas",
+                        "-I" + cuda_inc, *flags, "-o", tmp, src], check=True)
+        os.replace(tmp, so)
+    return so
+
+
+def csrc(*names):
+    return [os.path.join(CSRC, n) for n in names]

@@ -1,0 +1,134 @@
+"""K1 / K2 logic check on the CPU: csrc/aggregate.cu (aggregate_kernel, every experiment variant kVar, plus the two
+ordered re-fold kernels) and csrc/evict.cu are compiled by g++ on top of tests/emul/simt.h — one OS thread per CUDA
+thread, warp collectives / barriers / atomics / the TMA+mbarrier tile load mapped to host equivalents — and the flows
+that come out are compared with the oracle's Accounter bit for bit.  What this buys: a change to the kernels' logic
+is checked for exactness (under real preemptive concurrency, several CTAs at once) before any GPU time is spent;
+what it cannot say anything about: speed, registers, the device memory model.  The GPU parity tests stay the gate."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from common import gen_host
+from emul_build import build, csrc
+from test_kmap_emulation import aligned_copy
+
+_lib = None
+
+
+def emul():
+    global _lib
+    if _lib is None:
+        so = build("k1_emul", csrc("aggregate.cu", "evict.cu", "common.cuh", "kernels.cuh") + [__file__.replace("test_k1_emulation.py", "emul/simt.h")])
+        L = ctypes.CDLL(so)
+        L.k1_emul_new.restype = ctypes.c_void_p
+        L.k1_emul_new.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
+        L.k1_emul_free.argtypes = [ctypes.c_void_p]
+        L.k1_emul_ingest.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint, ctypes.c_int, ctypes.c_uint32]
+        L.k1_emul_evict.restype = ctypes.c_uint64
+        L.k1_emul_evict.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.k1_emul_live.restype = ctypes.c_uint64
+        L.k1_emul_live.argtypes = [ctypes.c_void_p]
+        L.k1_emul_counter.restype = ctypes.c_uint64
+        L.k1_emul_counter.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+class K1:
+    def __init__(self, max_entries, max_batch=1 << 16, var=0, grid=2, opt=0):
+        self.h = emul().k1_emul_new(max_entries, max_batch)
+        self.var, self.grid, self.opt, self.max_batch = var, grid, opt, max_batch
+
+    def ingest(self, recs):
+        a = aligned_copy(recs)
+        n = a.size // O.REC
+        for lo in range(0, n, self.max_batch):
+            c = min(self.max_batch, n - lo)
+            rc = emul().k1_emul_ingest(self.h, a[lo * O.REC:].ctypes.data, c, self.grid, self.var, self.opt)
+            assert rc == 0, f"emulated launch failed: {rc}"
+
+    def evict(self):
+        n = emul().k1_emul_live(self.h)
+        out = np.zeros(max(n, 1) * O.REC, dtype=np.uint8)
+        got = emul().k1_emul_evict(self.h, out.ctypes.data, n)
+        assert got == n, f"table scan found {got} flows, live counter says {n}"
+        return out[: n * O.REC].reshape(-1, O.REC)
+
+    def counter(self, which):
+        return emul().k1_emul_counter(self.h, which)
+
+    def close(self):
+        if self.h:
+            emul().k1_emul_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def same_flows(got, want):
+    got, want = O.sort_records(got), O.sort_records(want)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    if not np.array_equal(got, want):
+        g, w = got.view(O.REC_DTYPE).reshape(-1), want.view(O.REC_DTYPE).reshape(-1)
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        diff = [f for f in O.REC_DTYPE.names if not np.array_equal(g[bad[0]][f], w[bad[0]][f])]
+        raise AssertionError(f"{len(bad)} of {len(got)} flows differ; first {bad[0]}: {diff}: want {[w[bad[0]][f] for f in diff]} got {[g[bad[0]][f] for f in diff]}")
+
+
+VARIANTS = [0, 1, 2, 3, 4, 5]      # kVar of aggregate_kernel: 0 = the measured default, others = FA_K1_OPT experiments
+
+
+@pytest.mark.parametrize("var", VARIANTS)
+def test_zipf_stream_with_varying_descriptors_two_launches(var):
+    """Hot flows (cache, tile-local folds), order-dependent descriptor fields (ordered re-fold), a second launch that
+    meets the flows of the first one in the table."""
+    recs = gen_host(seed=7, n=24_000, n_keys=400, dist=1, varying=1)
+    k1 = K1(1 << 12, max_batch=16_000, var=var, grid=2)
+    k1.ingest(recs)
+    acc = O.Accounter(1 << 12)
+    acc.account(recs)
+    same_flows(k1.evict(), acc.evict())
+    assert k1.counter(1) == 0                                   # no spills
+
+
+@pytest.mark.parametrize("var", [0, 4])
+def test_uniform_keys_crowded_table(var):
+    """Mostly inserts, collision chains (load ~0.7 of the slots), no duplicates to speak of: the general probe loop."""
+    recs = gen_host(seed=8, n=6_000, n_keys=5_600, dist=0)
+    k1 = K1(6_000, max_batch=8_192, var=var, grid=3)            # 8192 slots
+    k1.ingest(recs)
+    acc = O.Accounter(1 << 14)
+    acc.account(recs)
+    same_flows(k1.evict(), acc.evict())
+
+
+@pytest.mark.parametrize("var", [0, 4])
+def test_eviction_then_reuse_of_the_table(var):
+    a = gen_host(seed=9, n=8_000, n_keys=900, dist=1)
+    b = gen_host(seed=10, n=8_000, n_keys=700, dist=1, varying=1, first=8_000)
+    k1 = K1(1 << 11, max_batch=8_192, var=var, grid=2)
+    for part in (a, b):
+        k1.ingest(part)
+        acc = O.Accounter(1 << 11)
+        acc.account(part)
+        same_flows(k1.evict(), acc.evict())
+
+
+@pytest.mark.parametrize("var", [0, 4])
+def test_pre_aggregated_records_and_wraparound(var):
+    """Records that are themselves flows (packets > 1, 64-bit byte counts that carry, u32 packet wrap, zero and
+    non-monotone timestamps): what the multi-GPU combine step feeds the owner."""
+    rng = np.random.default_rng(11)
+    recs = gen_host(seed=11, n=6_000, n_keys=150, dist=1).copy()
+    r = recs.view(O.REC_DTYPE).reshape(-1)
+    r["packets"] = rng.choice(np.array([1, 7, 0xFFFFFFF0, 0x80000000], dtype=np.uint32), len(r))
+    r["bytes"] = rng.choice(np.array([60, 0xFFFFFFFF, 0x1_0000_0001, 0xFFFFFFFF_FFFFFF00], dtype=np.uint64), len(r))
+    r["start"] = rng.choice(np.array([0, 5, 1 << 33, (1 << 40) + 3], dtype=np.uint64), len(r))
+    r["end"] = rng.choice(np.array([0, 9, 1 << 34, (1 << 41) + 1], dtype=np.uint64), len(r))
+    k1 = K1(1 << 10, max_batch=8_192, var=var, grid=2)
+    k1.ingest(recs)
+    acc = O.Accounter(1 << 10)
+    acc.account(recs)
+    same_flows(k1.evict(), acc.evict())
