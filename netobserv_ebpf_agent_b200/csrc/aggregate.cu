@@ -284,6 +284,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                            (v_end == 0 || (uint32_t)(v_end >> 32) == ce.end_hi);
                     if (same) {
                         is_rep = false;
+                        FA_EMUL_COUNT(2, 1);
                         if (kProf) c_cached++;
                         uint32_t* A = ce.acc;
                         const uint32_t b_lo = r3.z, b_hi = r3.w;
@@ -508,6 +509,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             }
             }
             __syncwarp();
+            if (lane == 0) { FA_EMUL_COUNT(0, c_end - c0); FA_EMUL_COUNT(1, nslow); }
             if (kProf && lane == 0) { c_reps += c_end - c0; c_slow += nslow; }
             FA_PROF_MARK(3);                                       // pipelined probe passes
             for (uint32_t base = 0; base < nslow; base += 4) {     // inserts, long collision chains, in-flight publishes

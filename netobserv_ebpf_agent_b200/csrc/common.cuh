@@ -128,8 +128,10 @@ FA_HD uint32_t diff4_masked(uint4 a, uint4 b, uint4 m) {
 // dynamic shared memory of a kernel; the host emulation of the tests (tests/emul/simt.h) hands out a per-CTA buffer
 #ifdef FA_HOST_EMUL
 #define FA_DYN_SMEM(name) uint8_t* name = simt::ctx().cta->smem
+#define FA_EMUL_COUNT(which, n) simt::count(which, n)      // path counters of the emulation (nothing on the device)
 #else
 #define FA_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#define FA_EMUL_COUNT(which, n) ((void)0)
 #endif
 
 #ifdef __CUDACC__

@@ -88,6 +88,10 @@ int k1_emul_ingest(void* h, const uint8_t* recs8, uint32_t n, unsigned grid, int
     return 0;
 }
 
+// path counters since the last call: 0 representatives probed, 1 of them through the general loop, 2 cache hits
+void k1_emul_paths(uint64_t out[3]) {
+    for (int i = 0; i < 3; i++) { out[i] = simt::g_counts[i]; simt::g_counts[i] = 0; }
+}
 uint64_t k1_emul_live(void* h) { return static_cast<Emul*>(h)->ctr->live; }
 uint64_t k1_emul_counter(void* h, int which) {
     Counters* c = static_cast<Emul*>(h)->ctr;

@@ -91,6 +91,10 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
     for (void* p : smem_raw) free(p);
 }
 
+// path counters a kernel may bump through FA_EMUL_COUNT (reset / read by the harness)
+inline unsigned long long g_counts[8] = {};
+inline void count(int which, unsigned long long n) { __atomic_fetch_add(&g_counts[which & 7], n, __ATOMIC_RELAXED); }
+
 inline void named_barrier(int id, unsigned count) {
     Cta& c = *ctx().cta;
     Barrier* b;

@@ -32,6 +32,7 @@ def emul():
         L.k1_emul_live.argtypes = [ctypes.c_void_p]
         L.k1_emul_counter.restype = ctypes.c_uint64
         L.k1_emul_counter.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.k1_emul_paths.argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -58,6 +59,13 @@ class K1:
 
     def counter(self, which):
         return emul().k1_emul_counter(self.h, which)
+
+    @staticmethod
+    def paths():
+        """(representatives probed, of them through the general loop, cache hits) since the last call."""
+        c = (ctypes.c_uint64 * 3)()
+        emul().k1_emul_paths(c)
+        return tuple(int(x) for x in c)
 
     def close(self):
         if self.h:
@@ -131,4 +139,27 @@ def test_pre_aggregated_records_and_wraparound(var):
     k1.ingest(recs)
     acc = O.Accounter(1 << 10)
     acc.account(recs)
+    same_flows(k1.evict(), acc.evict())
+
+
+@pytest.mark.parametrize("var", VARIANTS)
+def test_fast_paths_are_taken(var):
+    """A wrong compare in a fast path only costs speed (the flow drops to the general loop or to the ordered re-fold
+    and still comes out exact), so exactness alone would not notice it.  Constant descriptors, second launch over
+    flows that are all in the table: no re-fold, (almost) no general-loop probes, and the hot flows hit the cache."""
+    a = gen_host(seed=12, n=12_000, n_keys=500, dist=1)
+    b = gen_host(seed=12, n=12_000, n_keys=500, dist=1, first=12_000)
+    k1 = K1(1 << 12, max_batch=16_384, var=var, grid=2)
+    k1.ingest(a)
+    K1.paths()
+    k1.ingest(b)
+    reps, slow, cached = K1.paths()
+    new_flows = len(np.unique(np.concatenate([O.as_bytes(a).reshape(-1, O.REC)[:, :39], O.as_bytes(b).reshape(-1, O.REC)[:, :39]]), axis=0)) - \
+        len(np.unique(O.as_bytes(a).reshape(-1, O.REC)[:, :39], axis=0))
+    assert k1.counter(2) == 0                                   # no ordered re-fold
+    assert reps > 0 and slow <= new_flows + reps // 50, (reps, slow, new_flows)
+    assert cached > 12_000 // 10, cached                        # the Zipf head is served on-chip
+    acc = O.Accounter(1 << 12)
+    acc.account(a)
+    acc.account(b)
     same_flows(k1.evict(), acc.evict())
