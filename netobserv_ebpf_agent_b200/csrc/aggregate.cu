@@ -644,6 +644,283 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
 }
 
 // ------------------------------------------------------------------------------------
+// K1w — warp-independent variant of K1 (experiment, FA_K1_OPT bit 8; not the measured default).
+//
+// Same table protocol, cache, probe code and reductions as aggregate_kernel, but no team: every warp owns 32-record
+// sub-tiles (its own 4.6 KB TMA buffer + mbarrier), every record that misses the cache probes the table itself
+// (4 lanes per flow, 8 flows per round), and its totals stay in the owning lane's registers.  What goes away: the
+// tile-local election and duplicate fold (a path that runs at ~3 active lanes), the representative list, the
+// per-tile accumulators and both team barriers; what it costs: duplicates of an un-cached flow inside one tile probe
+// and reduce separately (commutative, so still exact).
+// ------------------------------------------------------------------------------------
+constexpr int kWWarps = 32;                      // warps per CTA
+constexpr int kWSub = 32;                        // records per sub-tile == lanes
+constexpr int kWLast = 1024;                     // "seen this flow a moment ago" filter (cache candidacy)
+constexpr int kWHot = 256;                       // direct-mapped cache of hot flows (the room the team structures took)
+struct __align__(128) WarpSmem {                 // 5,120 B per warp
+    uint4    tile[kWSub * kRecChunks];           // 4,608 B
+    uint32_t res[kWSub];                         //   128 B  table slot found for each probing lane
+    uint32_t mir_lo[kWSub];                      //   128 B
+    uint16_t mir_hi[kWSub];                      //    64 B
+    uint16_t fseen[kWSub];                       //    64 B
+    uint8_t  slow[kWSub];                        //    32 B  lanes whose flow needs the general probe loop
+    unsigned long long full_bar;
+    uint8_t  pad[88];
+};
+static_assert(sizeof(WarpSmem) == 5120, "WarpSmem");
+struct __align__(128) AggWSmem {                 // 221,200 B
+    WarpSmem w[kWWarps];
+    HotEntry hot[kWHot];
+    uint32_t last[kWLast];
+    uint32_t n_insert, n_spill, any_dirty, pad;
+};
+
+__device__ __forceinline__ void issue_sub_load(WarpSmem& s, const uint4* recs, uint32_t n, uint32_t sub) {
+    const uint32_t first = sub * kWSub;
+    const uint32_t bytes = min((uint32_t)kWSub, n - first) * kRecBytes;
+    mbar_expect_tx(&s.full_bar, bytes);
+    tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
+}
+
+template <bool kSketch, bool kDevN>
+__global__ void __launch_bounds__(kWWarps * 32, 1)
+aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
+                      uint32_t* __restrict__ spill_idx, SketchParams sk, uint32_t opt) {
+    FA_DYN_SMEM(smem_raw);
+    AggWSmem& cs = *reinterpret_cast<AggWSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem& s = cs.w[warp];
+    if (kDevN) n = min(n, (uint32_t)ctr->launch_n);
+    const uint32_t n_sub = (n + kWSub - 1) / kWSub;
+    const uint32_t sub_stride = gridDim.x * kWWarps;
+    const uint32_t sub0 = blockIdx.x * kWWarps + warp;
+    const bool use_cache = (opt & 2u) == 0;
+
+    if (threadIdx.x == 0) { cs.n_insert = 0; cs.n_spill = 0; cs.any_dirty = 0; }
+    if (threadIdx.x < kWHot) cs.hot[threadIdx.x].state = 0;
+    cs.last[threadIdx.x] = 0u;
+    if (lane == 0) { mbar_init(&s.full_bar, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (lane == 0 && sub0 < n_sub) issue_sub_load(s, recs, n, sub0);
+
+    const int g = lane >> 3, j = lane & 7;                       // 8-lane groups of the general probe loop
+    const uint4 cmask = chunk_mask(j);
+    const int rc = rec_chunk_of_line_chunk(j);
+    const int g4 = lane >> 2, j4 = lane & 3;                     // 4-lane groups of the pipelined passes
+    const uint4 cmaskA = chunk_mask(j4), cmaskB = chunk_mask(j4 + 4);
+    const int rcA = rec_chunk_of_line_chunk(j4), rcB = j4 + 5;
+    const uint32_t tmask = (uint32_t)t.mask;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t my_inserts = 0, my_spills = 0;
+    const uint4* T = s.tile;
+
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t sub = sub0 + it * sub_stride;
+        if (sub >= n_sub) break;
+        const uint32_t first = sub * kWSub;
+        const uint32_t cnt = min((uint32_t)kWSub, n - first);
+        mbar_wait(&s.full_bar, it & 1u);
+
+        // ------------------------------------------------------ hash, cache
+        const bool valid = (uint32_t)lane < cnt;
+        bool is_rep = valid;
+        uint32_t h32 = 0;
+        const uint4* R = T + lane * kRecChunks;
+        if (valid) {
+            const uint4 r0 = R[0], r1 = R[1], r2 = R[2];
+            const uint64_t h = slot_hash(key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
+                                                    u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)));
+            h32 = (uint32_t)h;
+            HotEntry& ce = cs.hot[(h32 >> 24) & (kWHot - 1)];
+            if (use_cache && *reinterpret_cast<volatile uint32_t*>(&ce.state) == 2u && ce.hash == h32) {
+                const uint4 r3 = R[3], r4 = R[4];
+                bool same = eq4_masked(ce.line[0], r0, chunk_mask(0)) && eq4_masked(ce.line[1], r1, chunk_mask(1)) &&
+                            eq4_masked(ce.line[2], r2, chunk_mask(2)) && eq4_masked(ce.line[3], r4, chunk_mask(3));
+#pragma unroll
+                for (int c = 5; c < 9; c++) same = same && eq4_masked(ce.line[c - 1], R[c], chunk_mask(c - 1));
+                const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+                const uint64_t v_ns = 0ull - v_start;
+                same = same && (v_start == 0 || (uint32_t)(v_ns >> 32) == ce.ns_hi) &&
+                       (v_end == 0 || (uint32_t)(v_end >> 32) == ce.end_hi);
+                if (same) {
+                    is_rep = false;
+                    FA_EMUL_COUNT(2, 1);
+                    uint32_t* A = ce.acc;
+                    const uint32_t b_lo = r3.z, b_hi = r3.w;
+                    const uint32_t prev = atomicAdd(&A[0], b_lo);
+                    const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
+                    if (hi_add) atomicAdd(&A[1], hi_add);
+                    atomicAdd(&A[2], r4.x);
+                    const uint32_t fl = r4.y >> 16;
+                    if (fl & ~A[3]) atomicOr(&A[3], fl);
+                    if (v_start && (uint32_t)v_ns > A[4]) atomicMax(&A[4], (uint32_t)v_ns);
+                    if (v_end && (uint32_t)v_end > A[5]) atomicMax(&A[5], (uint32_t)v_end);
+                }
+            }
+        }
+
+        // ------------------------------------------------------ probe: the warp's own un-cached records
+        const uint32_t repmask = __ballot_sync(0xFFFFFFFFu, is_rep);
+        const uint32_t nrep = (uint32_t)__popc(repmask);
+        const uint32_t home = h32 & tmask;
+        uint32_t nslow = 0;
+        constexpr int kRounds = 2;
+        for (uint32_t base = 0; base < nrep; base += 8u * kRounds) {
+            uint32_t ridx4[kRounds], slot4[kRounds];
+            uint32_t pend4 = 0;
+#pragma unroll
+            for (int r = 0; r < kRounds; r++) {
+                const uint32_t f = base + r * 8 + g4;
+                const bool act = f < nrep;
+                ridx4[r] = act ? __fns(repmask, 0, (int)f + 1) : 0u;     // the lane that owns the f-th probing record
+                if (act) pend4 |= 1u << r;
+                slot4[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx4[r]);
+            }
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                uint4 lineA[kRounds], lineB[kRounds];
+#pragma unroll
+                for (int r = 0; r < kRounds; r++) {
+                    lineA[r] = make_uint4(0, 0, 0, 0); lineB[r] = make_uint4(0, 0, 0, 0);
+                    if ((pend4 >> r) & 1u) {
+                        lineA[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4]);
+                        lineB[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4 + 4]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kRounds; r++) {
+                    const bool act = (pend4 >> r) & 1u;
+                    const uint4* RR = T + ridx4[r] * kRecChunks;
+                    bool eqA = eq4_masked(lineA[r], RR[rcA], cmaskA);
+                    const bool eqB = eq4_masked(lineB[r], RR[rcB], cmaskB);
+                    const uint64_t tag = u64_of(lineA[r].z, lineA[r].w);   // meaningful in lane j4 == 2 only
+                    bool settled = false;
+                    if (j4 == 2) {
+                        settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                                  (tag >> TAG_EPOCH_SHIFT) != epoch;
+                        eqA = eqA && settled;
+                    }
+                    const uint32_t eqb = ((__ballot_sync(0xFFFFFFFFu, eqA) >> (g4 * 4)) & 0xFu) |
+                                         (((__ballot_sync(0xFFFFFFFFu, eqB) >> (g4 * 4)) & 0xFu) << 4);
+                    const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g4 * 4 + 2)) & 1u;
+                    const bool fast = act && (eqb & 0x07u) == 0x07u;       // settled flow, key matches
+                    if (fast && j4 == 0) s.res[ridx4[r]] = slot4[r];
+                    if (fast && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
+                    if (fast && j4 == 2) {
+                        s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                        if ((eqb & 0xF8u) != 0xF8u) {                       // descriptor differs: ordered re-fold
+                            unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot4[r] * 8 + 2]) + 1;
+                            if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                            cs.any_dirty = 1;
+                        }
+                    }
+                    const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
+                    const bool to_slow = act && !fast && !collide;
+                    if (collide) slot4[r] = (slot4[r] + 1) & tmask;
+                    else pend4 &= ~(1u << r);
+                    const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j4 == 0);
+                    if (slowb) {
+                        if (to_slow && j4 == 0) s.slow[nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx4[r];
+                        nslow += __popc(slowb);
+                    }
+                }
+                if (!__any_sync(0xFFFFFFFFu, pend4 != 0u)) break;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { FA_EMUL_COUNT(0, nrep); FA_EMUL_COUNT(1, nslow); }
+        for (uint32_t base = 0; base < nslow; base += 4) {         // inserts, long collision chains, in-flight publishes
+            const uint32_t k = base + g;
+            const bool act = k < nslow;
+            const uint32_t ri = act ? s.slow[k] : 0;
+            const uint4 rchunk = T[ri * kRecChunks + rc];
+            const uint4 c2 = T[ri * kRecChunks + 2];
+            const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
+            const uint32_t start_slot = __shfl_sync(0xFFFFFFFFu, home, (int)ri);
+            const uint32_t got = probe_general(t, epoch, act, start_slot, rchunk, false, own_ns, g, j, cmask, my_inserts,
+                                               &cs.any_dirty);
+            if (act && j == 0) s.res[ri] = got;
+            if (act && j == 2) s.fseen[ri] = 0;                     // unknown: issue every reduction
+            if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------ every probing lane reduces its own record
+        if (is_rep) {
+            const uint32_t my_slot = s.res[lane];
+            const uint64_t floor_ns = u64_of(s.mir_lo[lane], s.mir_hi[lane]) << 16;      // <= hot.nstart, always
+            const uint32_t seen = s.fseen[lane];
+            const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
+            const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+            const uint64_t v_ns = 0ull - v_start;
+            // a flow met twice within a short while is hot: give it a cache entry if its slot of the cache is free
+            uint32_t* seen_at = &cs.last[(h32 >> 12) & (kWLast - 1)];
+            const uint32_t before = *reinterpret_cast<volatile uint32_t*>(seen_at);
+            *reinterpret_cast<volatile uint32_t*>(seen_at) = h32;
+            if (use_cache && before == h32 && my_slot != kResSpill) {
+                HotEntry& ce = cs.hot[(h32 >> 24) & (kWHot - 1)];
+                if (*reinterpret_cast<volatile uint32_t*>(&ce.state) == 0u && atomicCAS(&ce.state, 0u, 1u) == 0u) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) ce.line[c] = ld_cg_u4(&t.ident[(size_t)my_slot * 8 + c]);
+                    *reinterpret_cast<uint4*>(&ce.acc[0]) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(&ce.acc[4]) = make_uint4(0, 0, 0, 0);
+                    ce.hash = h32; ce.slot = my_slot;
+                    ce.ns_hi = (uint32_t)(v_ns >> 32); ce.end_hi = (uint32_t)(v_end >> 32);
+                    __threadfence_block();
+                    *reinterpret_cast<volatile uint32_t*>(&ce.state) = 2u;
+                }
+            }
+            if (kSketch) {
+                const uint4 r0 = R[0], r1 = R[1];
+                sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
+                                             u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)), r4.x);
+            }
+            if (my_slot != kResSpill) {
+                reduce_to_hot(t, my_slot, u64_of(r3.z, r3.w), r4.x, v_ns, v_end, r4.y >> 16, floor_ns, seen);
+            } else {                                               // table physically full: spill, never drop silently
+                const unsigned long long kk = atomicAdd(&ctr->scratch[2], 1ull);
+                spill_idx[kk] = first + lane;
+                my_spills++;
+            }
+        }
+        __syncwarp();                                              // nobody reads the sub-tile buffer any more
+        if (lane == 0) {
+            const uint32_t nx = sub + sub_stride;
+            if (nx < n_sub) { fence_proxy_async(); issue_sub_load(s, recs, n, nx); }
+        }
+    }
+
+    // ---------------------------------------------------------- counters + cache flush
+    my_inserts = __reduce_add_sync(0xFFFFFFFFu, my_inserts);
+    my_spills = __reduce_add_sync(0xFFFFFFFFu, my_spills);
+    if (lane == 0) {
+        if (my_inserts) atomicAdd(&cs.n_insert, my_inserts);
+        if (my_spills) atomicAdd(&cs.n_spill, my_spills);
+    }
+    __syncthreads();                                               // every warp is out of sub-tiles
+    if (threadIdx.x < kWHot) {
+        const HotEntry& ce = cs.hot[threadIdx.x];
+        if (ce.state == 2u) {
+            const uint32_t* A = ce.acc;
+            const uint64_t tag = u64_of(ce.line[2].z, ce.line[2].w);
+            const uint64_t floor_ns = u64_of(ce.line[3].x, ce.line[3].y >> 16) << 16;
+            reduce_to_hot(t, ce.slot, u64_of(A[0], A[1]), A[2], u64_of(A[4], ce.ns_hi), u64_of(A[5], ce.end_hi), A[3],
+                          floor_ns, (uint32_t)(tag >> TAG_FLAGS_SHIFT) & 0xFFFFu);
+            if (kSketch) {
+                const uint4 k0 = ce.line[0], k1 = ce.line[1], k2 = ce.line[2];
+                sketch_update(sk, key_premix(u64_of(k0.x, k0.y), u64_of(k0.z, k0.w), u64_of(k1.x, k1.y),
+                                             u64_of(k1.z, k1.w), u64_of(k2.x, k2.y)), A[2]);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (cs.n_insert) atomicAdd(&ctr->live, (unsigned long long)cs.n_insert);
+        if (cs.n_spill) atomicAdd(&ctr->spills, (unsigned long long)cs.n_spill);
+        if (cs.any_dirty) *reinterpret_cast<volatile unsigned long long*>(&ctr->dirty) = 1ull;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Ordered re-fold of flows flagged TAG_DIRTY (rare path; both kernels exit at once when
 // nothing was flagged).  fixup_scan: one thread per record finds its flow and, if dirty,
 // reduces min/max record indices into the flow's scratch entry.  fixup_apply: one thread
@@ -772,6 +1049,23 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
 #define FA_K1_ARGS a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk
     if (a.prof)
         aggregate_kernel<false, true, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, a.prof, a.opt);
+    else if (a.opt & 256u) {                              // warp-independent variant (experiment)
+        static bool wattr[64] = {};
+        const int wsmem = (int)sizeof(AggWSmem);
+        if (!wattr[dev & 63]) {
+            cudaFuncSetAttribute(aggregate_warp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
+            cudaFuncSetAttribute(aggregate_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
+            cudaFuncSetAttribute(aggregate_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
+            cudaFuncSetAttribute(aggregate_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
+            wattr[dev & 63] = true;
+        }
+        const uint32_t n_sub = (a.n + kWSub - 1) / kWSub;
+        const int wgrid = (int)min((uint32_t)a.sm_count, (n_sub + kWWarps - 1) / kWWarps);
+        if (a.sk.cms && dev_n) aggregate_warp_kernel<true, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
+        else if (a.sk.cms) aggregate_warp_kernel<true, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
+        else if (dev_n) aggregate_warp_kernel<false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
+        else aggregate_warp_kernel<false, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
+    }
     else if (a.sk.cms && dev_n)
         aggregate_kernel<true, false, true><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
     else if (a.sk.cms)

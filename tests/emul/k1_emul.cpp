@@ -35,6 +35,14 @@ void run_k1(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt)
         aggregate_kernel<false, false, false, kVar>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
     });
 }
+void run_k1w(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt) {
+    const uint64_t epoch = e->epoch;
+    Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx;
+    SketchParams sk{};
+    simt::launch(grid, kWWarps * 32, sizeof(AggWSmem), [=] {
+        aggregate_warp_kernel<false, false>(recs, n, t, epoch, ctr, spill, sk, opt);
+    });
+}
 }  // namespace
 
 extern "C" {
@@ -76,6 +84,11 @@ int k1_emul_ingest(void* h, const uint8_t* recs8, uint32_t n, unsigned grid, int
         case 3: run_k1<3>(e, recs, n, grid, opt); break;
         case 4: run_k1<4>(e, recs, n, grid, opt); break;
         case 5: run_k1<5>(e, recs, n, grid, opt); break;
+        case 8: {                                           // K1w, the warp-independent variant
+            const uint32_t n_sub = (n + kWSub - 1) / kWSub;
+            run_k1w(e, recs, n, std::min<unsigned>(grid, (n_sub + kWWarps - 1) / kWWarps), opt);
+            break;
+        }
         default: return -2;
     }
     Table t = e->t; Counters* ctr = e->ctr; FixupScratch* sc = e->scratch; const uint32_t ss = e->scratch_slots;
