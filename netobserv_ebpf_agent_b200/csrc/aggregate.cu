@@ -682,6 +682,76 @@ __device__ __forceinline__ void issue_sub_load(WarpSmem& s, const uint4* recs, u
     tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
 }
 
+// One batch of the pipelined probe passes of K1w: kRounds rounds of 8 flows (4 lanes per flow), all their identity
+// lines in flight together; pass 0 = home slot, pass 1 = next slot for the flows whose home slot holds another
+// settled flow.  Flows that need more (inserts, chains, in-flight publishes) are appended to s.slow.
+template <int kRounds>
+__device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, WarpSmem& s, uint32_t* any_dirty, uint32_t repmask,
+                                              uint32_t nrep, uint32_t base, uint32_t home, uint32_t tmask, uint32_t lt_mask,
+                                              int g4, int j4, uint4 cmaskA, uint4 cmaskB, int rcA, int rcB, uint32_t& nslow) {
+    const uint4* T = s.tile;
+    uint32_t ridx4[kRounds], slot4[kRounds];
+    uint32_t pend4 = 0;
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const uint32_t f = base + r * 8 + g4;
+        const bool act = f < nrep;
+        ridx4[r] = act ? __fns(repmask, 0, (int)f + 1) : 0u;     // the lane that owns the f-th probing record
+        if (act) pend4 |= 1u << r;
+        slot4[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx4[r]);
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        uint4 lineA[kRounds], lineB[kRounds];
+#pragma unroll
+        for (int r = 0; r < kRounds; r++) {
+            lineA[r] = make_uint4(0, 0, 0, 0); lineB[r] = make_uint4(0, 0, 0, 0);
+            if ((pend4 >> r) & 1u) {
+                lineA[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4]);
+                lineB[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4 + 4]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kRounds; r++) {
+            const bool act = (pend4 >> r) & 1u;
+            const uint4* RR = T + ridx4[r] * kRecChunks;
+            bool eqA = eq4_masked(lineA[r], RR[rcA], cmaskA);
+            const bool eqB = eq4_masked(lineB[r], RR[rcB], cmaskB);
+            const uint64_t tag = u64_of(lineA[r].z, lineA[r].w);   // meaningful in lane j4 == 2 only
+            bool settled = false;
+            if (j4 == 2) {
+                settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                          (tag >> TAG_EPOCH_SHIFT) != epoch;
+                eqA = eqA && settled;
+            }
+            const uint32_t eqb = ((__ballot_sync(0xFFFFFFFFu, eqA) >> (g4 * 4)) & 0xFu) |
+                                 (((__ballot_sync(0xFFFFFFFFu, eqB) >> (g4 * 4)) & 0xFu) << 4);
+            const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g4 * 4 + 2)) & 1u;
+            const bool fast = act && (eqb & 0x07u) == 0x07u;       // settled flow, key matches
+            if (fast && j4 == 0) s.res[ridx4[r]] = slot4[r];
+            if (fast && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
+            if (fast && j4 == 2) {
+                s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                if ((eqb & 0xF8u) != 0xF8u) {                       // descriptor differs: ordered re-fold
+                    unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot4[r] * 8 + 2]) + 1;
+                    if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                    *any_dirty = 1;
+                }
+            }
+            const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
+            const bool to_slow = act && !fast && !collide;
+            if (collide) slot4[r] = (slot4[r] + 1) & tmask;
+            else pend4 &= ~(1u << r);
+            const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j4 == 0);
+            if (slowb) {
+                if (to_slow && j4 == 0) s.slow[nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx4[r];
+                nslow += __popc(slowb);
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, pend4 != 0u)) break;
+    }
+}
+
 template <bool kSketch, bool kDevN>
 __global__ void __launch_bounds__(kWWarps * 32, 1)
 aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
@@ -720,6 +790,10 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
         const uint32_t first = sub * kWSub;
         const uint32_t cnt = min((uint32_t)kWSub, n - first);
         mbar_wait(&s.full_bar, it & 1u);
+        if ((opt & 32u) && lane == 0 && sub + sub_stride < n_sub) {     // optional: have L2 fetch the next sub-tile now
+            const uint32_t nf = (sub + sub_stride) * kWSub;
+            tma_prefetch_l2(recs + (size_t)nf * kRecChunks, min((uint32_t)kWSub, n - nf) * kRecBytes);
+        }
 
         // ------------------------------------------------------ hash, cache
         const bool valid = (uint32_t)lane < cnt;
@@ -764,67 +838,13 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
         const uint32_t nrep = (uint32_t)__popc(repmask);
         const uint32_t home = h32 & tmask;
         uint32_t nslow = 0;
-        constexpr int kRounds = 2;
-        for (uint32_t base = 0; base < nrep; base += 8u * kRounds) {
-            uint32_t ridx4[kRounds], slot4[kRounds];
-            uint32_t pend4 = 0;
-#pragma unroll
-            for (int r = 0; r < kRounds; r++) {
-                const uint32_t f = base + r * 8 + g4;
-                const bool act = f < nrep;
-                ridx4[r] = act ? __fns(repmask, 0, (int)f + 1) : 0u;     // the lane that owns the f-th probing record
-                if (act) pend4 |= 1u << r;
-                slot4[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx4[r]);
-            }
-#pragma unroll 1
-            for (int pass = 0; pass < 2; pass++) {
-                uint4 lineA[kRounds], lineB[kRounds];
-#pragma unroll
-                for (int r = 0; r < kRounds; r++) {
-                    lineA[r] = make_uint4(0, 0, 0, 0); lineB[r] = make_uint4(0, 0, 0, 0);
-                    if ((pend4 >> r) & 1u) {
-                        lineA[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4]);
-                        lineB[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4 + 4]);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < kRounds; r++) {
-                    const bool act = (pend4 >> r) & 1u;
-                    const uint4* RR = T + ridx4[r] * kRecChunks;
-                    bool eqA = eq4_masked(lineA[r], RR[rcA], cmaskA);
-                    const bool eqB = eq4_masked(lineB[r], RR[rcB], cmaskB);
-                    const uint64_t tag = u64_of(lineA[r].z, lineA[r].w);   // meaningful in lane j4 == 2 only
-                    bool settled = false;
-                    if (j4 == 2) {
-                        settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
-                                  (tag >> TAG_EPOCH_SHIFT) != epoch;
-                        eqA = eqA && settled;
-                    }
-                    const uint32_t eqb = ((__ballot_sync(0xFFFFFFFFu, eqA) >> (g4 * 4)) & 0xFu) |
-                                         (((__ballot_sync(0xFFFFFFFFu, eqB) >> (g4 * 4)) & 0xFu) << 4);
-                    const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g4 * 4 + 2)) & 1u;
-                    const bool fast = act && (eqb & 0x07u) == 0x07u;       // settled flow, key matches
-                    if (fast && j4 == 0) s.res[ridx4[r]] = slot4[r];
-                    if (fast && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
-                    if (fast && j4 == 2) {
-                        s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
-                        if ((eqb & 0xF8u) != 0xF8u) {                       // descriptor differs: ordered re-fold
-                            unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot4[r] * 8 + 2]) + 1;
-                            if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
-                            cs.any_dirty = 1;
-                        }
-                    }
-                    const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
-                    const bool to_slow = act && !fast && !collide;
-                    if (collide) slot4[r] = (slot4[r] + 1) & tmask;
-                    else pend4 &= ~(1u << r);
-                    const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j4 == 0);
-                    if (slowb) {
-                        if (to_slow && j4 == 0) s.slow[nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx4[r];
-                        nslow += __popc(slowb);
-                    }
-                }
-                if (!__any_sync(0xFFFFFFFFu, pend4 != 0u)) break;
+        for (uint32_t base = 0; base < nrep;) {                   // two rounds in flight while >= 9 flows remain
+            if (nrep - base > 8u) {
+                wprobe_rounds<2>(t, epoch, s, &cs.any_dirty, repmask, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
+                base += 16u;
+            } else {
+                wprobe_rounds<1>(t, epoch, s, &cs.any_dirty, repmask, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
+                base += 8u;
             }
         }
         __syncwarp();
