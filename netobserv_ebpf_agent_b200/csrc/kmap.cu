@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kKmThreads) km_evict_kernel(Table t, uint8_t* 
         km_evict_word_body(t, met, (uint32_t)w, out, cap, cursor);
 }
 
+#ifndef FA_HOST_EMUL
 // One batch: records [0, cut) may create flows, records [cut, n) find the map full.
 int launch_kmap_batch(KmParams P, uint32_t cut, int sm_count, cudaStream_t st) {
     if (!P.n) return 0;
@@ -59,5 +60,6 @@ int launch_kmap_evict(const Table& t, uint8_t* met, uint8_t* out, unsigned long 
     km_evict_kernel<<<sm_count * 8, kKmThreads, 0, st>>>(t, met, out, cap, cursor);
     return 1;
 }
+#endif  // FA_HOST_EMUL
 
 }  // namespace fa

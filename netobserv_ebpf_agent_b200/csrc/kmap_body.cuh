@@ -109,6 +109,27 @@ __device__ __forceinline__ void km_set_lo16(void* word, uint16_t v) {
     atomicAnd(reinterpret_cast<unsigned int*>(word), 0xFFFF0000u);
     atomicOr(reinterpret_cast<unsigned int*>(word), (unsigned int)v);
 }
+#elif defined(FA_HOST_EMUL)
+// SIMT emulation (tests/emul/simt.h): one OS thread per CUDA thread, so these have to be real atomics
+inline uint32_t km_add32(void* p, uint32_t v) { return __atomic_fetch_add(static_cast<uint32_t*>(p), v, __ATOMIC_SEQ_CST); }
+inline unsigned long long km_add64(void* p, unsigned long long v) { return __atomic_fetch_add(static_cast<unsigned long long*>(p), v, __ATOMIC_SEQ_CST); }
+inline void km_or32(void* p, uint32_t v) { __atomic_fetch_or(static_cast<uint32_t*>(p), v, __ATOMIC_SEQ_CST); }
+inline void km_max32(void* p, uint32_t v) {
+    uint32_t* q = static_cast<uint32_t*>(p); uint32_t cur = __atomic_load_n(q, __ATOMIC_SEQ_CST);
+    while (cur < v && !__atomic_compare_exchange_n(q, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+}
+inline uint32_t km_exch32(void* p, uint32_t v) { return __atomic_exchange_n(static_cast<uint32_t*>(p), v, __ATOMIC_SEQ_CST); }
+inline unsigned long long km_cas64(void* p, unsigned long long cmp, unsigned long long v) {
+    __atomic_compare_exchange_n(static_cast<unsigned long long*>(p), &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp;
+}
+inline unsigned long long km_ld_coherent64(const void* p) { return __atomic_load_n(static_cast<const unsigned long long*>(p), __ATOMIC_SEQ_CST); }
+inline uint32_t km_ld_coherent32(const void* p) { return __atomic_load_n(static_cast<const uint32_t*>(p), __ATOMIC_SEQ_CST); }
+inline void km_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void km_publish64(void* p, unsigned long long v) { __atomic_store_n(static_cast<unsigned long long*>(p), v, __ATOMIC_SEQ_CST); }
+inline void km_set_lo16(void* word, uint16_t v) {
+    __atomic_fetch_and(static_cast<uint32_t*>(word), 0xFFFF0000u, __ATOMIC_SEQ_CST);
+    __atomic_fetch_or(static_cast<uint32_t*>(word), (uint32_t)v, __ATOMIC_SEQ_CST);
+}
 #else
 inline uint32_t km_add32(void* p, uint32_t v) { uint32_t* q = static_cast<uint32_t*>(p); uint32_t o = *q; *q = o + v; return o; }
 inline unsigned long long km_add64(void* p, unsigned long long v) { auto* q = static_cast<unsigned long long*>(p); auto o = *q; *q = o + v; return o; }

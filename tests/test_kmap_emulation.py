@@ -4,7 +4,6 @@ result must equal the oracle's sequential map update (bpf/flows.c:76-143,222-288
 records and counters.  The device memory model and the launch plumbing are what tests/test_gpu_kernel_map.py adds."""
 import ctypes
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -12,25 +11,20 @@ import pytest
 import oracle_lib as O
 from common import gen_host
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-BUILD = os.path.join(HERE, "emul", "_build")
-SO = os.path.join(BUILD, "libkmap_emul.so")
-SRC = os.path.join(HERE, "emul", "kmap_emul.cpp")
-BODY = os.path.join(HERE, "..", "netobserv_ebpf_agent_b200", "csrc", "kmap_body.cuh")
-_lib = None
+from emul_build import EMUL, build, csrc
+
+# two ways of running the same kernel bodies on the CPU:
+#   shuffled  one index at a time, every pass in a seeded random order, plain memory operations (kmap_emul.cpp)
+#   simt      csrc/kmap.cu's kernels on tests/emul/simt.h: one OS thread per CUDA thread, real atomics, 3 CTAs at once
+BACKENDS = {"shuffled": "kmap_emul", "simt": "kmap_simt"}
+_libs = {}
 
 
-def emul():
-    global _lib
-    if _lib is not None:
-        return _lib
-    os.makedirs(BUILD, exist_ok=True)
-    newest = max(os.path.getmtime(SRC), os.path.getmtime(BODY), os.path.getmtime(os.path.join(os.path.dirname(BODY), "common.cuh")))
-    if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
-        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + cuda_inc, "-o", SO + ".tmp", SRC], check=True)
-        os.replace(SO + ".tmp", SO)
-    L = ctypes.CDLL(SO)
+def emul(backend="shuffled"):
+    if backend in _libs:
+        return _libs[backend]
+    so = build(BACKENDS[backend], csrc("kmap_body.cuh", "kmap.cu", "common.cuh", "kernels.cuh") + [os.path.join(EMUL, "simt.h")])
+    L = ctypes.CDLL(so)
     L.kmap_emul_new.restype = ctypes.c_void_p
     L.kmap_emul_new.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64]
     L.kmap_emul_free.argtypes = [ctypes.c_void_p]
@@ -42,8 +36,13 @@ def emul():
     L.kmap_emul_spilled.restype = ctypes.c_uint64
     L.kmap_emul_spilled.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
     L.kmap_emul_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-    _lib = L
+    _libs[backend] = L
     return L
+
+
+@pytest.fixture(params=sorted(BACKENDS))
+def backend(request):
+    return request.param
 
 
 def aligned_copy(recs):
@@ -57,8 +56,9 @@ def aligned_copy(recs):
 
 
 class Emul:
-    def __init__(self, max_entries, max_batch, ringbuf=True, spill_cap=1 << 16, seed=1):
-        self.h = emul().kmap_emul_new(max_entries, max_batch, 1 if ringbuf else 0, spill_cap, seed)
+    def __init__(self, max_entries, max_batch, ringbuf=True, spill_cap=1 << 16, seed=1, backend="shuffled"):
+        self.L = emul(backend)
+        self.h = self.L.kmap_emul_new(max_entries, max_batch, 1 if ringbuf else 0, spill_cap, seed)
         self.max_batch = max_batch
 
     def packets(self, recs):
@@ -66,29 +66,29 @@ class Emul:
         n = a.size // O.REC
         for lo in range(0, n, self.max_batch):
             c = min(self.max_batch, n - lo)
-            rc = emul().kmap_emul_batch(self.h, a[lo * O.REC:].ctypes.data, c)
+            rc = self.L.kmap_emul_batch(self.h, a[lo * O.REC:].ctypes.data, c)
             assert rc == 0, f"emulated batch failed: {rc}"
 
     def evict(self):
-        n = emul().kmap_emul_live(self.h)
+        n = self.L.kmap_emul_live(self.h)
         out = np.zeros(max(n, 1) * O.REC, dtype=np.uint8)
-        got = emul().kmap_emul_evict(self.h, out.ctypes.data, n)
+        got = self.L.kmap_emul_evict(self.h, out.ctypes.data, n)
         assert got == n, f"table scan found {got} flows, live counter says {n}"
         return out[: n * O.REC].reshape(-1, O.REC)
 
     def spilled(self, cap=1 << 16):
         out = np.zeros(cap * O.REC, dtype=np.uint8)
-        n = emul().kmap_emul_spilled(self.h, out.ctypes.data, cap)
+        n = self.L.kmap_emul_spilled(self.h, out.ctypes.data, cap)
         return out[: n * O.REC].reshape(-1, O.REC)
 
     def counters(self):
         c = (ctypes.c_uint64 * 6)()
-        emul().kmap_emul_counters(self.h, c)
+        self.L.kmap_emul_counters(self.h, c)
         return dict(intf_missed=c[0], fail_create=c[1], spill_cursor=c[2], spill_dropped=c[3], bset_count=c[4], table_full=c[5])
 
     def close(self):
         if self.h:
-            emul().kmap_emul_free(self.h)
+            self.L.kmap_emul_free(self.h)
             self.h = None
 
     __del__ = close
@@ -124,11 +124,13 @@ def messy_stream(seed, n, n_keys, n_ifaces=4, tls=True, zero_if=True):
     return recs
 
 
-def check(recs, max_entries, max_batch, ringbuf=True, seed=1, evict_every=None):
-    km = O.KernelMap(max_entries, ringbuf_fallback=ringbuf)
-    em = Emul(max_entries, max_batch, ringbuf=ringbuf, seed=seed)
+def check(recs, max_entries, max_batch, ringbuf=True, seed=1, evict_every=None, backend="shuffled"):
     b = O.as_bytes(recs)
     n = b.size // O.REC
+    if backend == "simt":                       # a launch costs ~800 OS threads there: at most 8 batches per stream
+        max_batch = max(max_batch, -(-n // 8))
+    km = O.KernelMap(max_entries, ringbuf_fallback=ringbuf)
+    em = Emul(max_entries, max_batch, ringbuf=ringbuf, seed=seed, backend=backend)
     step = evict_every or n
     for lo in range(0, n, step):
         part = b[lo * O.REC: (lo + step) * O.REC]
@@ -153,38 +155,38 @@ def check(recs, max_entries, max_batch, ringbuf=True, seed=1, evict_every=None):
     assert c["table_full"] == 0 and c["spill_dropped"] == 0
 
 
-def test_generator_stream_single_batch_and_chunked():
+def test_generator_stream_single_batch_and_chunked(backend):
     recs = gen_host(seed=60, n=100_000, n_keys=5_000, dist=1)
-    check(recs, 1 << 16, 100_000)
-    check(recs, 1 << 16, 7_001, seed=2)
+    check(recs, 1 << 16, 100_000, backend=backend)
+    check(recs, 1 << 16, 7_001, seed=2, backend=backend)
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13])
-def test_messy_stream_matches_the_sequential_map_update(seed):
+def test_messy_stream_matches_the_sequential_map_update(seed, backend):
     recs = messy_stream(seed, 60_000, 300)
-    check(recs, 1 << 12, 60_000, seed=seed)            # one batch: everything order-dependent happens inside a launch
-    check(recs, 1 << 12, 997, seed=seed + 100)         # many batches: state carried across launches
+    check(recs, 1 << 12, 60_000, seed=seed, backend=backend)            # one batch: everything order-dependent happens inside a launch
+    check(recs, 1 << 12, 997, seed=seed + 100, backend=backend)         # many batches: state carried across launches
 
 
-def test_many_interfaces_fill_the_observed_list():
+def test_many_interfaces_fill_the_observed_list(backend):
     recs = messy_stream(21, 40_000, 40, n_ifaces=12)
-    check(recs, 1 << 10, 40_000, seed=3)
-    check(recs, 1 << 10, 512, seed=4)
+    check(recs, 1 << 10, 40_000, seed=3, backend=backend)
+    check(recs, 1 << 10, 512, seed=4, backend=backend)
 
 
-def test_single_flow_many_interfaces():
+def test_single_flow_many_interfaces(backend):
     recs = messy_stream(22, 5_000, 1, n_ifaces=30)
-    check(recs, 16, 5_000, seed=5)
-    check(recs, 16, 64, seed=6)
+    check(recs, 16, 5_000, seed=5, backend=backend)
+    check(recs, 16, 64, seed=6, backend=backend)
 
 
-def test_full_map_spills_to_the_ring_buffer_or_counts():
+def test_full_map_spills_to_the_ring_buffer_or_counts(backend):
     recs = messy_stream(31, 30_000, 2_000, tls=False)
-    check(recs, 500, 30_000, ringbuf=True, seed=7)       # cut inside the first batch
-    check(recs, 500, 4_096, ringbuf=True, seed=8)        # map already full when later batches start
-    check(recs, 500, 4_096, ringbuf=False, seed=9)       # HASHMAP_FAIL_CREATE_FLOW instead
+    check(recs, 500, 30_000, ringbuf=True, seed=7, backend=backend)       # cut inside the first batch
+    check(recs, 500, 4_096, ringbuf=True, seed=8, backend=backend)        # map already full when later batches start
+    check(recs, 500, 4_096, ringbuf=False, seed=9, backend=backend)       # HASHMAP_FAIL_CREATE_FLOW instead
 
 
-def test_eviction_between_batches():
+def test_eviction_between_batches(backend):
     recs = messy_stream(41, 50_000, 800)
-    check(recs, 1 << 11, 2_048, seed=10, evict_every=10_000)
+    check(recs, 1 << 11, 2_048, seed=10, evict_every=10_000, backend=backend)
