@@ -664,8 +664,9 @@ struct __align__(128) WarpSmem {                 // 5,120 B per warp
     uint16_t mir_hi[kWSub];                      //    64 B
     uint16_t fseen[kWSub];                       //    64 B
     uint8_t  slow[kWSub];                        //    32 B  lanes whose flow needs the general probe loop
+    uint8_t  list[kWSub];                        //    32 B  the probing lanes, compacted
     unsigned long long full_bar;
-    uint8_t  pad[88];
+    uint8_t  pad[56];
 };
 static_assert(sizeof(WarpSmem) == 5120, "WarpSmem");
 struct __align__(128) AggWSmem {                 // 221,200 B
@@ -686,7 +687,7 @@ __device__ __forceinline__ void issue_sub_load(WarpSmem& s, const uint4* recs, u
 // lines in flight together; pass 0 = home slot, pass 1 = next slot for the flows whose home slot holds another
 // settled flow.  Flows that need more (inserts, chains, in-flight publishes) are appended to s.slow.
 template <int kRounds>
-__device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, WarpSmem& s, uint32_t* any_dirty, uint32_t repmask,
+__device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, WarpSmem& s, uint32_t* any_dirty,
                                               uint32_t nrep, uint32_t base, uint32_t home, uint32_t tmask, uint32_t lt_mask,
                                               int g4, int j4, uint4 cmaskA, uint4 cmaskB, int rcA, int rcB, uint32_t& nslow) {
     const uint4* T = s.tile;
@@ -696,7 +697,7 @@ __device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, Wa
     for (int r = 0; r < kRounds; r++) {
         const uint32_t f = base + r * 8 + g4;
         const bool act = f < nrep;
-        ridx4[r] = act ? __fns(repmask, 0, (int)f + 1) : 0u;     // the lane that owns the f-th probing record
+        ridx4[r] = act ? (uint32_t)s.list[f] : 0u;                // the lane that owns the f-th probing record
         if (act) pend4 |= 1u << r;
         slot4[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx4[r]);
     }
@@ -836,14 +837,16 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
         // ------------------------------------------------------ probe: the warp's own un-cached records
         const uint32_t repmask = __ballot_sync(0xFFFFFFFFu, is_rep);
         const uint32_t nrep = (uint32_t)__popc(repmask);
+        if (is_rep) s.list[__popc(repmask & lt_mask)] = (uint8_t)lane;
+        __syncwarp();
         const uint32_t home = h32 & tmask;
         uint32_t nslow = 0;
         for (uint32_t base = 0; base < nrep;) {                   // two rounds in flight while >= 9 flows remain
             if (nrep - base > 8u) {
-                wprobe_rounds<2>(t, epoch, s, &cs.any_dirty, repmask, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
+                wprobe_rounds<2>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
                 base += 16u;
             } else {
-                wprobe_rounds<1>(t, epoch, s, &cs.any_dirty, repmask, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
+                wprobe_rounds<1>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
                 base += 8u;
             }
         }
