@@ -95,3 +95,16 @@ def test_full_map_spills_to_the_ring_buffer_or_counts():
 def test_eviction_between_batches_and_large_batch():
     check(messy_stream(41, 50_000, 800), 1 << 11, 2_048, evict_every=10_000)
     check(messy_stream(42, 2_000_000, 100_000, n_ifaces=3), 1 << 18, 1 << 20)
+
+
+@needs_kmap
+def test_committed_fixture():
+    import netobserv_ebpf_agent_b200 as fa
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmap", "kmap_messy_seed11.npz"))
+    with fa.FlowAggEngine(int(z["max_entries"]), mode=fa.FA_MODE_KERNEL_MAP, max_batch=8_000, flags=fa.FA_F_RINGBUF_FALLBACK) as eng:
+        eng.ingest(z["records"])
+        assert np.array_equal(O.sort_records(eng.evict()), z["flows"])
+        sp = eng.read_spilled()
+        assert np.array_equal(sp[np.lexsort(sp.T[::-1])], z["spilled"])
+        st = eng.stats()
+    assert [st["observed_intf_missed"], st["hashmap_fail_create"]] == [int(x) for x in z["counters"]]

@@ -190,3 +190,15 @@ def test_full_map_spills_to_the_ring_buffer_or_counts(backend):
 def test_eviction_between_batches(backend):
     recs = messy_stream(41, 50_000, 800)
     check(recs, 1 << 11, 2_048, seed=10, evict_every=10_000, backend=backend)
+
+
+def test_committed_fixture(backend):
+    """tests/golden/kmap/kmap_messy_seed11.npz: full map (300 entries), spills, observed-interface misses."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmap", "kmap_messy_seed11.npz"))
+    em = Emul(int(z["max_entries"]), 8_000, ringbuf=True, backend=backend)
+    em.packets(z["records"])
+    assert np.array_equal(O.sort_records(em.evict()), z["flows"])
+    sp = em.spilled()
+    assert np.array_equal(sp[np.lexsort(sp.T[::-1])], z["spilled"])
+    c = em.counters()
+    assert [c["intf_missed"], c["fail_create"]] == [int(x) for x in z["counters"]]

@@ -89,3 +89,18 @@ def test_full_map_spills_to_ringbuffer_then_accounter():
     km2 = O.KernelMap(1, ringbuf_fallback=False)
     km2.packets(ev(K1, 1, 10, ifindex=1)); km2.packets(ev(K2, 2, 20, ifindex=1))
     assert km2.fail_create == 1 and km2.spilled() == 0                   # HASHMAP_FAIL_CREATE_FLOW (flows.c:285)
+
+
+def test_kernel_map_fixture_is_reproduced():
+    """tests/golden/kmap/kmap_messy_seed11.npz (made by make_kmap_golden.py): stream and oracle output are frozen."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden", "kmap"))
+    from make_kmap_golden import run
+    from test_kmap_emulation import messy_stream
+    z = np.load(os.path.join(here, "golden", "kmap", "kmap_messy_seed11.npz"))
+    assert np.array_equal(messy_stream(11, 8_000, 400, n_ifaces=9), z["records"])
+    flows, spilled, counters = run(z["records"], int(z["max_entries"]))
+    assert np.array_equal(flows, z["flows"]) and np.array_equal(spilled, z["spilled"]) and np.array_equal(counters, z["counters"])
+    assert len(z["flows"]) == 300 and len(z["spilled"]) > 0 and int(z["counters"][0]) > 0      # non-trivial: full map, spills, misses
