@@ -19,6 +19,7 @@ struct Emul {
     FixupScratch* scratch = nullptr; uint32_t scratch_slots = 0;
     uint32_t* spill_idx = nullptr;
     uint64_t max_batch = 0;
+    SketchParams sk{};                       // cms == nullptr: sketches off
 };
 void* zalloc(size_t bytes) {
     void* p = nullptr;
@@ -30,18 +31,24 @@ template <int kVar>
 void run_k1(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt) {
     const uint64_t epoch = e->epoch;
     Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx;
-    SketchParams sk{};
-    simt::launch(grid, kCtaThreads, sizeof(AggSmem), [=] {
-        aggregate_kernel<false, false, false, kVar>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
-    });
+    SketchParams sk = e->sk;
+    if (sk.cms && kVar == 0)
+        simt::launch(grid, kCtaThreads, sizeof(AggSmem), [=] {
+            aggregate_kernel<true, false, false, 0>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
+        });
+    else
+        simt::launch(grid, kCtaThreads, sizeof(AggSmem), [=] {
+            aggregate_kernel<false, false, false, kVar>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
+        });
 }
 void run_k1w(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt) {
     const uint64_t epoch = e->epoch;
     Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx;
-    SketchParams sk{};
-    simt::launch(grid, kWWarps * 32, sizeof(AggWSmem), [=] {
-        aggregate_warp_kernel<false, false>(recs, n, t, epoch, ctr, spill, sk, opt);
-    });
+    SketchParams sk = e->sk;
+    if (sk.cms)
+        simt::launch(grid, kWWarps * 32, sizeof(AggWSmem), [=] { aggregate_warp_kernel<true, false>(recs, n, t, epoch, ctr, spill, sk, opt); });
+    else
+        simt::launch(grid, kWWarps * 32, sizeof(AggWSmem), [=] { aggregate_warp_kernel<false, false>(recs, n, t, epoch, ctr, spill, sk, opt); });
 }
 }  // namespace
 
@@ -101,6 +108,18 @@ int k1_emul_ingest(void* h, const uint8_t* recs8, uint32_t n, unsigned grid, int
     return 0;
 }
 
+// fused count-min + HyperLogLog (variants 0 and 8 only); arrays are owned by the emulation
+void k1_emul_enable_sketch(void* h, uint32_t log2w, uint32_t depth, uint32_t p, uint64_t seed) {
+    Emul* e = static_cast<Emul*>(h);
+    e->sk.log2w = log2w; e->sk.depth = depth; e->sk.p = p; e->sk.seed = seed;
+    e->sk.cms = static_cast<unsigned long long*>(zalloc(((size_t)depth << log2w) * 8));
+    e->sk.hll = static_cast<uint32_t*>(zalloc(((size_t)1 << p) * 4));
+}
+void k1_emul_sketch_export(void* h, uint64_t* cms_out, uint8_t* hll_out) {
+    Emul* e = static_cast<Emul*>(h);
+    memcpy(cms_out, e->sk.cms, ((size_t)e->sk.depth << e->sk.log2w) * 8);
+    for (size_t i = 0; i < ((size_t)1 << e->sk.p); i++) hll_out[i] = (uint8_t)e->sk.hll[i];
+}
 // path counters since the last call: 0 representatives probed, 1 of them through the general loop, 2 cache hits
 void k1_emul_paths(uint64_t out[3]) {
     for (int i = 0; i < 3; i++) { out[i] = simt::g_counts[i]; simt::g_counts[i] = 0; }

@@ -33,6 +33,8 @@ def emul():
         L.k1_emul_counter.restype = ctypes.c_uint64
         L.k1_emul_counter.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.k1_emul_paths.argtypes = [ctypes.c_void_p]
+        L.k1_emul_enable_sketch.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
+        L.k1_emul_sketch_export.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -163,4 +165,26 @@ def test_fast_paths_are_taken(var):
     acc = O.Accounter(1 << 12)
     acc.account(a)
     acc.account(b)
+    same_flows(k1.evict(), acc.evict())
+
+
+@pytest.mark.parametrize("var", [0, 8])
+def test_fused_sketches_match_the_cpu_restatement(var):
+    """count-min += packets and HyperLogLog registers, updated from the fold paths (cache flush included)."""
+    lw, depth, p, seed = 10, 4, 8, 0xC0FFEE
+    recs = gen_host(seed=21, n=12_000, n_keys=700, dist=1)
+    k1 = K1(1 << 12, max_batch=16_384, var=var, grid=2)
+    emul().k1_emul_enable_sketch(k1.h, lw, depth, p, seed)
+    k1.ingest(recs)
+    cms = np.zeros(depth << lw, dtype=np.uint64)
+    hll = np.zeros(1 << p, dtype=np.uint8)
+    emul().k1_emul_sketch_export(k1.h, cms.ctypes.data, hll.ctypes.data)
+    b = O.as_bytes(recs)
+    want_cms = np.zeros(depth << lw, dtype=np.uint64)
+    want_hll = np.zeros(1 << p, dtype=np.uint8)
+    O.lib().oracle_cms_update(want_cms.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), lw, depth, seed, O._p(b), b.size // O.REC)
+    O.lib().oracle_hll_update(O._p(want_hll), p, seed, O._p(b), b.size // O.REC)
+    assert np.array_equal(cms, want_cms) and np.array_equal(hll, want_hll)
+    acc = O.Accounter(1 << 12)
+    acc.account(recs)
     same_flows(k1.evict(), acc.evict())
