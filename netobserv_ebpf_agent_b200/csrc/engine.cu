@@ -412,7 +412,7 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
         CU(cudaMalloc(&e->table.hot, slots * fa::kHotBytes));
         CU(cudaMemsetAsync(e->table.hot, 0, slots * fa::kHotBytes, e->stream));
     } else {
-        if (slots > (1ull << 31)) return fail(FA_E_INVAL, "fa_create: KERNEL_MAP mode supports at most 2^31 slots");
+        if (slots > (1ull << 30)) return fail(FA_E_INVAL, "fa_create: KERNEL_MAP mode supports at most 2^30 slots");
         CU(cudaMalloc(&e->km_met, slots * fa::kMetLineBytes));
         CU(cudaMemsetAsync(e->km_met, 0, slots * fa::kMetLineBytes, e->stream));
         CU(cudaMalloc(&e->km_slot_of, e->max_batch * 4));

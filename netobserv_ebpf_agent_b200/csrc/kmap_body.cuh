@@ -48,7 +48,8 @@ constexpr int KS_BHEAD = 72;       // 1 + index of the newest (flow, ifindex) se
 constexpr int KS_FULLAT = 76;      // 0: list never full in this batch; 1: full before it; i+2: filled by record i
 constexpr int KS_END = 80;
 
-constexpr uint32_t kKmNone = 0xFFFFFFFFu;
+constexpr uint32_t kKmNone = 0xFFFFFFFFu;     // slot_of[i]: the record found no room (spilled / counted)
+constexpr uint32_t kKmBorn = 0x80000000u;     // slot_of[i] bit 31: the record's flow was created in this batch
 
 // (flow, ifindex) scratch set entry
 struct KmBEntry {
@@ -210,11 +211,12 @@ FA_HD void km_resolve_body(const KmParams& P, uint32_t i) {
         probes++;
         if (probes > P.t.mask) km_add64(&P.c->table_full, 1ull);
     }
-    P.slot_of[i] = found;
     if (found != kKmNone) {
+        P.slot_of[i] = found | (born_now ? kKmBorn : 0u);        // slots <= 2^30 (checked by fa_create)
         if (born_now) km_max32(km_ident(P, found) + KS_NFIRST, ~i);
         return;
     }
+    P.slot_of[i] = kKmNone;
     // flows.c:262-286: the insert failed for a reason other than EEXIST
     if (P.ringbuf) {
         const unsigned long long at = km_add64(&P.c->spill_cursor, 1ull);
@@ -230,17 +232,16 @@ FA_HD void km_resolve_body(const KmParams& P, uint32_t i) {
     }
 }
 
-// true when record i created its flow in this batch
-FA_HD bool km_is_creator(const KmParams& P, uint32_t slot, uint32_t i) {
-    const uint8_t* L = km_ident(P, slot);
-    return (km_ld64(L + 40) >> TAG_EPOCH_SHIFT) == P.epoch && km_ld32(L + KS_NFIRST) == ~i;
+// true when record i created its flow in this batch (so = slot_of[i]: only flows born now look at the election)
+FA_HD bool km_is_creator(const KmParams& P, uint32_t so, uint32_t i) {
+    return (so & kKmBorn) && km_ld32(km_ident(P, so & ~kKmBorn) + KS_NFIRST) == ~i;
 }
 
 // ---- init ----------------------------------------------------------------------------------------------------
 FA_HD void km_init_body(const KmParams& P, uint32_t i) {
-    const uint32_t slot = P.slot_of[i];
-    if (slot == kKmNone || !km_is_creator(P, slot, i)) return;
-    uint8_t* M = km_met(P, slot);
+    const uint32_t so = P.slot_of[i];
+    if (so == kKmNone || !km_is_creator(P, so, i)) return;
+    uint8_t* M = km_met(P, so & ~kKmBorn);
     km_new_flow(km_rec(P, i) + kKeyBytes, M, 0);
     km_st64(M + 104, 0ull); km_st64(M + 112, 0ull); km_st64(M + 120, 0ull);
 }
@@ -255,8 +256,9 @@ FA_HD uint32_t km_bhash(uint64_t key, uint32_t mask) { return (uint32_t)(fmix64(
 
 // ---- fold ----------------------------------------------------------------------------------------------------
 FA_HD void km_fold_body(const KmParams& P, uint32_t i) {
-    const uint32_t slot = P.slot_of[i];
-    if (slot == kKmNone || km_is_creator(P, slot, i)) return;
+    const uint32_t so = P.slot_of[i];
+    if (so == kKmNone || km_is_creator(P, so, i)) return;
+    const uint32_t slot = so & ~kKmBorn;
     const uint8_t* ev = km_rec(P, i) + kKeyBytes;
     uint8_t* M = km_met(P, slot);
     uint8_t* L = km_ident(P, slot);
@@ -339,8 +341,9 @@ FA_HD void km_bresolve_body(const KmParams& P, uint32_t j) {
 
 // ---- order ---------------------------------------------------------------------------------------------------
 FA_HD void km_order_body(const KmParams& P, uint32_t i) {
-    const uint32_t slot = P.slot_of[i];
-    if (slot == kKmNone || km_is_creator(P, slot, i)) return;
+    const uint32_t so = P.slot_of[i];
+    if (so == kKmNone || km_is_creator(P, so, i)) return;
+    const uint32_t slot = so & ~kKmBorn;
     const uint8_t* R = km_rec(P, i);
     const uint8_t* ev = R + kKeyBytes;
     uint8_t* M = km_met(P, slot);
@@ -389,9 +392,9 @@ FA_HD void km_order_body(const KmParams& P, uint32_t i) {
 
 // ---- cleanup -------------------------------------------------------------------------------------------------
 FA_HD void km_cleanup_record_body(const KmParams& P, uint32_t i) {
-    const uint32_t slot = P.slot_of[i];
-    if (slot == kKmNone) return;
-    uint8_t* L = km_ident(P, slot);
+    const uint32_t so = P.slot_of[i];
+    if (so == kKmNone) return;
+    uint8_t* L = km_ident(P, so & ~kKmBorn);
     km_st64(L + 48, 0ull); km_st64(L + 56, 0ull); km_st64(L + 64, 0ull); km_st64(L + 72, 0ull);
 }
 FA_HD void km_cleanup_bset_body(const KmParams& P, uint32_t j) {
