@@ -148,7 +148,12 @@ typedef struct fa_additional_record {
 
 enum fa_mode {
     FA_MODE_ACCOUNTER  = 0, /* pkg/flow/account.go + pkg/model/flow_content.go:28-61 */
-    FA_MODE_KERNEL_MAP = 1  /* bpf/flows.c:98-143,222-288 (hit/miss semantics of aggregated_flows) */
+    FA_MODE_KERNEL_MAP = 1  /* bpf/flows.c:76-143,222-288: the map update of flow_monitor (first-seen-interface
+                               de-duplication, last-writer fields, observed-interface list, full map -> ring buffer
+                               or counter).  fa_ingest never returns FA_FULL in this mode; fa_evict is
+                               LookupAndDeleteMap.  Only FA_F_RINGBUF_FALLBACK may be set.  EXPERIMENTAL in this
+                               build: fa_create refuses the mode unless FA_EXPERIMENTAL_KERNEL_MAP=1 is set in the
+                               environment (kernels checked against the oracle in a host emulation, not yet on a GPU) */
 };
 
 typedef struct fa_config {
