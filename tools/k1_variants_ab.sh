@@ -10,7 +10,7 @@ for v in $VARIANTS; do
   echo "== parity FA_K1_OPT=$v"
   FA_K1_OPT=$v timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_golden_fixtures.py -x -q -m gpu 2>&1 | tail -2
 done
-for rep in 1 2; do
+for rep in $(seq 1 ${REPS:-2}); do
   for v in $VARIANTS; do
     echo "== perf FA_K1_OPT=$v (rep $rep)"
     FA_K1_OPT=$v STEPS=${STEPS:-30} bash tools/quick_perf.sh

@@ -1,6 +1,6 @@
 #!/bin/bash
 # quick perf check of K1 on the three workloads (device-resident inputs); prints Mpkts/s + roofline fraction
-for w in zipf1m zipf10m uniform10m; do
+for w in ${WORKLOADS:-zipf1m zipf10m uniform10m}; do
   timeout 300 python bench.py --workload $w --no-cpu --no-e2e --steps ${STEPS:-30} "$@" 2>&1 | python -c "
 import sys,json
 try:
