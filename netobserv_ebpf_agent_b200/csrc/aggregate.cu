@@ -840,6 +840,10 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
         if (is_rep) s.list[__popc(repmask & lt_mask)] = (uint8_t)lane;
         __syncwarp();
         const uint32_t home = h32 & tmask;
+        if ((opt & 64u) && is_rep) {                               // optional: start the table line's trip to L2 now
+            prefetch_l2(&t.ident[(size_t)home * 8]);
+            prefetch_l2(&t.ident[(size_t)home * 8 + 4]);
+        }
         uint32_t nslow = 0;
         for (uint32_t base = 0; base < nrep;) {                   // two rounds in flight while >= 9 flows remain
             if (nrep - base > 8u) {
