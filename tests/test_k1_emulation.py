@@ -188,3 +188,63 @@ def test_fused_sketches_match_the_cpu_restatement(var):
     acc = O.Accounter(1 << 12)
     acc.account(recs)
     same_flows(k1.evict(), acc.evict())
+
+
+@pytest.mark.parametrize("var", [0, 4, 8])
+def test_ragged_sizes_and_single_flow(var):
+    """Partial tiles / sub-tiles (n not a multiple of 32 or 256), one record, and one flow hammered by every thread."""
+    recs = gen_host(seed=13, n=1_000, n_keys=60, dist=1, varying=1)
+    for n in (1, 31, 33, 255, 257, 1_000):
+        k1 = K1(1 << 10, max_batch=4_096, var=var, grid=2)
+        k1.ingest(recs[:n])
+        acc = O.Accounter(1 << 10)
+        acc.account(recs[:n])
+        same_flows(k1.evict(), acc.evict())
+    one = gen_host(seed=14, n=3_000, n_keys=1, dist=0)
+    k1 = K1(1 << 10, max_batch=4_096, var=var, grid=2)
+    k1.ingest(one)
+    acc = O.Accounter(1 << 10)
+    acc.account(one)
+    same_flows(k1.evict(), acc.evict())
+
+
+@pytest.mark.parametrize("var", [0, 4, 8])
+def test_long_collision_chain(var):
+    """Forty flows whose home slot is the same: the probe has to walk a 40-slot chain (pipelined passes give up after
+    one step, the general loop does the rest), concurrently from every warp."""
+    import netobserv_ebpf_agent_b200 as fa
+    cand = gen_host(seed=15, n=60_000, n_keys=60_000, dist=0)
+    keys = np.unique(cand[:, :40], axis=0)
+    mask = 1023                                               # K1(700): 1024 slots
+    home = np.array([fa_slot(k) & mask for k in keys[:30_000]])
+    target = np.bincount(home, minlength=1024).argmax()
+    chain = keys[:30_000][home == target][:40]
+    assert len(chain) >= 20
+    rng = np.random.default_rng(15)
+    recs = cand[:4_000].copy()
+    recs[:, :40] = chain[rng.integers(0, len(chain), len(recs))]
+    k1 = K1(700, max_batch=4_096, var=var, grid=2)
+    K1.paths()
+    k1.ingest(recs[:2_000])
+    K1.paths()
+    k1.ingest(recs[2_000:])                                   # all 40 flows are in the table now
+    reps, slow, _ = K1.paths()
+    assert slow > reps // 2, (reps, slow)                     # the chain really exists: most probes need the general loop
+    acc = O.Accounter(1 << 12)
+    acc.account(recs)
+    same_flows(k1.evict(), acc.evict())
+
+
+def fa_slot(key40):
+    """slot_hash(premix(key)) of the spec, restated here for picking colliding keys."""
+    M = (1 << 64) - 1
+    w = [int.from_bytes(bytes(key40[i * 8:(i + 1) * 8]), "little") for i in range(5)]
+    w[4] &= 0x00FFFFFFFFFFFFFF
+    P1, P2 = 0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F
+    h = 0x243F6A8885A308D3
+    for i, (p, s) in enumerate(((P1, 32), (P2, 29), (P1, 32), (P2, 29), (P1, 32))):
+        h = ((h ^ w[i]) * p) & M
+        h ^= h >> s
+    x = h
+    x ^= x >> 33; x = (x * 0xFF51AFD7ED558CCD) & M; x ^= x >> 33; x = (x * 0xC4CEB9FE1A85EC53) & M; x ^= x >> 33
+    return x
