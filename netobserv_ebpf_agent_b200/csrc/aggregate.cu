@@ -753,7 +753,9 @@ __device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, Wa
     }
 }
 
-template <bool kSketch, bool kDevN>
+// kAgg (experiment, FA_K1_OPT bit 9): lanes of a warp that hit the same cache entry pre-reduce their record
+// (match.any + redux) and one of them issues the shared-memory atomics.
+template <bool kSketch, bool kDevN, bool kAgg = false>
 __global__ void __launch_bounds__(kWWarps * 32, 1)
 aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
                       uint32_t* __restrict__ spill_idx, SketchParams sk, uint32_t opt) {
@@ -800,6 +802,8 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
         const bool valid = (uint32_t)lane < cnt;
         bool is_rep = valid;
         uint32_t h32 = 0;
+        bool hit = false;                                          // kAgg: this lane's record goes into a cache entry
+        uint32_t hb_lo = 0, hb_hi = 0, hpk = 0, hfl = 0, hns = 0, hend = 0;
         const uint4* R = T + lane * kRecChunks;
         if (valid) {
             const uint4 r0 = R[0], r1 = R[1], r2 = R[2];
@@ -820,16 +824,53 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
                 if (same) {
                     is_rep = false;
                     FA_EMUL_COUNT(2, 1);
-                    uint32_t* A = ce.acc;
-                    const uint32_t b_lo = r3.z, b_hi = r3.w;
-                    const uint32_t prev = atomicAdd(&A[0], b_lo);
-                    const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
+                    if (kAgg) {                                    // folded after the warp has re-converged (below)
+                        hit = true;
+                        hb_lo = r3.z; hb_hi = r3.w; hpk = r4.x; hfl = r4.y >> 16;
+                        hns = v_start ? (uint32_t)v_ns : 0u; hend = v_end ? (uint32_t)v_end : 0u;
+                    } else {
+                        uint32_t* A = ce.acc;
+                        const uint32_t b_lo = r3.z, b_hi = r3.w;
+                        const uint32_t prev = atomicAdd(&A[0], b_lo);
+                        const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
+                        if (hi_add) atomicAdd(&A[1], hi_add);
+                        atomicAdd(&A[2], r4.x);
+                        const uint32_t fl = r4.y >> 16;
+                        if (fl & ~A[3]) atomicOr(&A[3], fl);
+                        if (v_start && (uint32_t)v_ns > A[4]) atomicMax(&A[4], (uint32_t)v_ns);
+                        if (v_end && (uint32_t)v_end > A[5]) atomicMax(&A[5], (uint32_t)v_end);
+                    }
+                }
+            }
+        }
+        if (kAgg) {
+            const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, hit);
+            if (hit) {
+                const uint32_t ci = (h32 >> 24) & (kWHot - 1);
+                const uint32_t peers = __match_any_sync(hitmask, ci);      // lanes folding into the same cache entry
+                // 32-bit sums are safe when every peer's byte count is small (32 x 2^26 < 2^32)
+                const bool small = __reduce_or_sync(peers, (hb_hi != 0u || hb_lo >= (1u << 26)) ? 1u : 0u) == 0u;
+                uint32_t* A = cs.hot[ci].acc;
+                if (small) {
+                    const uint32_t sb = __reduce_add_sync(peers, hb_lo), sp = __reduce_add_sync(peers, hpk);
+                    const uint32_t sf = __reduce_or_sync(peers, hfl);
+                    const uint32_t mn = __reduce_max_sync(peers, hns), me = __reduce_max_sync(peers, hend);
+                    if (lane == __ffs(peers) - 1) {
+                        const uint32_t prev = atomicAdd(&A[0], sb);
+                        if ((prev + sb) < prev) atomicAdd(&A[1], 1u);
+                        atomicAdd(&A[2], sp);
+                        if (sf & ~A[3]) atomicOr(&A[3], sf);
+                        if (mn > A[4]) atomicMax(&A[4], mn);
+                        if (me > A[5]) atomicMax(&A[5], me);
+                    }
+                } else {
+                    const uint32_t prev = atomicAdd(&A[0], hb_lo);
+                    const uint32_t hi_add = hb_hi + ((prev + hb_lo) < prev ? 1u : 0u);
                     if (hi_add) atomicAdd(&A[1], hi_add);
-                    atomicAdd(&A[2], r4.x);
-                    const uint32_t fl = r4.y >> 16;
-                    if (fl & ~A[3]) atomicOr(&A[3], fl);
-                    if (v_start && (uint32_t)v_ns > A[4]) atomicMax(&A[4], (uint32_t)v_ns);
-                    if (v_end && (uint32_t)v_end > A[5]) atomicMax(&A[5], (uint32_t)v_end);
+                    atomicAdd(&A[2], hpk);
+                    if (hfl & ~A[3]) atomicOr(&A[3], hfl);
+                    if (hns > A[4]) atomicMax(&A[4], hns);
+                    if (hend > A[5]) atomicMax(&A[5], hend);
                 }
             }
         }
@@ -1084,6 +1125,7 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
             cudaFuncSetAttribute(aggregate_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
             cudaFuncSetAttribute(aggregate_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
             cudaFuncSetAttribute(aggregate_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
+            cudaFuncSetAttribute(aggregate_warp_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
             wattr[dev & 63] = true;
         }
         const uint32_t n_sub = (a.n + kWSub - 1) / kWSub;
@@ -1091,6 +1133,7 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
         if (a.sk.cms && dev_n) aggregate_warp_kernel<true, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else if (a.sk.cms) aggregate_warp_kernel<true, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else if (dev_n) aggregate_warp_kernel<false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
+        else if (a.opt & 512u) aggregate_warp_kernel<false, false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else aggregate_warp_kernel<false, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
     }
     else if (a.sk.cms && dev_n)

@@ -41,6 +41,8 @@ private:
 struct Warp {
     Barrier bar{32};
     unsigned long long v[32];
+    std::mutex sub_mu;                                   // barriers of the lane subsets used by masked collectives
+    std::map<unsigned, std::unique_ptr<Barrier>> sub;
 };
 struct Cta {
     std::unique_ptr<Barrier> sync_all;
@@ -116,6 +118,24 @@ inline void exchange(unsigned long long mine, unsigned long long out[32]) {
     w.bar.wait();
 }
 
+// the lanes of `mask` (every one of them calls this with the same mask) exchange one 64-bit value
+inline void exchange_masked(unsigned mask, unsigned long long mine, unsigned long long out[32]) {
+    if (mask == 0xFFFFFFFFu) { exchange(mine, out); return; }
+    Warp& w = *ctx().warp;
+    if (!((mask >> ctx().lane) & 1u)) abort();
+    Barrier* b;
+    {
+        std::lock_guard<std::mutex> lk(w.sub_mu);
+        auto& slot = w.sub[mask];
+        if (!slot) slot = std::make_unique<Barrier>((unsigned)__builtin_popcount(mask));
+        b = slot.get();
+    }
+    w.v[ctx().lane] = mine;
+    b->wait();
+    for (int l = 0; l < 32; l++) out[l] = ((mask >> l) & 1u) ? w.v[l] : 0ull;
+    b->wait();
+}
+
 }  // namespace simt
 
 // ---------------------------------------------------------------------------------------------- CUDA spellings
@@ -154,9 +174,23 @@ template <typename T> inline T __shfl_up_sync(unsigned mask, T val, unsigned del
     T out; memcpy(&out, &v[src < 0 ? lane : src], sizeof(T)); return out;
 }
 inline unsigned __reduce_add_sync(unsigned mask, unsigned val) {
-    if (mask != 0xFFFFFFFFu) abort();
-    unsigned long long v[32]; simt::exchange(val, v);
-    unsigned r = 0; for (int l = 0; l < 32; l++) r += (unsigned)v[l];
+    unsigned long long v[32]; simt::exchange_masked(mask, val, v);
+    unsigned r = 0; for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) r += (unsigned)v[l];
+    return r;
+}
+inline unsigned __reduce_max_sync(unsigned mask, unsigned val) {
+    unsigned long long v[32]; simt::exchange_masked(mask, val, v);
+    unsigned r = 0; for (int l = 0; l < 32; l++) if (((mask >> l) & 1u) && (unsigned)v[l] > r) r = (unsigned)v[l];
+    return r;
+}
+inline unsigned __reduce_or_sync(unsigned mask, unsigned val) {
+    unsigned long long v[32]; simt::exchange_masked(mask, val, v);
+    unsigned r = 0; for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) r |= (unsigned)v[l];
+    return r;
+}
+inline unsigned __match_any_sync(unsigned mask, unsigned val) {
+    unsigned long long v[32]; simt::exchange_masked(mask, val, v);
+    unsigned r = 0; for (int l = 0; l < 32; l++) if (((mask >> l) & 1u) && (unsigned)v[l] == val) r |= 1u << l;
     return r;
 }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
