@@ -153,6 +153,7 @@ __global__ void dns_first_kernel(const uint8_t* __restrict__ recs, uint32_t n, T
     }
 }
 
+#ifndef FA_HOST_EMUL
 int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& t, uint64_t epoch, uint64_t seq0,
                         uint32_t* slot_of, Counters* ctr, int sm_count, cudaStream_t st) {
     if (!n) return 0;
@@ -166,6 +167,7 @@ int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& 
     }
     return 2;
 }
+#endif  // FA_HOST_EMUL
 
 // ---- eviction: patch the base with the feature effects, emit and clear the feature blocks -----------
 __device__ __forceinline__ void build_base(uint64_t& bs, uint64_t& be, uint32_t& beth, uint64_t nfs, uint64_t fe, uint64_t neth) {
@@ -241,11 +243,13 @@ __global__ void evict_features_kernel(Table t, const uint32_t* __restrict__ slot
     }
 }
 
+#ifndef FA_HOST_EMUL
 int launch_evict_features(const Table& t, const uint32_t* slot_of_out, unsigned long long n_out, uint8_t* out_recs,
                           uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present, int sm_count, cudaStream_t st) {
     if (!n_out) return 0;
     evict_features_kernel<<<sm_count * 8, 256, 0, st>>>(t, slot_of_out, n_out, out_recs, out_dns, out_add, out_present);
     return 1;
 }
+#endif  // FA_HOST_EMUL
 
 }  // namespace fa

@@ -8,6 +8,7 @@
 
 #include "../../netobserv_ebpf_agent_b200/csrc/aggregate.cu"
 #include "../../netobserv_ebpf_agent_b200/csrc/evict.cu"
+#include "../../netobserv_ebpf_agent_b200/csrc/features.cu"
 
 using namespace fa;
 
@@ -20,6 +21,8 @@ struct Emul {
     uint32_t* spill_idx = nullptr;
     uint64_t max_batch = 0;
     SketchParams sk{};                       // cms == nullptr: sketches off
+    uint32_t* slot_of = nullptr;             // feature folds: per-sample slot scratch
+    uint64_t feat_seq[2] = {0, 0};
 };
 void* zalloc(size_t bytes) {
     void* p = nullptr;
@@ -114,6 +117,42 @@ int k1_emul_ingest(void* h, const uint8_t* recs8, uint32_t n, unsigned grid, int
     });
     for (uint32_t i = 0; i < ss; i++) if (sc[i].key) return -3;       // scratch must be clean between launches
     return 0;
+}
+
+// K6 feature folds (kind 0 = additional 72-byte samples, 1 = dns 104-byte samples) and the merged eviction
+void k1_emul_enable_features(void* h) {
+    Emul* e = static_cast<Emul*>(h);
+    e->t.feat_add = static_cast<uint4*>(zalloc(e->slots * 80));
+    e->t.feat_dns = static_cast<uint4*>(zalloc(e->slots * 128));
+    e->slot_of = static_cast<uint32_t*>(zalloc(e->max_batch * 4));
+}
+int k1_emul_ingest_feature(void* h, int kind, const uint8_t* recs, uint32_t n) {
+    Emul* e = static_cast<Emul*>(h);
+    if (!e->slot_of || n == 0 || n > e->max_batch) return -1;
+    Table t = e->t; Counters* ctr = e->ctr; uint32_t* so = e->slot_of;
+    const uint64_t epoch = ++e->epoch, seq0 = e->feat_seq[kind];
+    if (kind == 0) {
+        simt::launch(2, 256, 0, [=] { additional_fold_kernel(recs, n, t, epoch, seq0, so, ctr); });
+        simt::launch(2, 256, 0, [=] { additional_first_kernel(recs, n, t, seq0, so); });
+    } else {
+        simt::launch(2, 256, 0, [=] { dns_fold_kernel(recs, n, t, epoch, seq0, so, ctr); });
+        simt::launch(2, 256, 0, [=] { dns_first_kernel(recs, n, t, seq0, so); });
+    }
+    e->feat_seq[kind] += n;
+    return 0;
+}
+uint64_t k1_emul_evict_features(void* h, uint8_t* out, uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present, uint64_t cap) {
+    Emul* e = static_cast<Emul*>(h);
+    Table t = e->t; Counters* ctr = e->ctr;
+    ctr->evict_out = 0;
+    uint32_t* slot_of_out = static_cast<uint32_t*>(zalloc((cap ? cap : 1) * 4));
+    uint4* o = reinterpret_cast<uint4*>(out);
+    simt::launch(2, 256, 0, [=] { evict_kernel<false>(t, o, slot_of_out, cap, ctr); });
+    const uint64_t n = ctr->evict_out;
+    simt::launch(2, 256, 0, [=] { evict_features_kernel(t, slot_of_out, n, out, out_dns, out_add, out_present); });
+    free(slot_of_out);
+    ctr->live = 0;
+    return n;
 }
 
 // fused count-min + HyperLogLog (variants 0 and 8 only); arrays are owned by the emulation

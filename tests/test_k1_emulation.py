@@ -33,6 +33,10 @@ def emul():
         L.k1_emul_counter.restype = ctypes.c_uint64
         L.k1_emul_counter.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.k1_emul_paths.argtypes = [ctypes.c_void_p]
+        L.k1_emul_enable_features.argtypes = [ctypes.c_void_p]
+        L.k1_emul_ingest_feature.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32]
+        L.k1_emul_evict_features.restype = ctypes.c_uint64
+        L.k1_emul_evict_features.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 4 + [ctypes.c_uint64]
         L.k1_emul_enable_sketch.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
         L.k1_emul_sketch_export.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
@@ -249,3 +253,46 @@ def fa_slot(key40):
     x = h
     x ^= x >> 33; x = (x * 0xFF51AFD7ED558CCD) & M; x ^= x >> 33; x = (x * 0xC4CEB9FE1A85EC53) & M; x ^= x >> 33
     return x
+
+
+def _aligned(b, align=16):
+    b = O.as_bytes(b)
+    raw = np.zeros(b.size + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    a = raw[off: off + b.size]
+    a[:] = b
+    return a
+
+
+@pytest.mark.parametrize("var", [0, 8])
+def test_feature_folds_and_feature_only_flows(var):
+    """K6 (RTT / IPsec / DNS folds, csrc/features.cu) next to K1: flows that exist only through feature samples get a
+    base-less entry which K1 then adopts whole when their first base record arrives (general probe loop), incl. the
+    ordered re-fold; the merged eviction equals the oracle's LookupAndDeleteMap view."""
+    from test_gpu_features import keys_of, make_add, make_dns
+    rng = np.random.default_rng(33)
+    base = gen_host(seed=33, n=9_000, n_keys=300, dist=1, varying=1)
+    keys = np.unique(base[:, :40], axis=0)
+    extra = keys_of(34, 60)                                    # never get a base record
+    allk = np.concatenate([keys, extra])
+    add, dns = make_add(rng, allk, 2_500), make_dns(rng, allk, 2_500)
+    k1 = K1(1 << 11, max_batch=16_384, var=var, grid=2)
+    emul().k1_emul_enable_features(k1.h)
+    om = O.FlowMap()
+    a_add, a_dns = _aligned(add, 8), _aligned(dns, 8)
+    assert emul().k1_emul_ingest_feature(k1.h, 0, a_add.ctypes.data, len(add)) == 0        # features first: base-less entries
+    k1.ingest(base[:5_000])
+    assert emul().k1_emul_ingest_feature(k1.h, 1, a_dns.ctypes.data, len(dns)) == 0
+    k1.ingest(base[5_000:])
+    om.fold_additional(add); om.account(base); om.fold_dns(dns)
+    n = emul().k1_emul_live(k1.h)
+    g_recs = np.zeros((n, O.REC), np.uint8); g_dns = np.zeros((n, O.DNS), np.uint8)
+    g_add = np.zeros((n, O.ADD), np.uint8); g_pres = np.zeros(n, np.uint8)
+    got = emul().k1_emul_evict_features(k1.h, g_recs.ctypes.data, g_dns.ctypes.data, g_add.ctypes.data, g_pres.ctypes.data, n)
+    assert got == n
+    o_recs, o_dns, o_add, o_pres = om.evict()
+    gp, op = O.sort_perm(g_recs), O.sort_perm(o_recs)
+    assert len(gp) == len(op) == len(allk)
+    for name, g, o in (("records", g_recs, o_recs), ("dns", g_dns, o_dns), ("additional", g_add, o_add),
+                       ("present", g_pres.reshape(-1, 1), o_pres.reshape(-1, 1))):
+        assert np.array_equal(g[gp], o[op]), name
