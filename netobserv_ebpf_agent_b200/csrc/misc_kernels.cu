@@ -14,11 +14,13 @@ __global__ void generate_kernel(GenDeviceParams p, uint64_t first_index, uint32_
         for (int c = 0; c < kRecChunks; c++) o[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
     }
 }
+#ifndef FA_HOST_EMUL
 int launch_generate(const GenDeviceParams& g, uint64_t first_index, uint32_t n, uint4* dst, cudaStream_t st) {
     if (!n) return 0;
     generate_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, first_index, n, dst);
     return 1;
 }
+#endif  // FA_HOST_EMUL
 
 // ------------------------------------------------------------------ "full" cut pre-pass
 // Reference pkg/flow/account.go:85-94: the first record whose key is new while the cache
@@ -93,6 +95,7 @@ __global__ void cut_select_kernel(const uint32_t* __restrict__ bitmap, uint32_t 
         *cut_out = cut;
     }
 }
+#ifndef FA_HOST_EMUL
 int launch_full_cut(const uint4* recs, uint32_t n, const Table& table, unsigned long long live,
                     unsigned long long max_entries, uint32_t* idx_set, uint32_t set_slots, uint32_t* bitmap,
                     uint32_t* cut_out, int sm_count, cudaStream_t st) {
@@ -104,6 +107,7 @@ int launch_full_cut(const uint4* recs, uint32_t n, const Table& table, unsigned 
     cut_select_kernel<<<1, 1024, 0, st>>>(bitmap, n, room, cut_out);
     return 3;
 }
+#endif  // FA_HOST_EMUL
 
 // ------------------------------------------------------------------ sketches
 __global__ void cms_query_kernel(SketchParams sk, const uint4* __restrict__ keys, uint32_t n, unsigned long long* est) {
@@ -121,19 +125,23 @@ __global__ void cms_query_kernel(SketchParams sk, const uint4* __restrict__ keys
         est[i] = m;
     }
 }
+#ifndef FA_HOST_EMUL
 int launch_cms_query(const SketchParams& sk, const uint4* keys, uint32_t n, unsigned long long* est, cudaStream_t st) {
     if (!n) return 0;
     cms_query_kernel<<<(n + 255) / 256, 256, 0, st>>>(sk, keys, n, est);
     return 1;
 }
+#endif  // FA_HOST_EMUL
 __global__ void hll_pack_kernel(SketchParams sk, uint8_t* out) {
     const uint32_t m = 1u << sk.p;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) out[i] = (uint8_t)sk.hll[i];
 }
+#ifndef FA_HOST_EMUL
 int launch_hll_pack(const SketchParams& sk, uint8_t* out_regs, cudaStream_t st) {
     hll_pack_kernel<<<64, 256, 0, st>>>(sk, out_regs);
     return 1;
 }
+#endif  // FA_HOST_EMUL
 
 // ------------------------------------------------------------------ K3 route_by_hash
 // owner = owner_hash(key) % n_shards.  Stable counting sort: per-CTA histogram -> exclusive
@@ -307,13 +315,16 @@ __global__ void route_peer_kernel(const uint4* __restrict__ recs, const unsigned
     }
     __threadfence_system();                                               // peer stores visible before the kernel retires
 }
+#ifndef FA_HOST_EMUL
 int launch_route_peer(const uint4* recs, const unsigned long long* n_dev, uint32_t max_n, uint32_t n_shards,
                       const PeerTargets& pt, unsigned long long cap, unsigned long long* overflow, cudaStream_t st) {
     if (!max_n) return 0;
     route_peer_kernel<<<(max_n + kRoutePerCta - 1) / kRoutePerCta, kRouteThreads, 0, st>>>(recs, n_dev, max_n, n_shards, pt, cap, overflow);
     return 1;
 }
+#endif  // FA_HOST_EMUL
 
+#ifndef FA_HOST_EMUL
 int launch_route(const uint4* recs, uint32_t n, uint32_t n_shards, uint4* out, unsigned long long* counts_dev,
                  uint32_t* tmp, int sm_count, cudaStream_t st) {
     if (!n) { cudaMemsetAsync(counts_dev, 0, n_shards * sizeof(unsigned long long), st); return 0; }
@@ -325,5 +336,6 @@ int launch_route(const uint4* recs, uint32_t n, uint32_t n_shards, uint4* out, u
     route_scatter_kernel<<<n_ctas, kRouteThreads, 0, st>>>(recs, n, n_shards, owner, hist, out);
     return 3;
 }
+#endif  // FA_HOST_EMUL
 
 }  // namespace fa

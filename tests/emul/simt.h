@@ -151,6 +151,7 @@ inline void __syncthreads() { simt::ctx().cta->sync_all->wait(); }
 inline void __syncwarp(unsigned = 0xFFFFFFFFu) { simt::ctx().warp->bar.wait(); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline long long clock64() { return 0; }
 
 inline unsigned __ballot_sync(unsigned mask, int pred) {
@@ -207,6 +208,7 @@ inline unsigned __fns(unsigned mask, unsigned base, int offset) {
 // ---- atomics (shared or global: both are plain host memory here) -------------------------------------------
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd_system(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicOr(unsigned long long* p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAnd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }

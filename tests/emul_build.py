@@ -18,8 +18,10 @@ def build(name, deps, flags=()):
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         tmp = so + f".tmp{os.getpid()}"
+        # -Bsymbolic: a library that defines test doubles of CUDA runtime entry points must bind its own calls to them
+        # even when the real libcudart is already loaded in the process
         subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas",
-                        "-I" + cuda_inc, *flags, "-o", tmp, src], check=True)
+                        "-Wl,-Bsymbolic", "-I" + cuda_inc, *flags, "-o", tmp, src], check=True)
         os.replace(tmp, so)
     return so
 

@@ -1,0 +1,77 @@
+"""The whole C ABI on the CPU: csrc/engine.cu compiled unchanged against a test double of the CUDA runtime, with the
+kernels running on tests/emul/simt.h (tests/emul/engine_emul.cpp).  What it checks is HOST logic together with the
+kernels' logic — chunking and staging, the exact "full" cut, KERNEL_MAP plumbing and its fallback ring, feature and
+sketch paths, error codes — through the same ctypes binding and the same helpers as the GPU tests, at sizes where a
+kernel launch (a few hundred to two thousand OS threads) is affordable.  It is test infrastructure: the package's
+loader cannot reach the emulated library (the handle is swapped in here, explicitly), the product has no CPU path,
+and the GPU tests remain the gate for everything the emulation cannot see (memory model, launch geometry, speed)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from common import assert_same_generations, gen_host, gpu_generations, oracle_generations
+from emul_build import EMUL, build, csrc
+
+
+@pytest.fixture(scope="module")
+def engine_emul():
+    import netobserv_ebpf_agent_b200._lib as L
+    so = build("engine_emul", csrc("engine.cu", "aggregate.cu", "evict.cu", "features.cu", "kmap.cu", "kmap_body.cuh",
+                                   "misc_kernels.cu", "common.cuh", "kernels.cuh", "flowgen.h") + [os.path.join(EMUL, "simt.h")])
+    lib = ctypes.CDLL(so)
+    for name, (res, args) in L.SIGNATURES.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, args
+    saved = L._lib
+    L._lib = lib
+    os.environ["FA_EXPERIMENTAL_KERNEL_MAP"] = "1"
+    try:
+        yield lib
+    finally:
+        L._lib = saved
+        os.environ.pop("FA_EXPERIMENTAL_KERNEL_MAP", None)
+
+
+def test_accounter_full_cuts_at_the_exact_record(engine_emul):
+    """maxEntries far below the number of flows: every 'full' generation of the Go Accounter, in order (host staging,
+    asynchronous live count, cut pre-pass, FA_FULL resume)."""
+    recs = gen_host(seed=10, n=300, n_keys=40)
+    want = oracle_generations([recs], 12)
+    got, st = gpu_generations([recs], 12, max_batch=256)
+    assert len(want) > 5
+    assert_same_generations(got, want)
+    assert st["full_cuts"] == len(want) - 1
+
+
+def test_chunked_host_ingest_and_refold(engine_emul):
+    recs = gen_host(seed=7, n=5_000, n_keys=60, dist=1, varying=1)
+    got, st = gpu_generations([recs[:3_000], recs[3_000:]], 1 << 10, max_batch=1_024)
+    assert_same_generations(got, oracle_generations([recs], 1 << 10))
+    assert st["order_fixups"] > 0 and st["records_ingested"] == 5_000 and st["h2d_bytes"] == 5_000 * 144
+
+
+def test_kernel_map_mode_through_the_c_abi(engine_emul):
+    from test_gpu_kernel_map import check
+    from test_kmap_emulation import messy_stream
+    check(messy_stream(51, 2_000, 120, n_ifaces=9), 1 << 9, 1_024)                       # two batches
+    check(messy_stream(52, 2_000, 400, tls=False), 150, 1_024, ringbuf=True)             # full map -> fallback ring
+    check(messy_stream(52, 1_500, 400, tls=False), 150, 1_024, ringbuf=False)            # ... or the counter
+    check(messy_stream(53, 1_600, 100), 1 << 8, 1_024, evict_every=800)
+
+
+def test_error_paths(engine_emul):
+    import netobserv_ebpf_agent_b200 as fa
+    with pytest.raises(fa.FlowAggError) as ei:
+        fa.FlowAggEngine(0)
+    assert ei.value.code == -22
+    with pytest.raises(fa.FlowAggError):
+        fa.FlowAggEngine(100, mode=fa.FA_MODE_KERNEL_MAP, flags=fa.FA_F_ENABLE_DNS)
+    with pytest.raises(fa.FlowAggError):
+        fa.FlowAggEngine(100, flags=fa.FA_F_RINGBUF_FALLBACK)
+    with fa.FlowAggEngine(100) as eng:
+        with pytest.raises(fa.FlowAggError):
+            eng.read_spilled()
+        assert eng.live_flows() == 0 and len(eng.evict()) == 0
