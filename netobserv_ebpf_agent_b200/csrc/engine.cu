@@ -247,8 +247,13 @@ int ingest_chunk_accounter(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint
         *consumed = n;
         return FA_OK;
     }
-    // slow path: find the first record whose key is new while the cache is full
-    e->st.kernel_launches += fa::launch_full_cut(reinterpret_cast<const uint4*>(d_recs), n, e->table, e->live_known, M,
+    // slow path: find the first record whose key is new while the cache is full.  The cut cannot come before `room`
+    // new keys have been seen, so it is looked for inside a window proportional to the room that is left: the pre-pass
+    // work stays linear in the records consumed however small the cache is.  A window without a cut is folded and the
+    // caller goes on with the rest of its chunk.
+    const uint64_t room = M > e->live_known ? M - e->live_known : 0;      // exact: the counters were just read
+    const uint32_t win = (uint32_t)std::min<uint64_t>(n, std::max<uint64_t>(4096, 4 * room));
+    e->st.kernel_launches += fa::launch_full_cut(reinterpret_cast<const uint4*>(d_recs), win, e->table, e->live_known, M,
                                                  e->d_cut_set, e->cut_set_slots, e->d_cut_bitmap, e->d_cut_out,
                                                  e->sm_count, e->stream);
     CU(cudaGetLastError());
@@ -262,7 +267,7 @@ int ingest_chunk_accounter(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint
         if (rc) return rc;
     }
     *consumed = cut;
-    if (cut < n) { e->st.full_cuts++; return FA_FULL; }
+    if (cut < win) { e->st.full_cuts++; return FA_FULL; }
     return FA_OK;
 }
 
@@ -336,10 +341,15 @@ int ingest_host(fa_engine* e, const uint8_t* h_recs, size_t n, size_t* consumed,
         CU(cudaEventRecord(e->ev_copied[sidx], e->copy_stream));
         CU(cudaStreamWaitEvent(e->stream, e->ev_copied[sidx], 0));
         e->st.h2d_bytes += bytes;
-        uint32_t took = 0;
-        rc = ingest_chunk(e, e->d_stage[sidx], c, &took);
+        uint32_t off = 0;                                            // a chunk may be folded in several windows
+        while (off < c) {
+            uint32_t took = 0;
+            rc = ingest_chunk(e, e->d_stage[sidx] + (size_t)off * fa::kRecBytes, c - off, &took);
+            off += took;
+            if (rc != FA_OK) break;
+        }
         CU(cudaEventRecord(e->ev_stage_free[sidx], e->stream));
-        done += took;
+        done += off;
         if (rc != FA_OK) break;
     }
     // the caller's buffer must not be referenced after return

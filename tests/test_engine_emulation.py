@@ -35,17 +35,6 @@ def engine_emul():
         os.environ.pop("FA_EXPERIMENTAL_KERNEL_MAP", None)
 
 
-def test_accounter_full_cuts_at_the_exact_record(engine_emul):
-    """maxEntries far below the number of flows: every 'full' generation of the Go Accounter, in order (host staging,
-    asynchronous live count, cut pre-pass, FA_FULL resume)."""
-    recs = gen_host(seed=10, n=300, n_keys=40)
-    want = oracle_generations([recs], 12)
-    got, st = gpu_generations([recs], 12, max_batch=256)
-    assert len(want) > 5
-    assert_same_generations(got, want)
-    assert st["full_cuts"] == len(want) - 1
-
-
 def test_chunked_host_ingest_and_refold(engine_emul):
     recs = gen_host(seed=7, n=5_000, n_keys=60, dist=1, varying=1)
     got, st = gpu_generations([recs[:3_000], recs[3_000:]], 1 << 10, max_batch=1_024)
@@ -75,3 +64,47 @@ def test_error_paths(engine_emul):
         with pytest.raises(fa.FlowAggError):
             eng.read_spilled()
         assert eng.live_flows() == 0 and len(eng.evict()) == 0
+
+
+def test_small_cache_windows_keep_the_cut_exact_and_the_prepass_linear(engine_emul):
+    """A cache much smaller than the batch (the reference's default is 5000 flows): the cut is searched in windows
+    proportional to the room left, every generation still ends at the exact record, and the number of launches grows
+    with the number of generations, not with generations x batch size."""
+    recs = gen_host(seed=71, n=4_000, n_keys=200, dist=1)
+    want = oracle_generations([recs], 60)
+    got, st = gpu_generations([recs], 60, max_batch=4_000)             # one host chunk, many cuts inside it
+    assert_same_generations(got, want)
+    gens = len(want) - 1
+    assert gens > 8 and st["full_cuts"] == gens
+    # per generation: <= 2 pre-passes (3 kernels each) + 2 folds (3 each) + the eviction; windows without a cut add folds
+    assert st["kernel_launches"] <= 16 * gens + 64, (st["kernel_launches"], gens)
+
+
+def test_device_resident_input_with_cuts(engine_emul):
+    import netobserv_ebpf_agent_b200 as fa
+    recs = gen_host(seed=72, n=1_500, n_keys=120, dist=1)
+    want = oracle_generations([recs], 40)
+    gens = []
+    with fa.FlowAggEngine(40, max_batch=1_024) as eng:
+        p = ctypes.c_void_p()
+        assert engine_emul.fa_device_alloc(eng._h, recs.size, ctypes.byref(p)) == 0
+        ctypes.memmove(p.value, np.ascontiguousarray(recs).ctypes.data, recs.size)
+        done, n = 0, len(recs)
+        while done < n:
+            rc, took = eng.ingest(p.value + done * 144, n - done)
+            done += took
+            if rc == fa.FA_FULL:
+                gens.append(O.sort_records(eng.evict()))
+        gens.append(O.sort_records(eng.evict()))
+        engine_emul.fa_device_free(eng._h, p)
+    assert_same_generations(gens, want)
+
+
+@pytest.mark.parametrize("max_entries,n_keys,n", [(1, 5, 14), (2, 3, 24)])
+def test_degenerate_cache_sizes(engine_emul, max_entries, n_keys, n):
+    """maxEntries 1 and 2 (tests/test_gpu_parity.py::test_full_cut_generations at emulation scale): room 0 / 1 windows."""
+    b = [gen_host(seed=10, n=n, n_keys=n_keys, dist=0, first=i * n) for i in range(2)]
+    got, st = gpu_generations(b, max_entries, max_batch=64)
+    want = oracle_generations(b, max_entries)
+    assert_same_generations(got, want)
+    assert st["full_cuts"] == len(want) - 1 and st["full_cuts"] > 0
