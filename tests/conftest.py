@@ -20,8 +20,32 @@ def _have_gpu():
         return False
 
 
+# FA_EMULATED_GPU=1 (manual, slow, never set by the driver): run the `gpu` tests against the engine emulation
+# (tests/emul/engine_emul.cpp: engine.cu on a CUDA-runtime test double, kernels on the SIMT emulation) — a way to put
+# a kernel variant (FA_K1_OPT=...) through the full parity suite when no GPU is at hand.  Tests that need torch.cuda
+# fail there and are to be deselected (-k "not device_pointer ...").
+_EMULATED = os.environ.get("FA_EMULATED_GPU") == "1"
+
+
+@pytest.fixture(scope="session", autouse=_EMULATED)
+def _emulated_engine():
+    import ctypes
+    import netobserv_ebpf_agent_b200._lib as L
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from emul_build import EMUL, build, csrc
+    so = build("engine_emul", csrc("engine.cu", "aggregate.cu", "evict.cu", "features.cu", "kmap.cu", "kmap_body.cuh",
+                                   "misc_kernels.cu", "common.cuh", "kernels.cuh", "flowgen.h") + [os.path.join(EMUL, "simt.h")])
+    lib = ctypes.CDLL(so)
+    for name, (res, args) in L.SIGNATURES.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, args
+    saved, L._lib = L._lib, lib
+    yield lib
+    L._lib = saved
+
+
 def pytest_collection_modifyitems(config, items):
-    if _have_gpu():
+    if _have_gpu() or _EMULATED:
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:

@@ -97,6 +97,36 @@ def kmap_bench(n_keys=1_000_000, B=1 << 24, steps=12):
     eng.close()
 
 
+def small_cache_bench(max_entries=5000, n_keys=1_000_000, B=1 << 22, steps=3):
+    """The reference's default CACHE_MAX_FLOWS (5000) against a stream with far more concurrent flows: every few
+    thousand records the cache is 'full' (account.go:85-94) -> exact cut, eviction, resume.  Throughput of that loop
+    with device-resident input and a device-resident eviction buffer (small caches)."""
+    eng = fa.FlowAggEngine(max_entries, max_batch=B, cuda_stream=stream.cuda_stream)
+    gp = fa.GenParams(seed=2, n_keys=n_keys, dist=1, zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0)
+    src = torch.empty(B * REC, dtype=torch.uint8, device=dev)
+    eng.gen_records(gp, 0, B, src)
+    out = torch.empty(max_entries * REC, dtype=torch.uint8, device=dev)
+    eng.sync()
+    gens = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        done = 0
+        while done < B:
+            rc, took = eng.ingest(src.data_ptr() + done * REC, B - done)
+            done += took
+            if rc == fa.FA_FULL:
+                eng.evict_into(out.data_ptr(), max_entries)
+                gens += 1
+    eng.evict_into(out.data_ptr(), max_entries)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = eng.stats()
+    print(json.dumps({"bench": "ACCOUNTER with a small cache", "max_entries": max_entries, "workload": f"{n_keys} Zipf-1.1 keys",
+                      "Mpkts_s": B * steps / dt / 1e6, "generations": gens, "records_per_generation": B * steps / max(gens, 1),
+                      "kernel_launches": st["kernel_launches"]}), flush=True)
+    eng.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sketch", "features"] + (["kmap"] if os.environ.get("FA_EXPERIMENTAL_KERNEL_MAP") == "1" else [])
     if "sketch" in which:
@@ -105,3 +135,5 @@ if __name__ == "__main__":
         feature_bench()
     if "kmap" in which:
         kmap_bench()
+    if "smallcache" in which:
+        small_cache_bench()
