@@ -676,11 +676,12 @@ struct __align__(128) AggWSmem {                 // 221,200 B
     uint32_t n_insert, n_spill, any_dirty, pad;
 };
 
-__device__ __forceinline__ void issue_sub_load(WarpSmem& s, const uint4* recs, uint32_t n, uint32_t sub) {
+__device__ __forceinline__ void issue_sub_load(WarpSmem& s, const uint4* recs, uint32_t n, uint32_t sub, bool evict_first) {
     const uint32_t first = sub * kWSub;
     const uint32_t bytes = min((uint32_t)kWSub, n - first) * kRecBytes;
     mbar_expect_tx(&s.full_bar, bytes);
-    tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
+    if (evict_first) tma_load_1d_stream(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
+    else tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
 }
 
 // One batch of the pipelined probe passes of K1w: kRounds rounds of 8 flows (4 lanes per flow), all their identity
@@ -774,7 +775,8 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
     cs.last[threadIdx.x] = 0u;
     if (lane == 0) { mbar_init(&s.full_bar, 1); fence_barrier_init(); }
     __syncthreads();
-    if (lane == 0 && sub0 < n_sub) issue_sub_load(s, recs, n, sub0);
+    const bool stream_hint = (opt & 1024u) != 0;                 // optional: L2 evict-first for the record stream
+    if (lane == 0 && sub0 < n_sub) issue_sub_load(s, recs, n, sub0, stream_hint);
 
     const int g = lane >> 3, j = lane & 7;                       // 8-lane groups of the general probe loop
     const uint4 cmask = chunk_mask(j);
@@ -954,7 +956,7 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
         __syncwarp();                                              // nobody reads the sub-tile buffer any more
         if (lane == 0) {
             const uint32_t nx = sub + sub_stride;
-            if (nx < n_sub) { fence_proxy_async(); issue_sub_load(s, recs, n, nx); }
+            if (nx < n_sub) { fence_proxy_async(); issue_sub_load(s, recs, n, nx, stream_hint); }
         }
     }
 

@@ -166,6 +166,15 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Same copy with an L2 evict-first policy: the record stream is read once, the table lines it would push out of L2 are
+// read again and again (SASS: UBLKCP with a cache-hint operand).
+__device__ __forceinline__ void tma_load_1d_stream(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 // Ask L2 to fetch a byte range (SASS: UBLKPF); used to run the HBM read of the next tiles ahead of
 // the shared-memory staging of the current one.
 __device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {

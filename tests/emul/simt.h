@@ -252,6 +252,7 @@ inline void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, un
     memcpy(smem_dst, gmem_src, bytes);
     __atomic_fetch_xor(bar, 1ull, __ATOMIC_SEQ_CST);
 }
+inline void tma_load_1d_stream(void* d, const void* s, uint32_t bytes, unsigned long long* bar) { tma_load_1d(d, s, bytes, bar); }
 inline void tma_prefetch_l2(const void*, uint32_t) {}
 inline void prefetch_l2(const void*) {}
 inline uint4 ld_cg_u4(const uint4* p) {                       // two 8-byte halves: a 16-byte line chunk may tear here
