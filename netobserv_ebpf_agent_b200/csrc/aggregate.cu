@@ -692,12 +692,15 @@ __device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, Wa
                                               uint32_t nrep, uint32_t base, uint32_t home, uint32_t tmask, uint32_t lt_mask,
                                               int g4, int j4, uint4 cmaskA, uint4 cmaskB, int rcA, int rcB, uint32_t& nslow) {
     const uint4* T = s.tile;
-    uint32_t ridx4[kRounds], slot4[kRounds];
+    uint32_t ridx4[kRounds], slot4[kRounds], actm[kRounds];
     uint32_t pend4 = 0;
 #pragma unroll
     for (int r = 0; r < kRounds; r++) {
         const uint32_t f = base + r * 8 + g4;
         const bool act = f < nrep;
+        // lanes of the groups that hold a flow in this round: 8 flows = all 32 lanes, fewer in the last round
+        const uint32_t nfl = nrep - base > (uint32_t)r * 8u ? min(8u, nrep - base - (uint32_t)r * 8u) : 0u;
+        actm[r] = nfl >= 8u ? 0xFFFFFFFFu : ((1u << (nfl * 4u)) - 1u);
         ridx4[r] = act ? (uint32_t)s.list[f] : 0u;                // the lane that owns the f-th probing record
         if (act) pend4 |= 1u << r;
         slot4[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx4[r]);
@@ -725,6 +728,15 @@ __device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, Wa
                 settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
                           (tag >> TAG_EPOCH_SHIFT) != epoch;
                 eqA = eqA && settled;
+            }
+            // common case first: every flow of the round is settled and matches in all 8 chunks -> one vote
+            const uint32_t okm = __ballot_sync(0xFFFFFFFFu, eqA && eqB);
+            if ((okm | ~actm[r]) == 0xFFFFFFFFu) {
+                if (act && j4 == 0) s.res[ridx4[r]] = slot4[r];
+                if (act && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
+                if (act && j4 == 2) s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                pend4 &= ~(1u << r);
+                continue;
             }
             const uint32_t eqb = ((__ballot_sync(0xFFFFFFFFu, eqA) >> (g4 * 4)) & 0xFu) |
                                  (((__ballot_sync(0xFFFFFFFFu, eqB) >> (g4 * 4)) & 0xFu) << 4);
