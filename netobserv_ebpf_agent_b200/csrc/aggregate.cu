@@ -429,6 +429,18 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                                       (tag >> TAG_EPOCH_SHIFT) != epoch;
                             eqA = eqA && settled;
                         }
+                        // common case first: every flow of the round is settled, matches in all 8 chunks and has no
+                        // tile-local descriptor conflict -> one vote
+                        const bool clean = j4 != 2 || s.tdirty[ridx4[r]] == 0;
+                        const uint32_t okm = __ballot_sync(0xFFFFFFFFu, eqA && eqB && clean);
+                        const uint32_t actm = __ballot_sync(0xFFFFFFFFu, act);
+                        if ((okm | ~actm) == 0xFFFFFFFFu) {
+                            if (act && j4 == 0) s.res[ridx4[r]] = slot4[r];
+                            if (act && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
+                            if (act && j4 == 2) s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                            pend4 &= ~(1u << r);
+                            continue;
+                        }
                         const uint32_t eqb = ((__ballot_sync(0xFFFFFFFFu, eqA) >> (g4 * 4)) & 0xFu) |
                                              (((__ballot_sync(0xFFFFFFFFu, eqB) >> (g4 * 4)) & 0xFu) << 4);
                         const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g4 * 4 + 2)) & 1u;
