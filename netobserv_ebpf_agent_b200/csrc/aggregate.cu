@@ -778,9 +778,83 @@ __device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, Wa
     }
 }
 
+// The same batch with 8 lanes per flow (one lane per 16-byte line chunk, one L1 wavefront per line instead of two):
+// kRounds rounds of 4 flows.  Costs twice the instructions per flow of wprobe_rounds; FA_K1_OPT bit 11 selects it.
+template <int kRounds>
+__device__ __forceinline__ void wprobe_rounds8(const Table& t, uint64_t epoch, WarpSmem& s, uint32_t* any_dirty,
+                                               uint32_t nrep, uint32_t base, uint32_t home, uint32_t tmask, uint32_t lt_mask,
+                                               int g, int j, uint4 cmask, int rc, uint32_t& nslow) {
+    const uint4* T = s.tile;
+    uint32_t ridx[kRounds], slot[kRounds], actm[kRounds];
+    uint32_t pend = 0;
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const uint32_t f = base + r * 4 + g;
+        const bool act = f < nrep;
+        const uint32_t nfl = nrep - base > (uint32_t)r * 4u ? min(4u, nrep - base - (uint32_t)r * 4u) : 0u;
+        actm[r] = nfl >= 4u ? 0xFFFFFFFFu : ((1u << (nfl * 8u)) - 1u);
+        ridx[r] = act ? (uint32_t)s.list[f] : 0u;
+        if (act) pend |= 1u << r;
+        slot[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx[r]);
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        uint4 line[kRounds];
+#pragma unroll
+        for (int r = 0; r < kRounds; r++) {
+            line[r] = make_uint4(0, 0, 0, 0);
+            if ((pend >> r) & 1u) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
+        }
+#pragma unroll
+        for (int r = 0; r < kRounds; r++) {
+            const bool act = (pend >> r) & 1u;
+            bool eq = eq4_masked(line[r], T[ridx[r] * kRecChunks + rc], cmask);
+            const uint64_t tag = u64_of(line[r].z, line[r].w);      // meaningful in lane j == 2 only
+            bool settled = false;
+            if (j == 2) {
+                settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                          (tag >> TAG_EPOCH_SHIFT) != epoch;
+                eq = eq && settled;
+            }
+            const uint32_t eqm = __ballot_sync(0xFFFFFFFFu, eq);
+            if ((eqm | ~actm[r]) == 0xFFFFFFFFu) {                  // every flow of the round: settled, all 8 chunks equal
+                if (act && j == 0) s.res[ridx[r]] = slot[r];
+                if (act && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
+                if (act && j == 2) s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                pend &= ~(1u << r);
+                continue;
+            }
+            const uint32_t eqb = (eqm >> (g * 8)) & 0xFFu;
+            const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g * 8 + 2)) & 1u;
+            const bool fast = act && (eqb & 0x07u) == 0x07u;
+            if (fast && j == 0) s.res[ridx[r]] = slot[r];
+            if (fast && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
+            if (fast && j == 2) {
+                s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                if ((eqb & 0xF8u) != 0xF8u) {
+                    unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
+                    if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                    *any_dirty = 1;
+                }
+            }
+            const bool collide = act && !fast && gsettled && pass == 0;
+            const bool to_slow = act && !fast && !collide;
+            if (collide) slot[r] = (slot[r] + 1) & tmask;
+            else pend &= ~(1u << r);
+            const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j == 0);
+            if (slowb) {
+                if (to_slow && j == 0) s.slow[nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx[r];
+                nslow += __popc(slowb);
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, pend != 0u)) break;
+    }
+}
+
 // kAgg (experiment, FA_K1_OPT bit 9): lanes of a warp that hit the same cache entry pre-reduce their record
 // (match.any + redux) and one of them issues the shared-memory atomics.
-template <bool kSketch, bool kDevN, bool kAgg = false>
+// kLanes8 (experiment, FA_K1_OPT bit 11): 8 lanes per flow in the pipelined probe passes (wprobe_rounds8).
+template <bool kSketch, bool kDevN, bool kAgg = false, bool kLanes8 = false>
 __global__ void __launch_bounds__(kWWarps * 32, 1)
 aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
                       uint32_t* __restrict__ spill_idx, SketchParams sk, uint32_t opt) {
@@ -912,6 +986,20 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
             prefetch_l2(&t.ident[(size_t)home * 8 + 4]);
         }
         uint32_t nslow = 0;
+        if (kLanes8) {                                             // 8 lanes per flow: 4 flows per round
+            for (uint32_t base = 0; base < nrep;) {
+                if (nrep - base > 8u) {
+                    wprobe_rounds8<4>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
+                    base += 16u;
+                } else if (nrep - base > 4u) {
+                    wprobe_rounds8<2>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
+                    base += 8u;
+                } else {
+                    wprobe_rounds8<1>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
+                    base += 4u;
+                }
+            }
+        } else
         for (uint32_t base = 0; base < nrep;) {                   // two rounds in flight while >= 9 flows remain
             if (nrep - base > 8u) {
                 wprobe_rounds<2>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
@@ -1152,6 +1240,7 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
             cudaFuncSetAttribute(aggregate_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
             cudaFuncSetAttribute(aggregate_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
             cudaFuncSetAttribute(aggregate_warp_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
+            cudaFuncSetAttribute(aggregate_warp_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
             wattr[dev & 63] = true;
         }
         const uint32_t n_sub = (a.n + kWSub - 1) / kWSub;
@@ -1159,6 +1248,7 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
         if (a.sk.cms && dev_n) aggregate_warp_kernel<true, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else if (a.sk.cms) aggregate_warp_kernel<true, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else if (dev_n) aggregate_warp_kernel<false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
+        else if (a.opt & 2048u) aggregate_warp_kernel<false, false, false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else if (a.opt & 512u) aggregate_warp_kernel<false, false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else aggregate_warp_kernel<false, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
     }
