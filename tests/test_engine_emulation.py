@@ -15,6 +15,9 @@ import oracle_lib as O
 from common import assert_same_generations, gen_host, gpu_generations, oracle_generations
 from emul_build import EMUL, build, csrc
 
+# a wedged emulation (it is thousands of OS threads) must not hang the suite: pytest-timeout, if installed
+pytestmark = pytest.mark.timeout(900)
+
 
 @pytest.fixture(scope="module")
 def engine_emul():

@@ -12,6 +12,9 @@ import pytest
 import oracle_lib as O
 from common import gen_host
 from emul_build import build, csrc
+
+# a wedged emulation (it is thousands of OS threads) must not hang the suite: pytest-timeout, if installed
+pytestmark = pytest.mark.timeout(900)
 from test_kmap_emulation import aligned_copy
 
 _lib = None

@@ -13,6 +13,9 @@ from common import gen_host
 
 from emul_build import EMUL, build, csrc
 
+# a wedged emulation (it is thousands of OS threads) must not hang the suite: pytest-timeout, if installed
+pytestmark = pytest.mark.timeout(900)
+
 # two ways of running the same kernel bodies on the CPU:
 #   shuffled  one index at a time, every pass in a seeded random order, plain memory operations (kmap_emul.cpp)
 #   simt      csrc/kmap.cu's kernels on tests/emul/simt.h: one OS thread per CUDA thread, real atomics, 3 CTAs at once
