@@ -18,3 +18,8 @@ timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench_default.json 2> $
 echo "== 6. ncu: launch list + full capture of K1w"
 FA_K1_OPT=256 timeout 600 ncu --set full --clock-control none --import-source on -k regex:aggregate_warp_kernel -s 3 -c 1 -o $OUT/prof_k1w -f \
     python bench.py --steps 4 --warmup 2 --no-cpu --no-e2e > $OUT/ncu_k1w.log 2>&1; tail -2 $OUT/ncu_k1w.log
+echo "== 7. ncu: fused-sketch K1 and the feature folds (SURVEY 8d asks for K4/K5/K6 captures too)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:aggregate_kernel -s 3 -c 1 -o $OUT/prof_k1_sketch -f \
+    python tools/bench_aux.py sketch > $OUT/ncu_sketch.log 2>&1; tail -1 $OUT/ncu_sketch.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'dns_fold_kernel|additional_fold_kernel' -c 2 -o $OUT/prof_k6 -f \
+    python tools/bench_aux.py features > $OUT/ncu_k6.log 2>&1; tail -1 $OUT/ncu_k6.log
