@@ -710,9 +710,7 @@ __device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, Wa
     for (int r = 0; r < kRounds; r++) {
         const uint32_t f = base + r * 8 + g4;
         const bool act = f < nrep;
-        // lanes of the groups that hold a flow in this round: 8 flows = all 32 lanes, fewer in the last round
-        const uint32_t nfl = nrep - base > (uint32_t)r * 8u ? min(8u, nrep - base - (uint32_t)r * 8u) : 0u;
-        actm[r] = nfl >= 8u ? 0xFFFFFFFFu : ((1u << (nfl * 4u)) - 1u);
+        actm[r] = __ballot_sync(0xFFFFFFFFu, act);                // lanes of the groups that hold a flow in this round
         ridx4[r] = act ? (uint32_t)s.list[f] : 0u;                // the lane that owns the f-th probing record
         if (act) pend4 |= 1u << r;
         slot4[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx4[r]);
@@ -791,8 +789,7 @@ __device__ __forceinline__ void wprobe_rounds8(const Table& t, uint64_t epoch, W
     for (int r = 0; r < kRounds; r++) {
         const uint32_t f = base + r * 4 + g;
         const bool act = f < nrep;
-        const uint32_t nfl = nrep - base > (uint32_t)r * 4u ? min(4u, nrep - base - (uint32_t)r * 4u) : 0u;
-        actm[r] = nfl >= 4u ? 0xFFFFFFFFu : ((1u << (nfl * 8u)) - 1u);
+        actm[r] = __ballot_sync(0xFFFFFFFFu, act);
         ridx[r] = act ? (uint32_t)s.list[f] : 0u;
         if (act) pend |= 1u << r;
         slot[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx[r]);
