@@ -153,6 +153,8 @@ struct fa_engine {
     uint32_t* km_slot_of = nullptr;
     fa::KmBEntry* km_bset = nullptr; uint32_t km_bset_slots = 0;
     uint32_t* km_blist = nullptr;
+    uint32_t *km_touched = nullptr, *km_deferred = nullptr, *km_brec = nullptr;   // v2 work lists
+    int km_impl = 2;                          // FA_KMAP_IMPL: 1 = seven per-record passes, 2 = per-flow finalisation
     uint8_t* km_spill = nullptr; uint64_t km_spill_cap = 0;
     fa::KmCounters* d_km_ctr = nullptr;
     fa::KmCounters* h_km_ctr = nullptr;       // pinned mirror
@@ -163,6 +165,7 @@ struct fa_engine {
 
 namespace fa {
 int launch_kmap_batch(KmParams P, uint32_t cut, int sm_count, cudaStream_t st);
+int launch_kmap_batch_v2(KmParams P, uint32_t cut, int sm_count, cudaStream_t st);
 int launch_kmap_evict(const Table& t, uint8_t* met, uint8_t* out, unsigned long long cap, unsigned long long* cursor,
                       int sm_count, cudaStream_t st);
 }
@@ -303,7 +306,9 @@ int ingest_chunk_kmap(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint32_t*
     P.c = e->d_km_ctr;
     P.spill = e->km_spill; P.spill_cap = e->km_spill_cap;
     P.bset = e->km_bset; P.bset_mask = e->km_bset_slots - 1; P.blist = e->km_blist;
-    e->st.kernel_launches += fa::launch_kmap_batch(P, cut, e->sm_count, e->stream);
+    P.touched = e->km_touched; P.deferred = e->km_deferred; P.brec = e->km_brec;
+    e->st.kernel_launches += e->km_impl == 1 ? fa::launch_kmap_batch(P, cut, e->sm_count, e->stream)
+                                             : fa::launch_kmap_batch_v2(P, cut, e->sm_count, e->stream);
     CU(cudaGetLastError());
     *consumed = n;
     return note_launch(e, n);
@@ -431,6 +436,10 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
         CU(cudaMalloc(&e->km_bset, (size_t)bs * sizeof(fa::KmBEntry)));
         CU(cudaMemsetAsync(e->km_bset, 0, (size_t)bs * sizeof(fa::KmBEntry), e->stream));
         CU(cudaMalloc(&e->km_blist, e->max_batch * 4));
+        CU(cudaMalloc(&e->km_touched, e->max_batch * 4));
+        CU(cudaMalloc(&e->km_deferred, e->max_batch * 4));
+        CU(cudaMalloc(&e->km_brec, e->max_batch * 4));
+        if (const char* ki = getenv("FA_KMAP_IMPL")) e->km_impl = ki[0] == '1' ? 1 : 2;
         if (cfg->flags & FA_F_RINGBUF_FALLBACK) {
             e->km_spill_cap = 131072;                   // >= the 16 MiB direct_flows ring (bpf/maps_definition.h:7-11)
             CU(cudaMalloc(&e->km_spill, e->km_spill_cap * fa::kRecBytes));
@@ -538,6 +547,7 @@ void fa_destroy(fa_engine* e) {
     cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out); cudaFree(e->d_slot_of);
     cudaFree(e->sk.cms); cudaFree(e->sk.hll);
     cudaFree(e->km_met); cudaFree(e->km_slot_of); cudaFree(e->km_bset); cudaFree(e->km_blist); cudaFree(e->km_spill);
+    cudaFree(e->km_touched); cudaFree(e->km_deferred); cudaFree(e->km_brec);
     cudaFree(e->d_km_ctr); if (e->h_km_ctr) cudaFreeHost(e->h_km_ctr);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;

@@ -47,6 +47,11 @@ constexpr int KS_NFIRST_VER = 68;  // max ~i over A records with a TLS version
 constexpr int KS_BHEAD = 72;       // 1 + index of the newest (flow, ifindex) set entry of this flow
 constexpr int KS_FULLAT = 76;      // 0: list never full in this batch; 1: full before it; i+2: filled by record i
 constexpr int KS_END = 80;
+// v2 only (per-flow finalisation): TLS versions seen on class A records, so that the mismatch flag needs no second
+// look at the records
+constexpr int KS_HVMAX = 80;       // max version
+constexpr int KS_NHVMIN = 84;      // max ~version (low 16 bits) | 0x10000 -> min version; 0 = none seen
+constexpr int KS_END2 = 88;
 
 constexpr uint32_t kKmNone = 0xFFFFFFFFu;     // slot_of[i]: the record found no room (spilled / counted)
 constexpr uint32_t kKmBorn = 0x80000000u;     // slot_of[i] bit 31: the record's flow was created in this batch
@@ -68,6 +73,10 @@ struct KmCounters {
     unsigned long long spill_dropped;    // ... that found the ring buffer full
     unsigned long long bset_count;       // (flow, ifindex) entries created in this batch
     unsigned long long table_full;       // records that found the table physically full (sizing error)
+    // v2: per-batch work lists
+    unsigned long long touched_count;    // flows that received class A / B records or were created in this batch
+    unsigned long long deferred_count;   // records of flows created in this batch (folded after their creator is known)
+    unsigned long long brec_count;       // class B records (direction merge / missed counter after bresolve)
 };
 
 struct KmParams {
@@ -84,6 +93,7 @@ struct KmParams {
     KmCounters* c;
     uint8_t* spill; unsigned long long spill_cap;
     KmBEntry* bset; uint32_t bset_mask; uint32_t* blist;
+    uint32_t* touched; uint32_t* deferred; uint32_t* brec;      // v2 work lists, n entries each
 };
 
 // ---- memory helpers ------------------------------------------------------------------------------------------
@@ -99,6 +109,7 @@ __device__ __forceinline__ uint32_t km_add32(void* p, uint32_t v) { return atomi
 __device__ __forceinline__ unsigned long long km_add64(void* p, unsigned long long v) { return atomicAdd(reinterpret_cast<unsigned long long*>(p), v); }
 __device__ __forceinline__ void km_or32(void* p, uint32_t v) { atomicOr(reinterpret_cast<unsigned int*>(p), v); }
 __device__ __forceinline__ void km_max32(void* p, uint32_t v) { atomicMax(reinterpret_cast<unsigned int*>(p), v); }
+__device__ __forceinline__ uint32_t km_max32_ret(void* p, uint32_t v) { return atomicMax(reinterpret_cast<unsigned int*>(p), v); }
 __device__ __forceinline__ uint32_t km_exch32(void* p, uint32_t v) { return atomicExch(reinterpret_cast<unsigned int*>(p), v); }
 __device__ __forceinline__ unsigned long long km_cas64(void* p, unsigned long long cmp, unsigned long long v) { return atomicCAS(reinterpret_cast<unsigned long long*>(p), cmp, v); }
 __device__ __forceinline__ unsigned long long km_ld_coherent64(const void* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
@@ -119,6 +130,11 @@ inline void km_max32(void* p, uint32_t v) {
     uint32_t* q = static_cast<uint32_t*>(p); uint32_t cur = __atomic_load_n(q, __ATOMIC_SEQ_CST);
     while (cur < v && !__atomic_compare_exchange_n(q, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
 }
+inline uint32_t km_max32_ret(void* p, uint32_t v) {
+    uint32_t* q = static_cast<uint32_t*>(p); uint32_t cur = __atomic_load_n(q, __ATOMIC_SEQ_CST);
+    while (cur < v && !__atomic_compare_exchange_n(q, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return cur;
+}
 inline uint32_t km_exch32(void* p, uint32_t v) { return __atomic_exchange_n(static_cast<uint32_t*>(p), v, __ATOMIC_SEQ_CST); }
 inline unsigned long long km_cas64(void* p, unsigned long long cmp, unsigned long long v) {
     __atomic_compare_exchange_n(static_cast<unsigned long long*>(p), &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp;
@@ -136,6 +152,7 @@ inline uint32_t km_add32(void* p, uint32_t v) { uint32_t* q = static_cast<uint32
 inline unsigned long long km_add64(void* p, unsigned long long v) { auto* q = static_cast<unsigned long long*>(p); auto o = *q; *q = o + v; return o; }
 inline void km_or32(void* p, uint32_t v) { *static_cast<uint32_t*>(p) |= v; }
 inline void km_max32(void* p, uint32_t v) { uint32_t* q = static_cast<uint32_t*>(p); if (*q < v) *q = v; }
+inline uint32_t km_max32_ret(void* p, uint32_t v) { uint32_t* q = static_cast<uint32_t*>(p); uint32_t o = *q; if (o < v) *q = v; return o; }
 inline uint32_t km_exch32(void* p, uint32_t v) { uint32_t* q = static_cast<uint32_t*>(p); uint32_t o = *q; *q = v; return o; }
 inline unsigned long long km_cas64(void* p, unsigned long long cmp, unsigned long long v) { auto* q = static_cast<unsigned long long*>(p); auto o = *q; if (o == cmp) *q = v; return o; }
 inline unsigned long long km_ld_coherent64(const void* p) { return *static_cast<const unsigned long long*>(p); }
@@ -400,6 +417,142 @@ FA_HD void km_cleanup_record_body(const KmParams& P, uint32_t i) {
 FA_HD void km_cleanup_bset_body(const KmParams& P, uint32_t j) {
     KmBEntry* e = &P.bset[P.blist[j]];
     e->key = 0ull; e->nfirst = 0u; e->next = 0u; e->kind = 0u; e->pos = 0u;
+}
+
+// ================================================================================================================
+// v2: the same decomposition with the per-record passes cut down to one.  Flows that existed before the batch know
+// their first-seen interface already, so their records are classified and folded inside `resolve`; what is
+// order-dependent is finished per FLOW (one thread per touched flow gathers the winning records by index) instead of
+// per record.  Only the records of flows created in this batch (the creator is not known until all of them have been
+// seen) and class B records (they need the result of bresolve) are revisited, through compact lists.
+//   resolve+fold [records] -> init, fold [deferred records] -> bresolve [new (flow, ifindex)] -> order B [B records]
+//   -> finish [touched flows] -> cleanup of the (flow, ifindex) set
+// ================================================================================================================
+
+// classify record i of an existing flow against its first-seen interface and fold the commutative parts
+FA_HD void km2_fold_record(const KmParams& P, uint32_t slot, uint32_t i, bool list_touch) {
+    const uint8_t* ev = km_rec(P, i) + kKeyBytes;
+    uint8_t* M = km_met(P, slot);
+    uint8_t* L = km_ident(P, slot);
+    const uint32_t ifindex = km_ld32(ev + KM_IFINDEX);
+    const int cls = km_class(M, ifindex);
+    if (cls == 0) return;
+    const uint32_t flags = km_ld16(ev + KM_FLAGS);
+    if (flags) km_or32(M + KM_ETH, flags << 16);
+    const uint32_t before = km_max32_ret(L + KS_LAST_AB, i + 1);
+    if (list_touch && before == 0u) P.touched[km_add64(&P.c->touched_count, 1ull)] = slot;     // first A/B record of the flow
+    if (cls == 1) {
+        km_add32(M + KM_PACKETS, 1u);
+        km_add64(M + KM_BYTES, km_ld64(ev + KM_BYTES));
+        km_max32(L + KS_LAST_A, i + 1);
+        const uint32_t ty = ev[KM_TLSTYPES];
+        if (ty) km_or32(M + KM_KEYSHARE, ty << 16);
+        if (ty == 0x02) {                                   // SERVER_HELLO (flows.c:119-124)
+            if (km_ld16(ev + KM_CIPHER) > 0) km_max32(L + KS_LAST_CIPHER, i + 1);
+            if (km_ld16(ev + KM_KEYSHARE) > 0) km_max32(L + KS_LAST_KEYSHARE, i + 1);
+        }
+        const uint32_t hv = km_ld16(ev + KM_SSLVER);
+        if (hv > 0) {
+            km_max32(L + KS_NFIRST_VER, ~i);
+            km_max32(L + KS_HVMAX, hv);
+            km_max32(L + KS_NHVMIN, 0x10000u | (~hv & 0xFFFFu));
+        }
+        return;
+    }
+    // class B: remember (flow, ifindex) with the first index it was seen at, and the record for the direction pass
+    P.brec[km_add64(&P.c->brec_count, 1ull)] = i;
+    const uint64_t key = km_bkey(slot, ifindex);
+    uint32_t s = km_bhash(key, P.bset_mask);
+    for (;;) {
+        KmBEntry* e = &P.bset[s];
+        unsigned long long cur = km_ld_coherent64(&e->key);
+        if (cur == 0ull) {
+            cur = km_cas64(&e->key, 0ull, key);
+            if (cur == 0ull) {
+                e->next = km_exch32(L + KS_BHEAD, s + 1);
+                P.blist[km_add64(&P.c->bset_count, 1ull)] = s;
+                cur = key;
+            }
+        }
+        if (cur == key) { km_max32(&e->nfirst, ~i); return; }
+        s = (s + 1) & P.bset_mask;
+    }
+}
+
+FA_HD void km2_resolve_fold_body(const KmParams& P, uint32_t i) {
+    km_resolve_body(P, i);
+    const uint32_t so = P.slot_of[i];
+    if (so == kKmNone) return;
+    if (so & kKmBorn) { P.deferred[km_add64(&P.c->deferred_count, 1ull)] = i; return; }   // creator not known yet
+    km2_fold_record(P, so, i, true);
+}
+FA_HD void km2_init_body(const KmParams& P, uint32_t k) {
+    const uint32_t i = P.deferred[k];
+    const uint32_t so = P.slot_of[i];
+    if (!km_is_creator(P, so, i)) return;
+    const uint32_t slot = so & ~kKmBorn;
+    uint8_t* M = km_met(P, slot);
+    km_new_flow(km_rec(P, i) + kKeyBytes, M, 0);
+    km_st64(M + 104, 0ull); km_st64(M + 112, 0ull); km_st64(M + 120, 0ull);
+    P.touched[km_add64(&P.c->touched_count, 1ull)] = slot;      // every flow created in this batch is finished below
+}
+FA_HD void km2_fold_deferred_body(const KmParams& P, uint32_t k) {
+    const uint32_t i = P.deferred[k];
+    const uint32_t so = P.slot_of[i];
+    if (km_is_creator(P, so, i)) return;
+    km2_fold_record(P, so & ~kKmBorn, i, false);
+}
+// class B record after bresolve (flows.c:126-142): missed counter or direction merge
+FA_HD void km2_order_b_body(const KmParams& P, uint32_t k) {
+    const uint32_t i = P.brec[k];
+    const uint32_t slot = P.slot_of[i] & ~kKmBorn;
+    const uint8_t* R = km_rec(P, i);
+    const uint8_t* ev = R + kKeyBytes;
+    uint8_t* M = km_met(P, slot);
+    const uint8_t* L = km_ident(P, slot);
+    const uint32_t full_at = km_ld32(L + KS_FULLAT);
+    if (full_at != 0 && i + 2u > full_at) {
+        if (R[36] != 0) km_add64(&P.c->intf_missed, 1ull);
+        return;
+    }
+    const uint64_t key = km_bkey(slot, km_ld32(ev + KM_IFINDEX));
+    uint32_t s = km_bhash(key, P.bset_mask);
+    while (P.bset[s].key != key) s = (s + 1) & P.bset_mask;
+    const KmBEntry* e = &P.bset[s];
+    if (e->kind == 2 && (uint32_t)~e->nfirst == i) return;
+    if (e->kind == 0) return;
+    volatile uint8_t* dirp = M + KM_OBSDIR + e->pos;
+    const uint8_t cur = *dirp, d = ev[KM_DIR];
+    if (cur != d && cur != 3) *dirp = 3;
+}
+// one thread per touched flow: the order-dependent fields from the records that won, then the scratch back to zero
+FA_HD void km2_finish_flow_body(const KmParams& P, uint32_t k) {
+    const uint32_t slot = P.touched[k];
+    uint8_t* M = km_met(P, slot);
+    uint8_t* L = km_ident(P, slot);
+    const uint32_t last_ab = km_ld32(L + KS_LAST_AB), last_a = km_ld32(L + KS_LAST_A);
+    if (last_ab) km_st64(M + KM_END, km_ld64(km_rec(P, last_ab - 1) + kKeyBytes + KM_START));       // last writer
+    if (last_a) {
+        const uint8_t* ev = km_rec(P, last_a - 1) + kKeyBytes;
+        M[KM_DSCP] = ev[KM_DSCP];
+        km_st32(M + KM_SAMPLING, km_ld32(ev + KM_SAMPLING));
+    }
+    const uint32_t lc = km_ld32(L + KS_LAST_CIPHER), lk = km_ld32(L + KS_LAST_KEYSHARE);
+    if (lc) km_st16(M + KM_CIPHER, km_ld16(km_rec(P, lc - 1) + kKeyBytes + KM_CIPHER));
+    if (lk) km_st16(M + KM_KEYSHARE, km_ld16(km_rec(P, lk - 1) + kKeyBytes + KM_KEYSHARE));
+    const uint32_t hvmax = km_ld32(L + KS_HVMAX);
+    if (hvmax) {                                                       // flows.c:111-118 over all class A records
+        const uint32_t hvmin = ~km_ld32(L + KS_NHVMIN) & 0xFFFFu;
+        const uint32_t v0 = km_ld16(M + KM_SSLVER);
+        if (v0 == 0) {                                                 // first record with a version sets it ...
+            const uint32_t first_ver = ~km_ld32(L + KS_NFIRST_VER);
+            km_st16(M + KM_SSLVER, km_ld16(km_rec(P, first_ver) + kKeyBytes + KM_SSLVER));
+            if (hvmax != hvmin) M[KM_MISC] |= 0x01;                    // ... any other value afterwards is a mismatch
+        } else if (hvmax != v0 || hvmin != v0) {
+            M[KM_MISC] |= 0x01;
+        }
+    }
+    km_st64(L + 48, 0ull); km_st64(L + 56, 0ull); km_st64(L + 64, 0ull); km_st64(L + 72, 0ull); km_st64(L + 80, 0ull);
 }
 
 // ---- evict: one call per occupancy word (32 slots) -------------------------------------------------------------

@@ -234,6 +234,21 @@ int launch_kmap_batch(KmParams P, uint32_t cut, int, cudaStream_t) {
     simt::launch(1, 32, 0, [=] { if (threadIdx.x == 0) km_reset_bset_count_kernel(c); });
     return launches + 6;
 }
+int launch_kmap_batch_v2(KmParams P, uint32_t cut, int, cudaStream_t) {
+    if (!P.n) return 0;
+    int launches = 0;
+    if (cut > 0) { KmParams Q = P; Q.lo = 0; Q.hi = cut; Q.allow_insert = 1; simt::launch(3, 256, 0, [=] { km2_resolve_fold_kernel(Q); }); launches++; }
+    if (cut < P.n) { KmParams Q = P; Q.lo = cut; Q.hi = P.n; Q.allow_insert = 0; simt::launch(3, 256, 0, [=] { km2_resolve_fold_kernel(Q); }); launches++; }
+    simt::launch(3, 256, 0, [=] { km2_init_kernel(P); });
+    simt::launch(3, 256, 0, [=] { km2_fold_deferred_kernel(P); });
+    simt::launch(3, 256, 0, [=] { km_bresolve_kernel(P); });
+    simt::launch(3, 256, 0, [=] { km2_order_b_kernel(P); });
+    simt::launch(3, 256, 0, [=] { km2_finish_kernel(P); });
+    simt::launch(3, 256, 0, [=] { km2_cleanup_kernel(P); });
+    KmCounters* c = P.c;
+    simt::launch(1, 32, 0, [=] { if (threadIdx.x == 0) km2_reset_counts_kernel(c); });
+    return launches + 7;
+}
 int launch_kmap_evict(const Table& table, uint8_t* met, uint8_t* out, unsigned long long cap, unsigned long long* cursor, int, cudaStream_t) {
     Table t = table;
     simt::launch(3, 256, 0, [=] { km_evict_kernel(t, met, out, cap, cursor); });

@@ -21,7 +21,8 @@ struct Emul {
     uint64_t max_entries, slots;
     int ringbuf;
     std::vector<uint8_t> ident, met, spill;
-    std::vector<uint32_t> occ, slot_of, blist;
+    std::vector<uint32_t> occ, slot_of, blist, touched, deferred, brec;
+    int impl = 1;
     std::vector<KmBEntry> bset;
     KmCounters c{};
     unsigned long long live = 0;
@@ -50,12 +51,14 @@ void* kmap_emul_new(uint64_t max_entries, uint64_t max_batch, int ringbuf, uint6
     e->ident.assign(slots * kIdentBytes + 64, 0); e->met.assign(slots * kMetLineBytes + 64, 0);
     e->occ.assign(slots / 32, 0);
     e->slot_of.assign(max_batch, 0); e->blist.assign(max_batch, 0);
+    e->touched.assign(max_batch, 0); e->deferred.assign(max_batch, 0); e->brec.assign(max_batch, 0);
     uint64_t bs = 1024; while (bs < 2 * max_batch) bs <<= 1;
     e->bset.assign(bs, KmBEntry{});
     e->spill.assign(spill_cap * kRecBytes + 64, 0);
     return e;
 }
 void kmap_emul_free(void* h) { delete static_cast<Emul*>(h); }
+void kmap_emul_set_impl(void* h, int impl) { static_cast<Emul*>(h)->impl = impl; }
 
 // one batch (n <= max_batch); recs must be 16-byte aligned
 int kmap_emul_batch(void* h, const uint8_t* recs, uint32_t n) {
@@ -83,7 +86,27 @@ int kmap_emul_batch(void* h, const uint8_t* recs, uint32_t n) {
     P.spill = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(e->spill.data()) + 15) & ~uintptr_t(15));
     P.spill_cap = (e->spill.size() - 64) / kRecBytes;
     P.bset = e->bset.data(); P.bset_mask = (uint32_t)e->bset.size() - 1; P.blist = e->blist.data();
+    P.touched = e->touched.data(); P.deferred = e->deferred.data(); P.brec = e->brec.data();
     std::vector<uint32_t> order;
+    if (e->impl == 2) {
+        if (cut > 0) { P.lo = 0; P.hi = cut; P.allow_insert = 1; shuffled(order, 0, cut, e->rng); for (uint32_t i : order) km2_resolve_fold_body(P, i); }
+        if (cut < n) { P.lo = cut; P.hi = n; P.allow_insert = 0; shuffled(order, cut, n, e->rng); for (uint32_t i : order) km2_resolve_fold_body(P, i); }
+        const uint32_t nd = (uint32_t)e->c.deferred_count;
+        shuffled(order, 0, nd, e->rng); for (uint32_t k : order) km2_init_body(P, k);
+        shuffled(order, 0, nd, e->rng); for (uint32_t k : order) km2_fold_deferred_body(P, k);
+        const uint32_t m2 = (uint32_t)e->c.bset_count;
+        shuffled(order, 0, m2, e->rng); for (uint32_t j : order) km_bresolve_body(P, j);
+        shuffled(order, 0, (uint32_t)e->c.brec_count, e->rng); for (uint32_t k : order) km2_order_b_body(P, k);
+        shuffled(order, 0, (uint32_t)e->c.touched_count, e->rng); for (uint32_t k : order) km2_finish_flow_body(P, k);
+        shuffled(order, 0, m2, e->rng); for (uint32_t j : order) km_cleanup_bset_body(P, j);
+        e->c.bset_count = 0; e->c.touched_count = 0; e->c.deferred_count = 0; e->c.brec_count = 0;
+        for (auto& b : e->bset) if (b.key || b.nfirst || b.next || b.kind || b.pos) return -2;
+        // every flow's scratch must be zero again
+        const uint8_t* id = reinterpret_cast<const uint8_t*>(P.t.ident);
+        for (uint64_t sl = 0; sl < e->slots; sl++)
+            for (int b = 48; b < 96; b++) if (id[sl * kIdentBytes + b]) return -3;
+        return 0;
+    }
     if (cut > 0) { P.lo = 0; P.hi = cut; P.allow_insert = 1; shuffled(order, 0, cut, e->rng); for (uint32_t i : order) km_resolve_body(P, i); }
     if (cut < n) { P.lo = cut; P.hi = n; P.allow_insert = 0; shuffled(order, cut, n, e->rng); for (uint32_t i : order) km_resolve_body(P, i); }
     shuffled(order, 0, n, e->rng); for (uint32_t i : order) km_init_body(P, i);

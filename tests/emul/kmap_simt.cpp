@@ -16,7 +16,8 @@ using namespace fa;
 namespace {
 struct Emul {
     uint64_t max_entries, slots; int ringbuf;
-    uint8_t *ident, *met, *spill; uint32_t *occ, *slot_of, *blist; KmBEntry* bset; uint32_t bset_slots;
+    uint8_t *ident, *met, *spill; uint32_t *occ, *slot_of, *blist, *touched, *deferred, *brec; KmBEntry* bset; uint32_t bset_slots;
+    int impl = 1;
     KmCounters* c; unsigned long long* live; uint64_t epoch = 0, spill_cap; size_t max_batch;
     std::unordered_set<std::string> keys;
 };
@@ -27,6 +28,7 @@ KmParams params(Emul* e) {
     P.t.ident = reinterpret_cast<uint4*>(e->ident); P.t.occ = e->occ; P.t.mask = e->slots - 1;
     P.met = e->met; P.slot_of = e->slot_of; P.live = e->live; P.c = e->c;
     P.spill = e->spill; P.spill_cap = e->spill_cap; P.bset = e->bset; P.bset_mask = e->bset_slots - 1; P.blist = e->blist;
+    P.touched = e->touched; P.deferred = e->deferred; P.brec = e->brec;
     return P;
 }
 constexpr unsigned kGrid = 3, kBlock = 256;
@@ -43,6 +45,8 @@ void* kmap_emul_new(uint64_t max_entries, uint64_t max_batch, int ringbuf, uint6
     e->ident = static_cast<uint8_t*>(zalloc(slots * kIdentBytes)); e->met = static_cast<uint8_t*>(zalloc(slots * kMetLineBytes));
     e->occ = static_cast<uint32_t*>(zalloc(slots / 8));
     e->slot_of = static_cast<uint32_t*>(zalloc(max_batch * 4)); e->blist = static_cast<uint32_t*>(zalloc(max_batch * 4));
+    e->touched = static_cast<uint32_t*>(zalloc(max_batch * 4)); e->deferred = static_cast<uint32_t*>(zalloc(max_batch * 4));
+    e->brec = static_cast<uint32_t*>(zalloc(max_batch * 4));
     uint32_t bs = 1024; while ((uint64_t)bs < 2 * max_batch) bs <<= 1;
     e->bset_slots = bs; e->bset = static_cast<KmBEntry*>(zalloc((size_t)bs * sizeof(KmBEntry)));
     e->spill = static_cast<uint8_t*>(zalloc(spill_cap * kRecBytes));
@@ -53,8 +57,10 @@ void* kmap_emul_new(uint64_t max_entries, uint64_t max_batch, int ringbuf, uint6
 void kmap_emul_free(void* h) {
     Emul* e = static_cast<Emul*>(h);
     free(e->ident); free(e->met); free(e->occ); free(e->slot_of); free(e->blist); free(e->bset); free(e->spill); free(e->c); free(e->live);
+    free(e->touched); free(e->deferred); free(e->brec);
     delete e;
 }
+void kmap_emul_set_impl(void* h, int impl) { static_cast<Emul*>(h)->impl = impl; }
 int kmap_emul_batch(void* h, const uint8_t* recs, uint32_t n) {
     Emul* e = static_cast<Emul*>(h);
     if (n > e->max_batch) return -1;
@@ -72,6 +78,22 @@ int kmap_emul_batch(void* h, const uint8_t* recs, uint32_t n) {
     }
     KmParams P = params(e);
     P.recs = recs; P.n = n; P.epoch = ++e->epoch;
+    if (e->impl == 2) {
+        if (cut > 0) { KmParams Q = P; Q.lo = 0; Q.hi = cut; Q.allow_insert = 1; simt::launch(kGrid, kBlock, 0, [=] { km2_resolve_fold_kernel(Q); }); }
+        if (cut < n) { KmParams Q = P; Q.lo = cut; Q.hi = n; Q.allow_insert = 0; simt::launch(kGrid, kBlock, 0, [=] { km2_resolve_fold_kernel(Q); }); }
+        simt::launch(kGrid, kBlock, 0, [=] { km2_init_kernel(P); });
+        simt::launch(kGrid, kBlock, 0, [=] { km2_fold_deferred_kernel(P); });
+        simt::launch(kGrid, kBlock, 0, [=] { km_bresolve_kernel(P); });
+        simt::launch(kGrid, kBlock, 0, [=] { km2_order_b_kernel(P); });
+        simt::launch(kGrid, kBlock, 0, [=] { km2_finish_kernel(P); });
+        simt::launch(kGrid, kBlock, 0, [=] { km2_cleanup_kernel(P); });
+        KmCounters* c2 = e->c;
+        simt::launch(1, 32, 0, [=] { if (threadIdx.x == 0) km2_reset_counts_kernel(c2); });
+        for (uint32_t i = 0; i < e->bset_slots; i++) if (e->bset[i].key || e->bset[i].nfirst || e->bset[i].next || e->bset[i].kind) return -2;
+        for (uint64_t sl = 0; sl < e->slots; sl++)
+            for (int b = 48; b < 96; b++) if (e->ident[sl * kIdentBytes + b]) return -3;
+        return 0;
+    }
     if (cut > 0) { KmParams Q = P; Q.lo = 0; Q.hi = cut; Q.allow_insert = 1; simt::launch(kGrid, kBlock, 0, [=] { km_resolve_kernel(Q); }); }
     if (cut < n) { KmParams Q = P; Q.lo = cut; Q.hi = n; Q.allow_insert = 0; simt::launch(kGrid, kBlock, 0, [=] { km_resolve_kernel(Q); }); }
     simt::launch(kGrid, kBlock, 0, [=] { km_init_kernel(P); });

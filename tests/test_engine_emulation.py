@@ -45,9 +45,12 @@ def test_chunked_host_ingest_and_refold(engine_emul):
     assert st["order_fixups"] > 0 and st["records_ingested"] == 5_000 and st["h2d_bytes"] == 5_000 * 144
 
 
-def test_kernel_map_mode_through_the_c_abi(engine_emul):
+@pytest.mark.parametrize("impl", ["1", "2"])
+def test_kernel_map_mode_through_the_c_abi(engine_emul, monkeypatch, impl):
+    """Both implementations of the map update (FA_KMAP_IMPL: 1 = seven per-record passes, 2 = per-flow finalisation)."""
     from test_gpu_kernel_map import check
     from test_kmap_emulation import messy_stream
+    monkeypatch.setenv("FA_KMAP_IMPL", impl)
     check(messy_stream(51, 2_000, 120, n_ifaces=9), 1 << 9, 1_024)                       # two batches
     check(messy_stream(52, 2_000, 400, tls=False), 150, 1_024, ringbuf=True)             # full map -> fallback ring
     check(messy_stream(52, 1_500, 400, tls=False), 150, 1_024, ringbuf=False)            # ... or the counter

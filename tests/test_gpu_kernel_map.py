@@ -28,6 +28,13 @@ def test_kernel_map_mode_is_refused_loudly_unless_asked_for():
     assert ei.value.code == -22 and "KERNEL_MAP" in str(ei.value)       # no silent fallback to ACCOUNTER semantics
 
 
+@pytest.fixture(params=["2", "1"], autouse=True)
+def kmap_impl(request, monkeypatch):
+    """FA_KMAP_IMPL: 2 = one streaming pass + per-flow finalisation (default), 1 = seven per-record passes."""
+    monkeypatch.setenv("FA_KMAP_IMPL", request.param)
+    return request.param
+
+
 def check(recs, max_entries, max_batch, ringbuf=True, evict_every=None):
     import netobserv_ebpf_agent_b200 as fa
     km = O.KernelMap(max_entries, ringbuf_fallback=ringbuf)

@@ -19,7 +19,8 @@ pytestmark = pytest.mark.timeout(900)
 # two ways of running the same kernel bodies on the CPU:
 #   shuffled  one index at a time, every pass in a seeded random order, plain memory operations (kmap_emul.cpp)
 #   simt      csrc/kmap.cu's kernels on tests/emul/simt.h: one OS thread per CUDA thread, real atomics, 3 CTAs at once
-BACKENDS = {"shuffled": "kmap_emul", "simt": "kmap_simt"}
+#   ...-v2    the per-flow finalisation variant (km2_* bodies / kernels) on the same two runners
+BACKENDS = {"shuffled": "kmap_emul", "simt": "kmap_simt", "shuffled-v2": "kmap_emul", "simt-v2": "kmap_simt"}
 _libs = {}
 
 
@@ -39,6 +40,7 @@ def emul(backend="shuffled"):
     L.kmap_emul_spilled.restype = ctypes.c_uint64
     L.kmap_emul_spilled.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
     L.kmap_emul_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.kmap_emul_set_impl.argtypes = [ctypes.c_void_p, ctypes.c_int]
     _libs[backend] = L
     return L
 
@@ -62,6 +64,7 @@ class Emul:
     def __init__(self, max_entries, max_batch, ringbuf=True, spill_cap=1 << 16, seed=1, backend="shuffled"):
         self.L = emul(backend)
         self.h = self.L.kmap_emul_new(max_entries, max_batch, 1 if ringbuf else 0, spill_cap, seed)
+        self.L.kmap_emul_set_impl(self.h, 2 if backend.endswith("-v2") else 1)
         self.max_batch = max_batch
 
     def packets(self, recs):
@@ -130,7 +133,7 @@ def messy_stream(seed, n, n_keys, n_ifaces=4, tls=True, zero_if=True):
 def check(recs, max_entries, max_batch, ringbuf=True, seed=1, evict_every=None, backend="shuffled"):
     b = O.as_bytes(recs)
     n = b.size // O.REC
-    if backend == "simt":                       # a launch costs ~800 OS threads there: at most 8 batches per stream
+    if backend.startswith("simt"):              # a launch costs ~800 OS threads there: at most 8 batches per stream
         max_batch = max(max_batch, -(-n // 8))
     km = O.KernelMap(max_entries, ringbuf_fallback=ringbuf)
     em = Emul(max_entries, max_batch, ringbuf=ringbuf, seed=seed, backend=backend)
