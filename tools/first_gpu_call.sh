@@ -14,6 +14,7 @@ echo "== 4. sketch / multi-engine paths with K1w"
 FA_K1_OPT=256 timeout 600 python -m pytest tests/test_gpu_sketch.py tests/test_gpu_features.py tests/test_gpu_host_cpp.py -x -q -m gpu > $OUT/k1w_other.log 2>&1; tail -2 $OUT/k1w_other.log
 echo "== 5. KERNEL_MAP throughput + e2e at N=1 (new bench code path)"
 FA_EXPERIMENTAL_KERNEL_MAP=1 timeout 300 python tools/bench_aux.py kmap smallcache > $OUT/kmap_bench.jsonl 2>&1; tail -2 $OUT/kmap_bench.jsonl
+FA_EXPERIMENTAL_KERNEL_MAP=1 FA_KMAP_IMPL=1 timeout 300 python tools/bench_aux.py kmap > $OUT/kmap_v1_bench.jsonl 2>&1; tail -1 $OUT/kmap_v1_bench.jsonl
 timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench_default.json 2> $OUT/bench_default.err; tail -c 600 $OUT/bench_default.json
 echo "== 6. ncu: launch list + full capture of K1w"
 FA_K1_OPT=256 timeout 600 ncu --set full --clock-control none --import-source on -k regex:aggregate_warp_kernel -s 3 -c 1 -o $OUT/prof_k1w -f \
