@@ -151,7 +151,10 @@ enum fa_mode {
     FA_MODE_KERNEL_MAP = 1  /* bpf/flows.c:76-143,222-288: the map update of flow_monitor (first-seen-interface
                                de-duplication, last-writer fields, observed-interface list, full map -> ring buffer
                                or counter).  fa_ingest never returns FA_FULL in this mode; fa_evict is
-                               LookupAndDeleteMap.  Only FA_F_RINGBUF_FALLBACK may be set.  EXPERIMENTAL in this
+                               LookupAndDeleteMap, merged with the feature folds when FA_F_ENABLE_RTT / FA_F_ENABLE_DNS are
+                               set (a flow first seen through a feature sample gets its base from the first packet that
+                               follows; such entries count towards max_entries, unlike in the reference where the
+                               feature maps are separate).  FA_F_ENABLE_SKETCH / FA_F_NO_FULL_CUT are refused.  EXPERIMENTAL in this
                                build: fa_create refuses the mode unless FA_EXPERIMENTAL_KERNEL_MAP=1 is set in the
                                environment (kernels checked against the oracle in a host emulation, not yet on a GPU) */
 };

@@ -167,7 +167,7 @@ namespace fa {
 int launch_kmap_batch(KmParams P, uint32_t cut, int sm_count, cudaStream_t st);
 int launch_kmap_batch_v2(KmParams P, uint32_t cut, int sm_count, cudaStream_t st);
 int launch_kmap_evict(const Table& t, uint8_t* met, uint8_t* out, unsigned long long cap, unsigned long long* cursor,
-                      int sm_count, cudaStream_t st);
+                      uint32_t* slot_of_out, int sm_count, cudaStream_t st);
 }
 
 namespace {
@@ -388,8 +388,8 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
         const char* ex = getenv("FA_EXPERIMENTAL_KERNEL_MAP");
         if (!ex || ex[0] != '1')
             return fail(FA_E_INVAL, "fa_create: mode KERNEL_MAP is experimental in this build (set FA_EXPERIMENTAL_KERNEL_MAP=1)");
-        if (cfg->flags & (FA_F_ENABLE_RTT | FA_F_ENABLE_DNS | FA_F_ENABLE_SKETCH | FA_F_NO_FULL_CUT))
-            return fail(FA_E_INVAL, "fa_create: mode KERNEL_MAP supports only FA_F_RINGBUF_FALLBACK (flags 0x%x)", cfg->flags);
+        if (cfg->flags & (FA_F_ENABLE_SKETCH | FA_F_NO_FULL_CUT))
+            return fail(FA_E_INVAL, "fa_create: mode KERNEL_MAP does not take FA_F_ENABLE_SKETCH / FA_F_NO_FULL_CUT (flags 0x%x)", cfg->flags);
     } else if (cfg->flags & FA_F_RINGBUF_FALLBACK) {
         return fail(FA_E_INVAL, "fa_create: FA_F_RINGBUF_FALLBACK needs mode KERNEL_MAP");
     }
@@ -639,38 +639,6 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
     if (live == 0) return FA_OK;
     if (!out_records) return fail(FA_E_INVAL, "fa_evict: null out_records");
     if (cap < live) return fail(FA_E_2BIG, "fa_evict: capacity %zu < %llu live flows", cap, (unsigned long long)live);
-    if (e->cfg.mode == FA_MODE_KERNEL_MAP) {
-        const bool dev_out = classify(out_records) == PTR_DEVICE;
-        uint8_t* d_out = static_cast<uint8_t*>(out_records);
-        if (!dev_out) {
-            if (e->evict_cap < live) {
-                cudaFree(e->d_evict); e->d_evict = nullptr; e->evict_cap = 0;
-                uint64_t want = std::max<uint64_t>(live, std::min<uint64_t>(e->cfg.max_entries, live * 2));
-                CU(cudaMalloc(&e->d_evict, want * fa::kRecBytes));
-                e->evict_cap = want;
-            }
-            d_out = e->d_evict;
-        }
-        CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
-        e->st.kernel_launches += fa::launch_kmap_evict(e->table, e->km_met, d_out, live, &e->d_ctr->evict_out, e->sm_count, e->stream);
-        CU(cudaGetLastError());
-        CU(cudaMemsetAsync(&e->d_ctr->live, 0, sizeof(unsigned long long), e->stream));
-        if (!dev_out) {
-            CU(cudaMemcpyAsync(out_records, d_out, live * fa::kRecBytes, cudaMemcpyDeviceToHost, e->stream));
-            e->st.d2h_bytes += live * fa::kRecBytes;
-        }
-        CU(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(fa::Counters), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-        if (e->h_ctr->evict_out != live)
-            return fail(FA_E_CUDA, "fa_evict: table scan found %llu flows, counter says %llu", (unsigned long long)e->h_ctr->evict_out, (unsigned long long)live);
-        if (out_present && classify(out_present) != PTR_DEVICE) memset(out_present, 0, live);
-        if (out_dns && classify(out_dns) != PTR_DEVICE) memset(out_dns, 0, live * 64);
-        if (out_additional && classify(out_additional) != PTR_DEVICE) memset(out_additional, 0, live * 32);
-        e->live_known = 0; e->unsynced_records = 0; e->ring_head = e->ring_tail;
-        e->st.flows_evicted += live;
-        *n_out = (size_t)live;
-        return FA_OK;
-    }
     const bool feats = e->table.feat_add || e->table.feat_dns;
     const PtrKind k = classify(out_records);
     uint8_t* d_out = nullptr;
@@ -701,8 +669,12 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
         d_pres = out_present ? (classify(out_present) == PTR_DEVICE ? out_present : e->d_evict_present) : nullptr;
     }
     CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
-    e->st.kernel_launches += fa::launch_evict(e->table, reinterpret_cast<uint4*>(d_out), feats ? e->d_slot_of_out : nullptr, live,
-                                              e->d_ctr, e->sm_count, e->stream);
+    if (e->cfg.mode == FA_MODE_KERNEL_MAP)
+        e->st.kernel_launches += fa::launch_kmap_evict(e->table, e->km_met, d_out, live, &e->d_ctr->evict_out,
+                                                       feats ? e->d_slot_of_out : nullptr, e->sm_count, e->stream);
+    else
+        e->st.kernel_launches += fa::launch_evict(e->table, reinterpret_cast<uint4*>(d_out), feats ? e->d_slot_of_out : nullptr, live,
+                                                  e->d_ctr, e->sm_count, e->stream);
     if (feats)
         e->st.kernel_launches += fa::launch_evict_features(e->table, e->d_slot_of_out, live, d_out, d_dns, d_add, d_pres,
                                                            e->sm_count, e->stream);

@@ -60,10 +60,10 @@ __global__ void km2_reset_counts_kernel(KmCounters* c) {
 }
 
 __global__ void __launch_bounds__(kKmThreads) km_evict_kernel(Table t, uint8_t* met, uint8_t* out, unsigned long long cap,
-                                                               unsigned long long* cursor) {
+                                                               unsigned long long* cursor, uint32_t* slot_of_out) {
     const uint64_t words = (t.mask + 1) >> 5;
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < words; w += (uint64_t)gridDim.x * blockDim.x)
-        km_evict_word_body(t, met, (uint32_t)w, out, cap, cursor);
+        km_evict_word_body(t, met, (uint32_t)w, out, cap, cursor, slot_of_out);
 }
 
 #ifndef FA_HOST_EMUL
@@ -101,8 +101,8 @@ int launch_kmap_batch_v2(KmParams P, uint32_t cut, int sm_count, cudaStream_t st
 }
 
 int launch_kmap_evict(const Table& t, uint8_t* met, uint8_t* out, unsigned long long cap, unsigned long long* cursor,
-                      int sm_count, cudaStream_t st) {
-    km_evict_kernel<<<sm_count * 8, kKmThreads, 0, st>>>(t, met, out, cap, cursor);
+                      uint32_t* slot_of_out, int sm_count, cudaStream_t st) {
+    km_evict_kernel<<<sm_count * 8, kKmThreads, 0, st>>>(t, met, out, cap, cursor, slot_of_out);
     return 1;
 }
 #endif  // FA_HOST_EMUL

@@ -220,6 +220,13 @@ FA_HD void km_resolve_body(const KmParams& P, uint32_t i) {
         km_fence();
         if (km_ld_coherent64(L) == k0 && km_ld_coherent64(L + 8) == k1 && km_ld_coherent64(L + 16) == k2 &&
             km_ld_coherent64(L + 24) == k3 && (km_ld_coherent64(L + 32) & 0x00FFFFFFFFFFFFFFull) == k4) {
+            if (!(tag & TAG_HAS_BASE)) {
+                // the flow exists through feature samples only (tracer.go:1179-1182: an empty base): this packet
+                // creates its kernel-map entry, i.e. the flow is born in this batch.  Not while the map is full.
+                if (!P.allow_insert) break;
+                km_cas64(L + 40, tag, (tag & ~(~0ull << TAG_EPOCH_SHIFT)) | TAG_HAS_BASE | (P.epoch << TAG_EPOCH_SHIFT));
+                continue;                                                          // re-read the tag: ours or a peer's claim
+            }
             found = (uint32_t)slot;
             born_now = (tag >> TAG_EPOCH_SHIFT) == P.epoch;
             break;
@@ -557,7 +564,7 @@ FA_HD void km2_finish_flow_body(const KmParams& P, uint32_t k) {
 
 // ---- evict: one call per occupancy word (32 slots) -------------------------------------------------------------
 FA_HD void km_evict_word_body(const Table& t, uint8_t* met, uint32_t w, uint8_t* out, unsigned long long cap,
-                              unsigned long long* cursor) {
+                              unsigned long long* cursor, uint32_t* slot_of_out = nullptr) {
     uint32_t bits = t.occ[w];
     if (!bits) return;
     t.occ[w] = 0u;
@@ -571,6 +578,7 @@ FA_HD void km_evict_word_body(const Table& t, uint8_t* met, uint32_t w, uint8_t*
             uint64_t* O = reinterpret_cast<uint64_t*>(out + (size_t)at * kRecBytes);
             for (int k = 0; k < 5; k++) O[k] = L[k];
             for (int k = 0; k < 13; k++) O[5 + k] = M[k];
+            if (slot_of_out) slot_of_out[at] = slot;                    // for the feature pass (evict_features_kernel)
         }
         for (int k = 0; k < 16; k++) { L[k] = 0ull; M[k] = 0ull; }
     }

@@ -482,6 +482,20 @@ static void update_existing_flow(oracle_kmap* k, uint8_t* agg, const uint8_t* ke
     }
 }
 
+/* flows.c:228-245 new_flow from a packet event */
+static void kmap_new_flow(const uint8_t* ev, uint8_t* nf) {
+    memset(nf, 0, OR_MET_SIZE);
+    st32(nf + M_IFINDEX, ld32(ev + M_IFINDEX)); nf[M_DIR] = ev[M_DIR];
+    st32(nf + M_PACKETS, 1); st64(nf + M_BYTES, ld64(ev + M_BYTES));
+    st16(nf + M_ETH, ld16(ev + M_ETH));
+    st64(nf + M_START, ld64(ev + M_START)); st64(nf + M_END, ld64(ev + M_START));
+    st16(nf + M_FLAGS, ld16(ev + M_FLAGS)); nf[M_DSCP] = ev[M_DSCP];
+    st32(nf + M_SAMPLING, ld32(ev + M_SAMPLING));
+    memcpy(nf + M_DSTMAC, ev + M_DSTMAC, 6); memcpy(nf + M_SRCMAC, ev + M_SRCMAC, 6);
+    st16(nf + M_SSLVER, ld16(ev + M_SSLVER)); st16(nf + M_CIPHER, ld16(ev + M_CIPHER));
+    st16(nf + M_KEYSHARE, ld16(ev + M_KEYSHARE)); nf[M_TLSTYPES] = ev[M_TLSTYPES];
+}
+
 void oracle_kmap_packets(oracle_kmap* k, const uint8_t* wire, size_t n) {
     uint8_t rec[OR_REC_SIZE];
     for (size_t i = 0; i < n; i++) {
@@ -489,17 +503,7 @@ void oracle_kmap_packets(oracle_kmap* k, const uint8_t* wire, size_t n) {
         const uint8_t* ev = rec + OR_ID_SIZE;
         int found; entry_t* e = fmap_get(&k->m, rec, 0, &found);        /* flows.c:222 */
         if (found) { update_existing_flow(k, e->c.metrics, rec, ev); continue; }
-        /* flows.c:228-245 new_flow */
-        uint8_t nf[OR_MET_SIZE]; memset(nf, 0, sizeof nf);
-        st32(nf + M_IFINDEX, ld32(ev + M_IFINDEX)); nf[M_DIR] = ev[M_DIR];
-        st32(nf + M_PACKETS, 1); st64(nf + M_BYTES, ld64(ev + M_BYTES));
-        st16(nf + M_ETH, ld16(ev + M_ETH));
-        st64(nf + M_START, ld64(ev + M_START)); st64(nf + M_END, ld64(ev + M_START));
-        st16(nf + M_FLAGS, ld16(ev + M_FLAGS)); nf[M_DSCP] = ev[M_DSCP];
-        st32(nf + M_SAMPLING, ld32(ev + M_SAMPLING));
-        memcpy(nf + M_DSTMAC, ev + M_DSTMAC, 6); memcpy(nf + M_SRCMAC, ev + M_SRCMAC, 6);
-        st16(nf + M_SSLVER, ld16(ev + M_SSLVER)); st16(nf + M_CIPHER, ld16(ev + M_CIPHER));
-        st16(nf + M_KEYSHARE, ld16(ev + M_KEYSHARE)); nf[M_TLSTYPES] = ev[M_TLSTYPES];
+        uint8_t nf[OR_MET_SIZE]; kmap_new_flow(ev, nf);
         if (k->m.n < k->max_entries) {                                  /* flows.c:247 BPF_NOEXIST */
             e = fmap_get(&k->m, rec, 1, &found);
             memcpy(e->c.metrics, nf, OR_MET_SIZE);
@@ -522,6 +526,20 @@ size_t oracle_kmap_spilled(oracle_kmap* k, uint8_t* out, size_t cap) {
     size_t c = k->n_spill < cap ? k->n_spill : cap;
     if (out && c) memcpy(out, k->spill, c * OR_REC_SIZE);
     size_t n = k->n_spill; k->n_spill = 0; return n;
+}
+
+/* LookupAndDeleteMap's merged view when the BASE is the kernel map (the reference's real deployment:
+ * aggregated_flows + the per-CPU feature maps, pkg/tracer/tracer.go:1063-1157).  No capacity limit here. */
+uint64_t oracle_flowmap_packets_kmap(oracle_flowmap* m, const uint8_t* wire, size_t n) {
+    oracle_kmap counters; memset(&counters, 0, sizeof counters);
+    uint8_t rec[OR_REC_SIZE];
+    for (size_t i = 0; i < n; i++) {
+        oracle_read_from(wire + i * OR_REC_SIZE, rec);
+        int found; entry_t* e = fmap_get(&m->m, rec, 1, &found);
+        if (e->has_base) update_existing_flow(&counters, e->c.metrics, rec, rec + OR_ID_SIZE);
+        else { kmap_new_flow(rec + OR_ID_SIZE, e->c.metrics); e->has_base = 1; }
+    }
+    return counters.intf_missed;
 }
 
 /* ------------------------------------------------------------- sketches */

@@ -106,6 +106,7 @@ size_t oracle_flowmap_evict(oracle_flowmap* m, uint8_t* out_recs, uint8_t* out_d
  * event whose metrics carry (ts=start, len=bytes, flags, dscp, sampling, ifindex,
  * direction, eth, macs, tls*). */
 typedef struct oracle_kmap oracle_kmap;
+uint64_t oracle_flowmap_packets_kmap(oracle_flowmap* m, const uint8_t* wire, size_t n);   /* returns OBSERVED_INTF_MISSED increments */
 oracle_kmap* oracle_kmap_new(size_t max_entries, int ringbuf_fallback);
 void   oracle_kmap_free(oracle_kmap* m);
 void   oracle_kmap_packets(oracle_kmap* m, const uint8_t* wire, size_t n);

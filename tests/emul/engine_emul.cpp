@@ -249,9 +249,10 @@ int launch_kmap_batch_v2(KmParams P, uint32_t cut, int, cudaStream_t) {
     simt::launch(1, 32, 0, [=] { if (threadIdx.x == 0) km2_reset_counts_kernel(c); });
     return launches + 7;
 }
-int launch_kmap_evict(const Table& table, uint8_t* met, uint8_t* out, unsigned long long cap, unsigned long long* cursor, int, cudaStream_t) {
+int launch_kmap_evict(const Table& table, uint8_t* met, uint8_t* out, unsigned long long cap, unsigned long long* cursor,
+                      uint32_t* slot_of_out, int, cudaStream_t) {
     Table t = table;
-    simt::launch(3, 256, 0, [=] { km_evict_kernel(t, met, out, cap, cursor); });
+    simt::launch(3, 256, 0, [=] { km_evict_kernel(t, met, out, cap, cursor, slot_of_out); });
     return 1;
 }
 

@@ -112,7 +112,7 @@ uint64_t kmap_emul_evict(void* h, uint8_t* out, uint64_t cap) {
     KmParams P = params(e);
     unsigned long long cursor = 0; unsigned long long* cp = &cursor;
     Table t = P.t; uint8_t* met = e->met;
-    simt::launch(kGrid, kBlock, 0, [=] { km_evict_kernel(t, met, out, cap, cp); });
+    simt::launch(kGrid, kBlock, 0, [=] { km_evict_kernel(t, met, out, cap, cp, nullptr); });
     *e->live = 0; e->keys.clear();
     for (size_t i = 0; i < e->slots * kIdentBytes; i++) if (e->ident[i]) return ~0ull;
     for (size_t i = 0; i < e->slots * kMetLineBytes; i++) if (e->met[i]) return ~0ull;

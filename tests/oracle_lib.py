@@ -64,6 +64,7 @@ def lib():
         "oracle_flowmap_new": (vp, []),
         "oracle_flowmap_free": (None, [vp]),
         "oracle_flowmap_account": (None, [vp, _u8p, sz]),
+        "oracle_flowmap_packets_kmap": (C.c_uint64, [vp, _u8p, sz]),
         "oracle_flowmap_fold_dns": (None, [vp, _u8p, sz]),
         "oracle_flowmap_fold_additional": (None, [vp, _u8p, sz]),
         "oracle_flowmap_len": (sz, [vp]),
@@ -185,6 +186,11 @@ class FlowMap:
     def account(self, recs):
         b = as_bytes(recs)
         lib().oracle_flowmap_account(self.h, _p(b), b.size // REC)
+
+    def packets_kmap(self, recs):
+        """Base = the kernel map's update (bpf/flows.c:222-288) instead of the Accounter's; returns intf_missed increments."""
+        b = as_bytes(recs)
+        return int(lib().oracle_flowmap_packets_kmap(self.h, _p(b), b.size // REC))
 
     def fold_dns(self, recs):
         b = as_bytes(recs)

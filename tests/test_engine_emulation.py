@@ -63,7 +63,7 @@ def test_error_paths(engine_emul):
         fa.FlowAggEngine(0)
     assert ei.value.code == -22
     with pytest.raises(fa.FlowAggError):
-        fa.FlowAggEngine(100, mode=fa.FA_MODE_KERNEL_MAP, flags=fa.FA_F_ENABLE_DNS)
+        fa.FlowAggEngine(100, mode=fa.FA_MODE_KERNEL_MAP, flags=fa.FA_F_ENABLE_SKETCH)
     with pytest.raises(fa.FlowAggError):
         fa.FlowAggEngine(100, flags=fa.FA_F_RINGBUF_FALLBACK)
     with fa.FlowAggEngine(100) as eng:
@@ -114,3 +114,26 @@ def test_degenerate_cache_sizes(engine_emul, max_entries, n_keys, n):
     want = oracle_generations(b, max_entries)
     assert_same_generations(got, want)
     assert st["full_cuts"] == len(want) - 1 and st["full_cuts"] > 0
+
+
+@pytest.mark.parametrize("impl", ["2", "1"])
+def test_kernel_map_base_with_feature_maps(engine_emul, monkeypatch, impl):
+    """The reference's real deployment: aggregated_flows as the base + the per-CPU feature maps, merged by
+    LookupAndDeleteMap (tracer.go:1063-1157).  Flows first seen through a feature sample get their kernel-map entry
+    from the first packet that follows; flows never seen by flow_monitor come out with an empty base."""
+    import netobserv_ebpf_agent_b200 as fa
+    from test_gpu_features import compare, keys_of, make_add, make_dns
+    from test_kmap_emulation import messy_stream
+    monkeypatch.setenv("FA_KMAP_IMPL", impl)
+    rng = np.random.default_rng(81)
+    pk = messy_stream(81, 3_000, 150, n_ifaces=5)
+    keys = np.unique(pk[:, :40], axis=0)
+    allk = np.concatenate([keys, keys_of(82, 30)])
+    add, dns = make_add(rng, allk, 900), make_dns(rng, allk, 900)
+    om = O.FlowMap()
+    with fa.FlowAggEngine(1 << 10, mode=fa.FA_MODE_KERNEL_MAP, flags=fa.FA_F_ENABLE_RTT | fa.FA_F_ENABLE_DNS, max_batch=1_024) as eng:
+        eng.ingest_additional(add); eng.ingest(pk[:1_500]); eng.ingest_dns(dns); eng.ingest(pk[1_500:])
+        om.fold_additional(add); missed = om.packets_kmap(pk); om.fold_dns(dns)
+        compare(eng, om)
+        assert eng.stats()["observed_intf_missed"] == missed
+        assert eng.live_flows() == 0

@@ -115,3 +115,21 @@ def test_committed_fixture():
         assert np.array_equal(sp[np.lexsort(sp.T[::-1])], z["spilled"])
         st = eng.stats()
     assert [st["observed_intf_missed"], st["hashmap_fail_create"]] == [int(x) for x in z["counters"]]
+
+
+@needs_kmap
+def test_kernel_map_base_with_feature_maps():
+    """aggregated_flows as the base + the per-CPU feature maps, merged by LookupAndDeleteMap (tracer.go:1063-1157)."""
+    import netobserv_ebpf_agent_b200 as fa
+    from test_gpu_features import compare, keys_of, make_add, make_dns
+    rng = np.random.default_rng(81)
+    pk = messy_stream(81, 60_000, 2_000, n_ifaces=5)
+    keys = np.unique(pk[:, :40], axis=0)
+    allk = np.concatenate([keys, keys_of(82, 300)])
+    add, dns = make_add(rng, allk, 20_000), make_dns(rng, allk, 20_000)
+    om = O.FlowMap()
+    with fa.FlowAggEngine(1 << 13, mode=fa.FA_MODE_KERNEL_MAP, flags=fa.FA_F_ENABLE_RTT | fa.FA_F_ENABLE_DNS, max_batch=16_384) as eng:
+        eng.ingest_additional(add); eng.ingest(pk[:30_000]); eng.ingest_dns(dns); eng.ingest(pk[30_000:])
+        om.fold_additional(add); missed = om.packets_kmap(pk); om.fold_dns(dns)
+        compare(eng, om)
+        assert eng.stats()["observed_intf_missed"] == missed and eng.live_flows() == 0
