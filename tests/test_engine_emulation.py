@@ -76,9 +76,9 @@ def test_small_cache_windows_keep_the_cut_exact_and_the_prepass_linear(engine_em
     """A cache much smaller than the batch (the reference's default is 5000 flows): the cut is searched in windows
     proportional to the room left, every generation still ends at the exact record, and the number of launches grows
     with the number of generations, not with generations x batch size."""
-    recs = gen_host(seed=71, n=4_000, n_keys=200, dist=1)
+    recs = gen_host(seed=71, n=2_400, n_keys=200, dist=1)
     want = oracle_generations([recs], 60)
-    got, st = gpu_generations([recs], 60, max_batch=4_000)             # one host chunk, many cuts inside it
+    got, st = gpu_generations([recs], 60, max_batch=2_400)             # one host chunk, many cuts inside it
     assert_same_generations(got, want)
     gens = len(want) - 1
     assert gens > 8 and st["full_cuts"] == gens
@@ -88,7 +88,7 @@ def test_small_cache_windows_keep_the_cut_exact_and_the_prepass_linear(engine_em
 
 def test_device_resident_input_with_cuts(engine_emul):
     import netobserv_ebpf_agent_b200 as fa
-    recs = gen_host(seed=72, n=1_500, n_keys=120, dist=1)
+    recs = gen_host(seed=72, n=900, n_keys=120, dist=1)
     want = oracle_generations([recs], 40)
     gens = []
     with fa.FlowAggEngine(40, max_batch=1_024) as eng:
@@ -106,7 +106,7 @@ def test_device_resident_input_with_cuts(engine_emul):
     assert_same_generations(gens, want)
 
 
-@pytest.mark.parametrize("max_entries,n_keys,n", [(1, 5, 14), (2, 3, 24)])
+@pytest.mark.parametrize("max_entries,n_keys,n", [(1, 5, 8), (2, 3, 14)])
 def test_degenerate_cache_sizes(engine_emul, max_entries, n_keys, n):
     """maxEntries 1 and 2 (tests/test_gpu_parity.py::test_full_cut_generations at emulation scale): room 0 / 1 windows."""
     b = [gen_host(seed=10, n=n, n_keys=n_keys, dist=0, first=i * n) for i in range(2)]

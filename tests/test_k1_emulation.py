@@ -94,7 +94,7 @@ def same_flows(got, want):
         raise AssertionError(f"{len(bad)} of {len(got)} flows differ; first {bad[0]}: {diff}: want {[w[bad[0]][f] for f in diff]} got {[g[bad[0]][f] for f in diff]}")
 
 
-VARIANTS = [0, 2, 4, 8, 9, 10]        # kVar of aggregate_kernel: 0 = the measured default, 1..5 = FA_K1_OPT experiments (1, 3, 5 only add a
+VARIANTS = [0, 4, 8, 9, 10]           # kVar of aggregate_kernel: 0 = the measured default, 1..5 = FA_K1_OPT experiments (1, 3, 5 only add a
                                    # prefetch, which is a no-op here);
                                    # 8 = aggregate_warp_kernel (K1w, the warp-independent variant), 9 = K1w + warp-aggregated cache folds, 10 = K1w with 8-lane probes
 
@@ -112,7 +112,7 @@ def test_zipf_stream_with_varying_descriptors_two_launches(var):
     assert k1.counter(1) == 0                                   # no spills
 
 
-@pytest.mark.parametrize("var", [0, 4, 8, 10])
+@pytest.mark.parametrize("var", [0, 8, 10])
 def test_uniform_keys_crowded_table(var):
     """Mostly inserts, collision chains (load ~0.7 of the slots), no duplicates to speak of: the general probe loop."""
     recs = gen_host(seed=8, n=6_000, n_keys=5_600, dist=0)
@@ -123,7 +123,7 @@ def test_uniform_keys_crowded_table(var):
     same_flows(k1.evict(), acc.evict())
 
 
-@pytest.mark.parametrize("var", [0, 4, 8])
+@pytest.mark.parametrize("var", [0, 8])
 def test_eviction_then_reuse_of_the_table(var):
     a = gen_host(seed=9, n=8_000, n_keys=900, dist=1)
     b = gen_host(seed=10, n=8_000, n_keys=700, dist=1, varying=1, first=8_000)
