@@ -669,41 +669,47 @@ constexpr int kWWarps = 32;                      // warps per CTA
 constexpr int kWSub = 32;                        // records per sub-tile == lanes
 constexpr int kWLast = 1024;                     // "seen this flow a moment ago" filter (cache candidacy)
 constexpr int kWHot = 256;                       // direct-mapped cache of hot flows (the room the team structures took)
-struct __align__(128) WarpSmem {                 // 5,120 B per warp
-    uint4    tile[kWSub * kRecChunks];           // 4,608 B
+template <int kBufs>
+struct __align__(128) WarpSmemT {                // 5,120 B per warp with one tile buffer, 9,728 B with two
+    uint4    tile[kBufs][kWSub * kRecChunks];    // 4,608 B each
     uint32_t res[kWSub];                         //   128 B  table slot found for each probing lane
     uint32_t mir_lo[kWSub];                      //   128 B
     uint16_t mir_hi[kWSub];                      //    64 B
     uint16_t fseen[kWSub];                       //    64 B
     uint8_t  slow[kWSub];                        //    32 B  lanes whose flow needs the general probe loop
     uint8_t  list[kWSub];                        //    32 B  the probing lanes, compacted
-    unsigned long long full_bar;
-    uint8_t  pad[56];
+    unsigned long long full_bar[kBufs];
+    uint8_t  pad[kBufs == 1 ? 56 : 48];
 };
-static_assert(sizeof(WarpSmem) == 5120, "WarpSmem");
-struct __align__(128) AggWSmem {                 // 221,200 B
-    WarpSmem w[kWWarps];
+using WarpSmem = WarpSmemT<1>;
+static_assert(sizeof(WarpSmemT<1>) == 5120 && sizeof(WarpSmemT<2>) == 9728, "WarpSmem");
+// kW warps per CTA: 32 warps with one tile buffer each (221,200 B), or 16 warps with two (213,008 B) - the latter
+// requests the next sub-tile before it works on the current one and may use twice the registers per thread
+template <int kW>
+struct __align__(128) AggWSmemT {
+    WarpSmemT<(kW == 32 ? 1 : 2)> w[kW];
     HotEntry hot[kWHot];
     uint32_t last[kWLast];
     uint32_t n_insert, n_spill, any_dirty, pad;
 };
+using AggWSmem = AggWSmemT<32>;
 
-__device__ __forceinline__ void issue_sub_load(WarpSmem& s, const uint4* recs, uint32_t n, uint32_t sub, bool evict_first) {
+__device__ __forceinline__ void issue_sub_load(uint4* tile, unsigned long long* bar, const uint4* recs, uint32_t n, uint32_t sub,
+                                               bool evict_first) {
     const uint32_t first = sub * kWSub;
     const uint32_t bytes = min((uint32_t)kWSub, n - first) * kRecBytes;
-    mbar_expect_tx(&s.full_bar, bytes);
-    if (evict_first) tma_load_1d_stream(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
-    else tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
+    mbar_expect_tx(bar, bytes);
+    if (evict_first) tma_load_1d_stream(tile, recs + (size_t)first * kRecChunks, bytes, bar);
+    else tma_load_1d(tile, recs + (size_t)first * kRecChunks, bytes, bar);
 }
 
 // One batch of the pipelined probe passes of K1w: kRounds rounds of 8 flows (4 lanes per flow), all their identity
 // lines in flight together; pass 0 = home slot, pass 1 = next slot for the flows whose home slot holds another
 // settled flow.  Flows that need more (inserts, chains, in-flight publishes) are appended to s.slow.
-template <int kRounds>
-__device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, WarpSmem& s, uint32_t* any_dirty,
+template <int kRounds, typename WS>
+__device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, WS& s, const uint4* T, uint32_t* any_dirty,
                                               uint32_t nrep, uint32_t base, uint32_t home, uint32_t tmask, uint32_t lt_mask,
                                               int g4, int j4, uint4 cmaskA, uint4 cmaskB, int rcA, int rcB, uint32_t& nslow) {
-    const uint4* T = s.tile;
     uint32_t ridx4[kRounds], slot4[kRounds], actm[kRounds];
     uint32_t pend4 = 0;
 #pragma unroll
@@ -778,11 +784,10 @@ __device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, Wa
 
 // The same batch with 8 lanes per flow (one lane per 16-byte line chunk, one L1 wavefront per line instead of two):
 // kRounds rounds of 4 flows.  Costs twice the instructions per flow of wprobe_rounds; FA_K1_OPT bit 11 selects it.
-template <int kRounds>
-__device__ __forceinline__ void wprobe_rounds8(const Table& t, uint64_t epoch, WarpSmem& s, uint32_t* any_dirty,
+template <int kRounds, typename WS>
+__device__ __forceinline__ void wprobe_rounds8(const Table& t, uint64_t epoch, WS& s, const uint4* T, uint32_t* any_dirty,
                                                uint32_t nrep, uint32_t base, uint32_t home, uint32_t tmask, uint32_t lt_mask,
                                                int g, int j, uint4 cmask, int rc, uint32_t& nslow) {
-    const uint4* T = s.tile;
     uint32_t ridx[kRounds], slot[kRounds], actm[kRounds];
     uint32_t pend = 0;
 #pragma unroll
@@ -851,27 +856,32 @@ __device__ __forceinline__ void wprobe_rounds8(const Table& t, uint64_t epoch, W
 // kAgg (experiment, FA_K1_OPT bit 9): lanes of a warp that hit the same cache entry pre-reduce their record
 // (match.any + redux) and one of them issues the shared-memory atomics.
 // kLanes8 (experiment, FA_K1_OPT bit 11): 8 lanes per flow in the pipelined probe passes (wprobe_rounds8).
-template <bool kSketch, bool kDevN, bool kAgg = false, bool kLanes8 = false>
-__global__ void __launch_bounds__(kWWarps * 32, 1)
+// kW (experiment, FA_K1_OPT bit 12): 16 warps per CTA with double-buffered sub-tiles instead of 32 with one buffer.
+template <bool kSketch, bool kDevN, bool kAgg = false, bool kLanes8 = false, int kW = kWWarps>
+__global__ void __launch_bounds__(kW * 32, 1)
 aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
                       uint32_t* __restrict__ spill_idx, SketchParams sk, uint32_t opt) {
     FA_DYN_SMEM(smem_raw);
-    AggWSmem& cs = *reinterpret_cast<AggWSmem*>(smem_raw);
+    constexpr int kBufs = kW == 32 ? 1 : 2;
+    AggWSmemT<kW>& cs = *reinterpret_cast<AggWSmemT<kW>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem& s = cs.w[warp];
+    WarpSmemT<kBufs>& s = cs.w[warp];
     if (kDevN) n = min(n, (uint32_t)ctr->launch_n);
     const uint32_t n_sub = (n + kWSub - 1) / kWSub;
-    const uint32_t sub_stride = gridDim.x * kWWarps;
-    const uint32_t sub0 = blockIdx.x * kWWarps + warp;
+    const uint32_t sub_stride = gridDim.x * kW;
+    const uint32_t sub0 = blockIdx.x * kW + warp;
     const bool use_cache = (opt & 2u) == 0;
 
     if (threadIdx.x == 0) { cs.n_insert = 0; cs.n_spill = 0; cs.any_dirty = 0; }
     if (threadIdx.x < kWHot) cs.hot[threadIdx.x].state = 0;
-    cs.last[threadIdx.x] = 0u;
-    if (lane == 0) { mbar_init(&s.full_bar, 1); fence_barrier_init(); }
+    for (int i = threadIdx.x; i < kWLast; i += kW * 32) cs.last[i] = 0u;
+    if (lane == 0) {
+        for (int b = 0; b < kBufs; b++) mbar_init(&s.full_bar[b], 1);
+        fence_barrier_init();
+    }
     __syncthreads();
     const bool stream_hint = (opt & 1024u) != 0;                 // optional: L2 evict-first for the record stream
-    if (lane == 0 && sub0 < n_sub) issue_sub_load(s, recs, n, sub0, stream_hint);
+    if (lane == 0 && sub0 < n_sub) issue_sub_load(s.tile[0], &s.full_bar[0], recs, n, sub0, stream_hint);
 
     const int g = lane >> 3, j = lane & 7;                       // 8-lane groups of the general probe loop
     const uint4 cmask = chunk_mask(j);
@@ -882,14 +892,19 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
     const uint32_t tmask = (uint32_t)t.mask;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t my_inserts = 0, my_spills = 0;
-    const uint4* T = s.tile;
 
     for (uint32_t it = 0;; ++it) {
         const uint32_t sub = sub0 + it * sub_stride;
         if (sub >= n_sub) break;
         const uint32_t first = sub * kWSub;
         const uint32_t cnt = min((uint32_t)kWSub, n - first);
-        mbar_wait(&s.full_bar, it & 1u);
+        const int buf = kBufs == 1 ? 0 : (int)(it & 1u);
+        if (kBufs == 2 && lane == 0 && sub + sub_stride < n_sub) {      // the other buffer was drained an iteration ago
+            fence_proxy_async();
+            issue_sub_load(s.tile[buf ^ 1], &s.full_bar[buf ^ 1], recs, n, sub + sub_stride, stream_hint);
+        }
+        mbar_wait(&s.full_bar[buf], kBufs == 1 ? (it & 1u) : ((it >> 1) & 1u));
+        const uint4* T = s.tile[buf];
         if ((opt & 32u) && lane == 0 && sub + sub_stride < n_sub) {     // optional: have L2 fetch the next sub-tile now
             const uint32_t nf = (sub + sub_stride) * kWSub;
             tma_prefetch_l2(recs + (size_t)nf * kRecChunks, min((uint32_t)kWSub, n - nf) * kRecBytes);
@@ -986,23 +1001,27 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
         if (kLanes8) {                                             // 8 lanes per flow: 4 flows per round
             for (uint32_t base = 0; base < nrep;) {
                 if (nrep - base > 8u) {
-                    wprobe_rounds8<4>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
+                    wprobe_rounds8<4>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
                     base += 16u;
                 } else if (nrep - base > 4u) {
-                    wprobe_rounds8<2>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
+                    wprobe_rounds8<2>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
                     base += 8u;
                 } else {
-                    wprobe_rounds8<1>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
+                    wprobe_rounds8<1>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
                     base += 4u;
                 }
             }
         } else
         for (uint32_t base = 0; base < nrep;) {                   // two rounds in flight while >= 9 flows remain
+            if (kW == 16 && nrep - base > 16u) {                   // half the warps, twice the registers: four rounds in flight
+                wprobe_rounds<4>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
+                base += 32u;
+            } else
             if (nrep - base > 8u) {
-                wprobe_rounds<2>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
+                wprobe_rounds<2>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
                 base += 16u;
             } else {
-                wprobe_rounds<1>(t, epoch, s, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
+                wprobe_rounds<1>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
                 base += 8u;
             }
         }
@@ -1065,7 +1084,7 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
         __syncwarp();                                              // nobody reads the sub-tile buffer any more
         if (lane == 0) {
             const uint32_t nx = sub + sub_stride;
-            if (nx < n_sub) { fence_proxy_async(); issue_sub_load(s, recs, n, nx, stream_hint); }
+            if (kBufs == 1 && nx < n_sub) { fence_proxy_async(); issue_sub_load(s.tile[0], &s.full_bar[0], recs, n, nx, stream_hint); }
         }
     }
 
@@ -1245,6 +1264,16 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
         if (a.sk.cms && dev_n) aggregate_warp_kernel<true, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else if (a.sk.cms) aggregate_warp_kernel<true, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else if (dev_n) aggregate_warp_kernel<false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
+        else if (a.opt & 4096u) {                         // 16 warps, double-buffered sub-tiles
+            const int wsmem16 = (int)sizeof(AggWSmemT<16>);
+            static bool w16attr[64] = {};
+            if (!w16attr[dev & 63]) {
+                cudaFuncSetAttribute(aggregate_warp_kernel<false, false, false, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem16);
+                w16attr[dev & 63] = true;
+            }
+            const int g16 = (int)min((uint32_t)a.sm_count, (n_sub + 15) / 16);
+            aggregate_warp_kernel<false, false, false, false, 16><<<g16, 16 * 32, wsmem16, st>>>(FA_K1_ARGS, a.opt);
+        }
         else if (a.opt & 2048u) aggregate_warp_kernel<false, false, false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else if (a.opt & 512u) aggregate_warp_kernel<false, false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
         else aggregate_warp_kernel<false, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);

@@ -130,6 +130,7 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t) {
         if (sk.cms && dev_n) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<true, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
         else if (sk.cms) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<true, false>(recs, n, t, epoch, ctr, spill, sk, opt); });
         else if (dev_n) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<false, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
+        else if (a.opt & 4096u) simt::launch(small((n_sub + 15) / 16, 3), 16 * 32, sizeof(AggWSmemT<16>), [=] { aggregate_warp_kernel<false, false, false, false, 16>(recs, n, t, epoch, ctr, spill, sk, opt); });
         else if (a.opt & 2048u) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<false, false, false, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
         else if (a.opt & 512u) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<false, false, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
         else simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<false, false>(recs, n, t, epoch, ctr, spill, sk, opt); });

@@ -94,6 +94,14 @@ int k1_emul_ingest(void* h, const uint8_t* recs8, uint32_t n, unsigned grid, int
         case 3: run_k1<3>(e, recs, n, grid, opt); break;
         case 4: run_k1<4>(e, recs, n, grid, opt); break;
         case 5: run_k1<5>(e, recs, n, grid, opt); break;
+        case 11: {                                          // K1w with 16 warps per CTA and double-buffered sub-tiles
+            const uint32_t n_sub = (n + kWSub - 1) / kWSub;
+            const unsigned g = std::min<unsigned>(grid, (n_sub + 15) / 16);
+            const uint64_t epoch = e->epoch;
+            Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx; SketchParams sk{};
+            simt::launch(g, 16 * 32, sizeof(AggWSmemT<16>), [=] { aggregate_warp_kernel<false, false, false, false, 16>(recs, n, t, epoch, ctr, spill, sk, opt); });
+            break;
+        }
         case 10: {                                          // K1w with 8 lanes per flow in the probe passes
             const uint32_t n_sub = (n + kWSub - 1) / kWSub;
             const unsigned g = std::min<unsigned>(grid, (n_sub + kWWarps - 1) / kWWarps);

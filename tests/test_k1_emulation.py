@@ -94,9 +94,9 @@ def same_flows(got, want):
         raise AssertionError(f"{len(bad)} of {len(got)} flows differ; first {bad[0]}: {diff}: want {[w[bad[0]][f] for f in diff]} got {[g[bad[0]][f] for f in diff]}")
 
 
-VARIANTS = [0, 4, 8, 9, 10]           # kVar of aggregate_kernel: 0 = the measured default, 1..5 = FA_K1_OPT experiments (1, 3, 5 only add a
+VARIANTS = [0, 4, 8, 9, 10, 11]       # kVar of aggregate_kernel: 0 = the measured default, 1..5 = FA_K1_OPT experiments (1, 3, 5 only add a
                                    # prefetch, which is a no-op here);
-                                   # 8 = aggregate_warp_kernel (K1w, the warp-independent variant), 9 = K1w + warp-aggregated cache folds, 10 = K1w with 8-lane probes
+                                   # 8 = aggregate_warp_kernel (K1w, the warp-independent variant), 9 = K1w + warp-aggregated cache folds, 10 = K1w with 8-lane probes, 11 = K1w with 16 warps per CTA and double-buffered sub-tiles
 
 
 @pytest.mark.parametrize("var", VARIANTS)
@@ -198,7 +198,7 @@ def test_fused_sketches_match_the_cpu_restatement(var):
     same_flows(k1.evict(), acc.evict())
 
 
-@pytest.mark.parametrize("var", [0, 4, 8, 9])
+@pytest.mark.parametrize("var", [0, 4, 8, 9, 11])
 def test_ragged_sizes_and_single_flow(var):
     """Partial tiles / sub-tiles (n not a multiple of 32 or 256), one record, and one flow hammered by every thread."""
     recs = gen_host(seed=13, n=1_000, n_keys=60, dist=1, varying=1)
@@ -216,7 +216,7 @@ def test_ragged_sizes_and_single_flow(var):
     same_flows(k1.evict(), acc.evict())
 
 
-@pytest.mark.parametrize("var", [0, 4, 8, 10])
+@pytest.mark.parametrize("var", [0, 4, 8, 10, 11])
 def test_long_collision_chain(var):
     """Two dozen flows whose home slot is the same: the probe has to walk a 24-slot chain (pipelined passes give up after
     one step, the general loop does the rest), concurrently from every warp."""
