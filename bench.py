@@ -1,15 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — flow-aggregation throughput on B200 (contract: see the task prompt / DESIGN.md §measurement).
+"""bench.py — flow-aggregation throughput on B200 (contract: the task prompt; measurement notes: DESIGN.md §7).
 
-A "step" is one pass of the hot path (K1 flow_aggregate, reached through fa_ingest of the C ABI) over one
-batch of synthetic 144-byte flow records.  Workloads (BASELINE.json):
-  zipf1m    configs[1]: 1 M Zipf-1.1 5-tuples            (default; the config the metric is quoted on)
-  zipf10m   north_star headline: 10 M Zipf-1.1 5-tuples
+A "step" is one pass of the hot path (K1 flow_aggregate, reached through fa_ingest of the C ABI) over one batch of
+synthetic 144-byte flow records that is already resident in HBM.  Workloads (BASELINE.json):
+  zipf10m    the configuration the metric is quoted on ("@10M 5-tuples"): 10 M Zipf-1.1 5-tuples (default)
   uniform10m worst case for table locality: 10 M uniform 5-tuples
-One JSON line on stdout (rank 0).  --impl reference times the CPU restatement of pkg/flow.Accounter
-(the Go reference cannot be built in this image) on a bounded sample of the same workload.
+  zipf1m     configs[1]: 1 M Zipf-1.1 5-tuples
+One JSON line on stdout (rank 0).  After the timed loop the engine's output is checked against the CPU oracle on a
+fresh prefix of the same stream (`parity_checked` = flows compared bit for bit; --no-verify skips it).
+--impl reference times the CPU restatement of pkg/flow.Accounter (the Go reference cannot be built in this image) on
+a bounded sample of the same workload; that arm never loads the product library.
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -24,15 +27,19 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 REC = 144
-# DRAM bytes per record of K1 from the committed ncu --set full capture (profiles/r1_k1_aggregate_ncu_summary.txt:
-# dram__bytes_read.sum 2.863857 GB + dram__bytes_write.sum 70.906 MB for one 16,777,216-record launch of the zipf1m
-# workload) -> 174.9 B/record against 144 algorithmic bytes (ratio 1.21: table lines + write-backs, no re-reads).
-NCU_DRAM_BYTES_PER_RECORD = {"zipf1m": (2.863857e9 + 70.906112e6) / 16777216}
+# flow cache sizing per workload: max_entries = 0.75 x 2^k gets exactly 2^k table slots (2^25 slots for
+# the 10 M-flow configurations = load 0.30, 2^21 for 1 M flows = load 0.48)
 WORKLOADS = {
-    "zipf1m": dict(n_keys=1_000_000, dist=1, seed=2, label="1e9-record stream, 1M Zipf-1.1 5-tuples (BASELINE configs[1])"),
-    "zipf10m": dict(n_keys=10_000_000, dist=1, seed=2, label="1e9-record stream, 10M Zipf-1.1 5-tuples (north_star headline)"),
-    "uniform10m": dict(n_keys=10_000_000, dist=0, seed=2, label="1e9-record stream, 10M uniform 5-tuples (worst-case locality)"),
+    "zipf10m": dict(n_keys=10_000_000, dist=1, seed=2, max_entries=3 << 23, no_full_cut=False,
+                    label="synthetic record stream, 10M Zipf-1.1 5-tuples (BASELINE metric: '@10M 5-tuples')"),
+    "uniform10m": dict(n_keys=10_000_000, dist=0, seed=2, max_entries=3 << 23, no_full_cut=False,
+                       label="synthetic record stream, 10M uniform 5-tuples (worst-case table locality)"),
+    # 1 M flows in 2^21 slots leave room for 0.57 M new flows only: every 2^22-record launch "could" overflow the cache,
+    # so this workload runs the table as a plain map (FA_F_NO_FULL_CUT: max_entries only sizes it)
+    "zipf1m": dict(n_keys=1_000_000, dist=1, seed=2, max_entries=3 << 19, no_full_cut=True,
+                   label="synthetic record stream, 1M Zipf-1.1 5-tuples (BASELINE configs[1])"),
 }
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")
 
 
 def peaks():
@@ -45,111 +52,179 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per record of K1 from the committed ncu --set full capture of this workload (profiles/), or None."""
+    try:
+        return json.load(open(TRAFFIC_FILE)).get(workload)
+    except Exception:
+        return None
+
+
+def make_config(args, wl, world):
+    """The workload description both arms print (identical keys and values for the same command line)."""
+    return {"workload": wl["label"], "workload_key": args.workload, "flows": wl["n_keys"], "record_bytes": REC,
+            "records_per_step_per_gpu": args.batch, "max_entries": wl["max_entries"],
+            "table_slots": 1 << (4 * wl["max_entries"] // 3 - 1).bit_length(),
+            "full_cut": "off (FA_F_NO_FULL_CUT)" if (wl["no_full_cut"] or world > 1) else "on (Accounter maxEntries rule)",
+            "l2_policy": f"inputs larger than L2 ({args.batch * REC / 1e6:.0f} MB per step)", "n_gpus": world}
+
+
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi samples with timestamps; only samples inside the timed window are kept."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.p = index, None
+        self.index, self.p, self.t0, self.t1 = index, None, None, None
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
+    def window_begin(self):
+        self.t0 = datetime.datetime.now()
+
+    def window_end(self):
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
         if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.p.terminate()
         try:
             out, _ = self.p.communicate(timeout=5)
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, near, reasons = [], [], [], set()
         for ln in out.strip().splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                s, m = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            inside = self.t0 is None or (self.t0 <= ts <= self.t1)
+            if not inside:
+                if self.t0 is not None and abs((ts - self.t0).total_seconds()) < 0.5:
+                    near.append(s)
+                continue
+            sm.append(s); mx.append(m)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        if not sm and near:                              # window shorter than the sampling period
+            sm = near
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window_ms": None if self.t0 is None else (self.t1 - self.t0).total_seconds() * 1e3,
+                "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------- CPU legs (oracle = checker / baseline)
-def host_sample(wl, n, first=0):
-    import netobserv_ebpf_agent_b200 as fa
-    p = fa.GenParams(seed=wl["seed"], n_keys=wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0)
-    return fa.gen_records_host(p, first, n)
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def oracle_gen(wl):
+    import oracle_lib as O
+    return O.Gen(wl["seed"], wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0)
 
 
 def cpu_baseline_port(wl, sample_records, passes=4):
     """Single-thread CPU restatement of pkg/flow.Accounter (one goroutine in the reference)."""
     import oracle_lib as O
-    sample = host_sample(wl, sample_records)
+    g = oracle_gen(wl)
+    sample = g.records(0, sample_records, threads=min(16, host_threads()))
     acc = O.Accounter(1 << 26)
     t0 = time.perf_counter()
-    for _ in range(passes):                          # ~10 s of CPU work: the same 2^25-record slice folded 4 times
+    for _ in range(passes):                          # ~10-20 s of CPU work: the same slice folded `passes` times
         acc.account(sample)
     flows = len(acc)
     acc.evict()
     dt = time.perf_counter() - t0
-    acc.close()
+    acc.close(); g.close()
     return {"value": passes * sample_records / dt / 1e6, "unit": "Mpkts/s", "cores": 1, "kind": "port",
             "sample": f"{passes} x {sample_records} records of the same stream, {flows} flows, incl. the final evict "
                       f"(CPU restatement of pkg/flow.Accounter; Go toolchain unavailable)", "seconds": dt}
 
 
 def run_reference(args, wl):
-    """--impl reference: the reference's CPU path for this step (Accounter restatement), all host threads."""
+    """--impl reference: the reference's CPU path for this step (Accounter restatement), all host threads.  Loads
+    only oracle/ — never the product library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:                                    # under torchrun only rank 0 runs the CPU arm
         return
     import oracle_lib as O
-    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    avail = host_threads()
     n = args.ref_sample
-    sample = host_sample(wl, n)
-    buf = np.ascontiguousarray(sample).view(np.uint8).reshape(-1)
-    out = np.zeros((min(n, wl["n_keys"]) + 1) * REC, dtype=np.uint8)
+    g = oracle_gen(wl)
+    ring = [g.records(i * n, n, threads=avail) for i in range(2)]          # inputs resident in host memory, like HBM for the GPU arm
 
-    def run(threads):
-        return O.lib().oracle_accounter_sharded_run(O._p(buf), n, threads, O._p(out), len(out) // REC)
-    # "all the host threads it can use": containers often expose more CPUs than they may run on, so pick the
-    # thread count that is actually fastest on this box (tried once each, outside the timed region)
+    # "all the host threads it can use": containers often expose more CPUs than they may run on, so pick the thread
+    # count that is actually fastest on this box (tried once each, outside the timed region)
     best, cores = None, avail
-    run(avail)                                       # touch the sample / warm the allocator first
-    for tcount in sorted({avail, max(1, avail // 2), max(1, avail // 4), max(1, avail // 8), min(avail, 16), min(avail, 8)}, reverse=True):
-        t0 = time.perf_counter(); run(tcount); dt = time.perf_counter() - t0
+    for tcount in sorted({avail, max(1, avail // 2), max(1, avail // 4), min(avail, 16), min(avail, 8)}, reverse=True):
+        acc = O.ShardedAccounter(tcount)
+        acc.account(ring[0])                                               # builds the maps
+        t0 = time.perf_counter(); acc.account(ring[1]); dt = time.perf_counter() - t0
+        acc.close()
         if best is None or dt < best:
             best, cores = dt, tcount
-
-    def step():
-        return run(cores)
-    for _ in range(args.warmup):
-        step()
+    acc = O.ShardedAccounter(cores)                                        # persistent maps: steady state like the GPU arm
+    for i in range(max(args.warmup, 1)):
+        acc.account(ring[i % 2])
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        flows = step()
+    for i in range(args.steps):
+        acc.account(ring[i % 2])
     dt = time.perf_counter() - t0
+    flows = len(acc)
+    acc.close(); g.close()
     v = n * args.steps / dt / 1e6
     line = {"impl": "reference", "metric": "Mpkts/s aggregated", "value": v, "unit": "Mpkts/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64/u32 integer", "data": "synthetic",
-            "config": {"workload": wl["label"], "records_per_step": n, "flows": int(flows)},
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64/u32 integer (add/or/min/max); no floating point",
+            "data": "synthetic", "config": make_config(args, wl, world),
             "cpu_baseline": {"value": v, "unit": "Mpkts/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} records/step; key-sharded over {cores} threads, each a private Accounter "
-                                       "(CPU restatement of pkg/flow.Accounter; Go toolchain unavailable)"},
+                             "sample": f"{n} records per step of the same stream ({flows} flows live), key-sharded over "
+                                       f"{cores} threads, each a private persistent Accounter map (CPU restatement of "
+                                       "pkg/flow.Accounter; Go toolchain unavailable)"},
             "e2e": {"value": v, "unit": "Mpkts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def record_order(r):
+    """Permutation that sorts (n,144) records by two independent 64-bit hashes of their 40-byte keys."""
+    k = np.ascontiguousarray(r[:, :40]).view("<u8")
+    c = np.array([0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0xD6E8FEB86659FD93, 0xFF51AFD7ED558CCD], dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        h1 = (k * c).sum(axis=1, dtype=np.uint64)
+        h2 = ((k ^ (k >> np.uint64(29))) * c[::-1]).sum(axis=1, dtype=np.uint64)
+    return np.lexsort((h2, h1))
+
+
+def oracle_flows(wl, first, n, chunk=1 << 22):
+    """The oracle's flows for records [first, first+n) of the workload stream, sorted like record_order()."""
+    import oracle_lib as O
+    threads = min(host_threads(), 32)
+    g = oracle_gen(wl)
+    acc = O.ShardedAccounter(threads)
+    buf = np.empty(chunk * REC, dtype=np.uint8)
+    done = 0
+    while done < n:
+        c = min(chunk, n - done)
+        acc.account(g.records(first + done, c, threads=threads, out=buf[: c * REC]))
+        done += c
+    out = acc.evict()
+    acc.close(); g.close()
+    return out[record_order(out)]
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -175,36 +250,46 @@ def run_ours(args, wl):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    if world > 1:
-        args.max_batch = B          # one route -> exchange -> fold round per step: amortises the host-side syncs
-    eng = fa.FlowAggEngine(args.max_entries, device=local, max_batch=args.max_batch, cuda_stream=stream.cuda_stream,
-                           flags=fa.FA_F_NO_FULL_CUT if (world > 1 and args.exchange == "peer") else 0)
+    max_batch = args.max_batch if world == 1 else args.mgpu_round
+    no_cut = wl["no_full_cut"] or world > 1          # N>1: the owner table is a plain map behind the exchange
+    eng = fa.FlowAggEngine(wl["max_entries"], device=local, max_batch=max_batch, cuda_stream=stream.cuda_stream,
+                           flags=fa.FA_F_NO_FULL_CUT if no_cut else 0)
     # one key universe for the whole job; every rank generates its own slice of the record stream
     gp = fa.GenParams(seed=wl["seed"], n_keys=wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100,
                       t0_ns=1_000_000, varying_desc=0)
     batches = []
     for i in range(ring):
         t = torch.empty(B * REC, dtype=torch.uint8, device=dev)
-        eng.gen_records(gp, (i * world + rank) * B, B, t)
+        for off in range(0, B, 1 << 24):                                   # generator launches of <= 2^24 records
+            c = min(1 << 24, B - off)
+            eng.gen_records(gp, (i * world + rank) * B + off, c, t[off * REC:])
         batches.append(t)
     eng.sync()
 
+    agg = None
     if world > 1:
         from netobserv_ebpf_agent_b200.sharded import PeerShardedAggregator, ShardedAggregator
         if args.exchange == "peer":
             # local combine (K1+K2) -> K3 fused with the exchange (peer stores over NVLink) -> K1 on the owner
-            agg = PeerShardedAggregator(eng, args.max_batch, dev)
+            agg = PeerShardedAggregator(eng, max_batch, dev)
         else:
             # local combine (K1+K2) -> K3 route -> NCCL all-to-all -> K1 on the owner
-            agg = ShardedAggregator(eng, args.max_batch, dev, combine=not args.no_combine)
+            agg = ShardedAggregator(eng, max_batch, dev, combine=not args.no_combine)
 
-    def step(i):
-        src = batches[i % ring]
+    def ingest_dev(ptr, n):
         if world == 1:
-            rc, took = eng.ingest(src.data_ptr(), B)
-            assert rc == 0 and took == B, (rc, took)
+            rc, took = eng.ingest(ptr, n)
+            assert rc == 0 and took == n, (rc, took)
         else:
-            agg.ingest(src, B)
+            agg.ingest(ptr, n)
+
+    def evict_dev():
+        """Lookup-and-delete everything into device memory -> (tensor, flows); re-uses the first input batch when it fits."""
+        nfl = eng.live_flows()
+        buf = batches[0] if nfl <= B else torch.empty(nfl * REC, dtype=torch.uint8, device=dev)
+        got = eng.evict_into(buf.data_ptr(), max(nfl, 1)) if nfl else 0
+        assert got == nfl, (got, nfl)
+        return buf, nfl
 
     def finish():                                    # N>1: drain + exchange the batch still in a scratch table
         if world > 1:
@@ -216,7 +301,7 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
-        step(i)
+        ingest_dev(batches[i % ring].data_ptr(), B)
     finish()
     barrier()
 
@@ -232,15 +317,18 @@ def run_ours(args, wl):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)                              # nvidia-smi needs a moment before its first sample
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    sampler.window_begin()
     ev[0].record()
     for i in range(args.steps):
-        step(args.warmup + i)
+        ingest_dev(batches[(args.warmup + i) % ring].data_ptr(), B)
         if i == args.steps - 1:
             finish()
         ev[i + 1].record()
     barrier()
+    sampler.window_end()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
@@ -252,6 +340,57 @@ def run_ours(args, wl):
     value = world * B * args.steps / (total_ms / 1e3) / 1e6
     launches = st1["kernel_launches"] - st0["kernel_launches"]
     flows = eng.live_flows()
+    nvlink = agg.exchange_stats() if (world > 1 and hasattr(agg, "exchange_stats")) else None
+
+    # ---------------------------------------------------------------- parity: the engine against the CPU oracle
+    # Fresh state, then records [V0, V0+V) of the same stream through the same engine / aggregator, evict, compare
+    # all flows bit for bit with the oracle's fold of the same records (rank 0; N>1: the ranks' evictions concatenated).
+    parity = None
+    if not args.no_verify:
+        V = args.verify_records - args.verify_records % world
+        V0 = 1 << 40                                 # far beyond anything the timed loop consumed
+        finish()
+        evict_dev()                                  # discard the timed loop's flows
+        mine = V // world
+        done = 0
+        while done < mine:                           # regenerate into the (now free) input ring, chunk by chunk
+            c = min(mine - done, 1 << 24, B)
+            eng.gen_records(gp, V0 + rank * mine + done, c, batches[-1])
+            ingest_dev(batches[-1].data_ptr(), c)
+            finish()
+            torch.cuda.synchronize()
+            done += c
+        out_dev, nfl = evict_dev()
+        if world > 1:                                # concatenate on rank 0 (padded all_gather of byte tensors)
+            cnt = torch.tensor([nfl], device=dev, dtype=torch.int64)
+            cnts = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(cnts, cnt)
+            cnts = [int(c.item()) for c in cnts]
+            pad = torch.zeros(max(cnts) * REC, dtype=torch.uint8, device=dev)
+            pad[: nfl * REC] = out_dev[: nfl * REC]
+            parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad, parts, dst=0)
+            if rank == 0:
+                ours = np.concatenate([p[: c * REC].cpu().numpy().reshape(-1, REC) for p, c in zip(parts, cnts)])
+        else:
+            ours = out_dev[: nfl * REC].cpu().numpy().reshape(-1, REC)
+        if rank == 0:
+            t0 = time.perf_counter()
+            want = oracle_flows(wl, V0, V)
+            ours = ours[record_order(ours)]
+            same = ours.shape == want.shape and bool(np.array_equal(ours, want))
+            parity = {"parity_checked": int(len(want)) if same else 0, "parity_ok": same, "records": V,
+                      "flows_engine": int(len(ours)), "flows_oracle": int(len(want)),
+                      "seconds": round(time.perf_counter() - t0, 2),
+                      "how": "fresh cache, records [2^40, 2^40+V) of the workload stream through the same engine"
+                             + ("" if world == 1 else f" (sharded over {world} GPUs, evictions concatenated)") +
+                             "; every flow record compared bit for bit with the CPU oracle's fold of the same records"}
+            if not same:
+                nbad = -1
+                if ours.shape == want.shape:
+                    nbad = int((ours != want).any(axis=1).sum())
+                parity["mismatching_flows"] = nbad
+        barrier()
 
     # ---------------------------------------------------------------- end-to-end through the C ABI, host buffers
     # Every rank feeds its own slice from pinned host memory over its own PCIe link (N > 1: through the sharded
@@ -261,21 +400,20 @@ def run_ours(args, wl):
     e2e = None
     host_ok = world == 1 or args.exchange == "peer"       # the NCCL variant's scratch streams are device-input only
     if not args.no_e2e and host_ok:
-        Be = min(args.e2e_batch, args.max_batch)
+        Be = min(args.e2e_batch, max_batch, B)
         prep_err = None
         hring, out_host = [], None
         try:
-            if world == 1:
-                eng.evict_into(batches[0].data_ptr(), B)      # reset the cache (flows <= B)
-            for i in range(min(4, ring + 1)):
+            finish()
+            evict_dev()                                    # reset the cache
+            for i in range(4):
                 h = torch.empty(Be * REC, dtype=torch.uint8).pin_memory()
-                d = torch.empty(Be * REC, dtype=torch.uint8, device=dev)
-                eng.gen_records(gp, ((ring + i) * world + rank) * B, Be, d)
+                d = batches[-1][: Be * REC]
+                eng.gen_records(gp, (1 << 41) + (i * world + rank) * Be, Be, d)
                 eng.sync()
                 h.copy_(d)
                 hring.append(h)
-                del d
-            out_host = torch.empty(min(args.max_entries, wl["n_keys"]) * REC, dtype=torch.uint8).pin_memory()
+            out_host = torch.empty(min(wl["max_entries"], wl["n_keys"]) * REC, dtype=torch.uint8).pin_memory()
         except Exception as ex:                                # noqa: BLE001 - reported in the JSON line
             prep_err = repr(ex)
         ok = torch.tensor([0 if prep_err else 1], device=dev, dtype=torch.int32)
@@ -320,33 +458,41 @@ def run_ours(args, wl):
     if rank == 0:
         peak, peak_src = peaks()
         kern_ms = statistics.mean(step_ms)
+        launches_per_step = max(1, (B + max_batch - 1) // max_batch)
+        per_launch = min(B, max_batch)
         achieved = B * REC / (kern_ms / 1e3) / 1e9
+        tr = ncu_traffic(args.workload) if world == 1 else None
+        cfg = make_config(args, wl, world)
+        cfg.update({"records_per_launch": per_launch, "live_flows": int(flows), "input_ring_batches": ring,
+                    "timed_region_ms": total_ms,
+                    "parallelism": "1 GPU" if world == 1 else
+                    f"hash-sharded x{world}: " + ("" if args.no_combine else "per-round local combine (K1+K2) -> ") +
+                    ("K3 fused with the exchange (peer stores over NVLink, device-side counts)" if args.exchange == "peer"
+                     else "K3 route -> NCCL all-to-all") + " -> K1 on the owner"})
+        if nvlink:
+            cfg["nvlink"] = nvlink
         line = {"metric": "Mpkts/s aggregated", "value": value, "unit": "Mpkts/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u64/u32 integer (add/or/min/max); no floating point", "data": "synthetic",
-                "config": {"workload": wl["label"], "records_per_step_per_gpu": B, "record_bytes": REC,
-                           "max_entries": args.max_entries, "max_batch": args.max_batch, "live_flows": int(flows),
-                           "input_ring_batches": ring, "l2_policy": f"inputs larger than L2 ({B * REC / 1e6:.0f} MB per step, "
-                           f"{ring} distinct batches cycled)",
-                           "parallelism": "1 GPU" if world == 1 else
-                           f"hash-sharded x{world}: " + ("" if args.no_combine else "per-batch local combine (K1+K2) -> ") +
-                           ("K3 fused with the exchange (peer stores over NVLink, device-side counts)" if args.exchange == "peer"
-                            else "K3 route -> NCCL all-to-all") + " -> K1 on the owner",
-                           "exchanged_records_per_step_rank0": (agg.exchanged_records // (args.steps + args.warmup)) if world > 1 else None},
+                "config": cfg,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": (NCU_DRAM_BYTES_PER_RECORD[args.workload] * min(B, args.max_batch)
-                                         if args.workload in NCU_DRAM_BYTES_PER_RECORD and world == 1 else None),
-                             "algorithmic_bytes_per_launch": REC * min(B, args.max_batch), "peak_source": peak_src,
-                             "kernel": "fa::aggregate_kernel (K1); 144 algorithmic bytes per record; duration = CUDA-event "
-                                       "time of one step = %d K1 launch(es) + 2 early-exit re-fold kernels each; traffic = "
-                                       "ncu dram bytes/record x records per launch" % max(1, B // min(B, args.max_batch))},
+                             "traffic": (tr["dram_bytes_per_record"] * per_launch) if tr else None,
+                             "traffic_source": tr["source"] if tr else None,
+                             "algorithmic_bytes_per_launch": REC * per_launch, "peak_source": peak_src,
+                             "kernel": "fa::aggregate (K1); 144 algorithmic bytes per record; duration = CUDA-event time of "
+                                       "one step / %d K1 launches (each followed by 2 early-exit re-fold kernels); traffic = "
+                                       "ncu dram bytes per record x records per launch" % launches_per_step},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "order_fixups": st1["order_fixups"] - st0["order_fixups"], "spills": st1["spills"]}
+        if parity:
+            line.update(parity)
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_port(wl, args.cpu_sample)
         print(json.dumps(line), flush=True)
+    if agg is not None and hasattr(agg, "close"):
+        agg.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -355,19 +501,21 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="zipf1m", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=1 << 24, help="records per step per GPU (2^24 x 60 steps ~ 1e9)")
-    ap.add_argument("--max-batch", type=int, default=1 << 24, help="records per K1 launch")
-    ap.add_argument("--max-entries", type=int, default=1 << 26,
-                    help="flow-cache capacity; >= flows + 3 x max_batch keeps fa_ingest on its zero-sync path")
-    ap.add_argument("--ring", type=int, default=8, help="distinct pre-generated input batches cycled through")
+    ap.add_argument("--workload", default="zipf10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=1 << 27,
+                    help="records per step per GPU (2^27 x 144 B = 19.3 GB; 20 steps = a timed region of >= 200 ms)")
+    ap.add_argument("--max-batch", type=int, default=1 << 22, help="records per K1 launch (N = 1)")
+    ap.add_argument("--mgpu-round", type=int, default=1 << 24, help="N>1: records per combine -> exchange -> fold round")
+    ap.add_argument("--ring", type=int, default=2, help="distinct pre-generated input batches cycled through")
     ap.add_argument("--e2e-batch", type=int, default=1 << 22)
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-sample", type=int, default=1 << 25)
     ap.add_argument("--ref-sample", type=int, default=1 << 24)
+    ap.add_argument("--verify-records", type=int, default=1 << 25)
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-combine", action="store_true", help="N>1: route raw records instead of per-batch partial flows")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

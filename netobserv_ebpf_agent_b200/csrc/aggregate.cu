@@ -585,10 +585,8 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 }
                 if (my_slot != kResSpill) {
                     reduce_to_hot(t, my_slot, t_bytes, t_packets, t_ns, t_end, t_flags, floor_ns, seen);
-                } else {                                           // table physically full: spill, never drop silently
-                    const unsigned long long kk = atomicAdd(&ctr->scratch[2], 1ull);
-                    spill_idx[kk] = first + my_ridx;
-                    my_spills++;
+                } else {                                           // table physically full (FA_F_NO_FULL_CUT mis-sizing): counted
+                    my_spills++;                                   // in fa_stats.spills, like HASHMAP_FAIL_CREATE_FLOW (flows.c:285)
                 }
             }
             FA_PROF_MARK(5);                                       // totals + reductions
@@ -1075,9 +1073,7 @@ aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint6
             }
             if (my_slot != kResSpill) {
                 reduce_to_hot(t, my_slot, u64_of(r3.z, r3.w), r4.x, v_ns, v_end, r4.y >> 16, floor_ns, seen);
-            } else {                                               // table physically full: spill, never drop silently
-                const unsigned long long kk = atomicAdd(&ctr->scratch[2], 1ull);
-                spill_idx[kk] = first + lane;
+            } else {                                               // table physically full: counted in fa_stats.spills
                 my_spills++;
             }
         }

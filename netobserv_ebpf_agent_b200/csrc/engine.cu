@@ -243,8 +243,15 @@ int ingest_chunk_accounter(fa_engine* e, const uint8_t* d_recs, uint32_t n, uint
         *consumed = n;
         return FA_OK;
     }
-    if (e->live_known + e->unsynced_records + n > M) {
-        int rc = sync_counters(e);                     // exact live count
+    // Launches still in flight may add up to unsynced_records flows.  When that bound does not leave room for this
+    // chunk, wait for the OLDEST launch's live-count read-back only (the stream keeps working on the younger ones),
+    // and drain the stream only when nothing is left in flight.
+    while (e->live_known + e->unsynced_records + n > M && e->ring_head != e->ring_tail) {
+        CU(cudaEventSynchronize(e->ev_live[e->ring_head % fa_engine::kLiveRing]));
+        retire_completed(e);
+    }
+    if (e->live_known + e->unsynced_records + n > M && e->unsynced_records) {
+        int rc = sync_counters(e);                     // exact live count (feature folds do not use the ring)
         if (rc) return rc;
     }
     if (e->live_known + e->unsynced_records + n <= M) { // cannot overflow: fast path
@@ -339,7 +346,16 @@ int ingest_host(fa_engine* e, const uint8_t* h_recs, size_t n, size_t* consumed,
     size_t done = 0;
     int rc = FA_OK;
     while (done < n) {
-        const uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
+        uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
+        if (e->cfg.mode == FA_MODE_ACCOUNTER && !(e->cfg.flags & FA_F_NO_FULL_CUT)) {
+            // A cache that is about to fill cuts the chunk after roughly `room` new keys: stage a window proportional
+            // to the room left, so that a "full" return does not leave most of a copied chunk unused (the caller
+            // hands the rest in again after its eviction).
+            retire_completed(e);
+            const uint64_t used = e->live_known + e->unsynced_records;
+            const uint64_t room = e->cfg.max_entries > used ? e->cfg.max_entries - used : 0;
+            if (room < c) c = (uint32_t)std::min<uint64_t>(c, std::max<uint64_t>(4096, 4 * room));
+        }
         const int sidx = e->stage_cur; e->stage_cur ^= 1;
         CU(cudaEventSynchronize(e->ev_stage_free[sidx]));            // previous consumer of this stage is done
         const size_t bytes = (size_t)c * fa::kRecBytes;
@@ -420,7 +436,7 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
 
     // table: load factor <= 0.75 at max_entries
-    uint64_t want = cfg->max_entries + cfg->max_entries / 3 + 1;
+    uint64_t want = (4 * cfg->max_entries + 2) / 3;          // 0.75 x 2^k entries get exactly 2^k slots
     uint64_t slots = 1024; while (slots < want) slots <<= 1;
     e->slots = slots;
     e->table.mask = slots - 1;

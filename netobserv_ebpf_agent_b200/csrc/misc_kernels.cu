@@ -99,10 +99,14 @@ __global__ void cut_select_kernel(const uint32_t* __restrict__ bitmap, uint32_t 
 int launch_full_cut(const uint4* recs, uint32_t n, const Table& table, unsigned long long live,
                     unsigned long long max_entries, uint32_t* idx_set, uint32_t set_slots, uint32_t* bitmap,
                     uint32_t* cut_out, int sm_count, cudaStream_t st) {
-    cudaMemsetAsync(idx_set, 0xFF, (size_t)set_slots * 4, st);
+    // the index set is sized (and cleared) by the window, not by max_batch: a small cache cuts every few thousand records
+    uint32_t use = 1024;
+    while (use < set_slots && (uint64_t)use < 2ull * n) use <<= 1;
+    cudaMemsetAsync(idx_set, 0xFF, (size_t)use * 4, st);
     cudaMemsetAsync(bitmap, 0, ((size_t)n + 31) / 32 * 4, st);
-    cut_scan_kernel<<<sm_count * 8, 256, 0, st>>>(recs, n, table, idx_set, set_slots - 1);
-    cut_mark_kernel<<<sm_count * 8, 256, 0, st>>>(idx_set, set_slots, bitmap);
+    const int g_scan = (int)min((uint32_t)(sm_count * 8), (n + 255u) / 256u), g_mark = (int)min((uint32_t)(sm_count * 8), (use + 255u) / 256u);
+    cut_scan_kernel<<<g_scan, 256, 0, st>>>(recs, n, table, idx_set, use - 1);
+    cut_mark_kernel<<<g_mark, 256, 0, st>>>(idx_set, use, bitmap);
     const unsigned long long room = max_entries > live ? max_entries - live : 0ull;
     cut_select_kernel<<<1, 1024, 0, st>>>(bitmap, n, room, cut_out);
     return 3;
@@ -233,6 +237,7 @@ __global__ void route_scatter_kernel(const uint4* __restrict__ recs, uint32_t n,
             for (int w = 0; w < kRouteThreads / 32; w++) t += wcount[w][threadIdx.x];
             cursor[threadIdx.x] += t;
         }
+        __syncthreads();                                  // wcount / cursor are re-used by the next round
         if (valid) {
             const uint4* R = recs + (size_t)i * kRecChunks;
             uint4* O = out + (size_t)dst * kRecChunks;
@@ -299,6 +304,7 @@ __global__ void route_peer_kernel(const uint4* __restrict__ recs, const unsigned
             for (int w = 0; w < kRouteThreads / 32; w++) t += wcount[w][threadIdx.x];
             cursor[threadIdx.x] += t;
         }
+        __syncthreads();                                  // wcount / cursor are re-used by the next round
         if (valid) {
             if (dst < cap) {
                 const uint4* R = recs + (size_t)i * kRecChunks;

@@ -115,6 +115,14 @@ public:
             if (rec) {
                 batch_.push_back(*rec);
                 if (batch_.size() == batchCap_) flush(out, nextTick);
+                // Go's select keeps servicing evictTick.C under sustained input (account.go:62-81): do not let a queue
+                // that is never empty starve the timeout eviction
+                if (std::chrono::steady_clock::now() >= nextTick) {
+                    flush(out, nextTick);
+                    nextTick = std::chrono::steady_clock::now() + evictTimeout_;
+                    size_t live = 0; fa_live_flows(eng_, &live);
+                    if (live != 0) evict(out, "timeout", false);
+                }
             } else if (closed) {                                  // account.go:73-80
                 flush(out, nextTick);
                 evict(out, "closing", true);

@@ -361,6 +361,69 @@ size_t oracle_accounter_sharded_run(const uint8_t* wire, size_t n, int n_threads
     return total;
 }
 
+/* persistent shards: same three passes, the maps survive the call */
+struct oracle_sharded { int T; amap* maps; };
+oracle_sharded* oracle_sharded_new(int n_threads) {
+    oracle_sharded* s = (oracle_sharded*)calloc(1, sizeof(*s));
+    s->T = n_threads < 1 ? 1 : n_threads;
+    s->maps = (amap*)calloc((size_t)s->T, sizeof(amap));
+    for (int t = 0; t < s->T; t++) amap_init(&s->maps[t], 1024);
+    return s;
+}
+void oracle_sharded_free(oracle_sharded* s) { if (s) { for (int t = 0; t < s->T; t++) amap_free(&s->maps[t]); free(s->maps); free(s); } }
+size_t oracle_sharded_len(const oracle_sharded* s) { size_t n = 0; for (int t = 0; t < s->T; t++) n += s->maps[t].n; return n; }
+void oracle_sharded_account(oracle_sharded* s, const uint8_t* wire, size_t n) {
+    const size_t T = (size_t)s->T;
+    uint16_t* owner = (uint16_t*)malloc((n ? n : 1) * sizeof(uint16_t));
+    uint32_t* list = (uint32_t*)malloc((n ? n : 1) * sizeof(uint32_t));
+    size_t* hist = (size_t*)calloc(T * T + 1, sizeof(size_t));
+    size_t* start = (size_t*)calloc(T + 1, sizeof(size_t));
+#pragma omp parallel num_threads(s->T)
+    {
+#ifdef _OPENMP
+        const size_t t = (size_t)omp_get_thread_num();
+#else
+        const size_t t = 0;
+#endif
+        const size_t lo = n * t / T, hi = n * (t + 1) / T;
+        for (size_t i = lo; i < hi; i++) {
+            const uint16_t o = (uint16_t)(oracle_owner_hash(wire + i * OR_REC_SIZE) % T);
+            owner[i] = o; hist[t * T + o]++;
+        }
+#pragma omp barrier
+#pragma omp single
+        {
+            size_t run = 0;
+            for (size_t o = 0; o < T; o++) {
+                start[o] = run;
+                for (size_t c = 0; c < T; c++) { const size_t v = hist[c * T + o]; hist[c * T + o] = run; run += v; }
+            }
+            start[T] = run;
+        }
+        for (size_t i = lo; i < hi; i++) list[hist[t * T + owner[i]]++] = (uint32_t)i;
+#pragma omp barrier
+        uint8_t rec[OR_REC_SIZE];
+        for (size_t k = start[t]; k < start[t + 1]; k++) {
+            oracle_read_from(wire + (size_t)list[k] * OR_REC_SIZE, rec);
+            amap_account(&s->maps[t], rec);
+        }
+    }
+    free(owner); free(list); free(hist); free(start);
+}
+size_t oracle_sharded_evict(oracle_sharded* s, uint8_t* out, size_t cap) {
+    size_t total = 0;
+    for (int t = 0; t < s->T; t++) {
+        amap* m = &s->maps[t];
+        if (out && total < cap) {
+            const size_t k = m->n < cap - total ? m->n : cap - total;
+            memcpy(out + total * OR_REC_SIZE, m->recs, k * OR_REC_SIZE);
+        }
+        total += m->n;
+        amap_clear(m);
+    }
+    return total;
+}
+
 /* -------------------------------------------------------------- flowmap */
 struct oracle_flowmap { fmap m; };
 oracle_flowmap* oracle_flowmap_new(void) { oracle_flowmap* m = (oracle_flowmap*)calloc(1, sizeof(*m)); fmap_init(&m->m, 1024); return m; }

@@ -88,6 +88,24 @@ size_t oracle_accounter_pop_generation(oracle_accounter* a, uint8_t* out_recs, s
 size_t oracle_accounter_sharded_run(const uint8_t* wire, size_t n, int n_threads,
                                     uint8_t* out_recs, size_t cap);
 
+/* Persistent variant for bench.py --impl reference: the T private Accounters live across calls (steady state, like
+ * the GPU arm's flow table), every call folds one batch. */
+typedef struct oracle_sharded oracle_sharded;
+oracle_sharded* oracle_sharded_new(int n_threads);
+void   oracle_sharded_free(oracle_sharded* s);
+void   oracle_sharded_account(oracle_sharded* s, const uint8_t* wire, size_t n);
+size_t oracle_sharded_len(const oracle_sharded* s);
+size_t oracle_sharded_evict(oracle_sharded* s, uint8_t* out_recs, size_t cap);   /* lookup-and-delete of every shard */
+
+/* --- synthetic stream (gen.c): CPU restatement of the workload generator, so that the CPU arms and the in-bench
+ * parity check never load the product library */
+typedef struct oracle_gen oracle_gen;
+oracle_gen* oracle_gen_new(uint64_t seed, uint64_t n_keys, uint32_t dist, uint32_t zipf_s_milli, uint64_t t0_ns,
+                           uint32_t varying_desc);
+void   oracle_gen_free(oracle_gen* g);
+void   oracle_gen_records(const oracle_gen* g, uint64_t first_index, size_t n, uint8_t* out, int n_threads);
+void   oracle_gen_key(const oracle_gen* g, uint64_t rank, uint8_t* key40);
+
 /* --- Map path with feature folds: LookupAndDeleteMap's merged view
  * (pkg/tracer/tracer.go:1063-1187) under the record-by-record fold contract
  * (SURVEY.md §8 a12'). */

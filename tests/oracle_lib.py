@@ -17,7 +17,7 @@ REC, ID, MET, DNS, ADD, DNSREC, ADDREC = 144, 40, 104, 64, 32, 104, 72
 
 
 def build(force=False):
-    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle.c", "oracle.h", "Makefile")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle.c", "gen.c", "oracle.h", "Makefile")]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return LIB_PATH
@@ -77,6 +77,15 @@ def lib():
         "oracle_kmap_spilled": (sz, [vp, _u8p, sz]),
         "oracle_kmap_counter_fail_create": (u64, [vp]),
         "oracle_kmap_counter_intf_missed": (u64, [vp]),
+        "oracle_sharded_new": (vp, [C.c_int]),
+        "oracle_sharded_free": (None, [vp]),
+        "oracle_sharded_account": (None, [vp, _u8p, sz]),
+        "oracle_sharded_len": (sz, [vp]),
+        "oracle_sharded_evict": (sz, [vp, _u8p, sz]),
+        "oracle_gen_new": (vp, [u64, u64, u32, u32, u64, u32]),
+        "oracle_gen_free": (None, [vp]),
+        "oracle_gen_records": (None, [vp, u64, sz, _u8p, C.c_int]),
+        "oracle_gen_key": (None, [vp, u64, _u8p]),
         "oracle_key_premix": (u64, [_u8p]),
         "oracle_slot_hash": (u64, [_u8p]),
         "oracle_owner_hash": (u64, [_u8p]),
@@ -138,6 +147,58 @@ def sort_perm(raw, width=REC):
     if len(r) == 0:
         return np.zeros(0, dtype=np.int64)
     return np.lexsort(r[:, :ID].T[::-1])
+
+
+class Gen:
+    """CPU restatement of the synthetic stream (oracle/gen.c): the workload without the product library."""
+
+    def __init__(self, seed, n_keys, dist=1, zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0):
+        self.h = lib().oracle_gen_new(seed, n_keys, dist, zipf_s_milli, t0_ns, varying_desc)
+
+    def records(self, first, n, threads=1, out=None):
+        if out is None:
+            out = np.empty(n * REC, dtype=np.uint8)
+        lib().oracle_gen_records(self.h, first, n, _p(out), threads)
+        return out.reshape(-1, REC)
+
+    def key(self, rank):
+        k = np.zeros(ID, dtype=np.uint8)
+        lib().oracle_gen_key(self.h, rank, _p(k))
+        return k
+
+    def close(self):
+        if self.h:
+            lib().oracle_gen_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class ShardedAccounter:
+    """T private Accounters keyed by owner hash, persistent across batches (bench.py --impl reference)."""
+
+    def __init__(self, threads):
+        self.h = lib().oracle_sharded_new(threads)
+
+    def account(self, recs):
+        b = as_bytes(recs)
+        lib().oracle_sharded_account(self.h, _p(b), b.size // REC)
+
+    def __len__(self):
+        return lib().oracle_sharded_len(self.h)
+
+    def evict(self):
+        n = len(self)
+        out = np.zeros(max(n, 1) * REC, dtype=np.uint8)
+        got = lib().oracle_sharded_evict(self.h, _p(out), n)
+        return out[: got * REC].reshape(-1, REC)
+
+    def close(self):
+        if self.h:
+            lib().oracle_sharded_free(self.h)
+            self.h = None
+
+    __del__ = close
 
 
 class Accounter:

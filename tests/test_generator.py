@@ -49,3 +49,25 @@ def test_slices_are_position_independent():
     b = np.concatenate([gen_host(seed=73, n=4_000, n_keys=1_000, dist=1, first=0),
                         gen_host(seed=73, n=6_000, n_keys=1_000, dist=1, first=4_000)])
     assert np.array_equal(a, b)
+
+
+def test_oracle_twin_matches_the_product_generator():
+    """oracle/gen.c (what the CPU arms and the in-bench parity check use) against the product's host generator."""
+    for seed, n_keys, dist, var in ((2, 1_000_000, 1, 0), (2, 10_000_000, 0, 0), (9, 777, 1, 1), (5, 3, 0, 1)):
+        g = O.Gen(seed, n_keys, dist=dist, varying_desc=var, t0_ns=55)
+        a = g.records(12_345, 20_000, threads=3)
+        b = gen_host(seed=seed, n=20_000, n_keys=n_keys, dist=dist, varying=var, first=12_345, t0=55)
+        assert np.array_equal(a, b)
+        g.close()
+
+
+def test_persistent_sharded_accounter_equals_the_sequential_one():
+    recs = gen_host(seed=75, n=60_000, n_keys=4_000, dist=1)
+    seq = O.Accounter(1 << 20)
+    seq.account(recs)
+    sh = O.ShardedAccounter(5)
+    sh.account(recs[:25_000]); sh.account(recs[25_000:])
+    assert len(sh) == len(seq)
+    assert np.array_equal(O.sort_records(sh.evict()), O.sort_records(seq.evict()))
+    assert len(sh) == 0
+    sh.close(); seq.close()

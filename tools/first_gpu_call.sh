@@ -9,7 +9,7 @@ echo "== 1. default GPU suite"; timeout 900 python -m pytest tests -x -q -m gpu 
 echo "== 2. KERNEL_MAP mode on the device (tests/test_gpu_kernel_map.py)"
 FA_EXPERIMENTAL_KERNEL_MAP=1 timeout 600 python -m pytest tests/test_gpu_kernel_map.py -x -q -m gpu > $OUT/kmap.log 2>&1; tail -3 $OUT/kmap.log
 echo "== 3. K1 variants: parity, then same-box perf (0 = default, 128 = 4-lane probes, 256 = K1w, 288 = K1w + L2 prefetch)"
-VARIANTS="0 256 4352 2304 768 128" REPS=1 WORKLOADS="zipf1m uniform10m" STEPS=20 bash tools/k1_variants_ab.sh > $OUT/k1_variants.log 2>&1; grep -E "==|Mpkts|passed|failed" $OUT/k1_variants.log | head -80
+VARIANTS="0 256 4352 2304 768 128" REPS=1 WORKLOADS="zipf1m zipf10m uniform10m" STEPS=20 bash tools/k1_variants_ab.sh > $OUT/k1_variants.log 2>&1; grep -E "==|Mpkts|passed|failed" $OUT/k1_variants.log | head -80
 echo "== 4. sketch / multi-engine paths with K1w"
 FA_K1_OPT=256 timeout 600 python -m pytest tests/test_gpu_sketch.py tests/test_gpu_features.py tests/test_gpu_host_cpp.py -x -q -m gpu > $OUT/k1w_other.log 2>&1; tail -2 $OUT/k1w_other.log
 echo "== 5. KERNEL_MAP throughput + e2e at N=1 (new bench code path)"
