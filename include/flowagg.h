@@ -271,6 +271,46 @@ int fa_hll_estimate(fa_engine* e, double* estimate);
 int fa_sketch_export(fa_engine* e, uint64_t* cms_out, size_t cms_words, uint8_t* hll_out, size_t hll_regs);
 int fa_sketch_reset(fa_engine* e);
 
+/* ----------------------------------------------- evicted flows -> protobuf (K8) */
+
+/* One row of the agent's interface table (ifaces.Registerer: ifindex -> {MAC -> name}, pkg/ifaces/registerer.go:153-190)
+ * with the UDN label NewIntfDirUdn would attach to that interface (pkg/model/record.go:168-185; "" = none). */
+typedef struct fa_iface_name {
+    uint32_t if_index;
+    uint8_t  mac[FA_MAC_LEN];
+    uint8_t  name_len;               /* <= 16 */
+    uint8_t  udn_len;                /* <= 64 */
+    char     name[16];
+    char     udn[64];
+} fa_iface_name;                     /* 92 bytes */
+
+#define FA_PB_WRAP_ENTRIES 0x1u      /* prefix every record with the pbflow.Records `entries` tag + length: the output (or any
+                                        run of whole records of it) is then a serialized pbflow.Records (gRPC exporter,
+                                        pkg/pbflow/proto.go:19-35); without it every record is one Kafka message value
+                                        (pkg/exporter/kafka_proto.go:49-60) */
+typedef struct fa_pb_params {
+    uint64_t now_unix_ns;            /* clock() at eviction  (pkg/flow/account.go:103) */
+    uint64_t mono_now_ns;            /* monoClock()          (account.go:104) */
+    uint8_t  agent_ip[FA_IP_LEN];    /* agent IP in 16-byte form (IPv4: ::ffff:a.b.c.d) */
+    uint32_t agent_ip_is_v4;         /* net.IP.To4() != nil */
+    uint32_t flags;                  /* FA_PB_* */
+    const fa_iface_name* ifaces;     /* host pointer, n_ifaces rows, copied by the call; NULL = every interface is "unknown" */
+    uint32_t n_ifaces;
+    uint32_t reserved;
+} fa_pb_params;
+
+/* Serialize n evicted flows (the outputs of fa_evict: records n x 144 B, and optionally dns n x 64 B, additional
+ * n x 32 B, present n bytes; host or device pointers) as pbflow.Record messages, fields in field-number order as
+ * protobuf-go writes them.  Replaces, batched: model.NewRecord (pkg/model/record.go:82-159: wall-clock times, interface
+ * list, DNS latency, RTT), pbflow.FlowToPB + proto.Marshal (pkg/pbflow/proto.go:39-149, proto/flow.proto:31-126) and
+ * getFlowKey (pkg/exporter/kafka_proto.go:37-47).
+ * out_bytes (host or device, out_cap bytes) receives the messages back to back; offsets (n + 1 u64, may be NULL) the
+ * start of each; keys_out (n x 32 B, may be NULL) the Kafka keys.  *out_len = bytes needed; FA_E_2BIG if > out_cap
+ * (nothing written).  Not produced (no such state in the engine): xlat, quic, network_events_metadata. */
+int fa_pb_encode(fa_engine* e, const void* records, const void* dns, const void* additional, const uint8_t* present,
+                 size_t n, const fa_pb_params* p, void* out_bytes, size_t out_cap, uint64_t* offsets, void* keys_out,
+                 size_t* out_len);
+
 /* Replaces: ReadGlobalCounter (pkg/tracer/tracer.go:1190-1226) + the metrics the
  * hot path increments (pkg/metrics/metrics.go:66-161). */
 int fa_get_stats(fa_engine* e, fa_stats* out);

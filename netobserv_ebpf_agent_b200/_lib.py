@@ -36,6 +36,20 @@ class Stats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
 
 
+class IfaceName(C.Structure):
+    _fields_ = [("if_index", C.c_uint32), ("mac", C.c_uint8 * 6), ("name_len", C.c_uint8), ("udn_len", C.c_uint8),
+                ("name", C.c_char * 16), ("udn", C.c_char * 64)]
+
+
+class PbParams(C.Structure):
+    _fields_ = [("now_unix_ns", C.c_uint64), ("mono_now_ns", C.c_uint64), ("agent_ip", C.c_uint8 * 16),
+                ("agent_ip_is_v4", C.c_uint32), ("flags", C.c_uint32), ("ifaces", C.POINTER(IfaceName)),
+                ("n_ifaces", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+FA_PB_WRAP_ENTRIES = 1
+
+
 class GenParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_keys", C.c_uint64), ("dist", C.c_uint32), ("zipf_s_milli", C.c_uint32),
                 ("t0_ns", C.c_uint64), ("varying_desc", C.c_uint32), ("reserved", C.c_uint32)]
@@ -67,6 +81,8 @@ SIGNATURES = {
     "fa_hll_estimate": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "fa_sketch_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "fa_sketch_reset": (C.c_int, [C.c_void_p]),
+    "fa_pb_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(PbParams),
+                               C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "fa_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "fa_sync": (C.c_int, [C.c_void_p]),
     "fa_owner_hash": (C.c_uint64, [C.c_void_p]),

@@ -654,463 +654,340 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
 }
 
 // ------------------------------------------------------------------------------------
-// K1w — warp-independent variant of K1 (experiment, FA_K1_OPT bit 8; not the measured default).
+// K1s — the streaming kernel: every warp runs its own software pipeline over 32-record slices.
 //
-// Same table protocol, cache, probe code and reductions as aggregate_kernel, but no team: every warp owns 32-record
-// sub-tiles (its own 4.6 KB TMA buffer + mbarrier), every record that misses the cache probes the table itself
-// (4 lanes per flow, 8 flows per round), and its totals stay in the owning lane's registers.  What goes away: the
-// tile-local election and duplicate fold (a path that runs at ~3 active lanes), the representative list, the
-// per-tile accumulators and both team barriers; what it costs: duplicates of an un-cached flow inside one tile probe
-// and reduce separately (commutative, so still exact).
+//   TMA (cp.async.bulk + mbarrier) stages the warp's next two slices (3 buffers of 4,608 B)
+//   front(s+1): one thread per record — hash; an exact 114-byte match against the warp's PRIVATE hot-flow cache folds
+//               the record on-chip with plain loads and stores (lanes that hit the same entry pre-reduce with
+//               match.any + redux: no shared-memory atomics anywhere); the identity lines of the records that missed
+//               are gathered with 16-byte cp.async copies (LDGSTS: 8 lanes per 128-byte line = one L1 wavefront per
+//               line, no registers, no wait) into the warp's line buffer
+//   back(s):    the gather of the PREVIOUS slice has landed meanwhile: one thread per record compares its line
+//               (XOR-swizzled, conflict-free) with its record, settled flows at their home slot reduce straight away
+//               (three fire-and-forget reductions); a home slot held by another flow looks one slot further; inserts,
+//               chains and in-flight publishes go to the 8-lane general probe shared with K1.
+// Nothing is shared between warps (no barriers, no elections, no atomics on shared memory); L2 / DRAM latency of the
+// table is hidden by the slice in between issue and use.  A flow seen three times within a short while (per-warp
+// filter) is installed in the private cache; entries age, a colder one is flushed (same reductions) and replaced.
+// Exactness is that of K1: the cache and the probe compare all 114 bytes, any descriptor mismatch flags the flow
+// TAG_DIRTY for the ordered re-fold below.
 // ------------------------------------------------------------------------------------
-constexpr int kWWarps = 32;                      // warps per CTA
-constexpr int kWSub = 32;                        // records per sub-tile == lanes
-constexpr int kWLast = 1024;                     // "seen this flow a moment ago" filter (cache candidacy)
-constexpr int kWHot = 256;                       // direct-mapped cache of hot flows (the room the team structures took)
-template <int kBufs>
-struct __align__(128) WarpSmemT {                // 5,120 B per warp with one tile buffer, 9,728 B with two
-    uint4    tile[kBufs][kWSub * kRecChunks];    // 4,608 B each
-    uint32_t res[kWSub];                         //   128 B  table slot found for each probing lane
-    uint32_t mir_lo[kWSub];                      //   128 B
-    uint16_t mir_hi[kWSub];                      //    64 B
-    uint16_t fseen[kWSub];                       //    64 B
-    uint8_t  slow[kWSub];                        //    32 B  lanes whose flow needs the general probe loop
-    uint8_t  list[kWSub];                        //    32 B  the probing lanes, compacted
-    unsigned long long full_bar[kBufs];
-    uint8_t  pad[kBufs == 1 ? 56 : 48];
-};
-using WarpSmem = WarpSmemT<1>;
-static_assert(sizeof(WarpSmemT<1>) == 5120 && sizeof(WarpSmemT<2>) == 9728, "WarpSmem");
-// kW warps per CTA: 32 warps with one tile buffer each (221,200 B), or 16 warps with two (213,008 B) - the latter
-// requests the next sub-tile before it works on the current one and may use twice the registers per thread
-template <int kW>
-struct __align__(128) AggWSmemT {
-    WarpSmemT<(kW == 32 ? 1 : 2)> w[kW];
-    HotEntry hot[kWHot];
-    uint32_t last[kWLast];
-    uint32_t n_insert, n_spill, any_dirty, pad;
-};
-using AggWSmem = AggWSmemT<32>;
+constexpr int kSW = 8;                            // warps per CTA (one CTA per SM)
+constexpr int kSSub = 32;                         // records per slice == lanes
+constexpr int kSC = 32;                           // private cache entries per warp (direct-mapped on the hash's top bits)
+constexpr int kSF = 256;                          // "seen recently" filter entries per warp
 
-__device__ __forceinline__ void issue_sub_load(uint4* tile, unsigned long long* bar, const uint4* recs, uint32_t n, uint32_t sub,
-                                               bool evict_first) {
-    const uint32_t first = sub * kWSub;
-    const uint32_t bytes = min((uint32_t)kWSub, n - first) * kRecBytes;
+struct __align__(16) SCacheEntry {                // 176 B: a stride of 44 words keeps 8 entries on distinct banks
+    uint4    line[8];                             // copy of the flow's identity line (key, tag, start mirror, descriptor)
+    unsigned long long bytes, ns, end;            // what the folded records add / max (ns = 0 - start, 0 = unset)
+    uint32_t packets, flags;
+    uint32_t hash, slot, hits, state;             // state 0 = empty
+};
+static_assert(sizeof(SCacheEntry) == 176, "SCacheEntry stride");
+struct __align__(128) SWarp {                     // 28,928 B per warp
+    uint4    rec[3][kSSub * kRecChunks];          // 13,824 B  three TMA-staged slices
+    uint4    line[2][kSSub * 8];                  //  8,192 B  gathered identity lines, chunk c of row r at r*8 + (c ^ (r & 7))
+    SCacheEntry cache[kSC];                       //  5,632 B
+    uint32_t filt[kSF];                           //  1,024 B  (hash & 0xFFFFFF00) | times seen
+    uint32_t res[kSSub];                          //    128 B  slots found by the general probe
+    unsigned long long full_bar[3];
+    uint8_t  list[kSSub];                         //  the probing lanes, compacted
+    uint8_t  slow[kSSub];                         //  lanes whose flow needs the general probe
+    uint8_t  pad[40];
+};
+static_assert(sizeof(SWarp) == 28928, "SWarp");
+
+#ifndef FA_HOST_EMUL
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {      // SASS: LDGSTS.E.BYPASS.128
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+#endif
+
+__device__ __forceinline__ void issue_slice_load(uint4* buf, unsigned long long* bar, const uint4* recs, uint32_t n, uint32_t sub) {
+    const uint32_t first = sub * kSSub;
+    const uint32_t bytes = min((uint32_t)kSSub, n - first) * kRecBytes;
     mbar_expect_tx(bar, bytes);
-    if (evict_first) tma_load_1d_stream(tile, recs + (size_t)first * kRecChunks, bytes, bar);
-    else tma_load_1d(tile, recs + (size_t)first * kRecChunks, bytes, bar);
+    tma_load_1d(buf, recs + (size_t)first * kRecChunks, bytes, bar);
 }
 
-// One batch of the pipelined probe passes of K1w: kRounds rounds of 8 flows (4 lanes per flow), all their identity
-// lines in flight together; pass 0 = home slot, pass 1 = next slot for the flows whose home slot holds another
-// settled flow.  Flows that need more (inserts, chains, in-flight publishes) are appended to s.slow.
-template <int kRounds, typename WS>
-__device__ __forceinline__ void wprobe_rounds(const Table& t, uint64_t epoch, WS& s, const uint4* T, uint32_t* any_dirty,
-                                              uint32_t nrep, uint32_t base, uint32_t home, uint32_t tmask, uint32_t lt_mask,
-                                              int g4, int j4, uint4 cmaskA, uint4 cmaskB, int rcA, int rcB, uint32_t& nslow) {
-    uint32_t ridx4[kRounds], slot4[kRounds], actm[kRounds];
-    uint32_t pend4 = 0;
-#pragma unroll
-    for (int r = 0; r < kRounds; r++) {
-        const uint32_t f = base + r * 8 + g4;
-        const bool act = f < nrep;
-        actm[r] = __ballot_sync(0xFFFFFFFFu, act);                // lanes of the groups that hold a flow in this round
-        ridx4[r] = act ? (uint32_t)s.list[f] : 0u;                // the lane that owns the f-th probing record
-        if (act) pend4 |= 1u << r;
-        slot4[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx4[r]);
-    }
-#pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        uint4 lineA[kRounds], lineB[kRounds];
-#pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            lineA[r] = make_uint4(0, 0, 0, 0); lineB[r] = make_uint4(0, 0, 0, 0);
-            if ((pend4 >> r) & 1u) {
-                lineA[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4]);
-                lineB[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4 + 4]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            const bool act = (pend4 >> r) & 1u;
-            const uint4* RR = T + ridx4[r] * kRecChunks;
-            bool eqA = eq4_masked(lineA[r], RR[rcA], cmaskA);
-            const bool eqB = eq4_masked(lineB[r], RR[rcB], cmaskB);
-            const uint64_t tag = u64_of(lineA[r].z, lineA[r].w);   // meaningful in lane j4 == 2 only
-            bool settled = false;
-            if (j4 == 2) {
-                settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
-                          (tag >> TAG_EPOCH_SHIFT) != epoch;
-                eqA = eqA && settled;
-            }
-            // common case first: every flow of the round is settled and matches in all 8 chunks -> one vote
-            const uint32_t okm = __ballot_sync(0xFFFFFFFFu, eqA && eqB);
-            if ((okm | ~actm[r]) == 0xFFFFFFFFu) {
-                if (act && j4 == 0) s.res[ridx4[r]] = slot4[r];
-                if (act && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
-                if (act && j4 == 2) s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
-                pend4 &= ~(1u << r);
-                continue;
-            }
-            const uint32_t eqb = ((__ballot_sync(0xFFFFFFFFu, eqA) >> (g4 * 4)) & 0xFu) |
-                                 (((__ballot_sync(0xFFFFFFFFu, eqB) >> (g4 * 4)) & 0xFu) << 4);
-            const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g4 * 4 + 2)) & 1u;
-            const bool fast = act && (eqb & 0x07u) == 0x07u;       // settled flow, key matches
-            if (fast && j4 == 0) s.res[ridx4[r]] = slot4[r];
-            if (fast && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
-            if (fast && j4 == 2) {
-                s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
-                if ((eqb & 0xF8u) != 0xF8u) {                       // descriptor differs: ordered re-fold
-                    unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot4[r] * 8 + 2]) + 1;
-                    if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
-                    *any_dirty = 1;
-                }
-            }
-            const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
-            const bool to_slow = act && !fast && !collide;
-            if (collide) slot4[r] = (slot4[r] + 1) & tmask;
-            else pend4 &= ~(1u << r);
-            const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j4 == 0);
-            if (slowb) {
-                if (to_slow && j4 == 0) s.slow[nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx4[r];
-                nslow += __popc(slowb);
-            }
-        }
-        if (!__any_sync(0xFFFFFFFFu, pend4 != 0u)) break;
+// what a record carries from front() to back()
+struct SCarry { uint32_t h32, home; bool probe; };
+
+// flush one private cache entry: the same reductions a probing record issues
+template <bool kSketch>
+__device__ __forceinline__ void scache_flush(const Table& t, const SketchParams& sk, const SCacheEntry& e) {
+    const uint64_t tag = u64_of(e.line[2].z, e.line[2].w);
+    const uint64_t floor_ns = u64_of(e.line[3].x, e.line[3].y >> 16) << 16;
+    reduce_to_hot(t, e.slot, e.bytes, e.packets, e.ns, e.end, e.flags, floor_ns, (uint32_t)(tag >> TAG_FLAGS_SHIFT) & 0xFFFFu);
+    if (kSketch) {
+        const uint4 k0 = e.line[0], k1 = e.line[1], k2 = e.line[2];
+        sketch_update(sk, key_premix(u64_of(k0.x, k0.y), u64_of(k0.z, k0.w), u64_of(k1.x, k1.y), u64_of(k1.z, k1.w),
+                                     u64_of(k2.x, k2.y)), e.packets);
     }
 }
 
-// The same batch with 8 lanes per flow (one lane per 16-byte line chunk, one L1 wavefront per line instead of two):
-// kRounds rounds of 4 flows.  Costs twice the instructions per flow of wprobe_rounds; FA_K1_OPT bit 11 selects it.
-template <int kRounds, typename WS>
-__device__ __forceinline__ void wprobe_rounds8(const Table& t, uint64_t epoch, WS& s, const uint4* T, uint32_t* any_dirty,
-                                               uint32_t nrep, uint32_t base, uint32_t home, uint32_t tmask, uint32_t lt_mask,
-                                               int g, int j, uint4 cmask, int rc, uint32_t& nslow) {
-    uint32_t ridx[kRounds], slot[kRounds], actm[kRounds];
-    uint32_t pend = 0;
-#pragma unroll
-    for (int r = 0; r < kRounds; r++) {
-        const uint32_t f = base + r * 4 + g;
-        const bool act = f < nrep;
-        actm[r] = __ballot_sync(0xFFFFFFFFu, act);
-        ridx[r] = act ? (uint32_t)s.list[f] : 0u;
-        if (act) pend |= 1u << r;
-        slot[r] = __shfl_sync(0xFFFFFFFFu, home, (int)ridx[r]);
-    }
-#pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        uint4 line[kRounds];
-#pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            line[r] = make_uint4(0, 0, 0, 0);
-            if ((pend >> r) & 1u) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
-        }
-#pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            const bool act = (pend >> r) & 1u;
-            bool eq = eq4_masked(line[r], T[ridx[r] * kRecChunks + rc], cmask);
-            const uint64_t tag = u64_of(line[r].z, line[r].w);      // meaningful in lane j == 2 only
-            bool settled = false;
-            if (j == 2) {
-                settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
-                          (tag >> TAG_EPOCH_SHIFT) != epoch;
-                eq = eq && settled;
-            }
-            const uint32_t eqm = __ballot_sync(0xFFFFFFFFu, eq);
-            if ((eqm | ~actm[r]) == 0xFFFFFFFFu) {                  // every flow of the round: settled, all 8 chunks equal
-                if (act && j == 0) s.res[ridx[r]] = slot[r];
-                if (act && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
-                if (act && j == 2) s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
-                pend &= ~(1u << r);
-                continue;
-            }
-            const uint32_t eqb = (eqm >> (g * 8)) & 0xFFu;
-            const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g * 8 + 2)) & 1u;
-            const bool fast = act && (eqb & 0x07u) == 0x07u;
-            if (fast && j == 0) s.res[ridx[r]] = slot[r];
-            if (fast && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
-            if (fast && j == 2) {
-                s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
-                if ((eqb & 0xF8u) != 0xF8u) {
-                    unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
-                    if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
-                    *any_dirty = 1;
-                }
-            }
-            const bool collide = act && !fast && gsettled && pass == 0;
-            const bool to_slow = act && !fast && !collide;
-            if (collide) slot[r] = (slot[r] + 1) & tmask;
-            else pend &= ~(1u << r);
-            const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j == 0);
-            if (slowb) {
-                if (to_slow && j == 0) s.slow[nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx[r];
-                nslow += __popc(slowb);
-            }
-        }
-        if (!__any_sync(0xFFFFFFFFu, pend != 0u)) break;
-    }
+// 64-bit sum / max over the lanes of `peers` (redux is 32 bits wide: four 16-bit partial sums are exact)
+__device__ __forceinline__ uint64_t peers_add_u64(uint32_t peers, uint64_t v) {
+    const uint32_t s0 = __reduce_add_sync(peers, (uint32_t)v & 0xFFFFu), s1 = __reduce_add_sync(peers, ((uint32_t)v >> 16) & 0xFFFFu);
+    const uint32_t s2 = __reduce_add_sync(peers, (uint32_t)(v >> 32) & 0xFFFFu), s3 = __reduce_add_sync(peers, (uint32_t)(v >> 48));
+    return (uint64_t)s0 + ((uint64_t)s1 << 16) + ((uint64_t)s2 << 32) + ((uint64_t)s3 << 48);
+}
+__device__ __forceinline__ uint64_t peers_max_u64(uint32_t peers, uint64_t v) {
+    const uint32_t mh = __reduce_max_sync(peers, (uint32_t)(v >> 32));
+    const uint32_t ml = __reduce_max_sync(peers, (uint32_t)(v >> 32) == mh ? (uint32_t)v : 0u);
+    return u64_of(ml, mh);
 }
 
-// kAgg (experiment, FA_K1_OPT bit 9): lanes of a warp that hit the same cache entry pre-reduce their record
-// (match.any + redux) and one of them issues the shared-memory atomics.
-// kLanes8 (experiment, FA_K1_OPT bit 11): 8 lanes per flow in the pipelined probe passes (wprobe_rounds8).
-// kW (experiment, FA_K1_OPT bit 12): 16 warps per CTA with double-buffered sub-tiles instead of 32 with one buffer.
-template <bool kSketch, bool kDevN, bool kAgg = false, bool kLanes8 = false, int kW = kWWarps>
-__global__ void __launch_bounds__(kW * 32, 1)
-aggregate_warp_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
-                      uint32_t* __restrict__ spill_idx, SketchParams sk, uint32_t opt) {
-    FA_DYN_SMEM(smem_raw);
-    constexpr int kBufs = kW == 32 ? 1 : 2;
-    AggWSmemT<kW>& cs = *reinterpret_cast<AggWSmemT<kW>*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmemT<kBufs>& s = cs.w[warp];
-    if (kDevN) n = min(n, (uint32_t)ctr->launch_n);
-    const uint32_t n_sub = (n + kWSub - 1) / kWSub;
-    const uint32_t sub_stride = gridDim.x * kW;
-    const uint32_t sub0 = blockIdx.x * kW + warp;
-    const bool use_cache = (opt & 2u) == 0;
-
-    if (threadIdx.x == 0) { cs.n_insert = 0; cs.n_spill = 0; cs.any_dirty = 0; }
-    if (threadIdx.x < kWHot) cs.hot[threadIdx.x].state = 0;
-    for (int i = threadIdx.x; i < kWLast; i += kW * 32) cs.last[i] = 0u;
-    if (lane == 0) {
-        for (int b = 0; b < kBufs; b++) mbar_init(&s.full_bar[b], 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-    const bool stream_hint = (opt & 1024u) != 0;                 // optional: L2 evict-first for the record stream
-    if (lane == 0 && sub0 < n_sub) issue_sub_load(s.tile[0], &s.full_bar[0], recs, n, sub0, stream_hint);
-
-    const int g = lane >> 3, j = lane & 7;                       // 8-lane groups of the general probe loop
-    const uint4 cmask = chunk_mask(j);
-    const int rc = rec_chunk_of_line_chunk(j);
-    const int g4 = lane >> 2, j4 = lane & 3;                     // 4-lane groups of the pipelined passes
-    const uint4 cmaskA = chunk_mask(j4), cmaskB = chunk_mask(j4 + 4);
-    const int rcA = rec_chunk_of_line_chunk(j4), rcB = j4 + 5;
-    const uint32_t tmask = (uint32_t)t.mask;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t my_inserts = 0, my_spills = 0;
-
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t sub = sub0 + it * sub_stride;
-        if (sub >= n_sub) break;
-        const uint32_t first = sub * kWSub;
-        const uint32_t cnt = min((uint32_t)kWSub, n - first);
-        const int buf = kBufs == 1 ? 0 : (int)(it & 1u);
-        if (kBufs == 2 && lane == 0 && sub + sub_stride < n_sub) {      // the other buffer was drained an iteration ago
-            fence_proxy_async();
-            issue_sub_load(s.tile[buf ^ 1], &s.full_bar[buf ^ 1], recs, n, sub + sub_stride, stream_hint);
-        }
-        mbar_wait(&s.full_bar[buf], kBufs == 1 ? (it & 1u) : ((it >> 1) & 1u));
-        const uint4* T = s.tile[buf];
-        if ((opt & 32u) && lane == 0 && sub + sub_stride < n_sub) {     // optional: have L2 fetch the next sub-tile now
-            const uint32_t nf = (sub + sub_stride) * kWSub;
-            tma_prefetch_l2(recs + (size_t)nf * kRecChunks, min((uint32_t)kWSub, n - nf) * kRecBytes);
-        }
-
-        // ------------------------------------------------------ hash, cache
-        const bool valid = (uint32_t)lane < cnt;
-        bool is_rep = valid;
-        uint32_t h32 = 0;
-        bool hit = false;                                          // kAgg: this lane's record goes into a cache entry
-        uint32_t hb_lo = 0, hb_hi = 0, hpk = 0, hfl = 0, hns = 0, hend = 0;
-        const uint4* R = T + lane * kRecChunks;
-        if (valid) {
-            const uint4 r0 = R[0], r1 = R[1], r2 = R[2];
-            const uint64_t h = slot_hash(key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
-                                                    u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)));
-            h32 = (uint32_t)h;
-            HotEntry& ce = cs.hot[(h32 >> 24) & (kWHot - 1)];
-            if (use_cache && *reinterpret_cast<volatile uint32_t*>(&ce.state) == 2u && ce.hash == h32) {
-                const uint4 r3 = R[3], r4 = R[4];
-                bool same = eq4_masked(ce.line[0], r0, chunk_mask(0)) && eq4_masked(ce.line[1], r1, chunk_mask(1)) &&
-                            eq4_masked(ce.line[2], r2, chunk_mask(2)) && eq4_masked(ce.line[3], r4, chunk_mask(3));
+// front(): hash, private-cache fold, gather issue for one slice
+__device__ __forceinline__ SCarry stream_front(SWarp& s, const uint4* Rbuf, uint4* Lbuf, uint32_t cnt, const Table& t,
+                                               uint32_t tmask, int lane, uint32_t lt_mask, bool use_cache) {
+    const bool valid = (uint32_t)lane < cnt;
+    const uint4* R = Rbuf + lane * kRecChunks;
+    uint32_t h32 = 0, ci = 0;
+    bool hit = false;
+    if (valid) {
+        const uint4 r0 = R[0], r1 = R[1], r2 = R[2];
+        h32 = (uint32_t)slot_hash(key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y), u64_of(r1.z, r1.w),
+                                             u64_of(r2.x, r2.y)));
+        ci = h32 >> 27;
+        const SCacheEntry& ce = s.cache[ci];
+        if (use_cache && ce.state != 0u && ce.hash == h32) {
+            uint32_t d = diff4_masked(ce.line[0], r0, chunk_mask(0)) | diff4_masked(ce.line[1], r1, chunk_mask(1)) |
+                         diff4_masked(ce.line[2], r2, chunk_mask(2));
 #pragma unroll
-                for (int c = 5; c < 9; c++) same = same && eq4_masked(ce.line[c - 1], R[c], chunk_mask(c - 1));
-                const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
-                const uint64_t v_ns = 0ull - v_start;
-                same = same && (v_start == 0 || (uint32_t)(v_ns >> 32) == ce.ns_hi) &&
-                       (v_end == 0 || (uint32_t)(v_end >> 32) == ce.end_hi);
-                if (same) {
-                    is_rep = false;
-                    FA_EMUL_COUNT(2, 1);
-                    if (kAgg) {                                    // folded after the warp has re-converged (below)
-                        hit = true;
-                        hb_lo = r3.z; hb_hi = r3.w; hpk = r4.x; hfl = r4.y >> 16;
-                        hns = v_start ? (uint32_t)v_ns : 0u; hend = v_end ? (uint32_t)v_end : 0u;
-                    } else {
-                        uint32_t* A = ce.acc;
-                        const uint32_t b_lo = r3.z, b_hi = r3.w;
-                        const uint32_t prev = atomicAdd(&A[0], b_lo);
-                        const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
-                        if (hi_add) atomicAdd(&A[1], hi_add);
-                        atomicAdd(&A[2], r4.x);
-                        const uint32_t fl = r4.y >> 16;
-                        if (fl & ~A[3]) atomicOr(&A[3], fl);
-                        if (v_start && (uint32_t)v_ns > A[4]) atomicMax(&A[4], (uint32_t)v_ns);
-                        if (v_end && (uint32_t)v_end > A[5]) atomicMax(&A[5], (uint32_t)v_end);
-                    }
-                }
-            }
+            for (int c = 3; c < 8; c++) d |= diff4_masked(ce.line[c], R[c + 1], chunk_mask(c));
+            hit = d == 0u;
         }
-        if (kAgg) {
-            const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, hit);
-            if (hit) {
-                const uint32_t ci = (h32 >> 24) & (kWHot - 1);
-                const uint32_t peers = __match_any_sync(hitmask, ci);      // lanes folding into the same cache entry
-                // 32-bit sums are safe when every peer's byte count is small (32 x 2^26 < 2^32)
-                const bool small = __reduce_or_sync(peers, (hb_hi != 0u || hb_lo >= (1u << 26)) ? 1u : 0u) == 0u;
-                uint32_t* A = cs.hot[ci].acc;
-                if (small) {
-                    const uint32_t sb = __reduce_add_sync(peers, hb_lo), sp = __reduce_add_sync(peers, hpk);
-                    const uint32_t sf = __reduce_or_sync(peers, hfl);
-                    const uint32_t mn = __reduce_max_sync(peers, hns), me = __reduce_max_sync(peers, hend);
-                    if (lane == __ffs(peers) - 1) {
-                        const uint32_t prev = atomicAdd(&A[0], sb);
-                        if ((prev + sb) < prev) atomicAdd(&A[1], 1u);
-                        atomicAdd(&A[2], sp);
-                        if (sf & ~A[3]) atomicOr(&A[3], sf);
-                        if (mn > A[4]) atomicMax(&A[4], mn);
-                        if (me > A[5]) atomicMax(&A[5], me);
-                    }
-                } else {
-                    const uint32_t prev = atomicAdd(&A[0], hb_lo);
-                    const uint32_t hi_add = hb_hi + ((prev + hb_lo) < prev ? 1u : 0u);
-                    if (hi_add) atomicAdd(&A[1], hi_add);
-                    atomicAdd(&A[2], hpk);
-                    if (hfl & ~A[3]) atomicOr(&A[3], hfl);
-                    if (hns > A[4]) atomicMax(&A[4], hns);
-                    if (hend > A[5]) atomicMax(&A[5], hend);
-                }
+    }
+    const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, hit);
+    if (hitmask) {                                                     // warp-uniform
+        if (hit) {
+            FA_EMUL_COUNT(2, 1);
+            const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
+            const uint64_t v_start = u64_of(r2.z, r2.w);
+            uint64_t bytes = u64_of(r3.z, r3.w), ns = v_start ? 0ull - v_start : 0ull, end = u64_of(r3.x, r3.y);
+            uint32_t packets = r4.x, flags = r4.y >> 16;
+            const uint32_t peers = __match_any_sync(hitmask, ci);     // lanes folding into the same entry
+            if (peers != (1u << lane)) {
+                bytes = peers_add_u64(peers, bytes);
+                packets = __reduce_add_sync(peers, packets);
+                flags = __reduce_or_sync(peers, flags);
+                ns = peers_max_u64(peers, ns);
+                end = peers_max_u64(peers, end);
             }
-        }
-
-        // ------------------------------------------------------ probe: the warp's own un-cached records
-        const uint32_t repmask = __ballot_sync(0xFFFFFFFFu, is_rep);
-        const uint32_t nrep = (uint32_t)__popc(repmask);
-        if (is_rep) s.list[__popc(repmask & lt_mask)] = (uint8_t)lane;
-        __syncwarp();
-        const uint32_t home = h32 & tmask;
-        if ((opt & 64u) && is_rep) {                               // optional: start the table line's trip to L2 now
-            prefetch_l2(&t.ident[(size_t)home * 8]);
-            prefetch_l2(&t.ident[(size_t)home * 8 + 4]);
-        }
-        uint32_t nslow = 0;
-        if (kLanes8) {                                             // 8 lanes per flow: 4 flows per round
-            for (uint32_t base = 0; base < nrep;) {
-                if (nrep - base > 8u) {
-                    wprobe_rounds8<4>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
-                    base += 16u;
-                } else if (nrep - base > 4u) {
-                    wprobe_rounds8<2>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
-                    base += 8u;
-                } else {
-                    wprobe_rounds8<1>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g, j, cmask, rc, nslow);
-                    base += 4u;
-                }
-            }
-        } else
-        for (uint32_t base = 0; base < nrep;) {                   // two rounds in flight while >= 9 flows remain
-            if (kW == 16 && nrep - base > 16u) {                   // half the warps, twice the registers: four rounds in flight
-                wprobe_rounds<4>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
-                base += 32u;
-            } else
-            if (nrep - base > 8u) {
-                wprobe_rounds<2>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
-                base += 16u;
-            } else {
-                wprobe_rounds<1>(t, epoch, s, T, &cs.any_dirty, nrep, base, home, tmask, lt_mask, g4, j4, cmaskA, cmaskB, rcA, rcB, nslow);
-                base += 8u;
+            if (lane == __ffs(peers) - 1) {                            // one lane per entry: plain read-modify-write
+                SCacheEntry& e = s.cache[ci];
+                e.bytes += bytes; e.packets += packets; e.flags |= flags;
+                if (ns > e.ns) e.ns = ns;
+                if (end > e.end) e.end = end;
+                e.hits += (uint32_t)__popc(peers);
             }
         }
         __syncwarp();
-        if (lane == 0) { FA_EMUL_COUNT(0, nrep); FA_EMUL_COUNT(1, nslow); }
-        for (uint32_t base = 0; base < nslow; base += 4) {         // inserts, long collision chains, in-flight publishes
+    }
+    const bool probe = valid && !hit;
+    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, probe);
+    const uint32_t npr = (uint32_t)__popc(pm);
+    if (probe) s.list[__popc(pm & lt_mask)] = (uint8_t)lane;
+    __syncwarp();
+    const uint32_t home = h32 & tmask;
+    const int g = lane >> 3, j = lane & 7;
+    for (uint32_t base = 0; base < npr; base += 4) {                   // 8 lanes per line, 4 lines per round
+        const uint32_t k = base + g;
+        const uint32_t src = k < npr ? (uint32_t)s.list[k] : 0u;
+        const uint32_t slot = __shfl_sync(0xFFFFFFFFu, home, (int)src);
+        if (k < npr) cp_async16(&Lbuf[src * 8 + (j ^ (src & 7))], &t.ident[(size_t)slot * 8 + j]);
+    }
+    cp_async_commit();
+    FA_EMUL_COUNT(0, lane == 0 ? npr : 0);
+    return SCarry{h32, home, probe};
+}
+
+// One thread checks a whole identity line against its record.  Returns 0 = this flow, settled; 1 = another settled
+// flow lives here; 2 = anything else (empty, being published, born in this launch, feature-only entry).
+__device__ __forceinline__ int line_verdict(const uint4* R, uint4 l0, uint4 l1, uint4 l2, uint4 l3, uint4 l4, uint4 l5, uint4 l6, uint4 l7,
+                                            uint64_t epoch, uint32_t& ddesc) {
+    const uint64_t tag = u64_of(l2.z, l2.w);
+    const bool settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) && (tag >> TAG_EPOCH_SHIFT) != epoch;
+    if (!settled) return 2;
+    const uint32_t dkey = diff4_masked(l0, R[0], chunk_mask(0)) | diff4_masked(l1, R[1], chunk_mask(1)) | diff4_masked(l2, R[2], chunk_mask(2));
+    if (dkey) return 1;
+    ddesc = diff4_masked(l3, R[4], chunk_mask(3)) | diff4_masked(l4, R[5], chunk_mask(4)) | diff4_masked(l5, R[6], chunk_mask(5)) |
+            diff4_masked(l6, R[7], chunk_mask(6)) | diff4_masked(l7, R[8], chunk_mask(7));
+    return 0;
+}
+
+// back(): compare, reduce, install for the slice whose gather was issued one iteration ago
+template <bool kSketch>
+__device__ __forceinline__ void stream_back(SWarp& s, const uint4* Rbuf, const uint4* Lbuf, SCarry c, const Table& t, uint64_t epoch,
+                                            uint32_t tmask, const SketchParams& sk, int lane, uint32_t lt_mask, bool use_cache,
+                                            uint32_t& my_inserts, uint32_t& my_spills, uint32_t& any_dirty) {
+    const uint4* R = Rbuf + lane * kRecChunks;
+    uint32_t slot = c.home;
+    uint64_t floor_ns = 0;
+    uint32_t seen = 0;
+    bool need_slow = false, at_home = false;
+    uint32_t ddesc = 0;
+    if (c.probe) {
+        const uint4* L = Lbuf + lane * 8;
+        const int sw = lane & 7;
+        uint4 l2 = L[2 ^ sw], l3 = L[3 ^ sw];
+        int v = line_verdict(R, L[0 ^ sw], L[1 ^ sw], l2, l3, L[4 ^ sw], L[5 ^ sw], L[6 ^ sw], L[7 ^ sw], epoch, ddesc);
+        at_home = v == 0;
+        if (v == 1) {                                                  // another flow at home: look one slot further, now
+            slot = (slot + 1) & tmask;
+            const uint4* G = &t.ident[(size_t)slot * 8];
+            l2 = ld_cg_u4(G + 2); l3 = ld_cg_u4(G + 3);
+            v = line_verdict(R, ld_cg_u4(G), ld_cg_u4(G + 1), l2, l3, ld_cg_u4(G + 4), ld_cg_u4(G + 5), ld_cg_u4(G + 6), ld_cg_u4(G + 7),
+                             epoch, ddesc);
+        }
+        if (v == 0) {
+            const uint64_t tag = u64_of(l2.z, l2.w);
+            floor_ns = u64_of(l3.x, l3.y >> 16) << 16;
+            seen = (uint32_t)(tag >> TAG_FLAGS_SHIFT) & 0xFFFFu;
+            if (ddesc) {                                               // descriptor differs: ordered re-fold
+                if (!(tag & TAG_DIRTY))
+                    atomicOr(reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot * 8 + 2]) + 1, (unsigned long long)TAG_DIRTY);
+                any_dirty = 1;
+            }
+        } else {
+            need_slow = true;
+        }
+    }
+    const uint32_t slowm = __ballot_sync(0xFFFFFFFFu, need_slow);
+    if (slowm) {                                                       // inserts, chains, in-flight publishes: 8 lanes per flow
+        const uint32_t nslow = (uint32_t)__popc(slowm);
+        if (need_slow) s.slow[__popc(slowm & lt_mask)] = (uint8_t)lane;
+        __syncwarp();
+        FA_EMUL_COUNT(1, lane == 0 ? nslow : 0);
+        const int g = lane >> 3, j = lane & 7;
+        const uint4 cmask = chunk_mask(j);
+        const int rc = rec_chunk_of_line_chunk(j);
+        for (uint32_t base = 0; base < nslow; base += 4) {
             const uint32_t k = base + g;
             const bool act = k < nslow;
-            const uint32_t ri = act ? s.slow[k] : 0;
-            const uint4 rchunk = T[ri * kRecChunks + rc];
-            const uint4 c2 = T[ri * kRecChunks + 2];
+            const uint32_t ri = act ? (uint32_t)s.slow[k] : 0u;
+            const uint4 rchunk = Rbuf[ri * kRecChunks + rc];
+            const uint4 c2 = Rbuf[ri * kRecChunks + 2];
             const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
-            const uint32_t start_slot = __shfl_sync(0xFFFFFFFFu, home, (int)ri);
-            const uint32_t got = probe_general(t, epoch, act, start_slot, rchunk, false, own_ns, g, j, cmask, my_inserts,
-                                               &cs.any_dirty);
+            const uint32_t start_slot = __shfl_sync(0xFFFFFFFFu, c.home, (int)ri);
+            const uint32_t got = probe_general(t, epoch, act, start_slot, rchunk, false, own_ns, g, j, cmask, my_inserts, &any_dirty);
             if (act && j == 0) s.res[ri] = got;
-            if (act && j == 2) s.fseen[ri] = 0;                     // unknown: issue every reduction
-            if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
         }
         __syncwarp();
-
-        // ------------------------------------------------------ every probing lane reduces its own record
-        if (is_rep) {
-            const uint32_t my_slot = s.res[lane];
-            const uint64_t floor_ns = u64_of(s.mir_lo[lane], s.mir_hi[lane]) << 16;      // <= hot.nstart, always
-            const uint32_t seen = s.fseen[lane];
-            const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
-            const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
-            const uint64_t v_ns = 0ull - v_start;
-            // a flow met twice within a short while is hot: give it a cache entry if its slot of the cache is free
-            uint32_t* seen_at = &cs.last[(h32 >> 12) & (kWLast - 1)];
-            const uint32_t before = *reinterpret_cast<volatile uint32_t*>(seen_at);
-            *reinterpret_cast<volatile uint32_t*>(seen_at) = h32;
-            if (use_cache && before == h32 && my_slot != kResSpill) {
-                HotEntry& ce = cs.hot[(h32 >> 24) & (kWHot - 1)];
-                if (*reinterpret_cast<volatile uint32_t*>(&ce.state) == 0u && atomicCAS(&ce.state, 0u, 1u) == 0u) {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) ce.line[c] = ld_cg_u4(&t.ident[(size_t)my_slot * 8 + c]);
-                    *reinterpret_cast<uint4*>(&ce.acc[0]) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4*>(&ce.acc[4]) = make_uint4(0, 0, 0, 0);
-                    ce.hash = h32; ce.slot = my_slot;
-                    ce.ns_hi = (uint32_t)(v_ns >> 32); ce.end_hi = (uint32_t)(v_end >> 32);
-                    __threadfence_block();
-                    *reinterpret_cast<volatile uint32_t*>(&ce.state) = 2u;
-                }
-            }
-            if (kSketch) {
-                const uint4 r0 = R[0], r1 = R[1];
-                sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
-                                             u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)), r4.x);
-            }
-            if (my_slot != kResSpill) {
-                reduce_to_hot(t, my_slot, u64_of(r3.z, r3.w), r4.x, v_ns, v_end, r4.y >> 16, floor_ns, seen);
-            } else {                                               // table physically full: counted in fa_stats.spills
-                my_spills++;
-            }
+        if (need_slow) { slot = s.res[lane]; floor_ns = 0; seen = 0; }    // unknown: issue every reduction
+    }
+    if (c.probe) {
+        const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
+        const uint64_t v_start = u64_of(r2.z, r2.w);
+        if (kSketch) {
+            const uint4 r0 = R[0], r1 = R[1];
+            sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y), u64_of(r1.z, r1.w),
+                                         u64_of(r2.x, r2.y)), r4.x);
         }
-        __syncwarp();                                              // nobody reads the sub-tile buffer any more
-        if (lane == 0) {
-            const uint32_t nx = sub + sub_stride;
-            if (kBufs == 1 && nx < n_sub) { fence_proxy_async(); issue_sub_load(s.tile[0], &s.full_bar[0], recs, n, nx, stream_hint); }
+        if (slot != kResSpill) reduce_to_hot(t, slot, u64_of(r3.z, r3.w), r4.x, 0ull - v_start, u64_of(r3.x, r3.y), r4.y >> 16, floor_ns, seen);
+        else my_spills++;                                              // table physically full: counted in fa_stats.spills
+    }
+    // ---- private cache: a flow met three times within a short while gets an entry; a colder incumbent is flushed
+    bool want = false;
+    const uint32_t ci = c.h32 >> 27;
+    if (use_cache && c.probe && at_home && ddesc == 0u) {
+        uint32_t* f = &s.filt[(c.h32 >> 8) & (kSF - 1)];
+        const uint32_t fv = *f;
+        const uint32_t cntf = ((fv ^ c.h32) & 0xFFFFFF00u) == 0u ? min((fv & 0xFFu) + 1u, 255u) : 1u;
+        *f = (c.h32 & 0xFFFFFF00u) | cntf;
+        const SCacheEntry& e = s.cache[ci];
+        want = cntf >= 3u && (e.state == 0u || (e.hash != c.h32 && e.hits < cntf));
+    }
+    uint32_t im = __ballot_sync(0xFFFFFFFFu, want);
+    for (int round = 0; im != 0u && round < 2; round++) {              // at most two installs per slice
+        const int src = __ffs(im) - 1;
+        im &= im - 1u;
+        const uint32_t eci = __shfl_sync(0xFFFFFFFFu, ci, src);
+        SCacheEntry& e = s.cache[eci];
+        const uint32_t src_hash = __shfl_sync(0xFFFFFFFFu, c.h32, src);
+        const bool go = e.state == 0u || e.hash != src_hash;           // not installed by the previous round
+        if (go) {
+            if (lane == src && e.state != 0u) scache_flush<kSketch>(t, sk, e);
+            __syncwarp();
+            if (lane < 8) e.line[lane] = Lbuf[src * 8 + (lane ^ (src & 7))];
+            if (lane == src) {
+                e.bytes = 0; e.ns = 0; e.end = 0; e.packets = 0; e.flags = 0;
+                e.hash = c.h32; e.slot = slot; e.hits = 0; e.state = 1u;
+            }
+            __syncwarp();
         }
     }
+}
 
+template <bool kSketch, bool kDevN>
+__global__ void __launch_bounds__(kSW * 32, 1)
+aggregate_stream_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr, SketchParams sk, uint32_t opt) {
+    FA_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SWarp& s = reinterpret_cast<SWarp*>(smem_raw)[warp];
+    if (kDevN) n = min(n, (uint32_t)ctr->launch_n);                // size known on the device only (multi-GPU receive side)
+    const uint32_t n_sub = (n + kSSub - 1) / kSSub;
+    const uint32_t stride = gridDim.x * kSW;
+    const uint32_t sub0 = blockIdx.x * kSW + warp;
+    const uint32_t n_it = sub0 < n_sub ? (n_sub - sub0 + stride - 1) / stride : 0u;
+    const bool use_cache = (opt & 2u) == 0;
+    const uint32_t tmask = (uint32_t)t.mask;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t my_inserts = 0, my_spills = 0, any_dirty = 0;
+
+    if (lane < kSC) { s.cache[lane].state = 0u; s.cache[lane].hash = 0u; s.cache[lane].hits = 0u; }
+    for (int i = lane; i < kSF; i += 32) s.filt[i] = 0u;
+    if (lane == 0) {
+        for (int b = 0; b < 3; b++) mbar_init(&s.full_bar[b], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (n_it != 0u) {
+        if (lane == 0) {
+            issue_slice_load(s.rec[0], &s.full_bar[0], recs, n, sub0);
+            if (n_it > 1u) issue_slice_load(s.rec[1], &s.full_bar[1], recs, n, sub0 + stride);
+        }
+        mbar_wait(&s.full_bar[0], 0u);
+        SCarry cur = stream_front(s, s.rec[0], s.line[0], min((uint32_t)kSSub, n - sub0 * kSSub), t, tmask, lane, lt_mask, use_cache);
+        uint32_t b_cur = 0, b_nxt = 1, b_ld = 2;                     // record buffers of slices it, it+1, it+2
+        for (uint32_t it = 0; it < n_it; ++it) {
+            const uint32_t sub = sub0 + it * stride;
+            if (it + 2u < n_it && lane == 0) {                       // buffer b_ld was drained by back(it-1)
+                fence_proxy_async();
+                issue_slice_load(s.rec[b_ld], &s.full_bar[b_ld], recs, n, sub + 2u * stride);
+            }
+            SCarry nxt{0u, 0u, false};
+            if (it + 1u < n_it) {
+                mbar_wait(&s.full_bar[b_nxt], ((it + 1u) / 3u) & 1u);
+                nxt = stream_front(s, s.rec[b_nxt], s.line[(it + 1u) & 1u], min((uint32_t)kSSub, n - (sub + stride) * kSSub), t, tmask,
+                                   lane, lt_mask, use_cache);
+            } else {
+                cp_async_commit();
+            }
+            cp_async_wait<1>();                                      // the gather of slice `it` has landed
+            __syncwarp();
+            stream_back<kSketch>(s, s.rec[b_cur], s.line[it & 1u], cur, t, epoch, tmask, sk, lane, lt_mask, use_cache, my_inserts,
+                                 my_spills, any_dirty);
+            __syncwarp();                                            // nobody reads slice `it` any more
+            cur = nxt;
+            const uint32_t b = b_cur; b_cur = b_nxt; b_nxt = b_ld; b_ld = b;
+            if ((it & 31u) == 31u && lane < kSC) s.cache[lane].hits >>= 1;     // ageing
+        }
+        cp_async_wait<0>();
+    }
+    __syncwarp();
     // ---------------------------------------------------------- counters + cache flush
+    if (lane < kSC && s.cache[lane].state != 0u) scache_flush<kSketch>(t, sk, s.cache[lane]);
     my_inserts = __reduce_add_sync(0xFFFFFFFFu, my_inserts);
     my_spills = __reduce_add_sync(0xFFFFFFFFu, my_spills);
+    any_dirty = __reduce_or_sync(0xFFFFFFFFu, any_dirty);
     if (lane == 0) {
-        if (my_inserts) atomicAdd(&cs.n_insert, my_inserts);
-        if (my_spills) atomicAdd(&cs.n_spill, my_spills);
-    }
-    __syncthreads();                                               // every warp is out of sub-tiles
-    if (threadIdx.x < kWHot) {
-        const HotEntry& ce = cs.hot[threadIdx.x];
-        if (ce.state == 2u) {
-            const uint32_t* A = ce.acc;
-            const uint64_t tag = u64_of(ce.line[2].z, ce.line[2].w);
-            const uint64_t floor_ns = u64_of(ce.line[3].x, ce.line[3].y >> 16) << 16;
-            reduce_to_hot(t, ce.slot, u64_of(A[0], A[1]), A[2], u64_of(A[4], ce.ns_hi), u64_of(A[5], ce.end_hi), A[3],
-                          floor_ns, (uint32_t)(tag >> TAG_FLAGS_SHIFT) & 0xFFFFu);
-            if (kSketch) {
-                const uint4 k0 = ce.line[0], k1 = ce.line[1], k2 = ce.line[2];
-                sketch_update(sk, key_premix(u64_of(k0.x, k0.y), u64_of(k0.z, k0.w), u64_of(k1.x, k1.y),
-                                             u64_of(k1.z, k1.w), u64_of(k2.x, k2.y)), A[2]);
-            }
-        }
-    }
-    if (threadIdx.x == 0) {
-        if (cs.n_insert) atomicAdd(&ctr->live, (unsigned long long)cs.n_insert);
-        if (cs.n_spill) atomicAdd(&ctr->spills, (unsigned long long)cs.n_spill);
-        if (cs.any_dirty) *reinterpret_cast<volatile unsigned long long*>(&ctr->dirty) = 1ull;
+        if (my_inserts) atomicAdd(&ctr->live, (unsigned long long)my_inserts);
+        if (my_spills) atomicAdd(&ctr->spills, (unsigned long long)my_spills);
+        if (any_dirty) *reinterpret_cast<volatile unsigned long long*>(&ctr->dirty) = 1ull;
     }
 }
 
@@ -1243,36 +1120,24 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
 #define FA_K1_ARGS a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk
     if (a.prof)
         aggregate_kernel<false, true, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, a.prof, a.opt);
-    else if (a.opt & 256u) {                              // warp-independent variant (experiment)
-        static bool wattr[64] = {};
-        const int wsmem = (int)sizeof(AggWSmem);
-        if (!wattr[dev & 63]) {
-            cudaFuncSetAttribute(aggregate_warp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
-            cudaFuncSetAttribute(aggregate_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
-            cudaFuncSetAttribute(aggregate_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
-            cudaFuncSetAttribute(aggregate_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
-            cudaFuncSetAttribute(aggregate_warp_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
-            cudaFuncSetAttribute(aggregate_warp_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
-            wattr[dev & 63] = true;
+    else if (a.opt & 256u) {                              // K1s: the streaming kernel
+        static bool sattr[64] = {};
+        const int ssmem = (int)(sizeof(SWarp) * kSW);
+        if (!sattr[dev & 63]) {
+            cudaFuncSetAttribute(aggregate_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssmem);
+            cudaFuncSetAttribute(aggregate_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssmem);
+            cudaFuncSetAttribute(aggregate_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssmem);
+            cudaFuncSetAttribute(aggregate_stream_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssmem);
+            sattr[dev & 63] = true;
         }
-        const uint32_t n_sub = (a.n + kWSub - 1) / kWSub;
-        const int wgrid = (int)min((uint32_t)a.sm_count, (n_sub + kWWarps - 1) / kWWarps);
-        if (a.sk.cms && dev_n) aggregate_warp_kernel<true, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
-        else if (a.sk.cms) aggregate_warp_kernel<true, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
-        else if (dev_n) aggregate_warp_kernel<false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
-        else if (a.opt & 4096u) {                         // 16 warps, double-buffered sub-tiles
-            const int wsmem16 = (int)sizeof(AggWSmemT<16>);
-            static bool w16attr[64] = {};
-            if (!w16attr[dev & 63]) {
-                cudaFuncSetAttribute(aggregate_warp_kernel<false, false, false, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem16);
-                w16attr[dev & 63] = true;
-            }
-            const int g16 = (int)min((uint32_t)a.sm_count, (n_sub + 15) / 16);
-            aggregate_warp_kernel<false, false, false, false, 16><<<g16, 16 * 32, wsmem16, st>>>(FA_K1_ARGS, a.opt);
-        }
-        else if (a.opt & 2048u) aggregate_warp_kernel<false, false, false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
-        else if (a.opt & 512u) aggregate_warp_kernel<false, false, true><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
-        else aggregate_warp_kernel<false, false><<<wgrid, kWWarps * 32, wsmem, st>>>(FA_K1_ARGS, a.opt);
+        const uint32_t n_sub = (a.n + kSSub - 1) / kSSub;
+        const int sgrid = (int)min((uint32_t)a.sm_count, (n_sub + kSW - 1) / kSW);
+#define FA_K1S_ARGS a.recs, a.n, a.table, a.epoch, a.ctr, a.sk, a.opt
+        if (a.sk.cms && dev_n) aggregate_stream_kernel<true, true><<<sgrid, kSW * 32, ssmem, st>>>(FA_K1S_ARGS);
+        else if (a.sk.cms) aggregate_stream_kernel<true, false><<<sgrid, kSW * 32, ssmem, st>>>(FA_K1S_ARGS);
+        else if (dev_n) aggregate_stream_kernel<false, true><<<sgrid, kSW * 32, ssmem, st>>>(FA_K1S_ARGS);
+        else aggregate_stream_kernel<false, false><<<sgrid, kSW * 32, ssmem, st>>>(FA_K1S_ARGS);
+#undef FA_K1S_ARGS
     }
     else if (a.sk.cms && dev_n)
         aggregate_kernel<true, false, true><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);

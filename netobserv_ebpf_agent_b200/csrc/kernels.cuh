@@ -68,6 +68,22 @@ int launch_evict_features(const Table& t, const uint32_t* slot_of_out, unsigned 
 int launch_cms_query(const SketchParams& sk, const uint4* keys, uint32_t n, unsigned long long* est, cudaStream_t st);
 int launch_hll_pack(const SketchParams& sk, uint8_t* out_regs, cudaStream_t st);
 
+// K8: evicted flows -> pbflow.Record wire bytes (pbflow.cu)
+struct PbIface { uint32_t if_index; uint8_t mac[6]; uint8_t name_len, udn_len; char name[16]; char udn[64]; };   // == fa_iface_name
+struct PbParams {
+    uint64_t now_unix_ns, mono_now_ns;
+    uint8_t  agent_ip[16];
+    uint32_t agent_is_v4;             // 1: agent_ip[12..16) is an IPv4 address
+    uint32_t wrap;                    // 1: every record is prefixed with the Records.entries tag + length
+    const PbIface* ifaces; uint32_t n_ifaces;
+};
+struct PbInputs { const uint8_t* recs; const uint8_t* dns; const uint8_t* add; const uint8_t* drop; const uint8_t* present; };
+// sizes: n u32 (message bodies), offsets: n + 1 u64, block_sums: ceil(n / 1024) u64 — device scratch
+int launch_pb_sizes(const PbInputs& in, uint32_t n, const PbParams& P, uint32_t* sizes, unsigned long long* offsets,
+                    unsigned long long* block_sums, int sm_count, cudaStream_t st);
+int launch_pb_write(const PbInputs& in, uint32_t n, const PbParams& P, const unsigned long long* offsets, const uint32_t* sizes,
+                    uint8_t* out, uint8_t* keys_out, cudaStream_t st);
+
 // generator
 struct GenDeviceParams;
 int launch_generate(const GenDeviceParams& g, uint64_t first_index, uint32_t n, uint4* dst, cudaStream_t st);

@@ -124,16 +124,13 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t) {
     const uint4* recs = a.recs; const uint32_t n = a.n; Table t = a.table; const uint64_t epoch = a.epoch;
     Counters* ctr = a.ctr; uint32_t* spill = a.spill_idx; SketchParams sk = a.sk; const uint32_t opt = a.opt;
     if (a.opt & 256u) {
-        const uint32_t n_sub = (n + kWSub - 1) / kWSub;
-        const unsigned g = small((n_sub + kWWarps - 1) / kWWarps, 2);
-        const size_t sm = sizeof(AggWSmem);
-        if (sk.cms && dev_n) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<true, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
-        else if (sk.cms) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<true, false>(recs, n, t, epoch, ctr, spill, sk, opt); });
-        else if (dev_n) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<false, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
-        else if (a.opt & 4096u) simt::launch(small((n_sub + 15) / 16, 3), 16 * 32, sizeof(AggWSmemT<16>), [=] { aggregate_warp_kernel<false, false, false, false, 16>(recs, n, t, epoch, ctr, spill, sk, opt); });
-        else if (a.opt & 2048u) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<false, false, false, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
-        else if (a.opt & 512u) simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<false, false, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
-        else simt::launch(g, kWWarps * 32, sm, [=] { aggregate_warp_kernel<false, false>(recs, n, t, epoch, ctr, spill, sk, opt); });
+        const uint32_t n_sub = (n + kSSub - 1) / kSSub;
+        const unsigned g = small((n_sub + kSW - 1) / kSW, 3);
+        const size_t sm = sizeof(SWarp) * kSW;
+        if (sk.cms && dev_n) simt::launch(g, kSW * 32, sm, [=] { aggregate_stream_kernel<true, true>(recs, n, t, epoch, ctr, sk, opt); });
+        else if (sk.cms) simt::launch(g, kSW * 32, sm, [=] { aggregate_stream_kernel<true, false>(recs, n, t, epoch, ctr, sk, opt); });
+        else if (dev_n) simt::launch(g, kSW * 32, sm, [=] { aggregate_stream_kernel<false, true>(recs, n, t, epoch, ctr, sk, opt); });
+        else simt::launch(g, kSW * 32, sm, [=] { aggregate_stream_kernel<false, false>(recs, n, t, epoch, ctr, sk, opt); });
     } else {
         const uint32_t n_tiles = (n + kTile - 1) / kTile;
         const unsigned g = small((n_tiles + kTeams - 1) / kTeams, 2);

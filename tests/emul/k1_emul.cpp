@@ -44,14 +44,14 @@ void run_k1(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt)
             aggregate_kernel<false, false, false, kVar>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
         });
 }
-void run_k1w(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt) {
+void run_k1s(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt) {
     const uint64_t epoch = e->epoch;
-    Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx;
+    Table t = e->t; Counters* ctr = e->ctr;
     SketchParams sk = e->sk;
     if (sk.cms)
-        simt::launch(grid, kWWarps * 32, sizeof(AggWSmem), [=] { aggregate_warp_kernel<true, false>(recs, n, t, epoch, ctr, spill, sk, opt); });
+        simt::launch(grid, kSW * 32, sizeof(SWarp) * kSW, [=] { aggregate_stream_kernel<true, false>(recs, n, t, epoch, ctr, sk, opt); });
     else
-        simt::launch(grid, kWWarps * 32, sizeof(AggWSmem), [=] { aggregate_warp_kernel<false, false>(recs, n, t, epoch, ctr, spill, sk, opt); });
+        simt::launch(grid, kSW * 32, sizeof(SWarp) * kSW, [=] { aggregate_stream_kernel<false, false>(recs, n, t, epoch, ctr, sk, opt); });
 }
 }  // namespace
 
@@ -94,33 +94,9 @@ int k1_emul_ingest(void* h, const uint8_t* recs8, uint32_t n, unsigned grid, int
         case 3: run_k1<3>(e, recs, n, grid, opt); break;
         case 4: run_k1<4>(e, recs, n, grid, opt); break;
         case 5: run_k1<5>(e, recs, n, grid, opt); break;
-        case 11: {                                          // K1w with 16 warps per CTA and double-buffered sub-tiles
-            const uint32_t n_sub = (n + kWSub - 1) / kWSub;
-            const unsigned g = std::min<unsigned>(grid, (n_sub + 15) / 16);
-            const uint64_t epoch = e->epoch;
-            Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx; SketchParams sk{};
-            simt::launch(g, 16 * 32, sizeof(AggWSmemT<16>), [=] { aggregate_warp_kernel<false, false, false, false, 16>(recs, n, t, epoch, ctr, spill, sk, opt); });
-            break;
-        }
-        case 10: {                                          // K1w with 8 lanes per flow in the probe passes
-            const uint32_t n_sub = (n + kWSub - 1) / kWSub;
-            const unsigned g = std::min<unsigned>(grid, (n_sub + kWWarps - 1) / kWWarps);
-            const uint64_t epoch = e->epoch;
-            Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx; SketchParams sk{};
-            simt::launch(g, kWWarps * 32, sizeof(AggWSmem), [=] { aggregate_warp_kernel<false, false, false, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
-            break;
-        }
-        case 9: {                                           // K1w with warp-aggregated cache folds
-            const uint32_t n_sub = (n + kWSub - 1) / kWSub;
-            const unsigned g = std::min<unsigned>(grid, (n_sub + kWWarps - 1) / kWWarps);
-            const uint64_t epoch = e->epoch;
-            Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx; SketchParams sk{};
-            simt::launch(g, kWWarps * 32, sizeof(AggWSmem), [=] { aggregate_warp_kernel<false, false, true>(recs, n, t, epoch, ctr, spill, sk, opt); });
-            break;
-        }
-        case 8: {                                           // K1w, the warp-independent variant
-            const uint32_t n_sub = (n + kWSub - 1) / kWSub;
-            run_k1w(e, recs, n, std::min<unsigned>(grid, (n_sub + kWWarps - 1) / kWWarps), opt);
+        case 8: {                                           // K1s, the streaming kernel
+            const uint32_t n_sub = (n + kSSub - 1) / kSSub;
+            run_k1s(e, recs, n, std::min<unsigned>(grid, (n_sub + kSW - 1) / kSW), opt);
             break;
         }
         default: return -2;

@@ -1,10 +1,8 @@
 """KERNEL_MAP mode (bpf/flows.c:76-143,222-288: lookup, update_existing_flow, add_observed_intf, insert with
 BPF_NOEXIST, ring-buffer fallback) on the GPU against the oracle, through the C ABI.
 
-Status: the kernels' logic is checked on the CPU through their host emulation (tests/test_kmap_emulation.py, same
-streams); on the device the mode is still behind FA_EXPERIMENTAL_KERNEL_MAP=1 because no B200 run has confirmed it
-yet.  Run this file with that variable set to validate; without it the parity tests skip and only the "refused
-loudly" check runs."""
+The same streams also run through the host emulation of the kernel bodies (tests/test_kmap_emulation.py); this file
+is the device-side gate (first green B200 run: round 2, both FA_KMAP_IMPL values)."""
 import os
 
 import numpy as np
@@ -15,17 +13,13 @@ from common import gen_host
 from test_kmap_emulation import messy_stream
 
 pytestmark = pytest.mark.gpu
-ENABLED = os.environ.get("FA_EXPERIMENTAL_KERNEL_MAP", "") == "1"
-needs_kmap = pytest.mark.skipif(not ENABLED, reason="set FA_EXPERIMENTAL_KERNEL_MAP=1 to run KERNEL_MAP mode on the GPU")
 
 
-def test_kernel_map_mode_is_refused_loudly_unless_asked_for():
+def test_kernel_map_mode_refuses_accounter_only_flags():
     import netobserv_ebpf_agent_b200 as fa
-    if ENABLED:
-        pytest.skip("mode enabled for this run")
     with pytest.raises(fa.FlowAggError) as ei:
-        fa.FlowAggEngine(100, mode=fa.FA_MODE_KERNEL_MAP)
-    assert ei.value.code == -22 and "KERNEL_MAP" in str(ei.value)       # no silent fallback to ACCOUNTER semantics
+        fa.FlowAggEngine(100, mode=fa.FA_MODE_KERNEL_MAP, flags=fa.FA_F_NO_FULL_CUT)
+    assert ei.value.code == -22 and "KERNEL_MAP" in str(ei.value)
 
 
 @pytest.fixture(params=["2", "1"], autouse=True)
@@ -66,7 +60,6 @@ def check(recs, max_entries, max_batch, ringbuf=True, evict_every=None):
     assert st["spills"] == 0 and st["ringbuf_dropped"] == 0
 
 
-@needs_kmap
 @pytest.mark.parametrize("dist,n_keys", [(0, 500), (1, 20_000)])
 def test_generator_streams(dist, n_keys):
     recs = gen_host(seed=60, n=200_000, n_keys=n_keys, dist=dist)
@@ -74,7 +67,6 @@ def test_generator_streams(dist, n_keys):
     check(recs, 1 << 20, 30_011)
 
 
-@needs_kmap
 @pytest.mark.parametrize("seed", [11, 12, 13])
 def test_messy_stream_matches_the_sequential_map_update(seed):
     recs = messy_stream(seed, 60_000, 300)
@@ -82,7 +74,6 @@ def test_messy_stream_matches_the_sequential_map_update(seed):
     check(recs, 1 << 12, 997)
 
 
-@needs_kmap
 def test_many_interfaces_fill_the_observed_list():
     recs = messy_stream(21, 40_000, 40, n_ifaces=12)
     check(recs, 1 << 10, 40_000)
@@ -90,7 +81,6 @@ def test_many_interfaces_fill_the_observed_list():
     check(messy_stream(22, 5_000, 1, n_ifaces=30), 16, 5_000)
 
 
-@needs_kmap
 def test_full_map_spills_to_the_ring_buffer_or_counts():
     recs = messy_stream(31, 30_000, 2_000, tls=False)
     check(recs, 500, 30_000, ringbuf=True)
@@ -98,13 +88,11 @@ def test_full_map_spills_to_the_ring_buffer_or_counts():
     check(recs, 500, 4_096, ringbuf=False)
 
 
-@needs_kmap
 def test_eviction_between_batches_and_large_batch():
     check(messy_stream(41, 50_000, 800), 1 << 11, 2_048, evict_every=10_000)
     check(messy_stream(42, 2_000_000, 100_000, n_ifaces=3), 1 << 18, 1 << 20)
 
 
-@needs_kmap
 def test_committed_fixture():
     import netobserv_ebpf_agent_b200 as fa
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmap", "kmap_messy_seed11.npz"))
@@ -117,7 +105,6 @@ def test_committed_fixture():
     assert [st["observed_intf_missed"], st["hashmap_fail_create"]] == [int(x) for x in z["counters"]]
 
 
-@needs_kmap
 def test_kernel_map_base_with_feature_maps():
     """aggregated_flows as the base + the per-CPU feature maps, merged by LookupAndDeleteMap (tracer.go:1063-1157)."""
     import netobserv_ebpf_agent_b200 as fa
@@ -128,7 +115,7 @@ def test_kernel_map_base_with_feature_maps():
     allk = np.concatenate([keys, keys_of(82, 300)])
     add, dns = make_add(rng, allk, 20_000), make_dns(rng, allk, 20_000)
     om = O.FlowMap()
-    with fa.FlowAggEngine(1 << 13, mode=fa.FA_MODE_KERNEL_MAP, flags=fa.FA_F_ENABLE_RTT | fa.FA_F_ENABLE_DNS, max_batch=16_384) as eng:
+    with fa.FlowAggEngine(1 << 15, mode=fa.FA_MODE_KERNEL_MAP, flags=fa.FA_F_ENABLE_RTT | fa.FA_F_ENABLE_DNS, max_batch=16_384) as eng:
         eng.ingest_additional(add); eng.ingest(pk[:30_000]); eng.ingest_dns(dns); eng.ingest(pk[30_000:])
         om.fold_additional(add); missed = om.packets_kmap(pk); om.fold_dns(dns)
         compare(eng, om)
