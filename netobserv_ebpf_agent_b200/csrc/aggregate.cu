@@ -81,11 +81,11 @@ __device__ __forceinline__ void issue_tile_load(TeamSmem& s, const uint4* recs, 
     tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
 }
 
-// Reductions of one flow's folded totals onto its hot line.  floor_ns <= hot.nstart always
-// (immutable start mirror), `seen` are flag bits the hot line is known to hold already.
+// Reductions of one flow's folded totals onto the accumulators of its line.  floor_ns <= hot.nstart always
+// (immutable start mirror), `seen` are flag bits the accumulators are known to hold already.
 __device__ __forceinline__ void reduce_to_hot(const Table& t, uint32_t slot, uint64_t bytes, uint32_t packets,
                                               uint64_t ns, uint64_t end, uint32_t flags, uint64_t floor_ns, uint32_t seen) {
-    uint8_t* hot = reinterpret_cast<uint8_t*>(t.hot) + (size_t)slot * kHotBytes;
+    uint8_t* hot = reinterpret_cast<uint8_t*>(t.ident) + (size_t)slot * kIdentBytes + L_HOT;   // same line as the key
     red_add_u64(hot, bytes);
     if (ns > floor_ns) red_max_u64(hot + 8, ns);
     if (end) red_max_u64(hot + 16, end);
@@ -112,20 +112,25 @@ __device__ __forceinline__ void sketch_update(const SketchParams& sk, uint64_t p
 // General probe of one flow per 8-lane group (4 flows per call): claims empty slots, waits for
 // slots being published, walks collisions, marks descriptor mismatches.  Returns the slot
 // (kResSpill when the table is physically full) in every lane of the group.
+// img = rec_image(record, j): lanes 0,1,2,5,6,7 hold what line chunk j is compared with / stored from, lanes 3 and 4
+// the two chunks of the cold line (read only for flows with TAG_HAS_OBS, written only when non-zero).
 __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch, bool active, uint32_t start_slot,
-                                                  uint4 rchunk, bool cta_dirty, uint64_t ins_ns, int g, int j, uint4 cmask,
+                                                  uint4 img, bool cta_dirty, uint64_t ins_ns, int g, int j, uint4 cmask,
                                                   uint32_t& my_inserts, uint32_t* any_dirty) {
     uint64_t slot = start_slot;
     bool done = !active;
     uint32_t nprobe = 0, result = kResSpill;
     uint64_t reload_slot = ~0ull;
+    const bool cold_lane = j == 3 || j == 4;
+    const bool rec_obs = ((__ballot_sync(0xFFFFFFFFu, cold_lane && (img.x | img.y | img.z | img.w) != 0u) >> (g * 8)) & 0x18u) != 0u;
     for (;;) {
         uint4 line = make_uint4(0, 0, 0, 0);
-        if (!done) line = ld_cg_u4(&t.ident[slot * 8 + j]);
+        if (!done && !cold_lane) line = ld_cg_u4(&t.ident[slot * 8 + j]);
         const uint32_t tag_lo = __shfl_sync(0xFFFFFFFFu, line.z, g * 8 + 2);
         const uint32_t tag_hi = __shfl_sync(0xFFFFFFFFu, line.w, g * 8 + 2);
         const uint64_t tag = u64_of(tag_lo, tag_hi);
-        const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq4_masked(line, rchunk, cmask)) >> (g * 8)) & 0xFFu;
+        if (!done && cold_lane && (tag & TAG_HAS_OBS)) line = ld_cg_u4(&t.cold[slot * 2 + (j - 3)]);
+        const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq4_masked(line, img, cmask)) >> (g * 8)) & 0xFFu;
         const uint32_t state = (uint32_t)(tag & TAG_STATE_MASK);
         unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[slot * 8 + 2]) + 1;
         // Claim either an empty slot, or the base of a flow that so far exists only through feature
@@ -138,14 +143,15 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
             won = atomicCAS(tagp, expect, want) == expect ? (state == 0 ? 1u : 2u) : 0u;
         }
         won = __shfl_sync(0xFFFFFFFFu, won, g * 8 + 2);
-        if (won) {
-            uint4 v = and4(rchunk, cmask);
-            if (j == 3) {                                       // start mirror around eth_protocol
+        if (won) {                                              // the accumulators (chunks 3, 4) of a free slot are zero already
+            uint4 v = and4(img, cmask);
+            if (j == 5) {                                       // start mirror around eth_protocol
                 const uint64_t m48 = ins_ns >> 16;
                 v.x = (uint32_t)m48; v.y |= (uint32_t)(m48 >> 32) << 16;
             }
             if (j == 2) *reinterpret_cast<uint2*>(&t.ident[slot * 8 + 2]) = make_uint2(v.x, v.y);   // key tail only
-            else st_cg_u4(&t.ident[slot * 8 + j], v);
+            else if (!cold_lane) st_cg_u4(&t.ident[slot * 8 + j], v);
+            else if (rec_obs) st_cg_u4(&t.cold[slot * 2 + (j - 3)], v);
             __threadfence();
         }
         __syncwarp();
@@ -153,7 +159,7 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
         if (won) {
             if (j == 2) {
                 const unsigned long long pub = (epoch << TAG_EPOCH_SHIFT) | TAG_HAS_BASE | TAG_PUBLISHED |
-                                               (cta_dirty ? TAG_DIRTY : 0ull);
+                                               (rec_obs ? TAG_HAS_OBS : 0ull) | (cta_dirty ? TAG_DIRTY : 0ull);
                 *reinterpret_cast<volatile unsigned long long*>(tagp) = pub;
                 if (won == 1u) {                               // a base claim does not add a flow
                     my_inserts++;
@@ -171,7 +177,7 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
                 __threadfence();
             } else if ((eqb & 0x07u) == 0x07u) {
                 hit = true;
-                const bool desc_eq = (eqb & 0xF8u) == 0xF8u;
+                const bool desc_eq = (eqb & 0xF8u) == 0xF8u;       // bits 3, 4: the cold line (zero == absent) agrees too
                 if ((!desc_eq || cta_dirty) && j == 2) {
                     if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
                     *any_dirty = 1;
@@ -191,11 +197,7 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
 // kProf: per-warp cycle counters per phase (FA_PHASE_PROFILE=1), summed into prof[0..7].
 #define FA_PROF_MARK(i) do { if (kProf) { const long long now_ = clock64(); pacc[i] += now_ - pt; pt = now_; } } while (0)
 
-// kVar: experiment variants, separate instantiations so that the default kernel's code is untouched (FA_K1_OPT bits
-// 5, 6 and 7 select them at launch): 1 = ask L2 for the team's next tile while the current one is processed,
-// 2 = branch-free record compares in the fold phase (OR-accumulated differences instead of short-circuit tests),
-// 4 = 4 lanes per flow in the pipelined probe passes.
-template <bool kSketch, bool kProf, bool kDevN, int kVar = 0>
+template <bool kSketch, bool kProf, bool kDevN>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr,
                  uint32_t* __restrict__ spill_idx, SketchParams sk, unsigned long long* prof, uint32_t opt) {
@@ -227,7 +229,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     const int g = lane >> 3;                  // flow group inside the warp (4 groups of 8 lanes)
     const int j = lane & 7;                   // 16-byte chunk of the identity line handled by this lane
     const uint4 cmask = chunk_mask(j);
-    const int rc = rec_chunk_of_line_chunk(j);
+    const bool cold_lane = j == 3 || j == 4;          // these lanes hold the record's cold image, not a line chunk
     const uint32_t tmask = (uint32_t)t.mask;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t my_inserts = 0, my_spills = 0;
@@ -243,13 +245,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         const uint32_t cnt = min((uint32_t)kTile, n - first);
         mbar_wait(&s.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
-        if ((kVar & 1) && tid == 0) {
-            const uint32_t nt = tile_idx + tile_stride;
-            if (nt < n_tiles) {
-                const uint32_t nfirst = nt * kTile;
-                tma_prefetch_l2(recs + (size_t)nfirst * kRecChunks, min((uint32_t)kTile, n - nfirst) * kRecBytes);
-            }
-        }
 
         // ------------------------------------------------------ E: hash, cache / elect, fold duplicates
         {
@@ -265,19 +260,12 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 HotEntry& ce = cs.hot[((uint32_t)h >> 26) & (kHotEntries - 1)];
                 if (use_cache && *reinterpret_cast<volatile uint32_t*>(&ce.state) == 2u && ce.hash == (uint32_t)h) {
                     const uint4 r3 = R[3], r4 = R[4];
-                    bool same;
-                    if (kVar & 2) {
-                        uint32_t d = diff4_masked(ce.line[0], r0, chunk_mask(0)) | diff4_masked(ce.line[1], r1, chunk_mask(1)) |
-                                     diff4_masked(ce.line[2], r2, chunk_mask(2)) | diff4_masked(ce.line[3], r4, chunk_mask(3));
-#pragma unroll
-                        for (int c = 5; c < 9; c++) d |= diff4_masked(ce.line[c - 1], R[c], chunk_mask(c - 1));
-                        same = d == 0u;
-                    } else {
-                        same = eq4_masked(ce.line[0], r0, chunk_mask(0)) && eq4_masked(ce.line[1], r1, chunk_mask(1)) &&
-                               eq4_masked(ce.line[2], r2, chunk_mask(2)) && eq4_masked(ce.line[3], r4, chunk_mask(3));
-#pragma unroll
-                        for (int c = 5; c < 9; c++) same = same && eq4_masked(ce.line[c - 1], R[c], chunk_mask(c - 1));
-                    }
+                    // cached flows have no cold line (see the install): the record must not carry one either
+                    const uint4 r6 = R[6], r8 = R[8];
+                    bool same = eq4_masked(ce.line[0], r0, chunk_mask(0)) && eq4_masked(ce.line[1], r1, chunk_mask(1)) &&
+                                eq4_masked(ce.line[2], r2, chunk_mask(2)) && eq4_masked(ce.line[5], r4, chunk_mask(5)) &&
+                                eq4_masked(ce.line[6], R[5], chunk_mask(6)) &&
+                                eq4_masked(ce.line[7], make_uint4(r6.x, r8.y, r8.z, 0u), chunk_mask(7)) && rec_cold_nz(r6, R[7], r8) == 0u;
                     const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
                     const uint64_t v_ns = 0ull - v_start;
                     same = same && (v_start == 0 || (uint32_t)(v_ns >> 32) == ce.ns_hi) &&
@@ -305,11 +293,8 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         if (old == kRepEmpty) break;
                         const uint4* O = T + old * kRecChunks;
                         const uint4 o2 = O[2];
-                        const bool key_eq = (kVar & 2)
-                            ? (diff4_masked(o2, r2, chunk_mask(2)) | diff4_masked(O[0], r0, chunk_mask(0)) |
-                               diff4_masked(O[1], r1, chunk_mask(1))) == 0u
-                            : (eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
-                               eq4_masked(O[1], r1, chunk_mask(1)));
+                        const bool key_eq = eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
+                                            eq4_masked(O[1], r1, chunk_mask(1));
                         if (key_eq) {
                             // Same key.  Fold into that representative with 32-bit shared atomics when the high
                             // words of the timestamps agree (the common case); otherwise go to the table on our own.
@@ -333,17 +318,9 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                                 if (v_end) atomicMax(&A[5], (uint32_t)v_end);
                                 atomicAdd(&A[6], 1u);                // duplicates seen: cache candidacy
                                 // exact descriptor compare against the representative (74 bytes, padding masked)
-                                bool same;
-                                if (kVar & 2) {
-                                    uint32_t d = diff4_masked(O[4], r4, chunk_mask(3));
+                                bool same = eq4_masked(O[4], r4, rec_desc_mask(4));
 #pragma unroll
-                                    for (int c = 5; c < 9; c++) d |= diff4_masked(O[c], R[c], chunk_mask(c - 1));
-                                    same = d == 0u;
-                                } else {
-                                    same = eq4_masked(O[4], r4, chunk_mask(3));
-#pragma unroll
-                                    for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
-                                }
+                                for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], rec_desc_mask(c));
                                 if (!same) s.tdirty[old] = 1;
                             }
                             break;
@@ -378,114 +355,34 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             uint32_t ridx[kInflight];
             uint32_t slot[kInflight];
             uint32_t pend = 0;                                     // rounds of this lane group still to be probed
-            if (!(kVar & 4)) {
 #pragma unroll
-                for (int r = 0; r < kInflight; r++) {
-                    const uint32_t k = c0 + r * 4 + g;
-                    ridx[r] = 0;
-                    if (k < c_end) { pend |= 1u << r; ridx[r] = s.glist[k]; }
-                    slot[r] = s.hs[ridx[r]] & tmask;
-                }
+            for (int r = 0; r < kInflight; r++) {
+                const uint32_t k = c0 + r * 4 + g;
+                ridx[r] = 0;
+                if (k < c_end) { pend |= 1u << r; ridx[r] = s.glist[k]; }
+                slot[r] = s.hs[ridx[r]] & tmask;
             }
             uint32_t nslow = 0;
-            if (kVar & 4) {
-                // Variant: 4 lanes per flow, each lane owns line chunks j4 and j4 + 4.  Same 16 lines in flight per
-                // warp, but one round now serves 8 flows, so the per-round bookkeeping (ballots, result stores,
-                // slow-list compaction) is issued half as often.  Costs one more L1 wavefront per line.
-                const int g4 = lane >> 2, j4 = lane & 3;
-                const uint4 cmaskA = chunk_mask(j4), cmaskB = chunk_mask(j4 + 4);
-                const int rcA = rec_chunk_of_line_chunk(j4), rcB = j4 + 5;
-                constexpr int kRounds = 2;
-                uint32_t ridx4[kRounds], slot4[kRounds];
-                uint32_t pend4 = 0;
-#pragma unroll
-                for (int r = 0; r < kRounds; r++) {
-                    const uint32_t k = c0 + r * 8 + g4;
-                    ridx4[r] = 0;
-                    if (k < c_end) { pend4 |= 1u << r; ridx4[r] = s.glist[k]; }
-                    slot4[r] = s.hs[ridx4[r]] & tmask;
-                }
-#pragma unroll 1
-                for (int pass = 0; pass < 2; pass++) {
-                    uint4 lineA[kRounds], lineB[kRounds];
-#pragma unroll
-                    for (int r = 0; r < kRounds; r++) {
-                        lineA[r] = make_uint4(0, 0, 0, 0); lineB[r] = make_uint4(0, 0, 0, 0);
-                        if ((pend4 >> r) & 1u) {
-                            lineA[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4]);
-                            lineB[r] = ld_cg_u4(&t.ident[(size_t)slot4[r] * 8 + j4 + 4]);
-                        }
-                    }
-#pragma unroll
-                    for (int r = 0; r < kRounds; r++) {
-                        const bool act = (pend4 >> r) & 1u;
-                        const uint4* RR = T + ridx4[r] * kRecChunks;
-                        bool eqA = eq4_masked(lineA[r], RR[rcA], cmaskA);
-                        const bool eqB = eq4_masked(lineB[r], RR[rcB], cmaskB);
-                        const uint64_t tag = u64_of(lineA[r].z, lineA[r].w);   // meaningful in lane j4 == 2 only
-                        bool settled = false;
-                        if (j4 == 2) {
-                            settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
-                                      (tag >> TAG_EPOCH_SHIFT) != epoch;
-                            eqA = eqA && settled;
-                        }
-                        // common case first: every flow of the round is settled, matches in all 8 chunks and has no
-                        // tile-local descriptor conflict -> one vote
-                        const bool clean = j4 != 2 || s.tdirty[ridx4[r]] == 0;
-                        const uint32_t okm = __ballot_sync(0xFFFFFFFFu, eqA && eqB && clean);
-                        const uint32_t actm = __ballot_sync(0xFFFFFFFFu, act);
-                        if ((okm | ~actm) == 0xFFFFFFFFu) {
-                            if (act && j4 == 0) s.res[ridx4[r]] = slot4[r];
-                            if (act && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
-                            if (act && j4 == 2) s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
-                            pend4 &= ~(1u << r);
-                            continue;
-                        }
-                        const uint32_t eqb = ((__ballot_sync(0xFFFFFFFFu, eqA) >> (g4 * 4)) & 0xFu) |
-                                             (((__ballot_sync(0xFFFFFFFFu, eqB) >> (g4 * 4)) & 0xFu) << 4);
-                        const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g4 * 4 + 2)) & 1u;
-                        const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches
-                        if (fast && j4 == 0) s.res[ridx4[r]] = slot4[r];
-                        if (fast && j4 == 3) { s.mir_lo[ridx4[r]] = lineA[r].x; s.mir_hi[ridx4[r]] = (uint16_t)(lineA[r].y >> 16); }
-                        if (fast && j4 == 2) {
-                            s.fseen[ridx4[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
-                            if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx4[r]] != 0) {
-                                unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot4[r] * 8 + 2]) + 1;
-                                if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
-                                cs.any_dirty = 1;
-                            }
-                        }
-                        const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
-                        const bool to_slow = act && !fast && !collide;
-                        if (collide) slot4[r] = (slot4[r] + 1) & tmask;
-                        else pend4 &= ~(1u << r);
-                        const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j4 == 0);
-                        if (slowb) {
-                            if (to_slow && j4 == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx4[r];
-                            nslow += __popc(slowb);
-                        }
-                    }
-                    if (!__any_sync(0xFFFFFFFFu, pend4 != 0u)) break;
-                }
-            } else {
             // 8 lanes per flow, 16 identity lines in flight per warp; pass 0 = home slot, pass 1 = next slot for
             // the flows whose home slot is held by another settled flow
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
 #pragma unroll
-                for (int r = 0; r < kInflight; r++) {
+                for (int r = 0; r < kInflight; r++) {                      // 96 of the line's 128 bytes: the accumulators stay in L2
                     line[r] = make_uint4(0, 0, 0, 0);
-                    if ((pend >> r) & 1u) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
+                    if (((pend >> r) & 1u) && !cold_lane) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
                 }
 #pragma unroll
                 for (int r = 0; r < kInflight; r++) {
                     const bool act = (pend >> r) & 1u;
-                    const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
+                    // lanes 3, 4 compare the record's cold image with zero: a flow with a cold line (TAG_HAS_OBS) is not
+                    // "settled" here and goes to the general loop, which reads it
+                    const uint4 rchunk = rec_image(T + ridx[r] * kRecChunks, j);
                     bool eq = eq4_masked(line[r], rchunk, cmask);
                     const uint64_t tag = u64_of(line[r].z, line[r].w);  // meaningful in lane j == 2 only
                     bool settled = false;
                     if (j == 2) {
-                        settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                        settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE | TAG_HAS_OBS)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
                                   (tag >> TAG_EPOCH_SHIFT) != epoch;
                         eq = eq && settled;
                     }
@@ -493,7 +390,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                     const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g * 8 + 2)) & 1u;
                     const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches
                     if (fast && j == 0) s.res[ridx[r]] = slot[r];
-                    if (fast && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
+                    if (fast && j == 5) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
                     if (fast && j == 2) {
                         s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
                         if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[r]] != 0) {
@@ -519,7 +416,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 }
                 if (!__any_sync(0xFFFFFFFFu, pend != 0u)) break;
             }
-            }
             __syncwarp();
             if (lane == 0) { FA_EMUL_COUNT(0, c_end - c0); FA_EMUL_COUNT(1, nslow); }
             if (kProf && lane == 0) { c_reps += c_end - c0; c_slow += nslow; }
@@ -528,7 +424,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint32_t k = base + g;
                 const bool act = k < nslow;
                 const uint32_t ri = act ? s.slow[warp][k] : 0;
-                const uint4 rchunk = T[ri * kRecChunks + rc];
+                const uint4 rchunk = rec_image(T + ri * kRecChunks, j);
                 const uint4 c2 = T[ri * kRecChunks + 2];
                 const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
                 const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
@@ -536,7 +432,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                                                    dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &cs.any_dirty);
                 if (act && j == 0) s.res[ri] = got;
                 if (act && j == 2) s.fseen[ri] = 0;                 // unknown: issue every reduction
-                if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
+                if (act && j == 5) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
             }
             __syncwarp();
             FA_PROF_MARK(4);                                       // general probe loop
@@ -574,7 +470,8 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         ce.hash = hh; ce.slot = my_slot;
                         ce.ns_hi = (uint32_t)(v_ns >> 32); ce.end_hi = (uint32_t)(v_end >> 32);
                         __threadfence_block();
-                        *reinterpret_cast<volatile uint32_t*>(&ce.state) = 2u;
+                        // only flows without a cold line are cached (the cache compares the 128-byte line alone)
+                        *reinterpret_cast<volatile uint32_t*>(&ce.state) = (ce.line[2].z & (uint32_t)TAG_HAS_OBS) ? 0u : 2u;
                         if (kProf) c_install++;
                     }
                 }
@@ -634,7 +531,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         if (ce.state == 2u) {
             const uint32_t* A = ce.acc;
             const uint64_t tag = u64_of(ce.line[2].z, ce.line[2].w);
-            const uint64_t floor_ns = u64_of(ce.line[3].x, ce.line[3].y >> 16) << 16;
+            const uint64_t floor_ns = u64_of(ce.line[5].x, ce.line[5].y >> 16) << 16;
             // ns / end windows: an untouched window (0) reads as a value no larger than the installing
             // record's own, which the table already holds -> a harmless no-op max.
             reduce_to_hot(t, ce.slot, u64_of(A[0], A[1]), A[2], u64_of(A[4], ce.ns_hi), u64_of(A[5], ce.end_hi), A[3],
@@ -719,7 +616,7 @@ struct SCarry { uint32_t h32, home; bool probe; };
 template <bool kSketch>
 __device__ __forceinline__ void scache_flush(const Table& t, const SketchParams& sk, const SCacheEntry& e) {
     const uint64_t tag = u64_of(e.line[2].z, e.line[2].w);
-    const uint64_t floor_ns = u64_of(e.line[3].x, e.line[3].y >> 16) << 16;
+    const uint64_t floor_ns = u64_of(e.line[5].x, e.line[5].y >> 16) << 16;
     reduce_to_hot(t, e.slot, e.bytes, e.packets, e.ns, e.end, e.flags, floor_ns, (uint32_t)(tag >> TAG_FLAGS_SHIFT) & 0xFFFFu);
     if (kSketch) {
         const uint4 k0 = e.line[0], k1 = e.line[1], k2 = e.line[2];
@@ -754,10 +651,11 @@ __device__ __forceinline__ SCarry stream_front(SWarp& s, const uint4* Rbuf, uint
         ci = h32 >> 27;
         const SCacheEntry& ce = s.cache[ci];
         if (use_cache && ce.state != 0u && ce.hash == h32) {
-            uint32_t d = diff4_masked(ce.line[0], r0, chunk_mask(0)) | diff4_masked(ce.line[1], r1, chunk_mask(1)) |
-                         diff4_masked(ce.line[2], r2, chunk_mask(2));
-#pragma unroll
-            for (int c = 3; c < 8; c++) d |= diff4_masked(ce.line[c], R[c + 1], chunk_mask(c));
+            const uint4 r6 = R[6], r8 = R[8];                       // cached flows have no cold line: neither may the record
+            const uint32_t d = diff4_masked(ce.line[0], r0, chunk_mask(0)) | diff4_masked(ce.line[1], r1, chunk_mask(1)) |
+                               diff4_masked(ce.line[2], r2, chunk_mask(2)) | diff4_masked(ce.line[5], R[4], chunk_mask(5)) |
+                               diff4_masked(ce.line[6], R[5], chunk_mask(6)) |
+                               diff4_masked(ce.line[7], make_uint4(r6.x, r8.y, r8.z, 0u), chunk_mask(7)) | rec_cold_nz(r6, R[7], r8);
             hit = d == 0u;
         }
     }
@@ -798,24 +696,27 @@ __device__ __forceinline__ SCarry stream_front(SWarp& s, const uint4* Rbuf, uint
         const uint32_t k = base + g;
         const uint32_t src = k < npr ? (uint32_t)s.list[k] : 0u;
         const uint32_t slot = __shfl_sync(0xFFFFFFFFu, home, (int)src);
-        if (k < npr) cp_async16(&Lbuf[src * 8 + (j ^ (src & 7))], &t.ident[(size_t)slot * 8 + j]);
+        if (k < npr && j != 3 && j != 4)                               // 96 of the 128 bytes: the accumulators stay in L2
+            cp_async16(&Lbuf[src * 8 + (j ^ (src & 7))], &t.ident[(size_t)slot * 8 + j]);
     }
     cp_async_commit();
     FA_EMUL_COUNT(0, lane == 0 ? npr : 0);
     return SCarry{h32, home, probe};
 }
 
-// One thread checks a whole identity line against its record.  Returns 0 = this flow, settled; 1 = another settled
-// flow lives here; 2 = anything else (empty, being published, born in this launch, feature-only entry).
-__device__ __forceinline__ int line_verdict(const uint4* R, uint4 l0, uint4 l1, uint4 l2, uint4 l3, uint4 l4, uint4 l5, uint4 l6, uint4 l7,
+// One thread checks a whole line against its record.  Returns 0 = this flow, settled; 1 = another settled flow lives
+// here; 2 = anything else (empty, being published, born in this launch, feature-only entry, flow with a cold line).
+__device__ __forceinline__ int line_verdict(const uint4* R, uint4 l0, uint4 l1, uint4 l2, uint4 l5, uint4 l6, uint4 l7,
                                             uint64_t epoch, uint32_t& ddesc) {
     const uint64_t tag = u64_of(l2.z, l2.w);
-    const bool settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) && (tag >> TAG_EPOCH_SHIFT) != epoch;
+    const bool settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE | TAG_HAS_OBS)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                         (tag >> TAG_EPOCH_SHIFT) != epoch;
     if (!settled) return 2;
     const uint32_t dkey = diff4_masked(l0, R[0], chunk_mask(0)) | diff4_masked(l1, R[1], chunk_mask(1)) | diff4_masked(l2, R[2], chunk_mask(2));
     if (dkey) return 1;
-    ddesc = diff4_masked(l3, R[4], chunk_mask(3)) | diff4_masked(l4, R[5], chunk_mask(4)) | diff4_masked(l5, R[6], chunk_mask(5)) |
-            diff4_masked(l6, R[7], chunk_mask(6)) | diff4_masked(l7, R[8], chunk_mask(7));
+    const uint4 r6 = R[6], r8 = R[8];
+    ddesc = diff4_masked(l5, R[4], chunk_mask(5)) | diff4_masked(l6, R[5], chunk_mask(6)) |
+            diff4_masked(l7, make_uint4(r6.x, r8.y, r8.z, 0u), chunk_mask(7)) | rec_cold_nz(r6, R[7], r8);
     return 0;
 }
 
@@ -833,19 +734,18 @@ __device__ __forceinline__ void stream_back(SWarp& s, const uint4* Rbuf, const u
     if (c.probe) {
         const uint4* L = Lbuf + lane * 8;
         const int sw = lane & 7;
-        uint4 l2 = L[2 ^ sw], l3 = L[3 ^ sw];
-        int v = line_verdict(R, L[0 ^ sw], L[1 ^ sw], l2, l3, L[4 ^ sw], L[5 ^ sw], L[6 ^ sw], L[7 ^ sw], epoch, ddesc);
+        uint4 l2 = L[2 ^ sw], l5 = L[5 ^ sw];
+        int v = line_verdict(R, L[0 ^ sw], L[1 ^ sw], l2, l5, L[6 ^ sw], L[7 ^ sw], epoch, ddesc);
         at_home = v == 0;
         if (v == 1) {                                                  // another flow at home: look one slot further, now
             slot = (slot + 1) & tmask;
             const uint4* G = &t.ident[(size_t)slot * 8];
-            l2 = ld_cg_u4(G + 2); l3 = ld_cg_u4(G + 3);
-            v = line_verdict(R, ld_cg_u4(G), ld_cg_u4(G + 1), l2, l3, ld_cg_u4(G + 4), ld_cg_u4(G + 5), ld_cg_u4(G + 6), ld_cg_u4(G + 7),
-                             epoch, ddesc);
+            l2 = ld_cg_u4(G + 2); l5 = ld_cg_u4(G + 5);
+            v = line_verdict(R, ld_cg_u4(G), ld_cg_u4(G + 1), l2, l5, ld_cg_u4(G + 6), ld_cg_u4(G + 7), epoch, ddesc);
         }
         if (v == 0) {
             const uint64_t tag = u64_of(l2.z, l2.w);
-            floor_ns = u64_of(l3.x, l3.y >> 16) << 16;
+            floor_ns = u64_of(l5.x, l5.y >> 16) << 16;
             seen = (uint32_t)(tag >> TAG_FLAGS_SHIFT) & 0xFFFFu;
             if (ddesc) {                                               // descriptor differs: ordered re-fold
                 if (!(tag & TAG_DIRTY))
@@ -864,12 +764,11 @@ __device__ __forceinline__ void stream_back(SWarp& s, const uint4* Rbuf, const u
         FA_EMUL_COUNT(1, lane == 0 ? nslow : 0);
         const int g = lane >> 3, j = lane & 7;
         const uint4 cmask = chunk_mask(j);
-        const int rc = rec_chunk_of_line_chunk(j);
         for (uint32_t base = 0; base < nslow; base += 4) {
             const uint32_t k = base + g;
             const bool act = k < nslow;
             const uint32_t ri = act ? (uint32_t)s.slow[k] : 0u;
-            const uint4 rchunk = Rbuf[ri * kRecChunks + rc];
+            const uint4 rchunk = rec_image(Rbuf + ri * kRecChunks, j);
             const uint4 c2 = Rbuf[ri * kRecChunks + 2];
             const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
             const uint32_t start_slot = __shfl_sync(0xFFFFFFFFu, c.home, (int)ri);
@@ -912,7 +811,7 @@ __device__ __forceinline__ void stream_back(SWarp& s, const uint4* Rbuf, const u
         if (go) {
             if (lane == src && e.state != 0u) scache_flush<kSketch>(t, sk, e);
             __syncwarp();
-            if (lane < 8) e.line[lane] = Lbuf[src * 8 + (lane ^ (src & 7))];
+            if (lane < 8 && lane != 3 && lane != 4) e.line[lane] = Lbuf[src * 8 + (lane ^ (src & 7))];
             if (lane == src) {
                 e.bytes = 0; e.ns = 0; e.end = 0; e.packets = 0; e.flags = 0;
                 e.hash = c.h32; e.slot = slot; e.hits = 0; e.state = 1u;
@@ -1055,12 +954,16 @@ __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint
         unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&L[2]) + 1;
         const unsigned long long tag = *tagp;
         const bool is_new = (tag >> TAG_EPOCH_SHIFT) == epoch;
-        // current descriptor state: line chunks 3..7 <-> record chunks 4..8
-        uint4 d3 = L[3], d4 = L[4], d5 = L[5], d6 = L[6], d7 = L[7];
-        const uint32_t mir_lo = d3.x, mir_hi = d3.y & 0xFFFF0000u;    // immutable start mirror stays
+        // current descriptor state as record chunks 4..8 (d3 .. d7), rebuilt from line chunks 5, 6, 7 and the cold line
+        const uint4 l5 = L[5], l6 = L[6], l7 = L[7];
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
+        if (tag & TAG_HAS_OBS) { c0 = t.cold[slot * 2]; c1 = t.cold[slot * 2 + 1]; }
+        const uint32_t mir_lo = l5.x, mir_hi = l5.y & 0xFFFF0000u;      // immutable start mirror stays
+        uint4 d3 = make_uint4(0u, l5.y & 0xFFFFu, l5.z, l5.w), d4 = l6, d5 = make_uint4(l7.x, c0.x, c0.y, c0.z),
+              d6 = make_uint4(c0.w, c1.x, c1.y, c1.z), d7 = make_uint4(c1.w, l7.y, l7.z, 0u);
         if (is_new) {                                      // state = the flow's first record, whole (account.go:95)
             const uint4* F = recs + (size_t)(~sc.nfirst) * kRecChunks;
-            d3 = and4(F[4], chunk_mask(3)); d4 = F[5]; d5 = and4(F[6], chunk_mask(5)); d6 = F[7]; d7 = and4(F[8], chunk_mask(7));
+            d3 = and4(F[4], rec_desc_mask(4)); d4 = F[5]; d5 = and4(F[6], rec_desc_mask(6)); d6 = F[7]; d7 = and4(F[8], rec_desc_mask(8));
         }
         // eth_protocol / dscp / sampling: last non-zero in stream order (flow_content.go:45-47,54-59)
         if (sc.eth)  { const uint4 x = recs[(size_t)(sc.eth - 1) * kRecChunks + 4]; d3.y = x.y & 0xFFFFu; }
@@ -1075,8 +978,16 @@ __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint
             const uint4 x4 = recs[(size_t)(~sc.ndmac) * kRecChunks + 4], x5 = recs[(size_t)(~sc.ndmac) * kRecChunks + 5];
             d3.w = (d3.w & 0xFFFFu) | (x4.w & 0xFFFF0000u); d4.x = x5.x;
         }
-        d3.x = mir_lo; d3.y = (d3.y & 0xFFFFu) | mir_hi;
-        L[3] = d3; L[4] = d4; L[5] = d5; L[6] = d6; L[7] = d7;
+        L[5] = make_uint4(mir_lo, (d3.y & 0xFFFFu) | mir_hi, d3.z, d3.w);
+        L[6] = d4;
+        L[7] = make_uint4(d5.x, d7.y, d7.z, 0u);
+        const uint32_t obs = rec_cold_nz(d5, d6, d7);
+        if (obs || (tag & TAG_HAS_OBS)) {                  // the cold line of a flow without TAG_HAS_OBS is zero and stays untouched
+            t.cold[slot * 2] = make_uint4(d5.y, d5.z & 0xFFFFu, d5.w, d6.x);
+            t.cold[slot * 2 + 1] = make_uint4(d6.y, d6.z, d6.w, d7.x);
+        }
+        if (obs && !(tag & TAG_HAS_OBS)) atomicOr(tagp, (unsigned long long)TAG_HAS_OBS);
+        if (!obs && (tag & TAG_HAS_OBS)) atomicAnd(tagp, ~(unsigned long long)TAG_HAS_OBS);
         atomicAnd(tagp, ~(unsigned long long)TAG_DIRTY);
         fixed++;
     }
@@ -1107,11 +1018,6 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
         cudaFuncSetAttribute(aggregate_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(aggregate_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(aggregate_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(aggregate_kernel<false, false, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
     const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
@@ -1145,16 +1051,6 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
         aggregate_kernel<true, false, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
     else if (dev_n)
         aggregate_kernel<false, false, true><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
-    else if ((a.opt & 224u) == 128u)                      // experiment variants (plain ingest only)
-        aggregate_kernel<false, false, false, 4><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
-    else if ((a.opt & 224u) == 160u)
-        aggregate_kernel<false, false, false, 5><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
-    else if ((a.opt & 96u) == 32u)
-        aggregate_kernel<false, false, false, 1><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
-    else if ((a.opt & 96u) == 64u)
-        aggregate_kernel<false, false, false, 2><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
-    else if ((a.opt & 96u) == 96u)
-        aggregate_kernel<false, false, false, 3><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
     else
         aggregate_kernel<false, false, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
 #undef FA_K1_ARGS

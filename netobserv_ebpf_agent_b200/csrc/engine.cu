@@ -442,8 +442,8 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     CU(cudaMalloc(&e->table.ident, slots * fa::kIdentBytes));
     CU(cudaMemsetAsync(e->table.ident, 0, slots * fa::kIdentBytes, e->stream));
     if (!kmap) {
-        CU(cudaMalloc(&e->table.hot, slots * fa::kHotBytes));
-        CU(cudaMemsetAsync(e->table.hot, 0, slots * fa::kHotBytes, e->stream));
+        CU(cudaMalloc(&e->table.cold, slots * fa::kColdBytes));
+        CU(cudaMemsetAsync(e->table.cold, 0, slots * fa::kColdBytes, e->stream));
     } else {
         if (slots > (1ull << 30)) return fail(FA_E_INVAL, "fa_create: KERNEL_MAP mode supports at most 2^30 slots");
         CU(cudaMalloc(&e->km_met, slots * fa::kMetLineBytes));
@@ -550,7 +550,7 @@ void fa_destroy(fa_engine* e) {
         cudaFree(e->d_prof);
     }
     if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
-    cudaFree(e->table.ident); cudaFree(e->table.hot); cudaFree(e->table.occ); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns);
+    cudaFree(e->table.ident); cudaFree(e->table.cold); cudaFree(e->table.occ); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns);
     cudaFree(e->d_ctr); if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_live_ring) cudaFreeHost(e->h_live_ring);
     for (int i = 0; i < fa_engine::kLiveRing; i++) if (e->ev_live[i]) cudaEventDestroy(e->ev_live[i]);

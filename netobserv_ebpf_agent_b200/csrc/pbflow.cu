@@ -254,7 +254,7 @@ constexpr int kPbStage = 64 * 1024;            // shared-memory image of the CTA
 __global__ void __launch_bounds__(kPbCta)
 pb_write_kernel(PbInputs in, uint32_t n, PbParams P, const unsigned long long* __restrict__ offsets, const uint32_t* __restrict__ sizes,
                 uint8_t* __restrict__ out, uint8_t* __restrict__ keys_out) {
-    extern __shared__ __align__(16) uint8_t stage[];
+    FA_DYN_SMEM(stage);
     const uint32_t first = blockIdx.x * kPbCta;
     const uint32_t last = min(n, first + kPbCta);
     const unsigned long long base = offsets[first], total = offsets[last] - base;

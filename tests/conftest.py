@@ -28,21 +28,38 @@ def _have_gpu():
 _EMULATED = os.environ.get("FA_EMULATED_GPU") == "1"
 
 
-@pytest.fixture(scope="session", autouse=_EMULATED)
-def _emulated_engine():
+def _load_engine_emulation():
     import ctypes
     import netobserv_ebpf_agent_b200._lib as L
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from emul_build import EMUL, build, csrc
     so = build("engine_emul", csrc("engine.cu", "aggregate.cu", "evict.cu", "features.cu", "kmap.cu", "kmap_body.cuh",
-                                   "misc_kernels.cu", "common.cuh", "kernels.cuh", "flowgen.h") + [os.path.join(EMUL, "simt.h")])
+                                   "misc_kernels.cu", "pbflow.cu", "common.cuh", "kernels.cuh", "flowgen.h") +
+               [os.path.join(EMUL, "simt.h"), os.path.join(ROOT, "include", "flowagg.h")])
     lib = ctypes.CDLL(so)
     for name, (res, args) in L.SIGNATURES.items():
         f = getattr(lib, name)
         f.restype, f.argtypes = res, args
+    return L, lib
+
+
+@pytest.fixture(scope="session", autouse=_EMULATED)
+def _emulated_engine():
+    L, lib = _load_engine_emulation()
     saved, L._lib = L._lib, lib
     yield lib
     L._lib = saved
+
+
+@pytest.fixture(scope="module")
+def engine_emul():
+    """The whole C ABI on the CPU (tests/emul/engine_emul.cpp) swapped in for libflowagg.so for one test module."""
+    L, lib = _load_engine_emulation()
+    saved, L._lib = L._lib, lib
+    try:
+        yield lib
+    finally:
+        L._lib = saved
 
 
 def pytest_collection_modifyitems(config, items):

@@ -24,6 +24,7 @@
 #include "../../netobserv_ebpf_agent_b200/csrc/features.cu"
 #include "../../netobserv_ebpf_agent_b200/csrc/kmap.cu"
 #include "../../netobserv_ebpf_agent_b200/csrc/misc_kernels.cu"
+#include "../../netobserv_ebpf_agent_b200/csrc/pbflow.cu"
 
 // ------------------------------------------------------------------------------------------------ CUDA runtime double
 namespace {
@@ -102,10 +103,12 @@ namespace {
 // grid sizes follow the product's formulas with the fake device's 4 SMs, capped so that a launch stays a few
 // hundred OS threads; CTAs of kernels with static shared arrays run one after the other
 unsigned small(unsigned grid, unsigned cap = 3) { return std::max(1u, std::min(grid, cap)); }
-void launch_serial(unsigned grid, unsigned block, const std::function<void()>& body) {
+void launch_serial(unsigned grid, unsigned block, const std::function<void()>& body, size_t smem_bytes = 0) {
+    std::vector<uint8_t> smem(smem_bytes + 256);
     for (unsigned b = 0; b < grid; b++) {
         std::vector<std::thread> th;
         simt::Cta cta; cta.sync_all = std::make_unique<simt::Barrier>(block);
+        cta.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~(uintptr_t)127);
         for (unsigned w = 0; w < block / 32; w++) cta.warps.push_back(std::make_unique<simt::Warp>());
         for (unsigned t = 0; t < block; t++)
             th.emplace_back([&, t] {
@@ -138,7 +141,6 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t) {
         if (sk.cms && dev_n) simt::launch(g, kCtaThreads, sm, [=] { aggregate_kernel<true, false, true>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt); });
         else if (sk.cms) simt::launch(g, kCtaThreads, sm, [=] { aggregate_kernel<true, false, false>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt); });
         else if (dev_n) simt::launch(g, kCtaThreads, sm, [=] { aggregate_kernel<false, false, true>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt); });
-        else if ((a.opt & 224u) == 128u) simt::launch(g, kCtaThreads, sm, [=] { aggregate_kernel<false, false, false, 4>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt); });
         else simt::launch(g, kCtaThreads, sm, [=] { aggregate_kernel<false, false, false>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt); });
     }
     FixupScratch* sc = a.scratch; const uint32_t ss = a.scratch_slots;
@@ -185,6 +187,25 @@ int launch_evict_features(const Table& table, const uint32_t* slot_of_out, unsig
     if (!n_out) return 0;
     Table t = table;
     simt::launch(2, 256, 0, [=] { evict_features_kernel(t, slot_of_out, n_out, out_recs, out_dns, out_add, out_present); });
+    return 1;
+}
+
+int launch_pb_sizes(const PbInputs& in_, uint32_t n, const PbParams& P_, uint32_t* sizes, unsigned long long* offsets,
+                    unsigned long long* block_sums, int, cudaStream_t) {
+    if (!n) return 0;
+    PbInputs in = in_; PbParams P = P_;
+    const uint32_t nb = (n + kScanBlock - 1) / kScanBlock;
+    simt::launch(2, 256, 0, [=] { pb_size_kernel(in, n, P, sizes); });
+    launch_serial(nb, kScanBlock, [=] { pb_scan_block_kernel(sizes, n, P.wrap, offsets, block_sums); });
+    launch_serial(1, kScanBlock, [=] { pb_scan_sums_kernel(block_sums, nb); });
+    launch_serial(nb, kScanBlock, [=] { pb_scan_add_kernel(offsets, n, block_sums, sizes, P.wrap); });
+    return 4;
+}
+int launch_pb_write(const PbInputs& in_, uint32_t n, const PbParams& P_, const unsigned long long* offsets, const uint32_t* sizes,
+                    uint8_t* out, uint8_t* keys_out, cudaStream_t) {
+    if (!n) return 0;
+    PbInputs in = in_; PbParams P = P_;
+    launch_serial((n + kPbCta - 1) / kPbCta, kPbCta, [=] { pb_write_kernel(in, n, P, offsets, sizes, out, keys_out); }, kPbStage);
     return 1;
 }
 

@@ -30,18 +30,17 @@ void* zalloc(size_t bytes) {
     memset(p, 0, bytes ? bytes : 1024);
     return p;
 }
-template <int kVar>
 void run_k1(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt) {
     const uint64_t epoch = e->epoch;
     Table t = e->t; Counters* ctr = e->ctr; uint32_t* spill = e->spill_idx;
     SketchParams sk = e->sk;
-    if (sk.cms && kVar == 0)
+    if (sk.cms)
         simt::launch(grid, kCtaThreads, sizeof(AggSmem), [=] {
-            aggregate_kernel<true, false, false, 0>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
+            aggregate_kernel<true, false, false>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
         });
     else
         simt::launch(grid, kCtaThreads, sizeof(AggSmem), [=] {
-            aggregate_kernel<false, false, false, kVar>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
+            aggregate_kernel<false, false, false>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
         });
 }
 void run_k1s(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt) {
@@ -64,7 +63,7 @@ void* k1_emul_new(uint64_t max_entries, uint64_t max_batch) {
     e->slots = slots; e->max_batch = max_batch;
     e->t.mask = slots - 1;
     e->t.ident = static_cast<uint4*>(zalloc(slots * kIdentBytes));
-    e->t.hot = static_cast<uint4*>(zalloc(slots * kHotBytes));
+    e->t.cold = static_cast<uint4*>(zalloc(slots * kColdBytes));
     e->t.occ = static_cast<uint32_t*>(zalloc(slots / 8));
     e->ctr = static_cast<Counters*>(zalloc(sizeof(Counters)));
     uint32_t ss = 1024; while ((uint64_t)ss < 2 * max_batch) ss <<= 1;
@@ -75,7 +74,7 @@ void* k1_emul_new(uint64_t max_entries, uint64_t max_batch) {
 }
 void k1_emul_free(void* h) {
     Emul* e = static_cast<Emul*>(h);
-    free(e->t.ident); free(e->t.hot); free(e->t.occ); free(e->ctr); free(e->scratch); free(e->spill_idx);
+    free(e->t.ident); free(e->t.cold); free(e->t.occ); free(e->ctr); free(e->scratch); free(e->spill_idx);
     delete e;
 }
 
@@ -88,12 +87,7 @@ int k1_emul_ingest(void* h, const uint8_t* recs8, uint32_t n, unsigned grid, int
     const uint32_t n_tiles = (n + kTile - 1) / kTile;
     grid = std::min<unsigned>(grid, (n_tiles + kTeams - 1) / kTeams);
     switch (var) {
-        case 0: run_k1<0>(e, recs, n, grid, opt); break;
-        case 1: run_k1<1>(e, recs, n, grid, opt); break;
-        case 2: run_k1<2>(e, recs, n, grid, opt); break;
-        case 3: run_k1<3>(e, recs, n, grid, opt); break;
-        case 4: run_k1<4>(e, recs, n, grid, opt); break;
-        case 5: run_k1<5>(e, recs, n, grid, opt); break;
+        case 0: run_k1(e, recs, n, grid, opt); break;
         case 8: {                                           // K1s, the streaming kernel
             const uint32_t n_sub = (n + kSSub - 1) / kSSub;
             run_k1s(e, recs, n, std::min<unsigned>(grid, (n_sub + kSW - 1) / kSW), opt);

@@ -13,29 +13,9 @@ import pytest
 
 import oracle_lib as O
 from common import assert_same_generations, gen_host, gpu_generations, oracle_generations
-from emul_build import EMUL, build, csrc
 
 # a wedged emulation (it is thousands of OS threads) must not hang the suite: pytest-timeout, if installed
 pytestmark = pytest.mark.timeout(900)
-
-
-@pytest.fixture(scope="module")
-def engine_emul():
-    import netobserv_ebpf_agent_b200._lib as L
-    so = build("engine_emul", csrc("engine.cu", "aggregate.cu", "evict.cu", "features.cu", "kmap.cu", "kmap_body.cuh",
-                                   "misc_kernels.cu", "common.cuh", "kernels.cuh", "flowgen.h") + [os.path.join(EMUL, "simt.h")])
-    lib = ctypes.CDLL(so)
-    for name, (res, args) in L.SIGNATURES.items():
-        f = getattr(lib, name)
-        f.restype, f.argtypes = res, args
-    saved = L._lib
-    L._lib = lib
-    os.environ["FA_EXPERIMENTAL_KERNEL_MAP"] = "1"
-    try:
-        yield lib
-    finally:
-        L._lib = saved
-        os.environ.pop("FA_EXPERIMENTAL_KERNEL_MAP", None)
 
 
 def test_chunked_host_ingest_and_refold(engine_emul):
