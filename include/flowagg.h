@@ -131,6 +131,23 @@ typedef struct fa_additional_record {
     fa_additional_metrics additional;  /* 40 */
 } fa_additional_record;              /* 72 bytes */
 
+/* Compact packet event, 64 bytes: what flow_monitor knows about one packet before it touches the map
+ * (bpf/flows.c:176-245) minus the MAC addresses and TLS fields — id 40 + ts 8 + len 4 + flags 2 + dscp 1 + dir 1 +
+ * ifindex 4 + sampling 4.  fa_ingest_events folds each event exactly like the single-packet flow record
+ * new_flow = {start = end = ts, bytes = len, packets = 1, eth_protocol (0x0800 for ::ffff:a.b.c.d keys, else 0x86DD),
+ * flags, dscp, sampling, if_index_first_seen, direction_first_seen, MACs = 0, everything else 0} (flows.c:228-245).
+ * 2.25 x fewer bytes over PCIe than the 144-byte ring-buffer record. */
+typedef struct fa_packet_event {
+    fa_flow_id id;                   /*  0 */
+    uint64_t mono_ts;                /* 40 pkt.current_ts */
+    uint32_t len;                    /* 48 */
+    uint16_t flags;                  /* 52 collapsed TCP flags (bpf/utils.h:24-51) */
+    uint8_t  dscp;                   /* 54 */
+    uint8_t  direction;              /* 55 */
+    uint32_t if_index;               /* 56 */
+    uint32_t sampling;               /* 60 */
+} fa_packet_event;                   /* 64 bytes */
+
 /* ------------------------------------------------------------- error codes */
 
 #define FA_OK          0
@@ -223,6 +240,11 @@ void fa_destroy(fa_engine* e);
  * Stream order == array order.  *consumed (may be NULL) receives the number of
  * records folded; it is < n only when the call returns FA_FULL. */
 int fa_ingest(fa_engine* e, const void* flow_records, size_t n, size_t* consumed);
+
+/* Same fold for n 64-byte packet events (host or device pointer): each event is expanded on the device into the
+ * single-packet record described at fa_packet_event and goes through the same kernels.  A separate measurement row
+ * (64 algorithmic bytes per packet); the headline stays on 144-byte records. */
+int fa_ingest_events(fa_engine* e, const void* packet_events, size_t n, size_t* consumed);
 
 /* Fold n (flow_id + additional_metrics) samples: RTT keep-max, IPsec rules.
  * Replaces: bpf/rtt_tracker.h:12-22,73-91 + AccumulateAdditional

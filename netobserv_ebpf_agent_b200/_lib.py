@@ -62,6 +62,7 @@ SIGNATURES = {
     "fa_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "fa_destroy": (None, [C.c_void_p]),
     "fa_ingest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "fa_ingest_events": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_ingest_additional": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_ingest_dns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_evict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
@@ -113,7 +114,10 @@ def lib():
         raise FlowAggError(FA_E_NODEV, f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                         "(there is no CPU fallback)")
     L = C.CDLL(p)
+    alt = "FA_LIB_NAME" in os.environ  # an older build kept for a same-box A/B may lack the newest entry points
     for name, (res, args) in SIGNATURES.items():
+        if alt and not hasattr(L, name):
+            continue
         f = getattr(L, name)          # AttributeError if the .so does not export a declared symbol
         f.restype, f.argtypes = res, args
     _lib = L

@@ -27,28 +27,30 @@ constexpr int R_START = 40, R_END = 48, R_BYTES = 56, R_PACKETS = 64, R_ETH = 68
 // One slot = one 128-byte line (everything the per-record path touches) + one 32-byte cold line (observed interfaces,
 // all-zero for almost every flow and then never read or written).
 //
-// line (8 x 16-byte chunks):
-//   chunk 0,1  [  0.. 32) key[0..32)
+// line (8 x 16-byte chunks; four 32-byte sectors):
+//   chunk 0,1  [  0.. 32) key[0..32)                                                       == record chunks 0, 1
 //   chunk 2    [ 32.. 40) key[32..40) (byte 39 forced to 0)
 //              [ 40.. 48) tag u64: 0 = EMPTY, else (epoch << 24) | (tcp flags already OR-ed into hot.flags << 8) | bits
-//   chunk 3    [ 48.. 56) hot.bytes   (add)          } the accumulators: only ever touched by fire-and-forget
-//              [ 56.. 64) hot.nstart = 0 - start (max -> min over non-zero starts, 0 if none)   } reductions, all-zero
-//   chunk 4    [ 64.. 72) hot.end     (max)          } == identity.  They live in the SAME line as the key, so the
-//              [ 72.. 76) hot.packets (add, wraps mod 2^32 like the Go u32)   } line a probe has just pulled into L2 is
-//              [ 76.. 80) hot.flags   (or; low 16 bits)                        } the line the reductions land on
-//   chunk 5    [ 80.. 84) start mirror, low 32 bits   } m48 = (0 - start_at_insert) >> 16: an immutable lower bound of
-//              [ 84.. 86) eth_protocol                } hot.nstart, so records that cannot lower the start skip that RED
-//              [ 86.. 88) start mirror, high 16 bits  }
-//              [ 88.. 96) src_mac[6] dst_mac[0..2)                        == record bytes [72..80)
-//   chunk 6    [ 96..112) dst_mac[2..6) if_index lock sampling            == record bytes [80..96)   (record chunk 5)
-//   chunk 7    [112..116) direction errno dscp nb_observed_intf           == record bytes [96..100)
-//              [116..124) ssl_version tls_cipher_suite tls_key_share tls_types misc_flags   == record bytes [132..140)
-//              [124..128) 0
-// cold line (2 chunks): observed_direction[6] + observed_intf[6] == record bytes [100..132), padding zeroed.
-//   TAG_HAS_OBS says whether it is non-zero; a flow without it never touches its cold line.
+//   chunk 3    [ 48.. 52) start mirror, low 32 bits   } m48 = (0 - start_at_insert) >> 16: an immutable lower bound of
+//              [ 52.. 54) eth_protocol                } hot.nstart, so records that cannot lower the start skip that RED
+//              [ 54.. 56) start mirror, high 16 bits  }
+//              [ 56.. 64) src_mac[6] dst_mac[0..2)                                          == record chunk 4, words z, w
+//   chunk 4    [ 64.. 72) hot.bytes   (add)            } the accumulators = the line's third SECTOR: only ever touched
+//              [ 72.. 80) hot.nstart = 0 - start (max -> min over non-zero starts, 0 if none)   } by fire-and-forget
+//   chunk 5    [ 80.. 88) hot.end     (max)            } reductions, all-zero == identity.  They live in the line a
+//              [ 88.. 92) hot.packets (add, wraps mod 2^32 like the Go u32)   } probe has just pulled into L2; the probe
+//              [ 92.. 96) hot.flags   (or; low 16 bits)                        } itself reads the other three sectors
+//   chunk 6    [ 96..112) dst_mac[2..6) if_index lock sampling                              == record chunk 5
+//   chunk 7    [112..124) observed_intf[5] | ssl_version tls_cipher_suite | tls_key_share tls_types misc_flags
+//                                                                                           == record chunk 8, words x, y, z
+//              [124..128) direction errno dscp nb_observed_intf                             == record chunk 6, word x
+// cold line (2 chunks): record chunk 6 without its word x (observed_direction[6], observed_intf[0]; padding zeroed)
+//   and record chunk 7 (observed_intf[1..5)).  TAG_HAS_OBS says whether it is non-zero; a flow without it never
+//   touches its cold line.  Every chunk of the line and of the cold line is ONE record chunk under a mask (chunk 7
+//   borrows one word), so an 8-lane probe group compares with one shared-memory load per lane and no shuffling.
 constexpr int kIdentBytes = 128;
 constexpr int kColdBytes  = 32;
-constexpr int L_HOT = 48;                    // byte offset of the accumulators inside the line
+constexpr int L_HOT = 64;                    // byte offset of the accumulators inside the line
 
 constexpr uint64_t TAG_STATE_MASK = 0x3ull;
 constexpr uint64_t TAG_CLAIMED    = 0x1ull;
@@ -117,31 +119,24 @@ FA_HD uint4 rec_desc_mask(int c) {
         default: return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     }
 }
-// chunk_mask(j): which bits of LINE chunk j are identity (compared with / stored from the record's image).
-// j: 0,1 key | 2 key tail (+tag, excluded) | 3,4: the cold-line images (full) | 5 eth + macs (mirror excluded) | 6 | 7.
+// Lane j of an 8-lane probe group holds the image of record chunk rec_chunk_of_lane(j): for j = 0,1,2,3,6,7 it is
+// compared with / stored to line chunk j, for j = 4,5 to the two chunks of the cold line (line chunks 4, 5 are the
+// accumulators and have no image).  Lane 7 additionally takes word x of record chunk 6 as its word w.
+FA_HD int rec_chunk_of_lane(int j) {
+    switch (j) { case 3: return 4; case 4: return 6; case 5: return 7; case 6: return 5; case 7: return 8; default: return j; }
+}
+// chunk_mask(j): which bits of lane j's image are identity.
 FA_HD uint4 chunk_mask(int j) {
     switch (j) {
-        case 2:  return make_uint4(0xFFFFFFFFu, 0x00FFFFFFu, 0u, 0u);
-        case 5:  return make_uint4(0u, 0x0000FFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        case 7:  return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+        case 2:  return make_uint4(0xFFFFFFFFu, 0x00FFFFFFu, 0u, 0u);                // key tail; tag excluded
+        case 3:  return make_uint4(0u, 0x0000FFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);        // eth + macs; mirror excluded
+        case 4:  return make_uint4(0u, 0xFFFFFFFFu, 0x0000FFFFu, 0xFFFFFFFFu);        // cold 0: record chunk 6 minus word x, padding
         default: return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     }
 }
-// The 16 bytes of a record (R = its 9 chunks) that lane j of an 8-lane probe group holds: for j = 0,1,2,5,6,7 what line
-// chunk j is compared with, for j = 3,4 the two chunks of the cold line (the accumulators have no image).
-FA_HD uint4 rec_image(const uint4* R, int j) {
-    switch (j) {
-        case 0: case 1: case 2: return R[j];
-        case 3: { const uint4 a = R[6], b = R[7]; return make_uint4(a.y, a.z & 0x0000FFFFu, a.w, b.x); }
-        case 4: { const uint4 a = R[7], b = R[8]; return make_uint4(a.y, a.z, a.w, b.x); }
-        case 5: return R[4];
-        case 6: return R[5];
-        default: { const uint4 a = R[6], b = R[8]; return make_uint4(a.x, b.y, b.z, 0u); }
-    }
-}
-FA_HD uint32_t rec_cold_nz(uint4 r6, uint4 r7, uint4 r8) {
-    return r6.y | (r6.z & 0x0000FFFFu) | r6.w | r7.x | r7.y | r7.z | r7.w | r8.x;
-}
+// image of lane 7 (and of the thread-per-record compares): record chunk 8's x, y, z and record chunk 6's x
+FA_HD uint4 rec_image7(uint4 r6, uint4 r8) { return make_uint4(r8.x, r8.y, r8.z, r6.x); }
+FA_HD uint32_t rec_cold_nz(uint4 r6, uint4 r7) { return r6.y | (r6.z & 0x0000FFFFu) | r6.w | r7.x | r7.y | r7.z | r7.w; }
 
 FA_HD uint4 and4(uint4 a, uint4 m) { return make_uint4(a.x & m.x, a.y & m.y, a.z & m.z, a.w & m.w); }
 FA_HD bool  eq4_masked(uint4 a, uint4 b, uint4 m) {

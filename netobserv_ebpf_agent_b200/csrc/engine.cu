@@ -127,6 +127,8 @@ struct fa_engine {
     uint32_t* d_cut_set = nullptr; uint32_t cut_set_slots = 0;
     uint32_t* d_cut_bitmap = nullptr; uint32_t* d_cut_out = nullptr; uint32_t* h_cut_out = nullptr;
 
+    uint8_t* d_events = nullptr;              // fa_ingest_events: raw 64-byte events of one chunk
+    uint8_t* d_expanded = nullptr;            // ... and their 144-byte expansion (events handed in as device memory)
     uint8_t* d_evict = nullptr; uint64_t evict_cap = 0;
     uint8_t* d_evict_dns = nullptr; uint8_t* d_evict_add = nullptr; uint8_t* d_evict_present = nullptr;
     uint32_t* d_slot_of_out = nullptr; uint64_t feat_evict_cap = 0;
@@ -561,7 +563,7 @@ void fa_destroy(fa_engine* e) {
     }
     cudaFree(e->d_scratch); cudaFree(e->d_spill_idx); cudaFree(e->d_cut_set); cudaFree(e->d_cut_bitmap); cudaFree(e->d_cut_out);
     if (e->h_cut_out) cudaFreeHost(e->h_cut_out);
-    cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts);
+    cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts); cudaFree(e->d_events); cudaFree(e->d_expanded);
     cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out); cudaFree(e->d_slot_of);
     cudaFree(e->sk.cms); cudaFree(e->sk.hll);
     cudaFree(e->km_met); cudaFree(e->km_slot_of); cudaFree(e->km_bset); cudaFree(e->km_blist); cudaFree(e->km_spill);
@@ -589,6 +591,53 @@ int fa_ingest(fa_engine* e, const void* recs, size_t n, size_t* consumed) {
         if (k == PTR_PAGEABLE && !e->h_stage[i]) CU(cudaHostAlloc(&e->h_stage[i], e->max_batch * fa::kRecBytes, cudaHostAllocDefault));
     }
     return ingest_host(e, static_cast<const uint8_t*>(recs), n, consumed, k == PTR_PINNED);
+}
+
+int fa_ingest_events(fa_engine* e, const void* events, size_t n, size_t* consumed) {
+    if (consumed) *consumed = 0;
+    if (!e) return fail(FA_E_INVAL, "fa_ingest_events: null engine");
+    if (n == 0) return FA_OK;
+    if (!events) return fail(FA_E_INVAL, "fa_ingest_events: null events");
+    static_assert(sizeof(fa_packet_event) == 64, "fa_packet_event ABI");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    const PtrKind k = classify(events);
+    if (k == PTR_DEVICE && (reinterpret_cast<uintptr_t>(events) & 15)) return fail(FA_E_INVAL, "fa_ingest_events: device events must be 16-byte aligned");
+    if (!e->d_expanded) CU(cudaMalloc(&e->d_expanded, e->max_batch * fa::kRecBytes));
+    if (k != PTR_DEVICE && !e->d_events) CU(cudaMalloc(&e->d_events, e->max_batch * 64));
+    size_t done = 0;
+    int rc = FA_OK;
+    while (done < n) {
+        uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
+        if (e->cfg.mode == FA_MODE_ACCOUNTER && !(e->cfg.flags & FA_F_NO_FULL_CUT)) {     // see ingest_host: stage by the room left
+            retire_completed(e);
+            const uint64_t used = e->live_known + e->unsynced_records;
+            const uint64_t room = e->cfg.max_entries > used ? e->cfg.max_entries - used : 0;
+            if (room < c) c = (uint32_t)std::min<uint64_t>(c, std::max<uint64_t>(4096, 4 * room));
+        }
+        const uint8_t* src = static_cast<const uint8_t*>(events) + done * 64;
+        const uint8_t* d_ev = src;
+        // the previous chunk's kernels read d_expanded / d_events: everything here is ordered on the engine's stream
+        if (k != PTR_DEVICE) {
+            CU(cudaMemcpyAsync(e->d_events, src, (size_t)c * 64, cudaMemcpyHostToDevice, e->stream));
+            e->st.h2d_bytes += (size_t)c * 64;
+            d_ev = e->d_events;
+        }
+        e->st.kernel_launches += fa::launch_expand_events(reinterpret_cast<const uint4*>(d_ev), c, reinterpret_cast<uint4*>(e->d_expanded), e->stream);
+        CU(cudaGetLastError());
+        uint32_t off = 0;
+        while (off < c) {                                   // a chunk may be folded in several windows ("full" cuts)
+            uint32_t took = 0;
+            rc = ingest_chunk(e, e->d_expanded + (size_t)off * fa::kRecBytes, c - off, &took);
+            off += took;
+            if (rc != FA_OK) break;
+        }
+        done += off;
+        if (rc != FA_OK) break;
+    }
+    if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->stream));   // the caller's buffer must not be referenced after return
+    if (consumed) *consumed = done;
+    return rc;
 }
 
 static int ingest_feature(fa_engine* e, int kind, const void* recs, size_t n, const char* who) {

@@ -38,7 +38,7 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
             while (rest) {
                 const int b = __ffs(rest) - 1; rest &= rest - 1;
                 const uint64_t slot = wi * 32 + b;
-                const uint4 h0 = ld_cg_u4(&t.ident[slot * 8 + 3]), h1 = ld_cg_u4(&t.ident[slot * 8 + 4]);
+                const uint4 h0 = ld_cg_u4(&t.ident[slot * 8 + 4]), h1 = ld_cg_u4(&t.ident[slot * 8 + 5]);
                 if ((h0.x | h0.y | h0.z | h0.w | h1.x | h1.y | h1.z | h1.w) != 0u) myact |= 1u << b;
             }
             mybits = myact;
@@ -77,15 +77,13 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
                 if (live) line = ld_cg_u4(&t.ident[slot * 8 + j]);
                 const int g8 = g * 8;
                 const bool has_obs = (__shfl_sync(0xFFFFFFFFu, line.z, g8 + 2) & (uint32_t)TAG_HAS_OBS) != 0u;
-                // lanes 5 and 7 fetch the two cold chunks (observed interfaces) of the few flows that have them
-                if (live && has_obs && (j == 5 || j == 7)) cold = ld_cg_u4(&t.cold[slot * 2 + (j == 5 ? 0 : 1)]);
-                // line chunk 3 = (bytes, nstart), chunk 4 = (end, packets, flags), chunk 5 = (mirror | eth, macs), chunk 7 = (dir.., ssl.., tls..)
-                const uint32_t ns_lo = __shfl_sync(0xFFFFFFFFu, line.z, g8 + 3), ns_hi = __shfl_sync(0xFFFFFFFFu, line.w, g8 + 3);
-                const uint32_t e_lo = __shfl_sync(0xFFFFFFFFu, line.x, g8 + 4), e_hi = __shfl_sync(0xFFFFFFFFu, line.y, g8 + 4);
-                const uint32_t l5y = __shfl_sync(0xFFFFFFFFu, line.y, g8 + 5), l5z = __shfl_sync(0xFFFFFFFFu, line.z, g8 + 5),
-                               l5w = __shfl_sync(0xFFFFFFFFu, line.w, g8 + 5);
-                const uint32_t l7x = __shfl_sync(0xFFFFFFFFu, line.x, g8 + 7);
-                const uint32_t c0w = __shfl_sync(0xFFFFFFFFu, cold.w, g8 + 5);
+                // lanes 6 and 7 fetch the two cold chunks (observed interfaces) of the few flows that have them
+                if (live && has_obs && j >= 6) cold = ld_cg_u4(&t.cold[slot * 2 + (j - 6)]);
+                // line chunk 3 = (mirror | eth, macs), 4 = (bytes, nstart), 5 = (end, packets, flags), 7 = (obs_intf[5], ssl.., tls.., dir..)
+                const uint32_t ns_lo = __shfl_sync(0xFFFFFFFFu, line.z, g8 + 4), ns_hi = __shfl_sync(0xFFFFFFFFu, line.w, g8 + 4);
+                const uint32_t b_lo = __shfl_sync(0xFFFFFFFFu, line.x, g8 + 4), b_hi = __shfl_sync(0xFFFFFFFFu, line.y, g8 + 4);
+                const uint32_t pk = __shfl_sync(0xFFFFFFFFu, line.z, g8 + 5), fl = __shfl_sync(0xFFFFFFFFu, line.w, g8 + 5);
+                const uint32_t l7w = __shfl_sync(0xFFFFFFFFu, line.w, g8 + 7);
                 if (live && idx < cap) {
                     uint4* O = out + idx * kRecChunks;
                     const uint64_t start = 0ull - u64_of(ns_lo, ns_hi);       // nstart = -start; 0 stays 0
@@ -94,23 +92,22 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
                     } else if (j == 2) {
                         O[2] = make_uint4(line.x, line.y & 0x00FFFFFFu, (uint32_t)start, (uint32_t)(start >> 32));
                     } else if (j == 3) {
-                        O[3] = make_uint4(e_lo, e_hi, line.x, line.y);          // end, bytes
-                    } else if (j == 4) {
-                        O[4] = make_uint4(line.z, (l5y & 0xFFFFu) | (line.w << 16), l5z, l5w);   // packets, eth | flags, macs
+                        O[4] = make_uint4(pk, (line.y & 0xFFFFu) | (fl << 16), line.z, line.w);   // packets, eth | flags, macs
                     } else if (j == 5) {
-                        O[6] = make_uint4(l7x, cold.x, cold.y, cold.z);         // dir errno dscp nb_obs | observed_direction | observed_intf[0]
+                        O[3] = make_uint4(line.x, line.y, b_lo, b_hi);          // end, bytes
                     } else if (j == 6) {
                         O[5] = line;                                            // dst_mac[2..6) if_index lock sampling
-                    } else {
-                        O[7] = make_uint4(c0w, cold.x, cold.y, cold.z);         // observed_intf[1..5)
-                        O[8] = make_uint4(cold.w, line.y, line.z, 0u);          // observed_intf[5] | ssl, cipher | key share, types, misc
+                        O[6] = make_uint4(l7w, cold.y, cold.z, cold.w);         // dir errno dscp nb_obs | observed_direction | observed_intf[0]
+                    } else if (j == 7) {
+                        O[7] = cold;                                            // observed_intf[1..5)
+                        O[8] = make_uint4(line.x, line.y, line.z, 0u);          // observed_intf[5] | ssl, cipher | key share, types, misc
                     }
                     if (slot_of_out && j == 0) slot_of_out[idx] = (uint32_t)slot;   // for the feature pass
                 }
                 // delete: tag -> EMPTY, accumulators -> identity, cold line -> zero  (drain: the accumulators only)
                 if (!kDrain && live && j == 2) *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(&t.ident[slot * 8 + 2]) + 8) = make_uint2(0u, 0u);
-                if (live && (j == 3 || j == 4)) t.ident[slot * 8 + j] = make_uint4(0, 0, 0, 0);
-                if (!kDrain && live && has_obs && (j == 5 || j == 7)) t.cold[slot * 2 + (j == 5 ? 0 : 1)] = make_uint4(0, 0, 0, 0);
+                if (live && (j == 4 || j == 5)) t.ident[slot * 8 + j] = make_uint4(0, 0, 0, 0);
+                if (!kDrain && live && has_obs && j >= 6) t.cold[slot * 2 + (j - 6)] = make_uint4(0, 0, 0, 0);
             }
         }
     }

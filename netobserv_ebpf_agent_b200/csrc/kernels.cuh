@@ -84,6 +84,9 @@ int launch_pb_sizes(const PbInputs& in, uint32_t n, const PbParams& P, uint32_t*
 int launch_pb_write(const PbInputs& in, uint32_t n, const PbParams& P, const unsigned long long* offsets, const uint32_t* sizes,
                     uint8_t* out, uint8_t* keys_out, cudaStream_t st);
 
+// 64-byte packet events -> single-packet 144-byte records (misc_kernels.cu)
+int launch_expand_events(const uint4* events, uint32_t n, uint4* recs_out, cudaStream_t st);
+
 // generator
 struct GenDeviceParams;
 int launch_generate(const GenDeviceParams& g, uint64_t first_index, uint32_t n, uint4* dst, cudaStream_t st);

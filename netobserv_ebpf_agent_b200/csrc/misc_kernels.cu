@@ -22,6 +22,37 @@ int launch_generate(const GenDeviceParams& g, uint64_t first_index, uint32_t n, 
 }
 #endif  // FA_HOST_EMUL
 
+// ------------------------------------------------------------------ packet events -> records
+// One 64-byte fa_packet_event (4 chunks) becomes the 144-byte record new_flow of bpf/flows.c:228-245 (9 chunks).
+// 4 lanes load an event coalesced; every lane of the warp then writes 16-byte chunks of the 8 records of its warp
+// round, so loads and stores are both full 128-bit, contiguous per record.
+__global__ void expand_events_kernel(const uint4* __restrict__ ev, uint32_t n, uint4* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4* E = ev + (size_t)i * 4;
+        const uint4 e0 = ld_stream_u4(E), e1 = ld_stream_u4(E + 1), e2 = ld_stream_u4(E + 2), e3 = ld_stream_u4(E + 3);
+        // e2 = key[32..40) | ts ; e3 = len | flags, dscp, dir | if_index | sampling
+        const bool v4 = e0.x == 0u && e0.y == 0u && e0.z == 0xFFFF0000u;       // ::ffff:a.b.c.d
+        const uint32_t eth = v4 ? 0x0800u : 0x86DDu;
+        const uint32_t flags = e3.y & 0xFFFFu, dscp = (e3.y >> 16) & 0xFFu, dir = e3.y >> 24;
+        uint4* O = out + (size_t)i * kRecChunks;
+        O[0] = e0; O[1] = e1;
+        O[2] = make_uint4(e2.x, e2.y & 0x00FFFFFFu, e2.z, e2.w);               // key tail | start = ts
+        O[3] = make_uint4(e2.z, e2.w, e3.x, 0u);                               // end = ts | bytes = len
+        O[4] = make_uint4(1u, eth | (flags << 16), 0u, 0u);                    // packets = 1 | eth, flags | MACs = 0
+        O[5] = make_uint4(0u, e3.z, 0u, e3.w);                                 // dst_mac tail | if_index | lock | sampling
+        O[6] = make_uint4(dir | (dscp << 16), 0u, 0u, 0u);                     // direction, errno, dscp, nb_observed_intf | ...
+        O[7] = make_uint4(0u, 0u, 0u, 0u);
+        O[8] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+#ifndef FA_HOST_EMUL
+int launch_expand_events(const uint4* events, uint32_t n, uint4* recs_out, cudaStream_t st) {
+    if (!n) return 0;
+    expand_events_kernel<<<(n + 255) / 256, 256, 0, st>>>(events, n, recs_out);
+    return 1;
+}
+#endif  // FA_HOST_EMUL
+
 // ------------------------------------------------------------------ "full" cut pre-pass
 // Reference pkg/flow/account.go:85-94: the first record whose key is new while the cache
 // already holds max_entries flows evicts everything.  Run only when a batch could overflow.

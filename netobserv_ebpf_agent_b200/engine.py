@@ -52,6 +52,16 @@ class FlowAggEngine:
         rc = check(lib().fa_ingest(self._h, _ptr(recs), n, C.byref(consumed)))
         return rc, consumed.value
 
+    def ingest_events(self, events, n=None):
+        """Fold 64-byte packet events (fa_packet_event; numpy / torch / raw address with n). Returns (status, consumed)."""
+        if n is None:
+            nb = _nbytes(events)
+            assert nb % 64 == 0
+            n = nb // 64
+        consumed = C.c_size_t(0)
+        rc = check(lib().fa_ingest_events(self._h, _ptr(events), n, C.byref(consumed)))
+        return rc, consumed.value
+
     def ingest_all(self, recs, on_full):
         """Accounter loop: fold everything, calling on_full(evicted_records) at each "full" cut
         (reference pkg/flow/account.go:85-94)."""

@@ -109,6 +109,21 @@ void oracle_accumulate_additional(oracle_content* p, const uint8_t* o) {
     merge_additional_block(p, o);
 }
 
+/* pkt_drop_metrics: start@0 end@8 bytes u16@16 packets u16@18 latest_drop_cause u32@20 latest_flags u16@24
+ * eth_protocol u16@26 latest_state u8@28 (bpf/types.h:142-151) */
+enum { P_START = 0, P_END = 8, P_BYTES = 16, P_PACKETS = 18, P_CAUSE = 20, P_FLAGS = 24, P_ETH = 26, P_STATE = 28 };
+static uint16_t add_u16_sat(uint16_t a, uint16_t b) { uint16_t x = (uint16_t)(a + b); return x < a ? 0xFFFF : x; }   /* flow_content.go:209-215 */
+void oracle_accumulate_drops(uint8_t* p_metrics104, uint8_t* p_drops32, uint8_t* has_drops, const uint8_t* o) {
+    /* pkg/model/flow_content.go:98-117 */
+    build_base_from_additional(p_metrics104, ld64(o + P_START), ld64(o + P_END), ld16(o + P_ETH));        /* :102 */
+    if (!*has_drops) { memcpy(p_drops32, o, OR_DROP_SIZE); memset(p_drops32 + 29, 0, 3); *has_drops = 1; return; }   /* :103-106 */
+    st16(p_drops32 + P_BYTES, add_u16_sat(ld16(p_drops32 + P_BYTES), ld16(o + P_BYTES)));                 /* :108 */
+    st16(p_drops32 + P_PACKETS, add_u16_sat(ld16(p_drops32 + P_PACKETS), ld16(o + P_PACKETS)));           /* :109 */
+    st16(p_drops32 + P_FLAGS, (uint16_t)(ld16(p_drops32 + P_FLAGS) | ld16(o + P_FLAGS)));                 /* :110 */
+    if (ld32(o + P_CAUSE) != 0) st32(p_drops32 + P_CAUSE, ld32(o + P_CAUSE));                             /* :111-113 */
+    if (o[P_STATE] != 0) p_drops32[P_STATE] = o[P_STATE];                                                 /* :114-116 */
+}
+
 void oracle_new_record_times(uint64_t now_unix_ns, uint64_t mono_now_ns, uint64_t start_mono,
                              uint64_t end_mono, uint64_t* tfs, uint64_t* tfe) {
     /* pkg/model/record.go:90-97: time.Duration(monoNow - start) then now.Add(-delta) */
@@ -147,8 +162,10 @@ typedef struct {
      * evict in LookupAndDeleteMap's order: base, then DNS, then additional
      * (pkg/tracer/tracer.go:1094-1151). */
     uint8_t  has_base;
-    uint64_t fs[2], fe[2];     /* [0]=dns [1]=additional: min non-zero start / max end */
-    uint16_t feth[2];          /* first non-zero eth_protocol in sample order */
+    uint64_t fs[3], fe[3];     /* [0]=dns [1]=additional [2]=packet drops: min non-zero start / max end */
+    uint16_t feth[3];          /* first non-zero eth_protocol in sample order */
+    uint8_t  drops[OR_DROP_SIZE]; uint8_t has_drops;     /* pkt_drop_metrics block (bpf/types.h:142-151) */
+    uint64_t rtt_min;          /* extension (no reference analogue): smallest non-zero flow_rtt, 0 = none */
 } entry_t;
 
 typedef struct {
@@ -464,25 +481,46 @@ void oracle_flowmap_fold_additional(oracle_flowmap* m, const uint8_t* recs, size
         add[31] = 0;
         feature_base_effect(e, 1, ld64(add + A_START), ld64(add + A_END), ld16(add + A_ETH));
         merge_additional_block(&e->c, add);
+        const uint64_t rtt = ld64(add + A_RTT);
+        if (rtt != 0 && (e->rtt_min == 0 || rtt < e->rtt_min)) e->rtt_min = rtt;
     }
 }
-size_t oracle_flowmap_evict(oracle_flowmap* m, uint8_t* out, uint8_t* out_dns, uint8_t* out_add,
-                            uint8_t* out_present, size_t cap) {
+void oracle_flowmap_fold_drops(oracle_flowmap* m, const uint8_t* recs, size_t n) {
+    uint8_t key[OR_ID_SIZE];
+    for (size_t i = 0; i < n; i++) {
+        memcpy(key, recs + i * OR_DROPREC_SIZE, OR_ID_SIZE); key[39] = 0;
+        int found; entry_t* e = fmap_get(&m->m, key, 1, &found);
+        const uint8_t* o = recs + i * OR_DROPREC_SIZE + OR_ID_SIZE;
+        feature_base_effect(e, 2, ld64(o + P_START), ld64(o + P_END), ld16(o + P_ETH));
+        uint8_t scratch_base[OR_MET_SIZE]; memset(scratch_base, 0, sizeof scratch_base);   /* base effect is kept apart (see entry_t) */
+        oracle_accumulate_drops(scratch_base, e->drops, &e->has_drops, o);
+    }
+}
+size_t oracle_flowmap_evict_ex(oracle_flowmap* m, uint8_t* out, uint8_t* out_dns, uint8_t* out_add, uint8_t* out_drops,
+                               uint64_t* out_rtt_min, uint8_t* out_present, size_t cap) {
     size_t k = m->m.n < cap ? m->m.n : cap;
     for (size_t i = 0; i < k; i++) {
         const entry_t* e = &m->m.ents[i];
         uint8_t met[OR_MET_SIZE];
         if (e->has_base) memcpy(met, e->c.metrics, OR_MET_SIZE); else memset(met, 0, OR_MET_SIZE);
+        /* LookupAndDeleteMap's order: DNS, packet drops, additional (pkg/tracer/tracer.go:1098-1151) */
         if (e->c.has_dns) build_base_from_additional(met, e->fs[0], e->fe[0], e->feth[0]);
+        if (e->has_drops) build_base_from_additional(met, e->fs[2], e->fe[2], e->feth[2]);
         if (e->c.has_additional) build_base_from_additional(met, e->fs[1], e->fe[1], e->feth[1]);
         memcpy(out + i * OR_REC_SIZE, e->key, OR_ID_SIZE);
         memcpy(out + i * OR_REC_SIZE + OR_ID_SIZE, met, OR_MET_SIZE);
         if (out_dns) { if (e->c.has_dns) memcpy(out_dns + i * OR_DNS_SIZE, e->c.dns, OR_DNS_SIZE); else memset(out_dns + i * OR_DNS_SIZE, 0, OR_DNS_SIZE); }
         if (out_add) { if (e->c.has_additional) memcpy(out_add + i * OR_ADD_SIZE, e->c.additional, OR_ADD_SIZE); else memset(out_add + i * OR_ADD_SIZE, 0, OR_ADD_SIZE); }
-        if (out_present) out_present[i] = (uint8_t)((e->c.has_dns ? 1 : 0) | (e->c.has_additional ? 2 : 0));
+        if (out_drops) { if (e->has_drops) memcpy(out_drops + i * OR_DROP_SIZE, e->drops, OR_DROP_SIZE); else memset(out_drops + i * OR_DROP_SIZE, 0, OR_DROP_SIZE); }
+        if (out_rtt_min) out_rtt_min[i] = e->rtt_min;
+        if (out_present) out_present[i] = (uint8_t)((e->c.has_dns ? 1 : 0) | (e->c.has_additional ? 2 : 0) | (e->has_drops ? 4 : 0));
     }
     size_t n = m->m.n; fmap_clear(&m->m);
     return n;
+}
+size_t oracle_flowmap_evict(oracle_flowmap* m, uint8_t* out, uint8_t* out_dns, uint8_t* out_add,
+                            uint8_t* out_present, size_t cap) {
+    return oracle_flowmap_evict_ex(m, out, out_dns, out_add, NULL, NULL, out_present, cap);
 }
 
 /* ----------------------------------------------------------- KERNEL_MAP */

@@ -38,7 +38,8 @@ extern "C" {
 enum {
     OR_ID_SIZE = 40, OR_MET_SIZE = 104, OR_REC_SIZE = 144,
     OR_DNS_SIZE = 64, OR_ADD_SIZE = 32,
-    OR_DNSREC_SIZE = 104, OR_ADDREC_SIZE = 72
+    OR_DNSREC_SIZE = 104, OR_ADDREC_SIZE = 72,
+    OR_DROP_SIZE = 32, OR_DROPREC_SIZE = 72
 };
 
 /* --- pkg/model/record.go:227-231 ReadFrom: binary.Read of 144 bytes; blank (padding)
@@ -61,6 +62,10 @@ typedef struct oracle_content {
 void oracle_accumulate_dns(oracle_content* p, const uint8_t* dns64);
 /* --- pkg/model/flow_content.go:154-177 */
 void oracle_accumulate_additional(oracle_content* p, const uint8_t* add32);
+
+/* --- pkg/model/flow_content.go:98-117 AccumulateDrops on (base metrics, pkt_drop_metrics block, presence flag);
+ * pinned by flow_content_test.go:55-104. */
+void oracle_accumulate_drops(uint8_t* p_metrics104, uint8_t* p_drops32, uint8_t* has_drops, const uint8_t* o_drops32);
 
 /* --- pkg/model/record.go:90-97: wall = now - (monoNow - mono), u64 arithmetic. */
 void oracle_new_record_times(uint64_t now_unix_ns, uint64_t mono_now_ns,
@@ -115,7 +120,12 @@ void   oracle_flowmap_free(oracle_flowmap* m);
 void   oracle_flowmap_account(oracle_flowmap* m, const uint8_t* wire, size_t n);          /* ACCOUNTER fold */
 void   oracle_flowmap_fold_dns(oracle_flowmap* m, const uint8_t* dnsrecs, size_t n);       /* n x 104 B */
 void   oracle_flowmap_fold_additional(oracle_flowmap* m, const uint8_t* addrecs, size_t n);/* n x 72 B */
+void   oracle_flowmap_fold_drops(oracle_flowmap* m, const uint8_t* droprecs, size_t n);      /* n x 72 B */
 size_t oracle_flowmap_len(const oracle_flowmap* m);
+/* like oracle_flowmap_evict, plus the packet-drop blocks (32 B, present bit 2) and the RTT minimum (extension:
+ * smallest non-zero flow_rtt of the flow's samples; PARITY UNPINNED — the reference keeps only the maximum) */
+size_t oracle_flowmap_evict_ex(oracle_flowmap* m, uint8_t* out_recs, uint8_t* out_dns, uint8_t* out_add, uint8_t* out_drops,
+                               uint64_t* out_rtt_min, uint8_t* out_present, size_t cap);
 size_t oracle_flowmap_evict(oracle_flowmap* m, uint8_t* out_recs, uint8_t* out_dns,
                             uint8_t* out_add, uint8_t* out_present, size_t cap);
 

@@ -190,6 +190,11 @@ int launch_evict_features(const Table& table, const uint32_t* slot_of_out, unsig
     return 1;
 }
 
+int launch_expand_events(const uint4* events, uint32_t n, uint4* recs_out, cudaStream_t) {
+    if (!n) return 0;
+    simt::launch(2, 256, 0, [=] { expand_events_kernel(events, n, recs_out); });
+    return 1;
+}
 int launch_pb_sizes(const PbInputs& in_, uint32_t n, const PbParams& P_, uint32_t* sizes, unsigned long long* offsets,
                     unsigned long long* block_sums, int, cudaStream_t) {
     if (!n) return 0;

@@ -68,6 +68,9 @@ def lib():
         "oracle_flowmap_fold_dns": (None, [vp, _u8p, sz]),
         "oracle_flowmap_fold_additional": (None, [vp, _u8p, sz]),
         "oracle_flowmap_len": (sz, [vp]),
+        "oracle_flowmap_fold_drops": (None, [vp, _u8p, sz]),
+        "oracle_flowmap_evict_ex": (sz, [vp, _u8p, _u8p, _u8p, _u8p, C.POINTER(u64), _u8p, sz]),
+        "oracle_accumulate_drops": (None, [_u8p, _u8p, _u8p, _u8p]),
         "oracle_flowmap_evict": (sz, [vp, _u8p, _u8p, _u8p, _u8p, sz]),
         "oracle_kmap_new": (vp, [sz, C.c_int]),
         "oracle_kmap_free": (None, [vp]),
@@ -122,6 +125,10 @@ assert DNS_DTYPE.itemsize == DNS
 ADD_DTYPE = np.dtype([("start", "<u8"), ("end", "<u8"), ("rtt", "<u8"), ("ipsec_ret", "<i4"),
                       ("eth", "<u2"), ("ipsec_enc", "u1"), ("pad", "u1")])
 assert ADD_DTYPE.itemsize == ADD
+DROP_DTYPE = np.dtype([("start", "<u8"), ("end", "<u8"), ("bytes", "<u2"), ("packets", "<u2"), ("cause", "<u4"), ("flags", "<u2"),
+                       ("eth", "<u2"), ("state", "u1"), ("pad", "u1", 3)])
+assert DROP_DTYPE.itemsize == 32
+DROPREC_DTYPE = np.dtype([("id", "u1", 40), ("drop", DROP_DTYPE)])
 DNSREC_DTYPE = np.dtype([("id", "u1", 40), ("dns", DNS_DTYPE)])
 ADDREC_DTYPE = np.dtype([("id", "u1", 40), ("add", ADD_DTYPE)])
 assert DNSREC_DTYPE.itemsize == DNSREC and ADDREC_DTYPE.itemsize == ADDREC
@@ -260,6 +267,20 @@ class FlowMap:
     def fold_additional(self, recs):
         b = as_bytes(recs)
         lib().oracle_flowmap_fold_additional(self.h, _p(b), b.size // ADDREC)
+
+    def fold_drops(self, recs):
+        b = as_bytes(recs)
+        lib().oracle_flowmap_fold_drops(self.h, _p(b), b.size // 72)
+
+    def evict_ex(self):
+        """-> records, dns, additional, packet drops (n,32), rtt_min (n,), present."""
+        n = len(self)
+        m = max(n, 1)
+        out, dns, add = np.zeros(m * REC, dtype=np.uint8), np.zeros(m * DNS, dtype=np.uint8), np.zeros(m * ADD, dtype=np.uint8)
+        drops, rmin, pres = np.zeros(m * 32, dtype=np.uint8), np.zeros(m, dtype=np.uint64), np.zeros(m, dtype=np.uint8)
+        got = lib().oracle_flowmap_evict_ex(self.h, _p(out), _p(dns), _p(add), _p(drops), rmin.ctypes.data_as(C.POINTER(C.c_uint64)), _p(pres), n)
+        return (out[: got * REC].reshape(-1, REC), dns[: got * DNS].reshape(-1, DNS), add[: got * ADD].reshape(-1, ADD),
+                drops[: got * 32].reshape(-1, 32), rmin[:got], pres[:got])
 
     def __len__(self):
         return lib().oracle_flowmap_len(self.h)

@@ -30,6 +30,7 @@ class FakeTensor:
         self.a = arr
         self.device = types.SimpleNamespace(index=0)
     def pin_memory(self): return self
+    def reshape(self, *a): return FakeTensor(self.a.reshape(*a))
     def data_ptr(self): return self.a.ctypes.data
     def numel(self): return self.a.size
     def element_size(self): return self.a.itemsize
@@ -105,6 +106,14 @@ class FakeEngine:
         self.launches += 3
         self.acc.account(mem(ptr if isinstance(ptr, int) else ptr.data_ptr(), n * REC))
         return 0, n
+    def ingest_events(self, ptr, n):
+        ev = mem(ptr, n * 64).reshape(-1, 64)
+        r = np.zeros((n, REC), dtype=np.uint8)
+        r[:, 0:40], r[:, 40:48], r[:, 48:56], r[:, 56:60] = ev[:, 0:40], ev[:, 40:48], ev[:, 40:48], ev[:, 48:52]
+        r[:, 64] = 1
+        self.acc.account(r)
+        self.launches += 4
+        return 0, n
     def live_flows(self): return len(self.acc)
     def evict_into(self, out, cap):
         r = self.acc.evict()
@@ -167,6 +176,7 @@ def test_single_gpu_line_has_every_contract_key_and_the_parity_check_runs(monkey
     assert line["n_gpus"] == 1 and "1M Zipf" in line["config"]["workload"]
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
     assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["e2e"]["events_row"]["value"] > 0 and line["e2e"]["events_row"]["h2d_bytes_per_step"] * 9 == line["e2e"]["h2d_bytes_per_step"] * 4
     assert line["gpu_launches"] > 0
     assert line["parity_ok"] and line["parity_checked"] == line["flows_oracle"] > 1000
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
