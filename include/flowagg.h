@@ -118,6 +118,19 @@ typedef struct fa_additional_metrics {
     uint8_t  pad_;                   /* 31 */
 } fa_additional_metrics;
 
+/* Packet-drop feature metrics, 32 bytes (reference bpf/types.h:142-151). */
+typedef struct fa_pkt_drop_metrics {
+    uint64_t start_mono_time_ts;     /*  0 */
+    uint64_t end_mono_time_ts;       /*  8 */
+    uint16_t bytes;                  /* 16 saturating */
+    uint16_t packets;                /* 18 saturating */
+    uint32_t latest_drop_cause;      /* 20 */
+    uint16_t latest_flags;           /* 24 */
+    uint16_t eth_protocol;           /* 26 */
+    uint8_t  latest_state;           /* 28 */
+    uint8_t  pad_[3];
+} fa_pkt_drop_metrics;
+
 /* Feature-stream input records: the key plus one feature sample — what the
  * reference keeps per CPU slot in aggregated_flows_dns / additional_flow_metrics
  * (bpf/maps_definition.h:24-31,64-71). */
@@ -130,6 +143,11 @@ typedef struct fa_additional_record {
     fa_flow_id            id;          /*  0 */
     fa_additional_metrics additional;  /* 40 */
 } fa_additional_record;              /* 72 bytes */
+
+typedef struct fa_pkt_drop_record {
+    fa_flow_id          id;            /*  0 */
+    fa_pkt_drop_metrics drops;         /* 40 */
+} fa_pkt_drop_record;                /* 72 bytes */
 
 /* Compact packet event, 64 bytes: what flow_monitor knows about one packet before it touches the map
  * (bpf/flows.c:176-245) minus the MAC addresses and TLS fields — id 40 + ts 8 + len 4 + flags 2 + dscp 1 + dir 1 +
@@ -196,6 +214,7 @@ typedef struct fa_config {
 #define FA_F_ENABLE_SKETCH  0x4u  /* fused count-min + HyperLogLog update in fa_ingest */
 #define FA_F_NO_FULL_CUT    0x8u  /* never return FA_FULL: max_entries only sizes the table (KERNEL_MAP-style caches,
                                      multi-GPU scratch / owner tables); a physically full table spills (fa_stats.spills) */
+#define FA_F_ENABLE_PKT_DROP 0x20u /* ENABLE_PKT_DROPS     (config.go) : fa_ingest_pkt_drops + the drop blocks at eviction */
 #define FA_F_RINGBUF_FALLBACK 0x10u /* KERNEL_MAP mode: ENABLE_FLOWS_RINGBUF_FALLBACK (config.go:286-288): packets whose flow
                                      cannot be created because the map is full are kept as single-packet records
                                      (errno = E2BIG, bpf/flows.c:262-279) and read back with fa_read_spilled(); without
@@ -218,6 +237,7 @@ typedef struct fa_stats {
     uint64_t hashmap_fail_create; /* KERNEL_MAP mode: HASHMAP_FAIL_CREATE_FLOW (flows.c:285)               */
     uint64_t ringbuf_spilled;     /* KERNEL_MAP mode: single-packet records handed to the fallback ring     */
     uint64_t ringbuf_dropped;     /* ... that found the ring full ("couldn't reserve space", flows.c:270)   */
+    uint64_t pkt_drops_ingested;  /* samples consumed by fa_ingest_pkt_drops */
 } fa_stats;
 
 typedef struct fa_engine fa_engine;
@@ -256,6 +276,10 @@ int fa_ingest_additional(fa_engine* e, const void* additional_records, size_t n)
  * (pkg/model/flow_content.go:76-96). */
 int fa_ingest_dns(fa_engine* e, const void* dns_records, size_t n);
 
+/* Fold n (flow_id + pkt_drop_metrics) samples: saturating u16 byte / packet sums, flags OR, latest non-zero cause and
+ * state.  Replaces: bpf/pkt_drops.h:10-23,80-98 + AccumulateDrops (pkg/model/flow_content.go:98-117). */
+int fa_ingest_pkt_drops(fa_engine* e, const void* pkt_drop_records, size_t n);
+
 /* Lookup-and-delete every live flow (host or device output pointers).
  * Replaces: FlowFetcher.LookupAndDeleteMap (pkg/tracer/tracer.go:1063-1157)
  * and Accounter.evict's map hand-over (pkg/flow/account.go:67-68,86-87).
@@ -264,6 +288,21 @@ int fa_ingest_dns(fa_engine* e, const void* dns_records, size_t n);
  * Output order is unspecified, as in the reference (Go map iteration). */
 int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additional,
              uint8_t* out_present, size_t cap, size_t* n_out);
+
+/* fa_evict with every per-flow block the engine can produce (all pointers but `records` may be NULL; host or device):
+ *   pkt_drops: cap x 32 B fa_pkt_drop_metrics (present bit 2);
+ *   rtt_min:   cap x u64, the smallest non-zero flow_rtt of the flow's samples, 0 if none — an extension for BASELINE
+ *              config 5 ("RTT min/max"); the reference keeps only the maximum (AccumulateAdditional), so this field has
+ *              no reference analogue and is PARITY UNPINNED (checked against the oracle's own definition). */
+typedef struct fa_evict_out {
+    void*     records;               /* cap x 144 B */
+    void*     dns;                   /* cap x 64 B  */
+    void*     additional;            /* cap x 32 B  */
+    void*     pkt_drops;             /* cap x 32 B  */
+    uint64_t* rtt_min;               /* cap x 8 B   */
+    uint8_t*  present;               /* cap bytes: bit0 DNS, bit1 additional, bit2 packet drops */
+} fa_evict_out;
+int fa_evict_ex(fa_engine* e, const fa_evict_out* out, size_t cap, size_t* n_out);
 
 /* Lookup-and-RESET (no reference analogue; building block of the multi-GPU local combiner, the counterpart of
  * the reference folding its per-CPU maps in user space, pkg/tracer/tracer.go:1159-1187): every flow that received
@@ -322,16 +361,16 @@ typedef struct fa_pb_params {
 } fa_pb_params;
 
 /* Serialize n evicted flows (the outputs of fa_evict: records n x 144 B, and optionally dns n x 64 B, additional
- * n x 32 B, present n bytes; host or device pointers) as pbflow.Record messages, fields in field-number order as
+ * n x 32 B, pkt_drops n x 32 B, present n bytes; host or device pointers) as pbflow.Record messages, fields in field-number order as
  * protobuf-go writes them.  Replaces, batched: model.NewRecord (pkg/model/record.go:82-159: wall-clock times, interface
  * list, DNS latency, RTT), pbflow.FlowToPB + proto.Marshal (pkg/pbflow/proto.go:39-149, proto/flow.proto:31-126) and
  * getFlowKey (pkg/exporter/kafka_proto.go:37-47).
  * out_bytes (host or device, out_cap bytes) receives the messages back to back; offsets (n + 1 u64, may be NULL) the
  * start of each; keys_out (n x 32 B, may be NULL) the Kafka keys.  *out_len = bytes needed; FA_E_2BIG if > out_cap
  * (nothing written).  Not produced (no such state in the engine): xlat, quic, network_events_metadata. */
-int fa_pb_encode(fa_engine* e, const void* records, const void* dns, const void* additional, const uint8_t* present,
-                 size_t n, const fa_pb_params* p, void* out_bytes, size_t out_cap, uint64_t* offsets, void* keys_out,
-                 size_t* out_len);
+int fa_pb_encode(fa_engine* e, const void* records, const void* dns, const void* additional, const void* pkt_drops,
+                 const uint8_t* present, size_t n, const fa_pb_params* p, void* out_bytes, size_t out_cap, uint64_t* offsets,
+                 void* keys_out, size_t* out_len);
 
 /* Replaces: ReadGlobalCounter (pkg/tracer/tracer.go:1190-1226) + the metrics the
  * hot path increments (pkg/metrics/metrics.go:66-161). */

@@ -8,7 +8,7 @@ REC_BYTES, ID_BYTES, DNS_BYTES, ADD_BYTES, DNSREC_BYTES, ADDREC_BYTES = 144, 40,
 FA_OK, FA_FULL = 0, 1
 FA_E_INVAL, FA_E_NOMEM, FA_E_CUDA, FA_E_NODEV, FA_E_2BIG, FA_E_CLOSED = -22, -12, -5, -19, -7, -9
 FA_MODE_ACCOUNTER, FA_MODE_KERNEL_MAP = 0, 1
-FA_F_ENABLE_RTT, FA_F_ENABLE_DNS, FA_F_ENABLE_SKETCH, FA_F_NO_FULL_CUT, FA_F_RINGBUF_FALLBACK = 1, 2, 4, 8, 16
+FA_F_ENABLE_RTT, FA_F_ENABLE_DNS, FA_F_ENABLE_SKETCH, FA_F_NO_FULL_CUT, FA_F_RINGBUF_FALLBACK, FA_F_ENABLE_PKT_DROP = 1, 2, 4, 8, 16, 32
 FA_GEN_UNIFORM, FA_GEN_ZIPF = 0, 1
 FA_ABI_VERSION = 1
 
@@ -30,10 +30,15 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "records_ingested", "dns_ingested", "additional_ingested", "flows_evicted", "evictions", "live_flows",
         "spills", "order_fixups", "full_cuts", "kernel_launches", "h2d_bytes", "d2h_bytes",
-        "observed_intf_missed", "hashmap_fail_create", "ringbuf_spilled", "ringbuf_dropped")]
+        "observed_intf_missed", "hashmap_fail_create", "ringbuf_spilled", "ringbuf_dropped", "pkt_drops_ingested")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+
+
+class EvictOut(C.Structure):
+    _fields_ = [("records", C.c_void_p), ("dns", C.c_void_p), ("additional", C.c_void_p), ("pkt_drops", C.c_void_p),
+                ("rtt_min", C.c_void_p), ("present", C.c_void_p)]
 
 
 class IfaceName(C.Structure):
@@ -65,6 +70,8 @@ SIGNATURES = {
     "fa_ingest_events": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_ingest_additional": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_ingest_dns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fa_ingest_pkt_drops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fa_evict_ex": (C.c_int, [C.c_void_p, C.POINTER(EvictOut), C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_evict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                            C.POINTER(C.c_size_t)]),
     "fa_drain_active": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -82,7 +89,7 @@ SIGNATURES = {
     "fa_hll_estimate": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "fa_sketch_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "fa_sketch_reset": (C.c_int, [C.c_void_p]),
-    "fa_pb_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(PbParams),
+    "fa_pb_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(PbParams),
                                C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "fa_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "fa_sync": (C.c_int, [C.c_void_p]),

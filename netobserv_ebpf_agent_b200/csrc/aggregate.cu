@@ -29,8 +29,11 @@
 
 namespace fa {
 
-constexpr int kTile      = 256;                 // records per tile == threads per team
-constexpr int kTeams     = 4;                   // teams per CTA (one CTA per SM)
+#ifndef FA_K1_TILE
+#define FA_K1_TILE 256
+#endif
+constexpr int kTile      = FA_K1_TILE;          // records per tile == threads per team
+constexpr int kTeams     = 1024 / kTile;        // teams per CTA (one CTA per SM): independent tile pipelines that fill each other's bubbles
 constexpr int kCtaThreads = kTile * kTeams;
 constexpr int kRepSlots  = 2 * kTile;
 constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
@@ -204,7 +207,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                  uint32_t* __restrict__ spill_idx, SketchParams sk, unsigned long long* prof, uint32_t opt) {
     FA_DYN_SMEM(smem_raw);
     AggSmem& cs = *reinterpret_cast<AggSmem*>(smem_raw);
-    const int team = threadIdx.x >> 8;
+    const int team = threadIdx.x / kTile;
     const int tid = threadIdx.x & (kTile - 1), lane = tid & 31, warp = tid >> 5;     // within the team
     TeamSmem& s = cs.team[team];
     if (kDevN) n = min(n, (uint32_t)ctr->launch_n);            // size known on the device only (multi-GPU receive side)
@@ -247,6 +250,10 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         const uint32_t cnt = min((uint32_t)kTile, n - first);
         mbar_wait(&s.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
+        if ((opt & 32u) && tid == 0) {                             // have L2 fetch the team's next tile while this one is worked on
+            const uint32_t nt = tile_idx + tile_stride;
+            if (nt < n_tiles) tma_prefetch_l2(recs + (size_t)nt * kTile * kRecChunks, min((uint32_t)kTile, n - nt * kTile) * kRecBytes);
+        }
 
         // ------------------------------------------------------ E: hash, cache / elect, fold duplicates
         {

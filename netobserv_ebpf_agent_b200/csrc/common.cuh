@@ -19,6 +19,7 @@ constexpr int kRecChunks  = 9;      // 16-byte chunks per record
 constexpr int kKeyBytes   = 40;
 constexpr int kDnsRecBytes = 104;   // flow_id + dns_metrics
 constexpr int kAddRecBytes = 72;    // flow_id + additional_metrics
+constexpr int kDropRecBytes = 72;   // flow_id + pkt_drop_metrics
 
 // byte offsets inside the 144-byte record
 constexpr int R_START = 40, R_END = 48, R_BYTES = 56, R_PACKETS = 64, R_ETH = 68, R_FLAGS = 70, R_DESC = 72;
@@ -66,6 +67,7 @@ struct Table {
     uint4*   cold;       // slots x 2 uint4: observed interfaces (KERNEL_MAP mode: nullptr, it keeps its own metrics lines)
     uint4*   feat_add;   // slots x 5 uint4 (80 B) or nullptr: additional_metrics fold state
     uint4*   feat_dns;   // slots x 8 uint4 (128 B) or nullptr: dns_metrics fold state
+    uint4*   feat_drop;  // slots x 6 uint4 (96 B) or nullptr: pkt_drop_metrics fold state
     uint32_t* occ;       // occupancy bitmap, 1 bit per slot: eviction visits live flows only
     uint64_t mask;       // slots - 1 (slots is a power of two)
 };

@@ -133,7 +133,8 @@ struct fa_engine {
     uint8_t* d_evict_dns = nullptr; uint8_t* d_evict_add = nullptr; uint8_t* d_evict_present = nullptr;
     uint32_t* d_slot_of_out = nullptr; uint64_t feat_evict_cap = 0;
     uint32_t* d_slot_of = nullptr;            // per-sample slot scratch of the feature folds
-    uint64_t feat_seq[2] = {0, 0};            // running sample numbers (additional, dns)
+    uint64_t feat_seq[3] = {0, 0, 0};         // running sample numbers (additional, dns, packet drops)
+    uint8_t* d_evict_drop = nullptr; unsigned long long* d_evict_rttmin = nullptr;
     uint32_t* d_route_tmp = nullptr; unsigned long long* d_route_counts = nullptr;
 
     fa::SketchParams sk{};
@@ -479,7 +480,11 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
         CU(cudaMalloc(&e->table.feat_dns, slots * 128));
         CU(cudaMemsetAsync(e->table.feat_dns, 0, slots * 128, e->stream));
     }
-    if (cfg->flags & (FA_F_ENABLE_RTT | FA_F_ENABLE_DNS)) CU(cudaMalloc(&e->d_slot_of, e_max_batch_tmp(cfg) * 4));
+    if (cfg->flags & FA_F_ENABLE_PKT_DROP) {
+        CU(cudaMalloc(&e->table.feat_drop, slots * 96));
+        CU(cudaMemsetAsync(e->table.feat_drop, 0, slots * 96, e->stream));
+    }
+    if (cfg->flags & (FA_F_ENABLE_RTT | FA_F_ENABLE_DNS | FA_F_ENABLE_PKT_DROP)) CU(cudaMalloc(&e->d_slot_of, e_max_batch_tmp(cfg) * 4));
     CU(cudaMalloc(&e->d_ctr, sizeof(fa::Counters)));
     CU(cudaMemsetAsync(e->d_ctr, 0, sizeof(fa::Counters), e->stream));
     CU(cudaHostAlloc(&e->h_ctr, sizeof(fa::Counters), cudaHostAllocDefault));
@@ -552,7 +557,7 @@ void fa_destroy(fa_engine* e) {
         cudaFree(e->d_prof);
     }
     if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
-    cudaFree(e->table.ident); cudaFree(e->table.cold); cudaFree(e->table.occ); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns);
+    cudaFree(e->table.ident); cudaFree(e->table.cold); cudaFree(e->table.occ); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns); cudaFree(e->table.feat_drop);
     cudaFree(e->d_ctr); if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_live_ring) cudaFreeHost(e->h_live_ring);
     for (int i = 0; i < fa_engine::kLiveRing; i++) if (e->ev_live[i]) cudaEventDestroy(e->ev_live[i]);
@@ -565,6 +570,7 @@ void fa_destroy(fa_engine* e) {
     if (e->h_cut_out) cudaFreeHost(e->h_cut_out);
     cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts); cudaFree(e->d_events); cudaFree(e->d_expanded);
     cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out); cudaFree(e->d_slot_of);
+    cudaFree(e->d_evict_drop); cudaFree(e->d_evict_rttmin);
     cudaFree(e->sk.cms); cudaFree(e->sk.hll);
     cudaFree(e->km_met); cudaFree(e->km_slot_of); cudaFree(e->km_bset); cudaFree(e->km_blist); cudaFree(e->km_spill);
     cudaFree(e->km_touched); cudaFree(e->km_deferred); cudaFree(e->km_brec);
@@ -641,14 +647,14 @@ int fa_ingest_events(fa_engine* e, const void* events, size_t n, size_t* consume
 }
 
 static int ingest_feature(fa_engine* e, int kind, const void* recs, size_t n, const char* who) {
-    const uint32_t flag = kind == 0 ? FA_F_ENABLE_RTT : FA_F_ENABLE_DNS;
+    const uint32_t flag = kind == 0 ? FA_F_ENABLE_RTT : kind == 1 ? FA_F_ENABLE_DNS : FA_F_ENABLE_PKT_DROP;
     if (!e) return fail(FA_E_INVAL, "%s: null engine", who);
-    if (!(e->cfg.flags & flag)) return fail(FA_E_INVAL, "%s: engine was created without %s", who, kind == 0 ? "FA_F_ENABLE_RTT" : "FA_F_ENABLE_DNS");
+    if (!(e->cfg.flags & flag)) return fail(FA_E_INVAL, "%s: engine was created without %s", who, kind == 0 ? "FA_F_ENABLE_RTT" : kind == 1 ? "FA_F_ENABLE_DNS" : "FA_F_ENABLE_PKT_DROP");
     if (n == 0) return FA_OK;
     if (!recs) return fail(FA_E_INVAL, "%s: null records", who);
     std::lock_guard<std::mutex> lk(e->mu);
     CU(cudaSetDevice(e->device));
-    const size_t rec_bytes = kind == 0 ? fa::kAddRecBytes : fa::kDnsRecBytes;
+    const size_t rec_bytes = kind == 1 ? fa::kDnsRecBytes : fa::kAddRecBytes;      // additional and packet-drop samples: 72 B
     const PtrKind k = classify(recs);
     if (k == PTR_DEVICE && (reinterpret_cast<uintptr_t>(recs) & 7)) return fail(FA_E_INVAL, "%s: device records must be 8-byte aligned", who);
     // feature samples may create flows: never let the table pass 7/8 of its slots
@@ -674,7 +680,7 @@ static int ingest_feature(fa_engine* e, int kind, const void* recs, size_t n, co
         CU(cudaGetLastError());
         e->feat_seq[kind] += c;
         e->unsynced_records += c;
-        if (kind == 0) e->st.additional_ingested += c; else e->st.dns_ingested += c;
+        if (kind == 0) e->st.additional_ingested += c; else if (kind == 1) e->st.dns_ingested += c; else e->st.pkt_drops_ingested += c;
         if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->stream));   // d_stage[0] is reused by the next chunk
         done += c;
     }
@@ -683,6 +689,7 @@ static int ingest_feature(fa_engine* e, int kind, const void* recs, size_t n, co
 
 int fa_ingest_additional(fa_engine* e, const void* recs, size_t n) { return ingest_feature(e, 0, recs, n, "fa_ingest_additional"); }
 int fa_ingest_dns(fa_engine* e, const void* recs, size_t n) { return ingest_feature(e, 1, recs, n, "fa_ingest_dns"); }
+int fa_ingest_pkt_drops(fa_engine* e, const void* recs, size_t n) { return ingest_feature(e, 2, recs, n, "fa_ingest_pkt_drops"); }
 
 int fa_live_flows(fa_engine* e, size_t* n) {
     if (!e || !n) return fail(FA_E_INVAL, "fa_live_flows: null argument");
@@ -694,10 +701,10 @@ int fa_live_flows(fa_engine* e, size_t* n) {
     return FA_OK;
 }
 
-int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additional, uint8_t* out_present,
-             size_t cap, size_t* n_out) {
+int fa_evict_ex(fa_engine* e, const fa_evict_out* o, size_t cap, size_t* n_out) {
     if (n_out) *n_out = 0;
-    if (!e || !n_out) return fail(FA_E_INVAL, "fa_evict: null argument");
+    if (!e || !n_out || !o) return fail(FA_E_INVAL, "fa_evict: null argument");
+    void* out_records = o->records; void* out_dns = o->dns; void* out_additional = o->additional; uint8_t* out_present = o->present;
     std::lock_guard<std::mutex> lk(e->mu);
     CU(cudaSetDevice(e->device));
     int rc = sync_counters(e);
@@ -707,7 +714,7 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
     if (live == 0) return FA_OK;
     if (!out_records) return fail(FA_E_INVAL, "fa_evict: null out_records");
     if (cap < live) return fail(FA_E_2BIG, "fa_evict: capacity %zu < %llu live flows", cap, (unsigned long long)live);
-    const bool feats = e->table.feat_add || e->table.feat_dns;
+    const bool feats = e->table.feat_add || e->table.feat_dns || e->table.feat_drop;
     const PtrKind k = classify(out_records);
     uint8_t* d_out = nullptr;
     if (k == PTR_DEVICE) {
@@ -722,18 +729,24 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
         d_out = e->d_evict;
     }
     // feature outputs are staged on the device unless the caller handed device pointers
-    uint8_t *d_dns = nullptr, *d_add = nullptr, *d_pres = nullptr;
+    uint8_t *d_dns = nullptr, *d_add = nullptr, *d_drop = nullptr, *d_pres = nullptr;
+    unsigned long long* d_rmin = nullptr;
     if (feats) {
         if (e->feat_evict_cap < live) {
             cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out);
-            e->d_evict_dns = e->d_evict_add = e->d_evict_present = nullptr; e->d_slot_of_out = nullptr; e->feat_evict_cap = 0;
+            cudaFree(e->d_evict_drop); cudaFree(e->d_evict_rttmin);
+            e->d_evict_dns = e->d_evict_add = e->d_evict_present = e->d_evict_drop = nullptr; e->d_evict_rttmin = nullptr;
+            e->d_slot_of_out = nullptr; e->feat_evict_cap = 0;
             uint64_t want = std::max<uint64_t>(live, std::min<uint64_t>(e->cfg.max_entries, live * 2));
             CU(cudaMalloc(&e->d_evict_dns, want * 64)); CU(cudaMalloc(&e->d_evict_add, want * 32));
+            CU(cudaMalloc(&e->d_evict_drop, want * 32)); CU(cudaMalloc(&e->d_evict_rttmin, want * 8));
             CU(cudaMalloc(&e->d_evict_present, want)); CU(cudaMalloc(&e->d_slot_of_out, want * 4));
             e->feat_evict_cap = want;
         }
         d_dns = out_dns ? (classify(out_dns) == PTR_DEVICE ? static_cast<uint8_t*>(out_dns) : e->d_evict_dns) : nullptr;
         d_add = out_additional ? (classify(out_additional) == PTR_DEVICE ? static_cast<uint8_t*>(out_additional) : e->d_evict_add) : nullptr;
+        d_drop = o->pkt_drops ? (classify(o->pkt_drops) == PTR_DEVICE ? static_cast<uint8_t*>(o->pkt_drops) : e->d_evict_drop) : nullptr;
+        d_rmin = o->rtt_min ? (classify(o->rtt_min) == PTR_DEVICE ? reinterpret_cast<unsigned long long*>(o->rtt_min) : e->d_evict_rttmin) : nullptr;
         d_pres = out_present ? (classify(out_present) == PTR_DEVICE ? out_present : e->d_evict_present) : nullptr;
     }
     CU(cudaMemsetAsync(&e->d_ctr->evict_out, 0, sizeof(unsigned long long), e->stream));
@@ -744,7 +757,7 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
         e->st.kernel_launches += fa::launch_evict(e->table, reinterpret_cast<uint4*>(d_out), feats ? e->d_slot_of_out : nullptr, live,
                                                   e->d_ctr, e->sm_count, e->stream);
     if (feats)
-        e->st.kernel_launches += fa::launch_evict_features(e->table, e->d_slot_of_out, live, d_out, d_dns, d_add, d_pres,
+        e->st.kernel_launches += fa::launch_evict_features(e->table, e->d_slot_of_out, live, d_out, d_dns, d_add, d_drop, d_rmin, d_pres,
                                                            e->sm_count, e->stream);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(&e->d_ctr->live, 0, sizeof(unsigned long long), e->stream));
@@ -755,6 +768,8 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
     if (feats) {
         if (out_dns && d_dns == e->d_evict_dns) { CU(cudaMemcpyAsync(out_dns, d_dns, live * 64, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += live * 64; }
         if (out_additional && d_add == e->d_evict_add) { CU(cudaMemcpyAsync(out_additional, d_add, live * 32, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += live * 32; }
+        if (o->pkt_drops && d_drop == e->d_evict_drop) { CU(cudaMemcpyAsync(o->pkt_drops, d_drop, live * 32, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += live * 32; }
+        if (o->rtt_min && d_rmin == e->d_evict_rttmin) { CU(cudaMemcpyAsync(o->rtt_min, d_rmin, live * 8, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += live * 8; }
         if (out_present && d_pres == e->d_evict_present) { CU(cudaMemcpyAsync(out_present, d_pres, live, cudaMemcpyDeviceToHost, e->stream)); e->st.d2h_bytes += live; }
     }
     CU(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(fa::Counters), cudaMemcpyDeviceToHost, e->stream));
@@ -765,6 +780,8 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
         if (out_present && classify(out_present) != PTR_DEVICE) memset(out_present, 0, live);
         if (out_dns && classify(out_dns) != PTR_DEVICE) memset(out_dns, 0, live * 64);
         if (out_additional && classify(out_additional) != PTR_DEVICE) memset(out_additional, 0, live * 32);
+        if (o->pkt_drops && classify(o->pkt_drops) != PTR_DEVICE) memset(o->pkt_drops, 0, live * 32);
+        if (o->rtt_min && classify(o->rtt_min) != PTR_DEVICE) memset(o->rtt_min, 0, live * 8);
     }
     e->live_known = 0; e->unsynced_records = 0; e->ring_head = e->ring_tail;
     e->st.flows_evicted += live;
@@ -772,11 +789,18 @@ int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additiona
     return FA_OK;
 }
 
+int fa_evict(fa_engine* e, void* out_records, void* out_dns, void* out_additional, uint8_t* out_present,
+             size_t cap, size_t* n_out) {
+    fa_evict_out o{};
+    o.records = out_records; o.dns = out_dns; o.additional = out_additional; o.present = out_present;
+    return fa_evict_ex(e, &o, cap, n_out);
+}
+
 int fa_drain_active(fa_engine* e, void* out_records_dev, size_t cap, size_t* n_out) {
     if (n_out) *n_out = 0;
     if (!e || !n_out || !out_records_dev) return fail(FA_E_INVAL, "fa_drain_active: null argument");
     if (classify(out_records_dev) != PTR_DEVICE) return fail(FA_E_INVAL, "fa_drain_active: out_records must be device memory");
-    if (e->table.feat_add || e->table.feat_dns) return fail(FA_E_INVAL, "fa_drain_active: not available with feature folds enabled");
+    if (e->table.feat_add || e->table.feat_dns || e->table.feat_drop) return fail(FA_E_INVAL, "fa_drain_active: not available with feature folds enabled");
     if (e->cfg.mode != FA_MODE_ACCOUNTER) return fail(FA_E_INVAL, "fa_drain_active: ACCOUNTER mode only");
     std::lock_guard<std::mutex> lk(e->mu);
     CU(cudaSetDevice(e->device));
@@ -795,7 +819,7 @@ int fa_drain_active(fa_engine* e, void* out_records_dev, size_t cap, size_t* n_o
 
 int fa_drain_active_counted(fa_engine* e, void* out_records_dev, size_t cap, uint64_t* n_dev_out) {
     if (!e || !out_records_dev || !n_dev_out) return fail(FA_E_INVAL, "fa_drain_active_counted: null argument");
-    if (e->table.feat_add || e->table.feat_dns) return fail(FA_E_INVAL, "fa_drain_active_counted: not available with feature folds enabled");
+    if (e->table.feat_add || e->table.feat_dns || e->table.feat_drop) return fail(FA_E_INVAL, "fa_drain_active_counted: not available with feature folds enabled");
     if (e->cfg.mode != FA_MODE_ACCOUNTER) return fail(FA_E_INVAL, "fa_drain_active_counted: ACCOUNTER mode only");
     std::lock_guard<std::mutex> lk(e->mu);
     CU(cudaSetDevice(e->device));
@@ -986,9 +1010,9 @@ int fa_read_spilled(fa_engine* e, void* out_records, size_t cap, size_t* n_out) 
 static_assert(sizeof(fa_iface_name) == sizeof(fa::PbIface) && offsetof(fa_iface_name, name) == offsetof(fa::PbIface, name) &&
               offsetof(fa_iface_name, udn) == offsetof(fa::PbIface, udn), "fa_iface_name layout");
 
-int fa_pb_encode(fa_engine* e, const void* records, const void* dns, const void* additional, const uint8_t* present,
-                 size_t n, const fa_pb_params* p, void* out_bytes, size_t out_cap, uint64_t* offsets, void* keys_out,
-                 size_t* out_len) {
+int fa_pb_encode(fa_engine* e, const void* records, const void* dns, const void* additional, const void* pkt_drops,
+                 const uint8_t* present, size_t n, const fa_pb_params* p, void* out_bytes, size_t out_cap, uint64_t* offsets,
+                 void* keys_out, size_t* out_len) {
     if (out_len) *out_len = 0;
     if (!e || !p || !out_len) return fail(FA_E_INVAL, "fa_pb_encode: null argument");
     if (n == 0) return FA_OK;
@@ -999,11 +1023,11 @@ int fa_pb_encode(fa_engine* e, const void* records, const void* dns, const void*
     CU(cudaSetDevice(e->device));
     struct DevBuf { void* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } };
     // inputs: device pointers are used in place, host buffers are staged
-    DevBuf in_bufs[4], out_buf, keys_buf;
-    const void* src[4] = {records, dns, additional, present};
-    const size_t width[4] = {fa::kRecBytes, 64, 32, 1};
-    const uint8_t* d_in[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < 4; i++) {
+    DevBuf in_bufs[5], out_buf, keys_buf;
+    const void* src[5] = {records, dns, additional, present, pkt_drops};
+    const size_t width[5] = {fa::kRecBytes, 64, 32, 1, 32};
+    const uint8_t* d_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 5; i++) {
         if (!src[i]) continue;
         if (classify(src[i]) == PTR_DEVICE) { d_in[i] = static_cast<const uint8_t*>(src[i]); continue; }
         CU(cudaMalloc(&in_bufs[i].p, n * width[i]));
@@ -1031,7 +1055,7 @@ int fa_pb_encode(fa_engine* e, const void* records, const void* dns, const void*
     P.agent_is_v4 = p->agent_ip_is_v4 ? 1u : 0u;
     P.wrap = (p->flags & FA_PB_WRAP_ENTRIES) ? 1u : 0u;
     P.ifaces = e->d_pb_ifaces; P.n_ifaces = p->n_ifaces;
-    fa::PbInputs in{d_in[0], d_in[1], d_in[2], nullptr, d_in[3]};
+    fa::PbInputs in{d_in[0], d_in[1], d_in[2], d_in[4], d_in[3]};
     e->st.kernel_launches += fa::launch_pb_sizes(in, (uint32_t)n, P, e->d_pb_sizes, e->d_pb_offsets, e->d_pb_sums, e->sm_count, e->stream);
     CU(cudaGetLastError());
     unsigned long long total = 0;

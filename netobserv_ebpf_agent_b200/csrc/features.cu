@@ -3,6 +3,7 @@
 //   additional_metrics (RTT / IPsec): bpf/rtt_tracker.h:12-22,73-91 + AccumulateAdditional
 //                                     (pkg/model/flow_content.go:154-177)
 //   dns_metrics:                      bpf/flows.c:145-158,291-330 + AccumulateDNS (flow_content.go:76-96)
+//   pkt_drop_metrics:                 bpf/pkt_drops.h:10-23,80-98 + AccumulateDrops (flow_content.go:98-117)
 //   base effects of both:             buildBaseFromAdditional (flow_content.go:63-74)
 //   merged view at eviction:          LookupAndDeleteMap (pkg/tracer/tracer.go:1098-1151,1159-1187)
 //
@@ -32,8 +33,16 @@ namespace fa {
 //   [32] nfs                          [40] fe
 //   [48] neth                         [56] flags (or, u32) | first.eth (u16 @60)
 //   [64] first.start                  [72] first.end          [80..112) first.name[32]   [112..128) spare
+// packet drops: 6 x uint4 (96 B)
+//   [ 0] nfirst                       [ 8] bytes sum (add; saturates to u16 at eviction == addUint16 chained)
+//   [16] packets sum                  [24] cause_seq = max (seq+1) over latest_drop_cause != 0 (the second pass stores the cause)
+//   [32] state_last = max (seq+1) << 8 | latest_state  over latest_state != 0
+//   [40] flags (or, u32) | first.eth (u16 @44)           [48] nfs        [56] fe        [64] neth
+//   [72] first.start                  [80] first.end                     [88] latest_drop_cause (u32)
+// additional, extension (no reference analogue): [72] nrtt_min = max ~rtt over rtt != 0 -> smallest non-zero RTT
 constexpr int kAddState = 5;    // uint4 per slot
 constexpr int kDnsState = 8;
+constexpr int kDropState = 6;
 
 __device__ __forceinline__ uint64_t ld_u64_unaligned8(const uint8_t* p) { return *reinterpret_cast<const uint64_t*>(p); }
 
@@ -92,7 +101,7 @@ __global__ void additional_fold_kernel(const uint8_t* __restrict__ recs, uint32_
         const uint64_t seq = seq0 + i;
         uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_add) + (size_t)slot * (kAddState * 16);
         red_max_u64(S + 0, ~seq);
-        if (rtt) red_max_u64(S + 8, rtt);
+        if (rtt) { red_max_u64(S + 8, rtt); red_max_u64(S + 72, ~rtt); }
         red_max_u64(S + 16, ((uint64_t)(ret ^ 0x80000000u) << 1) | enc | (1ull << 40));   // bit 40: "has a sample"
         if (start) red_max_u64(S + 24, 0ull - start);
         if (end) red_max_u64(S + 32, end);
@@ -153,12 +162,62 @@ __global__ void dns_first_kernel(const uint8_t* __restrict__ recs, uint32_t n, T
     }
 }
 
+// pkt_drop_metrics samples (flow_id 40 B + start 8, end 8, bytes u16, packets u16, latest_drop_cause u32, latest_flags u16,
+// eth_protocol u16, latest_state u8): AccumulateDrops in sample order
+__global__ void pktdrop_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, uint64_t seq0,
+                                    uint32_t* __restrict__ slot_of, Counters* ctr) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint8_t* R = recs + (size_t)i * kDropRecBytes;
+        uint64_t k[5]; load_key(R, k);
+        const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
+        slot_of[i] = slot;
+        if (slot == 0xFFFFFFFFu) { atomicAdd(&ctr->spills, 1ull); continue; }
+        const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48);
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(R + 56);        // bytes u16 | packets u16
+        const uint32_t cause = *reinterpret_cast<const uint32_t*>(R + 60);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(R + 64);        // latest_flags u16 | eth u16
+        const uint32_t state = R[68];
+        const uint32_t flags = w1 & 0xFFFFu, eth = w1 >> 16;
+        const uint64_t seq = seq0 + i;
+        uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_drop) + (size_t)slot * (kDropState * 16);
+        red_max_u64(S + 0, ~seq);
+        red_add_u64(S + 8, w0 & 0xFFFFu);
+        red_add_u64(S + 16, w0 >> 16);
+        if (cause) red_max_u64(S + 24, seq + 1);
+        if (state) red_max_u64(S + 32, ((seq + 1) << 8) | state);
+        if (flags) red_or_u32(S + 40, flags);
+        if (start) red_max_u64(S + 48, 0ull - start);
+        if (end) red_max_u64(S + 56, end);
+        if (eth) red_max_u64(S + 64, ~((seq << 16) | eth));
+    }
+}
+__global__ void pktdrop_first_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t seq0,
+                                     const uint32_t* __restrict__ slot_of) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = slot_of[i];
+        if (slot == 0xFFFFFFFFu) continue;
+        uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_drop) + (size_t)slot * (kDropState * 16);
+        const uint8_t* R = recs + (size_t)i * kDropRecBytes;
+        const uint64_t seq = seq0 + i;
+        if (*reinterpret_cast<const uint64_t*>(S) == ~seq) {                   // the flow's first sample: its block is adopted
+            *reinterpret_cast<uint16_t*>(S + 44) = *reinterpret_cast<const uint16_t*>(R + 66);
+            *reinterpret_cast<uint64_t*>(S + 72) = ld_u64_unaligned8(R + 40);
+            *reinterpret_cast<uint64_t*>(S + 80) = ld_u64_unaligned8(R + 48);
+        }
+        if (*reinterpret_cast<const uint64_t*>(S + 24) == seq + 1)             // the last sample with a drop cause
+            *reinterpret_cast<uint32_t*>(S + 88) = *reinterpret_cast<const uint32_t*>(R + 60);
+    }
+}
+
 #ifndef FA_HOST_EMUL
 int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& t, uint64_t epoch, uint64_t seq0,
                         uint32_t* slot_of, Counters* ctr, int sm_count, cudaStream_t st) {
     if (!n) return 0;
     const int grid = sm_count * 8;
-    if (kind == 0) {
+    if (kind == 2) {
+        pktdrop_fold_kernel<<<grid, 256, 0, st>>>(recs, n, t, epoch, seq0, slot_of, ctr);
+        pktdrop_first_kernel<<<grid, 256, 0, st>>>(recs, n, t, seq0, slot_of);
+    } else if (kind == 0) {
         additional_fold_kernel<<<grid, 256, 0, st>>>(recs, n, t, epoch, seq0, slot_of, ctr);
         additional_first_kernel<<<grid, 256, 0, st>>>(recs, n, t, seq0, slot_of);
     } else {
@@ -180,7 +239,8 @@ __device__ __forceinline__ void build_base(uint64_t& bs, uint64_t& be, uint32_t&
 
 __global__ void evict_features_kernel(Table t, const uint32_t* __restrict__ slot_of_out, unsigned long long n_out,
                                       uint8_t* __restrict__ out_recs, uint8_t* __restrict__ out_dns,
-                                      uint8_t* __restrict__ out_add, uint8_t* __restrict__ out_present) {
+                                      uint8_t* __restrict__ out_add, uint8_t* __restrict__ out_drop,
+                                      unsigned long long* __restrict__ out_rtt_min, uint8_t* __restrict__ out_present) {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_out;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t slot = slot_of_out[i];
@@ -212,10 +272,35 @@ __global__ void evict_features_kernel(Table t, const uint32_t* __restrict__ slot
                 for (int c = 0; c < 8; c++) reinterpret_cast<uint64_t*>(out_dns + i * 64)[c] = 0ull;
             }
         }
+        if (t.feat_drop) {                                // packet drops come second (tracer.go:1107-1115)
+            uint64_t* S = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(t.feat_drop) + (size_t)slot * (kDropState * 16));
+            if (S[0] != 0) {
+                present |= 4;
+                build_base(bs, be, beth, S[6], S[7], S[8]);
+                if (out_drop) {
+                    uint8_t* D = out_drop + i * 32;
+                    const uint8_t* Sb = reinterpret_cast<const uint8_t*>(S);
+                    *reinterpret_cast<uint64_t*>(D + 0) = S[9];                              // first.start
+                    *reinterpret_cast<uint64_t*>(D + 8) = S[10];                             // first.end
+                    *reinterpret_cast<uint16_t*>(D + 16) = (uint16_t)(S[1] > 0xFFFFull ? 0xFFFFull : S[1]);   // addUint16 saturates
+                    *reinterpret_cast<uint16_t*>(D + 18) = (uint16_t)(S[2] > 0xFFFFull ? 0xFFFFull : S[2]);
+                    *reinterpret_cast<uint32_t*>(D + 20) = *reinterpret_cast<const uint32_t*>(Sb + 88);   // latest_drop_cause: last non-zero
+                    *reinterpret_cast<uint16_t*>(D + 24) = (uint16_t)(*reinterpret_cast<const uint32_t*>(Sb + 40));  // latest_flags: or
+                    *reinterpret_cast<uint16_t*>(D + 26) = *reinterpret_cast<const uint16_t*>(Sb + 44);              // first.eth
+                    *reinterpret_cast<uint32_t*>(D + 28) = (uint32_t)(S[4] & 0xFFu);          // latest_state: last non-zero; padding
+                }
+#pragma unroll
+                for (int c = 0; c < 12; c++) S[c] = 0ull;
+            } else if (out_drop) {
+                for (int c = 0; c < 4; c++) reinterpret_cast<uint64_t*>(out_drop + i * 32)[c] = 0ull;
+            }
+        }
+        if (out_rtt_min) out_rtt_min[i] = 0ull;
         if (t.feat_add) {
             uint64_t* S = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(t.feat_add) + (size_t)slot * (kAddState * 16));
             if (S[0] != 0) {
                 present |= 2;
+                if (out_rtt_min) out_rtt_min[i] = S[9] ? ~S[9] : 0ull;                       // extension: smallest non-zero RTT
                 build_base(bs, be, beth, S[3], S[4], S[5]);
                 if (out_add) {
                     uint8_t* A = out_add + i * 32;
@@ -245,9 +330,10 @@ __global__ void evict_features_kernel(Table t, const uint32_t* __restrict__ slot
 
 #ifndef FA_HOST_EMUL
 int launch_evict_features(const Table& t, const uint32_t* slot_of_out, unsigned long long n_out, uint8_t* out_recs,
-                          uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present, int sm_count, cudaStream_t st) {
+                          uint8_t* out_dns, uint8_t* out_add, uint8_t* out_drop, unsigned long long* out_rtt_min,
+                          uint8_t* out_present, int sm_count, cudaStream_t st) {
     if (!n_out) return 0;
-    evict_features_kernel<<<sm_count * 8, 256, 0, st>>>(t, slot_of_out, n_out, out_recs, out_dns, out_add, out_present);
+    evict_features_kernel<<<sm_count * 8, 256, 0, st>>>(t, slot_of_out, n_out, out_recs, out_dns, out_add, out_drop, out_rtt_min, out_present);
     return 1;
 }
 #endif  // FA_HOST_EMUL

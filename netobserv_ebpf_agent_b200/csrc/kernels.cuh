@@ -58,11 +58,13 @@ int launch_full_cut(const uint4* recs, uint32_t n, const Table& table, unsigned 
                     unsigned long long max_entries, uint32_t* idx_set, uint32_t set_slots, uint32_t* bitmap,
                     uint32_t* cut_out, int sm_count, cudaStream_t st);
 
-// K6 feature folds (kind 0 = additional_metrics 72-B records, 1 = dns_metrics 104-B records); slot_of: n u32 scratch
+// K6 feature folds (kind 0 = additional_metrics 72-B records, 1 = dns_metrics 104-B records, 2 = pkt_drop_metrics 72-B
+// records); slot_of: n u32 scratch
 int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& t, uint64_t epoch, uint64_t seq0,
                         uint32_t* slot_of, Counters* ctr, int sm_count, cudaStream_t st);
 int launch_evict_features(const Table& t, const uint32_t* slot_of_out, unsigned long long n_out, uint8_t* out_recs,
-                          uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present, int sm_count, cudaStream_t st);
+                          uint8_t* out_dns, uint8_t* out_add, uint8_t* out_drop, unsigned long long* out_rtt_min,
+                          uint8_t* out_present, int sm_count, cudaStream_t st);
 
 // sketches
 int launch_cms_query(const SketchParams& sk, const uint4* keys, uint32_t n, unsigned long long* est, cudaStream_t st);

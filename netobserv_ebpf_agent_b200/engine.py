@@ -82,6 +82,10 @@ class FlowAggEngine:
         nb = _nbytes(recs)
         check(lib().fa_ingest_additional(self._h, _ptr(recs), nb // 72))
 
+    def ingest_pkt_drops(self, recs):
+        nb = _nbytes(recs)
+        check(lib().fa_ingest_pkt_drops(self._h, _ptr(recs), nb // 72))
+
     # -- evict ------------------------------------------------------------------
     def live_flows(self):
         n = C.c_size_t(0)
@@ -103,6 +107,21 @@ class FlowAggEngine:
             return out[:g], dns[:g], add[:g], pres[:g]
         check(lib().fa_evict(self._h, _ptr(out), None, None, None, cap, C.byref(got)))
         return out[: got.value]
+
+    def evict_ex(self):
+        """Lookup-and-delete all flows with every block -> records (n,144), dns (n,64), additional (n,32),
+        pkt_drops (n,32), rtt_min (n,) u64, present (n,)."""
+        from ._lib import EvictOut
+        n = self.live_flows()
+        cap = max(n, 1)
+        out, dns, add = np.zeros((cap, REC_BYTES), np.uint8), np.zeros((cap, 64), np.uint8), np.zeros((cap, 32), np.uint8)
+        drops, rmin, pres = np.zeros((cap, 32), np.uint8), np.zeros(cap, np.uint64), np.zeros(cap, np.uint8)
+        o = EvictOut(records=out.ctypes.data, dns=dns.ctypes.data, additional=add.ctypes.data, pkt_drops=drops.ctypes.data,
+                     rtt_min=rmin.ctypes.data, present=pres.ctypes.data)
+        got = C.c_size_t(0)
+        check(lib().fa_evict_ex(self._h, C.byref(o), cap, C.byref(got)))
+        g = got.value
+        return out[:g], dns[:g], add[:g], drops[:g], rmin[:g], pres[:g]
 
     def read_spilled(self, cap=131072):
         """KERNEL_MAP mode with FA_F_RINGBUF_FALLBACK: the single-packet records that could not enter the full map

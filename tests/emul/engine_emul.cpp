@@ -173,7 +173,10 @@ int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& 
                         uint32_t* slot_of, Counters* ctr, int, cudaStream_t) {
     if (!n) return 0;
     Table t = table;
-    if (kind == 0) {
+    if (kind == 2) {
+        simt::launch(2, 256, 0, [=] { pktdrop_fold_kernel(recs, n, t, epoch, seq0, slot_of, ctr); });
+        simt::launch(2, 256, 0, [=] { pktdrop_first_kernel(recs, n, t, seq0, slot_of); });
+    } else if (kind == 0) {
         simt::launch(2, 256, 0, [=] { additional_fold_kernel(recs, n, t, epoch, seq0, slot_of, ctr); });
         simt::launch(2, 256, 0, [=] { additional_first_kernel(recs, n, t, seq0, slot_of); });
     } else {
@@ -183,10 +186,11 @@ int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& 
     return 2;
 }
 int launch_evict_features(const Table& table, const uint32_t* slot_of_out, unsigned long long n_out, uint8_t* out_recs,
-                          uint8_t* out_dns, uint8_t* out_add, uint8_t* out_present, int, cudaStream_t) {
+                          uint8_t* out_dns, uint8_t* out_add, uint8_t* out_drop, unsigned long long* out_rtt_min,
+                          uint8_t* out_present, int, cudaStream_t) {
     if (!n_out) return 0;
     Table t = table;
-    simt::launch(2, 256, 0, [=] { evict_features_kernel(t, slot_of_out, n_out, out_recs, out_dns, out_add, out_present); });
+    simt::launch(2, 256, 0, [=] { evict_features_kernel(t, slot_of_out, n_out, out_recs, out_dns, out_add, out_drop, out_rtt_min, out_present); });
     return 1;
 }
 

@@ -135,7 +135,7 @@ uint64_t k1_emul_evict_features(void* h, uint8_t* out, uint8_t* out_dns, uint8_t
     uint4* o = reinterpret_cast<uint4*>(out);
     simt::launch(2, 256, 0, [=] { evict_kernel<false>(t, o, slot_of_out, cap, ctr); });
     const uint64_t n = ctr->evict_out;
-    simt::launch(2, 256, 0, [=] { evict_features_kernel(t, slot_of_out, n, out, out_dns, out_add, out_present); });
+    simt::launch(2, 256, 0, [=] { evict_features_kernel(t, slot_of_out, n, out, out_dns, out_add, nullptr, nullptr, out_present); });
     free(slot_of_out);
     ctr->live = 0;
     return n;

@@ -114,7 +114,7 @@ def _ip(msg, ip16, v4):
         msg.ipv6 = bytes(ip16)
 
 
-def flow_to_pb(rec144, dns64, add32, now_unix_ns, mono_now_ns, agent_ip16, agent_is_v4, ifaces):
+def flow_to_pb(rec144, dns64, add32, now_unix_ns, mono_now_ns, agent_ip16, agent_is_v4, ifaces, drop32=None):
     """NewRecord + FlowToPB for one evicted flow -> pbflow.Record message."""
     r = np.frombuffer(bytes(rec144), dtype=O.REC_DTYPE)[0]
     pb = Record()
@@ -132,6 +132,10 @@ def flow_to_pb(rec144, dns64, add32, now_unix_ns, mono_now_ns, agent_ip16, agent
     pb.bytes, pb.packets = int(r["bytes"]), int(r["packets"])
     _ip(pb.agent_ip, agent_ip16, agent_is_v4)
     pb.flags, pb.icmp_type, pb.icmp_code = int(r["flags"]), int(r["icmp_type"]), int(r["icmp_code"])
+    if drop32 is not None:                              # proto.go:86-92
+        p = np.frombuffer(bytes(drop32), dtype=O.DROP_DTYPE)[0]
+        pb.pkt_drop_bytes, pb.pkt_drop_packets = int(p["bytes"]), int(p["packets"])
+        pb.pkt_drop_latest_flags, pb.pkt_drop_latest_state, pb.pkt_drop_latest_drop_cause = int(p["flags"]), int(p["state"]), int(p["cause"])
     if dns64 is not None:
         d = np.frombuffer(bytes(dns64), dtype=O.DNS_DTYPE)[0]
         pb.dns_id, pb.dns_flags, pb.dns_errno = int(d["id"]), int(d["flags"]), int(d["errno"])

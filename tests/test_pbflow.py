@@ -14,7 +14,7 @@ import pbflow_ref as PB
 from common import gen_host
 
 
-def pb_encode(lib, h, recs, dns=None, add=None, present=None, now=1_700_000_000_123_456_789, mono=5_000_000_000_000,
+def pb_encode(lib, h, recs, dns=None, add=None, present=None, drops=None, now=1_700_000_000_123_456_789, mono=5_000_000_000_000,
               agent_ip=bytes(10) + b"\xff\xff" + bytes([10, 1, 2, 3]), agent_v4=1, ifaces=(), wrap=False, keys=True):
     from netobserv_ebpf_agent_b200._lib import IfaceName, PbParams
     recs = np.ascontiguousarray(recs).view(np.uint8).reshape(-1, 144)
@@ -32,13 +32,13 @@ def pb_encode(lib, h, recs, dns=None, add=None, present=None, now=1_700_000_000_
         p.agent_ip[i] = agent_ip[i]
     out_len = C.c_size_t(0)
     ptr = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None   # noqa: E731
-    rc = lib.fa_pb_encode(h, ptr(recs), ptr(dns), ptr(add), ptr(present), n, C.byref(p), None, 0, None, None, C.byref(out_len))
+    rc = lib.fa_pb_encode(h, ptr(recs), ptr(dns), ptr(add), ptr(drops), ptr(present), n, C.byref(p), None, 0, None, None, C.byref(out_len))
     assert rc == -7 and out_len.value > 0, rc                              # FA_E_2BIG reports the size
     out = np.zeros(out_len.value, dtype=np.uint8)
     offs = np.zeros(n + 1, dtype=np.uint64)
     kout = np.zeros((n, 32), dtype=np.uint8) if keys else None
-    rc = lib.fa_pb_encode(h, ptr(recs), ptr(dns), ptr(add), ptr(present), n, C.byref(p), ptr(out), out.size, ptr(offs), ptr(kout),
-                          C.byref(out_len))
+    rc = lib.fa_pb_encode(h, ptr(recs), ptr(dns), ptr(add), ptr(drops), ptr(present), n, C.byref(p), ptr(out), out.size, ptr(offs),
+                          ptr(kout), C.byref(out_len))
     assert rc == 0, (rc, lib.fa_last_error())
     assert offs[0] == 0 and offs[-1] == out.size == out_len.value
     return out.tobytes(), offs.astype(np.int64), kout
@@ -103,15 +103,19 @@ def check_batch(lib, h, n=3000, wrap=False):
         nm = names[i % len(names)]
         dv["name"][i] = list(nm[:32].ljust(32, b"\x00"))
     add.view(O.ADD_DTYPE).reshape(-1)["ipsec_ret"][::5] = -7
-    present = rng.integers(0, 4, n).astype(np.uint8)
+    drops = np.zeros(n, dtype=O.DROP_DTYPE)
+    drops["bytes"], drops["packets"] = rng.integers(0, 65536, n), rng.integers(0, 65536, n)
+    drops["cause"], drops["flags"], drops["state"] = rng.integers(0, 1 << 32, n), rng.integers(0, 1 << 16, n), rng.integers(0, 256, n)
+    drops = drops.view(np.uint8).reshape(n, 32)
+    present = rng.integers(0, 8, n).astype(np.uint8)
     ifaces = [(i, bytes([2, 0, 0, 0, 0, i]), f"eth{i}", "default" if i % 3 == 0 else "") for i in range(1, 12)]
     ifaces += [(3, bytes([2, 0, 0, 0, 9, 9]), "ens3-alt", "blue")]            # two rows for ifindex 3: disambiguated by MAC
     agent6 = bytes(range(0x20, 0x30))
-    raw, offs, keys = pb_encode(lib, h, recs, dns, add, present, ifaces=ifaces, agent_ip=agent6, agent_v4=0, wrap=wrap)
+    raw, offs, keys = pb_encode(lib, h, recs, dns, add, present, drops, ifaces=ifaces, agent_ip=agent6, agent_v4=0, wrap=wrap)
     now, mono = 1_700_000_000_123_456_789, 5_000_000_000_000
     for i in range(n):
         want = PB.flow_to_pb(recs[i].tobytes(), dns[i].tobytes() if present[i] & 1 else None, add[i].tobytes() if present[i] & 2 else None,
-                             now, mono, agent6, False, ifaces).SerializeToString()
+                             now, mono, agent6, False, ifaces, drops[i].tobytes() if present[i] & 4 else None).SerializeToString()
         got = raw[offs[i]:offs[i + 1]]
         if wrap:
             one = PB.Records(); one.ParseFromString(got)
@@ -179,7 +183,7 @@ def test_evicted_flows_go_straight_to_protobuf_from_device_memory():
             p.agent_ip[i] = b
         out = torch.empty(len(p_raw), dtype=torch.uint8, device="cuda")
         ln = C.c_size_t(0)
-        rc = fa.lib().fa_pb_encode(eng._h, C.c_void_p(dev.data_ptr()), None, None, None, n, C.byref(p), C.c_void_p(out.data_ptr()),
+        rc = fa.lib().fa_pb_encode(eng._h, C.c_void_p(dev.data_ptr()), None, None, None, None, n, C.byref(p), C.c_void_p(out.data_ptr()),
                                    out.numel(), None, None, C.byref(ln))
         assert rc == 0 and ln.value == len(p_raw)
         assert out.cpu().numpy().tobytes() == p_raw
