@@ -404,10 +404,32 @@ int fa_ipc_close(fa_engine* e, void* mapped);
 /* Like fa_drain_active, but asynchronous: the number of partial records lands in *n_dev_out (device memory). */
 int fa_drain_active_counted(fa_engine* e, void* out_records_dev, size_t cap, uint64_t* n_dev_out);
 /* Partition min(*n_dev, max_n) device-resident records (n_dev may be NULL: exactly max_n) by owner and store them
- * into peer_bufs[owner] (capacity cap records each), advancing *peer_counts[owner]. Records that do not fit are
- * counted in *overflow_dev. */
+ * into peer_bufs[owner] (capacity cap records each), advancing *peer_counts[owner].  overflow_dev points at two
+ * device u64: [0] += records that did not fit their receive buffer, [1] += records stored into a shard other than
+ * self_shard (x 144 B = the NVLink payload). */
 int fa_route_peer(fa_engine* e, const void* records_dev, const uint64_t* n_dev, size_t max_n, uint32_t n_shards,
-                  void* const* peer_bufs, uint64_t* const* peer_counts, size_t cap, uint64_t* overflow_dev);
+                  uint32_t self_shard, void* const* peer_bufs, uint64_t* const* peer_counts, size_t cap, uint64_t* overflow_dev);
+
+/* ---- the same exchange with ONE process driving all GPUs of a box (csrc/sharded.cu) ----
+ * What a Go host links: fa_sharded_* own one owner engine (+ one scratch combiner) per device, their streams, peer
+ * access and the double-buffered receive buffers; fa_sharded_ingest deals every host batch to the GPUs by position
+ * (each slice crosses its own PCIe link), every GPU combines its slice locally, routes the partial flow records to
+ * their owners over NVLink (fa_route_peer) and folds what it receives; the only synchronisation is device-side
+ * (events between the N streams).  cfg: mode ACCOUNTER; max_entries = flows of the whole box; max_batch = records per
+ * GPU and round (0 = 2^22); reserved0 bit 0 = route raw records (no local combiner); device / cuda_stream ignored.
+ * fa_sharded_evict == LookupAndDeleteMap over all owners (disjoint key sets, concatenated). */
+typedef struct fa_sharded fa_sharded;
+int  fa_sharded_create(const fa_config* cfg, const int32_t* devices, uint32_t n_devices, fa_sharded** out);
+void fa_sharded_destroy(fa_sharded* s);
+int  fa_sharded_ingest(fa_sharded* s, const void* flow_records_host, size_t n);
+/* device-resident batches: records_dev[i] (n_per_gpu[i] records) lives on devices[i] */
+int  fa_sharded_ingest_device(fa_sharded* s, const void* const* records_dev, const size_t* n_per_gpu);
+int  fa_sharded_evict(fa_sharded* s, void* out_records_host, size_t cap, size_t* n_out);
+int  fa_sharded_live_flows(fa_sharded* s, size_t* n);
+int  fa_sharded_sync(fa_sharded* s);
+/* sum of the owners' counters; nvlink_records = records that crossed to another GPU; receive_overflow must stay 0 */
+int  fa_sharded_get_stats(fa_sharded* s, fa_stats* sum, uint64_t* nvlink_records, uint64_t* receive_overflow);
+const char* fa_sharded_last_error(void);
 /* fa_ingest for a device-resident batch whose size (<= max_n) is only known on the device; reset_count != 0
  * zeroes *n_dev after the fold has been enqueued.  Requires FA_F_NO_FULL_CUT. */
 int fa_ingest_counted(fa_engine* e, const void* records_dev, uint64_t* n_dev, size_t max_n, int reset_count);

@@ -76,8 +76,17 @@ SIGNATURES = {
                            C.POINTER(C.c_size_t)]),
     "fa_drain_active": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_drain_active_counted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "fa_route_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p),
+    "fa_route_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p),
                                 C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p]),
+    "fa_sharded_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_int32), C.c_uint32, C.POINTER(C.c_void_p)]),
+    "fa_sharded_destroy": (None, [C.c_void_p]),
+    "fa_sharded_ingest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fa_sharded_ingest_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "fa_sharded_evict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "fa_sharded_live_flows": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "fa_sharded_sync": (C.c_int, [C.c_void_p]),
+    "fa_sharded_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fa_sharded_last_error": (C.c_char_p, []),
     "fa_ingest_counted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "fa_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fa_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),

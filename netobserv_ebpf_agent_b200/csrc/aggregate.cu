@@ -30,10 +30,11 @@
 namespace fa {
 
 #ifndef FA_K1_TILE
-#define FA_K1_TILE 256
+#define FA_K1_TILE 128
 #endif
 constexpr int kTile      = FA_K1_TILE;          // records per tile == threads per team
-constexpr int kTeams     = 1024 / kTile;        // teams per CTA (one CTA per SM): independent tile pipelines that fill each other's bubbles
+constexpr int kTeams     = 1024 / kTile;        // teams per CTA (one CTA per SM): independent tile pipelines that fill each other's
+                                                // bubbles (tile wait, team barriers); 8 x 128 measured +5 % over 4 x 256
 constexpr int kCtaThreads = kTile * kTeams;
 constexpr int kRepSlots  = 2 * kTile;
 constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
@@ -84,11 +85,11 @@ __device__ __forceinline__ void issue_tile_load(TeamSmem& s, const uint4* recs, 
     tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
 }
 
-// Reductions of one flow's folded totals onto the accumulators of its line.  floor_ns <= hot.nstart always
-// (immutable start mirror), `seen` are flag bits the accumulators are known to hold already.
+// Reductions of one flow's folded totals onto its hot line.  floor_ns <= hot.nstart always
+// (immutable start mirror), `seen` are flag bits the hot line is known to hold already.
 __device__ __forceinline__ void reduce_to_hot(const Table& t, uint32_t slot, uint64_t bytes, uint32_t packets,
                                               uint64_t ns, uint64_t end, uint32_t flags, uint64_t floor_ns, uint32_t seen) {
-    uint8_t* hot = reinterpret_cast<uint8_t*>(t.ident) + (size_t)slot * kIdentBytes + L_HOT;   // same line as the key
+    uint8_t* hot = reinterpret_cast<uint8_t*>(t.hot) + (size_t)slot * kHotBytes;
     red_add_u64(hot, bytes);
     if (ns > floor_ns) red_max_u64(hot + 8, ns);
     if (end) red_max_u64(hot + 16, end);
@@ -115,26 +116,20 @@ __device__ __forceinline__ void sketch_update(const SketchParams& sk, uint64_t p
 // General probe of one flow per 8-lane group (4 flows per call): claims empty slots, waits for
 // slots being published, walks collisions, marks descriptor mismatches.  Returns the slot
 // (kResSpill when the table is physically full) in every lane of the group.
-// img = lane j's image of the record (common.cuh): lanes 0,1,2,3,6,7 hold what line chunk j is compared with / stored
-// from, lanes 4 and 5 the two chunks of the cold line (read only for flows with TAG_HAS_OBS, written only when non-zero).
 __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch, bool active, uint32_t start_slot,
-                                                  uint4 img, bool cta_dirty, uint64_t ins_ns, int g, int j, uint4 cmask,
+                                                  uint4 rchunk, bool cta_dirty, uint64_t ins_ns, int g, int j, uint4 cmask,
                                                   uint32_t& my_inserts, uint32_t* any_dirty) {
     uint64_t slot = start_slot;
     bool done = !active;
     uint32_t nprobe = 0, result = kResSpill;
     uint64_t reload_slot = ~0ull;
-    const bool cold_lane = j == 4 || j == 5;
-    const bool rec_obs = ((__ballot_sync(0xFFFFFFFFu, cold_lane && ((img.x & cmask.x) | (img.y & cmask.y) | (img.z & cmask.z) |
-                                                                       (img.w & cmask.w)) != 0u) >> (g * 8)) & 0x30u) != 0u;
     for (;;) {
         uint4 line = make_uint4(0, 0, 0, 0);
-        if (!done && !cold_lane) line = ld_cg_u4(&t.ident[slot * 8 + j]);
+        if (!done) line = ld_cg_u4(&t.ident[slot * 8 + j]);
         const uint32_t tag_lo = __shfl_sync(0xFFFFFFFFu, line.z, g * 8 + 2);
         const uint32_t tag_hi = __shfl_sync(0xFFFFFFFFu, line.w, g * 8 + 2);
         const uint64_t tag = u64_of(tag_lo, tag_hi);
-        if (!done && cold_lane && (tag & TAG_HAS_OBS)) line = ld_cg_u4(&t.cold[slot * 2 + (j - 4)]);
-        const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq4_masked(line, img, cmask)) >> (g * 8)) & 0xFFu;
+        const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq4_masked(line, rchunk, cmask)) >> (g * 8)) & 0xFFu;
         const uint32_t state = (uint32_t)(tag & TAG_STATE_MASK);
         unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[slot * 8 + 2]) + 1;
         // Claim either an empty slot, or the base of a flow that so far exists only through feature
@@ -147,15 +142,14 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
             won = atomicCAS(tagp, expect, want) == expect ? (state == 0 ? 1u : 2u) : 0u;
         }
         won = __shfl_sync(0xFFFFFFFFu, won, g * 8 + 2);
-        if (won) {                                              // the accumulators (chunks 4, 5) of a free slot are zero already
-            uint4 v = and4(img, cmask);
+        if (won) {
+            uint4 v = and4(rchunk, cmask);
             if (j == 3) {                                       // start mirror around eth_protocol
                 const uint64_t m48 = ins_ns >> 16;
                 v.x = (uint32_t)m48; v.y |= (uint32_t)(m48 >> 32) << 16;
             }
             if (j == 2) *reinterpret_cast<uint2*>(&t.ident[slot * 8 + 2]) = make_uint2(v.x, v.y);   // key tail only
-            else if (!cold_lane) st_cg_u4(&t.ident[slot * 8 + j], v);
-            else if (rec_obs) st_cg_u4(&t.cold[slot * 2 + (j - 4)], v);
+            else st_cg_u4(&t.ident[slot * 8 + j], v);
             __threadfence();
         }
         __syncwarp();
@@ -163,7 +157,7 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
         if (won) {
             if (j == 2) {
                 const unsigned long long pub = (epoch << TAG_EPOCH_SHIFT) | TAG_HAS_BASE | TAG_PUBLISHED |
-                                               (rec_obs ? TAG_HAS_OBS : 0ull) | (cta_dirty ? TAG_DIRTY : 0ull);
+                                               (cta_dirty ? TAG_DIRTY : 0ull);
                 *reinterpret_cast<volatile unsigned long long*>(tagp) = pub;
                 if (won == 1u) {                               // a base claim does not add a flow
                     my_inserts++;
@@ -181,7 +175,7 @@ __device__ __forceinline__ uint32_t probe_general(const Table& t, uint64_t epoch
                 __threadfence();
             } else if ((eqb & 0x07u) == 0x07u) {
                 hit = true;
-                const bool desc_eq = (eqb & 0xF8u) == 0xF8u;       // bits 4, 5: the cold line (zero == absent) agrees too
+                const bool desc_eq = (eqb & 0xF8u) == 0xF8u;
                 if ((!desc_eq || cta_dirty) && j == 2) {
                     if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
                     *any_dirty = 1;
@@ -215,7 +209,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     const uint32_t tile_stride = gridDim.x * kTeams;
     const uint32_t tile0 = blockIdx.x * kTeams + team;
     const bool use_cache = (opt & 2u) == 0;
-    const bool full_line = (opt & 4u) != 0;
 
     if (threadIdx.x == 0) { cs.n_insert = 0; cs.n_spill = 0; cs.any_dirty = 0; }
     if (threadIdx.x < kHotEntries) cs.hot[threadIdx.x].state = 0;
@@ -233,8 +226,8 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
 
     const int g = lane >> 3;                  // flow group inside the warp (4 groups of 8 lanes)
     const int j = lane & 7;                   // 16-byte chunk of the identity line handled by this lane
-    const bool cold_lane = j == 4 || j == 5;          // these lanes hold the record's cold image, not a line chunk
-    const int rc = rec_chunk_of_lane(j);
+    const uint4 cmask = chunk_mask(j);
+    const int rc = rec_chunk_of_line_chunk(j);
     const uint32_t tmask = (uint32_t)t.mask;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t my_inserts = 0, my_spills = 0;
@@ -250,7 +243,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         const uint32_t cnt = min((uint32_t)kTile, n - first);
         mbar_wait(&s.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
-        if ((opt & 32u) && tid == 0) {                             // have L2 fetch the team's next tile while this one is worked on
+        if (!(opt & 32u) && tid == 0) {                            // have L2 fetch the team's next tile while this one is worked on
             const uint32_t nt = tile_idx + tile_stride;
             if (nt < n_tiles) tma_prefetch_l2(recs + (size_t)nt * kTile * kRecChunks, min((uint32_t)kTile, n - nt * kTile) * kRecBytes);
         }
@@ -265,20 +258,14 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint64_t h = slot_hash(key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
                                                         u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)));
                 s.hs[tid] = (uint32_t)h;
-                // the staged copy's chunk 8 becomes the image of line chunk 7: its padding word takes word x of chunk 6
-                // (direction, errno, dscp, nb_observed_intf), so every probe lane compares ONE chunk of the tile
-                reinterpret_cast<uint32_t*>(s.tile + tid * kRecChunks + 8)[3] = reinterpret_cast<const uint32_t*>(R + 6)[0];
                 // ---- hot-flow cache: an exact 114-byte match folds the record on-chip, no table traffic
                 HotEntry& ce = cs.hot[((uint32_t)h >> 26) & (kHotEntries - 1)];
                 if (use_cache && *reinterpret_cast<volatile uint32_t*>(&ce.state) == 2u && ce.hash == (uint32_t)h) {
                     const uint4 r3 = R[3], r4 = R[4];
-                    // cached flows have no cold line (see the install): the record must not carry one either
-                    uint32_t dd = diff4_masked(ce.line[0], r0, chunk_mask(0)) | diff4_masked(ce.line[1], r1, chunk_mask(1)) |
-                                  diff4_masked(ce.line[2], r2, chunk_mask(2)) | diff4_masked(ce.line[3], r4, chunk_mask(3));
-                    dd |= diff4_masked(ce.line[6], R[5], chunk_mask(6));
-                    dd |= diff4_masked(ce.line[7], R[8], chunk_mask(7));         // the staged chunk 8 is line chunk 7's image (above)
-                    dd |= rec_cold_nz(R[6], R[7]);
-                    bool same = dd == 0u;
+                    bool same = eq4_masked(ce.line[0], r0, chunk_mask(0)) && eq4_masked(ce.line[1], r1, chunk_mask(1)) &&
+                                eq4_masked(ce.line[2], r2, chunk_mask(2)) && eq4_masked(ce.line[3], r4, chunk_mask(3));
+#pragma unroll
+                    for (int c = 5; c < 9; c++) same = same && eq4_masked(ce.line[c - 1], R[c], chunk_mask(c - 1));
                     const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
                     const uint64_t v_ns = 0ull - v_start;
                     same = same && (v_start == 0 || (uint32_t)(v_ns >> 32) == ce.ns_hi) &&
@@ -331,9 +318,9 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                                 if (v_end) atomicMax(&A[5], (uint32_t)v_end);
                                 atomicAdd(&A[6], 1u);                // duplicates seen: cache candidacy
                                 // exact descriptor compare against the representative (74 bytes, padding masked)
-                                bool same = eq4_masked(O[4], r4, rec_desc_mask(4));
+                                bool same = eq4_masked(O[4], r4, chunk_mask(3));
 #pragma unroll
-                                for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], rec_desc_mask(c));
+                                for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
                                 if (!same) s.tdirty[old] = 1;
                             }
                             break;
@@ -381,24 +368,19 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
 #pragma unroll
-                for (int r = 0; r < kInflight; r++) {                      // three of the line's four sectors
+                for (int r = 0; r < kInflight; r++) {
                     line[r] = make_uint4(0, 0, 0, 0);
-                    if (((pend >> r) & 1u) && !cold_lane) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
-                    // the accumulators' sector: asked into L2 together with the rest of the line (one DRAM burst), so
-                    // that the reductions which follow find it there (FA_K1_OPT bit 2)
-                    if (full_line && ((pend >> r) & 1u) && j == 4) prefetch_l2(&t.ident[(size_t)slot[r] * 8 + 4]);
+                    if ((pend >> r) & 1u) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
                 }
 #pragma unroll
                 for (int r = 0; r < kInflight; r++) {
                     const bool act = (pend >> r) & 1u;
-                    // lanes 4, 5 compare the record's cold image with zero: a flow with a cold line (TAG_HAS_OBS) is not
-                    // "settled" here and goes to the general loop, which reads it
                     const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
-                    bool eq = eq4_masked(line[r], rchunk, chunk_mask(j));
+                    bool eq = eq4_masked(line[r], rchunk, cmask);
                     const uint64_t tag = u64_of(line[r].z, line[r].w);  // meaningful in lane j == 2 only
                     bool settled = false;
                     if (j == 2) {
-                        settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE | TAG_HAS_OBS)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                        settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
                                   (tag >> TAG_EPOCH_SHIFT) != epoch;
                         eq = eq && settled;
                     }
@@ -445,7 +427,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
                 const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
                 const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0,
-                                                   dup_ns > own_ns ? dup_ns : own_ns, g, j, chunk_mask(j), my_inserts, &cs.any_dirty);
+                                                   dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &cs.any_dirty);
                 if (act && j == 0) s.res[ri] = got;
                 if (act && j == 2) s.fseen[ri] = 0;                 // unknown: issue every reduction
                 if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
@@ -486,8 +468,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         ce.hash = hh; ce.slot = my_slot;
                         ce.ns_hi = (uint32_t)(v_ns >> 32); ce.end_hi = (uint32_t)(v_end >> 32);
                         __threadfence_block();
-                        // only flows without a cold line are cached (the cache compares the 128-byte line alone)
-                        *reinterpret_cast<volatile uint32_t*>(&ce.state) = (ce.line[2].z & (uint32_t)TAG_HAS_OBS) ? 0u : 2u;
+                        *reinterpret_cast<volatile uint32_t*>(&ce.state) = 2u;
                         if (kProf) c_install++;
                     }
                 }
@@ -655,7 +636,7 @@ __device__ __forceinline__ uint64_t peers_max_u64(uint32_t peers, uint64_t v) {
 
 // front(): hash, private-cache fold, gather issue for one slice
 __device__ __forceinline__ SCarry stream_front(SWarp& s, const uint4* Rbuf, uint4* Lbuf, uint32_t cnt, const Table& t,
-                                               uint32_t tmask, int lane, uint32_t lt_mask, bool use_cache, bool full_line) {
+                                               uint32_t tmask, int lane, uint32_t lt_mask, bool use_cache) {
     const bool valid = (uint32_t)lane < cnt;
     const uint4* R = Rbuf + lane * kRecChunks;
     uint32_t h32 = 0, ci = 0;
@@ -667,11 +648,10 @@ __device__ __forceinline__ SCarry stream_front(SWarp& s, const uint4* Rbuf, uint
         ci = h32 >> 27;
         const SCacheEntry& ce = s.cache[ci];
         if (use_cache && ce.state != 0u && ce.hash == h32) {
-            const uint4 r6 = R[6];                                  // cached flows have no cold line: neither may the record
-            const uint32_t d = diff4_masked(ce.line[0], r0, chunk_mask(0)) | diff4_masked(ce.line[1], r1, chunk_mask(1)) |
-                               diff4_masked(ce.line[2], r2, chunk_mask(2)) | diff4_masked(ce.line[3], R[4], chunk_mask(3)) |
-                               diff4_masked(ce.line[6], R[5], chunk_mask(6)) |
-                               diff4_masked(ce.line[7], rec_image7(r6, R[8]), chunk_mask(7)) | rec_cold_nz(r6, R[7]);
+            uint32_t d = diff4_masked(ce.line[0], r0, chunk_mask(0)) | diff4_masked(ce.line[1], r1, chunk_mask(1)) |
+                         diff4_masked(ce.line[2], r2, chunk_mask(2));
+#pragma unroll
+            for (int c = 3; c < 8; c++) d |= diff4_masked(ce.line[c], R[c + 1], chunk_mask(c));
             hit = d == 0u;
         }
     }
@@ -712,27 +692,24 @@ __device__ __forceinline__ SCarry stream_front(SWarp& s, const uint4* Rbuf, uint
         const uint32_t k = base + g;
         const uint32_t src = k < npr ? (uint32_t)s.list[k] : 0u;
         const uint32_t slot = __shfl_sync(0xFFFFFFFFu, home, (int)src);
-        if (k < npr && ((j != 4 && j != 5) || full_line))              // three of the four sectors (all four: FA_K1_OPT bit 2)
-            cp_async16(&Lbuf[src * 8 + (j ^ (src & 7))], &t.ident[(size_t)slot * 8 + j]);
+        if (k < npr) cp_async16(&Lbuf[src * 8 + (j ^ (src & 7))], &t.ident[(size_t)slot * 8 + j]);
     }
     cp_async_commit();
     FA_EMUL_COUNT(0, lane == 0 ? npr : 0);
     return SCarry{h32, home, probe};
 }
 
-// One thread checks a whole line against its record.  Returns 0 = this flow, settled; 1 = another settled flow lives
-// here; 2 = anything else (empty, being published, born in this launch, feature-only entry, flow with a cold line).
-__device__ __forceinline__ int line_verdict(const uint4* R, uint4 l0, uint4 l1, uint4 l2, uint4 l3, uint4 l6, uint4 l7,
+// One thread checks a whole identity line against its record.  Returns 0 = this flow, settled; 1 = another settled
+// flow lives here; 2 = anything else (empty, being published, born in this launch, feature-only entry).
+__device__ __forceinline__ int line_verdict(const uint4* R, uint4 l0, uint4 l1, uint4 l2, uint4 l3, uint4 l4, uint4 l5, uint4 l6, uint4 l7,
                                             uint64_t epoch, uint32_t& ddesc) {
     const uint64_t tag = u64_of(l2.z, l2.w);
-    const bool settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE | TAG_HAS_OBS)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
-                         (tag >> TAG_EPOCH_SHIFT) != epoch;
+    const bool settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) && (tag >> TAG_EPOCH_SHIFT) != epoch;
     if (!settled) return 2;
     const uint32_t dkey = diff4_masked(l0, R[0], chunk_mask(0)) | diff4_masked(l1, R[1], chunk_mask(1)) | diff4_masked(l2, R[2], chunk_mask(2));
     if (dkey) return 1;
-    const uint4 r6 = R[6];
-    ddesc = diff4_masked(l3, R[4], chunk_mask(3)) | diff4_masked(l6, R[5], chunk_mask(6)) |
-            diff4_masked(l7, rec_image7(r6, R[8]), chunk_mask(7)) | rec_cold_nz(r6, R[7]);
+    ddesc = diff4_masked(l3, R[4], chunk_mask(3)) | diff4_masked(l4, R[5], chunk_mask(4)) | diff4_masked(l5, R[6], chunk_mask(5)) |
+            diff4_masked(l6, R[7], chunk_mask(6)) | diff4_masked(l7, R[8], chunk_mask(7));
     return 0;
 }
 
@@ -751,13 +728,14 @@ __device__ __forceinline__ void stream_back(SWarp& s, const uint4* Rbuf, const u
         const uint4* L = Lbuf + lane * 8;
         const int sw = lane & 7;
         uint4 l2 = L[2 ^ sw], l3 = L[3 ^ sw];
-        int v = line_verdict(R, L[0 ^ sw], L[1 ^ sw], l2, l3, L[6 ^ sw], L[7 ^ sw], epoch, ddesc);
+        int v = line_verdict(R, L[0 ^ sw], L[1 ^ sw], l2, l3, L[4 ^ sw], L[5 ^ sw], L[6 ^ sw], L[7 ^ sw], epoch, ddesc);
         at_home = v == 0;
         if (v == 1) {                                                  // another flow at home: look one slot further, now
             slot = (slot + 1) & tmask;
             const uint4* G = &t.ident[(size_t)slot * 8];
             l2 = ld_cg_u4(G + 2); l3 = ld_cg_u4(G + 3);
-            v = line_verdict(R, ld_cg_u4(G), ld_cg_u4(G + 1), l2, l3, ld_cg_u4(G + 6), ld_cg_u4(G + 7), epoch, ddesc);
+            v = line_verdict(R, ld_cg_u4(G), ld_cg_u4(G + 1), l2, l3, ld_cg_u4(G + 4), ld_cg_u4(G + 5), ld_cg_u4(G + 6), ld_cg_u4(G + 7),
+                             epoch, ddesc);
         }
         if (v == 0) {
             const uint64_t tag = u64_of(l2.z, l2.w);
@@ -780,12 +758,12 @@ __device__ __forceinline__ void stream_back(SWarp& s, const uint4* Rbuf, const u
         FA_EMUL_COUNT(1, lane == 0 ? nslow : 0);
         const int g = lane >> 3, j = lane & 7;
         const uint4 cmask = chunk_mask(j);
+        const int rc = rec_chunk_of_line_chunk(j);
         for (uint32_t base = 0; base < nslow; base += 4) {
             const uint32_t k = base + g;
             const bool act = k < nslow;
             const uint32_t ri = act ? (uint32_t)s.slow[k] : 0u;
-            uint4 rchunk = Rbuf[ri * kRecChunks + rec_chunk_of_lane(j)];
-            if (j == 7) rchunk.w = Rbuf[ri * kRecChunks + 6].x;
+            const uint4 rchunk = Rbuf[ri * kRecChunks + rc];
             const uint4 c2 = Rbuf[ri * kRecChunks + 2];
             const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
             const uint32_t start_slot = __shfl_sync(0xFFFFFFFFu, c.home, (int)ri);
@@ -828,7 +806,7 @@ __device__ __forceinline__ void stream_back(SWarp& s, const uint4* Rbuf, const u
         if (go) {
             if (lane == src && e.state != 0u) scache_flush<kSketch>(t, sk, e);
             __syncwarp();
-            if (lane < 8 && lane != 4 && lane != 5) e.line[lane] = Lbuf[src * 8 + (lane ^ (src & 7))];
+            if (lane < 8) e.line[lane] = Lbuf[src * 8 + (lane ^ (src & 7))];
             if (lane == src) {
                 e.bytes = 0; e.ns = 0; e.end = 0; e.packets = 0; e.flags = 0;
                 e.hash = c.h32; e.slot = slot; e.hits = 0; e.state = 1u;
@@ -867,8 +845,7 @@ aggregate_stream_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uin
             if (n_it > 1u) issue_slice_load(s.rec[1], &s.full_bar[1], recs, n, sub0 + stride);
         }
         mbar_wait(&s.full_bar[0], 0u);
-        const bool full_line = (opt & 4u) != 0;
-        SCarry cur = stream_front(s, s.rec[0], s.line[0], min((uint32_t)kSSub, n - sub0 * kSSub), t, tmask, lane, lt_mask, use_cache, full_line);
+        SCarry cur = stream_front(s, s.rec[0], s.line[0], min((uint32_t)kSSub, n - sub0 * kSSub), t, tmask, lane, lt_mask, use_cache);
         uint32_t b_cur = 0, b_nxt = 1, b_ld = 2;                     // record buffers of slices it, it+1, it+2
         for (uint32_t it = 0; it < n_it; ++it) {
             const uint32_t sub = sub0 + it * stride;
@@ -880,7 +857,7 @@ aggregate_stream_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uin
             if (it + 1u < n_it) {
                 mbar_wait(&s.full_bar[b_nxt], ((it + 1u) / 3u) & 1u);
                 nxt = stream_front(s, s.rec[b_nxt], s.line[(it + 1u) & 1u], min((uint32_t)kSSub, n - (sub + stride) * kSSub), t, tmask,
-                                   lane, lt_mask, use_cache, full_line);
+                                   lane, lt_mask, use_cache);
             } else {
                 cp_async_commit();
             }
@@ -972,16 +949,12 @@ __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint
         unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&L[2]) + 1;
         const unsigned long long tag = *tagp;
         const bool is_new = (tag >> TAG_EPOCH_SHIFT) == epoch;
-        // current descriptor state as record chunks 4..8 (d3 .. d7), rebuilt from line chunks 3, 6, 7 and the cold line
-        const uint4 l3 = L[3], l6 = L[6], l7 = L[7];
-        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
-        if (tag & TAG_HAS_OBS) { c0 = t.cold[slot * 2]; c1 = t.cold[slot * 2 + 1]; }
-        const uint32_t mir_lo = l3.x, mir_hi = l3.y & 0xFFFF0000u;      // immutable start mirror stays
-        uint4 d3 = make_uint4(0u, l3.y & 0xFFFFu, l3.z, l3.w), d4 = l6, d5 = make_uint4(l7.w, c0.y, c0.z, c0.w), d6 = c1,
-              d7 = make_uint4(l7.x, l7.y, l7.z, 0u);
+        // current descriptor state: line chunks 3..7 <-> record chunks 4..8
+        uint4 d3 = L[3], d4 = L[4], d5 = L[5], d6 = L[6], d7 = L[7];
+        const uint32_t mir_lo = d3.x, mir_hi = d3.y & 0xFFFF0000u;    // immutable start mirror stays
         if (is_new) {                                      // state = the flow's first record, whole (account.go:95)
             const uint4* F = recs + (size_t)(~sc.nfirst) * kRecChunks;
-            d3 = and4(F[4], rec_desc_mask(4)); d4 = F[5]; d5 = and4(F[6], rec_desc_mask(6)); d6 = F[7]; d7 = and4(F[8], rec_desc_mask(8));
+            d3 = and4(F[4], chunk_mask(3)); d4 = F[5]; d5 = and4(F[6], chunk_mask(5)); d6 = F[7]; d7 = and4(F[8], chunk_mask(7));
         }
         // eth_protocol / dscp / sampling: last non-zero in stream order (flow_content.go:45-47,54-59)
         if (sc.eth)  { const uint4 x = recs[(size_t)(sc.eth - 1) * kRecChunks + 4]; d3.y = x.y & 0xFFFFu; }
@@ -996,16 +969,8 @@ __global__ void fixup_apply_kernel(const uint4* __restrict__ recs, Table t, uint
             const uint4 x4 = recs[(size_t)(~sc.ndmac) * kRecChunks + 4], x5 = recs[(size_t)(~sc.ndmac) * kRecChunks + 5];
             d3.w = (d3.w & 0xFFFFu) | (x4.w & 0xFFFF0000u); d4.x = x5.x;
         }
-        L[3] = make_uint4(mir_lo, (d3.y & 0xFFFFu) | mir_hi, d3.z, d3.w);
-        L[6] = d4;
-        L[7] = make_uint4(d7.x, d7.y, d7.z, d5.x);
-        const uint32_t obs = rec_cold_nz(d5, d6);
-        if (obs || (tag & TAG_HAS_OBS)) {                  // the cold line of a flow without TAG_HAS_OBS is zero and stays untouched
-            t.cold[slot * 2] = make_uint4(0u, d5.y, d5.z & 0xFFFFu, d5.w);
-            t.cold[slot * 2 + 1] = d6;
-        }
-        if (obs && !(tag & TAG_HAS_OBS)) atomicOr(tagp, (unsigned long long)TAG_HAS_OBS);
-        if (!obs && (tag & TAG_HAS_OBS)) atomicAnd(tagp, ~(unsigned long long)TAG_HAS_OBS);
+        d3.x = mir_lo; d3.y = (d3.y & 0xFFFFu) | mir_hi;
+        L[3] = d3; L[4] = d4; L[5] = d5; L[6] = d6; L[7] = d7;
         atomicAnd(tagp, ~(unsigned long long)TAG_DIRTY);
         fixed++;
     }

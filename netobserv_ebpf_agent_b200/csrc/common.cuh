@@ -25,46 +25,37 @@ constexpr int kDropRecBytes = 72;   // flow_id + pkt_drop_metrics
 constexpr int R_START = 40, R_END = 48, R_BYTES = 56, R_PACKETS = 64, R_ETH = 68, R_FLAGS = 70, R_DESC = 72;
 
 // ------------------------------------------------------------------ table layout
-// One slot = one 128-byte line (everything the per-record path touches) + one 32-byte cold line (observed interfaces,
-// all-zero for almost every flow and then never read or written).
+// One slot = one 128-byte "identity line" + one 32-byte "hot line".
 //
-// line (8 x 16-byte chunks; four 32-byte sectors):
-//   chunk 0,1  [  0.. 32) key[0..32)                                                       == record chunks 0, 1
-//   chunk 2    [ 32.. 40) key[32..40) (byte 39 forced to 0)
-//              [ 40.. 48) tag u64: 0 = EMPTY, else (epoch << 24) | (tcp flags already OR-ed into hot.flags << 8) | bits
-//   chunk 3    [ 48.. 52) start mirror, low 32 bits   } m48 = (0 - start_at_insert) >> 16: an immutable lower bound of
-//              [ 52.. 54) eth_protocol                } hot.nstart, so records that cannot lower the start skip that RED
-//              [ 54.. 56) start mirror, high 16 bits  }
-//              [ 56.. 64) src_mac[6] dst_mac[0..2)                                          == record chunk 4, words z, w
-//   chunk 4    [ 64.. 72) hot.bytes   (add)            } the accumulators = the line's third SECTOR: only ever touched
-//              [ 72.. 80) hot.nstart = 0 - start (max -> min over non-zero starts, 0 if none)   } by fire-and-forget
-//   chunk 5    [ 80.. 88) hot.end     (max)            } reductions, all-zero == identity.  They live in the line a
-//              [ 88.. 92) hot.packets (add, wraps mod 2^32 like the Go u32)   } probe has just pulled into L2; the probe
-//              [ 92.. 96) hot.flags   (or; low 16 bits)                        } itself reads the other three sectors
-//   chunk 6    [ 96..112) dst_mac[2..6) if_index lock sampling                              == record chunk 5
-//   chunk 7    [112..124) observed_intf[5] | ssl_version tls_cipher_suite | tls_key_share tls_types misc_flags
-//                                                                                           == record chunk 8, words x, y, z
-//              [124..128) direction errno dscp nb_observed_intf                             == record chunk 6, word x
-// cold line (2 chunks): record chunk 6 without its word x (observed_direction[6], observed_intf[0]; padding zeroed)
-//   and record chunk 7 (observed_intf[1..5)).  TAG_HAS_OBS says whether it is non-zero; a flow without it never
-//   touches its cold line.  Every chunk of the line and of the cold line is ONE record chunk under a mask (chunk 7
-//   borrows one word), so an 8-lane probe group compares with one shared-memory load per lane and no shuffling.
+// identity line (read-mostly; written once when the flow is created):
+//   [  0.. 40) key (byte 39 forced to 0)
+//   [ 40.. 48) tag   u64: 0 = EMPTY, else (epoch << 24) | (tcp flags already OR-ed into the hot line << 8) | bits
+//   [ 48.. 52) start mirror, low 32 bits   } m48 = (0 - start_at_insert) >> 16: an immutable lower bound of
+//   [ 52.. 54) eth_protocol                } hot.nstart, so records that cannot lower the start skip that RED
+//   [ 54.. 56) start mirror, high 16 bits  }
+//   [ 56..128) descriptor = record bytes [72..144) with padding zeroed
+// so that line chunk j (16 B) lines up with record chunk {0,1,2,4,5,6,7,8}[j].
+//
+// hot line (updated with fire-and-forget reductions; all-zero == identity):
+//   [ 0.. 8) bytes   (add)
+//   [ 8..16) nstart  = 0 - start_mono_time_ts (max)  -> min over non-zero starts, 0 if none
+//   [16..24) end     (max)
+//   [24..28) packets (add, wraps mod 2^32 like the Go u32)
+//   [28..32) flags   (or; low 16 bits)
 constexpr int kIdentBytes = 128;
-constexpr int kColdBytes  = 32;
-constexpr int L_HOT = 64;                    // byte offset of the accumulators inside the line
+constexpr int kHotBytes   = 32;
 
 constexpr uint64_t TAG_STATE_MASK = 0x3ull;
 constexpr uint64_t TAG_CLAIMED    = 0x1ull;
 constexpr uint64_t TAG_PUBLISHED  = 0x2ull;
 constexpr uint64_t TAG_DIRTY      = 0x4ull;   // order-dependent fields must be re-folded in stream order
 constexpr uint64_t TAG_HAS_BASE   = 0x8ull;   // at least one base flow record was folded (vs feature-only entry)
-constexpr uint64_t TAG_HAS_OBS    = 0x10ull;  // the cold line (observed interfaces) is non-zero
 constexpr int      TAG_FLAGS_SHIFT = 8;    // 16 bits: flag bits known to be set in hot.flags already
 constexpr int      TAG_EPOCH_SHIFT = 24;   // 40-bit launch counter
 
 struct Table {
-    uint4*   ident;      // slots x 8 uint4: key, tag, accumulators, descriptor
-    uint4*   cold;       // slots x 2 uint4: observed interfaces (KERNEL_MAP mode: nullptr, it keeps its own metrics lines)
+    uint4*   ident;      // slots x 8 uint4
+    uint4*   hot;        // slots x 2 uint4
     uint4*   feat_add;   // slots x 5 uint4 (80 B) or nullptr: additional_metrics fold state
     uint4*   feat_dns;   // slots x 8 uint4 (128 B) or nullptr: dns_metrics fold state
     uint4*   feat_drop;  // slots x 6 uint4 (96 B) or nullptr: pkt_drop_metrics fold state
@@ -109,36 +100,22 @@ FA_HD uint32_t cms_index(uint64_t a, uint64_t b, uint32_t row, uint32_t log2w) {
     return (uint32_t)(((a + (uint64_t)row * b) * 0x9E3779B97F4A7C15ull) >> (64 - log2w));
 }
 
-// ------------------------------------------------------------------ chunk masks and the record's line image
-// rec_desc_mask(c): which bits of RECORD chunk c (4..8) take part in a descriptor compare between two records.
-// Padding bytes (key byte 39, metrics bytes 66-67 and 100-103) are excluded: binary.Read leaves them zero
-// (reference pkg/model/record.go:227-231).
-FA_HD uint4 rec_desc_mask(int c) {
-    switch (c) {
-        case 4:  return make_uint4(0u, 0x0000FFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);      // packets, eth | flags, macs
-        case 6:  return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0x0000FFFFu, 0xFFFFFFFFu);
-        case 8:  return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
-        default: return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-    }
-}
-// Lane j of an 8-lane probe group holds the image of record chunk rec_chunk_of_lane(j): for j = 0,1,2,3,6,7 it is
-// compared with / stored to line chunk j, for j = 4,5 to the two chunks of the cold line (line chunks 4, 5 are the
-// accumulators and have no image).  Lane 7 additionally takes word x of record chunk 6 as its word w.
-FA_HD int rec_chunk_of_lane(int j) {
-    switch (j) { case 3: return 4; case 4: return 6; case 5: return 7; case 6: return 5; case 7: return 8; default: return j; }
-}
-// chunk_mask(j): which bits of lane j's image are identity.
+// ------------------------------------------------------------------ chunk masks
+// Which bits of line chunk j (as 4 LE u32 words) take part in the identity compare /
+// are stored on insert.  j: 0,1 key | 2 key tail (+tag, excluded) | 3 eth + desc[0..8) |
+// 4..7 desc[8..72).  Padding bytes (key byte 39, metrics bytes 66-67 and 100-103) are
+// excluded: binary.Read leaves them zero (reference pkg/model/record.go:227-231).
 FA_HD uint4 chunk_mask(int j) {
     switch (j) {
-        case 2:  return make_uint4(0xFFFFFFFFu, 0x00FFFFFFu, 0u, 0u);                // key tail; tag excluded
-        case 3:  return make_uint4(0u, 0x0000FFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);        // eth + macs; mirror excluded
-        case 4:  return make_uint4(0u, 0xFFFFFFFFu, 0x0000FFFFu, 0xFFFFFFFFu);        // cold 0: record chunk 6 minus word x, padding
+        case 2:  return make_uint4(0xFFFFFFFFu, 0x00FFFFFFu, 0u, 0u);
+        case 3:  return make_uint4(0u, 0x0000FFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        case 5:  return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0x0000FFFFu, 0xFFFFFFFFu);
+        case 7:  return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
         default: return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     }
 }
-// image of lane 7 (and of the thread-per-record compares): record chunk 8's x, y, z and record chunk 6's x
-FA_HD uint4 rec_image7(uint4 r6, uint4 r8) { return make_uint4(r8.x, r8.y, r8.z, r6.x); }
-FA_HD uint32_t rec_cold_nz(uint4 r6, uint4 r7) { return r6.y | (r6.z & 0x0000FFFFu) | r6.w | r7.x | r7.y | r7.z | r7.w; }
+// record chunk index that line chunk j is compared with
+FA_HD int rec_chunk_of_line_chunk(int j) { return j < 3 ? j : j + 1; }
 
 FA_HD uint4 and4(uint4 a, uint4 m) { return make_uint4(a.x & m.x, a.y & m.y, a.z & m.z, a.w & m.w); }
 FA_HD bool  eq4_masked(uint4 a, uint4 b, uint4 m) {

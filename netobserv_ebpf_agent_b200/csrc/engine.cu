@@ -445,8 +445,8 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     CU(cudaMalloc(&e->table.ident, slots * fa::kIdentBytes));
     CU(cudaMemsetAsync(e->table.ident, 0, slots * fa::kIdentBytes, e->stream));
     if (!kmap) {
-        CU(cudaMalloc(&e->table.cold, slots * fa::kColdBytes));
-        CU(cudaMemsetAsync(e->table.cold, 0, slots * fa::kColdBytes, e->stream));
+        CU(cudaMalloc(&e->table.hot, slots * fa::kHotBytes));
+        CU(cudaMemsetAsync(e->table.hot, 0, slots * fa::kHotBytes, e->stream));
     } else {
         if (slots > (1ull << 30)) return fail(FA_E_INVAL, "fa_create: KERNEL_MAP mode supports at most 2^30 slots");
         CU(cudaMalloc(&e->km_met, slots * fa::kMetLineBytes));
@@ -557,7 +557,7 @@ void fa_destroy(fa_engine* e) {
         cudaFree(e->d_prof);
     }
     if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
-    cudaFree(e->table.ident); cudaFree(e->table.cold); cudaFree(e->table.occ); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns); cudaFree(e->table.feat_drop);
+    cudaFree(e->table.ident); cudaFree(e->table.hot); cudaFree(e->table.occ); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns); cudaFree(e->table.feat_drop);
     cudaFree(e->d_ctr); if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_live_ring) cudaFreeHost(e->h_live_ring);
     for (int i = 0; i < fa_engine::kLiveRing; i++) if (e->ev_live[i]) cudaEventDestroy(e->ev_live[i]);
@@ -831,7 +831,7 @@ int fa_drain_active_counted(fa_engine* e, void* out_records_dev, size_t cap, uin
     return FA_OK;
 }
 
-int fa_route_peer(fa_engine* e, const void* recs, const uint64_t* n_dev, size_t max_n, uint32_t n_shards,
+int fa_route_peer(fa_engine* e, const void* recs, const uint64_t* n_dev, size_t max_n, uint32_t n_shards, uint32_t self_shard,
                   void* const* peer_bufs, uint64_t* const* peer_counts, size_t cap, uint64_t* overflow_dev) {
     if (!e || !recs || !peer_bufs || !peer_counts || !overflow_dev) return fail(FA_E_INVAL, "fa_route_peer: null argument");
     if (n_shards == 0 || n_shards > 16) return fail(FA_E_INVAL, "fa_route_peer: n_shards must be 1..16");
@@ -844,7 +844,7 @@ int fa_route_peer(fa_engine* e, const void* recs, const uint64_t* n_dev, size_t 
         pt.count[i] = reinterpret_cast<unsigned long long*>(peer_counts[i]);
     }
     e->st.kernel_launches += fa::launch_route_peer(static_cast<const uint4*>(recs), reinterpret_cast<const unsigned long long*>(n_dev),
-                                                   (uint32_t)max_n, n_shards, pt, cap, reinterpret_cast<unsigned long long*>(overflow_dev), e->stream);
+                                                   (uint32_t)max_n, n_shards, self_shard, pt, cap, reinterpret_cast<unsigned long long*>(overflow_dev), e->stream);
     CU(cudaGetLastError());
     return FA_OK;
 }

@@ -4,16 +4,16 @@
 // (pkg/flow/account.go:67-68,86-87,102-124).
 //
 // An occupancy bitmap finds the live slots; 8 lanes per live flow: one coalesced 128-byte
-// line load (key, tag, accumulators, descriptor), the 32-byte cold line only for the few flows
-// that have one, shuffles to reassemble the 144-byte record (9 x 16-byte stores), one
-// output-cursor atomic per 32 slots, and in-place clearing so the table comes out empty.
+// identity-line load, the 32-byte hot line by two of the lanes, shuffles to reassemble the
+// 144-byte record (9 x 16-byte stores), one output-cursor atomic per 32 slots, and in-place
+// clearing so the table comes out empty.
 #include "kernels.cuh"
 
 namespace fa {
 
 // kDrain = false: lookup-and-delete (the flow is removed).  kDrain = true: "lookup-and-reset": flows that
-// received records since the last drain are emitted and their accumulators are zeroed, but they stay in the table
-// (key, tag, descriptor, bitmap untouched) so the next batch hits them on the fast path.
+// received records since the last drain are emitted and their hot line is zeroed, but they stay in the table
+// (identity line, tag, bitmap untouched) so the next batch hits them on the fast path.
 template <bool kDrain>
 __global__ void __launch_bounds__(256)
 evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_out, unsigned long long cap, Counters* ctr) {
@@ -23,7 +23,7 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
     const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     // The occupancy bitmap (1 bit per slot, set when a flow is created) lets a warp skip 1024 empty slots with one
-    // coalesced load: eviction costs ~ (128 + 144) bytes per LIVE flow, not per slot.  One output-cursor
+    // coalesced load: eviction costs ~ (128 + 32 + 144) bytes per LIVE flow, not per slot.  One output-cursor
     // atomic per warp iteration (1024 slots).
     for (uint64_t w0 = warp_global * 32; w0 < n_words; w0 += n_warps * 32) {
         const uint64_t wi = w0 + lane;                  // lane l owns bitmap word w0 + l
@@ -33,12 +33,12 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
         if (nonempty == 0u) continue;
         if (kDrain) {
             // which of the live flows received records since the last drain?  Every lane walks the set bits of its
-            // own bitmap word (32 independent chains of 32-byte accumulator reads in flight per warp).
+            // own bitmap word (32 independent chains of 32-byte hot-line reads in flight per warp).
             uint32_t rest = mybits, myact = 0;
             while (rest) {
                 const int b = __ffs(rest) - 1; rest &= rest - 1;
                 const uint64_t slot = wi * 32 + b;
-                const uint4 h0 = ld_cg_u4(&t.ident[slot * 8 + 4]), h1 = ld_cg_u4(&t.ident[slot * 8 + 5]);
+                const uint4 h0 = ld_cg_u4(&t.hot[slot * 2]), h1 = ld_cg_u4(&t.hot[slot * 2 + 1]);
                 if ((h0.x | h0.y | h0.z | h0.w | h1.x | h1.y | h1.z | h1.w) != 0u) myact |= 1u << b;
             }
             mybits = myact;
@@ -73,17 +73,14 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
                 const uint32_t pos = live ? __fns(sbits, 0, within + 1) : 0u;
                 const uint64_t slot = (w0 + src) * 32 + pos;
                 const unsigned long long idx = base + f;
-                uint4 line = make_uint4(0, 0, 0, 0), cold = make_uint4(0, 0, 0, 0);
+                uint4 line = make_uint4(0, 0, 0, 0), hot = make_uint4(0, 0, 0, 0);
                 if (live) line = ld_cg_u4(&t.ident[slot * 8 + j]);
-                const int g8 = g * 8;
-                const bool has_obs = (__shfl_sync(0xFFFFFFFFu, line.z, g8 + 2) & (uint32_t)TAG_HAS_OBS) != 0u;
-                // lanes 6 and 7 fetch the two cold chunks (observed interfaces) of the few flows that have them
-                if (live && has_obs && j >= 6) cold = ld_cg_u4(&t.cold[slot * 2 + (j - 6)]);
-                // line chunk 3 = (mirror | eth, macs), 4 = (bytes, nstart), 5 = (end, packets, flags), 7 = (obs_intf[5], ssl.., tls.., dir..)
-                const uint32_t ns_lo = __shfl_sync(0xFFFFFFFFu, line.z, g8 + 4), ns_hi = __shfl_sync(0xFFFFFFFFu, line.w, g8 + 4);
-                const uint32_t b_lo = __shfl_sync(0xFFFFFFFFu, line.x, g8 + 4), b_hi = __shfl_sync(0xFFFFFFFFu, line.y, g8 + 4);
-                const uint32_t pk = __shfl_sync(0xFFFFFFFFu, line.z, g8 + 5), fl = __shfl_sync(0xFFFFFFFFu, line.w, g8 + 5);
-                const uint32_t l7w = __shfl_sync(0xFFFFFFFFu, line.w, g8 + 7);
+                if (live && j < 2) hot = ld_cg_u4(&t.hot[slot * 2 + j]);
+                // hot chunk 0 = (bytes, nstart), hot chunk 1 = (end, packets, flags)
+                const uint32_t b_lo = __shfl_sync(0xFFFFFFFFu, hot.x, g * 8), b_hi = __shfl_sync(0xFFFFFFFFu, hot.y, g * 8);
+                const uint32_t ns_lo = __shfl_sync(0xFFFFFFFFu, hot.z, g * 8), ns_hi = __shfl_sync(0xFFFFFFFFu, hot.w, g * 8);
+                const uint32_t e_lo = __shfl_sync(0xFFFFFFFFu, hot.x, g * 8 + 1), e_hi = __shfl_sync(0xFFFFFFFFu, hot.y, g * 8 + 1);
+                const uint32_t pk = __shfl_sync(0xFFFFFFFFu, hot.z, g * 8 + 1), fl = __shfl_sync(0xFFFFFFFFu, hot.w, g * 8 + 1);
                 if (live && idx < cap) {
                     uint4* O = out + idx * kRecChunks;
                     const uint64_t start = 0ull - u64_of(ns_lo, ns_hi);       // nstart = -start; 0 stays 0
@@ -92,22 +89,16 @@ evict_kernel(Table t, uint4* __restrict__ out, uint32_t* __restrict__ slot_of_ou
                     } else if (j == 2) {
                         O[2] = make_uint4(line.x, line.y & 0x00FFFFFFu, (uint32_t)start, (uint32_t)(start >> 32));
                     } else if (j == 3) {
-                        O[4] = make_uint4(pk, (line.y & 0xFFFFu) | (fl << 16), line.z, line.w);   // packets, eth | flags, macs
-                    } else if (j == 5) {
-                        O[3] = make_uint4(line.x, line.y, b_lo, b_hi);          // end, bytes
-                    } else if (j == 6) {
-                        O[5] = line;                                            // dst_mac[2..6) if_index lock sampling
-                        O[6] = make_uint4(l7w, cold.y, cold.z, cold.w);         // dir errno dscp nb_obs | observed_direction | observed_intf[0]
-                    } else if (j == 7) {
-                        O[7] = cold;                                            // observed_intf[1..5)
-                        O[8] = make_uint4(line.x, line.y, line.z, 0u);          // observed_intf[5] | ssl, cipher | key share, types, misc
+                        O[3] = make_uint4(e_lo, e_hi, b_lo, b_hi);              // end, bytes
+                        O[4] = make_uint4(pk, (line.y & 0xFFFFu) | (fl << 16), line.z, line.w);   // packets, eth|flags, desc[0..8)
+                    } else {
+                        O[j + 1] = line;                                        // desc[8..72)
                     }
                     if (slot_of_out && j == 0) slot_of_out[idx] = (uint32_t)slot;   // for the feature pass
                 }
-                // delete: tag -> EMPTY, accumulators -> identity, cold line -> zero  (drain: the accumulators only)
+                // delete: tag -> EMPTY, hot line -> identity  (drain: hot line only)
                 if (!kDrain && live && j == 2) *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(&t.ident[slot * 8 + 2]) + 8) = make_uint2(0u, 0u);
-                if (live && (j == 4 || j == 5)) t.ident[slot * 8 + j] = make_uint4(0, 0, 0, 0);
-                if (!kDrain && live && has_obs && j >= 6) t.cold[slot * 2 + (j - 6)] = make_uint4(0, 0, 0, 0);
+                if (live && j < 2) t.hot[slot * 2 + j] = make_uint4(0, 0, 0, 0);
             }
         }
     }

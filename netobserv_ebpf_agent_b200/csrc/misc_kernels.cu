@@ -286,7 +286,8 @@ __global__ void route_scatter_kernel(const uint4* __restrict__ recs, uint32_t n,
 // into peer memory (mapped with CUDA IPC).  No NCCL call, no size known to the host: the owner reads its
 // record count from its own memory.  n itself may live on the device (count of a preceding drain).
 __global__ void route_peer_kernel(const uint4* __restrict__ recs, const unsigned long long* __restrict__ n_dev, uint32_t max_n,
-                                  uint32_t n_shards, PeerTargets pt, unsigned long long cap, unsigned long long* overflow) {
+                                  uint32_t n_shards, uint32_t self_shard, PeerTargets pt, unsigned long long cap,
+                                  unsigned long long* overflow) {
     __shared__ uint32_t wcount[kRouteThreads / 32][kMaxShards];
     __shared__ uint32_t cta_cnt[kMaxShards];
     __shared__ unsigned long long cursor[kMaxShards];
@@ -309,8 +310,11 @@ __global__ void route_peer_kernel(const uint4* __restrict__ recs, const unsigned
         own[k] = (uint8_t)o;
     }
     __syncthreads();
-    if (threadIdx.x < n_shards)                          // reserve this CTA's range in every owner's receive buffer
+    if (threadIdx.x < n_shards) {                        // reserve this CTA's range in every owner's receive buffer
         cursor[threadIdx.x] = cta_cnt[threadIdx.x] ? atomicAdd_system(pt.count[threadIdx.x], (unsigned long long)cta_cnt[threadIdx.x]) : 0ull;
+        // overflow[1]: records that leave this GPU (x 144 B = the NVLink payload of the exchange)
+        if (threadIdx.x != self_shard && cta_cnt[threadIdx.x]) atomicAdd(overflow + 1, (unsigned long long)cta_cnt[threadIdx.x]);
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t round = 0; round < kRoutePerCta / kRouteThreads; round++) {
         const uint32_t k = round * kRouteThreads + threadIdx.x;
@@ -353,10 +357,10 @@ __global__ void route_peer_kernel(const uint4* __restrict__ recs, const unsigned
     __threadfence_system();                                               // peer stores visible before the kernel retires
 }
 #ifndef FA_HOST_EMUL
-int launch_route_peer(const uint4* recs, const unsigned long long* n_dev, uint32_t max_n, uint32_t n_shards,
+int launch_route_peer(const uint4* recs, const unsigned long long* n_dev, uint32_t max_n, uint32_t n_shards, uint32_t self_shard,
                       const PeerTargets& pt, unsigned long long cap, unsigned long long* overflow, cudaStream_t st) {
     if (!max_n) return 0;
-    route_peer_kernel<<<(max_n + kRoutePerCta - 1) / kRoutePerCta, kRouteThreads, 0, st>>>(recs, n_dev, max_n, n_shards, pt, cap, overflow);
+    route_peer_kernel<<<(max_n + kRoutePerCta - 1) / kRoutePerCta, kRouteThreads, 0, st>>>(recs, n_dev, max_n, n_shards, self_shard, pt, cap, overflow);
     return 1;
 }
 #endif  // FA_HOST_EMUL

@@ -49,6 +49,7 @@ int sfail(int code, const char* fmt, ...) {
 struct fa_sharded {
     uint32_t n = 0;
     uint64_t round_cap = 0;                       // records per source GPU and round
+    uint64_t recv_cap = 0;                        // records a receive buffer holds
     bool combine = true;
     std::mutex mu;
     struct Gpu {
@@ -105,6 +106,7 @@ int fa_sharded_create(const fa_config* cfg, const int32_t* devices, uint32_t n_d
     s->n = n_devices;
     s->round_cap = cfg->max_batch ? cfg->max_batch : (1ull << 22);
     s->combine = (cfg->reserved0 & 1u) == 0;              // reserved0 bit 0: route raw records, no local combiner
+    s->recv_cap = s->round_cap * n_devices;               // worst case: every source's whole round lands on one owner
     s->g.resize(n_devices);
     for (uint32_t i = 0; i < n_devices; i++) {
         auto& G = s->g[i];
@@ -121,11 +123,13 @@ int fa_sharded_create(const fa_config* cfg, const int32_t* devices, uint32_t n_d
         }
         SCU(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
         fa_config oc = *cfg;
-        oc.device = G.device; oc.flags = FA_F_NO_FULL_CUT; oc.cuda_stream = G.stream; oc.max_batch = s->round_cap; oc.reserved0 = 0;
+        oc.device = G.device; oc.flags = FA_F_NO_FULL_CUT; oc.cuda_stream = G.stream; oc.reserved0 = 0;
+        oc.max_batch = s->recv_cap;                       // an owner folds a whole receive buffer in one launch
         oc.max_entries = std::max<uint64_t>(1024, (cfg->max_entries + n_devices - 1) / n_devices * 5 / 4);   // owners hold ~1/N of the flows
         SFA(fa_create(&oc, &G.owner));
         if (s->combine) {
             fa_config lc = oc;
+            lc.max_batch = s->round_cap;
             lc.max_entries = std::max<uint64_t>(2 * s->round_cap, std::min<uint64_t>(cfg->max_entries, 1ull << 26));
             SFA(fa_create(&lc, &G.local));
         }
@@ -135,8 +139,7 @@ int fa_sharded_create(const fa_config* cfg, const int32_t* devices, uint32_t n_d
         SCU(cudaMalloc(&G.d_over, 16));
         SCU(cudaMemset(G.d_over, 0, 16));
         for (int b = 0; b < 2; b++) {
-            // worst case every record of every source's round lands on one owner: size by the round, overflow is counted
-            SCU(cudaMalloc(&G.recv[b], s->round_cap * kRec));
+            SCU(cudaMalloc(&G.recv[b], s->recv_cap * kRec));
             SCU(cudaMalloc(&G.recv_n[b], 8));
             SCU(cudaMemset(G.recv_n[b], 0, 8));
             SCU(cudaEventCreateWithFlags(&G.ev_routed[b], cudaEventDisableTiming));
@@ -170,7 +173,7 @@ static int sharded_round(fa_sharded* s, const size_t* cnt) {
                 SFA(fa_drain_active_counted(G.local, G.d_part, s->round_cap, G.d_part_n));
                 src = G.d_part; src_n = G.d_part_n; max_n = std::min<size_t>(s->round_cap, cnt[i]);
             }
-            SFA(fa_route_peer(G.owner, src, src_n, max_n, N, i, bufs, cnts, s->round_cap, G.d_over));
+            SFA(fa_route_peer(G.owner, src, src_n, max_n, N, i, bufs, cnts, s->recv_cap, G.d_over));
         }
         SCU(cudaEventRecord(G.ev_routed[b], G.stream));
         SCU(cudaEventRecord(G.ev_in_free, G.stream));
@@ -179,7 +182,7 @@ static int sharded_round(fa_sharded* s, const size_t* cnt) {
         auto& G = s->g[j];
         SCU(cudaSetDevice(G.device));
         for (uint32_t i = 0; i < N; i++) SCU(cudaStreamWaitEvent(G.stream, s->g[i].ev_routed[b], 0));
-        SFA(fa_ingest_counted(G.owner, G.recv[b], G.recv_n[b], s->round_cap, 1));
+        SFA(fa_ingest_counted(G.owner, G.recv[b], G.recv_n[b], s->recv_cap, 1));
         SCU(cudaEventRecord(G.ev_folded[b], G.stream));
     }
     s->rounds++;

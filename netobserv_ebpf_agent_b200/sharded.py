@@ -174,7 +174,7 @@ class PeerShardedAggregator:
             check(L.fa_device_alloc(engine._h, nbytes, C.byref(p)))
             return p.value
         self.mine = [(dalloc(self.recv_cap * REC_BYTES), dalloc(8)) for _ in range(2)]     # (buffer, counter) x 2
-        self.overflow = dalloc(8)
+        self.overflow = dalloc(16)                      # [0] receive-buffer overflow, [1] records stored into other GPUs
         # exchange the IPC handles of the four allocations and map every peer's
         hbuf = np.zeros((4, 64), dtype=np.uint8)
         for i, p in enumerate([self.mine[0][0], self.mine[0][1], self.mine[1][0], self.mine[1][1]]):
@@ -216,7 +216,7 @@ class PeerShardedAggregator:
             check(L.fa_drain_active_counted(self.local._h, C.c_void_p(self.part.data_ptr()), self.max_batch,
                                             C.c_void_p(self.part_n.data_ptr())))
             check(L.fa_route_peer(self.eng._h, C.c_void_p(self.part.data_ptr()), C.c_void_p(self.part_n.data_ptr()),
-                                  self.max_batch, self.world, self.bufs[b], self.cnts[b], self.recv_cap,
+                                  self.max_batch, self.world, self.rank, self.bufs[b], self.cnts[b], self.recv_cap,
                                   C.c_void_p(self.overflow)))
             dist.all_reduce(self.token)                    # stream-ordered barrier: every rank has delivered batch `step`
             check(L.fa_ingest_counted(self.eng._h, C.c_void_p(self.mine[b][0]), C.c_void_p(self.mine[b][1]),
@@ -225,16 +225,29 @@ class PeerShardedAggregator:
             done += c
         return 0
 
-    def flush(self):
+    def _counters(self):
+        import ctypes
         import torch
         torch.cuda.current_stream().synchronize()
-        ov = np.zeros(1, dtype=np.uint64)
-        import ctypes
+        ov = np.zeros(2, dtype=np.uint64)
         cudart = ctypes.CDLL("libcudart.so")
-        cudart.cudaMemcpy(ctypes.c_void_p(ov.ctypes.data), ctypes.c_void_p(self.overflow), 8, 2)
-        if int(ov[0]):
-            raise RuntimeError(f"peer receive buffer overflow: {int(ov[0])} records did not fit (raise recv_cap)")
+        cudart.cudaMemcpy(ctypes.c_void_p(ov.ctypes.data), ctypes.c_void_p(self.overflow), 16, 2)
+        return int(ov[0]), int(ov[1])
+
+    def flush(self):
+        overflow, _ = self._counters()
+        if overflow:
+            raise RuntimeError(f"peer receive buffer overflow: {overflow} records did not fit (raise recv_cap)")
+        spills = self.local.stats()["spills"] + self.eng.stats()["spills"]
+        if spills:                                   # a scratch / owner table that is physically full drops records
+            raise RuntimeError(f"{spills} records found a flow table physically full (raise max_entries / evict more often)")
         return 0
+
+    def exchange_stats(self):
+        """What crossed NVLink so far: records this rank stored into other GPUs' receive buffers (x 144 B)."""
+        _, remote = self._counters()
+        return {"nvlink_records_rank0": remote, "nvlink_bytes_rank0": remote * REC_BYTES, "rounds": self.step,
+                "nvlink_bytes_per_round_rank0": remote * REC_BYTES // max(self.step, 1)}
 
     def close(self):
         import torch.distributed as dist

@@ -38,6 +38,8 @@ def _load_engine_emulation():
                [os.path.join(EMUL, "simt.h"), os.path.join(ROOT, "include", "flowagg.h")])
     lib = ctypes.CDLL(so)
     for name, (res, args) in L.SIGNATURES.items():
+        if name.startswith("fa_sharded_"):            # csrc/sharded.cu (several GPUs, peer access) is not emulated
+            continue
         f = getattr(lib, name)
         f.restype, f.argtypes = res, args
     return L, lib

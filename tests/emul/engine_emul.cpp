@@ -235,7 +235,7 @@ int launch_generate(const GenDeviceParams& g_, uint64_t first_index, uint32_t n,
     simt::launch(2, 256, 0, [=] { generate_kernel(g, first_index, n, dst); });
     return 1;
 }
-int launch_route_peer(const uint4*, const unsigned long long*, uint32_t, uint32_t, const PeerTargets&, unsigned long long,
+int launch_route_peer(const uint4*, const unsigned long long*, uint32_t, uint32_t, uint32_t, const PeerTargets&, unsigned long long,
                       unsigned long long*, cudaStream_t) { abort(); }          // multi-GPU exchange: not emulated
 int launch_route(const uint4* recs, uint32_t n, uint32_t n_shards, uint4* out, unsigned long long* counts_dev, uint32_t* tmp,
                  int, cudaStream_t) {

@@ -63,7 +63,7 @@ void* k1_emul_new(uint64_t max_entries, uint64_t max_batch) {
     e->slots = slots; e->max_batch = max_batch;
     e->t.mask = slots - 1;
     e->t.ident = static_cast<uint4*>(zalloc(slots * kIdentBytes));
-    e->t.cold = static_cast<uint4*>(zalloc(slots * kColdBytes));
+    e->t.hot = static_cast<uint4*>(zalloc(slots * kHotBytes));
     e->t.occ = static_cast<uint32_t*>(zalloc(slots / 8));
     e->ctr = static_cast<Counters*>(zalloc(sizeof(Counters)));
     uint32_t ss = 1024; while ((uint64_t)ss < 2 * max_batch) ss <<= 1;
@@ -74,7 +74,7 @@ void* k1_emul_new(uint64_t max_entries, uint64_t max_batch) {
 }
 void k1_emul_free(void* h) {
     Emul* e = static_cast<Emul*>(h);
-    free(e->t.ident); free(e->t.cold); free(e->t.occ); free(e->ctr); free(e->scratch); free(e->spill_idx);
+    free(e->t.ident); free(e->t.hot); free(e->t.occ); free(e->ctr); free(e->scratch); free(e->spill_idx);
     delete e;
 }
 

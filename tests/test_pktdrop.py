@@ -124,4 +124,4 @@ def test_golden_gpu():
 
 @pytest.mark.gpu
 def test_random_streams_gpu():
-    check_random(n_keys=5_000, n_base=80_000, n_feat=60_000, max_entries=1 << 14, max_batch=1 << 15)
+    check_random(n_keys=5_000, n_base=80_000, n_feat=60_000, max_entries=1 << 17, max_batch=1 << 15)
