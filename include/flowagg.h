@@ -215,6 +215,11 @@ typedef struct fa_config {
 #define FA_F_NO_FULL_CUT    0x8u  /* never return FA_FULL: max_entries only sizes the table (KERNEL_MAP-style caches,
                                      multi-GPU scratch / owner tables); a physically full table spills (fa_stats.spills) */
 #define FA_F_ENABLE_PKT_DROP 0x20u /* ENABLE_PKT_DROPS     (config.go) : fa_ingest_pkt_drops + the drop blocks at eviction */
+#define FA_F_NONBLOCKING_EVICT 0x40u /* keep a second, empty flow table: fa_evict swaps the two under the engine lock — the
+                                     Accounter hands its map over and goes on with a fresh one, pkg/flow/account.go:67-68,
+                                     86-87 — and scans the retired table on its own stream, so fa_ingest (another thread)
+                                     never waits for the scan or the copy to the host.  Twice the table memory;
+                                     ACCOUNTER mode without feature folds */
 #define FA_F_RINGBUF_FALLBACK 0x10u /* KERNEL_MAP mode: ENABLE_FLOWS_RINGBUF_FALLBACK (config.go:286-288): packets whose flow
                                      cannot be created because the map is full are kept as single-packet records
                                      (errno = E2BIG, bpf/flows.c:262-279) and read back with fa_read_spilled(); without

@@ -9,6 +9,7 @@ FA_OK, FA_FULL = 0, 1
 FA_E_INVAL, FA_E_NOMEM, FA_E_CUDA, FA_E_NODEV, FA_E_2BIG, FA_E_CLOSED = -22, -12, -5, -19, -7, -9
 FA_MODE_ACCOUNTER, FA_MODE_KERNEL_MAP = 0, 1
 FA_F_ENABLE_RTT, FA_F_ENABLE_DNS, FA_F_ENABLE_SKETCH, FA_F_NO_FULL_CUT, FA_F_RINGBUF_FALLBACK, FA_F_ENABLE_PKT_DROP = 1, 2, 4, 8, 16, 32
+FA_F_NONBLOCKING_EVICT = 64
 FA_GEN_UNIFORM, FA_GEN_ZIPF = 0, 1
 FA_ABI_VERSION = 1
 

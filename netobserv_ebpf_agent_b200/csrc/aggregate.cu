@@ -30,11 +30,12 @@
 namespace fa {
 
 #ifndef FA_K1_TILE
-#define FA_K1_TILE 128
+#define FA_K1_TILE 256
 #endif
 constexpr int kTile      = FA_K1_TILE;          // records per tile == threads per team
 constexpr int kTeams     = 1024 / kTile;        // teams per CTA (one CTA per SM): independent tile pipelines that fill each other's
-                                                // bubbles (tile wait, team barriers); 8 x 128 measured +5 % over 4 x 256
+                                                // bubbles (tile wait, team barriers).  8 x 128 was measured: the TMA wait per tile
+                                                // stays, the work per tile halves -> slower on the Zipf workloads (profiles/README.md)
 constexpr int kCtaThreads = kTile * kTeams;
 constexpr int kRepSlots  = 2 * kTile;
 constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
@@ -243,7 +244,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         const uint32_t cnt = min((uint32_t)kTile, n - first);
         mbar_wait(&s.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
-        if (!(opt & 32u) && tid == 0) {                            // have L2 fetch the team's next tile while this one is worked on
+        if ((opt & 32u) && tid == 0) {                             // experiment: have L2 fetch the team's next tile now (no gain measured)
             const uint32_t nt = tile_idx + tile_stride;
             if (nt < n_tiles) tma_prefetch_l2(recs + (size_t)nt * kTile * kRecChunks, min((uint32_t)kTile, n - nt * kTile) * kRecBytes);
         }
@@ -548,344 +549,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
 }
 
 // ------------------------------------------------------------------------------------
-// K1s — the streaming kernel: every warp runs its own software pipeline over 32-record slices.
-//
-//   TMA (cp.async.bulk + mbarrier) stages the warp's next two slices (3 buffers of 4,608 B)
-//   front(s+1): one thread per record — hash; an exact 114-byte match against the warp's PRIVATE hot-flow cache folds
-//               the record on-chip with plain loads and stores (lanes that hit the same entry pre-reduce with
-//               match.any + redux: no shared-memory atomics anywhere); the identity lines of the records that missed
-//               are gathered with 16-byte cp.async copies (LDGSTS: 8 lanes per 128-byte line = one L1 wavefront per
-//               line, no registers, no wait) into the warp's line buffer
-//   back(s):    the gather of the PREVIOUS slice has landed meanwhile: one thread per record compares its line
-//               (XOR-swizzled, conflict-free) with its record, settled flows at their home slot reduce straight away
-//               (three fire-and-forget reductions); a home slot held by another flow looks one slot further; inserts,
-//               chains and in-flight publishes go to the 8-lane general probe shared with K1.
-// Nothing is shared between warps (no barriers, no elections, no atomics on shared memory); L2 / DRAM latency of the
-// table is hidden by the slice in between issue and use.  A flow seen three times within a short while (per-warp
-// filter) is installed in the private cache; entries age, a colder one is flushed (same reductions) and replaced.
-// Exactness is that of K1: the cache and the probe compare all 114 bytes, any descriptor mismatch flags the flow
-// TAG_DIRTY for the ordered re-fold below.
-// ------------------------------------------------------------------------------------
-constexpr int kSW = 8;                            // warps per CTA (one CTA per SM)
-constexpr int kSSub = 32;                         // records per slice == lanes
-constexpr int kSC = 32;                           // private cache entries per warp (direct-mapped on the hash's top bits)
-constexpr int kSF = 256;                          // "seen recently" filter entries per warp
-
-struct __align__(16) SCacheEntry {                // 176 B: a stride of 44 words keeps 8 entries on distinct banks
-    uint4    line[8];                             // copy of the flow's identity line (key, tag, start mirror, descriptor)
-    unsigned long long bytes, ns, end;            // what the folded records add / max (ns = 0 - start, 0 = unset)
-    uint32_t packets, flags;
-    uint32_t hash, slot, hits, state;             // state 0 = empty
-};
-static_assert(sizeof(SCacheEntry) == 176, "SCacheEntry stride");
-struct __align__(128) SWarp {                     // 28,928 B per warp
-    uint4    rec[3][kSSub * kRecChunks];          // 13,824 B  three TMA-staged slices
-    uint4    line[2][kSSub * 8];                  //  8,192 B  gathered identity lines, chunk c of row r at r*8 + (c ^ (r & 7))
-    SCacheEntry cache[kSC];                       //  5,632 B
-    uint32_t filt[kSF];                           //  1,024 B  (hash & 0xFFFFFF00) | times seen
-    uint32_t res[kSSub];                          //    128 B  slots found by the general probe
-    unsigned long long full_bar[3];
-    uint8_t  list[kSSub];                         //  the probing lanes, compacted
-    uint8_t  slow[kSSub];                         //  lanes whose flow needs the general probe
-    uint8_t  pad[40];
-};
-static_assert(sizeof(SWarp) == 28928, "SWarp");
-
-#ifndef FA_HOST_EMUL
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {      // SASS: LDGSTS.E.BYPASS.128
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int kPending> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
-#endif
-
-__device__ __forceinline__ void issue_slice_load(uint4* buf, unsigned long long* bar, const uint4* recs, uint32_t n, uint32_t sub) {
-    const uint32_t first = sub * kSSub;
-    const uint32_t bytes = min((uint32_t)kSSub, n - first) * kRecBytes;
-    mbar_expect_tx(bar, bytes);
-    tma_load_1d(buf, recs + (size_t)first * kRecChunks, bytes, bar);
-}
-
-// what a record carries from front() to back()
-struct SCarry { uint32_t h32, home; bool probe; };
-
-// flush one private cache entry: the same reductions a probing record issues
-template <bool kSketch>
-__device__ __forceinline__ void scache_flush(const Table& t, const SketchParams& sk, const SCacheEntry& e) {
-    const uint64_t tag = u64_of(e.line[2].z, e.line[2].w);
-    const uint64_t floor_ns = u64_of(e.line[3].x, e.line[3].y >> 16) << 16;
-    reduce_to_hot(t, e.slot, e.bytes, e.packets, e.ns, e.end, e.flags, floor_ns, (uint32_t)(tag >> TAG_FLAGS_SHIFT) & 0xFFFFu);
-    if (kSketch) {
-        const uint4 k0 = e.line[0], k1 = e.line[1], k2 = e.line[2];
-        sketch_update(sk, key_premix(u64_of(k0.x, k0.y), u64_of(k0.z, k0.w), u64_of(k1.x, k1.y), u64_of(k1.z, k1.w),
-                                     u64_of(k2.x, k2.y)), e.packets);
-    }
-}
-
-// 64-bit sum / max over the lanes of `peers` (redux is 32 bits wide: four 16-bit partial sums are exact)
-__device__ __forceinline__ uint64_t peers_add_u64(uint32_t peers, uint64_t v) {
-    const uint32_t s0 = __reduce_add_sync(peers, (uint32_t)v & 0xFFFFu), s1 = __reduce_add_sync(peers, ((uint32_t)v >> 16) & 0xFFFFu);
-    const uint32_t s2 = __reduce_add_sync(peers, (uint32_t)(v >> 32) & 0xFFFFu), s3 = __reduce_add_sync(peers, (uint32_t)(v >> 48));
-    return (uint64_t)s0 + ((uint64_t)s1 << 16) + ((uint64_t)s2 << 32) + ((uint64_t)s3 << 48);
-}
-__device__ __forceinline__ uint64_t peers_max_u64(uint32_t peers, uint64_t v) {
-    const uint32_t mh = __reduce_max_sync(peers, (uint32_t)(v >> 32));
-    const uint32_t ml = __reduce_max_sync(peers, (uint32_t)(v >> 32) == mh ? (uint32_t)v : 0u);
-    return u64_of(ml, mh);
-}
-
-// front(): hash, private-cache fold, gather issue for one slice
-__device__ __forceinline__ SCarry stream_front(SWarp& s, const uint4* Rbuf, uint4* Lbuf, uint32_t cnt, const Table& t,
-                                               uint32_t tmask, int lane, uint32_t lt_mask, bool use_cache) {
-    const bool valid = (uint32_t)lane < cnt;
-    const uint4* R = Rbuf + lane * kRecChunks;
-    uint32_t h32 = 0, ci = 0;
-    bool hit = false;
-    if (valid) {
-        const uint4 r0 = R[0], r1 = R[1], r2 = R[2];
-        h32 = (uint32_t)slot_hash(key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y), u64_of(r1.z, r1.w),
-                                             u64_of(r2.x, r2.y)));
-        ci = h32 >> 27;
-        const SCacheEntry& ce = s.cache[ci];
-        if (use_cache && ce.state != 0u && ce.hash == h32) {
-            uint32_t d = diff4_masked(ce.line[0], r0, chunk_mask(0)) | diff4_masked(ce.line[1], r1, chunk_mask(1)) |
-                         diff4_masked(ce.line[2], r2, chunk_mask(2));
-#pragma unroll
-            for (int c = 3; c < 8; c++) d |= diff4_masked(ce.line[c], R[c + 1], chunk_mask(c));
-            hit = d == 0u;
-        }
-    }
-    const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, hit);
-    if (hitmask) {                                                     // warp-uniform
-        if (hit) {
-            FA_EMUL_COUNT(2, 1);
-            const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
-            const uint64_t v_start = u64_of(r2.z, r2.w);
-            uint64_t bytes = u64_of(r3.z, r3.w), ns = v_start ? 0ull - v_start : 0ull, end = u64_of(r3.x, r3.y);
-            uint32_t packets = r4.x, flags = r4.y >> 16;
-            const uint32_t peers = __match_any_sync(hitmask, ci);     // lanes folding into the same entry
-            if (peers != (1u << lane)) {
-                bytes = peers_add_u64(peers, bytes);
-                packets = __reduce_add_sync(peers, packets);
-                flags = __reduce_or_sync(peers, flags);
-                ns = peers_max_u64(peers, ns);
-                end = peers_max_u64(peers, end);
-            }
-            if (lane == __ffs(peers) - 1) {                            // one lane per entry: plain read-modify-write
-                SCacheEntry& e = s.cache[ci];
-                e.bytes += bytes; e.packets += packets; e.flags |= flags;
-                if (ns > e.ns) e.ns = ns;
-                if (end > e.end) e.end = end;
-                e.hits += (uint32_t)__popc(peers);
-            }
-        }
-        __syncwarp();
-    }
-    const bool probe = valid && !hit;
-    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, probe);
-    const uint32_t npr = (uint32_t)__popc(pm);
-    if (probe) s.list[__popc(pm & lt_mask)] = (uint8_t)lane;
-    __syncwarp();
-    const uint32_t home = h32 & tmask;
-    const int g = lane >> 3, j = lane & 7;
-    for (uint32_t base = 0; base < npr; base += 4) {                   // 8 lanes per line, 4 lines per round
-        const uint32_t k = base + g;
-        const uint32_t src = k < npr ? (uint32_t)s.list[k] : 0u;
-        const uint32_t slot = __shfl_sync(0xFFFFFFFFu, home, (int)src);
-        if (k < npr) cp_async16(&Lbuf[src * 8 + (j ^ (src & 7))], &t.ident[(size_t)slot * 8 + j]);
-    }
-    cp_async_commit();
-    FA_EMUL_COUNT(0, lane == 0 ? npr : 0);
-    return SCarry{h32, home, probe};
-}
-
-// One thread checks a whole identity line against its record.  Returns 0 = this flow, settled; 1 = another settled
-// flow lives here; 2 = anything else (empty, being published, born in this launch, feature-only entry).
-__device__ __forceinline__ int line_verdict(const uint4* R, uint4 l0, uint4 l1, uint4 l2, uint4 l3, uint4 l4, uint4 l5, uint4 l6, uint4 l7,
-                                            uint64_t epoch, uint32_t& ddesc) {
-    const uint64_t tag = u64_of(l2.z, l2.w);
-    const bool settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) && (tag >> TAG_EPOCH_SHIFT) != epoch;
-    if (!settled) return 2;
-    const uint32_t dkey = diff4_masked(l0, R[0], chunk_mask(0)) | diff4_masked(l1, R[1], chunk_mask(1)) | diff4_masked(l2, R[2], chunk_mask(2));
-    if (dkey) return 1;
-    ddesc = diff4_masked(l3, R[4], chunk_mask(3)) | diff4_masked(l4, R[5], chunk_mask(4)) | diff4_masked(l5, R[6], chunk_mask(5)) |
-            diff4_masked(l6, R[7], chunk_mask(6)) | diff4_masked(l7, R[8], chunk_mask(7));
-    return 0;
-}
-
-// back(): compare, reduce, install for the slice whose gather was issued one iteration ago
-template <bool kSketch>
-__device__ __forceinline__ void stream_back(SWarp& s, const uint4* Rbuf, const uint4* Lbuf, SCarry c, const Table& t, uint64_t epoch,
-                                            uint32_t tmask, const SketchParams& sk, int lane, uint32_t lt_mask, bool use_cache,
-                                            uint32_t& my_inserts, uint32_t& my_spills, uint32_t& any_dirty) {
-    const uint4* R = Rbuf + lane * kRecChunks;
-    uint32_t slot = c.home;
-    uint64_t floor_ns = 0;
-    uint32_t seen = 0;
-    bool need_slow = false, at_home = false;
-    uint32_t ddesc = 0;
-    if (c.probe) {
-        const uint4* L = Lbuf + lane * 8;
-        const int sw = lane & 7;
-        uint4 l2 = L[2 ^ sw], l3 = L[3 ^ sw];
-        int v = line_verdict(R, L[0 ^ sw], L[1 ^ sw], l2, l3, L[4 ^ sw], L[5 ^ sw], L[6 ^ sw], L[7 ^ sw], epoch, ddesc);
-        at_home = v == 0;
-        if (v == 1) {                                                  // another flow at home: look one slot further, now
-            slot = (slot + 1) & tmask;
-            const uint4* G = &t.ident[(size_t)slot * 8];
-            l2 = ld_cg_u4(G + 2); l3 = ld_cg_u4(G + 3);
-            v = line_verdict(R, ld_cg_u4(G), ld_cg_u4(G + 1), l2, l3, ld_cg_u4(G + 4), ld_cg_u4(G + 5), ld_cg_u4(G + 6), ld_cg_u4(G + 7),
-                             epoch, ddesc);
-        }
-        if (v == 0) {
-            const uint64_t tag = u64_of(l2.z, l2.w);
-            floor_ns = u64_of(l3.x, l3.y >> 16) << 16;
-            seen = (uint32_t)(tag >> TAG_FLAGS_SHIFT) & 0xFFFFu;
-            if (ddesc) {                                               // descriptor differs: ordered re-fold
-                if (!(tag & TAG_DIRTY))
-                    atomicOr(reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot * 8 + 2]) + 1, (unsigned long long)TAG_DIRTY);
-                any_dirty = 1;
-            }
-        } else {
-            need_slow = true;
-        }
-    }
-    const uint32_t slowm = __ballot_sync(0xFFFFFFFFu, need_slow);
-    if (slowm) {                                                       // inserts, chains, in-flight publishes: 8 lanes per flow
-        const uint32_t nslow = (uint32_t)__popc(slowm);
-        if (need_slow) s.slow[__popc(slowm & lt_mask)] = (uint8_t)lane;
-        __syncwarp();
-        FA_EMUL_COUNT(1, lane == 0 ? nslow : 0);
-        const int g = lane >> 3, j = lane & 7;
-        const uint4 cmask = chunk_mask(j);
-        const int rc = rec_chunk_of_line_chunk(j);
-        for (uint32_t base = 0; base < nslow; base += 4) {
-            const uint32_t k = base + g;
-            const bool act = k < nslow;
-            const uint32_t ri = act ? (uint32_t)s.slow[k] : 0u;
-            const uint4 rchunk = Rbuf[ri * kRecChunks + rc];
-            const uint4 c2 = Rbuf[ri * kRecChunks + 2];
-            const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
-            const uint32_t start_slot = __shfl_sync(0xFFFFFFFFu, c.home, (int)ri);
-            const uint32_t got = probe_general(t, epoch, act, start_slot, rchunk, false, own_ns, g, j, cmask, my_inserts, &any_dirty);
-            if (act && j == 0) s.res[ri] = got;
-        }
-        __syncwarp();
-        if (need_slow) { slot = s.res[lane]; floor_ns = 0; seen = 0; }    // unknown: issue every reduction
-    }
-    if (c.probe) {
-        const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
-        const uint64_t v_start = u64_of(r2.z, r2.w);
-        if (kSketch) {
-            const uint4 r0 = R[0], r1 = R[1];
-            sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y), u64_of(r1.z, r1.w),
-                                         u64_of(r2.x, r2.y)), r4.x);
-        }
-        if (slot != kResSpill) reduce_to_hot(t, slot, u64_of(r3.z, r3.w), r4.x, 0ull - v_start, u64_of(r3.x, r3.y), r4.y >> 16, floor_ns, seen);
-        else my_spills++;                                              // table physically full: counted in fa_stats.spills
-    }
-    // ---- private cache: a flow met three times within a short while gets an entry; a colder incumbent is flushed
-    bool want = false;
-    const uint32_t ci = c.h32 >> 27;
-    if (use_cache && c.probe && at_home && ddesc == 0u) {
-        uint32_t* f = &s.filt[(c.h32 >> 8) & (kSF - 1)];
-        const uint32_t fv = *f;
-        const uint32_t cntf = ((fv ^ c.h32) & 0xFFFFFF00u) == 0u ? min((fv & 0xFFu) + 1u, 255u) : 1u;
-        *f = (c.h32 & 0xFFFFFF00u) | cntf;
-        const SCacheEntry& e = s.cache[ci];
-        want = cntf >= 3u && (e.state == 0u || (e.hash != c.h32 && e.hits < cntf));
-    }
-    uint32_t im = __ballot_sync(0xFFFFFFFFu, want);
-    for (int round = 0; im != 0u && round < 2; round++) {              // at most two installs per slice
-        const int src = __ffs(im) - 1;
-        im &= im - 1u;
-        const uint32_t eci = __shfl_sync(0xFFFFFFFFu, ci, src);
-        SCacheEntry& e = s.cache[eci];
-        const uint32_t src_hash = __shfl_sync(0xFFFFFFFFu, c.h32, src);
-        const bool go = e.state == 0u || e.hash != src_hash;           // not installed by the previous round
-        if (go) {
-            if (lane == src && e.state != 0u) scache_flush<kSketch>(t, sk, e);
-            __syncwarp();
-            if (lane < 8) e.line[lane] = Lbuf[src * 8 + (lane ^ (src & 7))];
-            if (lane == src) {
-                e.bytes = 0; e.ns = 0; e.end = 0; e.packets = 0; e.flags = 0;
-                e.hash = c.h32; e.slot = slot; e.hits = 0; e.state = 1u;
-            }
-            __syncwarp();
-        }
-    }
-}
-
-template <bool kSketch, bool kDevN>
-__global__ void __launch_bounds__(kSW * 32, 1)
-aggregate_stream_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, Counters* ctr, SketchParams sk, uint32_t opt) {
-    FA_DYN_SMEM(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SWarp& s = reinterpret_cast<SWarp*>(smem_raw)[warp];
-    if (kDevN) n = min(n, (uint32_t)ctr->launch_n);                // size known on the device only (multi-GPU receive side)
-    const uint32_t n_sub = (n + kSSub - 1) / kSSub;
-    const uint32_t stride = gridDim.x * kSW;
-    const uint32_t sub0 = blockIdx.x * kSW + warp;
-    const uint32_t n_it = sub0 < n_sub ? (n_sub - sub0 + stride - 1) / stride : 0u;
-    const bool use_cache = (opt & 2u) == 0;
-    const uint32_t tmask = (uint32_t)t.mask;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t my_inserts = 0, my_spills = 0, any_dirty = 0;
-
-    if (lane < kSC) { s.cache[lane].state = 0u; s.cache[lane].hash = 0u; s.cache[lane].hits = 0u; }
-    for (int i = lane; i < kSF; i += 32) s.filt[i] = 0u;
-    if (lane == 0) {
-        for (int b = 0; b < 3; b++) mbar_init(&s.full_bar[b], 1);
-        fence_barrier_init();
-    }
-    __syncwarp();
-    if (n_it != 0u) {
-        if (lane == 0) {
-            issue_slice_load(s.rec[0], &s.full_bar[0], recs, n, sub0);
-            if (n_it > 1u) issue_slice_load(s.rec[1], &s.full_bar[1], recs, n, sub0 + stride);
-        }
-        mbar_wait(&s.full_bar[0], 0u);
-        SCarry cur = stream_front(s, s.rec[0], s.line[0], min((uint32_t)kSSub, n - sub0 * kSSub), t, tmask, lane, lt_mask, use_cache);
-        uint32_t b_cur = 0, b_nxt = 1, b_ld = 2;                     // record buffers of slices it, it+1, it+2
-        for (uint32_t it = 0; it < n_it; ++it) {
-            const uint32_t sub = sub0 + it * stride;
-            if (it + 2u < n_it && lane == 0) {                       // buffer b_ld was drained by back(it-1)
-                fence_proxy_async();
-                issue_slice_load(s.rec[b_ld], &s.full_bar[b_ld], recs, n, sub + 2u * stride);
-            }
-            SCarry nxt{0u, 0u, false};
-            if (it + 1u < n_it) {
-                mbar_wait(&s.full_bar[b_nxt], ((it + 1u) / 3u) & 1u);
-                nxt = stream_front(s, s.rec[b_nxt], s.line[(it + 1u) & 1u], min((uint32_t)kSSub, n - (sub + stride) * kSSub), t, tmask,
-                                   lane, lt_mask, use_cache);
-            } else {
-                cp_async_commit();
-            }
-            cp_async_wait<1>();                                      // the gather of slice `it` has landed
-            __syncwarp();
-            stream_back<kSketch>(s, s.rec[b_cur], s.line[it & 1u], cur, t, epoch, tmask, sk, lane, lt_mask, use_cache, my_inserts,
-                                 my_spills, any_dirty);
-            __syncwarp();                                            // nobody reads slice `it` any more
-            cur = nxt;
-            const uint32_t b = b_cur; b_cur = b_nxt; b_nxt = b_ld; b_ld = b;
-            if ((it & 31u) == 31u && lane < kSC) s.cache[lane].hits >>= 1;     // ageing
-        }
-        cp_async_wait<0>();
-    }
-    __syncwarp();
-    // ---------------------------------------------------------- counters + cache flush
-    if (lane < kSC && s.cache[lane].state != 0u) scache_flush<kSketch>(t, sk, s.cache[lane]);
-    my_inserts = __reduce_add_sync(0xFFFFFFFFu, my_inserts);
-    my_spills = __reduce_add_sync(0xFFFFFFFFu, my_spills);
-    any_dirty = __reduce_or_sync(0xFFFFFFFFu, any_dirty);
-    if (lane == 0) {
-        if (my_inserts) atomicAdd(&ctr->live, (unsigned long long)my_inserts);
-        if (my_spills) atomicAdd(&ctr->spills, (unsigned long long)my_spills);
-        if (any_dirty) *reinterpret_cast<volatile unsigned long long*>(&ctr->dirty) = 1ull;
-    }
-}
-
-// ------------------------------------------------------------------------------------
 // Ordered re-fold of flows flagged TAG_DIRTY (rare path; both kernels exit at once when
 // nothing was flagged).  fixup_scan: one thread per record finds its flow and, if dirty,
 // reduces min/max record indices into the flow's scratch entry.  fixup_apply: one thread
@@ -1009,25 +672,6 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t st) {
 #define FA_K1_ARGS a.recs, a.n, a.table, a.epoch, a.ctr, a.spill_idx, a.sk
     if (a.prof)
         aggregate_kernel<false, true, false><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, a.prof, a.opt);
-    else if (a.opt & 256u) {                              // K1s: the streaming kernel
-        static bool sattr[64] = {};
-        const int ssmem = (int)(sizeof(SWarp) * kSW);
-        if (!sattr[dev & 63]) {
-            cudaFuncSetAttribute(aggregate_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssmem);
-            cudaFuncSetAttribute(aggregate_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssmem);
-            cudaFuncSetAttribute(aggregate_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssmem);
-            cudaFuncSetAttribute(aggregate_stream_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssmem);
-            sattr[dev & 63] = true;
-        }
-        const uint32_t n_sub = (a.n + kSSub - 1) / kSSub;
-        const int sgrid = (int)min((uint32_t)a.sm_count, (n_sub + kSW - 1) / kSW);
-#define FA_K1S_ARGS a.recs, a.n, a.table, a.epoch, a.ctr, a.sk, a.opt
-        if (a.sk.cms && dev_n) aggregate_stream_kernel<true, true><<<sgrid, kSW * 32, ssmem, st>>>(FA_K1S_ARGS);
-        else if (a.sk.cms) aggregate_stream_kernel<true, false><<<sgrid, kSW * 32, ssmem, st>>>(FA_K1S_ARGS);
-        else if (dev_n) aggregate_stream_kernel<false, true><<<sgrid, kSW * 32, ssmem, st>>>(FA_K1S_ARGS);
-        else aggregate_stream_kernel<false, false><<<sgrid, kSW * 32, ssmem, st>>>(FA_K1S_ARGS);
-#undef FA_K1S_ARGS
-    }
     else if (a.sk.cms && dev_n)
         aggregate_kernel<true, false, true><<<grid, kCtaThreads, smem, st>>>(FA_K1_ARGS, nullptr, a.opt);
     else if (a.sk.cms)

@@ -111,6 +111,15 @@ struct fa_engine {
 
     fa::Table table{};
     uint64_t slots = 0, epoch = 0;
+    // FA_F_NONBLOCKING_EVICT: a second, empty table.  fa_evict swaps the two under `mu` (the Accounter hands its map
+    // over and goes on with a fresh one, pkg/flow/account.go:67-68,86-87) and scans the retired one on its own stream.
+    fa::Table table_spare{};
+    bool double_buffered = false;
+    std::mutex evict_mu;                      // one eviction at a time (the reference's evictor is single-flight)
+    cudaStream_t evict_stream = nullptr;
+    cudaEvent_t ev_swap = nullptr;
+    fa::Counters* d_ctr_ev = nullptr;         // evict_out cursor of the scan of the retired table
+    unsigned long long* h_ev_out = nullptr;   // pinned
     fa::Counters* d_ctr = nullptr;
     fa::Counters* h_ctr = nullptr;            // pinned mirror
     uint64_t max_batch = 0;
@@ -472,6 +481,23 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
     }
     CU(cudaMalloc(&e->table.occ, slots / 8));
     CU(cudaMemsetAsync(e->table.occ, 0, slots / 8, e->stream));
+    if (cfg->flags & FA_F_NONBLOCKING_EVICT) {
+        if (kmap || (cfg->flags & (FA_F_ENABLE_RTT | FA_F_ENABLE_DNS | FA_F_ENABLE_PKT_DROP)))
+            return fail(FA_E_INVAL, "fa_create: FA_F_NONBLOCKING_EVICT is available in ACCOUNTER mode without feature folds");
+        e->table_spare.mask = slots - 1;
+        CU(cudaMalloc(&e->table_spare.ident, slots * fa::kIdentBytes));
+        CU(cudaMemsetAsync(e->table_spare.ident, 0, slots * fa::kIdentBytes, e->stream));
+        CU(cudaMalloc(&e->table_spare.hot, slots * fa::kHotBytes));
+        CU(cudaMemsetAsync(e->table_spare.hot, 0, slots * fa::kHotBytes, e->stream));
+        CU(cudaMalloc(&e->table_spare.occ, slots / 8));
+        CU(cudaMemsetAsync(e->table_spare.occ, 0, slots / 8, e->stream));
+        CU(cudaStreamCreateWithFlags(&e->evict_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&e->ev_swap, cudaEventDisableTiming));
+        CU(cudaMalloc(&e->d_ctr_ev, sizeof(fa::Counters)));
+        CU(cudaMemsetAsync(e->d_ctr_ev, 0, sizeof(fa::Counters), e->stream));
+        CU(cudaHostAlloc(&e->h_ev_out, 8, cudaHostAllocDefault));
+        e->double_buffered = true;
+    }
     if (cfg->flags & FA_F_ENABLE_RTT) {
         CU(cudaMalloc(&e->table.feat_add, slots * 80));
         CU(cudaMemsetAsync(e->table.feat_add, 0, slots * 80, e->stream));
@@ -557,6 +583,10 @@ void fa_destroy(fa_engine* e) {
         cudaFree(e->d_prof);
     }
     if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+    if (e->evict_stream) { cudaStreamSynchronize(e->evict_stream); cudaStreamDestroy(e->evict_stream); }
+    if (e->ev_swap) cudaEventDestroy(e->ev_swap);
+    cudaFree(e->table_spare.ident); cudaFree(e->table_spare.hot); cudaFree(e->table_spare.occ); cudaFree(e->d_ctr_ev);
+    if (e->h_ev_out) cudaFreeHost(e->h_ev_out);
     cudaFree(e->table.ident); cudaFree(e->table.hot); cudaFree(e->table.occ); cudaFree(e->table.feat_add); cudaFree(e->table.feat_dns); cudaFree(e->table.feat_drop);
     cudaFree(e->d_ctr); if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_live_ring) cudaFreeHost(e->h_live_ring);
@@ -701,9 +731,71 @@ int fa_live_flows(fa_engine* e, size_t* n) {
     return FA_OK;
 }
 
+// FA_F_NONBLOCKING_EVICT: swap the tables under `mu` (fa_ingest goes on at once, into the empty one), then lookup-and-
+// delete the retired table on the eviction stream.  Only the K1 launches already queued are waited for.
+static int evict_swapped(fa_engine* e, const fa_evict_out* o, size_t cap, size_t* n_out) {
+    std::lock_guard<std::mutex> elk(e->evict_mu);
+    CU(cudaSetDevice(e->device));
+    fa::Table retired{};
+    uint64_t live = 0;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        int rc = sync_counters(e);                     // the queued folds finish; exact live count
+        if (rc) return rc;
+        live = e->live_known;
+        e->st.evictions++;
+        if (live == 0) return FA_OK;
+        if (!o->records) return fail(FA_E_INVAL, "fa_evict: null out_records");
+        if (cap < live) return fail(FA_E_2BIG, "fa_evict: capacity %zu < %llu live flows", cap, (unsigned long long)live);
+        retired = e->table;
+        e->table = e->table_spare;                     // empty: the previous eviction deleted every flow in place
+        e->table_spare = retired;
+        CU(cudaMemsetAsync(&e->d_ctr->live, 0, sizeof(unsigned long long), e->stream));
+        CU(cudaEventRecord(e->ev_swap, e->stream));
+        e->live_known = 0; e->unsynced_records = 0; e->ring_head = e->ring_tail;
+        e->st.flows_evicted += live;
+    }
+    // from here on fa_ingest runs concurrently
+    const PtrKind k = classify(o->records);
+    uint8_t* d_out = static_cast<uint8_t*>(o->records);
+    if (k != PTR_DEVICE) {
+        if (e->evict_cap < live) {
+            cudaFree(e->d_evict); e->d_evict = nullptr; e->evict_cap = 0;
+            uint64_t want = std::max<uint64_t>(live, std::min<uint64_t>(e->cfg.max_entries, live * 2));
+            CU(cudaMalloc(&e->d_evict, want * fa::kRecBytes));
+            e->evict_cap = want;
+        }
+        d_out = e->d_evict;
+    }
+    CU(cudaStreamWaitEvent(e->evict_stream, e->ev_swap, 0));
+    CU(cudaMemsetAsync(&e->d_ctr_ev->evict_out, 0, sizeof(unsigned long long), e->evict_stream));
+    const int launched = fa::launch_evict(retired, reinterpret_cast<uint4*>(d_out), nullptr, live, e->d_ctr_ev, e->sm_count, e->evict_stream);
+    CU(cudaGetLastError());
+    if (k != PTR_DEVICE) CU(cudaMemcpyAsync(o->records, d_out, live * fa::kRecBytes, cudaMemcpyDeviceToHost, e->evict_stream));
+    CU(cudaMemcpyAsync(e->h_ev_out, &e->d_ctr_ev->evict_out, 8, cudaMemcpyDeviceToHost, e->evict_stream));
+    CU(cudaStreamSynchronize(e->evict_stream));
+    if (*e->h_ev_out != live)
+        return fail(FA_E_CUDA, "fa_evict: table scan found %llu flows, counter says %llu", *e->h_ev_out, (unsigned long long)live);
+    if (k != PTR_DEVICE) {
+        if (o->present) memset(o->present, 0, live);
+        if (o->dns) memset(o->dns, 0, live * 64);
+        if (o->additional) memset(o->additional, 0, live * 32);
+        if (o->pkt_drops) memset(o->pkt_drops, 0, live * 32);
+        if (o->rtt_min) memset(o->rtt_min, 0, live * 8);
+    }
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->st.kernel_launches += launched;
+        if (k != PTR_DEVICE) e->st.d2h_bytes += live * fa::kRecBytes;
+    }
+    *n_out = (size_t)live;
+    return FA_OK;
+}
+
 int fa_evict_ex(fa_engine* e, const fa_evict_out* o, size_t cap, size_t* n_out) {
     if (n_out) *n_out = 0;
     if (!e || !n_out || !o) return fail(FA_E_INVAL, "fa_evict: null argument");
+    if (e->double_buffered) return evict_swapped(e, o, cap, n_out);
     void* out_records = o->records; void* out_dns = o->dns; void* out_additional = o->additional; uint8_t* out_present = o->present;
     std::lock_guard<std::mutex> lk(e->mu);
     CU(cudaSetDevice(e->device));

@@ -92,10 +92,12 @@ class FlowAggEngine:
         check(lib().fa_live_flows(self._h, C.byref(n)))
         return n.value
 
-    def evict(self, features=False):
-        """Lookup-and-delete all flows -> (n,144) uint8 array [, dns (n,64), additional (n,32), present (n,)]."""
-        n = self.live_flows()
-        cap = max(n, 1)
+    def evict(self, features=False, cap=None):
+        """Lookup-and-delete all flows -> (n,144) uint8 array [, dns (n,64), additional (n,32), present (n,)].
+        cap: output capacity in flows (default: the live count right now; pass max_entries when another thread keeps
+        ingesting, FA_F_NONBLOCKING_EVICT)."""
+        if cap is None:
+            cap = max(self.live_flows(), 1)
         out = np.zeros((cap, REC_BYTES), dtype=np.uint8)
         got = C.c_size_t(0)
         if features:

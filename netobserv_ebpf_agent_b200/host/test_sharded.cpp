@@ -23,7 +23,10 @@ int main(int argc, char** argv) {
     if (n_gpus <= 0 || n_gpus > ndev) n_gpus = ndev;
     const size_t n = argc > 2 ? strtoull(argv[2], nullptr, 0) : 3000000, n_keys = argc > 3 ? strtoull(argv[3], nullptr, 0) : 200000;
 
-    fa_gen_params gp{}; gp.seed = 4; gp.n_keys = n_keys; gp.dist = FA_GEN_ZIPF; gp.zipf_s_milli = 1100; gp.t0_ns = 1000; gp.varying_desc = 1;
+    fa_gen_params gp{}; gp.seed = 4; gp.n_keys = n_keys; gp.dist = FA_GEN_ZIPF; gp.zipf_s_milli = 1100; gp.t0_ns = 1000;
+    // per-flow constant descriptors: the order-dependent fields (first MAC, last dscp ...) follow ARRIVAL order at the owner,
+    // which across sources / CTAs is not stream order — like the reference's merge of per-CPU entries in CPU order
+    gp.varying_desc = 0;
     std::vector<fa_flow_record> recs(n);
     CHECK(fa_gen_records(nullptr, &gp, 0, n, recs.data()) == FA_OK);          // host instance of the generator
 

@@ -126,15 +126,7 @@ int launch_aggregate(const AggLaunch& a, cudaStream_t) {
     const bool dev_n = (a.opt & 16u) != 0;
     const uint4* recs = a.recs; const uint32_t n = a.n; Table t = a.table; const uint64_t epoch = a.epoch;
     Counters* ctr = a.ctr; uint32_t* spill = a.spill_idx; SketchParams sk = a.sk; const uint32_t opt = a.opt;
-    if (a.opt & 256u) {
-        const uint32_t n_sub = (n + kSSub - 1) / kSSub;
-        const unsigned g = small((n_sub + kSW - 1) / kSW, 3);
-        const size_t sm = sizeof(SWarp) * kSW;
-        if (sk.cms && dev_n) simt::launch(g, kSW * 32, sm, [=] { aggregate_stream_kernel<true, true>(recs, n, t, epoch, ctr, sk, opt); });
-        else if (sk.cms) simt::launch(g, kSW * 32, sm, [=] { aggregate_stream_kernel<true, false>(recs, n, t, epoch, ctr, sk, opt); });
-        else if (dev_n) simt::launch(g, kSW * 32, sm, [=] { aggregate_stream_kernel<false, true>(recs, n, t, epoch, ctr, sk, opt); });
-        else simt::launch(g, kSW * 32, sm, [=] { aggregate_stream_kernel<false, false>(recs, n, t, epoch, ctr, sk, opt); });
-    } else {
+    {
         const uint32_t n_tiles = (n + kTile - 1) / kTile;
         const unsigned g = small((n_tiles + kTeams - 1) / kTeams, 2);
         const size_t sm = sizeof(AggSmem);

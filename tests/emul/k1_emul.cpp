@@ -43,15 +43,6 @@ void run_k1(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt)
             aggregate_kernel<false, false, false>(recs, n, t, epoch, ctr, spill, sk, nullptr, opt);
         });
 }
-void run_k1s(Emul* e, const uint4* recs, uint32_t n, unsigned grid, uint32_t opt) {
-    const uint64_t epoch = e->epoch;
-    Table t = e->t; Counters* ctr = e->ctr;
-    SketchParams sk = e->sk;
-    if (sk.cms)
-        simt::launch(grid, kSW * 32, sizeof(SWarp) * kSW, [=] { aggregate_stream_kernel<true, false>(recs, n, t, epoch, ctr, sk, opt); });
-    else
-        simt::launch(grid, kSW * 32, sizeof(SWarp) * kSW, [=] { aggregate_stream_kernel<false, false>(recs, n, t, epoch, ctr, sk, opt); });
-}
 }  // namespace
 
 extern "C" {
@@ -88,11 +79,6 @@ int k1_emul_ingest(void* h, const uint8_t* recs8, uint32_t n, unsigned grid, int
     grid = std::min<unsigned>(grid, (n_tiles + kTeams - 1) / kTeams);
     switch (var) {
         case 0: run_k1(e, recs, n, grid, opt); break;
-        case 8: {                                           // K1s, the streaming kernel
-            const uint32_t n_sub = (n + kSSub - 1) / kSSub;
-            run_k1s(e, recs, n, std::min<unsigned>(grid, (n_sub + kSW - 1) / kSW), opt);
-            break;
-        }
         default: return -2;
     }
     Table t = e->t; Counters* ctr = e->ctr; FixupScratch* sc = e->scratch; const uint32_t ss = e->scratch_slots;

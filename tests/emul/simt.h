@@ -267,10 +267,6 @@ inline void st_cg_u4(uint4* p, uint4 v) {
     __atomic_store_n(q + 1, (unsigned long long)v.z | ((unsigned long long)v.w << 32), __ATOMIC_SEQ_CST);
 }
 inline uint4 ld_stream_u4(const uint4* p) { return *p; }
-// cp.async (LDGSTS): the copy happens at issue, commit / wait are no-ops
-inline void cp_async16(void* smem_dst, const void* gmem_src) { const uint4 v = ld_cg_u4(static_cast<const uint4*>(gmem_src)); memcpy(smem_dst, &v, 16); }
-inline void cp_async_commit() {}
-template <int kPending> inline void cp_async_wait() {}
 inline void red_add_u64(void* p, unsigned long long v) { __atomic_fetch_add(static_cast<unsigned long long*>(p), v, __ATOMIC_SEQ_CST); }
 inline void red_max_u64(void* p, unsigned long long v) { simt_atomic_max(static_cast<unsigned long long*>(p), v); }
 inline void red_min_u64(void* p, unsigned long long v) { simt_atomic_min(static_cast<unsigned long long*>(p), v); }
