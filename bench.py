@@ -289,6 +289,8 @@ def run_ours(args, wl):
         buf = batches[0] if nfl <= B else torch.empty(nfl * REC, dtype=torch.uint8, device=dev)
         got = eng.evict_into(buf.data_ptr(), max(nfl, 1)) if nfl else 0
         assert got == nfl, (got, nfl)
+        if agg is not None:
+            agg.reset_local()                        # the combiners' cached keys go with the owners' flows
         return buf, nfl
 
     def finish():                                    # N>1: drain + exchange the batch still in a scratch table
@@ -531,13 +533,126 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- BASELINE config 5: RTT + DNS tracker path
+def feature_samples(wl, n_dns, n_rtt, seed=5):
+    """Host-built feature samples over the workload's key universe: (n_dns,104) DNS responses and (n_rtt,72) RTT samples."""
+    import oracle_lib as O
+    g = oracle_gen(wl)
+    rng = np.random.default_rng(seed)
+    kd = g.records(1 << 42, n_dns, threads=min(16, host_threads()))[:, :40]
+    kr = g.records((1 << 42) + n_dns, n_rtt, threads=min(16, host_threads()))[:, :40]
+    g.close()
+    dns = np.zeros(n_dns, dtype=O.DNSREC_DTYPE)
+    dns["id"] = kd
+    d = dns["dns"]
+    ts = 1_000_000 + np.arange(n_dns, dtype=np.uint64)
+    d["start"], d["end"] = ts, ts
+    d["latency"] = rng.integers(50_000, 40_000_000, n_dns)
+    d["id"], d["flags"], d["eth"] = rng.integers(1, 1 << 16, n_dns), 0x8180, 0x0800
+    d["errno"] = np.where(rng.random(n_dns) < 0.02, 3, 0)
+    d["name"][:, :13] = np.frombuffer(b"\x03www\x07example", dtype=np.uint8)
+    dns["dns"] = d
+    add = np.zeros(n_rtt, dtype=O.ADDREC_DTYPE)
+    add["id"] = kr
+    a = add["add"]
+    tr = 1_000_000 + np.arange(n_rtt, dtype=np.uint64)
+    a["start"], a["end"], a["eth"] = tr, tr, 0x0800
+    a["rtt"] = rng.integers(20_000, 80_000_000, n_rtt)
+    add["add"] = a
+    return dns, add
+
+
+def run_rttdns(args):
+    """configs[4]: 70 % flow records, 30 % DNS responses (flow_id + dns_metrics, 104 B), one RTT sample (72 B) per 10
+    packets of the TCP flows (80 % of the flows): K1 + the K6 feature folds + merged eviction, 1 GPU."""
+    import torch
+    import netobserv_ebpf_agent_b200 as fa
+    import oracle_lib as O
+    wl = WORKLOADS["zipf10m"]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    B = min(args.batch, 1 << 25)
+    Bf = B * 7 // 10; Bd = B - Bf; Br = Bf * 8 // 100
+    mb = 1 << 22
+    eng = fa.FlowAggEngine(wl["max_entries"], device=0, max_batch=mb, cuda_stream=stream.cuda_stream,
+                           flags=fa.FA_F_ENABLE_RTT | fa.FA_F_ENABLE_DNS | fa.FA_F_NO_FULL_CUT)
+    gp = fa.GenParams(seed=wl["seed"], n_keys=wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0)
+    base = [torch.empty(Bf * REC, dtype=torch.uint8, device=dev) for _ in range(2)]
+    for i, t in enumerate(base):
+        eng.gen_records(gp, i * Bf, Bf, t)
+    nd, nr = min(Bd, 1 << 22), min(Br, 1 << 21)                       # sample arrays are cycled within a step
+    dns_h, add_h = feature_samples(wl, nd, nr)
+    dns_d = torch.from_numpy(dns_h.view(np.uint8).reshape(-1).copy()).to(dev)
+    add_d = torch.from_numpy(add_h.view(np.uint8).reshape(-1).copy()).to(dev)
+    eng.sync()
+
+    def feed(ptr, n_have, n_want, width, call):
+        done = 0
+        while done < n_want:
+            c = min(n_have, n_want - done, mb)
+            call(C.c_void_p(ptr), c)
+            done += c
+
+    import ctypes as C
+    L = fa.lib()
+
+    def step(i):
+        rc, took = eng.ingest(base[i % 2].data_ptr(), Bf)
+        assert rc == 0 and took == Bf
+        feed(dns_d.data_ptr(), nd, Bd, 104, lambda p, c: fa._lib.check(L.fa_ingest_dns(eng._h, p, c)))
+        feed(add_d.data_ptr(), nr, Br, 72, lambda p, c: fa._lib.check(L.fa_ingest_additional(eng._h, p, c)))
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    st0 = eng.stats()
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.window_begin(); e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(); torch.cuda.synchronize(); sampler.window_end()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    st1 = eng.stats()
+    # parity on a fresh prefix: engine vs the oracle's LookupAndDeleteMap view
+    out = eng.evict(features=True)
+    del out
+    V = 1 << 21
+    vb = fa.gen_records_host(gp, 1 << 40, V)
+    eng.ingest(vb); eng.ingest_dns(dns_h[: V // 4]); eng.ingest_additional(add_h[: V // 8])
+    g_recs, g_dns, g_add, g_pres = eng.evict(features=True)
+    om = O.FlowMap(); om.account(vb); om.fold_dns(dns_h[: V // 4]); om.fold_additional(add_h[: V // 8])
+    o_recs, o_dns, o_add, o_pres = om.evict()
+    gp_, op_ = O.sort_perm(g_recs), O.sort_perm(o_recs)
+    same = len(gp_) == len(op_) and all(np.array_equal(g[gp_], o[op_]) for g, o in ((g_recs, o_recs), (g_dns, o_dns), (g_add, o_add), (g_pres, o_pres)))
+    peak, peak_src = peaks()
+    bytes_step = Bf * REC + Bd * 104 + Br * 72
+    achieved = bytes_step * args.steps / (ms / 1e3) / 1e9
+    line = {"metric": "Mpkts/s aggregated", "value": (Bf + Bd + Br) * args.steps / (ms / 1e3) / 1e6, "unit": "Mpkts/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64/u32 integer (add/or/min/max); no floating point", "data": "synthetic",
+            "config": {"workload": "RTT+DNS tracker path (BASELINE configs[4]): 70% flow records, 30% DNS responses, 1 RTT sample per 10 "
+                                   "packets of the TCP flows; 10M Zipf-1.1 5-tuples", "workload_key": "rttdns",
+                       "flow_records_per_step": Bf, "dns_samples_per_step": Bd, "rtt_samples_per_step": Br,
+                       "l2_policy": f"inputs larger than L2 ({bytes_step / 1e6:.0f} MB per step)", "n_gpus": 1},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "K1 + K6 feature folds (dns_fold / additional_fold); blended algorithmic bytes = "
+                                                            "144 B per flow record + 104 B per DNS sample + 72 B per RTT sample"},
+            "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]), "clocks": clocks,
+            "parity_checked": int(len(op_)) if same else 0, "parity_ok": bool(same)}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="zipf10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="zipf10m", choices=sorted(WORKLOADS) + ["rttdns"])
     ap.add_argument("--batch", type=int, default=1 << 27,
                     help="records per step per GPU (2^27 x 144 B = 19.3 GB; 20 steps = a timed region of >= 200 ms)")
     ap.add_argument("--max-batch", type=int, default=1 << 22, help="records per K1 launch (N = 1)")
@@ -556,6 +671,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-events", action="store_true", help="skip the 64-byte packet-event row of e2e")
     args = ap.parse_args()
+    if args.workload == "rttdns":
+        return run_rttdns(args)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)

@@ -136,6 +136,17 @@ class ShardedAggregator:
         assert rc == 0 and took == tot, (rc, took)
         return tot
 
+    def reset_local(self):
+        """See PeerShardedAggregator.reset_local."""
+        import torch
+        self.flush()
+        for loc in self.locals:
+            live = loc.live_flows()
+            if live:
+                tmp = torch.empty(live * REC_BYTES, dtype=torch.uint8, device=self.send.device)
+                loc.evict_into(tmp, live)
+                del tmp
+
     def close(self):
         for l in self.locals:
             l.close()
@@ -242,6 +253,17 @@ class PeerShardedAggregator:
         if spills:                                   # a scratch / owner table that is physically full drops records
             raise RuntimeError(f"{spills} records found a flow table physically full (raise max_entries / evict more often)")
         return 0
+
+    def reset_local(self):
+        """To be called whenever the owner tables are evicted: the combiner's scratch table caches keys WITH their start
+        mirror, so a flow that outlives its owner-side eviction would send partials without a start ("already covered").
+        Lookup-and-delete of the scratch table, output discarded."""
+        import torch
+        live = self.local.live_flows()
+        if live:
+            tmp = torch.empty(live * REC_BYTES, dtype=torch.uint8, device=self.part.device)
+            self.local.evict_into(tmp, live)
+            del tmp
 
     def exchange_stats(self):
         """What crossed NVLink so far: records this rank stored into other GPUs' receive buffers (x 144 B)."""

@@ -132,6 +132,7 @@ class FakeAgg:
     def ingest(self, records, n):
         self.eng.ingest(records if isinstance(records, int) else records.data_ptr(), n); return 0
     def flush(self): return 0
+    def reset_local(self): pass
     def exchange_stats(self): return {"nvlink_bytes_per_step_rank0": 0}
     def close(self): pass
 

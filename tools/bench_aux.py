@@ -79,7 +79,7 @@ def feature_bench(n_keys=1_000_000, B=1 << 22, steps=8):
 
 
 def kmap_bench(n_keys=1_000_000, B=1 << 24, steps=12):
-    """KERNEL_MAP mode (kmap.cu: 7 passes per batch) on the headline workload's stream; needs FA_EXPERIMENTAL_KERNEL_MAP=1."""
+    """KERNEL_MAP mode (kmap.cu) on a 1 M-key Zipf stream."""
     eng = fa.FlowAggEngine(1 << 24, mode=fa.FA_MODE_KERNEL_MAP, max_batch=B, cuda_stream=stream.cuda_stream)
     gp = fa.GenParams(seed=2, n_keys=n_keys, dist=1, zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0)
     ring = []
@@ -127,8 +127,39 @@ def small_cache_bench(max_entries=5000, n_keys=1_000_000, B=1 << 22, steps=3):
     eng.close()
 
 
+def pb_bench(n_keys=4_000_000, B=1 << 23):
+    """K8: evicted flows (device memory) -> pbflow.Record wire bytes (device memory): sizes + scan + write kernels."""
+    import ctypes as C
+    from netobserv_ebpf_agent_b200._lib import PbParams
+    eng = fa.FlowAggEngine(1 << 23, flags=fa.FA_F_NO_FULL_CUT, max_batch=1 << 22, cuda_stream=stream.cuda_stream)
+    gp = fa.GenParams(seed=6, n_keys=n_keys, dist=0, zipf_s_milli=1100, t0_ns=1_000_000, varying_desc=0)
+    src = torch.empty(B * REC, dtype=torch.uint8, device=dev)
+    eng.gen_records(gp, 0, B, src)
+    eng.ingest(src.data_ptr(), B)
+    n = eng.live_flows()
+    flows = torch.empty(n * REC, dtype=torch.uint8, device=dev)
+    assert eng.evict_into(flows, n) == n
+    p = PbParams(now_unix_ns=1_700_000_000_123_456_789, mono_now_ns=5_000_000_000_000, agent_ip_is_v4=1)
+    for i, b in enumerate(bytes(10) + b"\xff\xff" + bytes([10, 1, 2, 3])):
+        p.agent_ip[i] = b
+    ln = C.c_size_t(0)
+    L = fa.lib()
+    out = torch.empty(n * 200, dtype=torch.uint8, device=dev)
+    keys = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+
+    def run(_):
+        rc = L.fa_pb_encode(eng._h, C.c_void_p(flows.data_ptr()), None, None, None, None, n, C.byref(p), C.c_void_p(out.data_ptr()),
+                            out.numel(), None, C.c_void_p(keys.data_ptr()), C.byref(ln))
+        assert rc == 0, rc
+    run(0)
+    dt = timed(run, 5) / 5
+    print(json.dumps({"bench": "K8 pbflow encode (device in, device out)", "flows": n, "wire_bytes": ln.value, "bytes_per_flow": ln.value / n,
+                      "Mflows_s": n / dt / 1e6, "GB_s_in_plus_out": (n * REC + ln.value + n * 32) / dt / 1e9}), flush=True)
+    eng.close()
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sketch", "features"] + (["kmap"] if os.environ.get("FA_EXPERIMENTAL_KERNEL_MAP") == "1" else [])
+    which = sys.argv[1:] or ["sketch", "features", "kmap"]
     if "sketch" in which:
         sketch_bench()
     if "features" in which:
@@ -137,3 +168,6 @@ if __name__ == "__main__":
         kmap_bench()
     if "smallcache" in which:
         small_cache_bench()
+        small_cache_bench(max_entries=100_000)
+    if "pb" in which:
+        pb_bench()
