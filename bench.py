@@ -271,7 +271,11 @@ def run_ours(args, wl):
         from netobserv_ebpf_agent_b200.sharded import PeerShardedAggregator, ShardedAggregator
         if args.exchange == "peer":
             # local combine (K1+K2) -> K3 fused with the exchange (peer stores over NVLink) -> K1 on the owner
-            agg = PeerShardedAggregator(eng, max_batch, dev)
+            # the combiner's scratch table holds one round's distinct flows: never more than the key universe
+            k = 0
+            while (3 << k) < wl["n_keys"]:
+                k += 1
+            agg = PeerShardedAggregator(eng, max_batch, dev, local_entries=min(2 * max_batch, 3 << k), profile=True)
         else:
             # local combine (K1+K2) -> K3 route -> NCCL all-to-all -> K1 on the owner
             agg = ShardedAggregator(eng, max_batch, dev, combine=not args.no_combine)
@@ -343,6 +347,9 @@ def run_ours(args, wl):
     launches = st1["kernel_launches"] - st0["kernel_launches"]
     flows = eng.live_flows()
     nvlink = agg.exchange_stats() if (world > 1 and hasattr(agg, "exchange_stats")) else None
+    if nvlink is not None and getattr(agg, "profile", False):
+        rounds_timed = args.steps * ((B + max_batch - 1) // max_batch)
+        nvlink["phase_ms_per_round_rank0"] = {k_: round(v, 4) for k_, v in agg.phase_ms(rounds_timed).items()}
 
     # ---------------------------------------------------------------- parity: the engine against the CPU oracle
     # Fresh state, then records [V0, V0+V) of the same stream through the same engine / aggregator, evict, compare
@@ -655,7 +662,7 @@ def main():
     ap.add_argument("--workload", default="zipf10m", choices=sorted(WORKLOADS) + ["rttdns"])
     ap.add_argument("--batch", type=int, default=1 << 27,
                     help="records per step per GPU (2^27 x 144 B = 19.3 GB; 20 steps = a timed region of >= 200 ms)")
-    ap.add_argument("--max-batch", type=int, default=1 << 22, help="records per K1 launch (N = 1)")
+    ap.add_argument("--max-batch", type=int, default=1 << 23, help="records per K1 launch (N = 1)")
     ap.add_argument("--mgpu-round", type=int, default=1 << 24, help="N>1: records per combine -> exchange -> fold round")
     ap.add_argument("--ring", type=int, default=2, help="distinct pre-generated input batches cycled through")
     ap.add_argument("--e2e-batch", type=int, default=1 << 22)

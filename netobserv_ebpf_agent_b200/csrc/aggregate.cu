@@ -39,25 +39,24 @@ constexpr int kTeams     = 1024 / kTile;        // teams per CTA (one CTA per SM
 constexpr int kCtaThreads = kTile * kTeams;
 constexpr int kRepSlots  = 2 * kTile;
 constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
-constexpr int kHotEntries = 64;                 // CTA-wide cache of hot flows
+constexpr int kHotEntries = 96;                 // 64 primary entries + 32 second-chance entries (another slice of the hash)
 constexpr uint32_t kHotMinDups = 2;             // a flow with >= 3 records in one tile becomes a cache candidate
 constexpr uint32_t kRepEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kResSpill = 0xFFFFFFFFu;
 constexpr uint32_t kProbeLimit = 8192;
 
-struct __align__(128) TeamSmem {                  // 51,984 B per team
+struct __align__(128) TeamSmem {                  // 52,992 B per team
     uint4    tile[kTile * kRecChunks];            // 36,864 B  one TMA-staged tile of records
     uint32_t acc[kTile][8];                       //  8,192 B  what duplicates add to their representative
     uint32_t hs[kTile];                           //  1,024 B  low 32 bits of the slot hash
-    uint32_t res[kTile];                          //  1,024 B  table slot found for each representative
-    uint32_t mir_lo[kTile];                       //  1,024 B  start mirror of the flow found (see common.cuh)
+    uint4    res4[kTile];                         //  4,096 B  per representative: table slot | mirror lo | flags seen + mirror hi | -
     uint32_t rep[kRepSlots];                      //  2,048 B  tile-local key -> representative index
-    uint16_t mir_hi[kTile];                       //    512 B
-    uint16_t fseen[kTile];                        //    512 B  tcp flags already present in the flow's hot line
     uint8_t  tdirty[kTile];                       //    256 B  set by duplicates whose descriptor differs
     uint8_t  glist[kTile];                        //    256 B  team-wide compacted list of representatives
     uint8_t  slow[kTile / 32][32];                //    256 B  per-warp flows that need the general probe loop
-    unsigned long long full_bar;
+};
+struct __align__(16) TeamCtl {                    // kept outside TeamSmem so that four teams + the cache fit in 227 KB
+    unsigned long long full_bar;                  // mbarrier of the team's tile
     uint32_t nrep, next_chunk;
 };
 struct __align__(16) HotEntry {                   // 208 B: a stride of 52 words keeps 8 entries on distinct banks
@@ -70,20 +69,23 @@ struct __align__(16) HotEntry {                   // 208 B: a stride of 52 words
     uint32_t pad[7];
 };
 static_assert(sizeof(HotEntry) == 208, "HotEntry stride");
-struct __align__(128) AggSmem {                   // 220,240 B of the 227 KB an sm_100 CTA may use
+static_assert(kTile != 256 || sizeof(TeamSmem) == 52992, "TeamSmem has no padding to spare");
+struct __align__(128) AggSmem {                   // 232,064 B of the 232,448 B (227 KB) an sm_100 CTA may use
     TeamSmem team[kTeams];
     HotEntry hot[kHotEntries];
+    TeamCtl  ctl[kTeams];
     uint32_t n_insert, n_spill, any_dirty, pad;
 };
+static_assert(sizeof(AggSmem) <= 232448, "K1 shared memory exceeds what one sm_100 CTA can opt into");
 
 __device__ __forceinline__ void team_sync(int team) { named_barrier_sync(team + 1, kTile); }
 
-__device__ __forceinline__ void issue_tile_load(TeamSmem& s, const uint4* recs, uint32_t n, uint32_t tile_idx) {
+__device__ __forceinline__ void issue_tile_load(TeamSmem& s, TeamCtl& tc, const uint4* recs, uint32_t n, uint32_t tile_idx) {
     const uint32_t first = tile_idx * kTile;
     const uint32_t cnt = min((uint32_t)kTile, n - first);
     const uint32_t bytes = cnt * kRecBytes;
-    mbar_expect_tx(&s.full_bar, bytes);
-    tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &s.full_bar);
+    mbar_expect_tx(&tc.full_bar, bytes);
+    tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &tc.full_bar);
 }
 
 // Reductions of one flow's folded totals onto its hot line.  floor_ns <= hot.nstart always
@@ -205,6 +207,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     const int team = threadIdx.x / kTile;
     const int tid = threadIdx.x & (kTile - 1), lane = tid & 31, warp = tid >> 5;     // within the team
     TeamSmem& s = cs.team[team];
+    TeamCtl& tc = cs.ctl[team];
     if (kDevN) n = min(n, (uint32_t)ctr->launch_n);            // size known on the device only (multi-GPU receive side)
     const uint32_t n_tiles = (n + kTile - 1) / kTile;
     const uint32_t tile_stride = gridDim.x * kTeams;
@@ -214,16 +217,16 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     if (threadIdx.x == 0) { cs.n_insert = 0; cs.n_spill = 0; cs.any_dirty = 0; }
     if (threadIdx.x < kHotEntries) cs.hot[threadIdx.x].state = 0;
     if (tid == 0) {
-        mbar_init(&s.full_bar, 1);
+        mbar_init(&tc.full_bar, 1);
         fence_barrier_init();
-        s.nrep = 0; s.next_chunk = 0;
+        tc.nrep = 0; tc.next_chunk = 0;
     }
     s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;
     *reinterpret_cast<uint4*>(&s.acc[tid][0]) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(&s.acc[tid][4]) = make_uint4(0, 0, 0, 0);
     s.tdirty[tid] = 0;
     __syncthreads();
-    if (tid == 0 && tile0 < n_tiles) issue_tile_load(s, recs, n, tile0);
+    if (tid == 0 && tile0 < n_tiles) issue_tile_load(s, tc, recs, n, tile0);
 
     const int g = lane >> 3;                  // flow group inside the warp (4 groups of 8 lanes)
     const int j = lane & 7;                   // 16-byte chunk of the identity line handled by this lane
@@ -242,7 +245,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         if (tile_idx >= n_tiles) break;
         const uint32_t first = tile_idx * kTile;
         const uint32_t cnt = min((uint32_t)kTile, n - first);
-        mbar_wait(&s.full_bar, it & 1u);
+        mbar_wait(&tc.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
         if ((opt & 32u) && tid == 0) {                             // experiment: have L2 fetch the team's next tile now (no gain measured)
             const uint32_t nt = tile_idx + tile_stride;
@@ -260,7 +263,10 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                                                         u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)));
                 s.hs[tid] = (uint32_t)h;
                 // ---- hot-flow cache: an exact 114-byte match folds the record on-chip, no table traffic
-                HotEntry& ce = cs.hot[((uint32_t)h >> 26) & (kHotEntries - 1)];
+                uint32_t cidx = (uint32_t)h >> 26;                        // primary way
+                if (!(*reinterpret_cast<volatile uint32_t*>(&cs.hot[cidx].state) == 2u && cs.hot[cidx].hash == (uint32_t)h))
+                    cidx = 64u + (((uint32_t)h >> 21) & 31u);              // second chance
+                HotEntry& ce = cs.hot[cidx];
                 if (use_cache && *reinterpret_cast<volatile uint32_t*>(&ce.state) == 2u && ce.hash == (uint32_t)h) {
                     const uint4 r3 = R[3], r4 = R[4];
                     bool same = eq4_masked(ce.line[0], r0, chunk_mask(0)) && eq4_masked(ce.line[1], r1, chunk_mask(1)) &&
@@ -333,7 +339,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             // team-wide list of representatives, so that every warp probes an equal share
             const uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_rep);
             uint32_t lbase = 0;
-            if (lane == 0 && pending) lbase = atomicAdd(&s.nrep, (uint32_t)__popc(pending));
+            if (lane == 0 && pending) lbase = atomicAdd(&tc.nrep, (uint32_t)__popc(pending));
             lbase = __shfl_sync(0xFFFFFFFFu, lbase, 0);
             if (is_rep) s.glist[lbase + __popc(pending & lt_mask)] = (uint8_t)tid;
         }
@@ -341,14 +347,14 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         team_sync(team);                                           // S1: folds, hashes and the list are complete
         FA_PROF_MARK(2);                                           // S1 wait
 
-        const uint32_t nrep_total = s.nrep;
+        const uint32_t nrep_total = tc.nrep;
         s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;   // nobody reads the election table after S1
 
         // ------------------------------------------------------ probe: warps pull chunks of 16 flows (dynamic
         // balancing: a warp stuck behind a DRAM miss or an insert simply takes fewer chunks)
         for (;;) {
             uint32_t c0 = 0;
-            if (lane == 0) c0 = atomicAdd(&s.next_chunk, 4u * kInflight);
+            if (lane == 0) c0 = atomicAdd(&tc.next_chunk, 4u * kInflight);
             c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
             if (c0 >= nrep_total) break;
             const uint32_t c_end = min(nrep_total, c0 + 4u * kInflight);
@@ -388,10 +394,11 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                     const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq) >> (g * 8)) & 0xFFu;
                     const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g * 8 + 2)) & 1u;
                     const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches
-                    if (fast && j == 0) s.res[ridx[r]] = slot[r];
-                    if (fast && j == 3) { s.mir_lo[ridx[r]] = line[r].x; s.mir_hi[ridx[r]] = (uint16_t)(line[r].y >> 16); }
+                    uint32_t* const rw = reinterpret_cast<uint32_t*>(&s.res4[ridx[r]]);       // one address for the group's stores
+                    if (fast && j == 0) rw[0] = slot[r];
+                    if (fast && j == 3) { rw[1] = line[r].x; reinterpret_cast<uint16_t*>(rw + 2)[1] = (uint16_t)(line[r].y >> 16); }
                     if (fast && j == 2) {
-                        s.fseen[ridx[r]] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
+                        reinterpret_cast<uint16_t*>(rw + 2)[0] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
                         if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[r]] != 0) {
                             unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
                             if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
@@ -429,9 +436,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
                 const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0,
                                                    dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &cs.any_dirty);
-                if (act && j == 0) s.res[ri] = got;
-                if (act && j == 2) s.fseen[ri] = 0;                 // unknown: issue every reduction
-                if (act && j == 3) { s.mir_lo[ri] = 0; s.mir_hi[ri] = 0; }
+                if (act && j == 0) s.res4[ri] = make_uint4(got, 0u, 0u, 0u);   // mirror / seen flags unknown: issue every reduction
             }
             __syncwarp();
             FA_PROF_MARK(4);                                       // general probe loop
@@ -439,9 +444,10 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             // -------------------------------------------------- one lane per flow: totals, then the reductions
             if (c0 + lane < c_end) {
                 const uint32_t my_ridx = s.glist[c0 + lane];
-                const uint32_t my_slot = s.res[my_ridx];
-                const uint64_t floor_ns = u64_of(s.mir_lo[my_ridx], s.mir_hi[my_ridx]) << 16;   // <= hot.nstart, always
-                const uint32_t seen = s.fseen[my_ridx];
+                const uint4 rr = s.res4[my_ridx];
+                const uint32_t my_slot = rr.x;
+                const uint64_t floor_ns = u64_of(rr.y, rr.z >> 16) << 16;                      // <= hot.nstart, always
+                const uint32_t seen = rr.z & 0xFFFFu;
                 const uint4* R = T + my_ridx * kRecChunks;
                 const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
                 const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
@@ -460,7 +466,9 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 // a flow that shows up several times in one tile is hot: give it a cache entry if one is free
                 if (use_cache && a1.z >= kHotMinDups && my_slot != kResSpill) {
                     const uint32_t hh = s.hs[my_ridx];
-                    HotEntry& ce = cs.hot[(hh >> 26) & (kHotEntries - 1)];
+                    uint32_t iidx = hh >> 26;
+                    if (*reinterpret_cast<volatile uint32_t*>(&cs.hot[iidx].state) != 0u && cs.hot[iidx].hash != hh) iidx = 64u + ((hh >> 21) & 31u);
+                    HotEntry& ce = cs.hot[iidx];
                     if (*reinterpret_cast<volatile uint32_t*>(&ce.state) == 0u && atomicCAS(&ce.state, 0u, 1u) == 0u) {
 #pragma unroll
                         for (int c = 0; c < 8; c++) ce.line[c] = ld_cg_u4(&t.ident[(size_t)my_slot * 8 + c]);
@@ -489,9 +497,9 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         team_sync(team);                                           // S2: nobody reads the tile buffer any more
         FA_PROF_MARK(6);                                           // S2 wait
         if (tid == 0) {
-            s.nrep = 0; s.next_chunk = 0;
+            tc.nrep = 0; tc.next_chunk = 0;
             const uint32_t nt = tile_idx + tile_stride;
-            if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, recs, n, nt); }
+            if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, tc, recs, n, nt); }
         }
         FA_PROF_MARK(7);                                           // reductions
     }

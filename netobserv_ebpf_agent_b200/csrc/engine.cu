@@ -136,7 +136,6 @@ struct fa_engine {
     uint32_t* d_cut_set = nullptr; uint32_t cut_set_slots = 0;
     uint32_t* d_cut_bitmap = nullptr; uint32_t* d_cut_out = nullptr; uint32_t* h_cut_out = nullptr;
 
-    uint8_t* d_events = nullptr;              // fa_ingest_events: raw 64-byte events of one chunk
     uint8_t* d_expanded = nullptr;            // ... and their 144-byte expansion (events handed in as device memory)
     uint8_t* d_evict = nullptr; uint64_t evict_cap = 0;
     uint8_t* d_evict_dns = nullptr; uint8_t* d_evict_add = nullptr; uint8_t* d_evict_present = nullptr;
@@ -359,11 +358,42 @@ int ingest_device(fa_engine* e, const uint8_t* d_recs, size_t n, size_t* consume
     return FA_OK;
 }
 
+// Host data reaches the device through two staging buffers of stage_records() records: the copy of chunk k+1 (copy
+// stream) overlaps the kernels of chunk k (engine stream).  The staging grain is independent of max_batch, the K1
+// launch size for device-resident input: a large launch amortises K1's start-up, a small stage keeps the pipeline fine.
+static uint64_t stage_records(const fa_engine* e) { return std::min<uint64_t>(e->max_batch, 1ull << 22); }
+
+static int stage_alloc(fa_engine* e, bool pageable) {
+    for (int i = 0; i < 2; i++) {
+        if (!e->d_stage[i]) CU(cudaMalloc(&e->d_stage[i], stage_records(e) * fa::kRecBytes));
+        if (pageable && !e->h_stage[i]) CU(cudaHostAlloc(&e->h_stage[i], stage_records(e) * fa::kRecBytes, cudaHostAllocDefault));
+    }
+    return FA_OK;
+}
+
+// Copy `bytes` of host data into the next staging buffer; the engine stream waits for the copy.  -> *sidx for stage_release.
+static int stage_copy(fa_engine* e, const uint8_t* src, size_t bytes, bool pinned, int* sidx_out) {
+    const int sidx = e->stage_cur; e->stage_cur ^= 1;
+    CU(cudaEventSynchronize(e->ev_stage_free[sidx]));                // previous consumer of this stage is done
+    if (!pinned) { memcpy(e->h_stage[sidx], src, bytes); src = e->h_stage[sidx]; }
+    CU(cudaMemcpyAsync(e->d_stage[sidx], src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    CU(cudaEventRecord(e->ev_copied[sidx], e->copy_stream));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_copied[sidx], 0));
+    e->st.h2d_bytes += bytes;
+    *sidx_out = sidx;
+    return FA_OK;
+}
+
+static int stage_release(fa_engine* e, int sidx) {                   // the kernels enqueued so far were the stage's last readers
+    CU(cudaEventRecord(e->ev_stage_free[sidx], e->stream));
+    return FA_OK;
+}
+
 int ingest_host(fa_engine* e, const uint8_t* h_recs, size_t n, size_t* consumed, bool pinned) {
     size_t done = 0;
     int rc = FA_OK;
     while (done < n) {
-        uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
+        uint32_t c = (uint32_t)std::min<size_t>(n - done, stage_records(e));
         if (e->cfg.mode == FA_MODE_ACCOUNTER && !(e->cfg.flags & FA_F_NO_FULL_CUT)) {
             // A cache that is about to fill cuts the chunk after roughly `room` new keys: stage a window proportional
             // to the room left, so that a "full" return does not leave most of a copied chunk unused (the caller
@@ -373,15 +403,8 @@ int ingest_host(fa_engine* e, const uint8_t* h_recs, size_t n, size_t* consumed,
             const uint64_t room = e->cfg.max_entries > used ? e->cfg.max_entries - used : 0;
             if (room < c) c = (uint32_t)std::min<uint64_t>(c, std::max<uint64_t>(4096, 4 * room));
         }
-        const int sidx = e->stage_cur; e->stage_cur ^= 1;
-        CU(cudaEventSynchronize(e->ev_stage_free[sidx]));            // previous consumer of this stage is done
-        const size_t bytes = (size_t)c * fa::kRecBytes;
-        const uint8_t* src = h_recs + done * fa::kRecBytes;
-        if (!pinned) { memcpy(e->h_stage[sidx], src, bytes); src = e->h_stage[sidx]; }
-        CU(cudaMemcpyAsync(e->d_stage[sidx], src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
-        CU(cudaEventRecord(e->ev_copied[sidx], e->copy_stream));
-        CU(cudaStreamWaitEvent(e->stream, e->ev_copied[sidx], 0));
-        e->st.h2d_bytes += bytes;
+        int sidx = 0;
+        if (int src_rc = stage_copy(e, h_recs + done * fa::kRecBytes, (size_t)c * fa::kRecBytes, pinned, &sidx)) return src_rc;
         uint32_t off = 0;                                            // a chunk may be folded in several windows
         while (off < c) {
             uint32_t took = 0;
@@ -389,7 +412,7 @@ int ingest_host(fa_engine* e, const uint8_t* h_recs, size_t n, size_t* consumed,
             off += took;
             if (rc != FA_OK) break;
         }
-        CU(cudaEventRecord(e->ev_stage_free[sidx], e->stream));
+        if (int rel_rc = stage_release(e, sidx)) return rel_rc;
         done += off;
         if (rc != FA_OK) break;
     }
@@ -598,7 +621,7 @@ void fa_destroy(fa_engine* e) {
     }
     cudaFree(e->d_scratch); cudaFree(e->d_spill_idx); cudaFree(e->d_cut_set); cudaFree(e->d_cut_bitmap); cudaFree(e->d_cut_out);
     if (e->h_cut_out) cudaFreeHost(e->h_cut_out);
-    cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts); cudaFree(e->d_events); cudaFree(e->d_expanded);
+    cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts); cudaFree(e->d_expanded);
     cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out); cudaFree(e->d_slot_of);
     cudaFree(e->d_evict_drop); cudaFree(e->d_evict_rttmin);
     cudaFree(e->sk.cms); cudaFree(e->sk.hll);
@@ -622,10 +645,7 @@ int fa_ingest(fa_engine* e, const void* recs, size_t n, size_t* consumed) {
         if (reinterpret_cast<uintptr_t>(recs) & 15) return fail(FA_E_INVAL, "fa_ingest: device records must be 16-byte aligned");
         return ingest_device(e, static_cast<const uint8_t*>(recs), n, consumed);
     }
-    for (int i = 0; i < 2; i++) {
-        if (!e->d_stage[i]) CU(cudaMalloc(&e->d_stage[i], e->max_batch * fa::kRecBytes));
-        if (k == PTR_PAGEABLE && !e->h_stage[i]) CU(cudaHostAlloc(&e->h_stage[i], e->max_batch * fa::kRecBytes, cudaHostAllocDefault));
-    }
+    if (int rc = stage_alloc(e, k == PTR_PAGEABLE)) return rc;
     return ingest_host(e, static_cast<const uint8_t*>(recs), n, consumed, k == PTR_PINNED);
 }
 
@@ -640,11 +660,11 @@ int fa_ingest_events(fa_engine* e, const void* events, size_t n, size_t* consume
     const PtrKind k = classify(events);
     if (k == PTR_DEVICE && (reinterpret_cast<uintptr_t>(events) & 15)) return fail(FA_E_INVAL, "fa_ingest_events: device events must be 16-byte aligned");
     if (!e->d_expanded) CU(cudaMalloc(&e->d_expanded, e->max_batch * fa::kRecBytes));
-    if (k != PTR_DEVICE && !e->d_events) CU(cudaMalloc(&e->d_events, e->max_batch * 64));
+    if (k != PTR_DEVICE) { if (int arc = stage_alloc(e, k == PTR_PAGEABLE)) return arc; }
     size_t done = 0;
     int rc = FA_OK;
     while (done < n) {
-        uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
+        uint32_t c = (uint32_t)std::min<size_t>(n - done, k == PTR_DEVICE ? e->max_batch : stage_records(e));
         if (e->cfg.mode == FA_MODE_ACCOUNTER && !(e->cfg.flags & FA_F_NO_FULL_CUT)) {     // see ingest_host: stage by the room left
             retire_completed(e);
             const uint64_t used = e->live_known + e->unsynced_records;
@@ -653,14 +673,16 @@ int fa_ingest_events(fa_engine* e, const void* events, size_t n, size_t* consume
         }
         const uint8_t* src = static_cast<const uint8_t*>(events) + done * 64;
         const uint8_t* d_ev = src;
-        // the previous chunk's kernels read d_expanded / d_events: everything here is ordered on the engine's stream
+        // host events: staged like fa_ingest's records (the copy of the next chunk overlaps this chunk's kernels); the
+        // expansion and K1 of successive chunks are ordered on the engine's stream, so one d_expanded is enough
+        int sidx = -1;
         if (k != PTR_DEVICE) {
-            CU(cudaMemcpyAsync(e->d_events, src, (size_t)c * 64, cudaMemcpyHostToDevice, e->stream));
-            e->st.h2d_bytes += (size_t)c * 64;
-            d_ev = e->d_events;
+            if (int src_rc = stage_copy(e, src, (size_t)c * 64, k == PTR_PINNED, &sidx)) return src_rc;
+            d_ev = e->d_stage[sidx];
         }
         e->st.kernel_launches += fa::launch_expand_events(reinterpret_cast<const uint4*>(d_ev), c, reinterpret_cast<uint4*>(e->d_expanded), e->stream);
         CU(cudaGetLastError());
+        if (sidx >= 0) { if (int rel_rc = stage_release(e, sidx)) return rel_rc; }
         uint32_t off = 0;
         while (off < c) {                                   // a chunk may be folded in several windows ("full" cuts)
             uint32_t took = 0;
@@ -671,7 +693,7 @@ int fa_ingest_events(fa_engine* e, const void* events, size_t n, size_t* consume
         done += off;
         if (rc != FA_OK) break;
     }
-    if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->stream));   // the caller's buffer must not be referenced after return
+    if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->copy_stream));   // the caller's buffer must not be referenced after return
     if (consumed) *consumed = done;
     return rc;
 }
@@ -693,17 +715,16 @@ static int ingest_feature(fa_engine* e, int kind, const void* recs, size_t n, co
     if (e->live_known + n > e->slots - e->slots / 8)
         return fail(FA_E_2BIG, "%s: %zu samples could overfill the flow table (%llu live of %llu slots): evict first", who, n,
                     (unsigned long long)e->live_known, (unsigned long long)e->slots);
-    if (k != PTR_DEVICE && !e->d_stage[0]) CU(cudaMalloc(&e->d_stage[0], e->max_batch * fa::kRecBytes));
+    if (k != PTR_DEVICE) { if (int arc = stage_alloc(e, k == PTR_PAGEABLE)) return arc; }
     size_t done = 0;
     while (done < n) {
-        const uint32_t c = (uint32_t)std::min<size_t>(n - done, e->max_batch);
+        const uint32_t c = (uint32_t)std::min<size_t>(n - done, k == PTR_DEVICE ? e->max_batch : stage_records(e));
         const uint8_t* src = static_cast<const uint8_t*>(recs) + done * rec_bytes;
         const uint8_t* d = src;
+        int sidx = -1;
         if (k != PTR_DEVICE) {
-            CU(cudaMemcpyAsync(e->d_stage[0], src, (size_t)c * rec_bytes, cudaMemcpyHostToDevice, e->stream));
-            CU(cudaStreamSynchronize(e->stream));          // the caller's buffer is not referenced after return
-            e->st.h2d_bytes += (size_t)c * rec_bytes;
-            d = e->d_stage[0];
+            if (int src_rc = stage_copy(e, src, (size_t)c * rec_bytes, k == PTR_PINNED, &sidx)) return src_rc;
+            d = e->d_stage[sidx];
         }
         e->st.kernel_launches += fa::launch_feature_fold(kind, d, c, e->table, ++e->epoch, e->feat_seq[kind], e->d_slot_of,
                                                          e->d_ctr, e->sm_count, e->stream);
@@ -711,9 +732,10 @@ static int ingest_feature(fa_engine* e, int kind, const void* recs, size_t n, co
         e->feat_seq[kind] += c;
         e->unsynced_records += c;
         if (kind == 0) e->st.additional_ingested += c; else if (kind == 1) e->st.dns_ingested += c; else e->st.pkt_drops_ingested += c;
-        if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->stream));   // d_stage[0] is reused by the next chunk
+        if (sidx >= 0) { if (int rel_rc = stage_release(e, sidx)) return rel_rc; }
         done += c;
     }
+    if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->copy_stream));   // the caller's buffer is not referenced after return
     return FA_OK;
 }
 

@@ -164,7 +164,10 @@ class PeerShardedAggregator:
       (`fa_ingest_counted`, count read from its own device memory) and re-arms the buffer.
     Receive buffers are double-buffered so that batch k+1 may be delivered while batch k is being folded."""
 
-    def __init__(self, engine, max_batch, device, recv_cap=None):
+    def __init__(self, engine, max_batch, device, recv_cap=None, local_entries=None, profile=False):
+        """`local_entries` sizes the combiner's scratch table: it has to hold the DISTINCT flows of one round (default:
+        2 x max_batch, enough for any round; a smaller table that overflows makes flush() raise).  `profile` brackets
+        the phases of every round with CUDA events (no synchronisation), read back by exchange_stats()."""
         import torch
         import torch.distributed as dist
         from ._lib import FA_F_NO_FULL_CUT, check
@@ -173,7 +176,8 @@ class PeerShardedAggregator:
         self.eng, self.max_batch = engine, max_batch
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.recv_cap = recv_cap or max_batch
-        self.local = FlowAggEngine(2 * max_batch, device=device.index, max_batch=max_batch, flags=FA_F_NO_FULL_CUT,
+        self.profile, self._ev = profile, []
+        self.local = FlowAggEngine(local_entries or 2 * max_batch, device=device.index, max_batch=max_batch, flags=FA_F_NO_FULL_CUT,
                                    cuda_stream=torch.cuda.current_stream().cuda_stream)
         self.part = torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device)
         self.part_n = torch.zeros(1, dtype=torch.int64, device=device)
@@ -222,19 +226,46 @@ class PeerShardedAggregator:
         while done < n:
             c = min(self.max_batch, n - done)
             b = self.step & 1
+            mark = self._mark if self.profile else (lambda: None)
+            mark()
             rc, took = self.local.ingest(base + done * REC_BYTES, c)
             assert rc == 0 and took == c, (rc, took)
+            mark()
             check(L.fa_drain_active_counted(self.local._h, C.c_void_p(self.part.data_ptr()), self.max_batch,
                                             C.c_void_p(self.part_n.data_ptr())))
+            mark()
             check(L.fa_route_peer(self.eng._h, C.c_void_p(self.part.data_ptr()), C.c_void_p(self.part_n.data_ptr()),
                                   self.max_batch, self.world, self.rank, self.bufs[b], self.cnts[b], self.recv_cap,
                                   C.c_void_p(self.overflow)))
+            mark()
             dist.all_reduce(self.token)                    # stream-ordered barrier: every rank has delivered batch `step`
+            mark()
             check(L.fa_ingest_counted(self.eng._h, C.c_void_p(self.mine[b][0]), C.c_void_p(self.mine[b][1]),
                                       self.recv_cap, 1))
+            mark()
             self.step += 1
             done += c
         return 0
+
+    def _mark(self):
+        import torch
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self._ev.append(e)
+
+    def phase_ms(self, last_rounds=None):
+        """Mean milliseconds per round of (combine K1, drain K2, route K3 + peer stores, barrier, owner fold K1) over the
+        profiled rounds (the last `last_rounds` of them); the stream must be idle."""
+        import torch
+        torch.cuda.current_stream().synchronize()
+        ev = self._ev[-6 * last_rounds:] if last_rounds else self._ev
+        names = ("combine", "drain", "route", "barrier", "fold")
+        tot = dict.fromkeys(names, 0.0)
+        rounds = len(ev) // 6
+        for r in range(rounds):
+            for i, k in enumerate(names):
+                tot[k] += ev[6 * r + i].elapsed_time(ev[6 * r + i + 1])
+        return {k: v / max(rounds, 1) for k, v in tot.items()}
 
     def _counters(self):
         import ctypes

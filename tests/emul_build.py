@@ -13,7 +13,9 @@ def build(name, deps, flags=()):
     """Compile tests/emul/<name>.cpp into tests/emul/_build/lib<name>.so if any of `deps` is newer."""
     os.makedirs(BUILD, exist_ok=True)
     src = os.path.join(EMUL, name + ".cpp")
-    so = os.path.join(BUILD, "lib" + name + ".so")
+    extra = os.environ.get("FA_EMUL_CXXFLAGS", "").split()          # e.g. -DFA_K1_EXP=3: a kernel build variant under emulation
+    flags = tuple(flags) + tuple(extra)
+    so = os.path.join(BUILD, "lib" + name + ("_" + "".join(c for c in "".join(extra) if c.isalnum()) if extra else "") + ".so")
     newest = max(os.path.getmtime(p) for p in [src] + list(deps))
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
