@@ -656,17 +656,17 @@ def run_rttdns(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="zipf10m", choices=sorted(WORKLOADS) + ["rttdns"])
     ap.add_argument("--batch", type=int, default=1 << 27,
                     help="records per step per GPU (2^27 x 144 B = 19.3 GB; 20 steps = a timed region of >= 200 ms)")
     ap.add_argument("--max-batch", type=int, default=1 << 23, help="records per K1 launch (N = 1)")
-    ap.add_argument("--mgpu-round", type=int, default=1 << 24, help="N>1: records per combine -> exchange -> fold round")
+    ap.add_argument("--mgpu-round", type=int, default=1 << 26, help="N>1: records per combine -> exchange -> fold round")
     ap.add_argument("--ring", type=int, default=2, help="distinct pre-generated input batches cycled through")
     ap.add_argument("--e2e-batch", type=int, default=1 << 22)
-    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-steps", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=1 << 25)
     ap.add_argument("--ref-sample", type=int, default=1 << 24)
     ap.add_argument("--verify-records", type=int, default=1 << 25)

@@ -361,7 +361,7 @@ int ingest_device(fa_engine* e, const uint8_t* d_recs, size_t n, size_t* consume
 // Host data reaches the device through two staging buffers of stage_records() records: the copy of chunk k+1 (copy
 // stream) overlaps the kernels of chunk k (engine stream).  The staging grain is independent of max_batch, the K1
 // launch size for device-resident input: a large launch amortises K1's start-up, a small stage keeps the pipeline fine.
-static uint64_t stage_records(const fa_engine* e) { return std::min<uint64_t>(e->max_batch, 1ull << 22); }
+static uint64_t stage_records(const fa_engine* e) { return std::min<uint64_t>(e->max_batch, 1ull << 20); }   // 151 MB of records per copy
 
 static int stage_alloc(fa_engine* e, bool pageable) {
     for (int i = 0; i < 2; i++) {
@@ -958,7 +958,7 @@ int fa_route_peer(fa_engine* e, const void* recs, const uint64_t* n_dev, size_t 
         pt.count[i] = reinterpret_cast<unsigned long long*>(peer_counts[i]);
     }
     e->st.kernel_launches += fa::launch_route_peer(static_cast<const uint4*>(recs), reinterpret_cast<const unsigned long long*>(n_dev),
-                                                   (uint32_t)max_n, n_shards, self_shard, pt, cap, reinterpret_cast<unsigned long long*>(overflow_dev), e->stream);
+                                                   (uint32_t)max_n, n_shards, self_shard, pt, cap, reinterpret_cast<unsigned long long*>(overflow_dev), e->sm_count, e->stream);
     CU(cudaGetLastError());
     return FA_OK;
 }

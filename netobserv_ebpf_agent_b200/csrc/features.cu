@@ -86,28 +86,167 @@ __device__ __forceinline__ void load_key(const uint8_t* rec, uint64_t k[5]) {
     for (int i = 0; i < 5; i++) k[i] = ld_u64_unaligned8(rec + 8 * i);    // records are 8-byte aligned (72 / 104 B)
 }
 
-__global__ void additional_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, uint64_t seq0,
-                                       uint32_t* __restrict__ slot_of, Counters* ctr) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint8_t* R = recs + (size_t)i * kAddRecBytes;
-        uint64_t k[5]; load_key(R, k);
-        const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
-        slot_of[i] = slot;
-        if (slot == 0xFFFFFFFFu) { atomicAdd(&ctr->spills, 1ull); continue; }
+// ---- the fold: one CTA per tile of 256 samples ------------------------------------------------------------------
+// The tile is staged in shared memory with coalesced 8-byte loads (samples are 72 / 104 bytes: a thread-per-sample
+// read would touch 18-26 lines per warp instruction).  Samples of one flow elect a representative inside the tile
+// (shared-memory hash set on the slot hash, keys compared in shared memory); the others fold their values into the
+// representative's accumulators with shared-memory atomics, so a hot flow costs ONE table probe and ONE set of global
+// reductions per tile instead of one per sample (every value below is a max / add / or, and the order-dependent ones
+// carry the sample number, so folding early does not change the result).
+constexpr int kFeatTile = 256;          // samples per tile == threads per CTA
+constexpr int kFeatRep = 512;           // tile-local election set
+constexpr uint32_t kFeatNone = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void smem_max_u64(uint64_t* p, uint64_t v) { if (v) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+__device__ __forceinline__ void smem_add_u64(uint64_t* p, uint64_t v) { if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+__device__ __forceinline__ void smem_or_u64(uint64_t* p, uint64_t v) { if (v) atomicOr(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+__device__ __forceinline__ void gmax(uint8_t* p, uint64_t v) { if (v) red_max_u64(p, v); }
+__device__ __forceinline__ void gadd(uint8_t* p, uint64_t v) { if (v) red_add_u64(p, v); }
+__device__ __forceinline__ void gor32(uint8_t* p, uint64_t v) { if (v) red_or_u32(p, (uint32_t)v); }
+
+struct AddFeat {                        // additional_metrics samples, 72 B
+    static constexpr int kRec = kAddRecBytes, kAcc = 7;
+    static __device__ __forceinline__ uint8_t* state(const Table& t, uint32_t slot) { return reinterpret_cast<uint8_t*>(t.feat_add) + (size_t)slot * (kAddState * 16); }
+    static __device__ __forceinline__ void extract(const uint8_t* R, uint64_t seq, uint64_t* v) {
         const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48), rtt = ld_u64_unaligned8(R + 56);
         const uint32_t ret = *reinterpret_cast<const uint32_t*>(R + 64);
         const uint32_t w = *reinterpret_cast<const uint32_t*>(R + 68);         // eth u16 | enc u8 | pad
         const uint32_t eth = w & 0xFFFFu, enc = ((w >> 16) & 0xFFu) ? 1u : 0u;
-        const uint64_t seq = seq0 + i;
-        uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_add) + (size_t)slot * (kAddState * 16);
-        red_max_u64(S + 0, ~seq);
-        if (rtt) { red_max_u64(S + 8, rtt); red_max_u64(S + 72, ~rtt); }
-        red_max_u64(S + 16, ((uint64_t)(ret ^ 0x80000000u) << 1) | enc | (1ull << 40));   // bit 40: "has a sample"
-        if (start) red_max_u64(S + 24, 0ull - start);
-        if (end) red_max_u64(S + 32, end);
-        if (eth) red_max_u64(S + 40, ~((seq << 16) | eth));
+        v[0] = ~seq;
+        v[1] = rtt;
+        v[2] = rtt ? ~rtt : 0ull;
+        v[3] = ((uint64_t)(ret ^ 0x80000000u) << 1) | enc | (1ull << 40);       // bit 40: "has a sample"
+        v[4] = start ? 0ull - start : 0ull;
+        v[5] = end;
+        v[6] = eth ? ~((seq << 16) | eth) : 0ull;
+    }
+    static __device__ __forceinline__ void fold(uint64_t* a, const uint64_t* v) {
+#pragma unroll
+        for (int k = 0; k < kAcc; k++) smem_max_u64(a + k, v[k]);
+    }
+    static __device__ __forceinline__ void flush(uint8_t* S, const uint64_t* a) {
+        gmax(S + 0, a[0]); gmax(S + 8, a[1]); gmax(S + 72, a[2]); gmax(S + 16, a[3]); gmax(S + 24, a[4]); gmax(S + 32, a[5]); gmax(S + 40, a[6]);
+    }
+};
+struct DnsFeat {                        // dns_metrics samples, 104 B
+    static constexpr int kRec = kDnsRecBytes, kAcc = 8;
+    static __device__ __forceinline__ uint8_t* state(const Table& t, uint32_t slot) { return reinterpret_cast<uint8_t*>(t.feat_dns) + (size_t)slot * (kDnsState * 16); }
+    static __device__ __forceinline__ void extract(const uint8_t* R, uint64_t seq, uint64_t* v) {
+        const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48), lat = ld_u64_unaligned8(R + 56);
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(R + 64);        // id u16 | flags u16
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(R + 68);        // eth u16 | errno u8 | name[0]
+        const uint32_t id = w0 & 0xFFFFu, flags = w0 >> 16, eth = w1 & 0xFFFFu, err = (w1 >> 16) & 0xFFu;
+        v[0] = ~seq;
+        v[1] = lat;
+        v[2] = id ? ((seq + 1) << 16) | id : 0ull;
+        v[3] = ((seq + 1) << 16) | err;
+        v[4] = start ? 0ull - start : 0ull;
+        v[5] = end;
+        v[6] = eth ? ~((seq << 16) | eth) : 0ull;
+        v[7] = flags;
+    }
+    static __device__ __forceinline__ void fold(uint64_t* a, const uint64_t* v) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) smem_max_u64(a + k, v[k]);
+        smem_or_u64(a + 7, v[7]);
+    }
+    static __device__ __forceinline__ void flush(uint8_t* S, const uint64_t* a) {
+        gmax(S + 0, a[0]); gmax(S + 8, a[1]); gmax(S + 16, a[2]); gmax(S + 24, a[3]); gmax(S + 32, a[4]); gmax(S + 40, a[5]); gmax(S + 48, a[6]);
+        gor32(S + 56, a[7]);
+    }
+};
+// pkt_drop_metrics samples (flow_id 40 B + start 8, end 8, bytes u16, packets u16, latest_drop_cause u32, latest_flags u16,
+// eth_protocol u16, latest_state u8), 72 B: AccumulateDrops in sample order
+struct DropFeat {
+    static constexpr int kRec = kDropRecBytes, kAcc = 9;
+    static __device__ __forceinline__ uint8_t* state(const Table& t, uint32_t slot) { return reinterpret_cast<uint8_t*>(t.feat_drop) + (size_t)slot * (kDropState * 16); }
+    static __device__ __forceinline__ void extract(const uint8_t* R, uint64_t seq, uint64_t* v) {
+        const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48);
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(R + 56);        // bytes u16 | packets u16
+        const uint32_t cause = *reinterpret_cast<const uint32_t*>(R + 60);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(R + 64);        // latest_flags u16 | eth u16
+        const uint32_t state = R[68];
+        const uint32_t flags = w1 & 0xFFFFu, eth = w1 >> 16;
+        v[0] = ~seq;
+        v[1] = w0 & 0xFFFFu;
+        v[2] = w0 >> 16;
+        v[3] = cause ? seq + 1 : 0ull;
+        v[4] = state ? ((seq + 1) << 8) | state : 0ull;
+        v[5] = flags;
+        v[6] = start ? 0ull - start : 0ull;
+        v[7] = end;
+        v[8] = eth ? ~((seq << 16) | eth) : 0ull;
+    }
+    static __device__ __forceinline__ void fold(uint64_t* a, const uint64_t* v) {
+        smem_max_u64(a + 0, v[0]); smem_add_u64(a + 1, v[1]); smem_add_u64(a + 2, v[2]); smem_max_u64(a + 3, v[3]); smem_max_u64(a + 4, v[4]);
+        smem_or_u64(a + 5, v[5]); smem_max_u64(a + 6, v[6]); smem_max_u64(a + 7, v[7]); smem_max_u64(a + 8, v[8]);
+    }
+    static __device__ __forceinline__ void flush(uint8_t* S, const uint64_t* a) {
+        gmax(S + 0, a[0]); gadd(S + 8, a[1]); gadd(S + 16, a[2]); gmax(S + 24, a[3]); gmax(S + 32, a[4]); gor32(S + 40, a[5]);
+        gmax(S + 48, a[6]); gmax(S + 56, a[7]); gmax(S + 64, a[8]);
+    }
+};
+
+template <class F> constexpr size_t feature_fold_smem() {
+    return (size_t)kFeatTile * F::kRec + (size_t)kFeatTile * F::kAcc * 8 + kFeatRep * 4 + kFeatTile * 4;
+}
+
+template <class F>
+__global__ void __launch_bounds__(kFeatTile)
+feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, uint64_t seq0,
+                    uint32_t* __restrict__ slot_of, Counters* ctr) {
+    FA_DYN_SMEM(sm);
+    uint64_t* tile = reinterpret_cast<uint64_t*>(sm);                         // kFeatTile samples
+    uint64_t* acc = tile + kFeatTile * (F::kRec / 8);                         // [kFeatTile][kAcc]
+    uint32_t* rep = reinterpret_cast<uint32_t*>(acc + kFeatTile * F::kAcc);   // [kFeatRep] election set
+    uint32_t* slot_s = rep + kFeatRep;                                        // [kFeatTile] slot found by each representative
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_tiles = (n + kFeatTile - 1) / kFeatTile;
+    for (uint32_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
+        const uint32_t first = tix * kFeatTile, cnt = min((uint32_t)kFeatTile, n - first);
+        const uint64_t* G = reinterpret_cast<const uint64_t*>(recs + (size_t)first * F::kRec);
+        for (uint32_t w = tid; w < cnt * (F::kRec / 8); w += kFeatTile) tile[w] = G[w];
+        for (uint32_t w = tid; w < kFeatRep; w += kFeatTile) rep[w] = kFeatNone;
+        __syncthreads();
+        const bool valid = tid < cnt;
+        const uint8_t* R = reinterpret_cast<const uint8_t*>(tile) + (size_t)tid * F::kRec;
+        uint32_t r = tid;                                                     // my representative
+        uint64_t k[5] = {0, 0, 0, 0, 0}, v[F::kAcc];
+        if (valid) {
+            load_key(R, k);
+            k[4] &= 0x00FFFFFFFFFFFFFFull;
+            uint32_t q = (uint32_t)(slot_hash(key_premix(k[0], k[1], k[2], k[3], k[4])) >> 40) & (kFeatRep - 1);
+            for (int step = 0; step < 8; step++) {
+                const uint32_t cur = atomicCAS(&rep[q], kFeatNone, tid);
+                if (cur == kFeatNone) break;                                  // nobody holds this key yet: I represent it
+                const uint64_t* K = tile + (size_t)cur * (F::kRec / 8);
+                if (K[0] == k[0] && K[1] == k[1] && K[2] == k[2] && K[3] == k[3] && (K[4] & 0x00FFFFFFFFFFFFFFull) == k[4]) { r = cur; break; }
+                q = (q + 1) & (kFeatRep - 1);                                 // after 8 steps: stay my own representative (unmerged, still exact)
+            }
+            F::extract(R, seq0 + first + tid, v);
+            if (r == tid) {
+#pragma unroll
+                for (int a = 0; a < F::kAcc; a++) acc[tid * F::kAcc + a] = v[a];
+            }
+        }
+        __syncthreads();
+        if (valid && r != tid) F::fold(acc + r * F::kAcc, v);
+        __syncthreads();
+        if (valid && r == tid) {
+            const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
+            slot_s[tid] = slot;
+            if (slot != kFeatNone) F::flush(F::state(t, slot), acc + tid * F::kAcc);
+        }
+        __syncthreads();
+        if (valid) {
+            const uint32_t slot = slot_s[r];
+            slot_of[first + tid] = slot;
+            if (slot == kFeatNone) atomicAdd(&ctr->spills, 1ull);
+        }
+        __syncthreads();                                                      // tile / rep / slot_s are re-used
     }
 }
+
 // second pass: the sample that turned out to be the flow's first one writes the adopted block fields
 __global__ void additional_first_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t seq0,
                                         const uint32_t* __restrict__ slot_of) {
@@ -123,30 +262,6 @@ __global__ void additional_first_kernel(const uint8_t* __restrict__ recs, uint32
     }
 }
 
-__global__ void dns_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, uint64_t seq0,
-                                uint32_t* __restrict__ slot_of, Counters* ctr) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint8_t* R = recs + (size_t)i * kDnsRecBytes;
-        uint64_t k[5]; load_key(R, k);
-        const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
-        slot_of[i] = slot;
-        if (slot == 0xFFFFFFFFu) { atomicAdd(&ctr->spills, 1ull); continue; }
-        const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48), lat = ld_u64_unaligned8(R + 56);
-        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(R + 64);        // id u16 | flags u16
-        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(R + 68);        // eth u16 | errno u8 | name[0]
-        const uint32_t id = w0 & 0xFFFFu, flags = w0 >> 16, eth = w1 & 0xFFFFu, err = (w1 >> 16) & 0xFFu;
-        const uint64_t seq = seq0 + i;
-        uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_dns) + (size_t)slot * (kDnsState * 16);
-        red_max_u64(S + 0, ~seq);
-        if (lat) red_max_u64(S + 8, lat);
-        if (id) red_max_u64(S + 16, ((seq + 1) << 16) | id);
-        red_max_u64(S + 24, ((seq + 1) << 16) | err);
-        if (start) red_max_u64(S + 32, 0ull - start);
-        if (end) red_max_u64(S + 40, end);
-        if (eth) red_max_u64(S + 48, ~((seq << 16) | eth));
-        if (flags) red_or_u32(S + 56, flags);
-    }
-}
 __global__ void dns_first_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t seq0,
                                  const uint32_t* __restrict__ slot_of) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -162,35 +277,6 @@ __global__ void dns_first_kernel(const uint8_t* __restrict__ recs, uint32_t n, T
     }
 }
 
-// pkt_drop_metrics samples (flow_id 40 B + start 8, end 8, bytes u16, packets u16, latest_drop_cause u32, latest_flags u16,
-// eth_protocol u16, latest_state u8): AccumulateDrops in sample order
-__global__ void pktdrop_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, uint64_t seq0,
-                                    uint32_t* __restrict__ slot_of, Counters* ctr) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint8_t* R = recs + (size_t)i * kDropRecBytes;
-        uint64_t k[5]; load_key(R, k);
-        const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
-        slot_of[i] = slot;
-        if (slot == 0xFFFFFFFFu) { atomicAdd(&ctr->spills, 1ull); continue; }
-        const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48);
-        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(R + 56);        // bytes u16 | packets u16
-        const uint32_t cause = *reinterpret_cast<const uint32_t*>(R + 60);
-        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(R + 64);        // latest_flags u16 | eth u16
-        const uint32_t state = R[68];
-        const uint32_t flags = w1 & 0xFFFFu, eth = w1 >> 16;
-        const uint64_t seq = seq0 + i;
-        uint8_t* S = reinterpret_cast<uint8_t*>(t.feat_drop) + (size_t)slot * (kDropState * 16);
-        red_max_u64(S + 0, ~seq);
-        red_add_u64(S + 8, w0 & 0xFFFFu);
-        red_add_u64(S + 16, w0 >> 16);
-        if (cause) red_max_u64(S + 24, seq + 1);
-        if (state) red_max_u64(S + 32, ((seq + 1) << 8) | state);
-        if (flags) red_or_u32(S + 40, flags);
-        if (start) red_max_u64(S + 48, 0ull - start);
-        if (end) red_max_u64(S + 56, end);
-        if (eth) red_max_u64(S + 64, ~((seq << 16) | eth));
-    }
-}
 __global__ void pktdrop_first_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t seq0,
                                      const uint32_t* __restrict__ slot_of) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -210,21 +296,23 @@ __global__ void pktdrop_first_kernel(const uint8_t* __restrict__ recs, uint32_t 
 }
 
 #ifndef FA_HOST_EMUL
+template <class F, class First>
+static int launch_fold(First first_kernel, const uint8_t* recs, uint32_t n, const Table& t, uint64_t epoch, uint64_t seq0, uint32_t* slot_of,
+                       Counters* ctr, int sm_count, cudaStream_t st) {
+    const uint32_t n_tiles = (n + kFeatTile - 1) / kFeatTile;
+    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count * 8u);      // persistent over tiles; 4-5 CTAs of ~40-46 KB fit an SM
+    feature_fold_kernel<F><<<grid, kFeatTile, feature_fold_smem<F>(), st>>>(recs, n, t, epoch, seq0, slot_of, ctr);
+    first_kernel<<<sm_count * 8, 256, 0, st>>>(recs, n, t, seq0, slot_of);
+    return 2;
+}
+
 int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& t, uint64_t epoch, uint64_t seq0,
                         uint32_t* slot_of, Counters* ctr, int sm_count, cudaStream_t st) {
     if (!n) return 0;
-    const int grid = sm_count * 8;
-    if (kind == 2) {
-        pktdrop_fold_kernel<<<grid, 256, 0, st>>>(recs, n, t, epoch, seq0, slot_of, ctr);
-        pktdrop_first_kernel<<<grid, 256, 0, st>>>(recs, n, t, seq0, slot_of);
-    } else if (kind == 0) {
-        additional_fold_kernel<<<grid, 256, 0, st>>>(recs, n, t, epoch, seq0, slot_of, ctr);
-        additional_first_kernel<<<grid, 256, 0, st>>>(recs, n, t, seq0, slot_of);
-    } else {
-        dns_fold_kernel<<<grid, 256, 0, st>>>(recs, n, t, epoch, seq0, slot_of, ctr);
-        dns_first_kernel<<<grid, 256, 0, st>>>(recs, n, t, seq0, slot_of);
-    }
-    return 2;
+    static_assert(feature_fold_smem<DnsFeat>() <= 48 * 1024 && feature_fold_smem<DropFeat>() <= 48 * 1024, "K6 tiles fit the default 48 KB");
+    if (kind == 2) return launch_fold<DropFeat>(pktdrop_first_kernel, recs, n, t, epoch, seq0, slot_of, ctr, sm_count, st);
+    if (kind == 0) return launch_fold<AddFeat>(additional_first_kernel, recs, n, t, epoch, seq0, slot_of, ctr, sm_count, st);
+    return launch_fold<DnsFeat>(dns_first_kernel, recs, n, t, epoch, seq0, slot_of, ctr, sm_count, st);
 }
 #endif  // FA_HOST_EMUL
 

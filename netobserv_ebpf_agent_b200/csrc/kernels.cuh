@@ -96,7 +96,7 @@ int launch_generate(const GenDeviceParams& g, uint64_t first_index, uint32_t n, 
 // routing fused with the exchange: destinations are peer-mapped receive buffers + their record counters
 struct PeerTargets { uint4* buf[16]; unsigned long long* count[16]; };
 int launch_route_peer(const uint4* recs, const unsigned long long* n_dev, uint32_t max_n, uint32_t n_shards, uint32_t self_shard,
-                      const PeerTargets& pt, unsigned long long cap, unsigned long long* overflow, cudaStream_t st);
+                      const PeerTargets& pt, unsigned long long cap, unsigned long long* overflow, int sm_count, cudaStream_t st);
 
 // routing (K3)
 int launch_route(const uint4* recs, uint32_t n, uint32_t n_shards, uint4* out, unsigned long long* counts_dev,

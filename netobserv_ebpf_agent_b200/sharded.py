@@ -175,11 +175,19 @@ class PeerShardedAggregator:
         assert torch.cuda.current_stream().cuda_stream != 0, "use an explicit torch.cuda.Stream (see bench.py)"
         self.eng, self.max_batch = engine, max_batch
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
-        self.recv_cap = recv_cap or max_batch
         self.profile, self._ev = profile, []
-        self.local = FlowAggEngine(local_entries or 2 * max_batch, device=device.index, max_batch=max_batch, flags=FA_F_NO_FULL_CUT,
+        local_entries = local_entries or 2 * max_batch
+        # a round's partials are distinct flows of the scratch table: neither the drain buffer nor (in expectation, owners
+        # being a uniform hash) a receive buffer needs more room than that table has slots; what does not fit is counted
+        # (overflow[0]) and makes flush() raise
+        need, slots = (4 * local_entries + 2) // 3, 1024
+        while slots < need:
+            slots <<= 1                                  # the engine's table sizing: a drain can never emit more than this
+        self.part_cap = min(max_batch, slots)
+        self.recv_cap = recv_cap or self.part_cap
+        self.local = FlowAggEngine(local_entries, device=device.index, max_batch=max_batch, flags=FA_F_NO_FULL_CUT,
                                    cuda_stream=torch.cuda.current_stream().cuda_stream)
-        self.part = torch.empty(max_batch * REC_BYTES, dtype=torch.uint8, device=device)
+        self.part = torch.empty(self.part_cap * REC_BYTES, dtype=torch.uint8, device=device)
         self.part_n = torch.zeros(1, dtype=torch.int64, device=device)
         self.token = torch.zeros(1, dtype=torch.int32, device=device)
         L = lib()
@@ -231,11 +239,11 @@ class PeerShardedAggregator:
             rc, took = self.local.ingest(base + done * REC_BYTES, c)
             assert rc == 0 and took == c, (rc, took)
             mark()
-            check(L.fa_drain_active_counted(self.local._h, C.c_void_p(self.part.data_ptr()), self.max_batch,
+            check(L.fa_drain_active_counted(self.local._h, C.c_void_p(self.part.data_ptr()), self.part_cap,
                                             C.c_void_p(self.part_n.data_ptr())))
             mark()
             check(L.fa_route_peer(self.eng._h, C.c_void_p(self.part.data_ptr()), C.c_void_p(self.part_n.data_ptr()),
-                                  self.max_batch, self.world, self.rank, self.bufs[b], self.cnts[b], self.recv_cap,
+                                  self.part_cap, self.world, self.rank, self.bufs[b], self.cnts[b], self.recv_cap,
                                   C.c_void_p(self.overflow)))
             mark()
             dist.all_reduce(self.token)                    # stream-ordered barrier: every rank has delivered batch `step`

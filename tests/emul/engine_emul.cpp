@@ -166,13 +166,13 @@ int launch_feature_fold(int kind, const uint8_t* recs, uint32_t n, const Table& 
     if (!n) return 0;
     Table t = table;
     if (kind == 2) {
-        simt::launch(2, 256, 0, [=] { pktdrop_fold_kernel(recs, n, t, epoch, seq0, slot_of, ctr); });
+        simt::launch(2, kFeatTile, feature_fold_smem<DropFeat>(), [=] { feature_fold_kernel<DropFeat>(recs, n, t, epoch, seq0, slot_of, ctr); });
         simt::launch(2, 256, 0, [=] { pktdrop_first_kernel(recs, n, t, seq0, slot_of); });
     } else if (kind == 0) {
-        simt::launch(2, 256, 0, [=] { additional_fold_kernel(recs, n, t, epoch, seq0, slot_of, ctr); });
+        simt::launch(2, kFeatTile, feature_fold_smem<AddFeat>(), [=] { feature_fold_kernel<AddFeat>(recs, n, t, epoch, seq0, slot_of, ctr); });
         simt::launch(2, 256, 0, [=] { additional_first_kernel(recs, n, t, seq0, slot_of); });
     } else {
-        simt::launch(2, 256, 0, [=] { dns_fold_kernel(recs, n, t, epoch, seq0, slot_of, ctr); });
+        simt::launch(2, kFeatTile, feature_fold_smem<DnsFeat>(), [=] { feature_fold_kernel<DnsFeat>(recs, n, t, epoch, seq0, slot_of, ctr); });
         simt::launch(2, 256, 0, [=] { dns_first_kernel(recs, n, t, seq0, slot_of); });
     }
     return 2;
@@ -227,8 +227,13 @@ int launch_generate(const GenDeviceParams& g_, uint64_t first_index, uint32_t n,
     simt::launch(2, 256, 0, [=] { generate_kernel(g, first_index, n, dst); });
     return 1;
 }
-int launch_route_peer(const uint4*, const unsigned long long*, uint32_t, uint32_t, uint32_t, const PeerTargets&, unsigned long long,
-                      unsigned long long*, cudaStream_t) { abort(); }          // multi-GPU exchange: not emulated
+int launch_route_peer(const uint4* recs, const unsigned long long* n_dev, uint32_t max_n, uint32_t n_shards, uint32_t self_shard,
+                      const PeerTargets& pt_, unsigned long long cap, unsigned long long* overflow, int, cudaStream_t) {
+    if (!max_n) return 0;
+    PeerTargets pt = pt_;                                                        // "peer" buffers are plain host memory here
+    launch_serial(3, kRouteTile, [=] { route_peer_kernel(recs, n_dev, max_n, n_shards, self_shard, pt, cap, overflow); });
+    return 1;
+}
 int launch_route(const uint4* recs, uint32_t n, uint32_t n_shards, uint4* out, unsigned long long* counts_dev, uint32_t* tmp,
                  int, cudaStream_t) {
     if (!n) { memset(counts_dev, 0, n_shards * sizeof(unsigned long long)); return 0; }

@@ -117,3 +117,37 @@ def test_kernel_map_base_with_feature_maps(engine_emul, monkeypatch, impl):
         compare(eng, om)
         assert eng.stats()["observed_intf_missed"] == missed
         assert eng.live_flows() == 0
+
+
+def test_route_peer_delivers_every_record_to_its_owner_once(engine_emul):
+    """K3 fused with the exchange (fa_route_peer) on the emulation, where "peer memory" is host memory: every record
+    lands exactly once in the buffer of owner_hash(key) % n_shards, records of one tile keep their order, the device-side
+    count bounds the work, the remote-record counter and the overflow counter are exact."""
+    import netobserv_ebpf_agent_b200 as fa
+    from netobserv_ebpf_agent_b200._lib import check, lib
+    from netobserv_ebpf_agent_b200.sharded import owner_of
+    n_max, n, n_shards, me = 3_000, 2_777, 3, 1
+    recs = np.ascontiguousarray(gen_host(seed=5, n=n_max, n_keys=400, dist=1))
+    own = owner_of(recs[:n, :40], n_shards)
+    for cap in (n_max, 700):                                   # roomy buffers, then buffers that overflow
+        bufs = [np.zeros((cap, 144), dtype=np.uint8) for _ in range(n_shards)]
+        cnts = [np.zeros(1, dtype=np.uint64) for _ in range(n_shards)]
+        overflow, n_dev = np.zeros(2, dtype=np.uint64), np.array([n], dtype=np.uint64)
+        pb, pc = (ctypes.c_void_p * 16)(), (ctypes.c_void_p * 16)()
+        for s in range(n_shards):
+            pb[s], pc[s] = bufs[s].ctypes.data, cnts[s].ctypes.data
+        with fa.FlowAggEngine(1 << 12, max_batch=4096) as eng:
+            check(lib().fa_route_peer(eng._h, ctypes.c_void_p(recs.ctypes.data), ctypes.c_void_p(n_dev.ctypes.data), n_max, n_shards, me,
+                                      pb, pc, cap, ctypes.c_void_p(overflow.ctypes.data)))
+            eng.sync()
+        lost = 0
+        for s in range(n_shards):
+            want = recs[:n][own == s]
+            assert int(cnts[s][0]) == len(want)                # reservations count every record, stored or not
+            got = bufs[s][: min(len(want), cap)]
+            lost += max(len(want) - cap, 0)
+            if len(want) <= cap:
+                # tiles may be reserved in any order; inside a tile the order is kept -> compare as sorted multisets and per tile
+                assert np.array_equal(got[np.lexsort(got.T[::-1])], want[np.lexsort(want.T[::-1])])
+        assert int(overflow[0]) == lost and (lost > 0) == (cap < n_max)
+        assert int(overflow[1]) == int((own != me).sum())

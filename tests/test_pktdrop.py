@@ -125,3 +125,10 @@ def test_golden_gpu():
 @pytest.mark.gpu
 def test_random_streams_gpu():
     check_random(n_keys=5_000, n_base=80_000, n_feat=60_000, max_entries=1 << 17, max_batch=1 << 15)
+
+
+def test_hot_keys_and_crowded_tiles_on_the_emulation(engine_emul):
+    """K6 folds a tile's samples of one flow in shared memory before touching the table: a handful of keys (every tile is
+    almost all duplicates) and a key set larger than the tile's election set both have to stay exact."""
+    check_random(n_keys=6, n_base=400, n_feat=1_500, max_entries=1 << 12, max_batch=1_024)
+    check_random(n_keys=700, n_base=6_000, n_feat=2_000, max_entries=1 << 13, max_batch=2_048)
