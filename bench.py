@@ -271,11 +271,9 @@ def run_ours(args, wl):
         from netobserv_ebpf_agent_b200.sharded import PeerShardedAggregator, ShardedAggregator
         if args.exchange == "peer":
             # local combine (K1+K2) -> K3 fused with the exchange (peer stores over NVLink) -> K1 on the owner
-            # the combiner's scratch table holds one round's distinct flows: never more than the key universe
-            k = 0
-            while (3 << k) < wl["n_keys"]:
-                k += 1
-            agg = PeerShardedAggregator(eng, max_batch, dev, local_entries=min(2 * max_batch, 3 << k), profile=True)
+            # the combiner's scratch table holds one round's distinct flows: sized like the single-GPU table of the workload
+            # (same load factor, so the local K1 probes like the N=1 run), never more than a round can fill
+            agg = PeerShardedAggregator(eng, max_batch, dev, local_entries=min(2 * max_batch, wl["max_entries"]), profile=True)
         else:
             # local combine (K1+K2) -> K3 route -> NCCL all-to-all -> K1 on the owner
             agg = ShardedAggregator(eng, max_batch, dev, combine=not args.no_combine)

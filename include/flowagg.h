@@ -131,6 +131,22 @@ typedef struct fa_pkt_drop_metrics {
     uint8_t  pad_[3];
 } fa_pkt_drop_metrics;
 
+/* Raw packet snapshot for fa_ingest_snaps ((f4), the front end of flow_monitor): 24 bytes of what the TC hook knows
+ * about the skb, followed by the first (stride - 24) bytes of the frame, Ethernet header first.  `stride` is chosen by
+ * the caller (a multiple of 8, 40..256): 88 carries a "64-byte header snap"; 104 reaches the TCP flags of an IPv6 frame
+ * (14 + 40 + 20 = 74 header bytes).  cap_len = min(data_end - data, stride - 24) is the bound every header check of
+ * bpf/utils.h:54-167 runs against (a header that does not fit is not parsed, exactly as there). */
+typedef struct fa_packet_snap_hdr {
+    uint64_t mono_ts;                /*  0 pkt.current_ts = bpf_ktime_get_ns() (flows.c:180) */
+    uint32_t len;                    /*  8 skb->len */
+    uint32_t if_index;               /* 12 skb->ifindex */
+    uint32_t sampling;               /* 16 flow_sampling */
+    uint16_t cap_len;                /* 20 valid bytes of data[] */
+    uint8_t  direction;              /* 22 */
+    uint8_t  pad_;                   /* 23 */
+    /* uint8_t data[stride - 24] follows */
+} fa_packet_snap_hdr;                /* 24 bytes */
+
 /* Feature-stream input records: the key plus one feature sample — what the
  * reference keeps per CPU slot in aggregated_flows_dns / additional_flow_metrics
  * (bpf/maps_definition.h:24-31,64-71). */
@@ -243,6 +259,8 @@ typedef struct fa_stats {
     uint64_t ringbuf_spilled;     /* KERNEL_MAP mode: single-packet records handed to the fallback ring     */
     uint64_t ringbuf_dropped;     /* ... that found the ring full ("couldn't reserve space", flows.c:270)   */
     uint64_t pkt_drops_ingested;  /* samples consumed by fa_ingest_pkt_drops */
+    uint64_t snaps_ingested;      /* packet snapshots consumed by fa_ingest_snaps ...                       */
+    uint64_t snaps_discarded;     /* ... of which fill_ethhdr said DISCARD (not IP, truncated IP header)    */
 } fa_stats;
 
 typedef struct fa_engine fa_engine;
@@ -270,6 +288,15 @@ int fa_ingest(fa_engine* e, const void* flow_records, size_t n, size_t* consumed
  * single-packet record described at fa_packet_event and goes through the same kernels.  A separate measurement row
  * (64 algorithmic bytes per packet); the headline stays on 144-byte records. */
 int fa_ingest_events(fa_engine* e, const void* packet_events, size_t n, size_t* consumed);
+
+/* (f4) Raw-header front end: parse n packet snapshots (host or device pointer) on the device the way flow_monitor does
+ * before it touches the map — fill_ethhdr / fill_iphdr / fill_ip6hdr / fill_l4info / set_flags (bpf/utils.h:24-167) and
+ * the single-packet flow of bpf/flows.c:176-245 (start = end = ts, bytes = len, packets = 1, MACs, dscp, flags,
+ * sampling, if_index / direction first seen; no TLS / DNS / QUIC tracking: those read payload) — and fold the resulting
+ * records like fa_ingest.  Packets the reference discards (neither IPv4 nor IPv6, IP header beyond cap_len) are
+ * dropped and counted in fa_stats.snaps_discarded.  *consumed counts SNAPSHOTS (parsed or discarded); < n only with
+ * FA_FULL.  The flow filter (bpf/flows_filter.h) is not part of this entry point. */
+int fa_ingest_snaps(fa_engine* e, const void* snaps, size_t n, uint32_t stride, size_t* consumed);
 
 /* Fold n (flow_id + additional_metrics) samples: RTT keep-max, IPsec rules.
  * Replaces: bpf/rtt_tracker.h:12-22,73-91 + AccumulateAdditional

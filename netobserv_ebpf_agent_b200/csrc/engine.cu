@@ -137,6 +137,8 @@ struct fa_engine {
     uint32_t* d_cut_bitmap = nullptr; uint32_t* d_cut_out = nullptr; uint32_t* h_cut_out = nullptr;
 
     uint8_t* d_expanded = nullptr;            // ... and their 144-byte expansion (events handed in as device memory)
+    uint32_t* d_snap_src = nullptr;           // fa_ingest_snaps: snapshot index of every record parsed out of a chunk
+    uint32_t* d_snap_cnt = nullptr;           // ... records per CTA of the parse kernels, then the total (u64, 8-byte aligned)
     uint8_t* d_evict = nullptr; uint64_t evict_cap = 0;
     uint8_t* d_evict_dns = nullptr; uint8_t* d_evict_add = nullptr; uint8_t* d_evict_present = nullptr;
     uint32_t* d_slot_of_out = nullptr; uint64_t feat_evict_cap = 0;
@@ -622,6 +624,7 @@ void fa_destroy(fa_engine* e) {
     cudaFree(e->d_scratch); cudaFree(e->d_spill_idx); cudaFree(e->d_cut_set); cudaFree(e->d_cut_bitmap); cudaFree(e->d_cut_out);
     if (e->h_cut_out) cudaFreeHost(e->h_cut_out);
     cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts); cudaFree(e->d_expanded);
+    cudaFree(e->d_snap_src); cudaFree(e->d_snap_cnt);
     cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out); cudaFree(e->d_slot_of);
     cudaFree(e->d_evict_drop); cudaFree(e->d_evict_rttmin);
     cudaFree(e->sk.cms); cudaFree(e->sk.hll);
@@ -692,6 +695,71 @@ int fa_ingest_events(fa_engine* e, const void* events, size_t n, size_t* consume
         }
         done += off;
         if (rc != FA_OK) break;
+    }
+    if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->copy_stream));   // the caller's buffer must not be referenced after return
+    if (consumed) *consumed = done;
+    return rc;
+}
+
+int fa_ingest_snaps(fa_engine* e, const void* snaps, size_t n, uint32_t stride, size_t* consumed) {
+    if (consumed) *consumed = 0;
+    if (!e) return fail(FA_E_INVAL, "fa_ingest_snaps: null engine");
+    if (stride < 40 || stride > 152 || (stride & 7)) return fail(FA_E_INVAL, "fa_ingest_snaps: stride %u must be a multiple of 8 in 40..152", stride);
+    if (n == 0) return FA_OK;
+    if (!snaps) return fail(FA_E_INVAL, "fa_ingest_snaps: null snapshots");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    const PtrKind k = classify(snaps);
+    if (k == PTR_DEVICE && (reinterpret_cast<uintptr_t>(snaps) & 7)) return fail(FA_E_INVAL, "fa_ingest_snaps: device snapshots must be 8-byte aligned");
+    if (!e->d_expanded) CU(cudaMalloc(&e->d_expanded, e->max_batch * fa::kRecBytes));
+    if (!e->d_snap_src) CU(cudaMalloc(&e->d_snap_src, e->max_batch * sizeof(uint32_t)));
+    if (!e->d_snap_cnt) CU(cudaMalloc(&e->d_snap_cnt, (fa::kSnapMaxCtas + 2) * sizeof(uint32_t)));
+    if (k != PTR_DEVICE) { if (int arc = stage_alloc(e, k == PTR_PAGEABLE)) return arc; }
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(e->d_snap_cnt + fa::kSnapMaxCtas);
+    // host chunks are bounded by the staging buffers (stage_records() x 144 bytes), device chunks by max_batch records
+    const size_t per_chunk = k == PTR_DEVICE ? e->max_batch : std::min<uint64_t>(e->max_batch, stage_records(e) * fa::kRecBytes / stride);
+    size_t done = 0;
+    int rc = FA_OK;
+    while (done < n) {
+        const uint32_t c = (uint32_t)std::min<size_t>(n - done, per_chunk);
+        const uint8_t* src = static_cast<const uint8_t*>(snaps) + done * stride;
+        const uint8_t* d_sn = src;
+        int sidx = -1;
+        if (k != PTR_DEVICE) {
+            if (int src_rc = stage_copy(e, src, (size_t)c * stride, k == PTR_PINNED, &sidx)) return src_rc;
+            d_sn = e->d_stage[sidx];
+        }
+        e->st.kernel_launches += fa::launch_parse_snaps(d_sn, c, stride, e->d_snap_cnt, reinterpret_cast<uint4*>(e->d_expanded), e->d_snap_src,
+                                                        d_total, e->sm_count, e->stream);
+        CU(cudaGetLastError());
+        if (sidx >= 0) { if (int rel_rc = stage_release(e, sidx)) return rel_rc; }
+        // how many packets were submitted decides the launch sizes of the fold: one 8-byte read-back per chunk
+        unsigned long long m64 = 0;
+        CU(cudaMemcpyAsync(&m64, d_total, 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        const uint32_t m = (uint32_t)m64;
+        uint32_t off = 0;
+        while (off < m) {                                   // a chunk may be folded in several windows ("full" cuts)
+            uint32_t took = 0;
+            rc = ingest_chunk(e, e->d_expanded + (size_t)off * fa::kRecBytes, m - off, &took);
+            off += took;
+            if (rc != FA_OK) break;
+        }
+        if (rc == FA_FULL && off < m) {
+            // the cut is reported in snapshots: everything before the first record that was not folded, discarded ones included
+            uint32_t first_left = 0;
+            CU(cudaMemcpyAsync(&first_left, e->d_snap_src + off, 4, cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaStreamSynchronize(e->stream));
+            // discarded snapshots before the cut: first_left - off
+            e->st.snaps_ingested += first_left;
+            e->st.snaps_discarded += first_left - off;
+            done += first_left;
+            break;
+        }
+        if (rc != FA_OK) break;
+        e->st.snaps_ingested += c;
+        e->st.snaps_discarded += c - m;
+        done += c;
     }
     if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->copy_stream));   // the caller's buffer must not be referenced after return
     if (consumed) *consumed = done;

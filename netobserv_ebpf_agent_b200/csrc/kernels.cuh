@@ -88,6 +88,10 @@ int launch_pb_write(const PbInputs& in, uint32_t n, const PbParams& P, const uns
 
 // 64-byte packet events -> single-packet 144-byte records (misc_kernels.cu)
 int launch_expand_events(const uint4* events, uint32_t n, uint4* recs_out, cudaStream_t st);
+// (f4) packet snapshots -> records of the packets flow_monitor would submit, stable order; *n_out (device) = how many
+constexpr int kSnapMaxCtas = 1024;                 // cta_count has this many entries
+int launch_parse_snaps(const uint8_t* snaps, uint32_t n, uint32_t stride, uint32_t* cta_count, uint4* out_recs, uint32_t* src_of,
+                       unsigned long long* n_out, int sm_count, cudaStream_t st);
 
 // generator
 struct GenDeviceParams;

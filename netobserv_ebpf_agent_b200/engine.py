@@ -62,6 +62,17 @@ class FlowAggEngine:
         rc = check(lib().fa_ingest_events(self._h, _ptr(events), n, C.byref(consumed)))
         return rc, consumed.value
 
+    def ingest_snaps(self, snaps, stride, n=None):
+        """(f4) Fold raw packet snapshots (24-byte fa_packet_snap_hdr + frame bytes, `stride` bytes apart): parsed on the
+        device like flow_monitor's fill_ethhdr & co.  Returns (status, snapshots consumed)."""
+        if n is None:
+            nb = _nbytes(snaps)
+            assert nb % stride == 0
+            n = nb // stride
+        consumed = C.c_size_t(0)
+        rc = check(lib().fa_ingest_snaps(self._h, _ptr(snaps), n, stride, C.byref(consumed)))
+        return rc, consumed.value
+
     def ingest_all(self, recs, on_full):
         """Accounter loop: fold everything, calling on_full(evicted_records) at each "full" cut
         (reference pkg/flow/account.go:85-94)."""

@@ -689,3 +689,84 @@ double oracle_hll_estimate(const uint8_t* regs, uint32_t p) {
     if (e <= 2.5 * (double)m && zeros) e = (double)m * log((double)m / (double)zeros);
     return e;
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (f4) raw-header front end.  TEST INFRASTRUCTURE like the rest of this file.
+ * Follows bpf/utils.h:24-167 and bpf/flows.c:176-245; every bound check is the reference's "header end <= data_end". */
+static uint16_t be16(const uint8_t* p) { return (uint16_t)((p[0] << 8) | p[1]); }
+
+/* bpf/utils.h:24-50 set_flags: one flag per packet, first match of the chain */
+static uint16_t snap_tcp_flags(uint8_t f) {
+    const int fin = f & 0x01, syn = f & 0x02, rst = f & 0x04, psh = f & 0x08, ack = f & 0x10, urg = f & 0x20, ece = f & 0x40, cwr = f & 0x80;
+    if (ack && syn) return 0x100;          /* SYN_ACK_FLAG */
+    if (ack && fin) return 0x200;          /* FIN_ACK_FLAG */
+    if (ack && rst) return 0x400;          /* RST_ACK_FLAG */
+    if (fin) return 0x01;
+    if (syn) return 0x02;
+    if (ack) return 0x10;
+    if (rst) return 0x04;
+    if (psh) return 0x08;
+    if (urg) return 0x20;
+    if (ece) return 0x40;
+    if (cwr) return 0x80;
+    return 0;
+}
+
+int oracle_parse_snap(const uint8_t* snap, uint32_t stride, uint8_t* rec) {
+    uint64_t ts; uint32_t len, ifindex, sampling; uint16_t cap;
+    memcpy(&ts, snap, 8); memcpy(&len, snap + 8, 4); memcpy(&ifindex, snap + 12, 4); memcpy(&sampling, snap + 16, 4);
+    memcpy(&cap, snap + 20, 2);
+    const uint8_t direction = snap[22];
+    const uint8_t* d = snap + 24;
+    uint32_t end = cap;                                        /* data_end - data */
+    if (end > stride - 24) end = stride - 24;
+    memset(rec, 0, 144);
+    if (14 > end) return 0;                                    /* utils.h:154-156 */
+    const uint16_t eth = be16(d + 12);
+    uint32_t l4; uint8_t proto, dscp;
+    if (eth == 0x0800) {                                       /* utils.h:111-129: l4 = ip + sizeof(iphdr), options are not skipped */
+        l4 = 14 + 20;
+        if (l4 > end) return 0;
+        static const uint8_t ip4in6[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0xff, 0xff};
+        memcpy(rec + 0, ip4in6, 12); memcpy(rec + 12, d + 14 + 12, 4);
+        memcpy(rec + 16, ip4in6, 12); memcpy(rec + 28, d + 14 + 16, 4);
+        dscp = (d[14 + 1] >> 2) & 0x3F;
+        proto = d[14 + 9];
+    } else if (eth == 0x86DD) {                                /* utils.h:132-149: nexthdr taken as the transport, no extension walk */
+        l4 = 14 + 40;
+        if (l4 > end) return 0;
+        memcpy(rec + 0, d + 14 + 8, 16); memcpy(rec + 16, d + 14 + 24, 16);
+        dscp = (uint8_t)(((be16(d + 14) >> 4) >> 2) & 0x3F);
+        proto = d[14 + 6];
+    } else {
+        return 0;                                              /* utils.h:166: only IP-based flows */
+    }
+    uint16_t sport = 0, dport = 0, flags = 0; uint8_t itype = 0, icode = 0;
+    switch (proto) {                                           /* utils.h:53-104 */
+    case 6:   if (l4 + 20 <= end) { sport = be16(d + l4); dport = be16(d + l4 + 2); flags = snap_tcp_flags(d[l4 + 13]); } break;
+    case 17:  if (l4 + 8 <= end)  { sport = be16(d + l4); dport = be16(d + l4 + 2); } break;
+    case 132: if (l4 + 12 <= end) { sport = be16(d + l4); dport = be16(d + l4 + 2); } break;
+    case 1:   if (l4 + 8 <= end)  { itype = d[l4]; icode = d[l4 + 1]; } break;
+    case 58:  if (l4 + 8 <= end)  { itype = d[l4]; icode = d[l4 + 1]; } break;
+    default: break;
+    }
+    memcpy(rec + 32, &sport, 2); memcpy(rec + 34, &dport, 2);
+    rec[36] = proto; rec[37] = itype; rec[38] = icode;
+    /* flows.c:226-245 new_flow */
+    const uint64_t bytes = len; const uint32_t one = 1;
+    memcpy(rec + 40, &ts, 8); memcpy(rec + 48, &ts, 8); memcpy(rec + 56, &bytes, 8); memcpy(rec + 64, &one, 4);
+    memcpy(rec + 68, &eth, 2); memcpy(rec + 70, &flags, 2);
+    memcpy(rec + 72, d + 6, 6);                                /* src_mac = eth->h_source */
+    memcpy(rec + 78, d + 0, 6);                                /* dst_mac = eth->h_dest */
+    memcpy(rec + 84, &ifindex, 4); memcpy(rec + 92, &sampling, 4);
+    rec[96] = direction; rec[98] = dscp;
+    return 1;
+}
+
+size_t oracle_parse_snaps(const uint8_t* snaps, size_t n, uint32_t stride, uint8_t* out, uint32_t* src_of) {
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++)
+        if (oracle_parse_snap(snaps + i * stride, stride, out + m * 144)) { if (src_of) src_of[m] = (uint32_t)i; m++; }
+    return m;
+}

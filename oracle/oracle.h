@@ -145,6 +145,13 @@ size_t oracle_kmap_spilled(oracle_kmap* m, uint8_t* out_recs, size_t cap);
 uint64_t oracle_kmap_counter_fail_create(const oracle_kmap* m);
 uint64_t oracle_kmap_counter_intf_missed(const oracle_kmap* m);
 
+/* --- (f4) raw-header front end: bpf/utils.h:24-167 (set_flags, fill_l4info, fill_iphdr, fill_ip6hdr, fill_ethhdr) and
+ * the single-packet flow flow_monitor builds, bpf/flows.c:176-245.  snap = 24-byte header (ts u64, len u32, if_index
+ * u32, sampling u32, cap_len u16, direction u8, pad) + frame bytes; returns 1 and fills rec144 on SUBMIT, 0 on DISCARD.
+ * SOURCE-PINNED ONLY: the reference has no unit test for its eBPF parsing. */
+int    oracle_parse_snap(const uint8_t* snap, uint32_t stride, uint8_t* rec144);
+size_t oracle_parse_snaps(const uint8_t* snaps, size_t n, uint32_t stride, uint8_t* out_recs, uint32_t* src_of);
+
 /* --- hashes + sketches (this repo's spec; PARITY UNPINNED, see header comment) */
 uint64_t oracle_key_premix(const uint8_t* key40);
 uint64_t oracle_slot_hash(const uint8_t* key40);

@@ -104,10 +104,10 @@ int k1_emul_ingest_feature(void* h, int kind, const uint8_t* recs, uint32_t n) {
     Table t = e->t; Counters* ctr = e->ctr; uint32_t* so = e->slot_of;
     const uint64_t epoch = ++e->epoch, seq0 = e->feat_seq[kind];
     if (kind == 0) {
-        simt::launch(2, 256, 0, [=] { additional_fold_kernel(recs, n, t, epoch, seq0, so, ctr); });
+        simt::launch(2, kFeatTile, feature_fold_smem<AddFeat>(), [=] { feature_fold_kernel<AddFeat>(recs, n, t, epoch, seq0, so, ctr); });
         simt::launch(2, 256, 0, [=] { additional_first_kernel(recs, n, t, seq0, so); });
     } else {
-        simt::launch(2, 256, 0, [=] { dns_fold_kernel(recs, n, t, epoch, seq0, so, ctr); });
+        simt::launch(2, kFeatTile, feature_fold_smem<DnsFeat>(), [=] { feature_fold_kernel<DnsFeat>(recs, n, t, epoch, seq0, so, ctr); });
         simt::launch(2, 256, 0, [=] { dns_first_kernel(recs, n, t, seq0, so); });
     }
     e->feat_seq[kind] += n;

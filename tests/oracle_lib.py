@@ -92,6 +92,8 @@ def lib():
         "oracle_key_premix": (u64, [_u8p]),
         "oracle_slot_hash": (u64, [_u8p]),
         "oracle_owner_hash": (u64, [_u8p]),
+        "oracle_parse_snap": (C.c_int, [_u8p, u32, _u8p]),
+        "oracle_parse_snaps": (sz, [_u8p, sz, u32, _u8p, C.POINTER(u32)]),
         "oracle_cms_update": (None, [C.POINTER(u64), u32, u32, u64, _u8p, sz]),
         "oracle_cms_query": (None, [C.POINTER(u64), u32, u32, u64, _u8p, sz, C.POINTER(u64)]),
         "oracle_hll_update": (None, [_u8p, u32, u64, _u8p, sz]),
@@ -360,3 +362,14 @@ def read_from(wire):
     out = np.zeros(REC, dtype=np.uint8)
     lib().oracle_read_from(_p(w), _p(out))
     return out
+
+
+
+def parse_snaps(snaps, stride):
+    """(f4) oracle_parse_snaps: (n x stride) snapshot bytes -> (records (m,144), snapshot index of every record (m,))."""
+    b = np.ascontiguousarray(snaps).view(np.uint8).reshape(-1)
+    n = b.size // stride
+    out = np.zeros((n, 144), dtype=np.uint8)
+    src = np.zeros(n, dtype=np.uint32)
+    m = lib().oracle_parse_snaps(_p(b), n, stride, _p(out), src.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out[:m].copy(), src[:m].copy()

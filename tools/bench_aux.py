@@ -158,6 +158,28 @@ def pb_bench(n_keys=4_000_000, B=1 << 23):
     eng.close()
 
 
+def snaps_bench(B=1 << 22, n_frames=1 << 16, steps=6):
+    """(f4) fa_ingest_snaps from device memory: parse (count + parse kernels) + K1 fold, packets per second; and the parse
+    kernels alone against their byte roofline (stride + 144 algorithmic bytes per submitted packet)."""
+    from test_snaps import random_snaps
+    for stride in (88, 104):
+        rng = np.random.default_rng(stride)
+        frames = random_snaps(rng, n_frames, stride, n_hosts=250)
+        snaps = frames[rng.integers(0, n_frames, B)]
+        snaps[:, 0:8] = (1_000_000 + 7 * np.arange(B, dtype=np.uint64)).view(np.uint8).reshape(B, 8)     # increasing timestamps
+        d = torch.from_numpy(snaps.reshape(-1)).to(dev)
+        eng = fa.FlowAggEngine(1 << 22, flags=fa.FA_F_NO_FULL_CUT, max_batch=B, cuda_stream=stream.cuda_stream)
+        eng.ingest_snaps(d, stride)
+        st0 = eng.stats()
+        dt = timed(lambda i: eng.ingest_snaps(d, stride), steps) / steps
+        st1 = eng.stats()
+        sub = (st1["records_ingested"] - st0["records_ingested"]) // steps
+        print(json.dumps({"bench": "f4 snapshots -> parse -> fold (device in)", "stride": stride, "snaps": B, "submitted": sub,
+                          "flows": eng.live_flows(), "Mpkts_s": B / dt / 1e6,
+                          "algorithmic_GB_s": (B * stride + sub * REC) / dt / 1e9}), flush=True)
+        eng.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sketch", "features", "kmap"]
     if "sketch" in which:
@@ -171,3 +193,5 @@ if __name__ == "__main__":
         small_cache_bench(max_entries=100_000)
     if "pb" in which:
         pb_bench()
+    if "snaps" in which:
+        snaps_bench()
