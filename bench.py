@@ -661,7 +661,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 27,
                     help="records per step per GPU (2^27 x 144 B = 19.3 GB; 20 steps = a timed region of >= 200 ms)")
     ap.add_argument("--max-batch", type=int, default=1 << 23, help="records per K1 launch (N = 1)")
-    ap.add_argument("--mgpu-round", type=int, default=1 << 26, help="N>1: records per combine -> exchange -> fold round")
+    ap.add_argument("--mgpu-round", type=int, default=1 << 27, help="N>1: records per combine -> exchange -> fold round")
     ap.add_argument("--ring", type=int, default=2, help="distinct pre-generated input batches cycled through")
     ap.add_argument("--e2e-batch", type=int, default=1 << 22)
     ap.add_argument("--e2e-steps", type=int, default=32)

@@ -548,7 +548,9 @@ int fa_create(const fa_config* cfg, fa_engine** out) {
         CU(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
     }
     {
-        uint32_t ss = 1024; while ((uint64_t)ss < 2 * e->max_batch) ss <<= 1;
+        // one entry per flow that needs the ordered re-fold in a launch: at most one per record, and never more than the
+        // table has slots (entries are keyed by table slot)
+        uint32_t ss = 1024; while ((uint64_t)ss < 2 * std::min<uint64_t>(e->max_batch, e->slots)) ss <<= 1;
         e->scratch_slots = ss;
         CU(cudaMalloc(&e->d_scratch, (size_t)ss * sizeof(fa::FixupScratch)));
         CU(cudaMemsetAsync(e->d_scratch, 0, (size_t)ss * sizeof(fa::FixupScratch), e->stream));

@@ -212,8 +212,8 @@ def test_bad_strides_are_refused(engine_emul):
 
 @pytest.mark.gpu
 def test_snaps_gpu():
-    check(n=60_000, stride=104, max_entries=1 << 14, max_batch=16_384)
-    check(n=20_000, stride=88, max_entries=1 << 14, max_batch=1 << 20)
+    check(n=60_000, stride=104, max_entries=1 << 17, max_batch=16_384)
+    check(n=20_000, stride=88, max_entries=1 << 16, max_batch=1 << 20)
     check(n=5_000, stride=152, max_entries=1 << 14, max_batch=1 << 12)
     check_full_cut()
 
@@ -226,9 +226,9 @@ def test_snaps_from_device_memory_gpu():
     stride = 104
     snaps = random_snaps(np.random.default_rng(8), 30_000, stride)
     recs, _ = O.parse_snaps(snaps, stride)
-    acc = O.Accounter(1 << 14); acc.account(recs); want = O.sort_records(acc.evict()); acc.close()
+    acc = O.Accounter(1 << 16); acc.account(recs); want = O.sort_records(acc.evict()); acc.close()
     d = torch.from_numpy(snaps.reshape(-1).copy()).cuda()
-    with fa.FlowAggEngine(1 << 14, max_batch=8_192) as eng:
+    with fa.FlowAggEngine(1 << 16, max_batch=8_192) as eng:
         rc, took = eng.ingest_snaps(d, stride)
         assert rc == 0 and took == 30_000 and eng.stats()["h2d_bytes"] == 0
         assert np.array_equal(O.sort_records(eng.evict()), want)
