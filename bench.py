@@ -555,7 +555,7 @@ def feature_samples(wl, n_dns, n_rtt, seed=5):
     d["latency"] = rng.integers(50_000, 40_000_000, n_dns)
     d["id"], d["flags"], d["eth"] = rng.integers(1, 1 << 16, n_dns), 0x8180, 0x0800
     d["errno"] = np.where(rng.random(n_dns) < 0.02, 3, 0)
-    d["name"][:, :13] = np.frombuffer(b"\x03www\x07example", dtype=np.uint8)
+    d["name"][:, :13] = np.frombuffer(b"\x03www\x07example\x00", dtype=np.uint8)
     dns["dns"] = d
     add = np.zeros(n_rtt, dtype=O.ADDREC_DTYPE)
     add["id"] = kr

@@ -72,9 +72,14 @@ __device__ uint32_t find_or_create(const Table& t, uint64_t epoch, const uint64_
         }
         if (state == (uint32_t)TAG_CLAIMED) continue;   // being published by someone else
         __threadfence();                                // order the key reads after the tag observation
-        if (ld_cg_u64(L) == k[0] && ld_cg_u64(L + 1) == k[1] && ld_cg_u64(L + 2) == k[2] && ld_cg_u64(L + 3) == k[3] &&
-            (ld_cg_u64(L + 4) & 0x00FFFFFFFFFFFFFFull) == kk4)
-            return (uint32_t)slot;
+        {
+            // the five key words in three independent loads: one round trip, no short-circuit chain of dependent loads
+            const uint4 c0 = ld_cg_u4(&t.ident[slot * 8]), c1 = ld_cg_u4(&t.ident[slot * 8 + 1]);
+            const unsigned long long w4 = ld_cg_u64(L + 4);
+            const bool same = (u64_of(c0.x, c0.y) == k[0]) & (u64_of(c0.z, c0.w) == k[1]) & (u64_of(c1.x, c1.y) == k[2]) &
+                              (u64_of(c1.z, c1.w) == k[3]) & ((w4 & 0x00FFFFFFFFFFFFFFull) == kk4);
+            if (same) return (uint32_t)slot;
+        }
         slot = (slot + 1) & t.mask;
         probes++;
     }
@@ -120,12 +125,12 @@ struct AddFeat {                        // additional_metrics samples, 72 B
         v[5] = end;
         v[6] = eth ? ~((seq << 16) | eth) : 0ull;
     }
-    static __device__ __forceinline__ void fold(uint64_t* a, const uint64_t* v) {
+    static __device__ __forceinline__ void fold(uint64_t* a, int st, const uint64_t* v) {
 #pragma unroll
-        for (int k = 0; k < kAcc; k++) smem_max_u64(a + k, v[k]);
+        for (int k = 0; k < kAcc; k++) smem_max_u64(a + k * st, v[k]);
     }
-    static __device__ __forceinline__ void flush(uint8_t* S, const uint64_t* a) {
-        gmax(S + 0, a[0]); gmax(S + 8, a[1]); gmax(S + 72, a[2]); gmax(S + 16, a[3]); gmax(S + 24, a[4]); gmax(S + 32, a[5]); gmax(S + 40, a[6]);
+    static __device__ __forceinline__ void flush(uint8_t* S, const uint64_t* a, int st) {
+        gmax(S + 0, a[0 * st]); gmax(S + 8, a[1 * st]); gmax(S + 72, a[2 * st]); gmax(S + 16, a[3 * st]); gmax(S + 24, a[4 * st]); gmax(S + 32, a[5 * st]); gmax(S + 40, a[6 * st]);
     }
 };
 struct DnsFeat {                        // dns_metrics samples, 104 B
@@ -145,14 +150,14 @@ struct DnsFeat {                        // dns_metrics samples, 104 B
         v[6] = eth ? ~((seq << 16) | eth) : 0ull;
         v[7] = flags;
     }
-    static __device__ __forceinline__ void fold(uint64_t* a, const uint64_t* v) {
+    static __device__ __forceinline__ void fold(uint64_t* a, int st, const uint64_t* v) {
 #pragma unroll
-        for (int k = 0; k < 7; k++) smem_max_u64(a + k, v[k]);
-        smem_or_u64(a + 7, v[7]);
+        for (int k = 0; k < 7; k++) smem_max_u64(a + k * st, v[k]);
+        smem_or_u64(a + 7 * st, v[7]);
     }
-    static __device__ __forceinline__ void flush(uint8_t* S, const uint64_t* a) {
-        gmax(S + 0, a[0]); gmax(S + 8, a[1]); gmax(S + 16, a[2]); gmax(S + 24, a[3]); gmax(S + 32, a[4]); gmax(S + 40, a[5]); gmax(S + 48, a[6]);
-        gor32(S + 56, a[7]);
+    static __device__ __forceinline__ void flush(uint8_t* S, const uint64_t* a, int st) {
+        gmax(S + 0, a[0 * st]); gmax(S + 8, a[1 * st]); gmax(S + 16, a[2 * st]); gmax(S + 24, a[3 * st]); gmax(S + 32, a[4 * st]); gmax(S + 40, a[5 * st]); gmax(S + 48, a[6 * st]);
+        gor32(S + 56, a[7 * st]);
     }
 };
 // pkt_drop_metrics samples (flow_id 40 B + start 8, end 8, bytes u16, packets u16, latest_drop_cause u32, latest_flags u16,
@@ -177,18 +182,34 @@ struct DropFeat {
         v[7] = end;
         v[8] = eth ? ~((seq << 16) | eth) : 0ull;
     }
-    static __device__ __forceinline__ void fold(uint64_t* a, const uint64_t* v) {
-        smem_max_u64(a + 0, v[0]); smem_add_u64(a + 1, v[1]); smem_add_u64(a + 2, v[2]); smem_max_u64(a + 3, v[3]); smem_max_u64(a + 4, v[4]);
-        smem_or_u64(a + 5, v[5]); smem_max_u64(a + 6, v[6]); smem_max_u64(a + 7, v[7]); smem_max_u64(a + 8, v[8]);
+    static __device__ __forceinline__ void fold(uint64_t* a, int st, const uint64_t* v) {
+        smem_max_u64(a + 0 * st, v[0]); smem_add_u64(a + 1 * st, v[1]); smem_add_u64(a + 2 * st, v[2]); smem_max_u64(a + 3 * st, v[3]);
+        smem_max_u64(a + 4 * st, v[4]); smem_or_u64(a + 5 * st, v[5]); smem_max_u64(a + 6 * st, v[6]); smem_max_u64(a + 7 * st, v[7]);
+        smem_max_u64(a + 8 * st, v[8]);
     }
-    static __device__ __forceinline__ void flush(uint8_t* S, const uint64_t* a) {
-        gmax(S + 0, a[0]); gadd(S + 8, a[1]); gadd(S + 16, a[2]); gmax(S + 24, a[3]); gmax(S + 32, a[4]); gor32(S + 40, a[5]);
-        gmax(S + 48, a[6]); gmax(S + 56, a[7]); gmax(S + 64, a[8]);
+    static __device__ __forceinline__ void flush(uint8_t* S, const uint64_t* a, int st) {
+        gmax(S + 0, a[0 * st]); gadd(S + 8, a[1 * st]); gadd(S + 16, a[2 * st]); gmax(S + 24, a[3 * st]); gmax(S + 32, a[4 * st]); gor32(S + 40, a[5 * st]);
+        gmax(S + 48, a[6 * st]); gmax(S + 56, a[7 * st]); gmax(S + 64, a[8 * st]);
     }
 };
 
+// CTA-wide cache of hot flows, alive across the tiles of one launch: a flow with >= 3 samples in one tile is installed
+// (key, table slot, zeroed accumulators); later samples of that flow fold into the entry with shared-memory atomics and
+// touch neither the election nor the table; the entries are flushed with one set of reductions when the CTA runs out of
+// tiles.  Without it every tile sends its own reductions for the hottest flows to the same few L2 addresses.
+constexpr int kFeatHot = 32;
+constexpr uint32_t kFeatCached = 0xFFFFFFFEu;
+template <class F> struct FeatHot {
+    uint64_t key[5];
+    uint32_t state, slot;                       // state: 0 empty, 1 being filled, 2 live
+    uint64_t acc[F::kAcc];
+};
+
 template <class F> constexpr size_t feature_fold_smem() {
-    return (size_t)kFeatTile * F::kRec + (size_t)kFeatTile * F::kAcc * 8 + kFeatRep * 4 + kFeatTile * 4;
+    // tile (re-used for the representatives' accumulators once the keys are no longer needed) | election set | slots |
+    // duplicate counts | hot-flow cache
+    constexpr size_t tile = (size_t)kFeatTile * (F::kRec > F::kAcc * 8 ? F::kRec : F::kAcc * 8);
+    return tile + kFeatRep * 4 + kFeatTile * 4 + kFeatTile * 4 + kFeatHot * sizeof(FeatHot<F>);
 }
 
 template <class F>
@@ -196,55 +217,92 @@ __global__ void __launch_bounds__(kFeatTile)
 feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, uint64_t seq0,
                     uint32_t* __restrict__ slot_of, Counters* ctr) {
     FA_DYN_SMEM(sm);
-    uint64_t* tile = reinterpret_cast<uint64_t*>(sm);                         // kFeatTile samples
-    uint64_t* acc = tile + kFeatTile * (F::kRec / 8);                         // [kFeatTile][kAcc]
-    uint32_t* rep = reinterpret_cast<uint32_t*>(acc + kFeatTile * F::kAcc);   // [kFeatRep] election set
+    constexpr size_t kTileBytes = (size_t)kFeatTile * (F::kRec > F::kAcc * 8 ? F::kRec : F::kAcc * 8);
+    uint64_t* tile = reinterpret_cast<uint64_t*>(sm);                         // kFeatTile samples ...
+    uint64_t* acc = tile;                                                     // ... then [kAcc][kFeatTile] accumulators
+    uint32_t* rep = reinterpret_cast<uint32_t*>(sm + kTileBytes);             // [kFeatRep] election set
     uint32_t* slot_s = rep + kFeatRep;                                        // [kFeatTile] slot found by each representative
+    uint32_t* dupc = slot_s + kFeatTile;                                      // [kFeatTile] duplicates folded into it
+    FeatHot<F>* hot = reinterpret_cast<FeatHot<F>*>(dupc + kFeatTile);
     const uint32_t tid = threadIdx.x;
+    if (tid < kFeatHot) hot[tid].state = 0u;
     const uint32_t n_tiles = (n + kFeatTile - 1) / kFeatTile;
     for (uint32_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
         const uint32_t first = tix * kFeatTile, cnt = min((uint32_t)kFeatTile, n - first);
         const uint64_t* G = reinterpret_cast<const uint64_t*>(recs + (size_t)first * F::kRec);
-        for (uint32_t w = tid; w < cnt * (F::kRec / 8); w += kFeatTile) tile[w] = G[w];
+        if (cnt == (uint32_t)kFeatTile) {                                    // all loads in flight before the first store
+            uint64_t tmp[F::kRec / 8];
+#pragma unroll
+            for (int w = 0; w < F::kRec / 8; w++) tmp[w] = G[tid + w * kFeatTile];
+#pragma unroll
+            for (int w = 0; w < F::kRec / 8; w++) tile[tid + w * kFeatTile] = tmp[w];
+        } else {
+            for (uint32_t w = tid; w < cnt * (F::kRec / 8); w += kFeatTile) tile[w] = G[w];
+        }
         for (uint32_t w = tid; w < kFeatRep; w += kFeatTile) rep[w] = kFeatNone;
         __syncthreads();
         const bool valid = tid < cnt;
         const uint8_t* R = reinterpret_cast<const uint8_t*>(tile) + (size_t)tid * F::kRec;
-        uint32_t r = tid;                                                     // my representative
+        uint32_t r = tid, my_slot = kFeatNone, hq = 0;                        // my representative; cached flows: the entry's slot
         uint64_t k[5] = {0, 0, 0, 0, 0}, v[F::kAcc];
         if (valid) {
             load_key(R, k);
             k[4] &= 0x00FFFFFFFFFFFFFFull;
-            uint32_t q = (uint32_t)(slot_hash(key_premix(k[0], k[1], k[2], k[3], k[4])) >> 40) & (kFeatRep - 1);
-            for (int step = 0; step < 8; step++) {
-                const uint32_t cur = atomicCAS(&rep[q], kFeatNone, tid);
-                if (cur == kFeatNone) break;                                  // nobody holds this key yet: I represent it
-                const uint64_t* K = tile + (size_t)cur * (F::kRec / 8);
-                if (K[0] == k[0] && K[1] == k[1] && K[2] == k[2] && K[3] == k[3] && (K[4] & 0x00FFFFFFFFFFFFFFull) == k[4]) { r = cur; break; }
-                q = (q + 1) & (kFeatRep - 1);                                 // after 8 steps: stay my own representative (unmerged, still exact)
-            }
+            const uint64_t h = slot_hash(key_premix(k[0], k[1], k[2], k[3], k[4]));
             F::extract(R, seq0 + first + tid, v);
-            if (r == tid) {
-#pragma unroll
-                for (int a = 0; a < F::kAcc; a++) acc[tid * F::kAcc + a] = v[a];
+            hq = (uint32_t)(h >> 52) & (kFeatHot - 1);
+            FeatHot<F>& e = hot[hq];
+            if (e.state == 2u && e.key[0] == k[0] && e.key[1] == k[1] && e.key[2] == k[2] && e.key[3] == k[3] && e.key[4] == k[4]) {
+                r = kFeatCached;                                              // hot flow: no election, no probe, no global reduction
+                my_slot = e.slot;
+            } else {
+                uint32_t q = (uint32_t)(h >> 40) & (kFeatRep - 1);
+                for (int step = 0; step < 8; step++) {
+                    const uint32_t cur = atomicCAS(&rep[q], kFeatNone, tid);
+                    if (cur == kFeatNone) break;                              // nobody holds this key yet: I represent it
+                    const uint64_t* K = tile + (size_t)cur * (F::kRec / 8);
+                    if (K[0] == k[0] && K[1] == k[1] && K[2] == k[2] && K[3] == k[3] && (K[4] & 0x00FFFFFFFFFFFFFFull) == k[4]) { r = cur; break; }
+                    q = (q + 1) & (kFeatRep - 1);                             // after 8 steps: stay my own representative (unmerged, still exact)
+                }
             }
         }
+        if (valid && r == kFeatCached) F::fold(hot[hq].acc, 1, v);
+        __syncthreads();                                                      // the samples are parsed: the tile becomes the accumulators
+        if (valid && r == tid) {
+#pragma unroll
+            for (int a = 0; a < F::kAcc; a++) acc[a * kFeatTile + tid] = v[a];   // field-major: neighbours hit neighbouring banks
+            dupc[tid] = 0u;
+        }
         __syncthreads();
-        if (valid && r != tid) F::fold(acc + r * F::kAcc, v);
+        if (valid && r < (uint32_t)kFeatTile && r != tid) { F::fold(acc + r, kFeatTile, v); atomicAdd(&dupc[r], 1u); }
         __syncthreads();
         if (valid && r == tid) {
             const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
             slot_s[tid] = slot;
-            if (slot != kFeatNone) F::flush(F::state(t, slot), acc + tid * F::kAcc);
+            if (slot != kFeatNone) {
+                F::flush(F::state(t, slot), acc + tid, kFeatTile);
+                FeatHot<F>& e = hot[hq];
+                if (dupc[tid] >= 2u && atomicCAS(&e.state, 0u, 1u) == 0u) {    // three samples in one tile: worth an entry
+#pragma unroll
+                    for (int c = 0; c < 5; c++) e.key[c] = k[c];
+#pragma unroll
+                    for (int a = 0; a < F::kAcc; a++) e.acc[a] = 0ull;
+                    e.slot = slot;
+                    __threadfence_block();
+                    *reinterpret_cast<volatile uint32_t*>(&e.state) = 2u;     // readers look at it after the next barrier
+                }
+            }
         }
         __syncthreads();
         if (valid) {
-            const uint32_t slot = slot_s[r];
+            const uint32_t slot = r == kFeatCached ? my_slot : slot_s[r];
             slot_of[first + tid] = slot;
             if (slot == kFeatNone) atomicAdd(&ctr->spills, 1ull);
         }
         __syncthreads();                                                      // tile / rep / slot_s are re-used
     }
+    __syncthreads();
+    if (tid < kFeatHot && hot[tid].state == 2u) F::flush(F::state(t, hot[tid].slot), hot[tid].acc, 1);
 }
 
 // second pass: the sample that turned out to be the flow's first one writes the adopted block fields
@@ -300,7 +358,12 @@ template <class F, class First>
 static int launch_fold(First first_kernel, const uint8_t* recs, uint32_t n, const Table& t, uint64_t epoch, uint64_t seq0, uint32_t* slot_of,
                        Counters* ctr, int sm_count, cudaStream_t st) {
     const uint32_t n_tiles = (n + kFeatTile - 1) / kFeatTile;
-    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count * 8u);      // persistent over tiles; 4-5 CTAs of ~40-46 KB fit an SM
+    // persistent over tiles: exactly as many CTAs as are resident at once (a partial second wave would leave SMs idle)
+    static int per_sm = 0;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, feature_fold_kernel<F>, kFeatTile, feature_fold_smem<F>()) != cudaSuccess || per_sm < 1) per_sm = 4;
+    }
+    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(sm_count * per_sm));
     feature_fold_kernel<F><<<grid, kFeatTile, feature_fold_smem<F>(), st>>>(recs, n, t, epoch, seq0, slot_of, ctr);
     first_kernel<<<sm_count * 8, 256, 0, st>>>(recs, n, t, seq0, slot_of);
     return 2;

@@ -308,7 +308,15 @@ route_peer_kernel(const uint4* __restrict__ recs, const unsigned long long* __re
     for (uint32_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
         const uint32_t first = tix * kRouteTile, cnt = min((uint32_t)kRouteTile, n - first);
         const uint4* G = recs + (size_t)first * kRecChunks;
-        for (uint32_t q = tid; q < cnt * kRecChunks; q += kRouteTile) tile[q] = ld_stream_u4(G + q);
+        if (cnt == (uint32_t)kRouteTile) {                                   // all nine loads in flight before the first store
+            uint4 tmp[kRecChunks];
+#pragma unroll
+            for (int c = 0; c < kRecChunks; c++) tmp[c] = ld_stream_u4(G + tid + c * kRouteTile);
+#pragma unroll
+            for (int c = 0; c < kRecChunks; c++) tile[tid + c * kRouteTile] = tmp[c];
+        } else {
+            for (uint32_t q = tid; q < cnt * kRecChunks; q += kRouteTile) tile[q] = ld_stream_u4(G + q);
+        }
         if (tid < (kRouteTile / 32) * kMaxShards) (&wcount[0][0])[tid] = 0u;
         __syncthreads();
         uint32_t o = 0xFFu, rank = 0;

@@ -130,7 +130,15 @@ snap_parse_kernel(const uint8_t* __restrict__ snaps, uint32_t n, uint32_t stride
     for (uint32_t t = t0; t < t1; t++) {
         const uint32_t first = t * kSnapTile, cnt = min((uint32_t)kSnapTile, n - first);
         const uint64_t* G = reinterpret_cast<const uint64_t*>(snaps + (size_t)first * stride);
-        for (uint32_t w = tid; w < cnt * words; w += kSnapTile) tile[w] = G[w];
+        {                                                                 // groups of four loads in flight before their stores
+            const uint32_t total = cnt * words;
+            uint32_t w = tid;
+            for (; w + 3 * kSnapTile < total; w += 4 * kSnapTile) {
+                const uint64_t a0 = G[w], a1 = G[w + kSnapTile], a2 = G[w + 2 * kSnapTile], a3 = G[w + 3 * kSnapTile];
+                tile[w] = a0; tile[w + kSnapTile] = a1; tile[w + 2 * kSnapTile] = a2; tile[w + 3 * kSnapTile] = a3;
+            }
+            for (; w < total; w += kSnapTile) tile[w] = G[w];
+        }
         __syncthreads();
         const uint8_t* S = reinterpret_cast<const uint8_t*>(tile) + (size_t)tid * stride;
         const bool ok = tid < cnt && snap_submits(*reinterpret_cast<const uint64_t*>(S + 16), *reinterpret_cast<const uint64_t*>(S + 32), stride);
