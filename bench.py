@@ -250,6 +250,8 @@ def run_ours(args, wl):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
+    if args.max_batch is None:
+        args.max_batch = (1 << 24) if wl["no_full_cut"] else (1 << 23)
     max_batch = args.max_batch if world == 1 else args.mgpu_round
     no_cut = wl["no_full_cut"] or world > 1          # N>1: the owner table is a plain map behind the exchange
     eng = fa.FlowAggEngine(wl["max_entries"], device=local, max_batch=max_batch, cuda_stream=stream.cuda_stream,
@@ -660,7 +662,9 @@ def main():
     ap.add_argument("--workload", default="zipf10m", choices=sorted(WORKLOADS) + ["rttdns"])
     ap.add_argument("--batch", type=int, default=1 << 27,
                     help="records per step per GPU (2^27 x 144 B = 19.3 GB; 20 steps = a timed region of >= 200 ms)")
-    ap.add_argument("--max-batch", type=int, default=1 << 23, help="records per K1 launch (N = 1)")
+    ap.add_argument("--max-batch", type=int, default=None,
+                    help="records per K1 launch (N = 1); default 2^23 with the Accounter's maxEntries rule on (the largest size "
+                         "that keeps its fast-path test true on every workload), 2^24 for the plain-map workload zipf1m")
     ap.add_argument("--mgpu-round", type=int, default=1 << 27, help="N>1: records per combine -> exchange -> fold round")
     ap.add_argument("--ring", type=int, default=2, help="distinct pre-generated input batches cycled through")
     ap.add_argument("--e2e-batch", type=int, default=1 << 22)
