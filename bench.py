@@ -38,6 +38,13 @@ WORKLOADS = {
     # so this workload runs the table as a plain map (FA_F_NO_FULL_CUT: max_entries only sizes it)
     "zipf1m": dict(n_keys=1_000_000, dist=1, seed=2, max_entries=3 << 19, no_full_cut=True,
                    label="synthetic record stream, 1M Zipf-1.1 5-tuples (BASELINE configs[1])"),
+    # BASELINE configs[2]: the fused count-min (w = 2^20, d = 4) + HyperLogLog (p = 14) update inside K1, 100 M-key universe
+    # (a 2^27-record step touches ~7 M of them; the exact table stays on as a plain map so that the same run checks flows,
+    # sketch tables bit for bit against the CPU restatement, and the (eps, delta) / 3-sigma bounds against exact counts)
+    "sketch100m": dict(n_keys=100_000_000, dist=1, seed=3, max_entries=3 << 25, no_full_cut=True,
+                       sketch=dict(cms_log2_width=20, cms_depth=4, hll_precision=14, sketch_seed=0x5EED),
+                       label="synthetic record stream, 100M Zipf-1.1 5-tuples, K1 with the fused count-min (w=2^20, d=4) + "
+                             "HLL (p=14) update (BASELINE configs[2])"),
 }
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")
 
@@ -210,21 +217,34 @@ def record_order(r):
     return np.lexsort((h2, h1))
 
 
-def oracle_flows(wl, first, n, chunk=1 << 22):
-    """The oracle's flows for records [first, first+n) of the workload stream, sorted like record_order()."""
+def oracle_flows(wl, first, n, chunk=1 << 22, sketch=None):
+    """The oracle's flows for records [first, first+n) of the workload stream, sorted like record_order(); with `sketch`
+    (the workload's sketch parameters) also the CPU restatement's count-min table and HLL registers over the same records."""
+    import ctypes as C
     import oracle_lib as O
     threads = min(host_threads(), 32)
     g = oracle_gen(wl)
     acc = O.ShardedAccounter(threads)
     buf = np.empty(chunk * REC, dtype=np.uint8)
+    cms = hll = None
+    if sketch:
+        cms = np.zeros(sketch["cms_depth"] << sketch["cms_log2_width"], dtype=np.uint64)
+        hll = np.zeros(1 << sketch["hll_precision"], dtype=np.uint8)
     done = 0
     while done < n:
         c = min(chunk, n - done)
-        acc.account(g.records(first + done, c, threads=threads, out=buf[: c * REC]))
+        r = g.records(first + done, c, threads=threads, out=buf[: c * REC])
+        acc.account(r)
+        if sketch:
+            b = O.as_bytes(r)
+            O.lib().oracle_cms_update(cms.ctypes.data_as(C.POINTER(C.c_uint64)), sketch["cms_log2_width"], sketch["cms_depth"],
+                                      sketch["sketch_seed"], O._p(b), c)
+            O.lib().oracle_hll_update(O._p(hll), sketch["hll_precision"], sketch["sketch_seed"], O._p(b), c)
         done += c
     out = acc.evict()
     acc.close(); g.close()
-    return out[record_order(out)]
+    out = out[record_order(out)]
+    return (out, cms, hll) if sketch else out
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -255,7 +275,8 @@ def run_ours(args, wl):
     max_batch = args.max_batch if world == 1 else args.mgpu_round
     no_cut = wl["no_full_cut"] or world > 1          # N>1: the owner table is a plain map behind the exchange
     eng = fa.FlowAggEngine(wl["max_entries"], device=local, max_batch=max_batch, cuda_stream=stream.cuda_stream,
-                           flags=fa.FA_F_NO_FULL_CUT if no_cut else 0)
+                           flags=(fa.FA_F_NO_FULL_CUT if no_cut else 0) | (fa.FA_F_ENABLE_SKETCH if wl.get("sketch") else 0),
+                           **(wl.get("sketch") or {}))
     # one key universe for the whole job; every rank generates its own slice of the record stream
     gp = fa.GenParams(seed=wl["seed"], n_keys=wl["n_keys"], dist=wl["dist"], zipf_s_milli=1100,
                       t0_ns=1_000_000, varying_desc=0)
@@ -360,6 +381,8 @@ def run_ours(args, wl):
         V0 = 1 << 40                                 # far beyond anything the timed loop consumed
         finish()
         evict_dev()                                  # discard the timed loop's flows
+        if wl.get("sketch"):
+            eng.sketch_reset()
         mine = V // world
         done = 0
         while done < mine:                           # regenerate into the (now free) input ring, chunk by chunk
@@ -369,6 +392,10 @@ def run_ours(args, wl):
             finish()
             torch.cuda.synchronize()
             done += c
+        sk_ours = None
+        if wl.get("sketch"):                          # before the eviction: the table's exact counts are the yardstick
+            sp = wl["sketch"]
+            sk_ours = eng.sketch_export(sp["cms_log2_width"], sp["cms_depth"], sp["hll_precision"]) + (eng.hll_estimate(),)
         out_dev, nfl = evict_dev()
         if world > 1:                                # concatenate on rank 0 (padded all_gather of byte tensors)
             cnt = torch.tensor([nfl], device=dev, dtype=torch.int64)
@@ -385,7 +412,10 @@ def run_ours(args, wl):
             ours = out_dev[: nfl * REC].cpu().numpy().reshape(-1, REC)
         if rank == 0:
             t0 = time.perf_counter()
-            want = oracle_flows(wl, V0, V)
+            want = oracle_flows(wl, V0, V, sketch=wl.get("sketch"))
+            sk_want = None
+            if wl.get("sketch"):
+                want, *sk_want = want
             ours = ours[record_order(ours)]
             same = ours.shape == want.shape and bool(np.array_equal(ours, want))
             parity = {"parity_checked": int(len(want)) if same else 0, "parity_ok": same, "records": V,
@@ -394,6 +424,26 @@ def run_ours(args, wl):
                       "how": "fresh cache, records [2^40, 2^40+V) of the workload stream through the same engine"
                              + ("" if world == 1 else f" (sharded over {world} GPUs, evictions concatenated)") +
                              "; every flow record compared bit for bit with the CPU oracle's fold of the same records"}
+            if sk_ours is not None:
+                import math
+                import oracle_lib as O
+                sp = wl["sketch"]
+                cms, hll, est = sk_ours
+                parity["sketch_bit_exact"] = bool(np.array_equal(cms.reshape(-1), sk_want[0]) and np.array_equal(hll, sk_want[1]))
+                f = np.ascontiguousarray(want).view(O.REC_DTYPE).reshape(-1)
+                parity["hll_estimate"], parity["distinct_exact"] = est, int(len(f))
+                parity["hll_rel_err"] = abs(est - len(f)) / max(len(f), 1)
+                parity["hll_3sigma"] = 3 * 1.04 / math.sqrt(1 << sp["hll_precision"])
+                samp = want[:: max(1, len(want) // 200_000)]            # point queries on a sample of the flows
+                q = eng.cms_query(samp[:, :40]).astype(np.int64)
+                exact = np.ascontiguousarray(samp).view(O.REC_DTYPE).reshape(-1)["packets"].astype(np.int64)
+                eps_n = math.e / (1 << sp["cms_log2_width"]) * V
+                parity["cms_never_under"] = bool((q >= exact).all())
+                parity["cms_within_eps_frac"] = float(((q - exact) <= eps_n).mean())
+                parity["cms_bound_frac"] = 1 - math.exp(-sp["cms_depth"])
+                parity["parity_ok"] = bool(same and parity["sketch_bit_exact"] and parity["cms_never_under"]
+                                           and parity["hll_rel_err"] <= parity["hll_3sigma"]
+                                           and parity["cms_within_eps_frac"] >= parity["cms_bound_frac"] - 0.005)
             if not same:
                 nbad = -1
                 if ours.shape == want.shape:
@@ -422,7 +472,7 @@ def run_ours(args, wl):
                 eng.sync()
                 h.copy_(d)
                 hring.append(h)
-            out_host = torch.empty(min(wl["max_entries"], wl["n_keys"]) * REC, dtype=torch.uint8).pin_memory()
+            out_host = torch.empty(min(wl["max_entries"], wl["n_keys"], 1 << 25) * REC, dtype=torch.uint8).pin_memory()
         except Exception as ex:                                # noqa: BLE001 - reported in the JSON line
             prep_err = repr(ex)
         ok = torch.tensor([0 if prep_err else 1], device=dev, dtype=torch.int32)
