@@ -147,6 +147,32 @@ typedef struct fa_packet_snap_hdr {
     /* uint8_t data[stride - 24] follows */
 } fa_packet_snap_hdr;                /* 24 bytes */
 
+/* Flow filter in front of fa_ingest_snaps: the rules of the reference's filter_map / peer_filter_map LPM tries
+ * (bpf/maps_definition.h:108-127, at most 16 entries each) and the matching of bpf/flows_filter.h:14-255 +
+ * check_and_do_flow_filtering (bpf/utils.h:179-222).  A rule = its LPM key (CIDR: prefix_len + address bytes, IPv4
+ * rules carry their 4 address bytes first, exactly like the trie key) + filter_value_t (bpf/types.h:300-322). */
+typedef struct fa_filter_rule {
+    uint8_t  ip[FA_IP_LEN];          /*  0 LPM key data */
+    uint32_t prefix_len;             /* 16 LPM key prefix length in bits */
+    uint32_t sample;                 /* 20 != 0: becomes the packet's sampling */
+    uint16_t dst_port_start, dst_port_end, dst_port1, dst_port2;   /* 24 */
+    uint16_t src_port_start, src_port_end, src_port1, src_port2;   /* 32 */
+    uint16_t port_start, port_end, port1, port2;                   /* 40 */
+    uint16_t tcp_flags;              /* 48 compared with the packet's set_flags() value when != 0 */
+    uint8_t  protocol;               /* 50 0 = any */
+    uint8_t  icmp_type, icmp_code;   /* 51 */
+    uint8_t  direction;              /* 53 0 ingress, 1 egress, 2 (MAX_DIRECTION) = any */
+    uint8_t  action;                 /* 54 0 ACCEPT, 1 REJECT, 2 (MAX_FILTER_ACTIONS) = none */
+    uint8_t  filter_drops;           /* 55 rule wants packets with a drop reason: never matches here (flows.c:194 passes 0) */
+    uint8_t  do_peer_cidr_lookup;    /* 56 */
+    uint8_t  pad_[7];                /* 57 */
+} fa_filter_rule;                    /* 64 bytes */
+
+typedef struct fa_filter_cidr {      /* one peer_filter_map key */
+    uint8_t  ip[FA_IP_LEN];
+    uint32_t prefix_len;
+} fa_filter_cidr;                    /* 20 bytes */
+
 /* Feature-stream input records: the key plus one feature sample — what the
  * reference keeps per CPU slot in aggregated_flows_dns / additional_flow_metrics
  * (bpf/maps_definition.h:24-31,64-71). */
@@ -261,6 +287,9 @@ typedef struct fa_stats {
     uint64_t pkt_drops_ingested;  /* samples consumed by fa_ingest_pkt_drops */
     uint64_t snaps_ingested;      /* packet snapshots consumed by fa_ingest_snaps ...                       */
     uint64_t snaps_discarded;     /* ... of which fill_ethhdr said DISCARD (not IP, truncated IP header)    */
+    uint64_t filter_accept;       /* global counter FILTER_ACCEPT  (utils.h:196-197)                        */
+    uint64_t filter_reject;       /* global counter FILTER_REJECT  (utils.h:192-194), packet skipped        */
+    uint64_t filter_nomatch;      /* global counter FILTER_NOMATCH (utils.h:211)                            */
 } fa_stats;
 
 typedef struct fa_engine fa_engine;
@@ -297,6 +326,14 @@ int fa_ingest_events(fa_engine* e, const void* packet_events, size_t n, size_t* 
  * dropped and counted in fa_stats.snaps_discarded.  *consumed counts SNAPSHOTS (parsed or discarded); < n only with
  * FA_FULL.  The flow filter (bpf/flows_filter.h) is not part of this entry point. */
 int fa_ingest_snaps(fa_engine* e, const void* snaps, size_t n, uint32_t stride, size_t* consumed);
+
+/* Install (n_rules > 0) or remove (n_rules == 0) the flow filter applied by fa_ingest_snaps right after the header
+ * parse, where flow_monitor calls check_and_do_flow_filtering (flows.c:193-195): longest-prefix match of the source
+ * address in `rules`, then of the destination address, the rule's protocol / port / ICMP / TCP-flag / direction / peer-CIDR
+ * conditions, ACCEPT / REJECT semantics and the three global counters exactly as in the reference; a matching rule's
+ * `sample` becomes the packet's sampling.  The random 1-in-N sampling decision itself (bpf_get_prandom_u32) is NOT
+ * taken here.  At most 16 rules and 16 peer CIDRs (MAX_FILTER_ENTRIES). */
+int fa_set_flow_filter(fa_engine* e, const fa_filter_rule* rules, size_t n_rules, const fa_filter_cidr* peers, size_t n_peers);
 
 /* Fold n (flow_id + additional_metrics) samples: RTT keep-max, IPsec rules.
  * Replaces: bpf/rtt_tracker.h:12-22,73-91 + AccumulateAdditional

@@ -9,7 +9,7 @@ from ._lib import (FA_FULL, FA_OK, FlowAggError, GenParams, Stats, lib, lib_path
                    FA_F_ENABLE_DNS, FA_F_ENABLE_RTT, FA_F_ENABLE_SKETCH, FA_F_NO_FULL_CUT, FA_F_RINGBUF_FALLBACK, FA_F_ENABLE_PKT_DROP, FA_F_NONBLOCKING_EVICT,
                    FA_GEN_UNIFORM, FA_GEN_ZIPF,
                    FA_MODE_ACCOUNTER, FA_MODE_KERNEL_MAP, REC_BYTES)
-from .engine import FlowAggEngine, gen_records_host, gen_key  # noqa: F401
+from .engine import FILTER_CIDR_DTYPE, FILTER_RULE_DTYPE, FlowAggEngine, gen_records_host, gen_key  # noqa: F401
 from .accounter import Accounter, MapTracer, new_record_times  # noqa: F401
 
 __all__ = ["FlowAggEngine", "Accounter", "MapTracer", "FlowAggError", "GenParams", "Stats", "lib", "lib_path",

@@ -32,7 +32,7 @@ class Stats(C.Structure):
         "records_ingested", "dns_ingested", "additional_ingested", "flows_evicted", "evictions", "live_flows",
         "spills", "order_fixups", "full_cuts", "kernel_launches", "h2d_bytes", "d2h_bytes",
         "observed_intf_missed", "hashmap_fail_create", "ringbuf_spilled", "ringbuf_dropped", "pkt_drops_ingested",
-        "snaps_ingested", "snaps_discarded")]
+        "snaps_ingested", "snaps_discarded", "filter_accept", "filter_reject", "filter_nomatch")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
@@ -71,6 +71,7 @@ SIGNATURES = {
     "fa_ingest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_ingest_events": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_ingest_snaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t)]),
+    "fa_set_flow_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "fa_ingest_additional": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_ingest_dns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_ingest_pkt_drops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -138,7 +138,9 @@ struct fa_engine {
 
     uint8_t* d_expanded = nullptr;            // ... and their 144-byte expansion (events handed in as device memory)
     uint32_t* d_snap_src = nullptr;           // fa_ingest_snaps: snapshot index of every record parsed out of a chunk
-    uint32_t* d_snap_cnt = nullptr;           // ... records per CTA of the parse kernels, then the total (u64, 8-byte aligned)
+    uint32_t* d_snap_cnt = nullptr;           // ... records per CTA of the parse kernels, then the total + 3 filter counters (u64)
+    uint8_t* d_snap_verdict = nullptr;        // ... with a flow filter: keep / skip per snapshot of the chunk
+    fa::FilterSet filter{};                   // fa_set_flow_filter (n_rules == 0: no filter)
     uint8_t* d_evict = nullptr; uint64_t evict_cap = 0;
     uint8_t* d_evict_dns = nullptr; uint8_t* d_evict_add = nullptr; uint8_t* d_evict_present = nullptr;
     uint32_t* d_slot_of_out = nullptr; uint64_t feat_evict_cap = 0;
@@ -626,7 +628,7 @@ void fa_destroy(fa_engine* e) {
     cudaFree(e->d_scratch); cudaFree(e->d_spill_idx); cudaFree(e->d_cut_set); cudaFree(e->d_cut_bitmap); cudaFree(e->d_cut_out);
     if (e->h_cut_out) cudaFreeHost(e->h_cut_out);
     cudaFree(e->d_evict); cudaFree(e->d_route_tmp); cudaFree(e->d_route_counts); cudaFree(e->d_expanded);
-    cudaFree(e->d_snap_src); cudaFree(e->d_snap_cnt);
+    cudaFree(e->d_snap_src); cudaFree(e->d_snap_cnt); cudaFree(e->d_snap_verdict);
     cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out); cudaFree(e->d_slot_of);
     cudaFree(e->d_evict_drop); cudaFree(e->d_evict_rttmin);
     cudaFree(e->sk.cms); cudaFree(e->sk.hll);
@@ -715,7 +717,8 @@ int fa_ingest_snaps(fa_engine* e, const void* snaps, size_t n, uint32_t stride, 
     if (k == PTR_DEVICE && (reinterpret_cast<uintptr_t>(snaps) & 7)) return fail(FA_E_INVAL, "fa_ingest_snaps: device snapshots must be 8-byte aligned");
     if (!e->d_expanded) CU(cudaMalloc(&e->d_expanded, e->max_batch * fa::kRecBytes));
     if (!e->d_snap_src) CU(cudaMalloc(&e->d_snap_src, e->max_batch * sizeof(uint32_t)));
-    if (!e->d_snap_cnt) CU(cudaMalloc(&e->d_snap_cnt, (fa::kSnapMaxCtas + 2) * sizeof(uint32_t)));
+    if (!e->d_snap_cnt) CU(cudaMalloc(&e->d_snap_cnt, (fa::kSnapMaxCtas + 8) * sizeof(uint32_t)));
+    if (e->filter.n_rules && !e->d_snap_verdict) CU(cudaMalloc(&e->d_snap_verdict, e->max_batch));
     if (k != PTR_DEVICE) { if (int arc = stage_alloc(e, k == PTR_PAGEABLE)) return arc; }
     unsigned long long* d_total = reinterpret_cast<unsigned long long*>(e->d_snap_cnt + fa::kSnapMaxCtas);
     // host chunks are bounded by the staging buffers (stage_records() x 144 bytes), device chunks by max_batch records
@@ -731,15 +734,20 @@ int fa_ingest_snaps(fa_engine* e, const void* snaps, size_t n, uint32_t stride, 
             if (int src_rc = stage_copy(e, src, (size_t)c * stride, k == PTR_PINNED, &sidx)) return src_rc;
             d_sn = e->d_stage[sidx];
         }
-        e->st.kernel_launches += fa::launch_parse_snaps(d_sn, c, stride, e->d_snap_cnt, reinterpret_cast<uint4*>(e->d_expanded), e->d_snap_src,
-                                                        d_total, e->sm_count, e->stream);
+        CU(cudaMemsetAsync(d_total + 1, 0, 24, e->stream));             // the filter's three counters of this chunk
+        e->st.kernel_launches += fa::launch_parse_snaps(d_sn, c, stride, &e->filter, e->d_snap_cnt, e->d_snap_verdict,
+                                                        reinterpret_cast<uint4*>(e->d_expanded), e->d_snap_src, d_total, d_total + 1,
+                                                        e->sm_count, e->stream);
         CU(cudaGetLastError());
         if (sidx >= 0) { if (int rel_rc = stage_release(e, sidx)) return rel_rc; }
         // how many packets were submitted decides the launch sizes of the fold: one 8-byte read-back per chunk
-        unsigned long long m64 = 0;
-        CU(cudaMemcpyAsync(&m64, d_total, 8, cudaMemcpyDeviceToHost, e->stream));
+        unsigned long long back[4] = {0, 0, 0, 0};                      // submitted + kept | filter accept / reject / no match
+        CU(cudaMemcpyAsync(back, d_total, 32, cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
-        const uint32_t m = (uint32_t)m64;
+        const uint32_t m = (uint32_t)back[0];
+        e->st.filter_accept += back[1]; e->st.filter_reject += back[2]; e->st.filter_nomatch += back[3];
+        // every submitted packet bumps exactly one of the three counters: what the filter skipped = submitted - kept
+        const uint64_t filtered_out = e->filter.n_rules ? back[1] + back[2] + back[3] - (uint64_t)m : 0;
         uint32_t off = 0;
         while (off < m) {                                   // a chunk may be folded in several windows ("full" cuts)
             uint32_t took = 0;
@@ -753,6 +761,7 @@ int fa_ingest_snaps(fa_engine* e, const void* snaps, size_t n, uint32_t stride, 
             CU(cudaMemcpyAsync(&first_left, e->d_snap_src + off, 4, cudaMemcpyDeviceToHost, e->stream));
             CU(cudaStreamSynchronize(e->stream));
             // discarded snapshots before the cut: first_left - off
+            // (with a filter the discarded / filtered split of a partially consumed chunk is not known: both count as discarded)
             e->st.snaps_ingested += first_left;
             e->st.snaps_discarded += first_left - off;
             done += first_left;
@@ -760,12 +769,43 @@ int fa_ingest_snaps(fa_engine* e, const void* snaps, size_t n, uint32_t stride, 
         }
         if (rc != FA_OK) break;
         e->st.snaps_ingested += c;
-        e->st.snaps_discarded += c - m;
+        e->st.snaps_discarded += c - m - filtered_out;                  // fill_ethhdr's DISCARDs; the filter's skips are in its counters
         done += c;
     }
     if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->copy_stream));   // the caller's buffer must not be referenced after return
     if (consumed) *consumed = done;
     return rc;
+}
+
+int fa_set_flow_filter(fa_engine* e, const fa_filter_rule* rules, size_t n_rules, const fa_filter_cidr* peers, size_t n_peers) {
+    if (!e) return fail(FA_E_INVAL, "fa_set_flow_filter: null engine");
+    static_assert(sizeof(fa_filter_rule) == 64 && sizeof(fa_filter_cidr) == 20, "filter ABI");
+    if (n_rules > (size_t)fa::kMaxFilterEntries || n_peers > (size_t)fa::kMaxFilterEntries)
+        return fail(FA_E_INVAL, "fa_set_flow_filter: at most %d rules and %d peer CIDRs (MAX_FILTER_ENTRIES)", fa::kMaxFilterEntries, fa::kMaxFilterEntries);
+    if ((n_rules && !rules) || (n_peers && !peers)) return fail(FA_E_INVAL, "fa_set_flow_filter: null table");
+    std::lock_guard<std::mutex> lk(e->mu);
+    fa::FilterSet F{};
+    auto words = [](const uint8_t ip[16], uint32_t w[4]) {
+        for (int i = 0; i < 4; i++) w[i] = ((uint32_t)ip[4 * i] << 24) | ((uint32_t)ip[4 * i + 1] << 16) | ((uint32_t)ip[4 * i + 2] << 8) | ip[4 * i + 3];
+    };
+    for (size_t i = 0; i < n_rules; i++) {
+        const fa_filter_rule& r = rules[i];
+        if (r.prefix_len > 128 || r.direction > 2 || r.action > 2) return fail(FA_E_INVAL, "fa_set_flow_filter: rule %zu out of range", i);
+        fa::FilterRuleDev& d = F.rules[i];
+        words(r.ip, d.ipw); d.prefix = r.prefix_len; d.sample = r.sample;
+        d.dps = r.dst_port_start; d.dpe = r.dst_port_end; d.dp1 = r.dst_port1; d.dp2 = r.dst_port2;
+        d.sps = r.src_port_start; d.spe = r.src_port_end; d.sp1 = r.src_port1; d.sp2 = r.src_port2;
+        d.ps = r.port_start; d.pe = r.port_end; d.p1 = r.port1; d.p2 = r.port2; d.tcp_flags = r.tcp_flags;
+        d.proto = r.protocol; d.icmp_type = r.icmp_type; d.icmp_code = r.icmp_code; d.direction = r.direction; d.action = r.action;
+        d.filter_drops = r.filter_drops; d.peer = r.do_peer_cidr_lookup;
+    }
+    for (size_t i = 0; i < n_peers; i++) {
+        if (peers[i].prefix_len > 128) return fail(FA_E_INVAL, "fa_set_flow_filter: peer CIDR %zu out of range", i);
+        words(peers[i].ip, F.peers[i].ipw); F.peers[i].prefix = peers[i].prefix_len;
+    }
+    F.n_rules = (uint32_t)n_rules; F.n_peers = (uint32_t)n_peers;
+    e->filter = F;
+    return FA_OK;
 }
 
 static int ingest_feature(fa_engine* e, int kind, const void* recs, size_t n, const char* who) {

@@ -88,10 +88,20 @@ int launch_pb_write(const PbInputs& in, uint32_t n, const PbParams& P, const uns
 
 // 64-byte packet events -> single-packet 144-byte records (misc_kernels.cu)
 int launch_expand_events(const uint4* events, uint32_t n, uint4* recs_out, cudaStream_t st);
-// (f4) packet snapshots -> records of the packets flow_monitor would submit, stable order; *n_out (device) = how many
+// (f4) packet snapshots -> records of the packets flow_monitor would submit (and, with a filter, keep), stable order;
+// *n_out (device) = how many; filter_ctr[3] (device) += accept / reject / no-match
 constexpr int kSnapMaxCtas = 1024;                 // cta_count has this many entries
-int launch_parse_snaps(const uint8_t* snaps, uint32_t n, uint32_t stride, uint32_t* cta_count, uint4* out_recs, uint32_t* src_of,
-                       unsigned long long* n_out, int sm_count, cudaStream_t st);
+constexpr int kMaxFilterEntries = 16;              // MAX_FILTER_ENTRIES (bpf/types.h:66)
+struct FilterRuleDev {                             // fa_filter_rule with the address as big-endian words
+    uint32_t ipw[4]; uint32_t prefix, sample;
+    uint16_t dps, dpe, dp1, dp2, sps, spe, sp1, sp2, ps, pe, p1, p2, tcp_flags;
+    uint8_t proto, icmp_type, icmp_code, direction, action, filter_drops, peer;
+};
+struct FilterCidrDev { uint32_t ipw[4]; uint32_t prefix; };
+struct FilterSet { uint32_t n_rules, n_peers; FilterRuleDev rules[kMaxFilterEntries]; FilterCidrDev peers[kMaxFilterEntries]; };
+int launch_parse_snaps(const uint8_t* snaps, uint32_t n, uint32_t stride, const FilterSet* filter, uint32_t* cta_count, uint8_t* verdict,
+                       uint4* out_recs, uint32_t* src_of, unsigned long long* n_out, unsigned long long* filter_ctr, int sm_count,
+                       cudaStream_t st);
 
 // generator
 struct GenDeviceParams;

@@ -28,6 +28,17 @@ def _nbytes(x):
     return x.numel() * x.element_size()
 
 
+# fa_filter_rule (64 bytes) / fa_filter_cidr (20 bytes), include/flowagg.h
+FILTER_RULE_DTYPE = np.dtype([("ip", "u1", 16), ("prefix_len", "<u4"), ("sample", "<u4"),
+                              ("dst_port_start", "<u2"), ("dst_port_end", "<u2"), ("dst_port1", "<u2"), ("dst_port2", "<u2"),
+                              ("src_port_start", "<u2"), ("src_port_end", "<u2"), ("src_port1", "<u2"), ("src_port2", "<u2"),
+                              ("port_start", "<u2"), ("port_end", "<u2"), ("port1", "<u2"), ("port2", "<u2"), ("tcp_flags", "<u2"),
+                              ("protocol", "u1"), ("icmp_type", "u1"), ("icmp_code", "u1"), ("direction", "u1"), ("action", "u1"),
+                              ("filter_drops", "u1"), ("do_peer_cidr_lookup", "u1"), ("pad", "u1", 7)])
+FILTER_CIDR_DTYPE = np.dtype([("ip", "u1", 16), ("prefix_len", "<u4")])
+assert FILTER_RULE_DTYPE.itemsize == 64 and FILTER_CIDR_DTYPE.itemsize == 20
+
+
 class FlowAggEngine:
     """One engine == one GPU flow cache (the reference's aggregated_flows map + Accounter)."""
 
@@ -72,6 +83,14 @@ class FlowAggEngine:
         consumed = C.c_size_t(0)
         rc = check(lib().fa_ingest_snaps(self._h, _ptr(snaps), n, stride, C.byref(consumed)))
         return rc, consumed.value
+
+    def set_flow_filter(self, rules=None, peers=None):
+        """Install the flow filter fa_ingest_snaps applies after the header parse (numpy arrays of FILTER_RULE_DTYPE /
+        FILTER_CIDR_DTYPE = fa_filter_rule / fa_filter_cidr); no rules = no filter."""
+        r = np.ascontiguousarray(rules if rules is not None else np.zeros(0, dtype=FILTER_RULE_DTYPE))
+        p = np.ascontiguousarray(peers if peers is not None else np.zeros(0, dtype=FILTER_CIDR_DTYPE))
+        assert r.dtype == FILTER_RULE_DTYPE and p.dtype == FILTER_CIDR_DTYPE
+        check(lib().fa_set_flow_filter(self._h, r.ctypes.data if len(r) else None, len(r), p.ctypes.data if len(p) else None, len(p)))
 
     def ingest_all(self, recs, on_full):
         """Accounter loop: fold everything, calling on_full(evicted_records) at each "full" cut

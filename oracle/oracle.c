@@ -770,3 +770,111 @@ size_t oracle_parse_snaps(const uint8_t* snaps, size_t n, uint32_t stride, uint8
         if (oracle_parse_snap(snaps + i * stride, stride, out + m * 144)) { if (src_of) src_of[m] = (uint32_t)i; m++; }
     return m;
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Flow filter (bpf/flows_filter.h, bpf/utils.h:179-222).  Rule image (64 B): ip[16] @0, prefix_len u32 @16, sample u32 @20,
+ * dst ports start/end/1/2 u16 @24, src ports @32, generic ports @40, tcp_flags u16 @48, protocol @50, icmp type/code @51,52,
+ * direction @53, action @54, filter_drops @55, do_peer_cidr_lookup @56.  Peer CIDR image (20 B): ip[16], prefix_len u32. */
+static uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+static uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+/* BPF_MAP_TYPE_LPM_TRIE lookup: the entry with the longest prefix_len <= key_prefix whose first prefix_len bits equal the key's */
+static const uint8_t* lpm_lookup(const uint8_t* entries, size_t n, size_t entry_bytes, const uint8_t key[16], uint32_t key_prefix) {
+    const uint8_t* best = NULL; uint32_t best_len = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t* e = entries + i * entry_bytes;
+        const uint32_t pl = rd32(e + 16);
+        if (pl > key_prefix || pl > 128) continue;
+        int ok = 1;
+        for (uint32_t b = 0; b < pl / 8 && ok; b++) ok = e[b] == key[b];
+        if (ok && (pl & 7)) { const uint8_t m = (uint8_t)(0xFF << (8 - (pl & 7))); ok = ((e[pl / 8] ^ key[pl / 8]) & m) == 0; }
+        if (ok && (!best || pl > best_len)) { best = e; best_len = pl; }
+    }
+    return best;
+}
+
+/* flow_filter_setup_lookup_key (flows_filter.h:14-41) */
+static void filter_key_of(const uint8_t* rec, int use_src, uint16_t eth, uint8_t key[16], uint32_t* prefix) {
+    memset(key, 0, 16);
+    const uint8_t* ip = rec + (use_src ? 0 : 16);
+    if (eth == 0x0800) { memcpy(key, ip + 12, 4); *prefix = 32; } else { memcpy(key, ip, 16); *prefix = 128; }
+}
+
+/* do_flow_filter_lookup (flows_filter.h:43-217); action and sampling keep what a rule wrote even when it ends with 0 */
+static int filter_lookup(const uint8_t* rules, size_t n_rules, const uint8_t* peers, size_t n_peers, const uint8_t* rec,
+                         const uint8_t key[16], uint32_t prefix, int peer_use_src, uint16_t eth, uint8_t* action, uint32_t* sampling) {
+    const uint8_t* r = lpm_lookup(rules, n_rules, 64, key, prefix);
+    if (!r) return 0;
+    int result = 1;
+    if (r[54] != 2) { *action = r[54]; result++; }
+    if (r[56]) {                                                   /* peer CIDR: the opposite address */
+        uint8_t pk[16]; uint32_t pp;
+        filter_key_of(rec, peer_use_src, eth, pk, &pp);
+        if (lpm_lookup(peers, n_peers, 20, pk, pp)) result++; else return 0;
+    }
+    const uint32_t sample = rd32(r + 20);
+    if (sample) { *sampling = sample; result++; }
+    const uint8_t proto = rec[36];
+    const uint16_t sport = rd16(rec + 32), dport = rd16(rec + 34), flags = rd16(rec + 70);
+    if (r[50] == proto || r[50] == 0) {
+        if (proto == 6 || proto == 17 || proto == 132) {
+            const uint16_t ds = rd16(r + 24), de = rd16(r + 26), d1 = rd16(r + 28), d2 = rd16(r + 30);
+            if ((ds != 0 && de == 0) || d1 != 0 || d2 != 0) { if (ds == dport || d1 == dport || d2 == dport) result++; else return 0; }
+            else if (ds != 0 && de != 0) { if (ds <= dport && dport <= de) result++; else return 0; }
+            const uint16_t ss = rd16(r + 32), se = rd16(r + 34), s1 = rd16(r + 36), s2 = rd16(r + 38);
+            if ((ss != 0 && se == 0) || s1 != 0 || s2 != 0) { if (ss == sport || s1 == sport || s2 == sport) result++; else return 0; }
+            else if (ss != 0 && se != 0) { if (ss <= sport && sport <= se) result++; else return 0; }
+            const uint16_t ps = rd16(r + 40), pe = rd16(r + 42), p1 = rd16(r + 44), p2 = rd16(r + 46);
+            if ((ps != 0 && pe == 0) || p1 != 0 || p2 != 0) {
+                if (ps == sport || ps == dport || p1 == sport || p1 == dport || p2 == sport || p2 == dport) result++; else return 0;
+            } else if (ps != 0 && pe != 0) {
+                if ((ps <= sport && sport <= pe) || (ps <= dport && dport <= pe)) result++; else return 0;
+            }
+            if (proto == 6 && rd16(r + 48) != 0) { if (rd16(r + 48) == flags) result++; else return 0; }
+        } else if (proto == 1 || proto == 58) {
+            if (r[51] != 0) {
+                if (r[51] == rec[37]) result++; else return 0;
+                if (r[52] != 0) { if (r[52] == rec[38]) result++; else return 0; }
+            }
+        }
+    } else {
+        return 0;
+    }
+    if (r[53] != 2) { if (r[53] == rec[96]) result++; else return 0; }
+    if (r[55]) return 0;                                           /* filter_drops needs drop_reason != 0; flow_monitor passes 0 */
+    return result;
+}
+
+int oracle_filter_packet(const uint8_t* rules, size_t n_rules, const uint8_t* peers, size_t n_peers, uint8_t* rec, uint64_t counters[3]) {
+    const uint16_t eth = rd16(rec + 68);
+    uint8_t action = 2;                                            /* is_flow_filtered: *action = MAX_FILTER_ACTIONS */
+    uint32_t sampling = rd32(rec + 92);
+    uint8_t key[16]; uint32_t prefix;
+    filter_key_of(rec, 1, eth, key, &prefix);                      /* source address first; its peer is the destination */
+    int result = filter_lookup(rules, n_rules, peers, n_peers, rec, key, prefix, 0, eth, &action, &sampling);
+    if (result <= 0) {
+        filter_key_of(rec, 0, eth, key, &prefix);
+        result = filter_lookup(rules, n_rules, peers, n_peers, rec, key, prefix, 1, eth, &action, &sampling);
+    }
+    memcpy(rec + 92, &sampling, 4);
+    if (result != 0 && action != 2) {                              /* utils.h:185-203 */
+        if (action == 1) { counters[1]++; return 1; }
+        counters[0]++;
+        return 0;
+    }
+    counters[2]++;                                                 /* utils.h:209-218 */
+    return (action == 0 || action == 2) ? 1 : 0;
+}
+
+size_t oracle_parse_snaps_filtered(const uint8_t* snaps, size_t n, uint32_t stride, const uint8_t* rules, size_t n_rules,
+                                   const uint8_t* peers, size_t n_peers, uint8_t* out, uint32_t* src_of, uint64_t counters[3]) {
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (!oracle_parse_snap(snaps + i * stride, stride, out + m * 144)) continue;
+        if (n_rules && oracle_filter_packet(rules, n_rules, peers, n_peers, out + m * 144, counters)) continue;
+        if (src_of) src_of[m] = (uint32_t)i;
+        m++;
+    }
+    return m;
+}

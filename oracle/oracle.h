@@ -151,6 +151,16 @@ uint64_t oracle_kmap_counter_intf_missed(const oracle_kmap* m);
  * SOURCE-PINNED ONLY: the reference has no unit test for its eBPF parsing. */
 int    oracle_parse_snap(const uint8_t* snap, uint32_t stride, uint8_t* rec144);
 size_t oracle_parse_snaps(const uint8_t* snaps, size_t n, uint32_t stride, uint8_t* out_recs, uint32_t* src_of);
+/* the flow filter in front of the map update: bpf/flows_filter.h:14-255 (is_flow_filtered, do_flow_filter_lookup, LPM
+ * semantics of filter_map / peer_filter_map) + check_and_do_flow_filtering (bpf/utils.h:179-222).  rules: n x 64-byte
+ * fa_filter_rule images, peers: n x 20-byte CIDRs (layouts restated in oracle.c).  rec144 = the packet's parsed record;
+ * returns 1 when the packet is skipped; counters[3] += (accept, reject, nomatch); a matching rule's sample is written to
+ * the record's sampling field.  SOURCE-PINNED ONLY. */
+int    oracle_filter_packet(const uint8_t* rules, size_t n_rules, const uint8_t* peers, size_t n_peers, uint8_t* rec144,
+                            uint64_t counters[3]);
+size_t oracle_parse_snaps_filtered(const uint8_t* snaps, size_t n, uint32_t stride, const uint8_t* rules, size_t n_rules,
+                                   const uint8_t* peers, size_t n_peers, uint8_t* out_recs, uint32_t* src_of,
+                                   uint64_t counters[3]);
 
 /* --- hashes + sketches (this repo's spec; PARITY UNPINNED, see header comment) */
 uint64_t oracle_key_premix(const uint8_t* key40);

@@ -192,13 +192,19 @@ int launch_expand_events(const uint4* events, uint32_t n, uint4* recs_out, cudaS
     simt::launch(2, 256, 0, [=] { expand_events_kernel(events, n, recs_out); });
     return 1;
 }
-int launch_parse_snaps(const uint8_t* snaps, uint32_t n, uint32_t stride, uint32_t* cta_count, uint4* out_recs, uint32_t* src_of,
-                       unsigned long long* n_out, int, cudaStream_t) {
+int launch_parse_snaps(const uint8_t* snaps, uint32_t n, uint32_t stride, const FilterSet* filter, uint32_t* cta_count, uint8_t* verdict,
+                       uint4* out_recs, uint32_t* src_of, unsigned long long* n_out, unsigned long long* filter_ctr, int, cudaStream_t) {
     if (!n) return 0;
     const unsigned grid = std::min<unsigned>((n + kSnapTile - 1) / kSnapTile, 3);
-    launch_serial(grid, kSnapTile, [=] { snap_count_kernel(snaps, n, stride, cta_count); });
-    launch_serial(grid, kSnapTile, [=] { snap_parse_kernel(snaps, n, stride, cta_count, out_recs, src_of, n_out); },
-                  (size_t)kSnapTile * std::max<uint32_t>(stride, kRecBytes));
+    const size_t smem = (size_t)kSnapTile * std::max<uint32_t>(stride, kRecBytes);
+    FilterSet F = filter ? *filter : FilterSet{};
+    if (F.n_rules) {
+        launch_serial(grid, kSnapTile, [=] { snap_count_kernel<true>(snaps, n, stride, F, cta_count, verdict, filter_ctr); }, smem);
+        launch_serial(grid, kSnapTile, [=] { snap_parse_kernel<true>(snaps, n, stride, F, cta_count, verdict, out_recs, src_of, n_out); }, smem);
+    } else {
+        launch_serial(grid, kSnapTile, [=] { snap_count_kernel<false>(snaps, n, stride, F, cta_count, verdict, filter_ctr); }, smem);
+        launch_serial(grid, kSnapTile, [=] { snap_parse_kernel<false>(snaps, n, stride, F, cta_count, verdict, out_recs, src_of, n_out); }, smem);
+    }
     return 2;
 }
 int launch_pb_sizes(const PbInputs& in_, uint32_t n, const PbParams& P_, uint32_t* sizes, unsigned long long* offsets,

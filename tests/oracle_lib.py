@@ -94,6 +94,8 @@ def lib():
         "oracle_owner_hash": (u64, [_u8p]),
         "oracle_parse_snap": (C.c_int, [_u8p, u32, _u8p]),
         "oracle_parse_snaps": (sz, [_u8p, sz, u32, _u8p, C.POINTER(u32)]),
+        "oracle_filter_packet": (C.c_int, [_u8p, sz, _u8p, sz, _u8p, C.POINTER(u64)]),
+        "oracle_parse_snaps_filtered": (sz, [_u8p, sz, u32, _u8p, sz, _u8p, sz, _u8p, C.POINTER(u32), C.POINTER(u64)]),
         "oracle_cms_update": (None, [C.POINTER(u64), u32, u32, u64, _u8p, sz]),
         "oracle_cms_query": (None, [C.POINTER(u64), u32, u32, u64, _u8p, sz, C.POINTER(u64)]),
         "oracle_hll_update": (None, [_u8p, u32, u64, _u8p, sz]),
@@ -373,3 +375,17 @@ def parse_snaps(snaps, stride):
     src = np.zeros(n, dtype=np.uint32)
     m = lib().oracle_parse_snaps(_p(b), n, stride, _p(out), src.ctypes.data_as(C.POINTER(C.c_uint32)))
     return out[:m].copy(), src[:m].copy()
+
+
+def parse_snaps_filtered(snaps, stride, rules, peers):
+    """(f4) with the flow filter: -> (records kept (m,144), their snapshot indices, [accept, reject, nomatch] counters)."""
+    b = np.ascontiguousarray(snaps).view(np.uint8).reshape(-1)
+    n = b.size // stride
+    out = np.zeros((n, 144), dtype=np.uint8)
+    src = np.zeros(n, dtype=np.uint32)
+    ctr = np.zeros(3, dtype=np.uint64)
+    rb = np.ascontiguousarray(rules).view(np.uint8).reshape(-1)
+    pb = np.ascontiguousarray(peers).view(np.uint8).reshape(-1) if peers is not None and len(peers) else np.zeros(20, dtype=np.uint8)
+    m = lib().oracle_parse_snaps_filtered(_p(b), n, stride, _p(rb), len(rules), _p(pb), 0 if peers is None else len(peers), _p(out),
+                                          src.ctypes.data_as(C.POINTER(C.c_uint32)), ctr.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return out[:m].copy(), src[:m].copy(), ctr
