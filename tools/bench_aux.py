@@ -177,6 +177,17 @@ def snaps_bench(B=1 << 22, n_frames=1 << 16, steps=6):
         print(json.dumps({"bench": "f4 snapshots -> parse -> fold (device in)", "stride": stride, "snaps": B, "submitted": sub,
                           "flows": eng.live_flows(), "Mpkts_s": B / dt / 1e6,
                           "algorithmic_GB_s": (B * stride + sub * REC) / dt / 1e9}), flush=True)
+        if stride == 104:                                    # the same stream behind a 12-rule flow filter
+            from test_flow_filter import cidrs_of, random_rules
+            eng.evict(cap=1 << 22)
+            eng.set_flow_filter(random_rules(np.random.default_rng(5), 12), cidrs_of(([10, 1, 2, 0], 25)))
+            eng.ingest_snaps(d, stride)
+            st0 = eng.stats()
+            dt = timed(lambda i: eng.ingest_snaps(d, stride), steps) / steps
+            st1 = eng.stats()
+            kept = (st1["records_ingested"] - st0["records_ingested"]) // steps
+            print(json.dumps({"bench": "f4 snapshots -> parse -> 12-rule flow filter -> fold (device in)", "stride": stride, "snaps": B,
+                              "kept": kept, "Mpkts_s": B / dt / 1e6}), flush=True)
         eng.close()
 
 
