@@ -40,7 +40,10 @@ constexpr int kCtaThreads = kTile * kTeams;
 constexpr int kRepSlots  = 2 * kTile;
 constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
 constexpr int kHotEntries = 96;                 // 64 primary entries + 32 second-chance entries (another slice of the hash)
-constexpr uint32_t kHotMinDups = 2;             // a flow with >= 3 records in one tile becomes a cache candidate
+#ifndef FA_K1_MINDUPS
+#define FA_K1_MINDUPS 1
+#endif
+constexpr uint32_t kHotMinDups = FA_K1_MINDUPS; // a flow with >= 2 records in one tile becomes a cache candidate (1 / 2 / 3 measured: profiles/r2_ab_k1_mindups.log)
 constexpr uint32_t kRepEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kResSpill = 0xFFFFFFFFu;
 constexpr uint32_t kProbeLimit = 8192;
