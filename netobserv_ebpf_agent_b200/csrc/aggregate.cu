@@ -250,10 +250,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         const uint32_t cnt = min((uint32_t)kTile, n - first);
         mbar_wait(&tc.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
-        if ((opt & 32u) && tid == 0) {                             // experiment: have L2 fetch the team's next tile now (no gain measured)
-            const uint32_t nt = tile_idx + tile_stride;
-            if (nt < n_tiles) tma_prefetch_l2(recs + (size_t)nt * kTile * kRecChunks, min((uint32_t)kTile, n - nt * kTile) * kRecBytes);
-        }
 
         // ------------------------------------------------------ E: hash, cache / elect, fold duplicates
         {

@@ -152,9 +152,9 @@ struct fa_engine {
     fa::SketchParams sk{};
     unsigned long long* d_prof = nullptr;     // FA_PHASE_PROFILE=1: per-phase warp-cycle counters of K1
 #ifndef FA_K1_DEFAULT_OPT
-#define FA_K1_DEFAULT_OPT 0u                  // which K1 variant an engine uses unless FA_K1_OPT says otherwise (aggregate.cu)
+#define FA_K1_DEFAULT_OPT 0u                  // K1 switches an engine starts with (kernels.cuh, AggLaunch::opt); FA_K1_OPT overrides (diagnostics)
 #endif
-    uint32_t k1_opt = FA_K1_DEFAULT_OPT;      // FA_K1_OPT: experiment switches
+    uint32_t k1_opt = FA_K1_DEFAULT_OPT;
 
     // live-flow bookkeeping for the "full" rule: live_known is exact as of the last retired
     // launch; unsynced_records bounds the flows that launches still in flight can add.

@@ -35,7 +35,7 @@ struct AggLaunch {
     uint32_t     scratch_slots;
     int          sm_count;
     unsigned long long* prof; // 8 phase cycle counters (FA_PHASE_PROFILE=1) or nullptr
-    uint32_t     opt;        // experiment switches (FA_K1_OPT), 0 = default
+    uint32_t     opt;        // switches: 2 = no hot-flow cache (diagnostics), 16 = the record count is on the device (ctr->launch_n)
 };
 
 // K1: fold a batch of flow records into the table (ACCOUNTER semantics) and, when any
