@@ -39,7 +39,11 @@ constexpr int kTeams     = 1024 / kTile;        // teams per CTA (one CTA per SM
 constexpr int kCtaThreads = kTile * kTeams;
 constexpr int kRepSlots  = 2 * kTile;
 constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
-constexpr int kHotEntries = 96;                 // 64 primary entries + 32 second-chance entries (another slice of the hash)
+constexpr int kHot2 = kTile > 256 ? 16 : 32;    // second-chance entries (another slice of the hash); fewer when 512-record tiles need the room
+constexpr int kHotEntries = 64 + kHot2;         // 64 primary entries + the second-chance ones
+template <bool kWide> struct RepIdxOf { typedef uint8_t type; };
+template <> struct RepIdxOf<true> { typedef uint16_t type; };
+typedef RepIdxOf<(kTile > 256)>::type RepIdx;   // index of a record inside its tile
 #ifndef FA_K1_MINDUPS
 #define FA_K1_MINDUPS 1
 #endif
@@ -55,8 +59,8 @@ struct __align__(128) TeamSmem {                  // 52,992 B per team
     uint4    res4[kTile];                         //  4,096 B  per representative: table slot | mirror lo | flags seen + mirror hi | -
     uint32_t rep[kRepSlots];                      //  2,048 B  tile-local key -> representative index
     uint8_t  tdirty[kTile];                       //    256 B  set by duplicates whose descriptor differs
-    uint8_t  glist[kTile];                        //    256 B  team-wide compacted list of representatives
-    uint8_t  slow[kTile / 32][32];                //    256 B  per-warp flows that need the general probe loop
+    RepIdx   glist[kTile];                        //    256 B  team-wide compacted list of representatives
+    RepIdx   slow[kTile / 32][32];                //    256 B  per-warp flows that need the general probe loop
 };
 struct __align__(16) TeamCtl {                    // kept outside TeamSmem so that four teams + the cache fit in 227 KB
     unsigned long long full_bar;                  // mbarrier of the team's tile
@@ -264,7 +268,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 // ---- hot-flow cache: an exact 114-byte match folds the record on-chip, no table traffic
                 uint32_t cidx = (uint32_t)h >> 26;                        // primary way
                 if (!(*reinterpret_cast<volatile uint32_t*>(&cs.hot[cidx].state) == 2u && cs.hot[cidx].hash == (uint32_t)h))
-                    cidx = 64u + (((uint32_t)h >> 21) & 31u);              // second chance
+                    cidx = 64u + (((uint32_t)h >> 21) & (uint32_t)(kHot2 - 1));              // second chance
                 HotEntry& ce = cs.hot[cidx];
                 if (use_cache && *reinterpret_cast<volatile uint32_t*>(&ce.state) == 2u && ce.hash == (uint32_t)h) {
                     const uint4 r3 = R[3], r4 = R[4];
@@ -340,7 +344,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             uint32_t lbase = 0;
             if (lane == 0 && pending) lbase = atomicAdd(&tc.nrep, (uint32_t)__popc(pending));
             lbase = __shfl_sync(0xFFFFFFFFu, lbase, 0);
-            if (is_rep) s.glist[lbase + __popc(pending & lt_mask)] = (uint8_t)tid;
+            if (is_rep) s.glist[lbase + __popc(pending & lt_mask)] = (RepIdx)tid;
         }
         FA_PROF_MARK(1);                                           // E phase
         team_sync(team);                                           // S1: folds, hashes and the list are complete
@@ -415,7 +419,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                     }
                     const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j == 0);
                     if (slowb) {
-                        if (to_slow && j == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (uint8_t)ridx[r];
+                        if (to_slow && j == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (RepIdx)ridx[r];
                         nslow += __popc(slowb);
                     }
                 }
@@ -466,7 +470,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 if (use_cache && a1.z >= kHotMinDups && my_slot != kResSpill) {
                     const uint32_t hh = s.hs[my_ridx];
                     uint32_t iidx = hh >> 26;
-                    if (*reinterpret_cast<volatile uint32_t*>(&cs.hot[iidx].state) != 0u && cs.hot[iidx].hash != hh) iidx = 64u + ((hh >> 21) & 31u);
+                    if (*reinterpret_cast<volatile uint32_t*>(&cs.hot[iidx].state) != 0u && cs.hot[iidx].hash != hh) iidx = 64u + ((hh >> 21) & (uint32_t)(kHot2 - 1));
                     HotEntry& ce = cs.hot[iidx];
                     if (*reinterpret_cast<volatile uint32_t*>(&ce.state) == 0u && atomicCAS(&ce.state, 0u, 1u) == 0u) {
 #pragma unroll
