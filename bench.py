@@ -371,6 +371,13 @@ def run_ours(args, wl):
     if nvlink is not None and getattr(agg, "profile", False):
         rounds_timed = args.steps * ((B + max_batch - 1) // max_batch)
         nvlink["phase_ms_per_round_rank0"] = {k_: round(v, 4) for k_, v in agg.phase_ms(rounds_timed).items()}
+        # bytes crossing NVLink against the measured 770 GB/s per direction and GPU
+        rounds_per_step = max(1, (B + max_batch - 1) // max_batch)
+        per_step = nvlink["nvlink_bytes_per_round_rank0"] * rounds_per_step
+        nvlink["nvlink_frac_of_770gbs_over_the_step"] = round(per_step / (total_ms / args.steps / 1e3) / 770e9, 4)
+        rt = nvlink["phase_ms_per_round_rank0"].get("route", 0.0)
+        if rt > 0:
+            nvlink["nvlink_frac_of_770gbs_during_route"] = round(nvlink["nvlink_bytes_per_round_rank0"] / (rt / 1e3) / 770e9, 4)
 
     # ---------------------------------------------------------------- parity: the engine against the CPU oracle
     # Fresh state, then records [V0, V0+V) of the same stream through the same engine / aggregator, evict, compare
