@@ -44,6 +44,9 @@ constexpr int kHotEntries = 64 + kHot2;         // 64 primary entries + the seco
 template <bool kWide> struct RepIdxOf { typedef uint8_t type; };
 template <> struct RepIdxOf<true> { typedef uint16_t type; };
 typedef RepIdxOf<(kTile > 256)>::type RepIdx;   // index of a record inside its tile
+#ifndef FA_K1_STREAM_HINT
+#define FA_K1_STREAM_HINT 1   // record stream read with an L2 evict-first policy (+1.5 % / +3.7 % / +0.5 %: profiles/r2_ab_k1_l2_hints.log)
+#endif
 #ifndef FA_K1_MINDUPS
 #define FA_K1_MINDUPS 1
 #endif
@@ -92,7 +95,11 @@ __device__ __forceinline__ void issue_tile_load(TeamSmem& s, TeamCtl& tc, const 
     const uint32_t cnt = min((uint32_t)kTile, n - first);
     const uint32_t bytes = cnt * kRecBytes;
     mbar_expect_tx(&tc.full_bar, bytes);
+#if FA_K1_STREAM_HINT
+    tma_load_1d_stream(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &tc.full_bar);    // L2 evict-first for the record stream
+#else
     tma_load_1d(&s.tile[0], recs + (size_t)first * kRecChunks, bytes, &tc.full_bar);
+#endif
 }
 
 // Reductions of one flow's folded totals onto its hot line.  floor_ns <= hot.nstart always
