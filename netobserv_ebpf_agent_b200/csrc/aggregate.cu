@@ -47,6 +47,12 @@ typedef RepIdxOf<(kTile > 256)>::type RepIdx;   // index of a record inside its 
 #ifndef FA_K1_STREAM_HINT
 #define FA_K1_STREAM_HINT 1   // record stream read with an L2 evict-first policy (+1.5 % / +3.7 % / +0.5 %: profiles/r2_ab_k1_l2_hints.log)
 #endif
+#ifndef FA_K1_ETAG
+#define FA_K1_ETAG 0     // election slots carry hash bits; duplicate fold after the loop (A/B: profiles/r2_ab_k1_pipe.log)
+#endif
+#ifndef FA_K1_PIPE
+#define FA_K1_PIPE 0     // probe phase: even split of the list, software-pipelined rounds, compact second pass
+#endif
 #ifndef FA_K1_MINDUPS
 #define FA_K1_MINDUPS 1
 #endif
@@ -80,6 +86,7 @@ struct __align__(16) HotEntry {                   // 208 B: a stride of 52 words
 };
 static_assert(sizeof(HotEntry) == 208, "HotEntry stride");
 static_assert(kTile != 256 || sizeof(TeamSmem) == 52992, "TeamSmem has no padding to spare");
+static_assert(!FA_K1_ETAG || kTile <= 256, "election slots keep the tile index in 8 bits");
 struct __align__(128) AggSmem {                   // 232,064 B of the 232,448 B (227 KB) an sm_100 CTA may use
     TeamSmem team[kTeams];
     HotEntry hot[kHotEntries];
@@ -303,6 +310,55 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         if (v_end && (uint32_t)v_end > A[5]) atomicMax(&A[5], (uint32_t)v_end);
                     }
                 }
+#if FA_K1_ETAG
+                if (is_rep) {
+                    // election: the slot holds (23 hash bits << 8 | tile index), so a slot taken by another key is
+                    // walked past without touching the tile; the fold of a duplicate runs after the loop, once per
+                    // warp, instead of inside it at whatever iteration each lane found its representative
+                    uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
+                    const uint32_t mine = (((uint32_t)(h >> 16) & 0x7FFFFFu) << 8) | (uint32_t)tid;
+                    uint32_t dup_of = kRepEmpty;
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&s.rep[rs], kRepEmpty, mine);
+                        if (old == kRepEmpty) break;
+                        if (((old ^ mine) >> 8) == 0u) {
+                            const uint4* O = T + (old & 0xFFu) * kRecChunks;
+                            if (eq4_masked(O[2], r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
+                                eq4_masked(O[1], r1, chunk_mask(1))) { dup_of = old & 0xFFu; break; }
+                        }
+                        rs = (rs + 1) & (kRepSlots - 1);
+                    }
+                    if (dup_of != kRepEmpty) {
+                        // Same key.  Fold into that representative with 32-bit shared atomics when the high words of
+                        // the timestamps agree (the common case); otherwise go to the table on our own.
+                        const uint4* O = T + dup_of * kRecChunks;
+                        const uint4 r3 = R[3], r4 = R[4], o2 = O[2], o3 = O[3];
+                        const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+                        const uint64_t v_ns = 0ull - v_start;
+                        const uint64_t o_ns = 0ull - u64_of(o2.z, o2.w), o_end = u64_of(o3.x, o3.y);
+                        const bool ok = (v_start == 0 || (uint32_t)(v_ns >> 32) == (uint32_t)(o_ns >> 32)) &&
+                                        (v_end == 0 || (uint32_t)(v_end >> 32) == (uint32_t)(o_end >> 32));
+                        if (ok) {
+                            is_rep = false;
+                            uint32_t* A = s.acc[dup_of];
+                            const uint32_t b_lo = r3.z, b_hi = r3.w;
+                            const uint32_t prev = atomicAdd(&A[0], b_lo);
+                            const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
+                            if (hi_add) atomicAdd(&A[1], hi_add);
+                            atomicAdd(&A[2], r4.x);
+                            const uint32_t fl = r4.y >> 16;
+                            if (fl) atomicOr(&A[3], fl);
+                            if (v_start) atomicMax(&A[4], (uint32_t)v_ns);
+                            if (v_end) atomicMax(&A[5], (uint32_t)v_end);
+                            atomicAdd(&A[6], 1u);                    // duplicates seen: cache candidacy
+                            uint32_t d = diff4_masked(O[4], r4, chunk_mask(3));      // exact 74-byte descriptor compare
+#pragma unroll
+                            for (int c = 5; c < 9; c++) d |= diff4_masked(O[c], R[c], chunk_mask(c - 1));
+                            if (d) s.tdirty[dup_of] = 1;
+                        }
+                    }
+                }
+#else
                 if (is_rep) {
                     uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
                     for (;;) {
@@ -345,6 +401,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         rs = (rs + 1) & (kRepSlots - 1);
                     }
                 }
+#endif
             }
             // team-wide list of representatives, so that every warp probes an equal share
             const uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_rep);
@@ -360,6 +417,169 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         const uint32_t nrep_total = tc.nrep;
         s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;   // nobody reads the election table after S1
 
+#if FA_K1_PIPE
+        // ------------------------------------------------------ probe: the list is split evenly over the team's warps;
+        // a warp walks its share in rounds of 4 flows (8 lanes per flow) with four identity-line loads in flight at all
+        // times: the load of round r + 4 is issued as soon as round r has been compared.  Flows whose home slot holds
+        // another settled flow are collected and probed one slot further in a second, compact pass (rounds of 4 again)
+        // instead of re-running every round; whatever is left goes to the general loop.
+        {
+            constexpr uint32_t kWarps = kTile / 32;
+            const uint32_t per = (nrep_total + kWarps - 1) / kWarps;              // <= 32
+            const uint32_t w0 = min(nrep_total, (uint32_t)warp * per), w1 = min(nrep_total, w0 + per);
+            RepIdx* const wl = s.slow[warp];                                       // general-loop flows from the front, second-pass flows from the back
+            uint32_t nslow = 0, ncoll = 0;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                __syncwarp();
+                const RepIdx* const src = pass == 0 ? &s.glist[w0] : &wl[32u - ncoll];
+                const uint32_t cnt = pass == 0 ? w1 - w0 : ncoll;
+                const uint32_t nrounds = (cnt + 3u) >> 2;
+                uint4 line[4];
+                uint32_t ridx[4], slot[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    ridx[q] = 0u; slot[q] = 0u;
+                    line[q] = make_uint4(0, 0, 0, 0);
+                    if ((uint32_t)q < nrounds) {                                   // warp-uniform
+                        const uint32_t k = (uint32_t)q * 4u + g;
+                        const bool a = k < cnt;
+                        if (a) ridx[q] = (uint32_t)src[k];
+                        slot[q] = (s.hs[ridx[q]] + (uint32_t)pass) & tmask;
+                        if (a) line[q] = ld_cg_u4(&t.ident[(size_t)slot[q] * 8 + j]);
+                    }
+                }
+#pragma unroll 1
+                for (uint32_t base = 0; base < nrounds; base += 4) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t round = base + q;
+                        if (round >= nrounds) break;                               // warp-uniform
+                        const bool act = round * 4u + g < cnt;
+                        const uint4 rchunk = T[ridx[q] * kRecChunks + rc];
+                        bool eq = eq4_masked(line[q], rchunk, cmask);
+                        const uint64_t tag = u64_of(line[q].z, line[q].w);         // meaningful in lane j == 2 only
+                        bool settled = false;
+                        if (j == 2) {
+                            settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
+                                      (tag >> TAG_EPOCH_SHIFT) != epoch;
+                            eq = eq && settled;
+                        }
+                        const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq) >> (g * 8)) & 0xFFu;
+                        const bool fast = act && (eqb & 0x07u) == 0x07u;           // settled flow, key matches
+                        uint32_t* const rw = reinterpret_cast<uint32_t*>(&s.res4[ridx[q]]);
+                        if (fast && j == 0) rw[0] = slot[q];
+                        if (fast && j == 3) *reinterpret_cast<uint2*>(rw + 1) = make_uint2(line[q].x, line[q].y);   // start mirror (eth_protocol in between)
+                        if (fast && j == 2) {
+                            rw[3] = (uint32_t)(tag >> TAG_FLAGS_SHIFT);            // flag bits the hot line already holds (low 16)
+                            if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[q]] != 0) {
+                                unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[q] * 8 + 2]) + 1;
+                                if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
+                                cs.any_dirty = 1;
+                            }
+                        }
+                        const uint32_t nfb = __ballot_sync(0xFFFFFFFFu, act && !fast && j == 0);
+                        if (nfb) {                                                 // some flow of the round is not settled at this slot (uncommon)
+                            const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g * 8 + 2)) & 1u;
+                            const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
+                            const bool to_slow = act && !fast && !collide;
+                            if (kProf && j == 0) {
+                                if (collide) c_collide++;
+                                if (act && !fast && !gsettled) c_unsettled++;
+                            }
+                            const uint32_t collb = __ballot_sync(0xFFFFFFFFu, collide && j == 0);
+                            const uint32_t slowb = nfb & ~collb;
+                            if (collide && j == 0) wl[31u - (ncoll + __popc(collb & lt_mask))] = (RepIdx)ridx[q];
+                            ncoll += __popc(collb);
+                            if (to_slow && j == 0) wl[nslow + __popc(slowb & lt_mask)] = (RepIdx)ridx[q];
+                            nslow += __popc(slowb);
+                        }
+                        if (kProf && j == 0 && fast && pass == 1) c_p1fast++;
+                        if (round + 4u < nrounds) {                                // this register set's next flow: round + 4
+                            const uint32_t k = (round + 4u) * 4u + g;
+                            const bool a = k < cnt;
+                            ridx[q] = a ? (uint32_t)src[k] : 0u;
+                            slot[q] = (s.hs[ridx[q]] + (uint32_t)pass) & tmask;
+                            line[q] = make_uint4(0, 0, 0, 0);
+                            if (a) line[q] = ld_cg_u4(&t.ident[(size_t)slot[q] * 8 + j]);
+                        }
+                    }
+                }
+                if (ncoll == 0u) break;
+            }
+            __syncwarp();
+            if (lane == 0) { FA_EMUL_COUNT(0, w1 - w0); FA_EMUL_COUNT(1, nslow); }
+            if (kProf && lane == 0) { c_reps += w1 - w0; c_slow += nslow; }
+            FA_PROF_MARK(3);                                       // pipelined probe passes
+            for (uint32_t base = 0; base < nslow; base += 4) {     // inserts, long collision chains, in-flight publishes
+                const uint32_t k = base + g;
+                const bool act = k < nslow;
+                const uint32_t ri = act ? wl[k] : 0;
+                const uint4 rchunk = T[ri * kRecChunks + rc];
+                const uint4 c2 = T[ri * kRecChunks + 2];
+                const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
+                const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
+                const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0,
+                                                   dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &cs.any_dirty);
+                if (act && j == 0) s.res4[ri] = make_uint4(got, 0u, 0u, 0u);   // mirror / seen flags unknown: issue every reduction
+            }
+            __syncwarp();
+            FA_PROF_MARK(4);                                       // general probe loop
+
+            // -------------------------------------------------- one lane per flow: totals, then the reductions
+            if (w0 + lane < w1) {
+                const uint32_t my_ridx = s.glist[w0 + lane];
+                const uint4 rr = s.res4[my_ridx];
+                const uint32_t my_slot = rr.x;
+                const uint64_t floor_ns = u64_of(rr.y, rr.z >> 16) << 16;                      // <= hot.nstart, always
+                const uint32_t seen = rr.w & 0xFFFFu;
+                const uint4* R = T + my_ridx * kRecChunks;
+                const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
+                const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][4]);
+                const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
+                const uint64_t v_ns = 0ull - v_start;
+                const uint64_t t_bytes = u64_of(r3.z, r3.w) + u64_of(a0.x, a0.y);
+                const uint32_t t_packets = r4.x + a0.z;
+                const uint32_t t_flags = (r4.y >> 16) | a0.w;
+                const uint64_t c_ns = u64_of(a1.x, (uint32_t)(v_ns >> 32)), c_endts = u64_of(a1.y, (uint32_t)(v_end >> 32));
+                const uint64_t t_ns = c_ns > v_ns ? c_ns : v_ns;
+                const uint64_t t_end = c_endts > v_end ? c_endts : v_end;
+                *reinterpret_cast<uint4*>(&s.acc[my_ridx][0]) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(&s.acc[my_ridx][4]) = make_uint4(0, 0, 0, 0);
+                s.tdirty[my_ridx] = 0;
+                // a flow that shows up several times in one tile is hot: give it a cache entry if one is free
+                if (use_cache && a1.z >= kHotMinDups && my_slot != kResSpill) {
+                    const uint32_t hh = s.hs[my_ridx];
+                    uint32_t iidx = hh >> 26;
+                    if (*reinterpret_cast<volatile uint32_t*>(&cs.hot[iidx].state) != 0u && cs.hot[iidx].hash != hh) iidx = 64u + ((hh >> 21) & (uint32_t)(kHot2 - 1));
+                    HotEntry& ce = cs.hot[iidx];
+                    if (*reinterpret_cast<volatile uint32_t*>(&ce.state) == 0u && atomicCAS(&ce.state, 0u, 1u) == 0u) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) ce.line[c] = ld_cg_u4(&t.ident[(size_t)my_slot * 8 + c]);
+                        *reinterpret_cast<uint4*>(&ce.acc[0]) = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(&ce.acc[4]) = make_uint4(0, 0, 0, 0);
+                        ce.hash = hh; ce.slot = my_slot;
+                        ce.ns_hi = (uint32_t)(v_ns >> 32); ce.end_hi = (uint32_t)(v_end >> 32);
+                        __threadfence_block();
+                        *reinterpret_cast<volatile uint32_t*>(&ce.state) = 2u;
+                        if (kProf) c_install++;
+                    }
+                }
+                if (kSketch) {
+                    const uint4 r0 = R[0], r1 = R[1];
+                    sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
+                                                 u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)), t_packets);
+                }
+                if (my_slot != kResSpill) {
+                    reduce_to_hot(t, my_slot, t_bytes, t_packets, t_ns, t_end, t_flags, floor_ns, seen);
+                } else {                                           // table physically full (FA_F_NO_FULL_CUT mis-sizing): counted
+                    my_spills++;                                   // in fa_stats.spills, like HASHMAP_FAIL_CREATE_FLOW (flows.c:285)
+                }
+            }
+            FA_PROF_MARK(5);                                       // totals + reductions
+        }
+#else
         // ------------------------------------------------------ probe: warps pull chunks of 16 flows (dynamic
         // balancing: a warp stuck behind a DRAM miss or an insert simply takes fewer chunks)
         for (;;) {
@@ -504,6 +724,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             }
             FA_PROF_MARK(5);                                       // totals + reductions
         }
+#endif
         team_sync(team);                                           // S2: nobody reads the tile buffer any more
         FA_PROF_MARK(6);                                           // S2 wait
         if (tid == 0) {
