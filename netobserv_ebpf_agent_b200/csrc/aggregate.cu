@@ -53,6 +53,12 @@ typedef RepIdxOf<(kTile > 256)>::type RepIdx;   // index of a record inside its 
 #ifndef FA_K1_PIPE
 #define FA_K1_PIPE 0     // probe phase: even split of the list, software-pipelined rounds, compact second pass
 #endif
+#ifndef FA_K1_EARLY
+#define FA_K1_EARLY 0    // next tile's TMA issued by the last warp out of the probe phase; the reduce step works from the accumulators alone
+#endif
+#if FA_K1_EARLY && !(FA_K1_PIPE && FA_K1_ETAG)
+#error FA_K1_EARLY builds on FA_K1_PIPE and FA_K1_ETAG
+#endif
 #ifndef FA_K1_MINDUPS
 #define FA_K1_MINDUPS 1
 #endif
@@ -318,6 +324,17 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                     uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
                     const uint32_t mine = (((uint32_t)(h >> 16) & 0x7FFFFFu) << 8) | (uint32_t)tid;
                     uint32_t dup_of = kRepEmpty;
+#if FA_K1_EARLY
+                    {   // own values go into the accumulators BEFORE the record can be elected: whoever finds it in the
+                        // election set adds to initialised words, and the reduce step no longer needs the tile
+                        const uint4 r3 = R[3], r4 = R[4];
+                        const uint64_t v_ns = 0ull - u64_of(r2.z, r2.w);
+                        *reinterpret_cast<uint4*>(&s.acc[tid][0]) = make_uint4(r3.z, r3.w, r4.x, r4.y >> 16);   // bytes | packets | flags (dups << 16)
+                        *reinterpret_cast<uint4*>(&s.acc[tid][4]) = make_uint4((uint32_t)v_ns, r3.x, (uint32_t)(v_ns >> 32), r3.y);   // ns lo, end lo, ns hi, end hi
+                        s.tdirty[tid] = 0;
+                        __threadfence_block();
+                    }
+#endif
                     for (;;) {
                         const uint32_t old = atomicCAS(&s.rep[rs], kRepEmpty, mine);
                         if (old == kRepEmpty) break;
@@ -350,7 +367,11 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                             if (fl) atomicOr(&A[3], fl);
                             if (v_start) atomicMax(&A[4], (uint32_t)v_ns);
                             if (v_end) atomicMax(&A[5], (uint32_t)v_end);
+#if FA_K1_EARLY
+                            atomicAdd(&A[3], 1u << 16);              // duplicates seen (above the 16 flag bits): cache candidacy
+#else
                             atomicAdd(&A[6], 1u);                    // duplicates seen: cache candidacy
+#endif
                             uint32_t d = diff4_masked(O[4], r4, chunk_mask(3));      // exact 74-byte descriptor compare
 #pragma unroll
                             for (int c = 5; c < 9; c++) d |= diff4_masked(O[c], R[c], chunk_mask(c - 1));
@@ -525,6 +546,18 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             }
             __syncwarp();
             FA_PROF_MARK(4);                                       // general probe loop
+#if FA_K1_EARLY
+            if (lane == 0) {                                       // the warp is done with the tile: the last one out re-arms it
+                __threadfence_block();
+                if (atomicAdd(&tc.next_chunk, 1u) == kWarps - 1u) {
+                    tc.next_chunk = 0;
+                    tc.nrep = 0;                                   // every warp has read the list length; reset it before the
+                                                                   // next tile can arrive (its E phase starts right after S2)
+                    const uint32_t nt = tile_idx + tile_stride;
+                    if (!kSketch && nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, tc, recs, n, nt); }
+                }
+            }
+#endif
 
             // -------------------------------------------------- one lane per flow: totals, then the reductions
             if (w0 + lane < w1) {
@@ -533,6 +566,16 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint32_t my_slot = rr.x;
                 const uint64_t floor_ns = u64_of(rr.y, rr.z >> 16) << 16;                      // <= hot.nstart, always
                 const uint32_t seen = rr.w & 0xFFFFu;
+#if FA_K1_EARLY
+                const uint4* R = T + my_ridx * kRecChunks;          // (kSketch only: the tile stays until S2)
+                const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][4]);
+                const uint64_t t_bytes = u64_of(a0.x, a0.y);
+                const uint32_t t_packets = a0.z;
+                const uint32_t t_flags = a0.w & 0xFFFFu, n_dups = a0.w >> 16;
+                const uint64_t t_ns = u64_of(a1.x, a1.z), t_end = u64_of(a1.y, a1.w);
+                const uint64_t v_ns = t_ns, v_end = t_end;           // the cache entry's windows: high words only
+#else
                 const uint4* R = T + my_ridx * kRecChunks;
                 const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
                 const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
@@ -548,8 +591,10 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 *reinterpret_cast<uint4*>(&s.acc[my_ridx][0]) = make_uint4(0, 0, 0, 0);
                 *reinterpret_cast<uint4*>(&s.acc[my_ridx][4]) = make_uint4(0, 0, 0, 0);
                 s.tdirty[my_ridx] = 0;
+                const uint32_t n_dups = a1.z;
+#endif
                 // a flow that shows up several times in one tile is hot: give it a cache entry if one is free
-                if (use_cache && a1.z >= kHotMinDups && my_slot != kResSpill) {
+                if (use_cache && n_dups >= kHotMinDups && my_slot != kResSpill) {
                     const uint32_t hh = s.hs[my_ridx];
                     uint32_t iidx = hh >> 26;
                     if (*reinterpret_cast<volatile uint32_t*>(&cs.hot[iidx].state) != 0u && cs.hot[iidx].hash != hh) iidx = 64u + ((hh >> 21) & (uint32_t)(kHot2 - 1));
@@ -567,9 +612,9 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                     }
                 }
                 if (kSketch) {
-                    const uint4 r0 = R[0], r1 = R[1];
+                    const uint4 r0 = R[0], r1 = R[1], k2 = R[2];
                     sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
-                                                 u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)), t_packets);
+                                                 u64_of(r1.z, r1.w), u64_of(k2.x, k2.y)), t_packets);
                 }
                 if (my_slot != kResSpill) {
                     reduce_to_hot(t, my_slot, t_bytes, t_packets, t_ns, t_end, t_flags, floor_ns, seen);
@@ -728,9 +773,16 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         team_sync(team);                                           // S2: nobody reads the tile buffer any more
         FA_PROF_MARK(6);                                           // S2 wait
         if (tid == 0) {
+#if FA_K1_EARLY
+            if (kSketch) {                                         // the sketch update reads the keys in the reduce step: re-arm here
+                const uint32_t nt = tile_idx + tile_stride;
+                if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, tc, recs, n, nt); }
+            }
+#else
             tc.nrep = 0; tc.next_chunk = 0;
             const uint32_t nt = tile_idx + tile_stride;
             if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, tc, recs, n, nt); }
+#endif
         }
         FA_PROF_MARK(7);                                           // reductions
     }
