@@ -86,6 +86,53 @@ __device__ uint32_t find_or_create(const Table& t, uint64_t epoch, const uint64_
     return 0xFFFFFFFFu;
 }
 
+#ifndef FA_K6_V2
+#define FA_K6_V2 0      // one-round-trip probe, candidate-only second pass, one barrier less per tile (A/B: profiles/r2_ab_k6_v2.log)
+#endif
+#ifndef FA_K6_MINBLOCKS
+#define FA_K6_MINBLOCKS 1
+#endif
+
+// v2 probe: the three key chunks and the tag travel in ONE round trip (the tag shares a 16-byte chunk with the key tail).
+// Only a slot published during THIS launch (its tag carries the launch epoch) can have been read before its key was
+// visible: then, and only then, fence and read the line again.  Entries of earlier launches are complete.
+__device__ uint32_t find_or_create2(const Table& t, uint64_t epoch, const uint64_t k[5], unsigned long long* n_created) {
+    const uint64_t kk4 = k[4] & 0x00FFFFFFFFFFFFFFull;
+    const uint64_t h = slot_hash(key_premix(k[0], k[1], k[2], k[3], k[4]));
+    uint64_t slot = h & t.mask;
+    bool ordered = false;
+    for (uint32_t probes = 0; probes < 65536; ) {
+        const uint4* L4 = &t.ident[slot * 8];
+        const uint4 c0 = ld_cg_u4(L4), c1 = ld_cg_u4(L4 + 1), c2 = ld_cg_u4(L4 + 2);
+        const unsigned long long tag = u64_of(c2.z, c2.w);
+        const uint32_t state = (uint32_t)(tag & TAG_STATE_MASK);
+        unsigned long long* L = reinterpret_cast<unsigned long long*>(&t.ident[slot * 8]);
+        unsigned long long* tagp = L + 5;
+        if (state == 0) {
+            if (atomicCAS(tagp, 0ull, TAG_CLAIMED) == 0ull) {
+                L[0] = k[0]; L[1] = k[1]; L[2] = k[2]; L[3] = k[3]; L[4] = kk4;
+#pragma unroll
+                for (int c = 6; c < 16; c++) L[c] = 0ull;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long*>(tagp) = (epoch << TAG_EPOCH_SHIFT) | TAG_PUBLISHED;   // no TAG_HAS_BASE
+                red_or_u32(&t.occ[slot >> 5], 1u << (slot & 31));
+                atomicAdd(n_created, 1ull);
+                return (uint32_t)slot;
+            }
+            continue;                                   // lost the race: look at the slot again
+        }
+        if (state == (uint32_t)TAG_CLAIMED) continue;   // being published by someone else
+        if ((tag >> TAG_EPOCH_SHIFT) == epoch && !ordered) { __threadfence(); ordered = true; continue; }
+        const bool same = (u64_of(c0.x, c0.y) == k[0]) & (u64_of(c0.z, c0.w) == k[1]) & (u64_of(c1.x, c1.y) == k[2]) &
+                          (u64_of(c1.z, c1.w) == k[3]) & ((u64_of(c2.x, c2.y) & 0x00FFFFFFFFFFFFFFull) == kk4);
+        if (same) return (uint32_t)slot;
+        slot = (slot + 1) & t.mask;
+        probes++;
+        ordered = false;
+    }
+    return 0xFFFFFFFFu;
+}
+
 __device__ __forceinline__ void load_key(const uint8_t* rec, uint64_t k[5]) {
 #pragma unroll
     for (int i = 0; i < 5; i++) k[i] = ld_u64_unaligned8(rec + 8 * i);    // records are 8-byte aligned (72 / 104 B)
@@ -102,15 +149,24 @@ constexpr int kFeatTile = 256;          // samples per tile == threads per CTA
 constexpr int kFeatRep = 512;           // tile-local election set
 constexpr uint32_t kFeatNone = 0xFFFFFFFFu;
 
+#if FA_K6_V2
+// 64-bit shared-memory max / or are compare-and-swap loops: look first, most samples of a hot flow cannot change the value
+__device__ __forceinline__ void smem_max_u64(uint64_t* p, uint64_t v) { if (v > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+#else
 __device__ __forceinline__ void smem_max_u64(uint64_t* p, uint64_t v) { if (v) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+#endif
 __device__ __forceinline__ void smem_add_u64(uint64_t* p, uint64_t v) { if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+#if FA_K6_V2
+__device__ __forceinline__ void smem_or_u64(uint64_t* p, uint64_t v) { if (v & ~*reinterpret_cast<volatile uint64_t*>(p)) atomicOr(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+#else
 __device__ __forceinline__ void smem_or_u64(uint64_t* p, uint64_t v) { if (v) atomicOr(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+#endif
 __device__ __forceinline__ void gmax(uint8_t* p, uint64_t v) { if (v) red_max_u64(p, v); }
 __device__ __forceinline__ void gadd(uint8_t* p, uint64_t v) { if (v) red_add_u64(p, v); }
 __device__ __forceinline__ void gor32(uint8_t* p, uint64_t v) { if (v) red_or_u32(p, (uint32_t)v); }
 
 struct AddFeat {                        // additional_metrics samples, 72 B
-    static constexpr int kRec = kAddRecBytes, kAcc = 7;
+    static constexpr int kRec = kAddRecBytes, kAcc = 7, kCand2 = -1;
     static __device__ __forceinline__ uint8_t* state(const Table& t, uint32_t slot) { return reinterpret_cast<uint8_t*>(t.feat_add) + (size_t)slot * (kAddState * 16); }
     static __device__ __forceinline__ void extract(const uint8_t* R, uint64_t seq, uint64_t* v) {
         const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48), rtt = ld_u64_unaligned8(R + 56);
@@ -134,7 +190,7 @@ struct AddFeat {                        // additional_metrics samples, 72 B
     }
 };
 struct DnsFeat {                        // dns_metrics samples, 104 B
-    static constexpr int kRec = kDnsRecBytes, kAcc = 8;
+    static constexpr int kRec = kDnsRecBytes, kAcc = 8, kCand2 = -1;
     static __device__ __forceinline__ uint8_t* state(const Table& t, uint32_t slot) { return reinterpret_cast<uint8_t*>(t.feat_dns) + (size_t)slot * (kDnsState * 16); }
     static __device__ __forceinline__ void extract(const uint8_t* R, uint64_t seq, uint64_t* v) {
         const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48), lat = ld_u64_unaligned8(R + 56);
@@ -163,7 +219,7 @@ struct DnsFeat {                        // dns_metrics samples, 104 B
 // pkt_drop_metrics samples (flow_id 40 B + start 8, end 8, bytes u16, packets u16, latest_drop_cause u32, latest_flags u16,
 // eth_protocol u16, latest_state u8), 72 B: AccumulateDrops in sample order
 struct DropFeat {
-    static constexpr int kRec = kDropRecBytes, kAcc = 9;
+    static constexpr int kRec = kDropRecBytes, kAcc = 9, kCand2 = 3;     // accumulator 3 names the last sample with a drop cause
     static __device__ __forceinline__ uint8_t* state(const Table& t, uint32_t slot) { return reinterpret_cast<uint8_t*>(t.feat_drop) + (size_t)slot * (kDropState * 16); }
     static __device__ __forceinline__ void extract(const uint8_t* R, uint64_t seq, uint64_t* v) {
         const uint64_t start = ld_u64_unaligned8(R + 40), end = ld_u64_unaligned8(R + 48);
@@ -213,7 +269,7 @@ template <class F> constexpr size_t feature_fold_smem() {
 }
 
 template <class F>
-__global__ void __launch_bounds__(kFeatTile)
+__global__ void __launch_bounds__(kFeatTile, FA_K6_MINBLOCKS)
 feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint64_t epoch, uint64_t seq0,
                     uint32_t* __restrict__ slot_of, Counters* ctr) {
     FA_DYN_SMEM(sm);
@@ -230,6 +286,16 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
     for (uint32_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
         const uint32_t first = tix * kFeatTile, cnt = min((uint32_t)kFeatTile, n - first);
         const uint64_t* G = reinterpret_cast<const uint64_t*>(recs + (size_t)first * F::kRec);
+#if FA_K6_V2
+        {   // the CTA's next tile: ask L2 for it now, one 128-byte line per thread
+            const uint32_t ntx = tix + gridDim.x;
+            if (ntx < n_tiles) {
+                const uint8_t* nb = recs + (size_t)ntx * kFeatTile * F::kRec;
+                const uint32_t nbytes = min((uint32_t)kFeatTile, n - ntx * kFeatTile) * F::kRec;
+                if (tid * 128u < nbytes) prefetch_l2(nb + tid * 128u);
+            }
+        }
+#endif
         if (cnt == (uint32_t)kFeatTile) {                                    // all loads in flight before the first store
             uint64_t tmp[F::kRec / 8];
 #pragma unroll
@@ -240,6 +306,9 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
             for (uint32_t w = tid; w < cnt * (F::kRec / 8); w += kFeatTile) tile[w] = G[w];
         }
         for (uint32_t w = tid; w < kFeatRep; w += kFeatTile) rep[w] = kFeatNone;
+#if FA_K6_V2
+        if (tid < cnt) slot_of[first + tid] = kFeatNone;                      // only a flow's candidates for "first" / "last" get a slot below
+#endif
         __syncthreads();
         const bool valid = tid < cnt;
         const uint8_t* R = reinterpret_cast<const uint8_t*>(tile) + (size_t)tid * F::kRec;
@@ -277,8 +346,19 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
         if (valid && r < (uint32_t)kFeatTile && r != tid) { F::fold(acc + r, kFeatTile, v); atomicAdd(&dupc[r], 1u); }
         __syncthreads();
         if (valid && r == tid) {
+#if FA_K6_V2
+            const uint32_t slot = find_or_create2(t, epoch, k, &ctr->live);
+            if (slot == kFeatNone) atomicAdd(&ctr->spills, 1ull + dupc[tid]);
+            else {
+                // the tile's earliest sample of the flow (and, for drops, its last one with a cause) are the only ones the
+                // second pass has to look at: acc 0 = max ~seq, acc kCand2 = max (seq + 1)
+                slot_of[(uint32_t)(~acc[tid] - seq0)] = slot;
+                if (F::kCand2 >= 0) { const uint64_t c2 = acc[(F::kCand2 < 0 ? 0 : F::kCand2) * kFeatTile + tid]; if (c2) slot_of[(uint32_t)(c2 - 1 - seq0)] = slot; }
+            }
+#else
             const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
             slot_s[tid] = slot;
+#endif
             if (slot != kFeatNone) {
                 F::flush(F::state(t, slot), acc + tid, kFeatTile);
                 FeatHot<F>& e = hot[hq];
@@ -293,16 +373,24 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
                 }
             }
         }
+#if !FA_K6_V2
         __syncthreads();
         if (valid) {
             const uint32_t slot = r == kFeatCached ? my_slot : slot_s[r];
             slot_of[first + tid] = slot;
             if (slot == kFeatNone) atomicAdd(&ctr->spills, 1ull);
         }
+#endif
         __syncthreads();                                                      // tile / rep / slot_s are re-used
     }
     __syncthreads();
-    if (tid < kFeatHot && hot[tid].state == 2u) F::flush(F::state(t, hot[tid].slot), hot[tid].acc, 1);
+    if (tid < kFeatHot && hot[tid].state == 2u) {
+        F::flush(F::state(t, hot[tid].slot), hot[tid].acc, 1);
+#if FA_K6_V2
+        if (hot[tid].acc[0]) slot_of[(uint32_t)(~hot[tid].acc[0] - seq0)] = hot[tid].slot;
+        if (F::kCand2 >= 0) { const uint64_t c2 = hot[tid].acc[F::kCand2 < 0 ? 0 : F::kCand2]; if (c2) slot_of[(uint32_t)(c2 - 1 - seq0)] = hot[tid].slot; }
+#endif
+    }
 }
 
 // second pass: the sample that turned out to be the flow's first one writes the adopted block fields
