@@ -446,7 +446,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         // instead of re-running every round; whatever is left goes to the general loop.
         {
             constexpr uint32_t kWarps = kTile / 32;
-            const uint32_t per = (nrep_total + kWarps - 1) / kWarps;              // <= 32
+            const uint32_t per = ((nrep_total + kWarps - 1) / kWarps + 3u) & ~3u;  // <= 32, whole rounds: same longest warp, fewer half-empty rounds
             const uint32_t w0 = min(nrep_total, (uint32_t)warp * per), w1 = min(nrep_total, w0 + per);
             RepIdx* const wl = s.slow[warp];                                       // general-loop flows from the front, second-pass flows from the back
             uint32_t nslow = 0, ncoll = 0;
