@@ -490,7 +490,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         const bool fast = act && (eqb & 0x07u) == 0x07u;           // settled flow, key matches
                         uint32_t* const rw = reinterpret_cast<uint32_t*>(&s.res4[ridx[q]]);
                         if (fast && j == 0) rw[0] = slot[q];
-                        if (fast && j == 3) *reinterpret_cast<uint2*>(rw + 1) = make_uint2(line[q].x, line[q].y);   // start mirror (eth_protocol in between)
+                        if (fast && j == 3) { rw[1] = line[q].x; rw[2] = line[q].y; }           // start mirror (eth_protocol in between); rw + 1 is only 4-byte aligned
                         if (fast && j == 2) {
                             rw[3] = (uint32_t)(tag >> TAG_FLAGS_SHIFT);            // flag bits the hot line already holds (low 16)
                             if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[q]] != 0) {

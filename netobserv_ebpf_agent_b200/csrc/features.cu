@@ -87,10 +87,10 @@ __device__ uint32_t find_or_create(const Table& t, uint64_t epoch, const uint64_
 }
 
 #ifndef FA_K6_V2
-#define FA_K6_V2 0      // one-round-trip probe, candidate-only second pass, one barrier less per tile (A/B: profiles/r2_ab_k6_v2.log)
+#define FA_K6_V2 1      // one-round-trip probe, candidate-only second pass, one barrier less per tile: +9 % DNS / +8 % RTT (profiles/r2_ab_k6_v2.log)
 #endif
 #ifndef FA_K6_MINBLOCKS
-#define FA_K6_MINBLOCKS 1
+#define FA_K6_MINBLOCKS 4   // 64 registers: four CTAs per SM (5 -> 48 registers with spills: -3 %, 6: -10 %)
 #endif
 
 // v2 probe: the three key chunks and the tag travel in ONE round trip (the tag shares a 16-byte chunk with the key tail).
