@@ -48,16 +48,19 @@ typedef RepIdxOf<(kTile > 256)>::type RepIdx;   // index of a record inside its 
 #define FA_K1_STREAM_HINT 1   // record stream read with an L2 evict-first policy (+1.5 % / +3.7 % / +0.5 %: profiles/r2_ab_k1_l2_hints.log)
 #endif
 #ifndef FA_K1_ETAG
-#define FA_K1_ETAG 0     // election slots carry hash bits; duplicate fold after the loop (A/B: profiles/r2_ab_k1_pipe.log)
+#define FA_K1_ETAG 1     // election slots carry hash bits; duplicate fold after the loop (A/B: profiles/r2_ab_k1_pipe.log)
 #endif
 #ifndef FA_K1_PIPE
-#define FA_K1_PIPE 0     // probe phase: even split of the list, software-pipelined rounds, compact second pass
+#define FA_K1_PIPE 1     // probe phase: even split of the list, software-pipelined rounds, compact second pass
 #endif
 #ifndef FA_K1_EARLY
-#define FA_K1_EARLY 0    // next tile's TMA issued by the last warp out of the probe phase; the reduce step works from the accumulators alone
+#define FA_K1_EARLY 1    // next tile's TMA issued by the last warp out of the probe phase; the reduce step works from the accumulators alone
 #endif
 #if FA_K1_EARLY && !(FA_K1_PIPE && FA_K1_ETAG)
 #error FA_K1_EARLY builds on FA_K1_PIPE and FA_K1_ETAG
+#endif
+#ifndef FA_K1_PF
+#define FA_K1_PF 0       // ask L2 for the team's tile after next when a tile starts (A/B: profiles/r2_ab_k1_pipe.log)
 #endif
 #ifndef FA_K1_MINDUPS
 #define FA_K1_MINDUPS 1
@@ -272,6 +275,12 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         if (tile_idx >= n_tiles) break;
         const uint32_t first = tile_idx * kTile;
         const uint32_t cnt = min((uint32_t)kTile, n - first);
+#if FA_K1_PF
+        if (tid == 32) {                                           // L2 prefetch, two tiles ahead of the one being staged
+            const uint32_t pt_ = tile_idx + 2u * tile_stride;
+            if (pt_ < n_tiles) tma_prefetch_l2(recs + (size_t)pt_ * kTile * kRecChunks, min((uint32_t)kTile, n - pt_ * kTile) * kRecBytes);
+        }
+#endif
         mbar_wait(&tc.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
 
