@@ -717,8 +717,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="zipf10m", choices=sorted(WORKLOADS) + ["rttdns"])
-    ap.add_argument("--batch", type=int, default=1 << 27,
-                    help="records per step per GPU (2^27 x 144 B = 19.3 GB; 20 steps = a timed region of >= 200 ms)")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="records per step per GPU; default 3 x 2^26 at N = 1 (29 GB: at 16-17 Gpkt/s the driver's 20 steps are a "
+                         "timed region of >= 200 ms), 2^27 = one exchange round per step at N > 1 (10-11 ms per step)")
     ap.add_argument("--max-batch", type=int, default=None,
                     help="records per K1 launch (N = 1); default 2^23 with the Accounter's maxEntries rule on (the largest size "
                          "that keeps its fast-path test true on every workload), 2^24 for the plain-map workload zipf1m")
@@ -737,6 +738,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-events", action="store_true", help="skip the 64-byte packet-event row of e2e")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = (3 << 26) if args.gpus == 1 else (1 << 27)
     if args.workload == "rttdns":
         return run_rttdns(args)
     wl = WORKLOADS[args.workload]

@@ -2,21 +2,27 @@
 // open-addressed flow table with the semantics of the reference's userspace Accounter
 // (pkg/flow/account.go:82-96 + pkg/model/flow_content.go:28-61).
 //
-// One persistent CTA per SM, 1024 threads = 4 teams of 256.  Each team owns a stream of
-// 256-record tiles and synchronises with a named barrier; all teams share a small cache of
+// One persistent CTA per SM, 1024 threads = 8 teams of 128.  Each team owns a stream of
+// 128-record tiles and synchronises with a named barrier; all teams share a small cache of
 // the hottest flows.  Per tile:
-//   TMA bulk copy (cp.async.bulk + mbarrier) stages 36 KB of records in shared memory
+//   TMA bulk copy (cp.async.bulk + mbarrier) stages 18 KB of records in shared memory
 //   -> E: each thread hashes one record; a record of a cached hot flow folds straight into
-//      the cache's shared-memory accumulators; otherwise duplicates of a key inside the tile
-//      elect one representative (shared-memory CAS table) and fold into it with 32-bit
-//      shared atomics
-//   -> probe: the team's representatives are dealt evenly to its 8 warps; 8 lanes per flow,
-//      16 identity lines (128 B each, one coalesced load) in flight per warp, a masked 16-byte
-//      compare per lane and one ballot decide hit / miss
+//      the cache's shared-memory accumulators; every other record writes its own values into
+//      its accumulator words and enters the tile's election set (shared-memory CAS table whose
+//      slots carry hash bits): the first record of a key becomes its representative, later
+//      ones fold into the representative's accumulators with 32-bit shared atomics
+//   -> probe: the list of representatives is split evenly over the team's 4 warps; 8 lanes
+//      per flow, rounds of 4 flows, four identity lines (128 B each, one coalesced load) in
+//      flight per warp at all times (the load of round r + 4 is issued when round r has been
+//      compared); a masked 16-byte compare per lane and one ballot decide hit / miss; flows
+//      whose home slot holds another flow are collected and probed one slot on in a second,
+//      compact pass
 //   -> general loop (rare): inserts (CAS-claim, write, fence, publish), collisions, flows
 //      being published by another SM
-//   -> one lane per flow: three fire-and-forget reductions on the 32-byte hot line
-//      (RED.add bytes, RED.add packets, RED.max end; start / flags only when they can change it).
+//   -> the last warp out of the probe phase re-arms the tile's TMA for the team's next tile
+//   -> one lane per flow, from the accumulators alone: three fire-and-forget reductions on
+//      the 32-byte hot line (RED.add bytes, RED.add packets, RED.max end; start / flags only
+//      when they can change it).
 // The cache is flushed with the same reductions when the CTA runs out of tiles.
 //
 // Exactness of the order-dependent fields (eth_protocol / dscp / sampling = last non-zero,
@@ -30,37 +36,21 @@
 namespace fa {
 
 #ifndef FA_K1_TILE
-#define FA_K1_TILE 256
+#define FA_K1_TILE 128   // 8 teams x 128-record tiles: +8 % zipf10m, +12 % zipf1m, +3.5 % uniform10m over 4 x 256 (profiles/r2_ab_k1_pipe.log)
 #endif
 constexpr int kTile      = FA_K1_TILE;          // records per tile == threads per team
 constexpr int kTeams     = 1024 / kTile;        // teams per CTA (one CTA per SM): independent tile pipelines that fill each other's
-                                                // bubbles (tile wait, team barriers).  8 x 128 was measured: the TMA wait per tile
-                                                // stays, the work per tile halves -> slower on the Zipf workloads (profiles/README.md)
+                                                // bubbles (tile wait, team barriers).  With the dynamic chunk pulling of the first
+                                                // two rounds 8 x 128 lost to 4 x 256 (-4 ... -27 %); with the even split, the
+                                                // pipelined rounds and the early re-arm it wins: half as many warps per barrier
 constexpr int kCtaThreads = kTile * kTeams;
 constexpr int kRepSlots  = 2 * kTile;
-constexpr int kInflight  = 4;                   // probe rounds in flight per warp (4 flows per round)
-constexpr int kHot2 = kTile > 256 ? 16 : 32;    // second-chance entries (another slice of the hash); fewer when 512-record tiles need the room
+constexpr int kHot2 = 32;                       // second-chance entries (another slice of the hash)
 constexpr int kHotEntries = 64 + kHot2;         // 64 primary entries + the second-chance ones
-template <bool kWide> struct RepIdxOf { typedef uint8_t type; };
-template <> struct RepIdxOf<true> { typedef uint16_t type; };
-typedef RepIdxOf<(kTile > 256)>::type RepIdx;   // index of a record inside its tile
+typedef uint8_t RepIdx;                         // index of a record inside its tile
+static_assert(kTile == 128 || kTile == 256, "election slots and lists keep the tile index in 8 bits; 1024 threads per CTA");
 #ifndef FA_K1_STREAM_HINT
 #define FA_K1_STREAM_HINT 1   // record stream read with an L2 evict-first policy (+1.5 % / +3.7 % / +0.5 %: profiles/r2_ab_k1_l2_hints.log)
-#endif
-#ifndef FA_K1_ETAG
-#define FA_K1_ETAG 1     // election slots carry hash bits; duplicate fold after the loop (A/B: profiles/r2_ab_k1_pipe.log)
-#endif
-#ifndef FA_K1_PIPE
-#define FA_K1_PIPE 1     // probe phase: even split of the list, software-pipelined rounds, compact second pass
-#endif
-#ifndef FA_K1_EARLY
-#define FA_K1_EARLY 1    // next tile's TMA issued by the last warp out of the probe phase; the reduce step works from the accumulators alone
-#endif
-#if FA_K1_EARLY && !(FA_K1_PIPE && FA_K1_ETAG)
-#error FA_K1_EARLY builds on FA_K1_PIPE and FA_K1_ETAG
-#endif
-#ifndef FA_K1_PF
-#define FA_K1_PF 0       // ask L2 for the team's tile after next when a tile starts (A/B: profiles/r2_ab_k1_pipe.log)
 #endif
 #ifndef FA_K1_MINDUPS
 #define FA_K1_MINDUPS 1
@@ -70,19 +60,19 @@ constexpr uint32_t kRepEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kResSpill = 0xFFFFFFFFu;
 constexpr uint32_t kProbeLimit = 8192;
 
-struct __align__(128) TeamSmem {                  // 52,992 B per team
-    uint4    tile[kTile * kRecChunks];            // 36,864 B  one TMA-staged tile of records
-    uint32_t acc[kTile][8];                       //  8,192 B  what duplicates add to their representative
-    uint32_t hs[kTile];                           //  1,024 B  low 32 bits of the slot hash
-    uint4    res4[kTile];                         //  4,096 B  per representative: table slot | mirror lo | flags seen + mirror hi | -
-    uint32_t rep[kRepSlots];                      //  2,048 B  tile-local key -> representative index
-    uint8_t  tdirty[kTile];                       //    256 B  set by duplicates whose descriptor differs
-    RepIdx   glist[kTile];                        //    256 B  team-wide compacted list of representatives
-    RepIdx   slow[kTile / 32][32];                //    256 B  per-warp flows that need the general probe loop
+struct __align__(128) TeamSmem {                  // 26,496 B per team (128-record tiles)
+    uint4    tile[kTile * kRecChunks];            // 18,432 B  one TMA-staged tile of records
+    uint32_t acc[kTile][8];                       //  4,096 B  per record: bytes lo / hi | packets | flags + duplicates << 16 | ns lo | end lo | ns hi | end hi
+    uint32_t hs[kTile];                           //    512 B  low 32 bits of the slot hash
+    uint4    res4[kTile];                         //  2,048 B  per representative: table slot | start mirror lo | eth + mirror hi | flag bits the hot line holds
+    uint32_t rep[kRepSlots];                      //  1,024 B  tile-local election set: 23 hash bits << 8 | representative index
+    uint8_t  tdirty[kTile];                       //    128 B  set by duplicates whose descriptor differs
+    RepIdx   glist[kTile];                        //    128 B  team-wide compacted list of representatives
+    RepIdx   slow[kTile / 32][32];                //    128 B  per warp: general-loop flows from the front, second-pass flows from the back
 };
-struct __align__(16) TeamCtl {                    // kept outside TeamSmem so that four teams + the cache fit in 227 KB
+struct __align__(16) TeamCtl {                    // kept outside TeamSmem so that the teams + the cache fit in 227 KB
     unsigned long long full_bar;                  // mbarrier of the team's tile
-    uint32_t nrep, next_chunk;
+    uint32_t nrep, done;                          // representatives of the tile; warps that are through with its probes
 };
 struct __align__(16) HotEntry {                   // 208 B: a stride of 52 words keeps 8 entries on distinct banks
     uint4    line[8];                             // copy of the flow's identity line
@@ -94,9 +84,8 @@ struct __align__(16) HotEntry {                   // 208 B: a stride of 52 words
     uint32_t pad[7];
 };
 static_assert(sizeof(HotEntry) == 208, "HotEntry stride");
-static_assert(kTile != 256 || sizeof(TeamSmem) == 52992, "TeamSmem has no padding to spare");
-static_assert(!FA_K1_ETAG || kTile <= 256, "election slots keep the tile index in 8 bits");
-struct __align__(128) AggSmem {                   // 232,064 B of the 232,448 B (227 KB) an sm_100 CTA may use
+static_assert(kTile != 128 || sizeof(TeamSmem) == 26496, "TeamSmem has no padding to spare");
+struct __align__(128) AggSmem {                   // 232,080 B of the 232,448 B (227 KB) an sm_100 CTA may use
     TeamSmem team[kTeams];
     HotEntry hot[kHotEntries];
     TeamCtl  ctl[kTeams];
@@ -249,7 +238,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
     if (tid == 0) {
         mbar_init(&tc.full_bar, 1);
         fence_barrier_init();
-        tc.nrep = 0; tc.next_chunk = 0;
+        tc.nrep = 0; tc.done = 0;
     }
     s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;
     *reinterpret_cast<uint4*>(&s.acc[tid][0]) = make_uint4(0, 0, 0, 0);
@@ -275,12 +264,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         if (tile_idx >= n_tiles) break;
         const uint32_t first = tile_idx * kTile;
         const uint32_t cnt = min((uint32_t)kTile, n - first);
-#if FA_K1_PF
-        if (tid == 32) {                                           // L2 prefetch, two tiles ahead of the one being staged
-            const uint32_t pt_ = tile_idx + 2u * tile_stride;
-            if (pt_ < n_tiles) tma_prefetch_l2(recs + (size_t)pt_ * kTile * kRecChunks, min((uint32_t)kTile, n - pt_ * kTile) * kRecBytes);
-        }
-#endif
         mbar_wait(&tc.full_bar, it & 1u);
         FA_PROF_MARK(0);                                           // waiting for the tile
 
@@ -325,7 +308,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         if (v_end && (uint32_t)v_end > A[5]) atomicMax(&A[5], (uint32_t)v_end);
                     }
                 }
-#if FA_K1_ETAG
                 if (is_rep) {
                     // election: the slot holds (23 hash bits << 8 | tile index), so a slot taken by another key is
                     // walked past without touching the tile; the fold of a duplicate runs after the loop, once per
@@ -333,7 +315,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                     uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
                     const uint32_t mine = (((uint32_t)(h >> 16) & 0x7FFFFFu) << 8) | (uint32_t)tid;
                     uint32_t dup_of = kRepEmpty;
-#if FA_K1_EARLY
                     {   // own values go into the accumulators BEFORE the record can be elected: whoever finds it in the
                         // election set adds to initialised words, and the reduce step no longer needs the tile
                         const uint4 r3 = R[3], r4 = R[4];
@@ -343,7 +324,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         s.tdirty[tid] = 0;
                         __threadfence_block();
                     }
-#endif
                     for (;;) {
                         const uint32_t old = atomicCAS(&s.rep[rs], kRepEmpty, mine);
                         if (old == kRepEmpty) break;
@@ -376,11 +356,7 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                             if (fl) atomicOr(&A[3], fl);
                             if (v_start) atomicMax(&A[4], (uint32_t)v_ns);
                             if (v_end) atomicMax(&A[5], (uint32_t)v_end);
-#if FA_K1_EARLY
                             atomicAdd(&A[3], 1u << 16);              // duplicates seen (above the 16 flag bits): cache candidacy
-#else
-                            atomicAdd(&A[6], 1u);                    // duplicates seen: cache candidacy
-#endif
                             uint32_t d = diff4_masked(O[4], r4, chunk_mask(3));      // exact 74-byte descriptor compare
 #pragma unroll
                             for (int c = 5; c < 9; c++) d |= diff4_masked(O[c], R[c], chunk_mask(c - 1));
@@ -388,50 +364,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                         }
                     }
                 }
-#else
-                if (is_rep) {
-                    uint32_t rs = (uint32_t)(h >> 40) & (kRepSlots - 1);
-                    for (;;) {
-                        const uint32_t old = atomicCAS(&s.rep[rs], kRepEmpty, (uint32_t)tid);
-                        if (old == kRepEmpty) break;
-                        const uint4* O = T + old * kRecChunks;
-                        const uint4 o2 = O[2];
-                        const bool key_eq = eq4_masked(o2, r2, chunk_mask(2)) && eq4_masked(O[0], r0, chunk_mask(0)) &&
-                                            eq4_masked(O[1], r1, chunk_mask(1));
-                        if (key_eq) {
-                            // Same key.  Fold into that representative with 32-bit shared atomics when the high
-                            // words of the timestamps agree (the common case); otherwise go to the table on our own.
-                            const uint4 r3 = R[3], r4 = R[4], o3 = O[3];
-                            const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
-                            const uint64_t v_ns = 0ull - v_start;
-                            const uint64_t o_ns = 0ull - u64_of(o2.z, o2.w), o_end = u64_of(o3.x, o3.y);
-                            const bool ok = (v_start == 0 || (uint32_t)(v_ns >> 32) == (uint32_t)(o_ns >> 32)) &&
-                                            (v_end == 0 || (uint32_t)(v_end >> 32) == (uint32_t)(o_end >> 32));
-                            if (ok) {
-                                is_rep = false;
-                                uint32_t* A = s.acc[old];
-                                const uint32_t b_lo = r3.z, b_hi = r3.w;
-                                const uint32_t prev = atomicAdd(&A[0], b_lo);
-                                const uint32_t hi_add = b_hi + ((prev + b_lo) < prev ? 1u : 0u);
-                                if (hi_add) atomicAdd(&A[1], hi_add);
-                                atomicAdd(&A[2], r4.x);
-                                const uint32_t fl = r4.y >> 16;
-                                if (fl) atomicOr(&A[3], fl);
-                                if (v_start) atomicMax(&A[4], (uint32_t)v_ns);
-                                if (v_end) atomicMax(&A[5], (uint32_t)v_end);
-                                atomicAdd(&A[6], 1u);                // duplicates seen: cache candidacy
-                                // exact descriptor compare against the representative (74 bytes, padding masked)
-                                bool same = eq4_masked(O[4], r4, chunk_mask(3));
-#pragma unroll
-                                for (int c = 5; c < 9; c++) same = same && eq4_masked(O[c], R[c], chunk_mask(c - 1));
-                                if (!same) s.tdirty[old] = 1;
-                            }
-                            break;
-                        }
-                        rs = (rs + 1) & (kRepSlots - 1);
-                    }
-                }
-#endif
             }
             // team-wide list of representatives, so that every warp probes an equal share
             const uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_rep);
@@ -447,7 +379,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
         const uint32_t nrep_total = tc.nrep;
         s.rep[tid] = kRepEmpty; s.rep[tid + kTile] = kRepEmpty;   // nobody reads the election table after S1
 
-#if FA_K1_PIPE
         // ------------------------------------------------------ probe: the list is split evenly over the team's warps;
         // a warp walks its share in rounds of 4 flows (8 lanes per flow) with four identity-line loads in flight at all
         // times: the load of round r + 4 is issued as soon as round r has been compared.  Flows whose home slot holds
@@ -555,18 +486,16 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             }
             __syncwarp();
             FA_PROF_MARK(4);                                       // general probe loop
-#if FA_K1_EARLY
             if (lane == 0) {                                       // the warp is done with the tile: the last one out re-arms it
                 __threadfence_block();
-                if (atomicAdd(&tc.next_chunk, 1u) == kWarps - 1u) {
-                    tc.next_chunk = 0;
+                if (atomicAdd(&tc.done, 1u) == kWarps - 1u) {
+                    tc.done = 0;
                     tc.nrep = 0;                                   // every warp has read the list length; reset it before the
                                                                    // next tile can arrive (its E phase starts right after S2)
                     const uint32_t nt = tile_idx + tile_stride;
                     if (!kSketch && nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, tc, recs, n, nt); }
                 }
             }
-#endif
 
             // -------------------------------------------------- one lane per flow: totals, then the reductions
             if (w0 + lane < w1) {
@@ -575,7 +504,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint32_t my_slot = rr.x;
                 const uint64_t floor_ns = u64_of(rr.y, rr.z >> 16) << 16;                      // <= hot.nstart, always
                 const uint32_t seen = rr.w & 0xFFFFu;
-#if FA_K1_EARLY
                 const uint4* R = T + my_ridx * kRecChunks;          // (kSketch only: the tile stays until S2)
                 const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
                 const uint4 a1 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][4]);
@@ -584,24 +512,6 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
                 const uint32_t t_flags = a0.w & 0xFFFFu, n_dups = a0.w >> 16;
                 const uint64_t t_ns = u64_of(a1.x, a1.z), t_end = u64_of(a1.y, a1.w);
                 const uint64_t v_ns = t_ns, v_end = t_end;           // the cache entry's windows: high words only
-#else
-                const uint4* R = T + my_ridx * kRecChunks;
-                const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
-                const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
-                const uint4 a1 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][4]);
-                const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
-                const uint64_t v_ns = 0ull - v_start;
-                const uint64_t t_bytes = u64_of(r3.z, r3.w) + u64_of(a0.x, a0.y);
-                const uint32_t t_packets = r4.x + a0.z;
-                const uint32_t t_flags = (r4.y >> 16) | a0.w;
-                const uint64_t c_ns = u64_of(a1.x, (uint32_t)(v_ns >> 32)), c_endts = u64_of(a1.y, (uint32_t)(v_end >> 32));
-                const uint64_t t_ns = c_ns > v_ns ? c_ns : v_ns;
-                const uint64_t t_end = c_endts > v_end ? c_endts : v_end;
-                *reinterpret_cast<uint4*>(&s.acc[my_ridx][0]) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(&s.acc[my_ridx][4]) = make_uint4(0, 0, 0, 0);
-                s.tdirty[my_ridx] = 0;
-                const uint32_t n_dups = a1.z;
-#endif
                 // a flow that shows up several times in one tile is hot: give it a cache entry if one is free
                 if (use_cache && n_dups >= kHotMinDups && my_slot != kResSpill) {
                     const uint32_t hh = s.hs[my_ridx];
@@ -633,165 +543,13 @@ aggregate_kernel(const uint4* __restrict__ recs, uint32_t n, Table t, uint64_t e
             }
             FA_PROF_MARK(5);                                       // totals + reductions
         }
-#else
-        // ------------------------------------------------------ probe: warps pull chunks of 16 flows (dynamic
-        // balancing: a warp stuck behind a DRAM miss or an insert simply takes fewer chunks)
-        for (;;) {
-            uint32_t c0 = 0;
-            if (lane == 0) c0 = atomicAdd(&tc.next_chunk, 4u * kInflight);
-            c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
-            if (c0 >= nrep_total) break;
-            const uint32_t c_end = min(nrep_total, c0 + 4u * kInflight);
-            uint4 line[kInflight];
-            uint32_t ridx[kInflight];
-            uint32_t slot[kInflight];
-            uint32_t pend = 0;                                     // rounds of this lane group still to be probed
-#pragma unroll
-            for (int r = 0; r < kInflight; r++) {
-                const uint32_t k = c0 + r * 4 + g;
-                ridx[r] = 0;
-                if (k < c_end) { pend |= 1u << r; ridx[r] = s.glist[k]; }
-                slot[r] = s.hs[ridx[r]] & tmask;
-            }
-            uint32_t nslow = 0;
-            // 8 lanes per flow, 16 identity lines in flight per warp; pass 0 = home slot, pass 1 = next slot for
-            // the flows whose home slot is held by another settled flow
-#pragma unroll 1
-            for (int pass = 0; pass < 2; pass++) {
-#pragma unroll
-                for (int r = 0; r < kInflight; r++) {
-                    line[r] = make_uint4(0, 0, 0, 0);
-                    if ((pend >> r) & 1u) line[r] = ld_cg_u4(&t.ident[(size_t)slot[r] * 8 + j]);
-                }
-#pragma unroll
-                for (int r = 0; r < kInflight; r++) {
-                    const bool act = (pend >> r) & 1u;
-                    const uint4 rchunk = T[ridx[r] * kRecChunks + rc];
-                    bool eq = eq4_masked(line[r], rchunk, cmask);
-                    const uint64_t tag = u64_of(line[r].z, line[r].w);  // meaningful in lane j == 2 only
-                    bool settled = false;
-                    if (j == 2) {
-                        settled = (tag & (TAG_STATE_MASK | TAG_HAS_BASE)) == (TAG_PUBLISHED | TAG_HAS_BASE) &&
-                                  (tag >> TAG_EPOCH_SHIFT) != epoch;
-                        eq = eq && settled;
-                    }
-                    const uint32_t eqb = (__ballot_sync(0xFFFFFFFFu, eq) >> (g * 8)) & 0xFFu;
-                    const bool gsettled = (__ballot_sync(0xFFFFFFFFu, settled) >> (g * 8 + 2)) & 1u;
-                    const bool fast = act && (eqb & 0x07u) == 0x07u;   // settled flow, key matches
-                    uint32_t* const rw = reinterpret_cast<uint32_t*>(&s.res4[ridx[r]]);       // one address for the group's stores
-                    if (fast && j == 0) rw[0] = slot[r];
-                    if (fast && j == 3) { rw[1] = line[r].x; reinterpret_cast<uint16_t*>(rw + 2)[1] = (uint16_t)(line[r].y >> 16); }
-                    if (fast && j == 2) {
-                        reinterpret_cast<uint16_t*>(rw + 2)[0] = (uint16_t)(tag >> TAG_FLAGS_SHIFT);
-                        if ((eqb & 0xF8u) != 0xF8u || s.tdirty[ridx[r]] != 0) {
-                            unsigned long long* tagp = reinterpret_cast<unsigned long long*>(&t.ident[(size_t)slot[r] * 8 + 2]) + 1;
-                            if (!(tag & TAG_DIRTY)) atomicOr(tagp, (unsigned long long)TAG_DIRTY);
-                            cs.any_dirty = 1;
-                        }
-                    }
-                    const bool collide = act && !fast && gsettled && pass == 0;   // other settled flow: look one slot on
-                    const bool to_slow = act && !fast && !collide;
-                    if (collide) slot[r] = (slot[r] + 1) & tmask;
-                    else pend &= ~(1u << r);
-                    if (kProf && j == 0) {
-                        if (collide) c_collide++;
-                        if (fast && pass == 1) c_p1fast++;
-                        if (act && !fast && !gsettled) c_unsettled++;
-                    }
-                    const uint32_t slowb = __ballot_sync(0xFFFFFFFFu, to_slow && j == 0);
-                    if (slowb) {
-                        if (to_slow && j == 0) s.slow[warp][nslow + __popc(slowb & lt_mask)] = (RepIdx)ridx[r];
-                        nslow += __popc(slowb);
-                    }
-                }
-                if (!__any_sync(0xFFFFFFFFu, pend != 0u)) break;
-            }
-            __syncwarp();
-            if (lane == 0) { FA_EMUL_COUNT(0, c_end - c0); FA_EMUL_COUNT(1, nslow); }
-            if (kProf && lane == 0) { c_reps += c_end - c0; c_slow += nslow; }
-            FA_PROF_MARK(3);                                       // pipelined probe passes
-            for (uint32_t base = 0; base < nslow; base += 4) {     // inserts, long collision chains, in-flight publishes
-                const uint32_t k = base + g;
-                const bool act = k < nslow;
-                const uint32_t ri = act ? s.slow[warp][k] : 0;
-                const uint4 rchunk = T[ri * kRecChunks + rc];
-                const uint4 c2 = T[ri * kRecChunks + 2];
-                const uint64_t own_ns = 0ull - u64_of(c2.z, c2.w);
-                const uint64_t dup_ns = u64_of(s.acc[ri][4], (uint32_t)(own_ns >> 32));
-                const uint32_t got = probe_general(t, epoch, act, s.hs[ri] & tmask, rchunk, s.tdirty[ri] != 0,
-                                                   dup_ns > own_ns ? dup_ns : own_ns, g, j, cmask, my_inserts, &cs.any_dirty);
-                if (act && j == 0) s.res4[ri] = make_uint4(got, 0u, 0u, 0u);   // mirror / seen flags unknown: issue every reduction
-            }
-            __syncwarp();
-            FA_PROF_MARK(4);                                       // general probe loop
-
-            // -------------------------------------------------- one lane per flow: totals, then the reductions
-            if (c0 + lane < c_end) {
-                const uint32_t my_ridx = s.glist[c0 + lane];
-                const uint4 rr = s.res4[my_ridx];
-                const uint32_t my_slot = rr.x;
-                const uint64_t floor_ns = u64_of(rr.y, rr.z >> 16) << 16;                      // <= hot.nstart, always
-                const uint32_t seen = rr.z & 0xFFFFu;
-                const uint4* R = T + my_ridx * kRecChunks;
-                const uint4 r2 = R[2], r3 = R[3], r4 = R[4];
-                const uint4 a0 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][0]);
-                const uint4 a1 = *reinterpret_cast<const uint4*>(&s.acc[my_ridx][4]);
-                const uint64_t v_start = u64_of(r2.z, r2.w), v_end = u64_of(r3.x, r3.y);
-                const uint64_t v_ns = 0ull - v_start;
-                const uint64_t t_bytes = u64_of(r3.z, r3.w) + u64_of(a0.x, a0.y);
-                const uint32_t t_packets = r4.x + a0.z;
-                const uint32_t t_flags = (r4.y >> 16) | a0.w;
-                const uint64_t c_ns = u64_of(a1.x, (uint32_t)(v_ns >> 32)), c_endts = u64_of(a1.y, (uint32_t)(v_end >> 32));
-                const uint64_t t_ns = c_ns > v_ns ? c_ns : v_ns;
-                const uint64_t t_end = c_endts > v_end ? c_endts : v_end;
-                *reinterpret_cast<uint4*>(&s.acc[my_ridx][0]) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(&s.acc[my_ridx][4]) = make_uint4(0, 0, 0, 0);
-                s.tdirty[my_ridx] = 0;
-                // a flow that shows up several times in one tile is hot: give it a cache entry if one is free
-                if (use_cache && a1.z >= kHotMinDups && my_slot != kResSpill) {
-                    const uint32_t hh = s.hs[my_ridx];
-                    uint32_t iidx = hh >> 26;
-                    if (*reinterpret_cast<volatile uint32_t*>(&cs.hot[iidx].state) != 0u && cs.hot[iidx].hash != hh) iidx = 64u + ((hh >> 21) & (uint32_t)(kHot2 - 1));
-                    HotEntry& ce = cs.hot[iidx];
-                    if (*reinterpret_cast<volatile uint32_t*>(&ce.state) == 0u && atomicCAS(&ce.state, 0u, 1u) == 0u) {
-#pragma unroll
-                        for (int c = 0; c < 8; c++) ce.line[c] = ld_cg_u4(&t.ident[(size_t)my_slot * 8 + c]);
-                        *reinterpret_cast<uint4*>(&ce.acc[0]) = make_uint4(0, 0, 0, 0);
-                        *reinterpret_cast<uint4*>(&ce.acc[4]) = make_uint4(0, 0, 0, 0);
-                        ce.hash = hh; ce.slot = my_slot;
-                        ce.ns_hi = (uint32_t)(v_ns >> 32); ce.end_hi = (uint32_t)(v_end >> 32);
-                        __threadfence_block();
-                        *reinterpret_cast<volatile uint32_t*>(&ce.state) = 2u;
-                        if (kProf) c_install++;
-                    }
-                }
-                if (kSketch) {
-                    const uint4 r0 = R[0], r1 = R[1];
-                    sketch_update(sk, key_premix(u64_of(r0.x, r0.y), u64_of(r0.z, r0.w), u64_of(r1.x, r1.y),
-                                                 u64_of(r1.z, r1.w), u64_of(r2.x, r2.y)), t_packets);
-                }
-                if (my_slot != kResSpill) {
-                    reduce_to_hot(t, my_slot, t_bytes, t_packets, t_ns, t_end, t_flags, floor_ns, seen);
-                } else {                                           // table physically full (FA_F_NO_FULL_CUT mis-sizing): counted
-                    my_spills++;                                   // in fa_stats.spills, like HASHMAP_FAIL_CREATE_FLOW (flows.c:285)
-                }
-            }
-            FA_PROF_MARK(5);                                       // totals + reductions
-        }
-#endif
         team_sync(team);                                           // S2: nobody reads the tile buffer any more
         FA_PROF_MARK(6);                                           // S2 wait
         if (tid == 0) {
-#if FA_K1_EARLY
             if (kSketch) {                                         // the sketch update reads the keys in the reduce step: re-arm here
                 const uint32_t nt = tile_idx + tile_stride;
                 if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, tc, recs, n, nt); }
             }
-#else
-            tc.nrep = 0; tc.next_chunk = 0;
-            const uint32_t nt = tile_idx + tile_stride;
-            if (nt < n_tiles) { fence_proxy_async(); issue_tile_load(s, tc, recs, n, nt); }
-#endif
         }
         FA_PROF_MARK(7);                                           // reductions
     }
