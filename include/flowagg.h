@@ -231,9 +231,7 @@ enum fa_mode {
                                LookupAndDeleteMap, merged with the feature folds when FA_F_ENABLE_RTT / FA_F_ENABLE_DNS are
                                set (a flow first seen through a feature sample gets its base from the first packet that
                                follows; such entries count towards max_entries, unlike in the reference where the
-                               feature maps are separate).  FA_F_ENABLE_SKETCH / FA_F_NO_FULL_CUT are refused.  EXPERIMENTAL in this
-                               build: fa_create refuses the mode unless FA_EXPERIMENTAL_KERNEL_MAP=1 is set in the
-                               environment (kernels checked against the oracle in a host emulation, not yet on a GPU) */
+                               feature maps are separate).  FA_F_ENABLE_SKETCH / FA_F_NO_FULL_CUT are refused. */
 };
 
 typedef struct fa_config {
@@ -290,6 +288,10 @@ typedef struct fa_stats {
     uint64_t filter_accept;       /* global counter FILTER_ACCEPT  (utils.h:196-197)                        */
     uint64_t filter_reject;       /* global counter FILTER_REJECT  (utils.h:192-194), packet skipped        */
     uint64_t filter_nomatch;      /* global counter FILTER_NOMATCH (utils.h:211)                            */
+    uint64_t dns_packets_ingested;/* DNS packets consumed by fa_ingest_dns_packets (K7)                     */
+    uint64_t dns_queries_pending; /* len(dns_flows): queries waiting for their response                     */
+    uint64_t dns_map_full;        /* queries that found dns_flows at max_entries (errno 249 = (u8)-E2BIG)   */
+    uint64_t dns_queries_purged;  /* deleted by fa_purge_stale_dns                                          */
 } fa_stats;
 
 typedef struct fa_engine fa_engine;
@@ -389,7 +391,25 @@ int fa_live_flows(fa_engine* e, size_t* n);
  * bpf/maps_definition.h:7-11; later ones are dropped and counted).  out: host or device, cap records. */
 int fa_read_spilled(fa_engine* e, void* out_records, size_t cap, size_t* n_out);
 
-/* Replaces: FlowFetcher.DeleteMapsStaleEntries (pkg/tracer/tracer.go:1229-1257). */
+/* K7 — DNS query -> response correlation on the device.  Replaces: track_dns_packet and its dns_flows map
+ * (bpf/dns_tracker.h:23-37,68-127; bpf/maps_definition.h:81-89, max_entries 1 << 20) together with the dns_metrics
+ * sample flow_monitor derives from it (bpf/flows.c:210-213,291-330), followed by the fold of fa_ingest_dns.
+ * pkts: n x 104 bytes (host or device) in stream order, laid out like fa_dns_record: id = the packet's flow id;
+ * dns.end_mono_time_ts = the packet's timestamp; dns.id / dns.flags = the DNS header's id / flags in host order
+ * (QR = 0x8000); dns.eth_protocol; dns.name = the raw QNAME bytes; start / latency / errno are ignored.
+ *   query:    inserted if absent.  Already there -> the packet's flow gets a sample with errno 239 ((u8)-EEXIST: the
+ *             reference hands bpf_map_update_elem's return value on as dns_errno) and id = flags = latency = 0;
+ *             map at max_entries -> the same with errno 249 ((u8)-E2BIG; WHICH queries of a batch meet the full map is
+ *             not order-exact on the device).
+ *   response: the reversed tuple is looked up: found -> latency = ts - query ts and the entry is deleted, else errno 2
+ *             (ENOENT); one sample {start = end = ts, id, flags, latency, eth_protocol, name, errno} unless id == 0 and
+ *             errno == 0.
+ * Needs FA_F_ENABLE_DNS.  Bit-exact against the sequential restatement for any interleaving of the packets of a key. */
+int fa_ingest_dns_packets(fa_engine* e, const void* dns_packets, size_t n);
+
+/* Replaces: FlowFetcher.DeleteMapsStaleEntries (pkg/tracer/tracer.go:1229-1257): deletes the queries of
+ * fa_ingest_dns_packets with time.Duration(mono_now_ns - ts) >= timeout_ns (a signed compare, as in Go).  Without a
+ * correlated packet stream (latency pre-computed by the caller, fa_ingest_dns) there is nothing to purge. */
 int fa_purge_stale_dns(fa_engine* e, uint64_t mono_now_ns, uint64_t timeout_ns);
 
 /* Count-min point queries for n 40-byte keys (new capability; no reference). */

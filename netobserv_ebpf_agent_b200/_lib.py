@@ -32,7 +32,8 @@ class Stats(C.Structure):
         "records_ingested", "dns_ingested", "additional_ingested", "flows_evicted", "evictions", "live_flows",
         "spills", "order_fixups", "full_cuts", "kernel_launches", "h2d_bytes", "d2h_bytes",
         "observed_intf_missed", "hashmap_fail_create", "ringbuf_spilled", "ringbuf_dropped", "pkt_drops_ingested",
-        "snaps_ingested", "snaps_discarded", "filter_accept", "filter_reject", "filter_nomatch")]
+        "snaps_ingested", "snaps_discarded", "filter_accept", "filter_reject", "filter_nomatch",
+        "dns_packets_ingested", "dns_queries_pending", "dns_map_full", "dns_queries_purged")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
@@ -74,6 +75,7 @@ SIGNATURES = {
     "fa_set_flow_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "fa_ingest_additional": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_ingest_dns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fa_ingest_dns_packets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_ingest_pkt_drops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_evict_ex": (C.c_int, [C.c_void_p, C.POINTER(EvictOut), C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_evict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -183,6 +183,15 @@ struct fa_engine {
     uint64_t pb_cap = 0;
     fa::PbIface* d_pb_ifaces = nullptr; uint32_t pb_ifaces_cap = 0;
 
+    // K7 (dnscorr.cu): the dns_flows map + per-chunk scratch, allocated by the first fa_ingest_dns_packets
+    fa::DnsCorr dnsc{};                       // tab == nullptr until then
+    fa::DnsEntry* dnsc_spare = nullptr;       // the other table of a rebuild
+    unsigned long long* h_dnsc_ctr = nullptr; // pinned mirror of dnsc.ctr
+    uint32_t* d_dnsc_state = nullptr; uint8_t* d_dnsc_samples = nullptr; uint8_t* d_dnsc_out = nullptr; uint32_t* d_dnsc_warps = nullptr;
+    uint64_t dnsc_chunk = 0;                  // packets per launch_dns_correlate
+    uint64_t dnsc_used = 0;                   // upper bound of the table entries in use (present + answered keys)
+    uint64_t dnsc_slots = 0;                  // 4 x max_entries: answered keys keep their entry until the next rebuild
+
     fa_stats st{};
 };
 
@@ -632,6 +641,8 @@ void fa_destroy(fa_engine* e) {
     cudaFree(e->d_evict_dns); cudaFree(e->d_evict_add); cudaFree(e->d_evict_present); cudaFree(e->d_slot_of_out); cudaFree(e->d_slot_of);
     cudaFree(e->d_evict_drop); cudaFree(e->d_evict_rttmin);
     cudaFree(e->sk.cms); cudaFree(e->sk.hll);
+    cudaFree(e->dnsc.tab); cudaFree(e->dnsc_spare); cudaFree(e->dnsc.ctr); cudaFreeHost(e->h_dnsc_ctr);
+    cudaFree(e->d_dnsc_state); cudaFree(e->d_dnsc_samples); cudaFree(e->d_dnsc_out); cudaFree(e->d_dnsc_warps);
     cudaFree(e->km_met); cudaFree(e->km_slot_of); cudaFree(e->km_bset); cudaFree(e->km_blist); cudaFree(e->km_spill);
     cudaFree(e->km_touched); cudaFree(e->km_deferred); cudaFree(e->km_brec);
     cudaFree(e->d_km_ctr); if (e->h_km_ctr) cudaFreeHost(e->h_km_ctr);
@@ -1115,9 +1126,116 @@ int fa_ipc_close(fa_engine* e, void* mapped) {
     return FA_OK;
 }
 
-int fa_purge_stale_dns(fa_engine* e, uint64_t, uint64_t) {
+// ---------------------------------------------------------------- K7: DNS query -> response correlation (dnscorr.cu)
+static constexpr uint64_t kDnsMaxEntries = 1ull << 20;        // dns_flows max_entries (bpf/maps_definition.h:84); FA_DNS_MAX_ENTRIES overrides (tests)
+
+static int dnsc_sync(fa_engine* e) {                          // device counters -> pinned mirror
+    CU(cudaMemcpyAsync(e->h_dnsc_ctr, e->dnsc.ctr, fa::DNSC_N * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->st.dns_queries_pending = e->h_dnsc_ctr[fa::DNSC_PRESENT];
+    e->st.dns_map_full = e->h_dnsc_ctr[fa::DNSC_FULL];
+    e->st.dns_queries_purged = e->h_dnsc_ctr[fa::DNSC_PURGED];
+    return FA_OK;
+}
+
+static int dnsc_init(fa_engine* e) {
+    if (e->dnsc.tab) return FA_OK;
+    e->dnsc_chunk = std::min<uint64_t>(e->max_batch, 1ull << 20);
+    uint64_t max_entries = kDnsMaxEntries;
+    if (const char* me = getenv("FA_DNS_MAX_ENTRIES")) max_entries = std::max<uint64_t>(1, strtoull(me, nullptr, 0));
+    uint64_t kDnsSlots = 64; while (kDnsSlots < 4 * max_entries) kDnsSlots <<= 1;
+    e->dnsc_slots = kDnsSlots;
+    fa::DnsEntry* tab = nullptr;
+    CU(cudaMalloc(&tab, kDnsSlots * sizeof(fa::DnsEntry)));
+    CU(cudaMemsetAsync(tab, 0, kDnsSlots * sizeof(fa::DnsEntry), e->stream));
+    CU(cudaMalloc(&e->dnsc.ctr, fa::DNSC_N * 8));
+    CU(cudaMemsetAsync(e->dnsc.ctr, 0, fa::DNSC_N * 8, e->stream));
+    CU(cudaHostAlloc(&e->h_dnsc_ctr, fa::DNSC_N * 8, cudaHostAllocDefault));
+    CU(cudaMalloc(&e->d_dnsc_state, e->dnsc_chunk * 4));
+    CU(cudaMalloc(&e->d_dnsc_samples, e->dnsc_chunk * fa::kDnsRecBytes));
+    CU(cudaMalloc(&e->d_dnsc_out, e->dnsc_chunk * fa::kDnsRecBytes));
+    CU(cudaMalloc(&e->d_dnsc_warps, (e->dnsc_chunk + 31) / 32 * 4));
+    e->dnsc.mask = kDnsSlots - 1; e->dnsc.max_entries = max_entries;
+    e->dnsc.tab = tab;
+    return FA_OK;
+}
+
+// move the pending queries into an empty table: the entries of answered queries are dropped
+static int dnsc_rebuild(fa_engine* e) {
+    if (!e->dnsc_spare) CU(cudaMalloc(&e->dnsc_spare, e->dnsc_slots * sizeof(fa::DnsEntry)));
+    CU(cudaMemsetAsync(e->dnsc_spare, 0, e->dnsc_slots * sizeof(fa::DnsEntry), e->stream));
+    CU(cudaMemsetAsync(&e->dnsc.ctr[fa::DNSC_CREATED], 0, 8, e->stream));
+    fa::DnsCorr to = e->dnsc;
+    to.tab = e->dnsc_spare;
+    e->st.kernel_launches += fa::launch_dns_rebuild(e->dnsc, to, e->sm_count, e->stream);
+    CU(cudaGetLastError());
+    std::swap(e->dnsc.tab, e->dnsc_spare);
+    if (int rc = dnsc_sync(e)) return rc;
+    e->dnsc_used = e->h_dnsc_ctr[fa::DNSC_CREATED];
+    return FA_OK;
+}
+
+int fa_ingest_dns_packets(fa_engine* e, const void* pkts, size_t n) {
+    const char* who = "fa_ingest_dns_packets";
+    if (!e) return fail(FA_E_INVAL, "%s: null engine", who);
+    if (!(e->cfg.flags & FA_F_ENABLE_DNS)) return fail(FA_E_INVAL, "%s: engine was created without FA_F_ENABLE_DNS", who);
+    if (n == 0) return FA_OK;
+    if (!pkts) return fail(FA_E_INVAL, "%s: null packets", who);
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(cudaSetDevice(e->device));
+    if (int rc = dnsc_init(e)) return rc;
+    const PtrKind k = classify(pkts);
+    if (k == PTR_DEVICE && (reinterpret_cast<uintptr_t>(pkts) & 7)) return fail(FA_E_INVAL, "%s: device packets must be 8-byte aligned", who);
+    int rc = sync_counters(e);
+    if (rc) return rc;
+    if (e->live_known + n > e->slots - e->slots / 8)          // every packet may add a sample for a new flow
+        return fail(FA_E_2BIG, "%s: %zu packets could overfill the flow table (%llu live of %llu slots): evict first", who, n,
+                    (unsigned long long)e->live_known, (unsigned long long)e->slots);
+    if (k != PTR_DEVICE) { if (int arc = stage_alloc(e, k == PTR_PAGEABLE)) return arc; }
+    size_t done = 0;
+    while (done < n) {
+        // a chunk never takes more than a quarter of the table: with at most max_entries = slots / 4 present keys after a
+        // rebuild the table stays at most half full, so a probe sequence cannot run out
+        const uint64_t cmax = std::min<uint64_t>(e->dnsc_chunk, e->dnsc_slots / 4);
+        const uint32_t c = (uint32_t)std::min<size_t>(n - done, k == PTR_DEVICE ? cmax : std::min<uint64_t>(cmax, stage_records(e)));
+        if (e->dnsc_used + c > e->dnsc_slots / 2) { if (int rrc = dnsc_rebuild(e)) return rrc; }
+        const uint8_t* src = static_cast<const uint8_t*>(pkts) + done * fa::kDnsRecBytes;
+        const uint8_t* d = src;
+        int sidx = -1;
+        if (k != PTR_DEVICE) {
+            if (int src_rc = stage_copy(e, src, (size_t)c * fa::kDnsRecBytes, k == PTR_PINNED, &sidx)) return src_rc;
+            d = e->d_stage[sidx];
+        }
+        e->st.kernel_launches += fa::launch_dns_correlate(d, c, e->dnsc, e->d_dnsc_state, e->d_dnsc_samples, e->d_dnsc_warps, e->d_dnsc_out,
+                                                          e->sm_count, e->stream);
+        CU(cudaGetLastError());
+        if (sidx >= 0) { if (int rel_rc = stage_release(e, sidx)) return rel_rc; }
+        if (int src2 = dnsc_sync(e)) return src2;             // how many samples the chunk produced (sizes the fold)
+        e->dnsc_used += c;
+        const uint32_t m = (uint32_t)e->h_dnsc_ctr[fa::DNSC_EMITTED];
+        if (m) {
+            e->st.kernel_launches += fa::launch_feature_fold(1, e->d_dnsc_out, m, e->table, ++e->epoch, e->feat_seq[1], e->d_slot_of,
+                                                             e->d_ctr, e->sm_count, e->stream);
+            CU(cudaGetLastError());
+            e->feat_seq[1] += m;
+            e->unsynced_records += m;
+            e->st.dns_ingested += m;
+        }
+        e->st.dns_packets_ingested += c;
+        done += c;
+    }
+    if (k != PTR_DEVICE) CU(cudaStreamSynchronize(e->copy_stream));
+    return FA_OK;
+}
+
+int fa_purge_stale_dns(fa_engine* e, uint64_t mono_now_ns, uint64_t timeout_ns) {
     if (!e) return fail(FA_E_INVAL, "fa_purge_stale_dns: null engine");
-    return FA_OK;   // pre-computed-latency DNS contract (SURVEY.md §8 a12'): no query table to purge
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->dnsc.tab) return FA_OK;   // no packet stream was correlated (pre-computed-latency contract, SURVEY.md §8 a12'): nothing to purge
+    CU(cudaSetDevice(e->device));
+    e->st.kernel_launches += fa::launch_dns_purge(e->dnsc, mono_now_ns, timeout_ns, e->sm_count, e->stream);
+    CU(cudaGetLastError());
+    return dnsc_sync(e);
 }
 
 int fa_cms_query(fa_engine* e, const void* keys, size_t n, uint64_t* est) {

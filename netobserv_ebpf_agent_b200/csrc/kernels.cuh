@@ -103,6 +103,24 @@ int launch_parse_snaps(const uint8_t* snaps, uint32_t n, uint32_t stride, const 
                        uint4* out_recs, uint32_t* src_of, unsigned long long* n_out, unsigned long long* filter_ctr, int sm_count,
                        cudaStream_t st);
 
+// K7 DNS query -> response correlation (dnscorr.cu): the dns_flows map of bpf/maps_definition.h:81-89 on the device
+struct __align__(64) DnsEntry {                    // one key of dns_flows, 64 B
+    unsigned long long key[5];                     // dns_flow_id: src_ip | dst_ip | src_port, dst_port << 16, id << 32, protocol << 48
+    unsigned long long ts;                         // the map's value while `present`
+    uint32_t tag;                                  // 0 empty, 1 being written, 2 published
+    uint32_t present;                              // the map holds the key (a deleted key keeps its entry until the next rebuild)
+    uint32_t next[2];                              // per batch: smallest unprocessed packet index of the key, by round parity
+};
+enum { DNSC_REMAINING = 0, DNSC_CREATED, DNSC_EMITTED, DNSC_PRESENT, DNSC_FULL, DNSC_PURGED, DNSC_N = 8 };
+struct DnsCorr { DnsEntry* tab; uint64_t mask; unsigned long long* ctr; unsigned long long max_entries; };
+constexpr int kDnsRounds = 6;                      // round kernels per batch (later ones exit at once); the tail takes the rest
+// pkts: n x 104 B in stream order; state: n u32; samples: n x 104 B scratch; warp_count: ceil(n / 32) u32; out: n x 104 B,
+// receives ctr[DNSC_EMITTED] samples in stream order
+int launch_dns_correlate(const uint8_t* pkts, uint32_t n, const DnsCorr& d, uint32_t* state, uint8_t* samples, uint32_t* warp_count,
+                         uint8_t* out, int sm_count, cudaStream_t st);
+int launch_dns_purge(const DnsCorr& d, uint64_t now, uint64_t timeout, int sm_count, cudaStream_t st);
+int launch_dns_rebuild(const DnsCorr& from, const DnsCorr& to, int sm_count, cudaStream_t st);
+
 // generator
 struct GenDeviceParams;
 int launch_generate(const GenDeviceParams& g, uint64_t first_index, uint32_t n, uint4* dst, cudaStream_t st);

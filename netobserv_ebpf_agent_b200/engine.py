@@ -108,6 +108,16 @@ class FlowAggEngine:
         nb = _nbytes(recs)
         check(lib().fa_ingest_dns(self._h, _ptr(recs), nb // 104))
 
+    def ingest_dns_packets(self, pkts):
+        """K7: raw DNS packets (104 bytes each: flow id + timestamp, DNS id / flags, QNAME) in stream order; queries and
+        responses are correlated on the device (bpf/dns_tracker.h:68-127) and the resulting samples folded like ingest_dns."""
+        nb = _nbytes(pkts)
+        check(lib().fa_ingest_dns_packets(self._h, _ptr(pkts), nb // 104))
+
+    def purge_stale_dns(self, mono_now_ns, timeout_ns):
+        """DeleteMapsStaleEntries (pkg/tracer/tracer.go:1229-1257) for the queries of ingest_dns_packets."""
+        check(lib().fa_purge_stale_dns(self._h, mono_now_ns, timeout_ns))
+
     def ingest_additional(self, recs):
         nb = _nbytes(recs)
         check(lib().fa_ingest_additional(self._h, _ptr(recs), nb // 72))

@@ -878,3 +878,98 @@ size_t oracle_parse_snaps_filtered(const uint8_t* snaps, size_t n, uint32_t stri
     }
     return m;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K7: DNS query -> response correlation (bpf/dns_tracker.h:23-37,68-127 + bpf/flows.c:210-213,291-330), sequential.
+ * dns_flow_id (bpf/types.h:250-257) restated as a 40-byte image: src_ip 16 | dst_ip 16 | src_port 2 | dst_port 2 | id 2 |
+ * protocol 1 | 0.  A chained hash map with exact byte compare stands in for the BPF hash map.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct dnsc_node { struct dnsc_node* next; uint8_t key[40]; uint64_t ts; } dnsc_node;
+struct oracle_dnscorr { dnsc_node** bucket; size_t n_buckets, len, max_entries; };
+
+oracle_dnscorr* oracle_dnscorr_new(size_t max_entries) {
+    oracle_dnscorr* m = (oracle_dnscorr*)calloc(1, sizeof *m);
+    m->n_buckets = 1; while (m->n_buckets < 2 * max_entries + 16) m->n_buckets <<= 1;
+    m->bucket = (dnsc_node**)calloc(m->n_buckets, sizeof *m->bucket);
+    m->max_entries = max_entries;
+    return m;
+}
+void oracle_dnscorr_free(oracle_dnscorr* m) {
+    if (!m) return;
+    for (size_t b = 0; b < m->n_buckets; b++) for (dnsc_node* x = m->bucket[b]; x;) { dnsc_node* nx = x->next; free(x); x = nx; }
+    free(m->bucket); free(m);
+}
+size_t oracle_dnscorr_pending(const oracle_dnscorr* m) { return m->len; }
+
+static size_t dnsc_bucket(const oracle_dnscorr* m, const uint8_t* key) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    for (int i = 0; i < 40; i++) { h ^= key[i]; h *= 0x100000001B3ull; }
+    return (size_t)(h ^ (h >> 29)) & (m->n_buckets - 1);
+}
+/* fill_dns_id (dns_tracker.h:23-37) */
+static void dnsc_key(const uint8_t* pkt, uint16_t dns_id, int reverse, uint8_t key[40]) {
+    memset(key, 0, 40);
+    memcpy(key, pkt + (reverse ? 16 : 0), 16);            /* src_ip */
+    memcpy(key + 16, pkt + (reverse ? 0 : 16), 16);       /* dst_ip */
+    memcpy(key + 32, pkt + (reverse ? 34 : 32), 2);       /* src_port */
+    memcpy(key + 34, pkt + (reverse ? 32 : 34), 2);       /* dst_port */
+    memcpy(key + 36, &dns_id, 2);
+    key[38] = pkt[36];                                    /* transport_protocol */
+}
+
+size_t oracle_dnscorr_packets(oracle_dnscorr* m, const uint8_t* pkts, size_t n, uint8_t* out) {
+    size_t n_out = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t* P = pkts + i * OR_DNSREC_SIZE;
+        uint64_t ts; uint16_t id, flags;
+        memcpy(&ts, P + 48, 8); memcpy(&id, P + 64, 2); memcpy(&flags, P + 66, 2);
+        uint8_t key[40];
+        int dns_errno = 0;                                /* what track_dns_packet returns (flows.c:212) */
+        uint16_t pkt_dns_id = 0, pkt_dns_flags = 0; uint64_t pkt_latency = 0; int has_name = 0;
+        if ((flags & 0x8000u) == 0) {                     /* query: BPF_NOEXIST insert (dns_tracker.h:92-100) */
+            dnsc_key(P, id, 0, key);
+            const size_t b = dnsc_bucket(m, key);
+            dnsc_node* x = m->bucket[b];
+            while (x && memcmp(x->key, key, 40)) x = x->next;
+            if (x) dns_errno = -17;                       /* -EEXIST */
+            else if (m->len >= m->max_entries) dns_errno = -7;   /* -E2BIG: the map is full */
+            else {
+                x = (dnsc_node*)malloc(sizeof *x);
+                memcpy(x->key, key, 40); x->ts = ts; x->next = m->bucket[b]; m->bucket[b] = x; m->len++;
+            }
+        } else {                                          /* response: lookup of the reversed tuple + delete (:101-110) */
+            dnsc_key(P, id, 1, key);
+            const size_t b = dnsc_bucket(m, key);
+            dnsc_node** px = &m->bucket[b];
+            while (*px && memcmp((*px)->key, key, 40)) px = &(*px)->next;
+            if (*px) { dnsc_node* x = *px; pkt_latency = ts - x->ts; *px = x->next; free(x); m->len--; }
+            else dns_errno = 2;                           /* ENOENT */
+            pkt_dns_id = id; pkt_dns_flags = flags; has_name = 1;
+        }
+        if (pkt_dns_id != 0 || dns_errno != 0) {          /* flows.c:291: one dns_metrics sample for the packet's flow */
+            uint8_t* S = out + n_out * OR_DNSREC_SIZE;
+            memset(S, 0, OR_DNSREC_SIZE);
+            memcpy(S, P, OR_ID_SIZE);
+            memcpy(S + 40, &ts, 8); memcpy(S + 48, &ts, 8);              /* start = end = pkt.current_ts */
+            memcpy(S + 56, &pkt_latency, 8);
+            memcpy(S + 64, &pkt_dns_id, 2); memcpy(S + 66, &pkt_dns_flags, 2);
+            memcpy(S + 68, P + 68, 2);                                   /* eth_protocol */
+            S[70] = (uint8_t)dns_errno;                                  /* u8 field: -17 -> 239, -7 -> 249 */
+            if (has_name) memcpy(S + 71, P + 71, 32);
+            n_out++;
+        }
+    }
+    return n_out;
+}
+
+size_t oracle_dnscorr_purge(oracle_dnscorr* m, uint64_t now, uint64_t timeout) {
+    size_t gone = 0;
+    for (size_t b = 0; b < m->n_buckets; b++) {
+        dnsc_node** px = &m->bucket[b];
+        while (*px) {
+            if ((int64_t)(now - (*px)->ts) >= (int64_t)timeout) { dnsc_node* x = *px; *px = x->next; free(x); m->len--; gone++; }
+            else px = &(*px)->next;
+        }
+    }
+    return gone;
+}

@@ -162,6 +162,27 @@ size_t oracle_parse_snaps_filtered(const uint8_t* snaps, size_t n, uint32_t stri
                                    const uint8_t* peers, size_t n_peers, uint8_t* out_recs, uint32_t* src_of,
                                    uint64_t counters[3]);
 
+/* --- K7: DNS query -> response correlation, the dns_flows map of bpf/dns_tracker.h:23-37,68-127 together with what
+ * flow_monitor does with the result (bpf/flows.c:210-213,291-330: a per-flow dns_metrics sample when pkt.dns_id != 0 or
+ * dns_errno != 0).  Input: n 104-byte DNS packets in stream order = flow_id (40 B) + dns_metrics layout (64 B) with
+ * end_mono_time_ts = the packet's timestamp, id / flags = the DNS header fields in host order (QR = 0x8000),
+ * eth_protocol, name; latency / errno / start are ignored.  Per packet, sequentially:
+ *   query    (QR = 0): bpf_map_update_elem(dns_flows, {src, dst, ports, id, proto}, ts, BPF_NOEXIST); the return value is the
+ *                      packet's dns_errno (track_dns_packet returns `ret`): 0, or -EEXIST / -E2BIG truncated to the u8 errno
+ *                      field (239 / 249) -> a sample with id = flags = latency = 0 and no name (pkt.dns_id stays 0)
+ *   response (QR = 1): lookup of the REVERSED tuple: found -> latency = ts - value, entry deleted; else dns_errno = ENOENT (2);
+ *                      sample {start = end = ts, id, flags, latency, eth_protocol, name, errno} unless id == 0 and errno == 0
+ * out_samples (n x 104 B at most) receives the samples in stream order, ready for AccumulateDNS; returns their number.
+ * max_entries = the map's capacity (reference: 1 << 20).  SOURCE-PINNED ONLY: the reference has no unit test for it. */
+typedef struct oracle_dnscorr oracle_dnscorr;
+oracle_dnscorr* oracle_dnscorr_new(size_t max_entries);
+void   oracle_dnscorr_free(oracle_dnscorr* m);
+size_t oracle_dnscorr_packets(oracle_dnscorr* m, const uint8_t* pkts, size_t n, uint8_t* out_samples);
+size_t oracle_dnscorr_pending(const oracle_dnscorr* m);
+/* FlowFetcher.lookupAndDeleteDNSMap (pkg/tracer/tracer.go:1235-1257): delete every query with
+ * time.Duration(now - ts) >= timeout (signed 64-bit compare); returns the number deleted */
+size_t oracle_dnscorr_purge(oracle_dnscorr* m, uint64_t mono_now_ns, uint64_t timeout_ns);
+
 /* --- hashes + sketches (this repo's spec; PARITY UNPINNED, see header comment) */
 uint64_t oracle_key_premix(const uint8_t* key40);
 uint64_t oracle_slot_hash(const uint8_t* key40);

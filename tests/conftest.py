@@ -34,7 +34,7 @@ def _load_engine_emulation():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from emul_build import EMUL, build, csrc
     so = build("engine_emul", csrc("engine.cu", "aggregate.cu", "evict.cu", "features.cu", "kmap.cu", "kmap_body.cuh",
-                                   "misc_kernels.cu", "pbflow.cu", "common.cuh", "kernels.cuh", "flowgen.h") +
+                                   "misc_kernels.cu", "pbflow.cu", "snaps.cu", "dnscorr.cu", "common.cuh", "kernels.cuh", "flowgen.h") +
                [os.path.join(EMUL, "simt.h"), os.path.join(ROOT, "include", "flowagg.h")])
     lib = ctypes.CDLL(so)
     for name, (res, args) in L.SIGNATURES.items():

@@ -26,6 +26,7 @@
 #include "../../netobserv_ebpf_agent_b200/csrc/misc_kernels.cu"
 #include "../../netobserv_ebpf_agent_b200/csrc/pbflow.cu"
 #include "../../netobserv_ebpf_agent_b200/csrc/snaps.cu"
+#include "../../netobserv_ebpf_agent_b200/csrc/dnscorr.cu"
 
 // ------------------------------------------------------------------------------------------------ CUDA runtime double
 namespace {
@@ -187,6 +188,31 @@ int launch_evict_features(const Table& table, const uint32_t* slot_of_out, unsig
     return 1;
 }
 
+int launch_dns_correlate(const uint8_t* pkts, uint32_t n, const DnsCorr& dc, uint32_t* state, uint8_t* samples, uint32_t* warp_count,
+                         uint8_t* out, int, cudaStream_t) {
+    if (!n) return 0;
+    const DnsCorr d = dc;
+    // FA_EMUL_DNS_ROUNDS=0: no round kernels, so that the single-thread tail is exercised as well
+    const char* rs = getenv("FA_EMUL_DNS_ROUNDS");
+    const uint32_t rounds = rs ? (uint32_t)atoi(rs) : (uint32_t)kDnsRounds;
+    simt::launch(2, 256, 0, [=] { dns_resolve_kernel(pkts, n, d, state, samples); });
+    for (uint32_t r = 0; r < rounds; r++) simt::launch(2, 256, 0, [=] { dns_round_kernel(pkts, n, d, state, samples, r & 1u); });
+    simt::launch(1, 32, 0, [=] { dns_tail_kernel(pkts, n, d, state, samples); });
+    simt::launch(2, 256, 0, [=] { dns_count_kernel(state, n, warp_count); });
+    simt::launch(1, 32, 0, [=] { dns_scan_kernel(warp_count, (n + 31) / 32, d.ctr); });
+    simt::launch(2, 256, 0, [=] { dns_scatter_kernel(state, n, warp_count, samples, out); });
+    return 5 + (int)rounds;
+}
+int launch_dns_purge(const DnsCorr& dc, uint64_t now, uint64_t timeout, int, cudaStream_t) {
+    const DnsCorr d = dc;
+    simt::launch(2, 256, 0, [=] { dns_purge_kernel(d, now, timeout); });
+    return 1;
+}
+int launch_dns_rebuild(const DnsCorr& from, const DnsCorr& to, int, cudaStream_t) {
+    const DnsCorr f = from, t = to;
+    simt::launch(2, 256, 0, [=] { dns_rebuild_kernel(f, t); });
+    return 1;
+}
 int launch_expand_events(const uint4* events, uint32_t n, uint4* recs_out, cudaStream_t) {
     if (!n) return 0;
     simt::launch(2, 256, 0, [=] { expand_events_kernel(events, n, recs_out); });

@@ -96,6 +96,11 @@ def lib():
         "oracle_parse_snaps": (sz, [_u8p, sz, u32, _u8p, C.POINTER(u32)]),
         "oracle_filter_packet": (C.c_int, [_u8p, sz, _u8p, sz, _u8p, C.POINTER(u64)]),
         "oracle_parse_snaps_filtered": (sz, [_u8p, sz, u32, _u8p, sz, _u8p, sz, _u8p, C.POINTER(u32), C.POINTER(u64)]),
+        "oracle_dnscorr_new": (vp, [sz]),
+        "oracle_dnscorr_free": (None, [vp]),
+        "oracle_dnscorr_packets": (sz, [vp, _u8p, sz, _u8p]),
+        "oracle_dnscorr_pending": (sz, [vp]),
+        "oracle_dnscorr_purge": (sz, [vp, u64, u64]),
         "oracle_cms_update": (None, [C.POINTER(u64), u32, u32, u64, _u8p, sz]),
         "oracle_cms_query": (None, [C.POINTER(u64), u32, u32, u64, _u8p, sz, C.POINTER(u64)]),
         "oracle_hll_update": (None, [_u8p, u32, u64, _u8p, sz]),
@@ -389,3 +394,28 @@ def parse_snaps_filtered(snaps, stride, rules, peers):
     m = lib().oracle_parse_snaps_filtered(_p(b), n, stride, _p(rb), len(rules), _p(pb), 0 if peers is None else len(peers), _p(out),
                                           src.ctypes.data_as(C.POINTER(C.c_uint32)), ctr.ctypes.data_as(C.POINTER(C.c_uint64)))
     return out[:m].copy(), src[:m].copy(), ctr
+
+
+class DnsCorrelator:
+    """dns_flows + the sample flow_monitor emits per DNS packet (bpf/dns_tracker.h:68-127, bpf/flows.c:291-330), sequential."""
+
+    def __init__(self, max_entries=1 << 20):
+        self.h = lib().oracle_dnscorr_new(max_entries)
+
+    def packets(self, pkts):
+        a = np.ascontiguousarray(as_bytes(pkts))
+        n = a.size // DNSREC
+        out = np.zeros(max(n, 1) * DNSREC, dtype=np.uint8)
+        k = lib().oracle_dnscorr_packets(self.h, _p(a), n, _p(out))
+        return out[: k * DNSREC].reshape(-1, DNSREC)
+
+    def pending(self):
+        return lib().oracle_dnscorr_pending(self.h)
+
+    def purge(self, now, timeout):
+        return lib().oracle_dnscorr_purge(self.h, now, timeout)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_dnscorr_free(self.h)
+            self.h = None
