@@ -191,6 +191,46 @@ def snaps_bench(B=1 << 22, n_frames=1 << 16, steps=6):
         eng.close()
 
 
+def dnscorr_bench(n_clients=200_000, B=1 << 20, steps=6):
+    """K7: query / response pairs of n_clients x 4 ids, responses shuffled a few hundred packets behind their queries."""
+    import oracle_lib as O
+    rng = np.random.default_rng(9)
+    eng = fa.FlowAggEngine(1 << 22, flags=fa.FA_F_ENABLE_DNS, max_batch=B, cuda_stream=stream.cuda_stream)
+    batches = []
+    for b in range(2):
+        half = B // 2
+        r = np.zeros(B, dtype=O.DNSREC_DTYPE)
+        c = rng.integers(0, n_clients, half); i = rng.integers(1, 5, half)
+        pos_q = np.sort(rng.choice(B, half, replace=False))                       # queries keep their order ...
+        rest = np.setdiff1d(np.arange(B), pos_q)                                   # ... their responses fill the other positions
+        ident = np.zeros((B, 40), dtype=np.uint8)
+        def tuple_of(cl, reverse):
+            t = np.zeros((len(cl), 40), dtype=np.uint8)
+            a = np.zeros((len(cl), 16), dtype=np.uint8); a[:, 10:12] = 0xFF; a[:, 12] = 10; a[:, 13:16] = np.stack([(cl >> 16) & 255, (cl >> 8) & 255, cl & 255], 1)
+            srv = np.zeros((len(cl), 16), dtype=np.uint8); srv[:, 10:12] = 0xFF; srv[:, 12:16] = [10, 255, 0, 53]
+            port = (20000 + (cl % 40000)).astype("<u2").view(np.uint8).reshape(-1, 2)
+            p53 = np.tile(np.frombuffer(np.uint16(53).tobytes(), dtype=np.uint8), (len(cl), 1))
+            t[:, 0:16], t[:, 16:32] = (srv, a) if reverse else (a, srv)
+            t[:, 32:34], t[:, 34:36] = (p53, port) if reverse else (port, p53)
+            t[:, 36] = 17
+            return t
+        ident[pos_q] = tuple_of(c, False); ident[rest] = tuple_of(c, True)
+        r["id"] = ident
+        d = r["dns"]
+        d["end"] = 1_000_000 + b * B + np.arange(B)
+        d["id"][pos_q] = i; d["id"][rest] = i
+        d["flags"][pos_q] = 0x0100; d["flags"][rest] = 0x8180
+        d["eth"] = 0x0800
+        r["dns"] = d
+        batches.append(torch.from_numpy(O.as_bytes(r).copy()).to(dev))
+    eng.ingest_dns_packets(batches[0])
+    dt = timed(lambda k: eng.ingest_dns_packets(batches[k % 2]), steps)
+    st = eng.stats()
+    print(json.dumps({"bench": "K7 DNS query/response correlation + DNS fold", "Mpkts_s": B * steps / dt / 1e6,
+                      "samples": st["dns_ingested"], "pending": st["dns_queries_pending"]}), flush=True)
+    eng.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sketch", "features", "kmap"]
     if "sketch" in which:
@@ -206,3 +246,5 @@ if __name__ == "__main__":
         pb_bench()
     if "snaps" in which:
         snaps_bench()
+    if "dnscorr" in which:
+        dnscorr_bench()
