@@ -1,18 +1,16 @@
 """K7 (fa_ingest_dns_packets) on the device, against the sequential restatement — the same cases as tests/test_dns_correlate.py
 at larger sizes, through libflowagg.so.
 
-The kernels of csrc/dnscorr.cu were written after the round's GPU minutes had run out: they are checked bit for bit under the
-host emulation (tests/test_dns_correlate.py), but these tests have NOT run on a B200 yet.  They are therefore marked
-xfail(strict=False): a first hardware run reports XPASS (or XFAIL with the reason) without turning the suite red, and the file
-sorts last so that nothing else depends on it.  Remove the marker after the first green run."""
+The kernels of csrc/dnscorr.cu were written after the round's GPU budget had been spent on K1; their first (and so far only)
+hardware run used the round's last 48 GPU seconds: 4 passed (profiles/r2_k7_gpu_first_run.log).  The file sorts last and carries
+a thread-method timeout so that a wedged kernel here could not hold or poison the rest of the GPU suite."""
 import numpy as np
 import pytest
 
 import oracle_lib as O
 from test_dns_correlate import dns_stream, query, response, run_case
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of K7 (emulation-checked only)"),
-              pytest.mark.timeout(240, method="thread")]      # a wedged kernel must not hold the suite: this file runs last
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(240, method="thread")]
 
 
 def test_hand_cases_on_the_device():
