@@ -46,57 +46,15 @@ constexpr int kDropState = 6;
 
 __device__ __forceinline__ uint64_t ld_u64_unaligned8(const uint8_t* p) { return *reinterpret_cast<const uint64_t*>(p); }
 
-// Find the flow's slot, creating a feature-only entry when the key is new.  One thread per sample.
-__device__ uint32_t find_or_create(const Table& t, uint64_t epoch, const uint64_t k[5], unsigned long long* n_created) {
-    const uint64_t kk4 = k[4] & 0x00FFFFFFFFFFFFFFull;
-    const uint64_t h = slot_hash(key_premix(k[0], k[1], k[2], k[3], k[4]));
-    uint64_t slot = h & t.mask;
-    for (uint32_t probes = 0; probes < 65536; ) {
-        unsigned long long* L = reinterpret_cast<unsigned long long*>(&t.ident[slot * 8]);
-        unsigned long long* tagp = L + 5;
-        unsigned long long tag = ld_cg_u64(tagp);
-        const uint32_t state = (uint32_t)(tag & TAG_STATE_MASK);
-        if (state == 0) {
-            if (atomicCAS(tagp, 0ull, TAG_CLAIMED) == 0ull) {
-                // key, then an all-zero descriptor (the base is empty until a base record arrives)
-                L[0] = k[0]; L[1] = k[1]; L[2] = k[2]; L[3] = k[3]; L[4] = kk4;
-#pragma unroll
-                for (int c = 6; c < 16; c++) L[c] = 0ull;
-                __threadfence();
-                *reinterpret_cast<volatile unsigned long long*>(tagp) = TAG_PUBLISHED;   // no TAG_HAS_BASE, epoch 0
-                red_or_u32(&t.occ[slot >> 5], 1u << (slot & 31));
-                atomicAdd(n_created, 1ull);
-                return (uint32_t)slot;
-            }
-            continue;                                   // lost the race: look at the slot again
-        }
-        if (state == (uint32_t)TAG_CLAIMED) continue;   // being published by someone else
-        __threadfence();                                // order the key reads after the tag observation
-        {
-            // the five key words in three independent loads: one round trip, no short-circuit chain of dependent loads
-            const uint4 c0 = ld_cg_u4(&t.ident[slot * 8]), c1 = ld_cg_u4(&t.ident[slot * 8 + 1]);
-            const unsigned long long w4 = ld_cg_u64(L + 4);
-            const bool same = (u64_of(c0.x, c0.y) == k[0]) & (u64_of(c0.z, c0.w) == k[1]) & (u64_of(c1.x, c1.y) == k[2]) &
-                              (u64_of(c1.z, c1.w) == k[3]) & ((w4 & 0x00FFFFFFFFFFFFFFull) == kk4);
-            if (same) return (uint32_t)slot;
-        }
-        slot = (slot + 1) & t.mask;
-        probes++;
-    }
-    return 0xFFFFFFFFu;
-}
-
-#ifndef FA_K6_V2
-#define FA_K6_V2 1      // one-round-trip probe, candidate-only second pass, one barrier less per tile: +9 % DNS / +8 % RTT (profiles/r2_ab_k6_v2.log)
-#endif
 #ifndef FA_K6_MINBLOCKS
 #define FA_K6_MINBLOCKS 4   // 64 registers: four CTAs per SM (5 -> 48 registers with spills: -3 %, 6: -10 %)
 #endif
 
-// v2 probe: the three key chunks and the tag travel in ONE round trip (the tag shares a 16-byte chunk with the key tail).
+// Find the flow's slot, creating a feature-only entry when the key is new.  One thread per representative sample.
+// The three key chunks and the tag travel in ONE round trip (the tag shares a 16-byte chunk with the key tail).
 // Only a slot published during THIS launch (its tag carries the launch epoch) can have been read before its key was
 // visible: then, and only then, fence and read the line again.  Entries of earlier launches are complete.
-__device__ uint32_t find_or_create2(const Table& t, uint64_t epoch, const uint64_t k[5], unsigned long long* n_created) {
+__device__ uint32_t find_or_create(const Table& t, uint64_t epoch, const uint64_t k[5], unsigned long long* n_created) {
     const uint64_t kk4 = k[4] & 0x00FFFFFFFFFFFFFFull;
     const uint64_t h = slot_hash(key_premix(k[0], k[1], k[2], k[3], k[4]));
     uint64_t slot = h & t.mask;
@@ -149,18 +107,10 @@ constexpr int kFeatTile = 256;          // samples per tile == threads per CTA
 constexpr int kFeatRep = 512;           // tile-local election set
 constexpr uint32_t kFeatNone = 0xFFFFFFFFu;
 
-#if FA_K6_V2
 // 64-bit shared-memory max / or are compare-and-swap loops: look first, most samples of a hot flow cannot change the value
 __device__ __forceinline__ void smem_max_u64(uint64_t* p, uint64_t v) { if (v > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
-#else
-__device__ __forceinline__ void smem_max_u64(uint64_t* p, uint64_t v) { if (v) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
-#endif
 __device__ __forceinline__ void smem_add_u64(uint64_t* p, uint64_t v) { if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
-#if FA_K6_V2
 __device__ __forceinline__ void smem_or_u64(uint64_t* p, uint64_t v) { if (v & ~*reinterpret_cast<volatile uint64_t*>(p)) atomicOr(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
-#else
-__device__ __forceinline__ void smem_or_u64(uint64_t* p, uint64_t v) { if (v) atomicOr(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
-#endif
 __device__ __forceinline__ void gmax(uint8_t* p, uint64_t v) { if (v) red_max_u64(p, v); }
 __device__ __forceinline__ void gadd(uint8_t* p, uint64_t v) { if (v) red_add_u64(p, v); }
 __device__ __forceinline__ void gor32(uint8_t* p, uint64_t v) { if (v) red_or_u32(p, (uint32_t)v); }
@@ -262,7 +212,7 @@ template <class F> struct FeatHot {
 };
 
 template <class F> constexpr size_t feature_fold_smem() {
-    // tile (re-used for the representatives' accumulators once the keys are no longer needed) | election set | slots |
+    // tile (re-used for the representatives' accumulators once the keys are no longer needed) | election set | 1 KB spare |
     // duplicate counts | hot-flow cache
     constexpr size_t tile = (size_t)kFeatTile * (F::kRec > F::kAcc * 8 ? F::kRec : F::kAcc * 8);
     return tile + kFeatRep * 4 + kFeatTile * 4 + kFeatTile * 4 + kFeatHot * sizeof(FeatHot<F>);
@@ -277,8 +227,8 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
     uint64_t* tile = reinterpret_cast<uint64_t*>(sm);                         // kFeatTile samples ...
     uint64_t* acc = tile;                                                     // ... then [kAcc][kFeatTile] accumulators
     uint32_t* rep = reinterpret_cast<uint32_t*>(sm + kTileBytes);             // [kFeatRep] election set
-    uint32_t* slot_s = rep + kFeatRep;                                        // [kFeatTile] slot found by each representative
-    uint32_t* dupc = slot_s + kFeatTile;                                      // [kFeatTile] duplicates folded into it
+    uint32_t* dupc = rep + kFeatRep + kFeatTile;                              // (1 KB kept free after the election set: the measured layout)
+                                                                              //                                      // [kFeatTile] duplicates folded into it
     FeatHot<F>* hot = reinterpret_cast<FeatHot<F>*>(dupc + kFeatTile);
     const uint32_t tid = threadIdx.x;
     if (tid < kFeatHot) hot[tid].state = 0u;
@@ -286,7 +236,6 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
     for (uint32_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
         const uint32_t first = tix * kFeatTile, cnt = min((uint32_t)kFeatTile, n - first);
         const uint64_t* G = reinterpret_cast<const uint64_t*>(recs + (size_t)first * F::kRec);
-#if FA_K6_V2
         {   // the CTA's next tile: ask L2 for it now, one 128-byte line per thread
             const uint32_t ntx = tix + gridDim.x;
             if (ntx < n_tiles) {
@@ -295,7 +244,6 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
                 if (tid * 128u < nbytes) prefetch_l2(nb + tid * 128u);
             }
         }
-#endif
         if (cnt == (uint32_t)kFeatTile) {                                    // all loads in flight before the first store
             uint64_t tmp[F::kRec / 8];
 #pragma unroll
@@ -306,13 +254,11 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
             for (uint32_t w = tid; w < cnt * (F::kRec / 8); w += kFeatTile) tile[w] = G[w];
         }
         for (uint32_t w = tid; w < kFeatRep; w += kFeatTile) rep[w] = kFeatNone;
-#if FA_K6_V2
         if (tid < cnt) slot_of[first + tid] = kFeatNone;                      // only a flow's candidates for "first" / "last" get a slot below
-#endif
         __syncthreads();
         const bool valid = tid < cnt;
         const uint8_t* R = reinterpret_cast<const uint8_t*>(tile) + (size_t)tid * F::kRec;
-        uint32_t r = tid, my_slot = kFeatNone, hq = 0;                        // my representative; cached flows: the entry's slot
+        uint32_t r = tid, hq = 0;                                             // my representative (kFeatCached: a hot-flow cache entry)
         uint64_t k[5] = {0, 0, 0, 0, 0}, v[F::kAcc];
         if (valid) {
             load_key(R, k);
@@ -323,7 +269,6 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
             FeatHot<F>& e = hot[hq];
             if (e.state == 2u && e.key[0] == k[0] && e.key[1] == k[1] && e.key[2] == k[2] && e.key[3] == k[3] && e.key[4] == k[4]) {
                 r = kFeatCached;                                              // hot flow: no election, no probe, no global reduction
-                my_slot = e.slot;
             } else {
                 uint32_t q = (uint32_t)(h >> 40) & (kFeatRep - 1);
                 for (int step = 0; step < 8; step++) {
@@ -346,8 +291,7 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
         if (valid && r < (uint32_t)kFeatTile && r != tid) { F::fold(acc + r, kFeatTile, v); atomicAdd(&dupc[r], 1u); }
         __syncthreads();
         if (valid && r == tid) {
-#if FA_K6_V2
-            const uint32_t slot = find_or_create2(t, epoch, k, &ctr->live);
+            const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
             if (slot == kFeatNone) atomicAdd(&ctr->spills, 1ull + dupc[tid]);
             else {
                 // the tile's earliest sample of the flow (and, for drops, its last one with a cause) are the only ones the
@@ -355,10 +299,6 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
                 slot_of[(uint32_t)(~acc[tid] - seq0)] = slot;
                 if (F::kCand2 >= 0) { const uint64_t c2 = acc[(F::kCand2 < 0 ? 0 : F::kCand2) * kFeatTile + tid]; if (c2) slot_of[(uint32_t)(c2 - 1 - seq0)] = slot; }
             }
-#else
-            const uint32_t slot = find_or_create(t, epoch, k, &ctr->live);
-            slot_s[tid] = slot;
-#endif
             if (slot != kFeatNone) {
                 F::flush(F::state(t, slot), acc + tid, kFeatTile);
                 FeatHot<F>& e = hot[hq];
@@ -373,23 +313,13 @@ feature_fold_kernel(const uint8_t* __restrict__ recs, uint32_t n, Table t, uint6
                 }
             }
         }
-#if !FA_K6_V2
-        __syncthreads();
-        if (valid) {
-            const uint32_t slot = r == kFeatCached ? my_slot : slot_s[r];
-            slot_of[first + tid] = slot;
-            if (slot == kFeatNone) atomicAdd(&ctr->spills, 1ull);
-        }
-#endif
-        __syncthreads();                                                      // tile / rep / slot_s are re-used
+        __syncthreads();                                                      // tile / rep are re-used
     }
     __syncthreads();
     if (tid < kFeatHot && hot[tid].state == 2u) {
         F::flush(F::state(t, hot[tid].slot), hot[tid].acc, 1);
-#if FA_K6_V2
         if (hot[tid].acc[0]) slot_of[(uint32_t)(~hot[tid].acc[0] - seq0)] = hot[tid].slot;
         if (F::kCand2 >= 0) { const uint64_t c2 = hot[tid].acc[F::kCand2 < 0 ? 0 : F::kCand2]; if (c2) slot_of[(uint32_t)(c2 - 1 - seq0)] = hot[tid].slot; }
-#endif
     }
 }
 
