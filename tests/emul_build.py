@@ -22,7 +22,11 @@ def build(name, deps, flags=()):
         tmp = so + f".tmp{os.getpid()}"
         # -Bsymbolic: a library that defines test doubles of CUDA runtime entry points must bind its own calls to them
         # even when the real libcudart is already loaded in the process
+        # -fsanitize=alignment: the device faults on a misaligned vector access that x86 silently performs (an 8-byte
+        # shared-memory store to a 4-byte-aligned address got through the emulation once and cost a GPU call); UBSan's
+        # alignment check sees the same thing through the CUDA vector types' alignment attributes and aborts the test
         subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas",
+                        "-fsanitize=alignment", "-fno-sanitize-recover=alignment",
                         "-Wl,-Bsymbolic", "-I" + cuda_inc, *flags, "-o", tmp, src], check=True)
         os.replace(tmp, so)
     return so
