@@ -26,7 +26,7 @@ def build(name, deps, flags=()):
         # shared-memory store to a 4-byte-aligned address got through the emulation once and cost a GPU call); UBSan's
         # alignment check sees the same thing through the CUDA vector types' alignment attributes and aborts the test
         subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas",
-                        "-fsanitize=alignment", "-fno-sanitize-recover=alignment",
+                        "-fsanitize=alignment,bounds", "-fno-sanitize-recover=alignment,bounds",   # bounds: fixed-size shared arrays
                         "-Wl,-Bsymbolic", "-I" + cuda_inc, *flags, "-o", tmp, src], check=True)
         os.replace(tmp, so)
     return so
