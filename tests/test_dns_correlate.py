@@ -199,3 +199,38 @@ def test_needs_the_dns_flag(engine_emul):
         with pytest.raises(fa.FlowAggError):
             eng.ingest_dns_packets(query(1, 1))
         eng.purge_stale_dns(10, 1)                                 # nothing to purge: OK
+
+
+def test_restatement_agrees_with_an_independent_python_model():
+    """A second, dict-based restatement written from the source text alone (dns_tracker.h:92-110, flows.c:291-330): the C oracle
+    and it must agree on every sample of a messy stream."""
+    s = dns_stream(21, 4_000, n_clients=25, n_ids=3, dup=0.3, orphan=0.15, zero_id=0.1)
+    got = O.DnsCorrelator(max_entries=40).packets(s).view(O.DNSREC_DTYPE).reshape(-1)
+    dns_flows, want = {}, []
+    for p in s.view(O.DNSREC_DTYPE).reshape(-1):
+        ident, d = bytes(p["id"]), p["dns"]
+        ts, did, flags = int(d["end"]), int(d["id"]), int(d["flags"])
+        src, dst, sp, dp, proto = ident[0:16], ident[16:32], ident[32:34], ident[34:36], ident[36]
+        errno, latency, pid, pflags, name = 0, 0, 0, 0, bytes(32)
+        if not flags & QR:
+            key = (src, dst, sp, dp, did, proto)
+            if key in dns_flows:
+                errno = (-17) & 0xFF
+            elif len(dns_flows) >= 40:
+                errno = (-7) & 0xFF
+            else:
+                dns_flows[key] = ts
+        else:
+            key = (dst, src, dp, sp, did, proto)
+            if key in dns_flows:
+                latency = ts - dns_flows.pop(key)
+            else:
+                errno = 2
+            pid, pflags, name = did, flags, bytes(d["name"])
+        if pid or errno:
+            want.append((ident, ts, ts, latency, pid, pflags, int(d["eth"]), errno, name))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        gd = g["dns"]
+        assert (bytes(g["id"]), int(gd["start"]), int(gd["end"]), int(gd["latency"]), int(gd["id"]), int(gd["flags"]), int(gd["eth"]),
+                int(gd["errno"]), bytes(gd["name"])) == w
