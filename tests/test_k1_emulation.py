@@ -5,6 +5,7 @@ that come out are compared with the oracle's Accounter bit for bit.  What this b
 is checked for exactness (under real preemptive concurrency, several CTAs at once) before any GPU time is spent;
 what it cannot say anything about: speed, registers, the device memory model.  The GPU parity tests stay the gate."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -298,3 +299,17 @@ def test_feature_folds_and_feature_only_flows(var):
     for name, g, o in (("records", g_recs, o_recs), ("dns", g_dns, o_dns), ("additional", g_add, o_add),
                        ("present", g_pres.reshape(-1, 1), o_pres.reshape(-1, 1))):
         assert np.array_equal(g[gp], o[op]), name
+
+
+def test_tile_256_build_parameter_stays_exact(monkeypatch):
+    """FA_K1_TILE=256 (4 teams of 256, the shape the round's A/Bs compare against) must keep compiling and stay bit-exact:
+    a second emulation library built with the flag, run in a subprocess so that it does not displace the default one."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys; sys.path.insert(0, %r); os.environ['FA_EMUL_CXXFLAGS'] = '-DFA_K1_TILE=256'\n"
+        "import test_k1_emulation as T\n"
+        "T.test_zipf_stream_with_varying_descriptors_two_launches(0); T.test_uniform_keys_crowded_table(0); T.test_long_collision_chain(0)\n"
+        "print('tile256 ok')\n" % os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=850)
+    assert out.returncode == 0 and "tile256 ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
